@@ -1,0 +1,795 @@
+// deodr_b200: sm_100a kernels + C-ABI (include/deodr_b200.h) of the differentiable rasteriser.
+//
+// Pipeline of one forward pass (all on the caller's stream):
+//   bin_tri(count) -> scan -> bin_tri(fill)                       per-tile triangle lists (unordered: the z test is
+//                                                                  order independent, see phase_tri_test)
+//   select silhouette edges -> depth keys -> stable radix sort    far-to-near order of DR.h:2781 (CUB)
+//   bin_edge(count) -> scan -> bin_edge(fill) -> sort_tile_edges  per-tile edge lists in far-to-near order
+//   raster_fwd                                                    one CTA per 16x16 tile: z-buffer, owner ids, colour,
+//                                                                  ordered edge overdraw, single framebuffer write
+// and of one backward pass:
+//   raster_bwd                                                    per tile: edge replay + reverse sweep, interior
+//                                                                  adjoint scattered to the vertices
+//   finalize_edges                                                per edge: plane adjoints -> vertex adjoints
+//
+// There is no CPU fallback: every entry point fails with DEODR_B200_ECUDA if no device is usable.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+#include "../../include/deodr_b200.h"
+#include "phases.h"
+
+using namespace deodr;
+
+// ------------------------------------------------------------------------------------------------ device Env
+
+struct DevEnv {
+    static __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
+    static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
+    static __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
+    // vertex-gradient scatter; null slots are skipped
+    static __device__ __forceinline__ void emit(float *p, float v) { atomicAdd(p, v); }
+};
+
+static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirror DeodrSceneView");
+
+// ------------------------------------------------------------------------------------------------- kernels
+
+__global__ void k_bin_tri(SceneView s, double sigma, int tiles_x, int mode, int *tile_count, const int *tile_offset,
+                          int *tile_cursor, int *refs, uint8_t *edge_selected) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.nb_triangles) return;
+    bin_triangle<DevEnv>(s, k, sigma, tiles_x, mode, tile_count, tile_offset, tile_cursor, refs, edge_selected);
+}
+
+__global__ void k_bin_edge(SceneView s, const int *edge_sorted, const int *num_edges, double sigma, int tiles_x,
+                           int mode, int *tile_count, const int *tile_offset, int *tile_cursor, int *refs) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *num_edges) return;
+    bin_edge<DevEnv>(s, edge_sorted[r], r, sigma, tiles_x, mode, tile_count, tile_offset, tile_cursor, refs);
+}
+
+// Exclusive scan of the tile counts rounded up to a multiple of 4 entries (16-byte aligned list starts).
+// Single CTA of 1024 threads; offsets[n] and *total receive the grand total.
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int *count, int *offset, int n, int *total) {
+    __shared__ int partial[1024];
+    const int tid = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int lo = tid * per, hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += (count[i] + 3) & ~3;
+    partial[tid] = sum;
+    __syncthreads();
+    for (int step = 1; step < 1024; step <<= 1) {
+        int v = tid >= step ? partial[tid - step] : 0;
+        __syncthreads();
+        partial[tid] += v;
+        __syncthreads();
+    }
+    int run = partial[tid] - sum;
+    for (int i = lo; i < hi; i++) {
+        offset[i] = run;
+        run += (count[i] + 3) & ~3;
+    }
+    if (tid == 1023) {
+        offset[n] = partial[1023];
+        *total = partial[1023];
+    }
+}
+
+__global__ void k_edge_keys(SceneView s, const int *edge_ids, const int *num_edges, unsigned long long *keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *num_edges) return;
+    int k = edge_ids[i] / 3;
+    double d0 = s.depths[s.faces[3 * k]], d1 = s.depths[s.faces[3 * k + 1]], d2 = s.depths[s.faces[3 * k + 2]];
+    keys[i] = depth_desc_key(DADD(DADD(DADD(0.0, d0), d1), d2));
+}
+
+// Orders every tile's edge list by far-to-near rank (ranks are unique): rank-counting sort, one CTA per tile.
+__global__ void k_sort_tile_edges(const int *count, const int *offset, const int *refs_in, int *refs_out) {
+    const int tile = blockIdx.x;
+    const int n = count[tile], base = offset[tile];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int mine = refs_in[base + i], pos = 0;
+        for (int j = 0; j < n; j++) pos += refs_in[base + j] < mine;
+        refs_out[base + pos] = mine;
+    }
+}
+
+struct TieTable {
+    int *pairs;     // (own, bown) per tie pixel
+    int *counter;   // number of entries requested so far (may exceed capacity: overflow)
+    int capacity;
+};
+
+template <int MAXC>
+__global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, int tiles_x, const int *tri_count,
+                                                   const int *tri_offset, const int *tri_refs, const int *edge_count,
+                                                   const int *edge_offset, const int *edge_refs,
+                                                   const int *edge_sorted, TieTable ties, float *image,
+                                                   double *z_buffer, int *owner, int *face_id) {
+    __shared__ TileShared sh;
+    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const Tile tile = tile_of(tile_id, tiles_x);
+    const int c = tid % TS, r = tid / TS;
+    const int x = tile.x0 + c, y = tile.y0 + r;
+    const bool inside = x < s.width && y < s.height;
+
+    PixelState<MAXC> p;
+    p.z = __longlong_as_double(0x7ff0000000000000LL);
+    p.own = -1;
+    p.bown = -1;
+
+    const int n_tri = tri_count[tile_id], tri_base = tri_offset[tile_id];
+    for (int base = 0; base < n_tri; base += TRI_CHUNK) {
+        const int m = min(TRI_CHUNK, n_tri - base);
+        phase_tri_setup(s, tid, m, tri_refs + tri_base + base, &sh);
+        __syncthreads();
+        phase_tri_masks(s, tid, m, tile, &sh);
+        __syncthreads();
+        if (inside) phase_tri_test<MAXC>(s, tid, m, tile, &sh, &p);
+        __syncthreads();
+    }
+    if (inside) phase_shade<MAXC>(s, x, y, &p);
+
+    const int n_edge = edge_count ? edge_count[tile_id] : 0;
+    if (n_edge > 0) {
+        const int edge_base = edge_offset[tile_id];
+        for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
+            const int m = min(EDGE_CHUNK, n_edge - base);
+            phase_edge_setup(s, tid, m, edge_refs + edge_base + base, edge_sorted, sigma, &sh);
+            __syncthreads();
+            phase_edge_spans(s, tid, m, tile, &sh);
+            __syncthreads();
+            if (inside) phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
+            __syncthreads();
+        }
+    }
+    if (!inside) return;
+    const size_t idx = (size_t)y * s.width + x;
+    z_buffer[idx] = p.z;
+    for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
+    int code = p.bown;
+    if (p.own != p.bown) {  // exact z tie between distinct triangles: keep both ids in the side table
+        int slot = atomicAdd(ties.counter, 1);
+        if (slot < ties.capacity) {
+            ties.pairs[2 * slot] = p.own;
+            ties.pairs[2 * slot + 1] = p.bown;
+            code = -2 - slot;
+        }
+    }
+    owner[idx] = code;
+    if (face_id) face_id[idx] = p.own;
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_count,
+                                                   const int *edge_offset, const int *edge_refs,
+                                                   const int *edge_sorted, TieTable ties, const double *z_buffer,
+                                                   const int *owner, const float *image_b, DeodrGrads grads,
+                                                   double *edge_acc) {
+    __shared__ TileShared sh;
+    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const Tile tile = tile_of(tile_id, tiles_x);
+    const int c = tid % TS, r = tid / TS;
+    const int x = tile.x0 + c, y = tile.y0 + r;
+    const bool inside = x < s.width && y < s.height;
+    const size_t idx = inside ? (size_t)y * s.width + x : 0;
+
+    PixelState<MAXC> p;
+    AdjointState<MAXC> a;
+    a.has_colour = false;
+    p.z = __longlong_as_double(0x7ff0000000000000LL);
+    p.own = p.bown = -1;
+    if (inside) {
+        p.z = z_buffer[idx];
+        int code = owner[idx];
+        if (code <= -2) {
+            p.own = ties.pairs[2 * (-2 - code)];
+            p.bown = ties.pairs[2 * (-2 - code) + 1];
+        } else {
+            p.own = p.bown = code;
+        }
+        for (int k = 0; k < s.nb_colors; k++) a.g[k] = image_b[idx * s.nb_colors + k];
+    }
+
+    const int n_edge = edge_count ? edge_count[tile_id] : 0;
+    if (n_edge > 0) {
+        const int edge_base = edge_offset[tile_id];
+        const bool single = n_edge <= EDGE_CHUNK;
+        // pass A: forward replay (far to near) to obtain the final colour in fp64
+        for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
+            const int m = min(EDGE_CHUNK, n_edge - base);
+            phase_edge_setup(s, tid, m, edge_refs + edge_base + base, edge_sorted, sigma, &sh);
+            __syncthreads();
+            phase_edge_spans(s, tid, m, tile, &sh);
+            __syncthreads();
+            if (inside) phase_edge_replay<MAXC>(s, x, y, r, m, &sh, p, &a);
+            if (single) {
+                if (inside && a.has_colour)
+                    phase_edge_adjoint<MAXC, DevEnv>(s, x, y, r, m, &sh, p, &a, edge_acc, grads.texture_b);
+            }
+            __syncthreads();
+        }
+        // pass B: reverse sweep (near to far), chunks in reverse order
+        if (!single) {
+            const int last = ((n_edge - 1) / EDGE_CHUNK) * EDGE_CHUNK;
+            for (int base = last; base >= 0; base -= EDGE_CHUNK) {
+                const int m = min(EDGE_CHUNK, n_edge - base);
+                phase_edge_setup(s, tid, m, edge_refs + edge_base + base, edge_sorted, sigma, &sh);
+                __syncthreads();
+                phase_edge_spans(s, tid, m, tile, &sh);
+                __syncthreads();
+                if (inside && a.has_colour)
+                    phase_edge_adjoint<MAXC, DevEnv>(s, x, y, r, m, &sh, p, &a, edge_acc, grads.texture_b);
+                __syncthreads();
+            }
+        }
+    }
+    if (inside && p.bown >= 0)
+        phase_interior_adjoint<MAXC, DevEnv>(s, x, y, p, a.g, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
+                                             grads.texture_b);
+}
+
+__global__ void k_finalize_edges(SceneView s, const int *edge_sorted, const int *num_edges, double sigma,
+                                 const double *edge_acc, DeodrGrads grads) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *num_edges) return;
+    finalize_edge<DevEnv>(s, edge_sorted[r], sigma, edge_acc + (size_t)r * edge_acc_stride(s.nb_colors), grads.ij_b,
+                          grads.colors_b, grads.uv_b, grads.shade_b);
+}
+
+__global__ void k_check_scene(SceneView s, int *bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * s.nb_triangles) return;
+    if (s.faces[i] >= (uint32_t)s.nb_vertices) atomicOr(bad, 1);
+    if (s.faces_uv[i] >= (uint32_t)s.nb_uv) atomicOr(bad, 2);
+}
+
+__global__ void k_f64_to_f32(const double *in, float *out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+__global__ void k_f32_to_f64(const float *in, double *out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+
+static thread_local char g_error[512] = "";
+
+static int set_error(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_error, sizeof(g_error), fmt, detail);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t err__ = (expr);                                                             \
+        if (err__ != cudaSuccess) {                                                             \
+            snprintf(g_error, sizeof(g_error), "%s failed: %s", #expr, cudaGetErrorString(err__)); \
+            return DEODR_B200_ECUDA;                                                            \
+        }                                                                                       \
+    } while (0)
+
+// growable device buffer
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need, int64_t *accounted) {
+        if (need <= bytes) return DEODR_B200_OK;
+        if (ptr) {
+            CUDA_TRY(cudaFree(ptr));
+            *accounted -= (int64_t)bytes;
+            ptr = nullptr;
+            bytes = 0;
+        }
+        size_t want = need + need / 4 + 256;
+        CUDA_TRY(cudaMalloc(&ptr, want));
+        bytes = want;
+        *accounted += (int64_t)want;
+        return DEODR_B200_OK;
+    }
+    template <class T>
+    T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct DeodrWorkspace {
+    int device = 0;
+    int64_t bytes = 0;
+    int64_t launches = 0;
+    int *host_totals = nullptr;  // pinned: [0] tri refs, [1] selected edges, [2] edge refs, [3] tie counter, [4] flags
+    // forward state
+    int tiles_x = 0, tiles_y = 0, num_tiles = 0;
+    int num_edges = 0;           // silhouette edges of the last forward pass
+    double sigma = -1;
+    int fwd_valid = 0;
+    int fwd_T = 0, fwd_H = 0, fwd_W = 0, fwd_C = 0;
+    DevBuf tri_count, tri_offset, tri_cursor, tri_refs;
+    DevBuf edge_flags, edge_ids, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
+    DevBuf edge_count, edge_offset, edge_cursor, edge_refs_tmp, edge_refs;
+    DevBuf scalars;              // device ints: [0] tri total, [1] num selected, [2] edge total, [3] tie counter, [4] flags
+    DevBuf tie_pairs;
+    int tie_capacity = 0;
+    DevBuf edge_acc;
+    // host-path staging (canonical device copies of a DeodrHostScene)
+    DevBuf h_faces, h_faces_uv, h_ij, h_depths, h_uv, h_colors, h_shade, h_edgeflags, h_textured, h_shaded, h_texture,
+        h_background, h_stage64, h_image, h_z, h_owner, h_image_b, h_grads;
+};
+
+static int sm_count_cached = 0;
+
+static inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
+
+template <int MAXC>
+static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
+                       float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
+    k_raster_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->tri_count.as<int>(),
+                                                     ws->tri_offset.as<int>(), ws->tri_refs.as<int>(), edge_count,
+                                                     ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
+                                                     ws->edge_sorted.as<int>(), ties, image, z, owner, face_id);
+}
+
+template <int MAXC>
+static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
+                       const double *z, const int *owner, const float *image_b, const DeodrGrads &g, cudaStream_t st) {
+    k_raster_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
+                                                     ws->edge_refs.as<int>(), ws->edge_sorted.as<int>(), ties, z, owner,
+                                                     image_b, g, ws->edge_acc.as<double>());
+}
+
+static int validate_view(const DeodrSceneView *v, bool backward) {
+    if (!v) return set_error(DEODR_B200_EINVAL, "scene == NULL");
+    if (!v->faces) return set_error(DEODR_B200_EINVAL, "scene.faces == NULL");
+    if (!v->faces_uv) return set_error(DEODR_B200_EINVAL, "scene.faces_uv == NULL");
+    if (!v->depths) return set_error(DEODR_B200_EINVAL, "scene.depths == NULL");
+    if (!v->uv) return set_error(DEODR_B200_EINVAL, "scene.uv == NULL");
+    if (!v->ij) return set_error(DEODR_B200_EINVAL, "scene.ij == NULL");
+    if (!v->shade) return set_error(DEODR_B200_EINVAL, "scene.shade == NULL");
+    if (!v->colors) return set_error(DEODR_B200_EINVAL, "scene.colors == NULL");
+    if (!v->edgeflags) return set_error(DEODR_B200_EINVAL, "scene.edgeflags == NULL");
+    if (!v->textured) return set_error(DEODR_B200_EINVAL, "scene.textured == NULL");
+    if (!v->shaded) return set_error(DEODR_B200_EINVAL, "scene.shaded == NULL");
+    if (!v->texture) return set_error(DEODR_B200_EINVAL, "scene.texture == NULL");
+    if (!v->background_image && !v->background_color)
+        return set_error(DEODR_B200_EINVAL, "scene.background == NULL and scene.background_color == NULL");
+    if (v->height <= 0 || v->width <= 0 || v->height > 32767 || v->width > 32767)
+        return set_error(DEODR_B200_EINVAL, "image sides must be in [1, 32767] (short loop counters, DR.h:925)");
+    if (v->nb_colors < 1 || v->nb_colors > 16)
+        return set_error(DEODR_B200_EUNSUPPORTED, "nb_colors must be in [1, 16]");
+    if (v->nb_triangles < 0 || v->nb_vertices < 0 || v->nb_uv < 0)
+        return set_error(DEODR_B200_EINVAL, "negative size");
+    if (backward) {
+        if (!v->backface_culling)
+            return set_error(DEODR_B200_EUNSUPPORTED,
+                             "You have to use backface_culling true if you ant to compute gradients");
+        if (v->perspective_correct)
+            return set_error(DEODR_B200_EUNSUPPORTED,
+                             "backward gradient propagation not supported yet with perspective_correct=True");
+    }
+    return DEODR_B200_OK;
+}
+
+extern "C" {
+
+const char *deodr_b200_last_error(void) { return g_error; }
+const char *deodr_b200_version(void) { return "deodr_b200 0.1 (sm_100a)"; }
+
+int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
+    if (!out) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return set_error(DEODR_B200_ECUDA, "no CUDA device available (%s): deodr_b200 has no CPU fallback",
+                         cudaGetErrorString(err));
+    if (device < 0 || device >= count) return set_error(DEODR_B200_EINVAL, "bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    DeodrWorkspace *ws = new (std::nothrow) DeodrWorkspace();
+    if (!ws) return set_error(DEODR_B200_ENOMEM, "out of host memory");
+    ws->device = device;
+    CUDA_TRY(cudaMallocHost(&ws->host_totals, 8 * sizeof(int)));
+    if (ws->scalars.ensure(8 * sizeof(int), &ws->bytes)) return DEODR_B200_ECUDA;
+    if (!sm_count_cached) cudaDeviceGetAttribute(&sm_count_cached, cudaDevAttrMultiProcessorCount, device);
+    *out = ws;
+    return DEODR_B200_OK;
+}
+
+void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
+    if (!ws) return;
+    cudaSetDevice(ws->device);
+    DevBuf *bufs[] = {&ws->tri_count, &ws->tri_offset, &ws->tri_cursor, &ws->tri_refs, &ws->edge_flags, &ws->edge_ids,
+                      &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp, &ws->edge_count,
+                      &ws->edge_offset, &ws->edge_cursor, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
+                      &ws->tie_pairs, &ws->edge_acc, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
+                      &ws->h_colors, &ws->h_shade, &ws->h_edgeflags, &ws->h_textured, &ws->h_shaded, &ws->h_texture,
+                      &ws->h_background, &ws->h_stage64, &ws->h_image, &ws->h_z, &ws->h_owner, &ws->h_image_b,
+                      &ws->h_grads};
+    for (DevBuf *b : bufs)
+        if (b->ptr) cudaFree(b->ptr);
+    if (ws->host_totals) cudaFreeHost(ws->host_totals);
+    delete ws;
+}
+
+int64_t deodr_b200_workspace_bytes(const DeodrWorkspace *ws) { return ws ? ws->bytes : 0; }
+int64_t deodr_b200_workspace_launches(const DeodrWorkspace *ws) { return ws ? ws->launches : 0; }
+
+int deodr_b200_check_scene(DeodrWorkspace *ws, const DeodrSceneView *scene, void *stream) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    if (int rc = validate_view(scene, false)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ws->device));
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    int *flag = ws->scalars.as<int>() + 4;
+    CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    if (s.nb_triangles > 0) {
+        k_check_scene<<<grid_for(3 * (size_t)s.nb_triangles, 256), 256, 0, st>>>(s, flag);
+        ws->launches++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ws->host_totals + 4, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ws->host_totals[4] & 1) return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
+    if (ws->host_totals[4] & 2) return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
+    return DEODR_B200_OK;
+}
+
+int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, float *image, double *z_buffer,
+                      int32_t *owner, int32_t *face_id, void *stream) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    if (int rc = validate_view(scene, false)) return rc;
+    if (!image) return set_error(DEODR_B200_EINVAL, "image_ptr is NULL");
+    if (!z_buffer) return set_error(DEODR_B200_EINVAL, "z_buffer_ptr is NULL");
+    if (!owner) return set_error(DEODR_B200_EINVAL, "owner is NULL");
+    if (!(sigma >= 0)) return set_error(DEODR_B200_EINVAL, "sigma must be >= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ws->device));
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    ws->fwd_valid = 0;
+    const int T = s.nb_triangles;
+    ws->tiles_x = (s.width + TS - 1) / TS;
+    ws->tiles_y = (s.height + TS - 1) / TS;
+    ws->num_tiles = ws->tiles_x * ws->tiles_y;
+    const int nt = ws->num_tiles;
+    const size_t tile_bytes = (size_t)(nt + 1) * sizeof(int);
+    int rc = 0;
+    rc |= ws->tri_count.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->tri_offset.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->tri_cursor.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->edge_count.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->edge_cursor.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->edge_flags.ensure((size_t)3 * T + 16, &ws->bytes);
+    rc |= ws->edge_ids.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
+    if (ws->tie_capacity == 0) {
+        ws->tie_capacity = 1 << 16;
+        rc |= ws->tie_pairs.ensure((size_t)2 * ws->tie_capacity * sizeof(int), &ws->bytes);
+    }
+    if (rc) return DEODR_B200_ECUDA;
+    int *scal = ws->scalars.as<int>();
+    CUDA_TRY(cudaMemsetAsync(scal, 0, 8 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(ws->tri_count.ptr, 0, tile_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(ws->tri_cursor.ptr, 0, tile_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(ws->edge_count.ptr, 0, tile_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(ws->edge_cursor.ptr, 0, tile_bytes, st));
+
+    // ---- triangles: count -> scan ; silhouette edges: select
+    const bool with_edges = sigma > 0 && T > 0;
+    if (T > 0) {
+        k_bin_tri<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, 0, ws->tri_count.as<int>(), nullptr, nullptr,
+                                                    nullptr, ws->edge_flags.as<uint8_t>());
+        ws->launches++;
+    }
+    k_scan_tiles<<<1, 1024, 0, st>>>(ws->tri_count.as<int>(), ws->tri_offset.as<int>(), nt, scal + 0);
+    ws->launches++;
+    if (with_edges) {
+        size_t temp = 0;
+        cub::CountingInputIterator<int> ids(0);
+        CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, temp, ids, ws->edge_flags.as<uint8_t>(), ws->edge_ids.as<int>(),
+                                            scal + 1, 3 * T, st));
+        if (ws->cub_temp.ensure(temp, &ws->bytes)) return DEODR_B200_ECUDA;
+        CUDA_TRY(cub::DeviceSelect::Flagged(ws->cub_temp.ptr, temp, ids, ws->edge_flags.as<uint8_t>(),
+                                            ws->edge_ids.as<int>(), scal + 1, 3 * T, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int tri_total = ws->host_totals[0];
+    const int E = with_edges ? ws->host_totals[1] : 0;
+    ws->num_edges = E;
+    if (ws->tri_refs.ensure(((size_t)tri_total + 4) * sizeof(int), &ws->bytes)) return DEODR_B200_ECUDA;
+    if (T > 0) {
+        k_bin_tri<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, 1, nullptr, ws->tri_offset.as<int>(),
+                                                    ws->tri_cursor.as<int>(), ws->tri_refs.as<int>(), nullptr);
+        ws->launches++;
+    }
+
+    // ---- silhouette edges: far-to-near order, tile lists
+    if (E > 0) {
+        rc = 0;
+        rc |= ws->edge_keys_in.ensure((size_t)E * 8, &ws->bytes);
+        rc |= ws->edge_keys_out.ensure((size_t)E * 8, &ws->bytes);
+        rc |= ws->edge_sorted.ensure((size_t)E * sizeof(int), &ws->bytes);
+        if (rc) return DEODR_B200_ECUDA;
+        k_edge_keys<<<grid_for(E, 256), 256, 0, st>>>(s, ws->edge_ids.as<int>(), scal + 1,
+                                                      ws->edge_keys_in.as<unsigned long long>());
+        ws->launches++;
+        size_t temp = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp, ws->edge_keys_in.as<unsigned long long>(),
+                                                 ws->edge_keys_out.as<unsigned long long>(), ws->edge_ids.as<int>(),
+                                                 ws->edge_sorted.as<int>(), E, 0, 64, st));
+        if (ws->cub_temp.ensure(temp, &ws->bytes)) return DEODR_B200_ECUDA;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp, ws->edge_keys_in.as<unsigned long long>(),
+                                                 ws->edge_keys_out.as<unsigned long long>(), ws->edge_ids.as<int>(),
+                                                 ws->edge_sorted.as<int>(), E, 0, 64, st));
+        k_bin_edge<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma, ws->tiles_x, 0,
+                                                     ws->edge_count.as<int>(), nullptr, nullptr, nullptr);
+        k_scan_tiles<<<1, 1024, 0, st>>>(ws->edge_count.as<int>(), ws->edge_offset.as<int>(), nt, scal + 2);
+        ws->launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(ws->host_totals + 2, scal + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const int edge_total = ws->host_totals[2];
+        rc = 0;
+        rc |= ws->edge_refs_tmp.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
+        rc |= ws->edge_refs.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
+        if (rc) return DEODR_B200_ECUDA;
+        k_bin_edge<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma, ws->tiles_x, 1,
+                                                     nullptr, ws->edge_offset.as<int>(), ws->edge_cursor.as<int>(),
+                                                     ws->edge_refs_tmp.as<int>());
+        k_sort_tile_edges<<<nt, 128, 0, st>>>(ws->edge_count.as<int>(), ws->edge_offset.as<int>(),
+                                              ws->edge_refs_tmp.as<int>(), ws->edge_refs.as<int>());
+        ws->launches += 2;
+    }
+
+    // ---- raster
+    TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
+    const int *edge_count = E > 0 ? ws->edge_count.as<int>() : nullptr;
+    const int C = s.nb_colors;
+    if (C == 1) launch_fwd<1>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
+    else if (C <= 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
+    else if (C <= 4) launch_fwd<4>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
+    else launch_fwd<16>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
+    ws->launches++;
+    CUDA_TRY(cudaGetLastError());
+    ws->sigma = sigma;
+    ws->fwd_T = T; ws->fwd_H = s.height; ws->fwd_W = s.width; ws->fwd_C = C;
+    ws->fwd_valid = 1;
+    return DEODR_B200_OK;
+}
+
+int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, const double *z_buffer,
+                        const int32_t *owner, const float *image_b, const DeodrGrads *grads, void *stream) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    if (int rc = validate_view(scene, true)) return rc;
+    if (!z_buffer || !owner) return set_error(DEODR_B200_EINVAL, "z_buffer / owner is NULL");
+    if (!image_b) return set_error(DEODR_B200_EINVAL, "image_b_ptr is NULL");
+    if (!grads) return set_error(DEODR_B200_EINVAL, "grads == NULL");
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    if (!ws->fwd_valid || ws->sigma != sigma || ws->fwd_T != s.nb_triangles || ws->fwd_H != s.height ||
+        ws->fwd_W != s.width || ws->fwd_C != s.nb_colors)
+        return set_error(DEODR_B200_EINVAL, "render_b must follow render on the same workspace, scene and sigma");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ws->device));
+    // the tie table must not have overflowed in the forward pass
+    int *scal = ws->scalars.as<int>();
+    CUDA_TRY(cudaMemcpyAsync(ws->host_totals + 3, scal + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ws->host_totals[3] > ws->tie_capacity)
+        return set_error(DEODR_B200_EUNSUPPORTED, "more exact z-buffer ties than the tie table holds");
+    const int E = ws->num_edges, C = s.nb_colors;
+    DeodrGrads g = *grads;
+    if (!g.ij_b || !g.colors_b || !g.uv_b || !g.shade_b)
+        return set_error(DEODR_B200_EINVAL, "ij_b / colors_b / uv_b / shade_b must be provided");
+    if (E > 0) {
+        size_t acc_bytes = (size_t)E * edge_acc_stride(C) * sizeof(double);
+        if (ws->edge_acc.ensure(acc_bytes, &ws->bytes)) return DEODR_B200_ECUDA;
+        CUDA_TRY(cudaMemsetAsync(ws->edge_acc.ptr, 0, acc_bytes, st));
+    }
+    TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
+    const int *edge_count = E > 0 ? ws->edge_count.as<int>() : nullptr;
+    if (C == 1) launch_bwd<1>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
+    else if (C <= 3) launch_bwd<3>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
+    else if (C <= 4) launch_bwd<4>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
+    else launch_bwd<16>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
+    ws->launches++;
+    if (E > 0) {
+        k_finalize_edges<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma,
+                                                           ws->edge_acc.as<double>(), g);
+        ws->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return DEODR_B200_OK;
+}
+
+// ------------------------------------------------------------------------------- reference-shaped host entry points
+
+static int upload_f64_as_f32(DeodrWorkspace *ws, DevBuf &dst, const double *src, size_t n, cudaStream_t st) {
+    if (dst.ensure(n * sizeof(float) + 16, &ws->bytes)) return DEODR_B200_ECUDA;
+    if (n == 0) return DEODR_B200_OK;
+    if (ws->h_stage64.ensure(n * sizeof(double), &ws->bytes)) return DEODR_B200_ECUDA;
+    CUDA_TRY(cudaMemcpyAsync(ws->h_stage64.ptr, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_f64_to_f32<<<grid_for(n, 256), 256, 0, st>>>(ws->h_stage64.as<double>(), dst.as<float>(), n);
+    ws->launches++;
+    // the staging buffer is reused by the next upload: order is guaranteed by the stream
+    return DEODR_B200_OK;
+}
+
+static int upload_raw(DeodrWorkspace *ws, DevBuf &dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (dst.ensure(bytes + 16, &ws->bytes)) return DEODR_B200_ECUDA;
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(dst.ptr, src, bytes, cudaMemcpyHostToDevice, st));
+    return DEODR_B200_OK;
+}
+
+static int check_host_scene(const DeodrHostScene *h, bool backward) {
+    if (!h) return set_error(DEODR_B200_EINVAL, "scene == NULL");
+    if (!h->faces) return set_error(DEODR_B200_EINVAL, "scene.faces == NULL");
+    if (!h->faces_uv) return set_error(DEODR_B200_EINVAL, "scene.faces_uv == NULL");
+    if (!h->depths) return set_error(DEODR_B200_EINVAL, "scene.depths == NULL");
+    if (!h->uv) return set_error(DEODR_B200_EINVAL, "scene.uv == NULL");
+    if (!h->ij) return set_error(DEODR_B200_EINVAL, "scene.ij == NULL");
+    if (!h->shade) return set_error(DEODR_B200_EINVAL, "scene.shade == NULL");
+    if (!h->colors) return set_error(DEODR_B200_EINVAL, "scene.colors == NULL");
+    if (!h->edgeflags) return set_error(DEODR_B200_EINVAL, "scene.edgeflags == NULL");
+    if (!h->textured) return set_error(DEODR_B200_EINVAL, "scene.textured == NULL");
+    if (!h->shaded) return set_error(DEODR_B200_EINVAL, "scene.shaded == NULL");
+    if (!h->texture) return set_error(DEODR_B200_EINVAL, "scene.texture == NULL");
+    if (!h->background_image && !h->background_color)
+        return set_error(DEODR_B200_EINVAL, "scene.background == NULL and scene.background_color == NULL");
+    if (backward) {
+        if (!h->uv_b) return set_error(DEODR_B200_EINVAL, "scene.uv_b == NULL");
+        if (!h->ij_b) return set_error(DEODR_B200_EINVAL, "scene.ij_b == NULL");
+        if (!h->shade_b) return set_error(DEODR_B200_EINVAL, "scene.shade_b == NULL");
+        if (!h->colors_b) return set_error(DEODR_B200_EINVAL, "scene.colors_b == NULL");
+        if (!h->texture_b) return set_error(DEODR_B200_EINVAL, "scene.texture_b == NULL");
+    }
+    for (int64_t k = 0; k < (int64_t)h->nb_triangles * 3; k++) {
+        if (h->faces[k] >= (uint32_t)h->nb_vertices)
+            return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
+        if (h->faces_uv[k] >= (uint32_t)h->nb_uv)
+            return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
+    }
+    return DEODR_B200_OK;
+}
+
+// uploads a host scene into the workspace staging buffers and fills the device view
+static int stage_host_scene(DeodrWorkspace *ws, const DeodrHostScene *h, DeodrSceneView *v, cudaStream_t st) {
+    const size_t T = h->nb_triangles, V = h->nb_vertices, U = h->nb_uv, C = h->nb_colors;
+    const size_t P = (size_t)h->height * h->width, tex = (size_t)h->texture_height * h->texture_width * C;
+    int rc = 0;
+    rc |= upload_raw(ws, ws->h_faces, h->faces, T * 3 * sizeof(uint32_t), st);
+    rc |= upload_raw(ws, ws->h_faces_uv, h->faces_uv, T * 3 * sizeof(uint32_t), st);
+    rc |= upload_raw(ws, ws->h_ij, h->ij, V * 2 * sizeof(double), st);
+    rc |= upload_raw(ws, ws->h_depths, h->depths, V * sizeof(double), st);
+    rc |= upload_raw(ws, ws->h_uv, h->uv, U * 2 * sizeof(double), st);
+    rc |= upload_raw(ws, ws->h_edgeflags, h->edgeflags, T * 3, st);
+    rc |= upload_raw(ws, ws->h_textured, h->textured, T, st);
+    rc |= upload_raw(ws, ws->h_shaded, h->shaded, T, st);
+    if (rc) return rc;
+    if ((rc = upload_f64_as_f32(ws, ws->h_colors, h->colors, V * C, st))) return rc;
+    if ((rc = upload_f64_as_f32(ws, ws->h_shade, h->shade, V, st))) return rc;
+    if ((rc = upload_f64_as_f32(ws, ws->h_texture, h->texture, tex, st))) return rc;
+    if (h->background_image) rc = upload_f64_as_f32(ws, ws->h_background, h->background_image, P * C, st);
+    else rc = upload_f64_as_f32(ws, ws->h_background, h->background_color, C, st);
+    if (rc) return rc;
+    memset(v, 0, sizeof(*v));
+    v->faces = ws->h_faces.as<uint32_t>();
+    v->faces_uv = ws->h_faces_uv.as<uint32_t>();
+    v->ij = ws->h_ij.as<double>();
+    v->depths = ws->h_depths.as<double>();
+    v->uv = ws->h_uv.as<double>();
+    v->colors = ws->h_colors.as<float>();
+    v->shade = ws->h_shade.as<float>();
+    v->edgeflags = ws->h_edgeflags.as<uint8_t>();
+    v->textured = ws->h_textured.as<uint8_t>();
+    v->shaded = ws->h_shaded.as<uint8_t>();
+    v->texture = ws->h_texture.as<float>();
+    if (h->background_image) v->background_image = ws->h_background.as<float>();
+    else v->background_color = ws->h_background.as<float>();
+    v->nb_triangles = h->nb_triangles; v->nb_vertices = h->nb_vertices; v->nb_uv = h->nb_uv;
+    v->height = h->height; v->width = h->width; v->nb_colors = h->nb_colors;
+    v->texture_height = h->texture_height; v->texture_width = h->texture_width;
+    v->clockwise = h->clockwise; v->backface_culling = h->backface_culling; v->strict_edge = h->strict_edge;
+    v->perspective_correct = h->perspective_correct; v->integer_pixel_centers = h->integer_pixel_centers;
+    return DEODR_B200_OK;
+}
+
+static int host_forward(DeodrWorkspace *ws, const DeodrHostScene *h, double sigma, DeodrSceneView *v, cudaStream_t st) {
+    if (int rc = stage_host_scene(ws, h, v, st)) return rc;
+    const size_t P = (size_t)h->height * h->width, C = h->nb_colors;
+    int rc = 0;
+    rc |= ws->h_image.ensure(P * C * sizeof(float), &ws->bytes);
+    rc |= ws->h_z.ensure(P * sizeof(double), &ws->bytes);
+    rc |= ws->h_owner.ensure(P * sizeof(int), &ws->bytes);
+    if (rc) return DEODR_B200_ECUDA;
+    return deodr_b200_render(ws, v, sigma, ws->h_image.as<float>(), ws->h_z.as<double>(), ws->h_owner.as<int>(),
+                             nullptr, st);
+}
+
+int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, double *image, double *z_buffer,
+                           double sigma, int antialiase_error, const double *obs, double *err_buffer) {
+    (void)obs; (void)err_buffer;
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    if (antialiase_error)
+        return set_error(DEODR_B200_EUNSUPPORTED, "antialiase_error mode is not implemented by deodr_b200 yet");
+    if (int rc = check_host_scene(scene, false)) return rc;
+    if (!image) return set_error(DEODR_B200_EINVAL, "image_ptr is NULL");
+    if (!z_buffer) return set_error(DEODR_B200_EINVAL, "z_buffer_ptr is NULL");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    cudaStream_t st = 0;
+    DeodrSceneView v;
+    if (int rc = host_forward(ws, scene, sigma, &v, st)) return rc;
+    const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
+    if (ws->h_stage64.ensure(P * C * sizeof(double), &ws->bytes)) return DEODR_B200_ECUDA;
+    k_f32_to_f64<<<grid_for(P * C, 256), 256, 0, st>>>(ws->h_image.as<float>(), ws->h_stage64.as<double>(), P * C);
+    ws->launches++;
+    CUDA_TRY(cudaMemcpyAsync(image, ws->h_stage64.ptr, P * C * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(z_buffer, ws->h_z.ptr, P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DEODR_B200_OK;
+}
+
+int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, double *image, double *z_buffer,
+                             double *image_b, double sigma, int antialiase_error, const double *obs,
+                             double *err_buffer, double *err_buffer_b) {
+    (void)obs; (void)err_buffer; (void)err_buffer_b; (void)image; (void)z_buffer;
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    if (antialiase_error)
+        return set_error(DEODR_B200_EUNSUPPORTED, "antialiase_error mode is not implemented by deodr_b200 yet");
+    if (int rc = check_host_scene(scene, true)) return rc;
+    if (!scene->backface_culling)
+        return set_error(DEODR_B200_EUNSUPPORTED, "You have to use backface_culling true if you ant to compute gradients");
+    if (scene->perspective_correct)
+        return set_error(DEODR_B200_EUNSUPPORTED,
+                         "backward gradient propagation not supported yet with perspective_correct=True");
+    if (!image_b) return set_error(DEODR_B200_EINVAL, "image_b_ptr is NULL");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    cudaStream_t st = 0;
+    DeodrSceneView v;
+    // The forward state (owner ids, tile edge lists) is rebuilt from the scene: the call is stateless like the
+    // reference's, which also re-derives everything from the scene and the z-buffer.
+    if (int rc = host_forward(ws, scene, sigma, &v, st)) return rc;
+    const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
+    const size_t V = scene->nb_vertices, U = scene->nb_uv;
+    const size_t tex = (size_t)scene->texture_height * scene->texture_width * C;
+    if (int rc = upload_f64_as_f32(ws, ws->h_image_b, image_b, P * C, st)) return rc;
+    const size_t n_ij = 2 * V, n_col = V * C, n_uv = 2 * U, n_sh = V, n_grad = n_ij + n_col + n_uv + n_sh + tex;
+    if (ws->h_grads.ensure(n_grad * sizeof(float), &ws->bytes)) return DEODR_B200_ECUDA;
+    CUDA_TRY(cudaMemsetAsync(ws->h_grads.ptr, 0, n_grad * sizeof(float), st));
+    DeodrGrads g;
+    g.ij_b = ws->h_grads.as<float>();
+    g.colors_b = g.ij_b + n_ij;
+    g.uv_b = g.colors_b + n_col;
+    g.shade_b = g.uv_b + n_uv;
+    g.texture_b = g.shade_b + n_sh;
+    if (int rc = deodr_b200_render_b(ws, &v, sigma, ws->h_z.as<double>(), ws->h_owner.as<int>(),
+                                     ws->h_image_b.as<float>(), &g, st))
+        return rc;
+    std::vector<float> host(n_grad);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), ws->h_grads.ptr, n_grad * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const float *p = host.data();
+    for (size_t i = 0; i < n_ij; i++) scene->ij_b[i] += (double)p[i];
+    p += n_ij;
+    for (size_t i = 0; i < n_col; i++) scene->colors_b[i] += (double)p[i];
+    p += n_col;
+    for (size_t i = 0; i < n_uv; i++) scene->uv_b[i] += (double)p[i];
+    p += n_uv;
+    for (size_t i = 0; i < n_sh; i++) scene->shade_b[i] += (double)p[i];
+    p += n_sh;
+    for (size_t i = 0; i < tex; i++) scene->texture_b[i] += (double)p[i];
+    return DEODR_B200_OK;
+}
+
+}  // extern "C"

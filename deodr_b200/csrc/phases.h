@@ -1,0 +1,465 @@
+// Barrier-separated phases of the binning and tile-raster kernels, written as __host__ __device__ functions of the
+// thread index.  kernels.cu strings them together with __syncthreads() in between; the CPU emulation harness under
+// tests/emul (test infrastructure) calls the same functions in `for (tid ...)` loops, which is how the kernel logic
+// is checked against the oracle in a container without a GPU.
+//
+// `Env` supplies the few operations that differ between the two worlds (atomics, warp aggregation).
+#pragma once
+
+#include "shade.h"
+
+namespace deodr {
+
+constexpr int TS = 16;            // tile side in pixels
+constexpr int NT = TS * TS;       // threads per tile CTA, one per pixel
+constexpr int TRI_CHUNK = 128;    // triangle records staged in shared memory per pass
+constexpr int EDGE_CHUNK = 64;    // edge records staged in shared memory per pass
+
+struct TriRec {
+    TriGeom g;
+    int32_t id;
+    int32_t pad;
+};
+
+struct TileShared {
+    union {
+        struct {
+            TriRec rec[TRI_CHUNK];
+            uint16_t mask[TRI_CHUNK][TS];  // bit c of mask[t][r]: pixel (col c, row r) of the tile is covered by t
+        } tri;
+        struct {
+            EdgeRec rec[EDGE_CHUNK];
+            uint32_t span[EDGE_CHUNK][TS];  // x_begin | x_end << 16 (absolute, int16 each); empty if begin > end
+        } edge;
+    };
+};
+
+struct Tile {
+    int x0, y0;  // pixel origin
+};
+
+DEODR_HD Tile tile_of(int tile_id, int tiles_x) {
+    Tile t;
+    t.y0 = (tile_id / tiles_x) * TS;
+    t.x0 = (tile_id % tiles_x) * TS;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------- binning
+
+// Tiles overlapped by the exact bounding box of a drawn triangle (rows/cols the reference can touch).
+struct TileBox {
+    int tx0, tx1, ty0, ty1;  // inclusive; empty if tx0 > tx1
+};
+
+DEODR_HD TileBox tri_tile_box(const TriGeom &g, int width, int height) {
+    TileBox b;
+    int y0, y1;
+    tri_row_range(g, height, &y0, &y1);
+    int x0 = g.x_min < 0 ? 0 : g.x_min, x1 = g.x_max > width - 1 ? width - 1 : g.x_max;
+    if (y0 > y1 || x0 > x1) { b.tx0 = 1; b.tx1 = 0; b.ty0 = 1; b.ty1 = 0; return b; }
+    b.tx0 = x0 / TS; b.tx1 = x1 / TS; b.ty0 = y0 / TS; b.ty1 = y1 / TS;
+    return b;
+}
+
+DEODR_HD TileBox edge_tile_box(const EdgeGeom &g, const double V[2][2], double sigma, int width) {
+    TileBox b;
+    double lo = fmin(V[0][0], V[1][0]) - sigma, hi = fmax(V[0][0], V[1][0]) + sigma;
+    int x0 = (int)floor(fmax(lo, -1.0)) - 1, x1 = (int)ceil(fmin(hi, (double)width)) + 1;
+    if (x0 < 0) x0 = 0;
+    if (x1 > width - 1) x1 = width - 1;
+    if (g.y_begin > g.y_end || x0 > x1) { b.tx0 = 1; b.tx1 = 0; b.ty0 = 1; b.ty1 = 0; return b; }
+    b.tx0 = x0 / TS; b.tx1 = x1 / TS; b.ty0 = g.y_begin / TS; b.ty1 = g.y_end / TS;
+    return b;
+}
+
+// One thread per triangle.  mode 0 (count): tile_count[tile] += 1 and the effective edge flags are written;
+// mode 1 (fill): the triangle index is appended to the tile's list.
+template <class Env>
+DEODR_HD void bin_triangle(const SceneView &s, int k, double sigma, int tiles_x, int mode, int *tile_count,
+                           const int *tile_offset, int *tile_cursor, int *refs, uint8_t *edge_selected) {
+    uint32_t vid[3];
+    double V[3][2], Zv[3];
+    gather_tri(s, k, vid, V, Zv);
+    TriClass c = classify_tri(s, k, V, Zv);
+    if (mode == 0 && edge_selected)
+        for (int n = 0; n < 3; n++)  // DR.h:2839-2853: overdrawn iff sigma > 0, signedArea > 0 and the flag is set
+            edge_selected[3 * k + n] = (uint8_t)(sigma > 0 && c.area_positive && s.edgeflags[3 * k + n]);
+    if (!c.drawn) return;
+    remove_offset(V, 3, pixel_offset(s));
+    TriGeom g;
+    tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
+    TileBox b = tri_tile_box(g, s.width, s.height);
+    for (int ty = b.ty0; ty <= b.ty1; ty++)
+        for (int tx = b.tx0; tx <= b.tx1; tx++) {
+            int t = ty * tiles_x + tx;
+            if (mode == 0) Env::atomic_add(&tile_count[t], 1);
+            else refs[tile_offset[t] + Env::atomic_add(&tile_cursor[t], 1)] = k;
+        }
+}
+
+// One thread per silhouette edge in far-to-near order (rank r).
+template <class Env>
+DEODR_HD void bin_edge(const SceneView &s, int edge_id, int rank, double sigma, int tiles_x, int mode, int *tile_count,
+                       const int *tile_offset, int *tile_cursor, int *refs) {
+    int k = edge_id / 3, n = edge_id - 3 * k;
+    double V[2][2], Zv[2];
+    for (int i = 0; i < 2; i++) {
+        uint32_t v = s.faces[3 * k + edge_vertex(n, i)];
+        V[i][0] = s.ij[2 * (size_t)v];
+        V[i][1] = s.ij[2 * (size_t)v + 1];
+        Zv[i] = s.depths[v];
+    }
+    remove_offset(V, 2, pixel_offset(s));
+    EdgeGeom g;
+    edge_geom(V, Zv, s.height, sigma, s.clockwise != 0, s.perspective_correct != 0, &g, nullptr, nullptr, nullptr);
+    TileBox b = edge_tile_box(g, V, sigma, s.width);
+    for (int ty = b.ty0; ty <= b.ty1; ty++)
+        for (int tx = b.tx0; tx <= b.tx1; tx++) {
+            int t = ty * tiles_x + tx;
+            if (mode == 0) Env::atomic_add(&tile_count[t], 1);
+            else refs[tile_offset[t] + Env::atomic_add(&tile_cursor[t], 1)] = rank;
+        }
+}
+
+// ------------------------------------------------------------------------------------------- tile kernel phases
+
+template <int MAXC>
+struct PixelState {
+    double z;        // running z-buffer value of the pixel
+    int own;         // forward owner: lowest index among the triangles reaching the minimum z (strict '<', DR.h:961)
+    int bown;        // adjoint owner: highest such index (DR.h:1024 walked in reverse index order)
+    float col[MAXC];
+};
+
+// Phase T1: thread tid < n sets up the record of triangle list[tid].
+DEODR_HD void phase_tri_setup(const SceneView &s, int tid, int n, const int *list, TileShared *sh) {
+    if (tid >= n) return;
+    int k = list[tid];
+    uint32_t vid[3];
+    double V[3][2], Zv[3];
+    gather_tri(s, k, vid, V, Zv);
+    remove_offset(V, 3, pixel_offset(s));
+    tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &sh->tri.rec[tid].g, nullptr);
+    sh->tri.rec[tid].id = k;
+}
+
+// Phase T2: (triangle, row) items -> 16-bit coverage masks of the tile row.
+DEODR_HD void phase_tri_masks(const SceneView &s, int tid, int n, Tile tile, TileShared *sh) {
+    for (int item = tid; item < n * TS; item += NT) {
+        int t = item / TS, r = item % TS;
+        int y = tile.y0 + r;
+        uint32_t m = 0;
+        if (y < s.height) {
+            int xb, xe;
+            tri_row_span(sh->tri.rec[t].g, y, s.width, s.height, s.strict_edge != 0, &xb, &xe);
+            xb -= tile.x0;
+            xe -= tile.x0;
+            if (xb < 0) xb = 0;
+            if (xe > TS - 1) xe = TS - 1;
+            if (xb <= xe) m = ((1u << (xe - xb + 1)) - 1u) << xb;
+        }
+        sh->tri.mask[t][r] = (uint16_t)m;
+    }
+}
+
+// Phase T3: each pixel walks the chunk and keeps the minimum z, order-independently:
+//   own = min index among ties (what a strict '<' walk in ascending index order leaves, DR.h:961),
+//   bown = max index among ties (what the '==' walk in descending index order finds first, DR.h:1024).
+template <int MAXC>
+DEODR_HD void phase_tri_test(const SceneView &s, int tid, int n, Tile tile, const TileShared *sh, PixelState<MAXC> *p) {
+    int c = tid % TS, r = tid / TS;
+    int x = tile.x0 + c, y = tile.y0 + r;
+    for (int t = 0; t < n; t++) {
+        if (!((sh->tri.mask[t][r] >> c) & 1)) continue;
+        double z = tri_z(sh->tri.rec[t].g, x, y, s.perspective_correct != 0);
+        int id = sh->tri.rec[t].id;
+        if (z < p->z) { p->z = z; p->own = id; p->bown = id; }
+        else if (z == p->z && p->own >= 0) { if (id < p->own) p->own = id; if (id > p->bown) p->bown = id; }
+    }
+}
+
+// Phase S: background + owner colour.
+template <int MAXC>
+DEODR_HD void phase_shade(const SceneView &s, int x, int y, PixelState<MAXC> *p) {
+    const int C = s.nb_colors;
+    if (p->own < 0) {
+        if (s.background_image) {
+            const float *bg = s.background_image + ((size_t)y * s.width + x) * C;
+            for (int c = 0; c < C; c++) p->col[c] = bg[c];
+        } else {
+            for (int c = 0; c < C; c++) p->col[c] = s.background_color[c];
+        }
+        return;
+    }
+    Owner<MAXC> o;
+    owner_colour<MAXC>(s, p->own, x, y, p->z, &o, p->col);
+}
+
+// Phase E1: thread tid < n sets up the record of the edge with far-to-near rank list[tid].
+DEODR_HD void phase_edge_setup(const SceneView &s, int tid, int n, const int *list, const int *edge_sorted,
+                               double sigma, TileShared *sh) {
+    if (tid >= n) return;
+    int rank = list[tid];
+    edge_record(s, edge_sorted[rank], rank, sigma, &sh->edge.rec[tid]);
+}
+
+// Phase E2: (edge, row) items -> x spans.
+DEODR_HD void phase_edge_spans(const SceneView &s, int tid, int n, Tile tile, TileShared *sh) {
+    for (int item = tid; item < n * TS; item += NT) {
+        int e = item / TS, r = item % TS;
+        int y = tile.y0 + r;
+        uint32_t packed = 1u;  // begin = 1, end = 0: empty
+        const EdgeGeom &g = sh->edge.rec[e].g;
+        if (y >= g.y_begin && y <= g.y_end) {
+            int xb, xe;
+            edge_row_span(g, s.width, y, &xb, &xe);
+            if (xb <= xe) packed = ((uint32_t)(uint16_t)(int16_t)xb) | (((uint32_t)(uint16_t)(int16_t)xe) << 16);
+        }
+        sh->edge.span[e][r] = packed;
+    }
+}
+
+DEODR_HD bool edge_covers(const TileShared *sh, int e, int r, int x) {
+    uint32_t packed = sh->edge.span[e][r];
+    int xb = (int16_t)(packed & 0xffffu), xe = (int16_t)(packed >> 16);
+    return x >= xb && x <= xe;
+}
+
+// Phase E3 (forward): overdraw in list order.  image = T*image + (1-T)*A where Z_edge < z_buffer (DR.h:1632-1641).
+template <int MAXC>
+DEODR_HD void phase_edge_blend(const SceneView &s, int x, int y, int r, int n, const TileShared *sh, PixelState<MAXC> *p) {
+    const int C = s.nb_colors;
+    for (int e = 0; e < n; e++) {
+        if (!edge_covers(sh, e, r, x)) continue;
+        const EdgeRec &rec = sh->edge.rec[e];
+        double ze = edge_z(rec, x, y, s.perspective_correct != 0);
+        if (!(ze < p->z)) continue;
+        EdgeHit<MAXC> h;
+        edge_hit<MAXC>(s, rec, x, y, ze, &h);
+        float T = (float)h.T, omT = (float)(1.0 - h.T);
+        for (int c = 0; c < C; c++) p->col[c] = p->col[c] * T + omT * h.A[c];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------- adjoint
+
+// Running state of a pixel during the backward edge sweep.  The colour is tracked in fp64 so that the un-blend
+// (DR.h:1738) recovers the colour each edge saw as accurately as the reference does.
+template <int MAXC>
+struct AdjointState {
+    double col[MAXC];   // colour of the pixel after the edges processed so far (forward) / before them (reverse)
+    float g[MAXC];      // adjoint of the pixel colour
+    bool has_colour;    // col[] initialised (done lazily: only pixels inside an edge band need it)
+};
+
+// Forward replay over one chunk (edges in list order) in fp64: col <- T*col + (1-T)*A.
+template <int MAXC>
+DEODR_HD void phase_edge_replay(const SceneView &s, int x, int y, int r, int n, const TileShared *sh,
+                                const PixelState<MAXC> &p, AdjointState<MAXC> *a) {
+    const int C = s.nb_colors;
+    for (int e = 0; e < n; e++) {
+        if (!edge_covers(sh, e, r, x)) continue;
+        const EdgeRec &rec = sh->edge.rec[e];
+        double ze = edge_z(rec, x, y, false);
+        if (!(ze < p.z)) continue;
+        if (!a->has_colour) {
+            PixelState<MAXC> q = p;
+            phase_shade<MAXC>(s, x, y, &q);
+            for (int c = 0; c < C; c++) a->col[c] = (double)q.col[c];
+            a->has_colour = true;
+        }
+        EdgeHit<MAXC> h;
+        edge_hit<MAXC>(s, rec, x, y, ze, &h);
+        for (int c = 0; c < C; c++) a->col[c] = a->col[c] * h.T + (1.0 - h.T) * (double)h.A[c];
+    }
+}
+
+// Reverse sweep over one chunk (edges in reverse list order): un-blend, per-edge plane adjoints, g <- T*g.
+// DR.h:1726-1749 (interpolated) / DR.h:2008-2032 (textured), accumulated per edge as moments over (x, y, 1).
+template <int MAXC, class Env>
+DEODR_HD void phase_edge_adjoint(const SceneView &s, int x, int y, int r, int n, const TileShared *sh,
+                                 const PixelState<MAXC> &p, AdjointState<MAXC> *a, double *edge_acc, float *texture_b) {
+    const int C = s.nb_colors;
+    const int stride = edge_acc_stride(C);
+    for (int e = n - 1; e >= 0; e--) {
+        if (!edge_covers(sh, e, r, x)) continue;
+        const EdgeRec &rec = sh->edge.rec[e];
+        double ze = edge_z(rec, x, y, false);
+        if (!(ze < p.z)) continue;
+        EdgeHit<MAXC> h;
+        edge_hit<MAXC>(s, rec, x, y, ze, &h);
+        double *acc = edge_acc + (size_t)rec.rank * stride;
+        const double T = h.T, omT = 1.0 - h.T;
+        double T_B = 0;
+        const double t3[3] = {(double)x, (double)y, 1.0};
+        if (rec.textured) {
+            double L_B = 0;
+            float e0_B = 0, e1_B = 0;
+            for (int c = 0; c < C; c++) {
+                double gc = (double)a->g[c];
+                double prev = (a->col[c] - omT * (double)h.A[c]) / T;  // colour before this edge
+                T_B += gc * (prev - (double)h.A[c]);
+                a->col[c] = prev;
+                float A_B = (float)(omT * gc) * h.L;                    // adjoint of the texture sample
+                L_B += omT * gc * (double)h.texval[c];
+                texture_fetch_duv(h.tap, s.texture, c, A_B, &e0_B, &e1_B);
+                if (texture_b) {
+                    float w00 = (1.0f - h.tap.e0) * (1.0f - h.tap.e1), w10 = h.tap.e0 * (1.0f - h.tap.e1);
+                    float w01 = (1.0f - h.tap.e0) * h.tap.e1, w11 = h.tap.e0 * h.tap.e1;
+                    Env::atomic_add(texture_b + h.tap.i00 + c, w00 * A_B);
+                    Env::atomic_add(texture_b + h.tap.i10 + c, w10 * A_B);
+                    Env::atomic_add(texture_b + h.tap.i01 + c, w01 * A_B);
+                    Env::atomic_add(texture_b + h.tap.i11 + c, w11 * A_B);
+                }
+                a->g[c] = (float)(gc * T);
+            }
+            double U_B = h.tap.out0 ? 0.0 : (double)e0_B, V_B = h.tap.out1 ? 0.0 : (double)e1_B;
+            for (int j = 0; j < 3; j++) {
+                Env::atomic_add(acc + 3 + j, L_B * t3[j]);
+                Env::atomic_add(acc + 6 + j, U_B * t3[j]);
+                Env::atomic_add(acc + 9 + j, V_B * t3[j]);
+            }
+        } else {
+            for (int c = 0; c < C; c++) {
+                double gc = (double)a->g[c];
+                double prev = (a->col[c] - omT * (double)h.A[c]) / T;
+                T_B += gc * (prev - (double)h.A[c]);
+                a->col[c] = prev;
+                double A_B = omT * gc;
+                for (int j = 0; j < 3; j++) Env::atomic_add(acc + 12 + 3 * c + j, A_B * t3[j]);
+                a->g[c] = (float)(gc * T);
+            }
+        }
+        for (int j = 0; j < 3; j++) Env::atomic_add(acc + j, T_B * t3[j]);
+    }
+}
+
+// Interior adjoint of one pixel: the residual colour adjoint g goes to the adjoint owner's vertices.
+// Per pixel, with barycentrics b_v and their gradients (closed form of DR.h:841-858 / 1138-1156):
+//   attr_b[v]  += (d colour / d attr) g * b_v
+//   ij_b[v][d] += - b_v * sum_c g_c * d colour_c / d x_d
+template <int MAXC, class Env>
+DEODR_HD void phase_interior_adjoint(const SceneView &s, int x, int y, const PixelState<MAXC> &p, const float *g,
+                                     float *ij_b, float *colors_b, float *uv_b, float *shade_b, float *texture_b) {
+    const int C = s.nb_colors;
+    const int k = p.bown;
+    Owner<MAXC> o;
+    float colour[MAXC];
+    owner_colour<MAXC>(s, k, x, y, p.z, &o, colour);
+    float dcdx = 0, dcdy = 0;  // sum_c g_c * d colour_c / dx, dy
+    if (o.textured) {
+        float L_B = 0, e0_B = 0, e1_B = 0;
+        for (int c = 0; c < C; c++) {
+            float A_B = g[c] * o.L;
+            L_B += g[c] * o.texval[c];
+            texture_fetch_duv(o.tap, s.texture, c, A_B, &e0_B, &e1_B);
+            if (texture_b) {
+                float w00 = (1.0f - o.tap.e0) * (1.0f - o.tap.e1), w10 = o.tap.e0 * (1.0f - o.tap.e1);
+                float w01 = (1.0f - o.tap.e0) * o.tap.e1, w11 = o.tap.e0 * o.tap.e1;
+                Env::atomic_add(texture_b + o.tap.i00 + c, w00 * A_B);
+                Env::atomic_add(texture_b + o.tap.i10 + c, w10 * A_B);
+                Env::atomic_add(texture_b + o.tap.i01 + c, w01 * A_B);
+                Env::atomic_add(texture_b + o.tap.i11 + c, w11 * A_B);
+            }
+        }
+        float U_B = o.tap.out0 ? 0.0f : e0_B, V_B = o.tap.out1 ? 0.0f : e1_B;
+        float dudx = 0, dudy = 0, dvdx = 0, dvdy = 0, dLdx = 0, dLdy = 0;
+        for (int i = 0; i < 3; i++) {
+            float gx = (float)o.bary.gx[i], gy = (float)o.bary.gy[i];
+            float ui = (float)s.uv[2 * (size_t)o.uvid[i]], vi = (float)s.uv[2 * (size_t)o.uvid[i] + 1];
+            float li = s.shade[o.vid[i]];
+            dudx += gx * ui; dudy += gy * ui; dvdx += gx * vi; dvdy += gy * vi; dLdx += gx * li; dLdy += gy * li;
+            Env::emit(uv_b + 2 * (size_t)o.uvid[i], U_B * o.w[i]);
+            Env::emit(uv_b + 2 * (size_t)o.uvid[i] + 1, V_B * o.w[i]);
+            Env::emit(shade_b + o.vid[i], L_B * o.w[i]);
+        }
+        dcdx = U_B * dudx + V_B * dvdx + L_B * dLdx;
+        dcdy = U_B * dudy + V_B * dvdy + L_B * dLdy;
+    } else {
+        const float *a0 = s.colors + (size_t)o.vid[0] * C, *a1 = s.colors + (size_t)o.vid[1] * C,
+                    *a2 = s.colors + (size_t)o.vid[2] * C;
+        float gx0 = (float)o.bary.gx[0], gx1 = (float)o.bary.gx[1], gx2 = (float)o.bary.gx[2];
+        float gy0 = (float)o.bary.gy[0], gy1 = (float)o.bary.gy[1], gy2 = (float)o.bary.gy[2];
+        for (int c = 0; c < C; c++) {
+            dcdx += g[c] * (gx0 * a0[c] + gx1 * a1[c] + gx2 * a2[c]);
+            dcdy += g[c] * (gy0 * a0[c] + gy1 * a1[c] + gy2 * a2[c]);
+            for (int i = 0; i < 3; i++) Env::emit(colors_b + (size_t)o.vid[i] * C + c, g[c] * o.w[i]);
+        }
+    }
+    for (int i = 0; i < 3; i++) {
+        Env::emit(ij_b + 2 * (size_t)o.vid[i], -o.w[i] * dcdx);
+        Env::emit(ij_b + 2 * (size_t)o.vid[i] + 1, -o.w[i] * dcdy);
+    }
+}
+
+// One thread per sorted silhouette edge: turn the accumulated plane adjoints into vertex adjoints.
+// DR.h:1758-1773 / 2045-2060 followed by get_edge_stencil_equations_B DR.h:1462-1539.
+template <class Env>
+DEODR_HD void finalize_edge(const SceneView &s, int edge_id, double sigma, const double *acc, float *ij_b,
+                            float *colors_b, float *uv_b, float *shade_b) {
+    const int C = s.nb_colors;
+    int k = edge_id / 3, n = edge_id - 3 * k;
+    uint32_t vid[2], uvid[2];
+    double V[2][2], Zv[2];
+    for (int i = 0; i < 2; i++) {
+        int loc = edge_vertex(n, i);
+        vid[i] = s.faces[3 * k + loc];
+        uvid[i] = s.faces_uv[3 * k + loc];
+        V[i][0] = s.ij[2 * (size_t)vid[i]];
+        V[i][1] = s.ij[2 * (size_t)vid[i] + 1];
+        Zv[i] = s.depths[vid[i]];
+    }
+    remove_offset(V, 2, pixel_offset(s));
+    EdgeGeom g;
+    double E[9], Einv[9], nt[3];
+    edge_geom(V, Zv, s.height, sigma, s.clockwise != 0, false, &g, E, Einv, nt);
+    const bool textured = s.textured[k] && s.shaded[k];
+    double Einv_B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < 3; j++) Einv_B[6 + j] += acc[j] * (1.0 / sigma);  // T = (row 2 of Einv) / sigma
+    if (textured) {
+        for (int q = 0; q < 2; q++) {  // edge vertex q
+            double sh_b = 0, u_b = 0, v_b = 0;
+            double shade_q = (double)s.shade[vid[q]];
+            double uq = s.uv[2 * (size_t)uvid[q]], vq = s.uv[2 * (size_t)uvid[q] + 1];
+            for (int j = 0; j < 3; j++) {
+                sh_b += acc[3 + j] * Einv[3 * q + j];
+                u_b += acc[6 + j] * Einv[3 * q + j];
+                v_b += acc[9 + j] * Einv[3 * q + j];
+                Einv_B[3 * q + j] += acc[3 + j] * shade_q + acc[6 + j] * uq + acc[9 + j] * vq;
+            }
+            Env::atomic_add(shade_b + vid[q], (float)sh_b);
+            Env::atomic_add(uv_b + 2 * (size_t)uvid[q], (float)u_b);
+            Env::atomic_add(uv_b + 2 * (size_t)uvid[q] + 1, (float)v_b);
+        }
+    } else {
+        for (int q = 0; q < 2; q++)
+            for (int c = 0; c < C; c++) {
+                double col_b = 0, a = (double)s.colors[(size_t)vid[q] * C + c];
+                for (int j = 0; j < 3; j++) {
+                    col_b += acc[12 + 3 * c + j] * Einv[3 * q + j];
+                    Einv_B[3 * q + j] += a * acc[12 + 3 * c + j];
+                }
+                Env::atomic_add(colors_b + (size_t)vid[q] * C + c, (float)col_b);
+            }
+    }
+    double E_B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    inv3x3_adjoint(Einv, Einv_B, E_B);
+    double V_B[2][2] = {{E_B[0], E_B[3]}, {E_B[1], E_B[4]}};
+    // normal n = nt * inv_norm, inv_norm = 1/|nt|  (DR.h:1508-1538)
+    double n_B[2] = {E_B[2], E_B[5]};
+    double inv_norm = nt[2];
+    double nt_B[2] = {n_B[0] * inv_norm, n_B[1] * inv_norm};
+    double inv_norm_B = n_B[0] * nt[0] + n_B[1] * nt[1];
+    double nor_s_B = -inv_norm_B * (inv_norm * inv_norm) * 0.5 * inv_norm;
+    nt_B[0] += 2 * nt[0] * nor_s_B;
+    nt_B[1] += 2 * nt[1] * nor_s_B;
+    if (s.clockwise) { V_B[0][1] += nt_B[0]; V_B[1][1] -= nt_B[0]; V_B[1][0] += nt_B[1]; V_B[0][0] -= nt_B[1]; }
+    else             { V_B[0][1] -= nt_B[0]; V_B[1][1] += nt_B[0]; V_B[1][0] -= nt_B[1]; V_B[0][0] += nt_B[1]; }
+    for (int i = 0; i < 2; i++) {
+        Env::atomic_add(ij_b + 2 * (size_t)vid[i], (float)V_B[i][0]);
+        Env::atomic_add(ij_b + 2 * (size_t)vid[i] + 1, (float)V_B[i][1]);
+    }
+}
+
+}  // namespace deodr

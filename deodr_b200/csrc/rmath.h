@@ -1,0 +1,308 @@
+// Exact (fp64, reference-operation-order) geometry of the raster hot path: triangle stencil setup, per-row spans,
+// z planes, silhouette-edge band setup and spans.  Everything that decides WHICH pixel is covered and WHAT z it gets
+// lives here, so that the z-buffer / owner id can be bit-identical to the reference
+// (C++/DifferentiableRenderer.h, "DR.h" below).
+//
+// The functions are __host__ __device__: the CUDA kernels (kernels.cu) call them on the device, and the CPU
+// emulation harness under tests/emul (test infrastructure, never shipped) calls the very same code on the host to
+// check it against the oracle without a GPU.
+//
+// No FMA contraction is allowed in this file: on the device every product/sum goes through __dmul_rn/__dadd_rn
+// (never fused by ptxas); the host harness is compiled with -ffp-contract=off.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DEODR_HD __host__ __device__ __forceinline__
+#else
+#define DEODR_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+#define DDIV(a, b) __ddiv_rn((a), (b))
+#define DSQRT(a) __dsqrt_rn((a))
+#else
+#define DMUL(a, b) ((a) * (b))
+#define DADD(a, b) ((a) + (b))
+#define DSUB(a, b) ((a) - (b))
+#define DDIV(a, b) ((a) / (b))
+#define DSQRT(a) sqrt((a))
+#endif
+
+namespace deodr {
+
+// a*b - c*d with two roundings on the products and one on the difference (never fused)
+DEODR_HD double diff_of_products(double a, double b, double c, double d) { return DSUB(DMUL(a, b), DMUL(c, d)); }
+
+// DR.h:92-117: T = transposed cofactors of S times 1/det; det = (S0*T0 + S1*T3) + S2*T6.
+DEODR_HD void inv3x3(const double *S, double *T) {
+    T[0] = diff_of_products(S[4], S[8], S[7], S[5]);
+    T[3] = -diff_of_products(S[3], S[8], S[6], S[5]);
+    T[6] = diff_of_products(S[3], S[7], S[6], S[4]);
+    T[1] = -diff_of_products(S[1], S[8], S[7], S[2]);
+    T[4] = diff_of_products(S[0], S[8], S[6], S[2]);
+    T[7] = -diff_of_products(S[0], S[7], S[6], S[1]);
+    T[2] = diff_of_products(S[1], S[5], S[4], S[2]);
+    T[5] = -diff_of_products(S[0], S[5], S[3], S[2]);
+    T[8] = diff_of_products(S[0], S[4], S[3], S[1]);
+    double det = DADD(DADD(DMUL(S[0], T[0]), DMUL(S[1], T[3])), DMUL(S[2], T[6]));
+    double inv_det = DDIV(1.0, det);
+    for (int k = 0; k < 9; k++) T[k] = DMUL(T[k], inv_det);
+}
+
+// (short) conversion of the reference: double -> int32 (truncation) -> low 16 bits, sign-extended.
+DEODR_HD int to_short(double v) {
+#if defined(__CUDA_ARCH__)
+    int i = __double2int_rz(v);
+#else
+    int i = (int)v;
+#endif
+    return (int)(int16_t)(i & 0xffff);
+}
+
+// Largest x in [x_min, x_max] such that pred(x') holds for every x' in (x_min, x]; pred is monotone in x'
+// (a rounded product with a fixed factor is monotone), so the reference's incremental loops of DR.h:461-476 and
+// DR.h:501-516 are equivalent to this bisection.  mode: 0 '<=', 1 '>=', 2 '<', 3 '>'.
+DEODR_HD int monotone_search(double a, double b, int x_min, int x_max, int mode) {
+    int lo = x_min, hi = x_max;  // invariant: pred holds on (x_min, lo]; fails at hi+1 (or hi == x_max)
+    while (lo < hi) {
+        int mid = lo + ((hi - lo + 1) >> 1);  // candidate x, tests x' = mid (the loop tests (x+1) with x = mid-1)
+        double p = DMUL((double)mid, b);
+        bool ok = mode == 0 ? (p <= a) : mode == 1 ? (p >= a) : mode == 2 ? (p < a) : (p > a);
+        if (ok) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// DR.h:440-479: min(x_max, max(x_min, floor(a/b))) with the robust fall-back.  Result passes through `short`.
+DEODR_HD int floor_div_clamped(double a, double b, int x_min, int x_max) {
+    if (DMUL(fabs(b), 32767.0) > DADD(fabs(a), fabs(b))) {
+        int x = to_short(floor(DDIV(a, b)));
+        if (x < x_min) x = to_short((double)x_min);
+        if (x > x_max) x = to_short((double)x_max);
+        return x;
+    }
+    return monotone_search(a, b, x_min, x_max, b > 0 ? 0 : 1);
+}
+
+// DR.h:481-519
+DEODR_HD int ceil_div_clamped(double a, double b, int x_min, int x_max) {
+    if (DMUL(fabs(b), 32767.0) > DADD(fabs(a), fabs(b))) {
+        int x = to_short(ceil(DDIV(a, b)));
+        if (x < x_min) x = to_short((double)x_min);
+        if (x > x_max) x = to_short((double)x_max);
+        return x;
+    }
+    return monotone_search(a, b, x_min, x_max, b > 0 ? 2 : 3);
+}
+
+// ------------------------------------------------------------------------------------------------ triangles
+
+// DR.h:391-398 on the caller-supplied (un-offset) vertices; only the sign is used.
+DEODR_HD double signed_area(const double V[3][2], bool clockwise) {
+    double ux = DSUB(V[1][0], V[0][0]), uy = DSUB(V[1][1], V[0][1]);
+    double vx = DSUB(V[2][0], V[0][0]), vy = DSUB(V[2][1], V[0][1]);
+    return DMUL(DMUL(0.5, DSUB(DMUL(ux, vy), DMUL(vx, uy))), clockwise ? 1.0 : -1.0);
+}
+
+// Raster record of one triangle: what the tile kernel keeps in shared memory.
+struct TriGeom {
+    double eq[3][3];  // edge equations a x + b y + c  (DR.h:373-389)
+    double zp[3];     // z (or 1/z when perspective_correct) plane: zp[0] x + zp[1] y + zp[2]
+    int16_t x_min, x_max;
+    int16_t y_begin[2], y_end[2];
+    uint8_t left[2], right[2];
+};
+
+DEODR_HD void edge_equation(double e[3], const double v1[2], const double v2[2], bool cw) {
+    if (cw) { e[0] = DSUB(v1[1], v2[1]); e[1] = DSUB(v2[0], v1[0]); }
+    else    { e[0] = DSUB(v2[1], v1[1]); e[1] = DSUB(v1[0], v2[0]); }
+    e[2] = DMUL(-0.5, DADD(DMUL(e[0], DADD(v1[0], v2[0])), DMUL(e[1], DADD(v1[1], v2[1]))));
+}
+
+// three compare-exchanges of DR.h:400-426; only what the caller needs: sorted values and the index of min / max
+DEODR_HD void order3(const double v[3], double sv[3], int idx[3]) {
+    sv[0] = v[0]; sv[1] = v[1]; sv[2] = v[2];
+    idx[0] = 0; idx[1] = 1; idx[2] = 2;
+    if (sv[0] > sv[1]) { double t = sv[0]; sv[0] = sv[1]; sv[1] = t; int i = idx[0]; idx[0] = idx[1]; idx[1] = i; }
+    if (sv[0] > sv[2]) { double t = sv[0]; sv[0] = sv[2]; sv[2] = t; int i = idx[0]; idx[0] = idx[2]; idx[2] = i; }
+    if (sv[1] > sv[2]) { double t = sv[1]; sv[1] = sv[2]; sv[2] = t; int i = idx[1]; idx[1] = idx[2]; idx[2] = i; }
+}
+
+// DR.h:633-739 (stencil) + DR.h:787 / 775 (z plane).  V already has the pixel-centre offset removed.
+// Minv (xy1_to_bary) is returned for callers that need the reference's planes; pass nullptr otherwise.
+DEODR_HD void tri_geom(const double V[3][2], const double Zv[3], bool strict, bool persp, TriGeom *g, double *Minv_out) {
+    double M[9], Minv[9];
+    for (int v = 0; v < 3; v++) { M[v] = V[v][0]; M[3 + v] = V[v][1]; M[6 + v] = 1.0; }
+    inv3x3(M, Minv);
+    bool cw = signed_area(V, true) > 0;
+    edge_equation(g->eq[0], V[0], V[1], cw);
+    edge_equation(g->eq[1], V[1], V[2], cw);
+    edge_equation(g->eq[2], V[2], V[0], cw);
+    double xu[3] = {V[0][0], V[1][0], V[2][0]}, yu[3] = {V[0][1], V[1][1], V[2][1]}, xs[3], ys[3];
+    int xo[3], yo[3];
+    order3(xu, xs, xo);
+    order3(yu, ys, yo);
+    g->x_min = (int16_t)(strict ? to_short(floor(xs[0])) : to_short(ceil(xs[0])));
+    g->x_max = (int16_t)to_short(floor(xs[2]));
+    // NB: "(short)floor(y) + 1" is computed in int and then stored in an int: no 16-bit wrap of the +1
+    int yb0 = strict ? to_short(floor(ys[0])) + 1 : to_short(ceil(ys[0]));
+    int yb1 = strict ? to_short(floor(ys[1])) + 1 : to_short(ceil(ys[1]));
+    // the +1 can only leave the int16 range at 32768, far outside any image: saturate for storage
+    g->y_begin[0] = (int16_t)(yb0 > 32767 ? 32767 : yb0);
+    g->y_begin[1] = (int16_t)(yb1 > 32767 ? 32767 : yb1);
+    g->y_end[0] = (int16_t)to_short(floor(ys[1]));
+    g->y_end[1] = (int16_t)to_short(floor(ys[2]));
+    int id = yo[0];
+    if (g->eq[id][0] > 0) { g->right[0] = (uint8_t)((id + 2) % 3); g->left[0] = (uint8_t)id; }
+    else                  { g->right[0] = (uint8_t)id;             g->left[0] = (uint8_t)((id + 2) % 3); }
+    id = yo[2];
+    if (g->eq[id][0] < 0) { g->right[1] = (uint8_t)id;             g->left[1] = (uint8_t)((id + 2) % 3); }
+    else                  { g->right[1] = (uint8_t)((id + 2) % 3); g->left[1] = (uint8_t)id; }
+    double zv[3] = {Zv[0], Zv[1], Zv[2]};
+    if (persp) for (int i = 0; i < 3; i++) zv[i] = DDIV(1.0, Zv[i]);
+    // mul_vect_matrix3x3 DR.h:272-280: ((0 + Minv[i] z0) + Minv[3+i] z1) + Minv[6+i] z2
+    for (int i = 0; i < 3; i++)
+        g->zp[i] = DADD(DADD(DADD(0.0, DMUL(Minv[i], zv[0])), DMUL(Minv[3 + i], zv[1])), DMUL(Minv[6 + i], zv[2]));
+    if (Minv_out) for (int i = 0; i < 9; i++) Minv_out[i] = Minv[i];
+}
+
+// DR.h:864-906 for one half.  Returns an empty span as x_begin > x_end.
+DEODR_HD void tri_half_span(const TriGeom &g, int half, int y, int width, bool strict, int *x_begin, int *x_end) {
+    const double *l = g.eq[g.left[half]], *r = g.eq[g.right[half]];
+    int x_min = g.x_min, x_max = g.x_max;
+    if (x_min < 0) x_min = 0;
+    if (x_max > width - 1) x_max = width - 1;
+    int xb = x_min, xe = x_max;
+    double num = -DADD(DMUL(l[1], (double)y), l[2]);
+    int tmp = strict ? to_short((double)(1 + floor_div_clamped(num, l[0], x_min - 1, x_max)))
+                     : ceil_div_clamped(num, l[0], x_min - 1, x_max);
+    if (tmp > xb) xb = tmp;
+    num = -DADD(DMUL(r[1], (double)y), r[2]);
+    tmp = floor_div_clamped(num, r[0], x_min - 1, x_max);
+    if (tmp < xe) xe = tmp;
+    *x_begin = xb;
+    *x_end = xe;
+}
+
+// Coverage of row y = union of the (at most two) halves containing the row.  In non-strict mode the row of the
+// middle vertex can belong to both halves (DR.h:697-711); the reference then draws both spans, and since the z of a
+// pixel does not depend on the half the result is the union.  Both spans share the long-edge bound, so the union is
+// an interval.
+DEODR_HD void tri_row_span(const TriGeom &g, int y, int width, int height, bool strict, int *x_begin, int *x_end) {
+    int xb = 1, xe = 0;
+    for (int half = 0; half < 2; half++) {
+        int y0 = g.y_begin[half], y1 = g.y_end[half];
+        if (y0 < 0) y0 = 0;
+        if (y1 > height - 1) y1 = height - 1;
+        if (y < y0 || y > y1) continue;
+        int b, e;
+        tri_half_span(g, half, y, width, strict, &b, &e);
+        if (b > e) continue;
+        if (xb > xe) { xb = b; xe = e; }
+        else { if (b < xb) xb = b; if (e > xe) xe = e; }
+    }
+    *x_begin = xb;
+    *x_end = xe;
+}
+
+// rows that can be covered (both halves), clipped to the image; empty as y0 > y1
+DEODR_HD void tri_row_range(const TriGeom &g, int height, int *y0, int *y1) {
+    int a = g.y_begin[0] < g.y_begin[1] ? g.y_begin[0] : g.y_begin[1];
+    int b = g.y_end[0] > g.y_end[1] ? g.y_end[0] : g.y_end[1];
+    if (a < 0) a = 0;
+    if (b > height - 1) b = height - 1;
+    *y0 = a;
+    *y1 = b;
+}
+
+// DR.h:934 + 960 (and 946-947 with perspective_correct): Z0y = ((0 + zp0*0) + zp1*y) + zp2 ; Z = Z0y + zp0*x.
+// For finite planes (0 + zp0*0) is +0, so Z0y = zp1*y + zp2 exactly.
+DEODR_HD double plane_row(const double *p, int y) { return DADD(DADD(DADD(0.0, DMUL(p[0], 0.0)), DMUL(p[1], (double)y)), DMUL(p[2], 1.0)); }
+DEODR_HD double plane_at(const double *p, double row0, int x) { return DADD(row0, DMUL(p[0], (double)x)); }
+DEODR_HD double tri_z(const TriGeom &g, int x, int y, bool persp) {
+    double z = plane_at(g.zp, plane_row(g.zp, y), x);
+    return persp ? DDIV(1.0, z) : z;
+}
+
+// ---------------------------------------------------------------------------------------------- silhouette edges
+
+struct EdgeGeom {
+    double ineq[12];  // rows 0,1: edge barycentrics b0,b1; row 2: T = distance/sigma; row 3: 1 - T  (DR.h:1420-1435)
+    double zp[3];     // z plane along the edge (DR.h:1577 / 1564)
+    int y_begin, y_end;
+};
+
+// DR.h:1366-1460 + the z plane.  V = the two end points (offset removed), Zv their depths.
+// E / Einv / nt / inv_norm are returned for the adjoint (pass nullptr when not needed).
+DEODR_HD void edge_geom(const double V[2][2], const double Zv[2], int height, double sigma, bool cw, bool persp,
+                        EdgeGeom *g, double *E_out, double *Einv_out, double *nt_out) {
+    double n[2], E[9], Einv[9];
+    if (cw) { n[0] = DSUB(V[0][1], V[1][1]); n[1] = DSUB(V[1][0], V[0][0]); }
+    else    { n[0] = DSUB(V[1][1], V[0][1]); n[1] = DSUB(V[0][0], V[1][0]); }
+    double inv_norm = DDIV(1.0, DSQRT(DADD(DMUL(n[0], n[0]), DMUL(n[1], n[1]))));
+    if (nt_out) { nt_out[0] = n[0]; nt_out[1] = n[1]; nt_out[2] = inv_norm; }
+    n[0] = DMUL(n[0], inv_norm);
+    n[1] = DMUL(n[1], inv_norm);
+    E[0] = V[0][0]; E[1] = V[1][0]; E[2] = n[0];
+    E[3] = V[0][1]; E[4] = V[1][1]; E[5] = n[1];
+    E[6] = 1.0; E[7] = 1.0; E[8] = 0.0;
+    inv3x3(E, Einv);
+    double inv_sigma = DDIV(1.0, sigma);
+    for (int k = 0; k < 6; k++) g->ineq[k] = Einv[k];
+    for (int k = 0; k < 3; k++) g->ineq[6 + k] = DMUL(inv_sigma, Einv[6 + k]);
+    g->ineq[9] = -g->ineq[6];
+    g->ineq[10] = -g->ineq[7];
+    g->ineq[11] = DSUB(1.0, g->ineq[8]);
+    int yb = height - 1;
+    for (int k = 0; k < 2; k++)
+        if (DSUB(V[k][1], sigma) < (double)yb) yb = (int)floor(DSUB(V[k][1], sigma)) + 1;
+    if (yb < 0) yb = 0;
+    int ye = 0;
+    for (int k = 0; k < 2; k++)
+        if (DADD(V[k][1], sigma) > (double)ye) ye = (int)floor(DADD(V[k][1], sigma));
+    if (ye > height - 1) ye = height - 1;
+    g->y_begin = yb;
+    g->y_end = ye;
+    double zv[2] = {Zv[0], Zv[1]};
+    if (persp) { zv[0] = DDIV(1.0, Zv[0]); zv[1] = DDIV(1.0, Zv[1]); }
+    // mul_matrix(1,2,3) DR.h:296-309: (0 + z0*Einv[k]) + z1*Einv[3+k]
+    for (int k = 0; k < 3; k++) g->zp[k] = DADD(DADD(0.0, DMUL(zv[0], Einv[k])), DMUL(zv[1], Einv[3 + k]));
+    if (E_out) for (int k = 0; k < 9; k++) { E_out[k] = E[k]; Einv_out[k] = Einv[k]; }
+}
+
+// DR.h:2620-2648: the four half-planes are applied in sequence, each clamped against the running bounds.
+DEODR_HD void edge_row_span(const EdgeGeom &g, int width, int y, int *x_begin, int *x_end) {
+    int xb = 0, xe = width - 1;
+    for (int k = 0; k < 4; k++) {
+        const double *q = g.ineq + 3 * k;
+        double num = -DADD(DMUL(q[1], (double)y), q[2]);
+        if (q[0] < 0) {
+            int t = floor_div_clamped(num, q[0], xb - 1, xe + 1);
+            if (t < xe) xe = t;
+        } else {
+            int t = to_short((double)(1 + floor_div_clamped(num, q[0], xb - 1, xe + 1)));
+            if (t > xb) xb = t;
+        }
+    }
+    *x_begin = xb;
+    *x_end = xe;
+}
+
+// sort key: radix-ascending order of this key == descending order of the depth sum (DR.h:2656-2662, 2781)
+DEODR_HD uint64_t depth_desc_key(double s) {
+#if defined(__CUDA_ARCH__)
+    uint64_t b = (uint64_t)__double_as_longlong(s);
+#else
+    union { double d; uint64_t u; } cvt; cvt.d = s; uint64_t b = cvt.u;
+#endif
+    uint64_t asc = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    return ~asc;
+}
+
+}  // namespace deodr

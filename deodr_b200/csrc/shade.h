@@ -1,0 +1,286 @@
+// Per-pixel attribute math of the raster hot path (colours fp32, geometry / uv fp64): barycentrics of the owner
+// triangle, Gouraud / textured-Gouraud colour, bilinear texture tap, silhouette-edge blend, and the per-pixel
+// adjoint contributions.  Coverage and z are decided by rmath.h; nothing here changes WHICH pixel is drawn, so this
+// file may use FMA freely.  __host__ __device__ for the same reason as rmath.h (tests/emul runs it on the CPU).
+//
+// Reference semantics restated here: DR.h:779-785 + 960-965 (interpolated), DR.h:1079-1087 + 1243-1251 (textured
+// gouraud), DR.h:521-560 / 562-631 (bilinear sample and its adjoint), DR.h:1629-1644 / 1877-1902 (edge blend),
+// DR.h:841-858 / 1138-1156 (triangle adjoint), expressed per pixel instead of per scan-line.
+#pragma once
+
+#include "rmath.h"
+
+namespace deodr {
+
+struct SceneView {
+    const uint32_t *faces;             // [T,3]
+    const uint32_t *faces_uv;          // [T,3]
+    const double *ij;                  // [V,2]  col 0 = x (column), col 1 = y (row)
+    const double *depths;              // [V]
+    const double *uv;                  // [Nuv,2] texel coordinates (col 0 = texture column)
+    const float *colors;               // [V,C]
+    const float *shade;                // [V]
+    const uint8_t *edgeflags;          // [T,3]
+    const uint8_t *textured;           // [T]
+    const uint8_t *shaded;             // [T]
+    const float *texture;              // [Ht,Wt,C]
+    const float *background_image;     // [H,W,C] or null
+    const float *background_color;     // [C] or null
+    int nb_triangles, nb_vertices, nb_uv;
+    int height, width, nb_colors;
+    int texture_height, texture_width;
+    int clockwise, backface_culling, strict_edge, perspective_correct, integer_pixel_centers;
+};
+
+DEODR_HD double pixel_offset(const SceneView &s) { return s.integer_pixel_centers ? 0.0 : 0.5; }
+
+// Classification of DR.h:2751-2779: depth-sum key, all-vertices-in-front test, signed area on the UN-offset ij.
+struct TriClass {
+    double sum_depth;
+    bool area_positive;  // signedArea > 0 (0 when a vertex is behind the camera)
+    bool drawn;          // rasterised by pass 1 (DR.h:2786, 2798, 2813)
+    bool textured;       // textured && shaded
+};
+
+DEODR_HD void gather_tri(const SceneView &s, int k, uint32_t vid[3], double V[3][2], double Zv[3]) {
+    for (int i = 0; i < 3; i++) {
+        vid[i] = s.faces[3 * k + i];
+        V[i][0] = s.ij[2 * (size_t)vid[i]];
+        V[i][1] = s.ij[2 * (size_t)vid[i] + 1];
+        Zv[i] = s.depths[vid[i]];
+    }
+}
+
+DEODR_HD TriClass classify_tri(const SceneView &s, int k, const double V[3][2], const double Zv[3]) {
+    TriClass c;
+    c.sum_depth = DADD(DADD(DADD(0.0, Zv[0]), Zv[1]), Zv[2]);
+    bool in_front = !(Zv[0] < 0) && !(Zv[1] < 0) && !(Zv[2] < 0);
+    c.area_positive = in_front && (signed_area(V, s.clockwise != 0) > 0);
+    c.textured = s.textured[k] && s.shaded[k];
+    c.drawn = (c.area_positive || !s.backface_culling) && (c.textured || !s.textured[k]);
+    return c;
+}
+
+DEODR_HD void remove_offset(double V[][2], int n, double off) {
+    for (int i = 0; i < n; i++) { V[i][0] = DSUB(V[i][0], off); V[i][1] = DSUB(V[i][1], off); }
+}
+
+// Vertex pair of silhouette edge n of a face: (1,0), (2,1), (0,2)  (DR.h:2822)
+DEODR_HD int edge_vertex(int n, int i) { return i == 0 ? (n + 1) % 3 : n; }
+
+// ------------------------------------------------------------------------------------------------ barycentrics
+
+struct Bary {
+    double b[3];        // barycentric coordinates of the pixel centre
+    double gx[3], gy[3];  // d b / d x, d b / d y
+};
+
+// Barycentrics in the frame of vertex 0 (well conditioned for small triangles far from the origin).
+DEODR_HD void tri_bary(const double V[3][2], int x, int y, Bary *o) {
+    double e1x = V[1][0] - V[0][0], e1y = V[1][1] - V[0][1];
+    double e2x = V[2][0] - V[0][0], e2y = V[2][1] - V[0][1];
+    double px = (double)x - V[0][0], py = (double)y - V[0][1];
+    double inv = 1.0 / (e1x * e2y - e2x * e1y);
+    o->gx[1] = e2y * inv;  o->gy[1] = -e2x * inv;
+    o->gx[2] = -e1y * inv; o->gy[2] = e1x * inv;
+    o->gx[0] = -(o->gx[1] + o->gx[2]);
+    o->gy[0] = -(o->gy[1] + o->gy[2]);
+    o->b[1] = px * o->gx[1] + py * o->gy[1];
+    o->b[2] = px * o->gx[2] + py * o->gy[2];
+    o->b[0] = 1.0 - o->b[1] - o->b[2];
+}
+
+// ------------------------------------------------------------------------------------------------------ texture
+
+struct Tap {
+    int i00, i10, i01, i11;  // texel offsets, already multiplied by C
+    float e0, e1;
+    bool out0, out1;
+};
+
+// DR.h:527-556: clamp-to-edge bilinear tap at texel coordinate (u = column, v = row)
+DEODR_HD Tap texture_tap(double u, double v, int tex_w, int tex_h, int C) {
+    Tap t;
+    double fu = floor(u), fv = floor(v);
+    int f0 = (int)fu, f1 = (int)fv;
+    double e0 = u - fu, e1 = v - fv;
+    t.out0 = t.out1 = false;
+    if (f0 < 0) { t.out0 = true; f0 = 0; e0 = 0; }
+    if (f0 > tex_w - 2) { t.out0 = true; f0 = tex_w - 2; e0 = 1; }
+    if (f1 < 0) { t.out1 = true; f1 = 0; e1 = 0; }
+    if (f1 > tex_h - 2) { t.out1 = true; f1 = tex_h - 2; e1 = 1; }
+    t.i00 = C * (f0 + tex_w * f1);
+    t.i10 = t.i00 + C;
+    t.i01 = C * (f0 + tex_w * (f1 + 1));
+    t.i11 = t.i01 + C;
+    t.e0 = (float)e0;
+    t.e1 = (float)e1;
+    return t;
+}
+
+DEODR_HD float texture_fetch(const Tap &t, const float *tex, int k) {
+    float top = (1.0f - t.e0) * tex[t.i00 + k] + t.e0 * tex[t.i10 + k];
+    float bot = (1.0f - t.e0) * tex[t.i01 + k] + t.e0 * tex[t.i11 + k];
+    return top * (1.0f - t.e1) + bot * t.e1;
+}
+
+// adjoint of texture_fetch w.r.t. (u, v): accumulates into e_B (DR.h:609-619); the caller applies the clamp masks
+DEODR_HD void texture_fetch_duv(const Tap &t, const float *tex, int k, float a_B, float *e0_B, float *e1_B) {
+    float top = (1.0f - t.e0) * tex[t.i00 + k] + t.e0 * tex[t.i10 + k];
+    float bot = (1.0f - t.e0) * tex[t.i01 + k] + t.e0 * tex[t.i11 + k];
+    *e1_B += a_B * (bot - top);
+    *e0_B += a_B * (1.0f - t.e1) * (tex[t.i10 + k] - tex[t.i00 + k]) + a_B * t.e1 * (tex[t.i11 + k] - tex[t.i01 + k]);
+}
+
+// -------------------------------------------------------------------------------------------- owner-triangle data
+
+// Everything a pixel needs from its owner triangle, gathered once.
+template <int MAXC>
+struct Owner {
+    Bary bary;
+    uint32_t vid[3], uvid[3];
+    bool textured;
+    float w[3];        // interpolation weights (barycentrics; times 1/z_k * Z when perspective_correct)
+    // textured path
+    double u, v;
+    float L;
+    Tap tap;
+    float texval[MAXC];
+};
+
+// Colour of pixel (x, y) inside its owner triangle k.  `Z` is the pixel's z-buffer value (used only by the
+// perspective-correct variant, DR.h:943-955 / 1206-1229).  Fills `o` for the adjoint.
+template <int MAXC>
+DEODR_HD void owner_colour(const SceneView &s, int k, int x, int y, double Z, Owner<MAXC> *o, float *colour) {
+    const int C = s.nb_colors;
+    double V[3][2], Zv[3];
+    gather_tri(s, k, o->vid, V, Zv);
+    remove_offset(V, 3, pixel_offset(s));
+    tri_bary(V, x, y, &o->bary);
+    o->textured = s.textured[k] && s.shaded[k];
+    double wd[3] = {o->bary.b[0], o->bary.b[1], o->bary.b[2]};
+    if (s.perspective_correct)
+        for (int i = 0; i < 3; i++) wd[i] = wd[i] / Zv[i] * Z;
+    for (int i = 0; i < 3; i++) o->w[i] = (float)wd[i];
+    if (o->textured) {
+        o->u = 0; o->v = 0; o->L = 0;
+        for (int i = 0; i < 3; i++) {
+            o->uvid[i] = s.faces_uv[3 * k + i];
+            o->u += wd[i] * s.uv[2 * (size_t)o->uvid[i]];
+            o->v += wd[i] * s.uv[2 * (size_t)o->uvid[i] + 1];
+            o->L += o->w[i] * s.shade[o->vid[i]];
+        }
+        o->tap = texture_tap(o->u, o->v, s.texture_width, s.texture_height, C);
+        for (int c = 0; c < C; c++) {
+            o->texval[c] = texture_fetch(o->tap, s.texture, c);
+            colour[c] = o->texval[c] * o->L;
+        }
+    } else {
+        const float *a0 = s.colors + (size_t)o->vid[0] * C, *a1 = s.colors + (size_t)o->vid[1] * C,
+                    *a2 = s.colors + (size_t)o->vid[2] * C;
+        for (int c = 0; c < C; c++) colour[c] = o->w[0] * a0[c] + o->w[1] * a1[c] + o->w[2] * a2[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ edge records
+
+// Shared-memory record of one silhouette edge of a tile list.
+struct EdgeRec {
+    EdgeGeom g;
+    uint32_t vid[2], uvid[2];
+    int32_t rank;     // position in the far-to-near order (index into the sorted edge array / accumulators)
+    uint8_t textured;
+    double inv_z[2];  // 1/z of the end points (perspective_correct only)
+};
+
+DEODR_HD void edge_record(const SceneView &s, int edge_id, int rank, double sigma, EdgeRec *r) {
+    int k = edge_id / 3, n = edge_id - 3 * k;
+    double V[2][2], Zv[2];
+    for (int i = 0; i < 2; i++) {
+        int loc = edge_vertex(n, i);
+        r->vid[i] = s.faces[3 * k + loc];
+        r->uvid[i] = s.faces_uv[3 * k + loc];
+        V[i][0] = s.ij[2 * (size_t)r->vid[i]];
+        V[i][1] = s.ij[2 * (size_t)r->vid[i] + 1];
+        Zv[i] = s.depths[r->vid[i]];
+        r->inv_z[i] = 1.0 / Zv[i];
+    }
+    remove_offset(V, 2, pixel_offset(s));
+    edge_geom(V, Zv, s.height, sigma, s.clockwise != 0, s.perspective_correct != 0, &r->g, nullptr, nullptr, nullptr);
+    r->rank = rank;
+    r->textured = (uint8_t)(s.textured[k] && s.shaded[k]);
+}
+
+// What one edge contributes at one pixel of its band.
+template <int MAXC>
+struct EdgeHit {
+    double T;        // transparency of the overdraw: image = T*image + (1-T)*A   (DR.h:1634-1641)
+    double b[2];     // edge barycentrics of the pixel
+    float w[2];      // attribute weights (b, or b/z*Z when perspective_correct)
+    float A[MAXC];   // edge colour at the pixel
+    // textured
+    double u, v;
+    float L;
+    Tap tap;
+    float texval[MAXC];
+};
+
+// Z of the edge at the pixel (DR.h:1631 / 1611-1612) - the exact quantity compared with the z-buffer.
+DEODR_HD double edge_z(const EdgeRec &r, int x, int y, bool persp) {
+    double z = plane_at(r.g.zp, plane_row(r.g.zp, y), x);
+    return persp ? DDIV(1.0, z) : z;
+}
+
+template <int MAXC>
+DEODR_HD void edge_hit(const SceneView &s, const EdgeRec &r, int x, int y, double Ze, EdgeHit<MAXC> *h) {
+    const int C = s.nb_colors;
+    const double *q = r.g.ineq;
+    h->b[0] = q[0] * x + q[1] * y + q[2];
+    h->b[1] = q[3] * x + q[4] * y + q[5];
+    h->T = plane_at(q + 6, plane_row(q + 6, y), x);
+    double wd[2] = {h->b[0], h->b[1]};
+    if (s.perspective_correct) { wd[0] = wd[0] * r.inv_z[0] * Ze; wd[1] = wd[1] * r.inv_z[1] * Ze; }
+    h->w[0] = (float)wd[0];
+    h->w[1] = (float)wd[1];
+    if (r.textured) {
+        h->u = wd[0] * s.uv[2 * (size_t)r.uvid[0]] + wd[1] * s.uv[2 * (size_t)r.uvid[1]];
+        h->v = wd[0] * s.uv[2 * (size_t)r.uvid[0] + 1] + wd[1] * s.uv[2 * (size_t)r.uvid[1] + 1];
+        h->L = h->w[0] * s.shade[r.vid[0]] + h->w[1] * s.shade[r.vid[1]];
+        h->tap = texture_tap(h->u, h->v, s.texture_width, s.texture_height, C);
+        for (int c = 0; c < C; c++) {
+            h->texval[c] = texture_fetch(h->tap, s.texture, c);
+            h->A[c] = h->texval[c] * h->L;
+        }
+    } else {
+        const float *a0 = s.colors + (size_t)r.vid[0] * C, *a1 = s.colors + (size_t)r.vid[1] * C;
+        for (int c = 0; c < C; c++) h->A[c] = h->w[0] * a0[c] + h->w[1] * a1[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------ per-edge adjoint finalisation
+
+// Layout of the per-edge fp64 accumulators filled by the backward tile kernel (one row per sorted edge):
+//   [0..2]   transp_B : sum T_B * (x, y, 1)
+//   [3..5]   L_B      : sum L_B * (x, y, 1)                 (textured)
+//   [6..11]  UV_B     : sum UV_B[q] * (x, y, 1), q = 0, 1   (textured)
+//   [12..]   A_B      : sum A_B[c] * (x, y, 1), c < C       (interpolated)
+DEODR_HD int edge_acc_stride(int C) { return 12 + 3 * C; }
+
+// Adjoint of inv3x3 (DR.h:124-232): S_B += d(inv)/dS^T T_B, with Tinv = inv(S):  S_B = -Tinv^T T_B Tinv^T.
+DEODR_HD void inv3x3_adjoint(const double *Tinv, const double *T_B, double *S_B) {
+    double tmp[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double a = 0;
+            for (int k = 0; k < 3; k++) a += Tinv[3 * k + i] * T_B[3 * k + j];
+            tmp[3 * i + j] = a;
+        }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double a = 0;
+            for (int k = 0; k < 3; k++) a += tmp[3 * i + k] * Tinv[3 * j + k];
+            S_B[3 * i + j] -= a;
+        }
+}
+
+}  // namespace deodr

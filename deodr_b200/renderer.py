@@ -1,0 +1,209 @@
+"""Device-resident front-end of the sm_100a rasteriser (thin ctypes layer over ``include/deodr_b200.h``).
+
+``DeviceScene`` holds the canonical device copy of a ``Scene2DBase``-shaped object (fp64 ij / depths / uv, fp32
+colours / shade / texture, u32 faces, u8 flags) as torch CUDA tensors; ``Renderer`` owns a ``DeodrWorkspace`` and
+launches the forward (``renderScene``, DifferentiableRenderer.h:2717) and adjoint (``renderScene_B``,
+DifferentiableRenderer.h:2903) passes on torch's current CUDA stream.  PyTorch is used for device memory and streams
+only; all arithmetic happens in ``libdeodr_b200.so``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _np(a, dtype):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(a), dtype=dtype)
+
+
+class DeviceScene:
+    """Canonical device copy of a 2.5D scene (fields of ``Scene2DBase``, deodr/differentiable_renderer.py:16-45)."""
+
+    _F64 = ("ij", "depths", "uv")
+    _F32 = ("colors", "shade", "texture")
+    _U8 = ("edgeflags", "textured", "shaded")
+
+    def __init__(self, scene, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("deodr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.height, self.width, self.nb_colors = int(scene.height), int(scene.width), int(scene.nb_colors)
+        self.clockwise = bool(scene.clockwise)
+        self.backface_culling = bool(scene.backface_culling)
+        self.strict_edge = bool(scene.strict_edge)
+        self.perspective_correct = bool(scene.perspective_correct)
+        self.integer_pixel_centers = bool(scene.integer_pixel_centers)
+        self.t: Dict[str, torch.Tensor] = {}
+        # uint32 indices are stored as int32 bit patterns (torch has no general uint32 support)
+        self.t["faces"] = self._up(_np(scene.faces, np.uint32).view(np.int32))
+        self.t["faces_uv"] = self._up(_np(scene.faces_uv, np.uint32).view(np.int32))
+        for name in self._F64:
+            self.t[name] = self._up(_np(getattr(scene, name), np.float64))
+        for name in self._F32:
+            self.t[name] = self._up(_np(getattr(scene, name), np.float32))
+        for name in self._U8:
+            self.t[name] = self._up(_np(getattr(scene, name), np.uint8))
+        bg_image = getattr(scene, "background_image", None)
+        bg_color = getattr(scene, "background_color", None)
+        assert (bg_image is not None) != (bg_color is not None), "provide background_image xor background_color"
+        self.t["background_image"] = self._up(_np(bg_image, np.float32)) if bg_image is not None else None
+        self.t["background_color"] = self._up(_np(bg_color, np.float32)) if bg_color is not None else None
+        self._check_shapes()
+
+    def _up(self, a: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(a).to(self.device)
+
+    def _check_shapes(self) -> None:
+        t = self.t
+        T, V, U = t["faces"].shape[0], t["depths"].shape[0], t["uv"].shape[0]
+        assert t["faces"].shape == (T, 3) and t["faces_uv"].shape == (T, 3)
+        assert t["ij"].shape == (V, 2) and t["uv"].shape == (U, 2)
+        assert t["colors"].shape == (V, self.nb_colors) and t["shade"].shape == (V,)
+        assert t["edgeflags"].shape == (T, 3) and t["textured"].shape == (T,) and t["shaded"].shape == (T,)
+        if t["texture"].numel() > 0:
+            assert t["texture"].dim() == 3 and t["texture"].shape[2] == self.nb_colors
+        if t["background_image"] is not None:
+            assert t["background_image"].shape == (self.height, self.width, self.nb_colors)
+        else:
+            assert t["background_color"].shape == (self.nb_colors,)
+
+    def update(self, **arrays) -> None:
+        """Refresh per-iteration inputs (e.g. ``ij=...``, ``colors=...``) in place; tensors or numpy arrays."""
+        for name, value in arrays.items():
+            dst = self.t[name]
+            if isinstance(value, torch.Tensor):
+                dst.copy_(value.to(dst.dtype).reshape(dst.shape), non_blocking=True)
+            else:
+                np_dtype = {torch.float64: np.float64, torch.float32: np.float32, torch.uint8: np.uint8,
+                            torch.int32: np.int32}[dst.dtype]
+                dst.copy_(torch.from_numpy(_np(value, np_dtype)).reshape(dst.shape), non_blocking=True)
+
+    def view(self) -> _cabi.SceneView:
+        t = self.t
+        v = _cabi.SceneView()
+        for name in ("faces", "faces_uv", "ij", "depths", "uv", "colors", "shade", "edgeflags", "textured", "shaded",
+                     "texture"):
+            setattr(v, name, t[name].data_ptr())
+        v.background_image = t["background_image"].data_ptr() if t["background_image"] is not None else None
+        v.background_color = t["background_color"].data_ptr() if t["background_color"] is not None else None
+        v.nb_triangles, v.nb_vertices, v.nb_uv = t["faces"].shape[0], t["depths"].shape[0], t["uv"].shape[0]
+        v.height, v.width, v.nb_colors = self.height, self.width, self.nb_colors
+        if t["texture"].dim() == 3:
+            v.texture_height, v.texture_width = t["texture"].shape[0], t["texture"].shape[1]
+        v.clockwise = int(self.clockwise)
+        v.backface_culling = int(self.backface_culling)
+        v.strict_edge = int(self.strict_edge)
+        v.perspective_correct = int(self.perspective_correct)
+        v.integer_pixel_centers = int(self.integer_pixel_centers)
+        return v
+
+    def zero_grads(self) -> Dict[str, torch.Tensor]:
+        t = self.t
+        return {
+            "ij_b": torch.zeros(t["ij"].shape, dtype=torch.float32, device=self.device),
+            "colors_b": torch.zeros(t["colors"].shape, dtype=torch.float32, device=self.device),
+            "uv_b": torch.zeros(t["uv"].shape, dtype=torch.float32, device=self.device),
+            "shade_b": torch.zeros(t["shade"].shape, dtype=torch.float32, device=self.device),
+            "texture_b": torch.zeros(t["texture"].shape, dtype=torch.float32, device=self.device),
+        }
+
+
+class Renderer:
+    """Owns one ``DeodrWorkspace`` (one per device / stream)."""
+
+    def __init__(self, device: Optional[int] = None):
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("deodr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self._ws = C.c_void_p()
+        _cabi.check(self.lib.deodr_b200_workspace_create(C.byref(self._ws), self.device_index))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ws", None) and self._ws.value:
+                self.lib.deodr_b200_workspace_destroy(self._ws)
+                self._ws = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.deodr_b200_workspace_launches(self._ws))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.deodr_b200_workspace_bytes(self._ws))
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device_index).cuda_stream
+
+    def check_scene(self, scene: DeviceScene) -> None:
+        v = scene.view()
+        _cabi.check(self.lib.deodr_b200_check_scene(self._ws, C.byref(v), self._stream()))
+
+    def render(self, scene: DeviceScene, sigma: float, face_id: bool = False, out: Optional[dict] = None):
+        """Forward pass -> dict(image[H,W,C] f32, z_buffer[H,W] f64, owner[H,W] i32, face_id[H,W] i32 | None)."""
+        dev, H, W, Cc = scene.device, scene.height, scene.width, scene.nb_colors
+        if out is None:
+            out = {
+                "image": torch.empty((H, W, Cc), dtype=torch.float32, device=dev),
+                "z_buffer": torch.empty((H, W), dtype=torch.float64, device=dev),
+                "owner": torch.empty((H, W), dtype=torch.int32, device=dev),
+                "face_id": torch.empty((H, W), dtype=torch.int32, device=dev) if face_id else None,
+            }
+        v = scene.view()
+        fid = out.get("face_id")
+        _cabi.check(self.lib.deodr_b200_render(
+            self._ws, C.byref(v), float(sigma), out["image"].data_ptr(), out["z_buffer"].data_ptr(),
+            out["owner"].data_ptr(), fid.data_ptr() if fid is not None else None, self._stream()))
+        return out
+
+    def render_b(self, scene: DeviceScene, sigma: float, fwd: dict, image_b: torch.Tensor,
+                 grads: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Adjoint pass; accumulates into ``grads`` (created zeroed if None) and returns it."""
+        if grads is None:
+            grads = scene.zero_grads()
+        image_b = image_b.to(device=scene.device, dtype=torch.float32).contiguous()
+        assert image_b.shape == (scene.height, scene.width, scene.nb_colors)
+        v = scene.view()
+        g = _cabi.Grads(*(grads[k].data_ptr() if grads.get(k) is not None and grads[k].numel() > 0 else None
+                          for k in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b")))
+        _cabi.check(self.lib.deodr_b200_render_b(
+            self._ws, C.byref(v), float(sigma), fwd["z_buffer"].data_ptr(), fwd["owner"].data_ptr(),
+            image_b.data_ptr(), C.byref(g), self._stream()))
+        return grads
+
+    # ---- reference-shaped host entry points (fp64 numpy in / out), used by differentiable_renderer_cython.py ----
+    def render_host(self, host_scene: _cabi.HostScene, image: np.ndarray, z_buffer: np.ndarray, sigma: float,
+                    antialiase_error: bool = False, obs=None, err_buffer=None) -> None:
+        _cabi.check(self.lib.deodr_b200_render_host(
+            self._ws, C.byref(host_scene), image.ctypes.data, z_buffer.ctypes.data, float(sigma),
+            int(bool(antialiase_error)), obs.ctypes.data if obs is not None else None,
+            err_buffer.ctypes.data if err_buffer is not None else None))
+
+    def render_b_host(self, host_scene: _cabi.HostScene, image: np.ndarray, z_buffer: np.ndarray,
+                      image_b: Optional[np.ndarray], sigma: float, antialiase_error: bool = False, obs=None,
+                      err_buffer=None, err_buffer_b=None) -> None:
+        ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
+        _cabi.check(self.lib.deodr_b200_render_b_host(
+            self._ws, C.byref(host_scene), image.ctypes.data, z_buffer.ctypes.data, ptr(image_b), float(sigma),
+            int(bool(antialiase_error)), ptr(obs), ptr(err_buffer), ptr(err_buffer_b)))
+
+
+_default: Dict[int, Renderer] = {}
+
+
+def default_renderer(device: Optional[int] = None) -> Renderer:
+    idx = torch.cuda.current_device() if device is None else int(device)
+    if idx not in _default:
+        _default[idx] = Renderer(idx)
+    return _default[idx]

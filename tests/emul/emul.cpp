@@ -1,0 +1,243 @@
+// TEST INFRASTRUCTURE ONLY - CPU emulation of the CUDA kernels of deodr_b200/csrc/kernels.cu.
+//
+// The kernels are written as barrier-separated phases (deodr_b200/csrc/phases.h) that are __host__ __device__.
+// This harness compiles the SAME phase functions with g++ and runs each CTA as `for (tid ...)` loops per phase, with
+// the same control flow as the __global__ wrappers, so that the kernel logic and numerics can be checked against the
+// oracle in a container that has no GPU.  It is never linked into, loaded by or shipped with the product library,
+// and it is not a fallback: deodr_b200 fails loudly without CUDA.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../../deodr_b200/csrc/phases.h"
+#include "../../include/deodr_b200.h"
+
+using namespace deodr;
+
+struct HostEnv {
+    static int atomic_add(int *p, int v) { int old = *p; *p += v; return old; }
+    static void atomic_add(float *p, float v) { *p += v; }
+    static void atomic_add(double *p, double v) { *p += v; }
+    static void emit(float *p, float v) { *p += v; }
+};
+
+struct EmulState {
+    int tiles_x = 0, tiles_y = 0, nt = 0, E = 0;
+    std::vector<int> tri_count, tri_offset, tri_refs, edge_count, edge_offset, edge_refs, edge_sorted;
+    std::vector<int> tie_pairs;
+};
+
+static EmulState g_state;
+
+static void scan_tiles(const std::vector<int> &count, std::vector<int> &offset) {
+    int run = 0;
+    offset.resize(count.size() + 1);
+    for (size_t i = 0; i < count.size(); i++) { offset[i] = run; run += (count[i] + 3) & ~3; }
+    offset[count.size()] = run;
+}
+
+template <int MAXC>
+static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *image, double *z_buffer, int *owner,
+                       int *face_id) {
+    std::vector<PixelState<MAXC>> px(NT);
+    TileShared *sh = new TileShared;
+    for (int tile_id = 0; tile_id < st.nt; tile_id++) {
+        const Tile tile = tile_of(tile_id, st.tiles_x);
+        for (int tid = 0; tid < NT; tid++) { px[tid].z = std::numeric_limits<double>::infinity(); px[tid].own = px[tid].bown = -1; }
+        auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
+        const int n_tri = st.tri_count[tile_id], tri_base = st.tri_offset[tile_id];
+        for (int base = 0; base < n_tri; base += TRI_CHUNK) {
+            const int m = std::min(TRI_CHUNK, n_tri - base);
+            for (int tid = 0; tid < NT; tid++) phase_tri_setup(s, tid, m, st.tri_refs.data() + tri_base + base, sh);
+            for (int tid = 0; tid < NT; tid++) phase_tri_masks(s, tid, m, tile, sh);
+            for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<MAXC>(s, tid, m, tile, sh, &px[tid]);
+        }
+        for (int tid = 0; tid < NT; tid++)
+            if (inside(tid)) phase_shade<MAXC>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, &px[tid]);
+        const int n_edge = st.E > 0 ? st.edge_count[tile_id] : 0;
+        if (n_edge > 0) {
+            const int edge_base = st.edge_offset[tile_id];
+            for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
+                const int m = std::min(EDGE_CHUNK, n_edge - base);
+                for (int tid = 0; tid < NT; tid++)
+                    phase_edge_setup(s, tid, m, st.edge_refs.data() + edge_base + base, st.edge_sorted.data(), sigma, sh);
+                for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
+                for (int tid = 0; tid < NT; tid++)
+                    if (inside(tid))
+                        phase_edge_blend<MAXC>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, tid / TS, m, sh, &px[tid]);
+            }
+        }
+        for (int tid = 0; tid < NT; tid++) {
+            if (!inside(tid)) continue;
+            const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+            const size_t idx = (size_t)y * s.width + x;
+            const PixelState<MAXC> &p = px[tid];
+            z_buffer[idx] = p.z;
+            for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
+            int code = p.bown;
+            if (p.own != p.bown) {
+                int slot = (int)st.tie_pairs.size() / 2;
+                st.tie_pairs.push_back(p.own);
+                st.tie_pairs.push_back(p.bown);
+                code = -2 - slot;
+            }
+            owner[idx] = code;
+            if (face_id) face_id[idx] = p.own;
+        }
+    }
+    delete sh;
+}
+
+template <int MAXC>
+static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const double *z_buffer, const int *owner,
+                       const float *image_b, const DeodrGrads &g, double *edge_acc) {
+    std::vector<PixelState<MAXC>> px(NT);
+    std::vector<AdjointState<MAXC>> adj(NT);
+    TileShared *sh = new TileShared;
+    for (int tile_id = 0; tile_id < st.nt; tile_id++) {
+        const Tile tile = tile_of(tile_id, st.tiles_x);
+        auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
+        for (int tid = 0; tid < NT; tid++) {
+            PixelState<MAXC> &p = px[tid];
+            AdjointState<MAXC> &a = adj[tid];
+            a.has_colour = false;
+            p.z = std::numeric_limits<double>::infinity();
+            p.own = p.bown = -1;
+            if (!inside(tid)) continue;
+            const size_t idx = (size_t)(tile.y0 + tid / TS) * s.width + tile.x0 + tid % TS;
+            p.z = z_buffer[idx];
+            int code = owner[idx];
+            if (code <= -2) { p.own = st.tie_pairs[2 * (-2 - code)]; p.bown = st.tie_pairs[2 * (-2 - code) + 1]; }
+            else p.own = p.bown = code;
+            for (int k = 0; k < s.nb_colors; k++) a.g[k] = image_b[idx * s.nb_colors + k];
+        }
+        const int n_edge = st.E > 0 ? st.edge_count[tile_id] : 0;
+        if (n_edge > 0) {
+            const int edge_base = st.edge_offset[tile_id];
+            const bool single = n_edge <= EDGE_CHUNK;
+            for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
+                const int m = std::min(EDGE_CHUNK, n_edge - base);
+                for (int tid = 0; tid < NT; tid++)
+                    phase_edge_setup(s, tid, m, st.edge_refs.data() + edge_base + base, st.edge_sorted.data(), sigma, sh);
+                for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
+                for (int tid = 0; tid < NT; tid++) {
+                    if (!inside(tid)) continue;
+                    const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+                    phase_edge_replay<MAXC>(s, x, y, tid / TS, m, sh, px[tid], &adj[tid]);
+                    if (single && adj[tid].has_colour)
+                        phase_edge_adjoint<MAXC, HostEnv>(s, x, y, tid / TS, m, sh, px[tid], &adj[tid], edge_acc, g.texture_b);
+                }
+            }
+            if (!single) {
+                const int last = ((n_edge - 1) / EDGE_CHUNK) * EDGE_CHUNK;
+                for (int base = last; base >= 0; base -= EDGE_CHUNK) {
+                    const int m = std::min(EDGE_CHUNK, n_edge - base);
+                    for (int tid = 0; tid < NT; tid++)
+                        phase_edge_setup(s, tid, m, st.edge_refs.data() + edge_base + base, st.edge_sorted.data(), sigma, sh);
+                    for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
+                    for (int tid = 0; tid < NT; tid++) {
+                        if (!inside(tid) || !adj[tid].has_colour) continue;
+                        phase_edge_adjoint<MAXC, HostEnv>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, tid / TS, m, sh,
+                                                          px[tid], &adj[tid], edge_acc, g.texture_b);
+                    }
+                }
+            }
+        }
+        for (int tid = 0; tid < NT; tid++)
+            if (inside(tid) && px[tid].bown >= 0)
+                phase_interior_adjoint<MAXC, HostEnv>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, px[tid], adj[tid].g,
+                                                      g.ij_b, g.colors_b, g.uv_b, g.shade_b, g.texture_b);
+    }
+    delete sh;
+}
+
+extern "C" {
+
+// Same contract as deodr_b200_render, with HOST pointers in the canonical layout.
+int emul_render(const DeodrSceneView *scene, double sigma, float *image, double *z_buffer, int32_t *owner,
+                int32_t *face_id) {
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    EmulState &st = g_state;
+    st = EmulState();
+    const int T = s.nb_triangles;
+    st.tiles_x = (s.width + TS - 1) / TS;
+    st.tiles_y = (s.height + TS - 1) / TS;
+    st.nt = st.tiles_x * st.tiles_y;
+    st.tri_count.assign(st.nt, 0);
+    std::vector<uint8_t> flags((size_t)3 * T + 1, 0);
+    for (int k = 0; k < T; k++)
+        bin_triangle<HostEnv>(s, k, sigma, st.tiles_x, 0, st.tri_count.data(), nullptr, nullptr, nullptr, flags.data());
+    scan_tiles(st.tri_count, st.tri_offset);
+    st.tri_refs.assign(st.tri_offset[st.nt] + 4, -1);
+    std::vector<int> cursor(st.nt, 0);
+    // fill in DESCENDING triangle order: the device fills in an arbitrary order, the result must not depend on it
+    for (int k = T - 1; k >= 0; k--)
+        bin_triangle<HostEnv>(s, k, sigma, st.tiles_x, 1, nullptr, st.tri_offset.data(), cursor.data(), st.tri_refs.data(), nullptr);
+    // silhouette edges: select in index order, stable sort by the depth key
+    std::vector<int> ids;
+    if (sigma > 0)
+        for (int i = 0; i < 3 * T; i++) if (flags[i]) ids.push_back(i);
+    st.E = (int)ids.size();
+    if (st.E > 0) {
+        std::vector<uint64_t> keys(st.E);
+        for (int i = 0; i < st.E; i++) {
+            int k = ids[i] / 3;
+            double d0 = s.depths[s.faces[3 * k]], d1 = s.depths[s.faces[3 * k + 1]], d2 = s.depths[s.faces[3 * k + 2]];
+            keys[i] = depth_desc_key(((0.0 + d0) + d1) + d2);
+        }
+        std::vector<int> perm(st.E);
+        for (int i = 0; i < st.E; i++) perm[i] = i;
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+        st.edge_sorted.resize(st.E);
+        for (int i = 0; i < st.E; i++) st.edge_sorted[i] = ids[perm[i]];
+        st.edge_count.assign(st.nt, 0);
+        for (int r = 0; r < st.E; r++)
+            bin_edge<HostEnv>(s, st.edge_sorted[r], r, sigma, st.tiles_x, 0, st.edge_count.data(), nullptr, nullptr, nullptr);
+        scan_tiles(st.edge_count, st.edge_offset);
+        std::vector<int> tmp(st.edge_offset[st.nt] + 4, -1);
+        std::fill(cursor.begin(), cursor.end(), 0);
+        for (int r = st.E - 1; r >= 0; r--)  // reversed on purpose, see above
+            bin_edge<HostEnv>(s, st.edge_sorted[r], r, sigma, st.tiles_x, 1, nullptr, st.edge_offset.data(), cursor.data(), tmp.data());
+        st.edge_refs.assign(tmp.size(), -1);
+        for (int t = 0; t < st.nt; t++) {  // k_sort_tile_edges
+            const int n = st.edge_count[t], base = st.edge_offset[t];
+            for (int i = 0; i < n; i++) {
+                int mine = tmp[base + i], pos = 0;
+                for (int j = 0; j < n; j++) pos += tmp[base + j] < mine;
+                st.edge_refs[base + pos] = mine;
+            }
+        }
+    }
+    const int C = s.nb_colors;
+    if (C == 1) raster_fwd<1>(s, sigma, st, image, z_buffer, owner, face_id);
+    else if (C <= 3) raster_fwd<3>(s, sigma, st, image, z_buffer, owner, face_id);
+    else if (C <= 4) raster_fwd<4>(s, sigma, st, image, z_buffer, owner, face_id);
+    else raster_fwd<16>(s, sigma, st, image, z_buffer, owner, face_id);
+    return 0;
+}
+
+// Same contract as deodr_b200_render_b (must follow emul_render on the same scene).
+int emul_render_b(const DeodrSceneView *scene, double sigma, const double *z_buffer, const int32_t *owner,
+                  const float *image_b, const DeodrGrads *grads) {
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    EmulState &st = g_state;
+    const int C = s.nb_colors;
+    std::vector<double> acc((size_t)std::max(st.E, 1) * edge_acc_stride(C), 0.0);
+    if (C == 1) raster_bwd<1>(s, sigma, st, z_buffer, owner, image_b, *grads, acc.data());
+    else if (C <= 3) raster_bwd<3>(s, sigma, st, z_buffer, owner, image_b, *grads, acc.data());
+    else if (C <= 4) raster_bwd<4>(s, sigma, st, z_buffer, owner, image_b, *grads, acc.data());
+    else raster_bwd<16>(s, sigma, st, z_buffer, owner, image_b, *grads, acc.data());
+    for (int r = 0; r < st.E; r++)
+        finalize_edge<HostEnv>(s, st.edge_sorted[r], sigma, acc.data() + (size_t)r * edge_acc_stride(C), grads->ij_b,
+                               grads->colors_b, grads->uv_b, grads->shade_b);
+    return 0;
+}
+
+int emul_num_ties(void) { return (int)g_state.tie_pairs.size() / 2; }
+int emul_num_edges(void) { return g_state.E; }
+int emul_tri_refs(void) { return g_state.tri_offset.empty() ? 0 : g_state.tri_offset.back(); }
+}
