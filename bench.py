@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: fwd+bwd Mpixels/s of the differentiable rasteriser (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path on the host cores
+
+Workload (N = 1): BASELINE.json configs[4] - S-mesh(708): 1,002,528-triangle closed torus, 2048x2048, C = 3, Gouraud
+vertex colours, sigma = 1 edge-overdraw antialiasing, dense image_b; one "step" = per-iteration refresh of ij/colours
++ gradient clear + renderScene (forward) + renderScene_B (adjoint) of one view.  N > 1: weak scaling over the
+batch-of-views axis (one view per rank, same mesh, different camera), plus ONE NCCL all-reduce per step of the
+gradient of the shared parameter (vertex colours, colors_b[V,C]); ij_b is per view.
+
+One JSON line on rank 0; keys follow the driver contract, plus `roofline`, `cpu_baseline`, `e2e`, `clocks`.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (torus n, width, height, textured, nb_colors, description)
+    "c5": (708, 2048, 2048, False, 3, "1M-tri synthetic torus mesh (T=1002528), 2048x2048, C=3, sigma=1, fwd+bwd"),
+    "c3": (158, 1024, 1024, True, 3, "50k-tri textured torus mesh (T=49928), 1024x1024, bilinear UV, sigma=1, fwd+bwd"),
+    "c4": (316, 512, 512, False, 3, "200k-tri torus mesh (T=199712), 512x512 RGB view, sigma=1, fwd+bwd"),
+    "dev": (100, 512, 512, False, 3, "development-size torus"),
+}
+METRIC = "fwd+bwd Mpixels/s"
+UNIT = "Mpixels/s"
+SIGMA = 1.0
+
+
+def algorithmic_bytes(scene):
+    """canonical layout, every plane / record touched once per direction."""
+    P, C = scene.height * scene.width, scene.nb_colors
+    T, V, U = scene.faces.shape[0], scene.depths.shape[0], scene.uv.shape[0]
+    b_fwd = P * (4 * C + 8 + 4) + T * (12 + 3 + 2) + V * (16 + 8 + 4 * C)
+    b_bwd = b_fwd + V * (8 + 4 * C)
+    if scene.textured.any():
+        tex = scene.texture.size * 4
+        b_fwd += T * 12 + U * 16 + V * 4 + tex
+        b_bwd += T * 12 + U * 16 + V * 4 + tex + U * 8 + V * 4 + tex
+    return b_fwd, b_bwd
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_scene(workload: str, view: int, n_views: int):
+    from deodr_b200.scenes import torus_scene
+
+    n, W, H, textured, C, _ = WORKLOADS[workload]
+    return torus_scene(n, W, H, view=view, n_views=n_views, textured=textured, nb_colors=C)
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from deodr_b200.renderer import DeviceScene, Renderer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+
+    scene = build_scene(args.workload, view=rank, n_views=max(world, 1))
+    H, W, C = scene.height, scene.width, scene.nb_colors
+    P = H * W
+    renderer = Renderer(local)
+    ds = DeviceScene(scene, dev)
+    ij_dev = ds.t["ij"].clone()
+    colors_dev = ds.t["colors"].clone()
+    image_b = torch.from_numpy(np.random.default_rng(1 + rank).random((H, W, C), dtype=np.float32) * 2 - 1).to(dev)
+    grads = ds.zero_grads()
+    out = None
+
+    def step():
+        nonlocal out
+        ds.update(ij=ij_dev, colors=colors_dev)          # per-iteration refresh of the optimised inputs
+        for g in grads.values():
+            g.zero_()                                     # callers clear scene.*_b before every backward
+        out = renderer.render(ds, SIGMA, out=out)
+        renderer.render_b(ds, SIGMA, out, image_b, grads)
+        if world > 1:
+            dist.all_reduce(grads["colors_b"])            # shared-parameter gradient, one call per step
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    renderer.timing_enable(8 * args.steps + 8)
+    launches0 = renderer.launches
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        step()
+    stop.record()
+    fence()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = renderer.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    phases = renderer.timing_collect()
+    renderer.timing_enable(0)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * P / (ms_per_step * 1e-3) / 1e6
+
+    # ---- per-kernel durations inside the timed region -> roofline of the dominant kernel
+    per_phase = {}
+    for name, ms in phases:
+        per_phase.setdefault(name, []).append(ms)
+    b_fwd, b_bwd = algorithmic_bytes(scene)
+    peak, peak_src = measured_peak_gbs()
+    roofline = None
+    if per_phase.get("raster_fwd") and per_phase.get("raster_bwd"):
+        t_fwd, t_bwd = statistics.mean(per_phase["raster_fwd"]), statistics.mean(per_phase["raster_bwd"])
+        kernel, t_k, b_k = ("raster_bwd", t_bwd, b_bwd) if t_bwd >= t_fwd else ("raster_fwd", t_fwd, b_fwd)
+        achieved = b_k / (t_k * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}).get(kernel)
+        except Exception:
+            pass
+        roofline = {
+            "bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": b_k, "kernel_ms": round(t_k, 4),
+            "phase_ms": {k: round(statistics.mean(v), 4) for k, v in per_phase.items()},
+            "step_algorithmic_bytes": b_fwd + b_bwd,
+            "step_frac_of_peak": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+        }
+
+    # ---- end to end through the reference-facing plugin call with HOST (numpy fp64) buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, scene, world, dev)
+
+    # ---- CPU baseline beside it: rank 0, N = 1 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = time_cpu(scene, threads=1, repeats=1)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 geometry/z + f32 colours/gradients", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {WORKLOADS[args.workload][5]}",
+            "triangles": int(scene.faces.shape[0]), "vertices": int(scene.depths.shape[0]), "height": H, "width": W,
+            "nb_colors": C, "sigma": SIGMA, "views_per_gpu": 1,
+            "parallelism": f"views x{world}" + (" + NCCL all-reduce(colors_b)" if world > 1 else ""),
+            "l2_policy": "inputs larger than L2: each step touches >= %.0f MB (algorithmic) vs 126 MB L2" % ((b_fwd + b_bwd) / 1e6),
+        },
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_e2e(args, scene, world, dev):
+    """Same metric through renderSceneCpp / renderSceneBCpp (deodr_b200.differentiable_renderer_cython): numpy fp64
+    host arrays in, numpy fp64 host arrays out, host<->device copies inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    from deodr_b200 import differentiable_renderer_cython as shim
+    from deodr_b200.differentiable_renderer import Scene2D
+
+    H, W, C = scene.height, scene.width, scene.nb_colors
+    s2 = Scene2D(**{k: getattr(scene, k) for k in (
+        "faces", "faces_uv", "ij", "depths", "textured", "uv", "shade", "colors", "shaded", "edgeflags", "height",
+        "width", "nb_colors", "texture", "background_image", "background_color", "clockwise", "backface_culling",
+        "strict_edge", "perspective_correct", "integer_pixel_centers")})
+    image = np.empty((H, W, C))
+    z = np.empty((H, W))
+    image_b = np.random.default_rng(1).random((H, W, C)) * 2 - 1
+    steps = max(1, min(args.steps, args.e2e_steps))
+
+    def step():
+        s2.clear_gradients()
+        shim.renderSceneCpp(s2, SIGMA, image, z)
+        shim.renderSceneBCpp(s2, SIGMA, image, z, image_b)
+
+    for _ in range(min(args.warmup, 2)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    scene_bytes = sum(np.asarray(getattr(scene, k)).size * (4 if k.startswith("faces") else 1 if k in
+                      ("edgeflags", "textured", "shaded") else 8) for k in
+                      ("faces", "faces_uv", "ij", "depths", "uv", "shade", "colors", "edgeflags", "textured", "shaded",
+                       "texture"))
+    bg = scene.background_image if scene.background_image is not None else scene.background_color
+    scene_bytes += np.asarray(bg).size * 8
+    grads_bytes = 4 * (s2.ij_b.size + s2.colors_b.size + s2.uv_b.size + s2.shade_b.size + s2.texture_b.size)
+    h2d = 2 * scene_bytes + image_b.size * 8                 # scene staged by both calls + image_b
+    d2h = image.size * 8 + z.size * 8 + grads_bytes          # image, z_buffer, gradients
+    return {"value": round(world * H * W / dt / 1e6, 2), "unit": UNIT, "ms_per_step": round(dt * 1e3, 3),
+            "steps": steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "api": "renderSceneCpp + renderSceneBCpp (numpy fp64 host buffers, pageable)"}
+
+
+# ------------------------------------------------------------------------------------------- CPU (reference) arm
+
+
+def time_cpu(scene, threads: int, repeats: int):
+    """fwd+bwd of the SAME scene on the host cores with the reference core (oracle/_ref) or, if it is not built, the
+    C restatement (oracle port).  `threads` independent copies run concurrently (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle.oracle import Oracle, available
+
+    kind = "reference" if available("reference") else "port"
+    oracle = Oracle(kind)
+    H, W, C = scene.height, scene.width, scene.nb_colors
+    image_b = np.random.default_rng(1).random((H, W, C)) * 2 - 1
+
+    def one(_):
+        image, z = oracle.render(scene, SIGMA)
+        oracle.render_b(scene, SIGMA, image, z, image_b)
+
+    times = []
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            list(pool.map(one, range(threads)))
+            times.append(time.perf_counter() - t0)
+    dt = statistics.median(times)
+    return {"value": round(threads * H * W / dt / 1e6, 3), "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{threads} x 1 view fwd+bwd of the same workload, {repeats} repeat(s), {dt:.2f} s each",
+            "seconds_per_step": round(dt, 3), "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return  # the reference has no GPU / multi-process path: rank 0 alone measures the host
+    scene = build_scene(args.workload, view=0, n_views=max(world, 1))
+    threads = max(1, min(os.cpu_count() or 1, args.cpu_threads))
+    for _ in range(min(args.warmup, 1)):
+        time_cpu(scene, threads, 1)
+    res = time_cpu(scene, threads, max(1, min(args.steps, args.ref_steps)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(res["seconds_per_step"] * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][5]}", "threads": threads,
+                   "bounded_sample": res["sample"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=10, help="cap on the e2e (host-buffer) timed steps")
+    ap.add_argument("--ref-steps", type=int, default=5, help="cap on the bounded reference-arm repeats")
+    ap.add_argument("--cpu-threads", type=int, default=64, help="cap on the reference-arm host threads")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    import __graft_entry__ as entry
+
+    if not os.path.exists(entry.LIB):
+        entry.build()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

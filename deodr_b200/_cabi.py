@@ -115,6 +115,9 @@ SYMBOLS = [
      [C.c_void_p, C.POINTER(HostScene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p,
       C.c_void_p, C.c_void_p]),
     ("deodr_b200_check_scene", C.c_int, [C.c_void_p, C.POINTER(SceneView), C.c_void_p]),
+    ("deodr_b200_timing_enable", C.c_int, [C.c_void_p, C.c_int]),
+    ("deodr_b200_timing_collect", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    ("deodr_b200_phase_name", C.c_char_p, [C.c_int]),
     ("deodr_b200_last_error", C.c_char_p, []),
     ("deodr_b200_version", C.c_char_p, []),
 ]

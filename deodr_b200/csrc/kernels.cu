@@ -17,7 +17,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <cmath>
 #include <cstdio>
@@ -310,6 +310,10 @@ struct DeodrWorkspace {
     int device = 0;
     int64_t bytes = 0;
     int64_t launches = 0;
+    // optional per-phase event timing (bench / profiling)
+    std::vector<cudaEvent_t> ev_start, ev_stop;
+    std::vector<int> ev_phase;
+    int ev_used = 0;
     int *host_totals = nullptr;  // pinned: [0] tri refs, [1] selected edges, [2] edge refs, [3] tie counter, [4] flags
     // forward state
     int tiles_x = 0, tiles_y = 0, num_tiles = 0;
@@ -330,6 +334,23 @@ struct DeodrWorkspace {
 };
 
 static int sm_count_cached = 0;
+
+// RAII bracket: records a (start, stop) event pair around a group of launches when timing is enabled
+struct PhaseTimer {
+    DeodrWorkspace *ws;
+    cudaStream_t st;
+    int slot;
+    PhaseTimer(DeodrWorkspace *w, int phase, cudaStream_t s) : ws(w), st(s), slot(-1) {
+        if (ws->ev_used < (int)ws->ev_start.size()) {
+            slot = ws->ev_used++;
+            ws->ev_phase[slot] = phase;
+            cudaEventRecord(ws->ev_start[slot], st);
+        }
+    }
+    ~PhaseTimer() {
+        if (slot >= 0) cudaEventRecord(ws->ev_stop[slot], st);
+    }
+};
 
 static inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
 
@@ -352,17 +373,20 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
 
 static int validate_view(const DeodrSceneView *v, bool backward) {
     if (!v) return set_error(DEODR_B200_EINVAL, "scene == NULL");
-    if (!v->faces) return set_error(DEODR_B200_EINVAL, "scene.faces == NULL");
-    if (!v->faces_uv) return set_error(DEODR_B200_EINVAL, "scene.faces_uv == NULL");
-    if (!v->depths) return set_error(DEODR_B200_EINVAL, "scene.depths == NULL");
-    if (!v->uv) return set_error(DEODR_B200_EINVAL, "scene.uv == NULL");
-    if (!v->ij) return set_error(DEODR_B200_EINVAL, "scene.ij == NULL");
-    if (!v->shade) return set_error(DEODR_B200_EINVAL, "scene.shade == NULL");
-    if (!v->colors) return set_error(DEODR_B200_EINVAL, "scene.colors == NULL");
-    if (!v->edgeflags) return set_error(DEODR_B200_EINVAL, "scene.edgeflags == NULL");
-    if (!v->textured) return set_error(DEODR_B200_EINVAL, "scene.textured == NULL");
-    if (!v->shaded) return set_error(DEODR_B200_EINVAL, "scene.shaded == NULL");
-    if (!v->texture) return set_error(DEODR_B200_EINVAL, "scene.texture == NULL");
+    // zero-sized arrays may legitimately come with a null data pointer
+    const bool tris = v->nb_triangles > 0, verts = v->nb_vertices > 0;
+    if (tris && !v->faces) return set_error(DEODR_B200_EINVAL, "scene.faces == NULL");
+    if (tris && !v->faces_uv) return set_error(DEODR_B200_EINVAL, "scene.faces_uv == NULL");
+    if (verts && !v->depths) return set_error(DEODR_B200_EINVAL, "scene.depths == NULL");
+    if (v->nb_uv > 0 && !v->uv) return set_error(DEODR_B200_EINVAL, "scene.uv == NULL");
+    if (verts && !v->ij) return set_error(DEODR_B200_EINVAL, "scene.ij == NULL");
+    if (verts && !v->shade) return set_error(DEODR_B200_EINVAL, "scene.shade == NULL");
+    if (verts && !v->colors) return set_error(DEODR_B200_EINVAL, "scene.colors == NULL");
+    if (tris && !v->edgeflags) return set_error(DEODR_B200_EINVAL, "scene.edgeflags == NULL");
+    if (tris && !v->textured) return set_error(DEODR_B200_EINVAL, "scene.textured == NULL");
+    if (tris && !v->shaded) return set_error(DEODR_B200_EINVAL, "scene.shaded == NULL");
+    if (v->texture_height > 0 && v->texture_width > 0 && !v->texture)
+        return set_error(DEODR_B200_EINVAL, "scene.texture == NULL");
     if (!v->background_image && !v->background_color)
         return set_error(DEODR_B200_EINVAL, "scene.background == NULL and scene.background_color == NULL");
     if (v->height <= 0 || v->width <= 0 || v->height > 32767 || v->width > 32767)
@@ -386,6 +410,46 @@ extern "C" {
 
 const char *deodr_b200_last_error(void) { return g_error; }
 const char *deodr_b200_version(void) { return "deodr_b200 0.1 (sm_100a)"; }
+
+const char *deodr_b200_phase_name(int phase) {
+    static const char *names[] = {"bin_tri",    "bin_tri_fill", "edge_order",   "edge_bin",
+                                  "raster_fwd", "raster_bwd",   "edge_finalize"};
+    return phase >= 0 && phase < DEODR_B200_PH_COUNT ? names[phase] : "?";
+}
+
+int deodr_b200_timing_enable(DeodrWorkspace *ws, int max_records) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    for (cudaEvent_t e : ws->ev_start) cudaEventDestroy(e);
+    for (cudaEvent_t e : ws->ev_stop) cudaEventDestroy(e);
+    ws->ev_start.clear();
+    ws->ev_stop.clear();
+    ws->ev_phase.clear();
+    ws->ev_used = 0;
+    for (int i = 0; i < max_records; i++) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreate(&a));
+        CUDA_TRY(cudaEventCreate(&b));
+        ws->ev_start.push_back(a);
+        ws->ev_stop.push_back(b);
+        ws->ev_phase.push_back(0);
+    }
+    return DEODR_B200_OK;
+}
+
+int deodr_b200_timing_collect(DeodrWorkspace *ws, int32_t *phase, float *ms, int capacity) {
+    if (!ws || !phase || !ms) return -1;
+    int n = ws->ev_used < capacity ? ws->ev_used : capacity;
+    for (int i = 0; i < n; i++) {
+        if (cudaEventSynchronize(ws->ev_stop[i]) != cudaSuccess) return -1;
+        float t = 0;
+        if (cudaEventElapsedTime(&t, ws->ev_start[i], ws->ev_stop[i]) != cudaSuccess) return -1;
+        phase[i] = ws->ev_phase[i];
+        ms[i] = t;
+    }
+    ws->ev_used = 0;
+    return n;
+}
 
 int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
     if (!out) return set_error(DEODR_B200_EINVAL, "ws == NULL");
@@ -419,6 +483,8 @@ void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     for (DevBuf *b : bufs)
         if (b->ptr) cudaFree(b->ptr);
     if (ws->host_totals) cudaFreeHost(ws->host_totals);
+    for (cudaEvent_t e : ws->ev_start) cudaEventDestroy(e);
+    for (cudaEvent_t e : ws->ev_stop) cudaEventDestroy(e);
     delete ws;
 }
 
@@ -479,6 +545,9 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     }
     if (rc) return DEODR_B200_ECUDA;
     int *scal = ws->scalars.as<int>();
+    const bool with_edges = sigma > 0 && T > 0;
+    {
+    PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI, st);
     CUDA_TRY(cudaMemsetAsync(scal, 0, 8 * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(ws->tri_count.ptr, 0, tile_bytes, st));
     CUDA_TRY(cudaMemsetAsync(ws->tri_cursor.ptr, 0, tile_bytes, st));
@@ -486,7 +555,6 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     CUDA_TRY(cudaMemsetAsync(ws->edge_cursor.ptr, 0, tile_bytes, st));
 
     // ---- triangles: count -> scan ; silhouette edges: select
-    const bool with_edges = sigma > 0 && T > 0;
     if (T > 0) {
         k_bin_tri<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, 0, ws->tri_count.as<int>(), nullptr, nullptr,
                                                     nullptr, ws->edge_flags.as<uint8_t>());
@@ -496,12 +564,13 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     ws->launches++;
     if (with_edges) {
         size_t temp = 0;
-        cub::CountingInputIterator<int> ids(0);
+        thrust::counting_iterator<int> ids(0);
         CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, temp, ids, ws->edge_flags.as<uint8_t>(), ws->edge_ids.as<int>(),
                                             scal + 1, 3 * T, st));
         if (ws->cub_temp.ensure(temp, &ws->bytes)) return DEODR_B200_ECUDA;
         CUDA_TRY(cub::DeviceSelect::Flagged(ws->cub_temp.ptr, temp, ids, ws->edge_flags.as<uint8_t>(),
                                             ws->edge_ids.as<int>(), scal + 1, 3 * T, st));
+    }
     }
     CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -510,6 +579,7 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     ws->num_edges = E;
     if (ws->tri_refs.ensure(((size_t)tri_total + 4) * sizeof(int), &ws->bytes)) return DEODR_B200_ECUDA;
     if (T > 0) {
+        PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI_FILL, st);
         k_bin_tri<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, 1, nullptr, ws->tri_offset.as<int>(),
                                                     ws->tri_cursor.as<int>(), ws->tri_refs.as<int>(), nullptr);
         ws->launches++;
@@ -522,6 +592,8 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
         rc |= ws->edge_keys_out.ensure((size_t)E * 8, &ws->bytes);
         rc |= ws->edge_sorted.ensure((size_t)E * sizeof(int), &ws->bytes);
         if (rc) return DEODR_B200_ECUDA;
+        {
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, st);
         k_edge_keys<<<grid_for(E, 256), 256, 0, st>>>(s, ws->edge_ids.as<int>(), scal + 1,
                                                       ws->edge_keys_in.as<unsigned long long>());
         ws->launches++;
@@ -533,6 +605,8 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp, ws->edge_keys_in.as<unsigned long long>(),
                                                  ws->edge_keys_out.as<unsigned long long>(), ws->edge_ids.as<int>(),
                                                  ws->edge_sorted.as<int>(), E, 0, 64, st));
+        }
+        PhaseTimer timer_bin(ws, DEODR_B200_PH_EDGE_BIN, st);
         k_bin_edge<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma, ws->tiles_x, 0,
                                                      ws->edge_count.as<int>(), nullptr, nullptr, nullptr);
         k_scan_tiles<<<1, 1024, 0, st>>>(ws->edge_count.as<int>(), ws->edge_offset.as<int>(), nt, scal + 2);
@@ -556,11 +630,14 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
     const int *edge_count = E > 0 ? ws->edge_count.as<int>() : nullptr;
     const int C = s.nb_colors;
+    {
+    PhaseTimer timer(ws, DEODR_B200_PH_RASTER_FWD, st);
     if (C == 1) launch_fwd<1>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
     else if (C <= 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
     else if (C <= 4) launch_fwd<4>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
     else launch_fwd<16>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
     ws->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
     ws->sigma = sigma;
     ws->fwd_T = T; ws->fwd_H = s.height; ws->fwd_W = s.width; ws->fwd_C = C;
@@ -590,21 +667,26 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
         return set_error(DEODR_B200_EUNSUPPORTED, "more exact z-buffer ties than the tie table holds");
     const int E = ws->num_edges, C = s.nb_colors;
     DeodrGrads g = *grads;
-    if (!g.ij_b || !g.colors_b || !g.uv_b || !g.shade_b)
+    if ((s.nb_vertices > 0 && (!g.ij_b || !g.colors_b || !g.shade_b)) || (s.nb_uv > 0 && !g.uv_b))
         return set_error(DEODR_B200_EINVAL, "ij_b / colors_b / uv_b / shade_b must be provided");
     if (E > 0) {
         size_t acc_bytes = (size_t)E * edge_acc_stride(C) * sizeof(double);
         if (ws->edge_acc.ensure(acc_bytes, &ws->bytes)) return DEODR_B200_ECUDA;
-        CUDA_TRY(cudaMemsetAsync(ws->edge_acc.ptr, 0, acc_bytes, st));
     }
     TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
     const int *edge_count = E > 0 ? ws->edge_count.as<int>() : nullptr;
+    {
+    PhaseTimer timer(ws, DEODR_B200_PH_RASTER_BWD, st);
+    if (E > 0)
+        CUDA_TRY(cudaMemsetAsync(ws->edge_acc.ptr, 0, (size_t)E * edge_acc_stride(C) * sizeof(double), st));
     if (C == 1) launch_bwd<1>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
     else if (C <= 3) launch_bwd<3>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
     else if (C <= 4) launch_bwd<4>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
     else launch_bwd<16>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
     ws->launches++;
+    }
     if (E > 0) {
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FINALIZE, st);
         k_finalize_edges<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma,
                                                            ws->edge_acc.as<double>(), g);
         ws->launches++;

@@ -143,6 +143,19 @@ class Renderer:
     def workspace_bytes(self) -> int:
         return int(self.lib.deodr_b200_workspace_bytes(self._ws))
 
+    def timing_enable(self, max_records: int) -> None:
+        """Record CUDA-event pairs around the kernel groups of the next render / render_b calls."""
+        _cabi.check(self.lib.deodr_b200_timing_enable(self._ws, int(max_records)))
+
+    def timing_collect(self, capacity: int = 4096):
+        """-> list of (phase name, milliseconds) in launch order; synchronises the recorded events."""
+        phase = (C.c_int32 * capacity)()
+        ms = (C.c_float * capacity)()
+        n = self.lib.deodr_b200_timing_collect(self._ws, phase, ms, capacity)
+        if n < 0:
+            raise RuntimeError("timing_collect failed")
+        return [(self.lib.deodr_b200_phase_name(phase[i]).decode(), float(ms[i])) for i in range(n)]
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device_index).cuda_stream
 

@@ -141,6 +141,25 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
 /* Index-range validation of a device scene (checkSceneValid, DR.h:2703-2714); synchronises the stream. */
 int deodr_b200_check_scene(DeodrWorkspace *ws, const DeodrSceneView *scene, void *stream);
 
+/* Per-kernel device timing with CUDA events recorded on the launching stream (for bench.py's roofline).
+ * enable: pre-creates `max_records` event pairs (0 disables and frees them).  Every instrumented launch group of the
+ * following render / render_b calls then records one (phase, start, stop) triple until the pool is exhausted.
+ * collect: synchronises the recorded events, writes up to `capacity` (phase, milliseconds) pairs in launch order,
+ * resets the pool and returns the number of records written (negative on error). */
+enum {
+    DEODR_B200_PH_BIN_TRI = 0,      /* memsets + bin_tri(count) + scan + silhouette-edge select */
+    DEODR_B200_PH_BIN_TRI_FILL = 1, /* bin_tri(fill) */
+    DEODR_B200_PH_EDGE_ORDER = 2,   /* depth keys + stable radix sort of the silhouette edges */
+    DEODR_B200_PH_EDGE_BIN = 3,     /* bin_edge(count) + scan + bin_edge(fill) + per-tile ordering */
+    DEODR_B200_PH_RASTER_FWD = 4,   /* the forward tile kernel */
+    DEODR_B200_PH_RASTER_BWD = 5,   /* the backward tile kernel (+ accumulator memset) */
+    DEODR_B200_PH_EDGE_FINALIZE = 6,/* per-edge adjoint finalisation */
+    DEODR_B200_PH_COUNT = 7
+};
+int deodr_b200_timing_enable(DeodrWorkspace *ws, int max_records);
+int deodr_b200_timing_collect(DeodrWorkspace *ws, int32_t *phase, float *ms, int capacity);
+const char *deodr_b200_phase_name(int phase);
+
 const char *deodr_b200_last_error(void);
 const char *deodr_b200_version(void);
 
