@@ -28,6 +28,7 @@
 
 #include "../../include/deodr_b200.h"
 #include "phases.h"
+#include "workspace.h"
 
 using namespace deodr;
 
@@ -46,9 +47,10 @@ static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirro
 // ------------------------------------------------------------------------------------------------- kernels
 
 __global__ void k_bin_tri(SceneView s, double sigma, int tiles_x, int mode, int *tile_count, const int *tile_offset,
-                          int *tile_cursor, int *refs, uint8_t *edge_selected) {
+                          int *tile_cursor, int *refs, uint8_t *edge_selected, const int *bad_indices) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.nb_triangles) return;
+    if (bad_indices && *bad_indices) return;  // out-of-range face indices found by k_check_scene: touch nothing
     bin_triangle<DevEnv>(s, k, sigma, tiles_x, mode, tile_count, tile_offset, tile_cursor, refs, edge_selected);
 }
 
@@ -256,82 +258,12 @@ __global__ void k_check_scene(SceneView s, int *bad) {
     if (s.faces_uv[i] >= (uint32_t)s.nb_uv) atomicOr(bad, 2);
 }
 
-__global__ void k_f64_to_f32(const double *in, float *out, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (float)in[i];
-}
-
-__global__ void k_f32_to_f64(const float *in, double *out, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (double)in[i];
-}
-
 // ------------------------------------------------------------------------------------------------- host side
 
-static thread_local char g_error[512] = "";
-
-static int set_error(int code, const char *fmt, const char *detail = "") {
-    snprintf(g_error, sizeof(g_error), fmt, detail);
-    return code;
+char *deodr_error_buffer() {
+    static thread_local char buffer[512] = "";
+    return buffer;
 }
-
-#define CUDA_TRY(expr)                                                                          \
-    do {                                                                                        \
-        cudaError_t err__ = (expr);                                                             \
-        if (err__ != cudaSuccess) {                                                             \
-            snprintf(g_error, sizeof(g_error), "%s failed: %s", #expr, cudaGetErrorString(err__)); \
-            return DEODR_B200_ECUDA;                                                            \
-        }                                                                                       \
-    } while (0)
-
-// growable device buffer
-struct DevBuf {
-    void *ptr = nullptr;
-    size_t bytes = 0;
-    int ensure(size_t need, int64_t *accounted) {
-        if (need <= bytes) return DEODR_B200_OK;
-        if (ptr) {
-            CUDA_TRY(cudaFree(ptr));
-            *accounted -= (int64_t)bytes;
-            ptr = nullptr;
-            bytes = 0;
-        }
-        size_t want = need + need / 4 + 256;
-        CUDA_TRY(cudaMalloc(&ptr, want));
-        bytes = want;
-        *accounted += (int64_t)want;
-        return DEODR_B200_OK;
-    }
-    template <class T>
-    T *as() const { return static_cast<T *>(ptr); }
-};
-
-struct DeodrWorkspace {
-    int device = 0;
-    int64_t bytes = 0;
-    int64_t launches = 0;
-    // optional per-phase event timing (bench / profiling)
-    std::vector<cudaEvent_t> ev_start, ev_stop;
-    std::vector<int> ev_phase;
-    int ev_used = 0;
-    int *host_totals = nullptr;  // pinned: [0] tri refs, [1] selected edges, [2] edge refs, [3] tie counter, [4] flags
-    // forward state
-    int tiles_x = 0, tiles_y = 0, num_tiles = 0;
-    int num_edges = 0;           // silhouette edges of the last forward pass
-    double sigma = -1;
-    int fwd_valid = 0;
-    int fwd_T = 0, fwd_H = 0, fwd_W = 0, fwd_C = 0;
-    DevBuf tri_count, tri_offset, tri_cursor, tri_refs;
-    DevBuf edge_flags, edge_ids, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
-    DevBuf edge_count, edge_offset, edge_cursor, edge_refs_tmp, edge_refs;
-    DevBuf scalars;              // device ints: [0] tri total, [1] num selected, [2] edge total, [3] tie counter, [4] flags
-    DevBuf tie_pairs;
-    int tie_capacity = 0;
-    DevBuf edge_acc;
-    // host-path staging (canonical device copies of a DeodrHostScene)
-    DevBuf h_faces, h_faces_uv, h_ij, h_depths, h_uv, h_colors, h_shade, h_edgeflags, h_textured, h_shaded, h_texture,
-        h_background, h_stage64, h_image, h_z, h_owner, h_image_b, h_grads;
-};
 
 static int sm_count_cached = 0;
 
@@ -408,7 +340,7 @@ static int validate_view(const DeodrSceneView *v, bool backward) {
 
 extern "C" {
 
-const char *deodr_b200_last_error(void) { return g_error; }
+const char *deodr_b200_last_error(void) { return deodr_error_buffer(); }
 const char *deodr_b200_version(void) { return "deodr_b200 0.1 (sm_100a)"; }
 
 const char *deodr_b200_phase_name(int phase) {
@@ -478,10 +410,11 @@ void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
                       &ws->edge_offset, &ws->edge_cursor, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
                       &ws->tie_pairs, &ws->edge_acc, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
                       &ws->h_colors, &ws->h_shade, &ws->h_edgeflags, &ws->h_textured, &ws->h_shaded, &ws->h_texture,
-                      &ws->h_background, &ws->h_stage64, &ws->h_image, &ws->h_z, &ws->h_owner, &ws->h_image_b,
+                      &ws->h_background, &ws->h_image, &ws->h_z, &ws->h_owner, &ws->h_image_b,
                       &ws->h_grads};
     for (DevBuf *b : bufs)
         if (b->ptr) cudaFree(b->ptr);
+    deodr_host_path_destroy(ws);
     if (ws->host_totals) cudaFreeHost(ws->host_totals);
     for (cudaEvent_t e : ws->ev_start) cudaEventDestroy(e);
     for (cudaEvent_t e : ws->ev_stop) cudaEventDestroy(e);
@@ -513,6 +446,13 @@ int deodr_b200_check_scene(DeodrWorkspace *ws, const DeodrSceneView *scene, void
 
 int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, float *image, double *z_buffer,
                       int32_t *owner, int32_t *face_id, void *stream) {
+    return deodr_render_impl(ws, scene, sigma, image, z_buffer, owner, face_id, stream, false);
+}
+
+}  // extern "C"
+
+int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, float *image, double *z_buffer,
+                      int32_t *owner, int32_t *face_id, void *stream, bool check_indices) {
     if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
     if (int rc = validate_view(scene, false)) return rc;
     if (!image) return set_error(DEODR_B200_EINVAL, "image_ptr is NULL");
@@ -556,8 +496,13 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
 
     // ---- triangles: count -> scan ; silhouette edges: select
     if (T > 0) {
+        if (check_indices) {  // checkSceneValid (DR.h:2703-2714) on the device, before anything dereferences an index
+            k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, scal + 4);
+            ws->launches++;
+        }
         k_bin_tri<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, 0, ws->tri_count.as<int>(), nullptr, nullptr,
-                                                    nullptr, ws->edge_flags.as<uint8_t>());
+                                                    nullptr, ws->edge_flags.as<uint8_t>(),
+                                                    check_indices ? scal + 4 : nullptr);
         ws->launches++;
     }
     k_scan_tiles<<<1, 1024, 0, st>>>(ws->tri_count.as<int>(), ws->tri_offset.as<int>(), nt, scal + 0);
@@ -572,8 +517,12 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
                                             ws->edge_ids.as<int>(), scal + 1, 3 * T, st));
     }
     }
-    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (check_indices && (ws->host_totals[4] & 1))
+        return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
+    if (check_indices && (ws->host_totals[4] & 2))
+        return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
     const int tri_total = ws->host_totals[0];
     const int E = with_edges ? ws->host_totals[1] : 0;
     ws->num_edges = E;
@@ -581,7 +530,7 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     if (T > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI_FILL, st);
         k_bin_tri<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, 1, nullptr, ws->tri_offset.as<int>(),
-                                                    ws->tri_cursor.as<int>(), ws->tri_refs.as<int>(), nullptr);
+                                                    ws->tri_cursor.as<int>(), ws->tri_refs.as<int>(), nullptr, nullptr);
         ws->launches++;
     }
 
@@ -645,6 +594,8 @@ int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     return DEODR_B200_OK;
 }
 
+extern "C" {
+
 int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, const double *z_buffer,
                         const int32_t *owner, const float *image_b, const DeodrGrads *grads, void *stream) {
     if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
@@ -692,185 +643,6 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
         ws->launches++;
     }
     CUDA_TRY(cudaGetLastError());
-    return DEODR_B200_OK;
-}
-
-// ------------------------------------------------------------------------------- reference-shaped host entry points
-
-static int upload_f64_as_f32(DeodrWorkspace *ws, DevBuf &dst, const double *src, size_t n, cudaStream_t st) {
-    if (dst.ensure(n * sizeof(float) + 16, &ws->bytes)) return DEODR_B200_ECUDA;
-    if (n == 0) return DEODR_B200_OK;
-    if (ws->h_stage64.ensure(n * sizeof(double), &ws->bytes)) return DEODR_B200_ECUDA;
-    CUDA_TRY(cudaMemcpyAsync(ws->h_stage64.ptr, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_f64_to_f32<<<grid_for(n, 256), 256, 0, st>>>(ws->h_stage64.as<double>(), dst.as<float>(), n);
-    ws->launches++;
-    // the staging buffer is reused by the next upload: order is guaranteed by the stream
-    return DEODR_B200_OK;
-}
-
-static int upload_raw(DeodrWorkspace *ws, DevBuf &dst, const void *src, size_t bytes, cudaStream_t st) {
-    if (dst.ensure(bytes + 16, &ws->bytes)) return DEODR_B200_ECUDA;
-    if (bytes) CUDA_TRY(cudaMemcpyAsync(dst.ptr, src, bytes, cudaMemcpyHostToDevice, st));
-    return DEODR_B200_OK;
-}
-
-static int check_host_scene(const DeodrHostScene *h, bool backward) {
-    if (!h) return set_error(DEODR_B200_EINVAL, "scene == NULL");
-    if (!h->faces) return set_error(DEODR_B200_EINVAL, "scene.faces == NULL");
-    if (!h->faces_uv) return set_error(DEODR_B200_EINVAL, "scene.faces_uv == NULL");
-    if (!h->depths) return set_error(DEODR_B200_EINVAL, "scene.depths == NULL");
-    if (!h->uv) return set_error(DEODR_B200_EINVAL, "scene.uv == NULL");
-    if (!h->ij) return set_error(DEODR_B200_EINVAL, "scene.ij == NULL");
-    if (!h->shade) return set_error(DEODR_B200_EINVAL, "scene.shade == NULL");
-    if (!h->colors) return set_error(DEODR_B200_EINVAL, "scene.colors == NULL");
-    if (!h->edgeflags) return set_error(DEODR_B200_EINVAL, "scene.edgeflags == NULL");
-    if (!h->textured) return set_error(DEODR_B200_EINVAL, "scene.textured == NULL");
-    if (!h->shaded) return set_error(DEODR_B200_EINVAL, "scene.shaded == NULL");
-    if (!h->texture) return set_error(DEODR_B200_EINVAL, "scene.texture == NULL");
-    if (!h->background_image && !h->background_color)
-        return set_error(DEODR_B200_EINVAL, "scene.background == NULL and scene.background_color == NULL");
-    if (backward) {
-        if (!h->uv_b) return set_error(DEODR_B200_EINVAL, "scene.uv_b == NULL");
-        if (!h->ij_b) return set_error(DEODR_B200_EINVAL, "scene.ij_b == NULL");
-        if (!h->shade_b) return set_error(DEODR_B200_EINVAL, "scene.shade_b == NULL");
-        if (!h->colors_b) return set_error(DEODR_B200_EINVAL, "scene.colors_b == NULL");
-        if (!h->texture_b) return set_error(DEODR_B200_EINVAL, "scene.texture_b == NULL");
-    }
-    for (int64_t k = 0; k < (int64_t)h->nb_triangles * 3; k++) {
-        if (h->faces[k] >= (uint32_t)h->nb_vertices)
-            return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
-        if (h->faces_uv[k] >= (uint32_t)h->nb_uv)
-            return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
-    }
-    return DEODR_B200_OK;
-}
-
-// uploads a host scene into the workspace staging buffers and fills the device view
-static int stage_host_scene(DeodrWorkspace *ws, const DeodrHostScene *h, DeodrSceneView *v, cudaStream_t st) {
-    const size_t T = h->nb_triangles, V = h->nb_vertices, U = h->nb_uv, C = h->nb_colors;
-    const size_t P = (size_t)h->height * h->width, tex = (size_t)h->texture_height * h->texture_width * C;
-    int rc = 0;
-    rc |= upload_raw(ws, ws->h_faces, h->faces, T * 3 * sizeof(uint32_t), st);
-    rc |= upload_raw(ws, ws->h_faces_uv, h->faces_uv, T * 3 * sizeof(uint32_t), st);
-    rc |= upload_raw(ws, ws->h_ij, h->ij, V * 2 * sizeof(double), st);
-    rc |= upload_raw(ws, ws->h_depths, h->depths, V * sizeof(double), st);
-    rc |= upload_raw(ws, ws->h_uv, h->uv, U * 2 * sizeof(double), st);
-    rc |= upload_raw(ws, ws->h_edgeflags, h->edgeflags, T * 3, st);
-    rc |= upload_raw(ws, ws->h_textured, h->textured, T, st);
-    rc |= upload_raw(ws, ws->h_shaded, h->shaded, T, st);
-    if (rc) return rc;
-    if ((rc = upload_f64_as_f32(ws, ws->h_colors, h->colors, V * C, st))) return rc;
-    if ((rc = upload_f64_as_f32(ws, ws->h_shade, h->shade, V, st))) return rc;
-    if ((rc = upload_f64_as_f32(ws, ws->h_texture, h->texture, tex, st))) return rc;
-    if (h->background_image) rc = upload_f64_as_f32(ws, ws->h_background, h->background_image, P * C, st);
-    else rc = upload_f64_as_f32(ws, ws->h_background, h->background_color, C, st);
-    if (rc) return rc;
-    memset(v, 0, sizeof(*v));
-    v->faces = ws->h_faces.as<uint32_t>();
-    v->faces_uv = ws->h_faces_uv.as<uint32_t>();
-    v->ij = ws->h_ij.as<double>();
-    v->depths = ws->h_depths.as<double>();
-    v->uv = ws->h_uv.as<double>();
-    v->colors = ws->h_colors.as<float>();
-    v->shade = ws->h_shade.as<float>();
-    v->edgeflags = ws->h_edgeflags.as<uint8_t>();
-    v->textured = ws->h_textured.as<uint8_t>();
-    v->shaded = ws->h_shaded.as<uint8_t>();
-    v->texture = ws->h_texture.as<float>();
-    if (h->background_image) v->background_image = ws->h_background.as<float>();
-    else v->background_color = ws->h_background.as<float>();
-    v->nb_triangles = h->nb_triangles; v->nb_vertices = h->nb_vertices; v->nb_uv = h->nb_uv;
-    v->height = h->height; v->width = h->width; v->nb_colors = h->nb_colors;
-    v->texture_height = h->texture_height; v->texture_width = h->texture_width;
-    v->clockwise = h->clockwise; v->backface_culling = h->backface_culling; v->strict_edge = h->strict_edge;
-    v->perspective_correct = h->perspective_correct; v->integer_pixel_centers = h->integer_pixel_centers;
-    return DEODR_B200_OK;
-}
-
-static int host_forward(DeodrWorkspace *ws, const DeodrHostScene *h, double sigma, DeodrSceneView *v, cudaStream_t st) {
-    if (int rc = stage_host_scene(ws, h, v, st)) return rc;
-    const size_t P = (size_t)h->height * h->width, C = h->nb_colors;
-    int rc = 0;
-    rc |= ws->h_image.ensure(P * C * sizeof(float), &ws->bytes);
-    rc |= ws->h_z.ensure(P * sizeof(double), &ws->bytes);
-    rc |= ws->h_owner.ensure(P * sizeof(int), &ws->bytes);
-    if (rc) return DEODR_B200_ECUDA;
-    return deodr_b200_render(ws, v, sigma, ws->h_image.as<float>(), ws->h_z.as<double>(), ws->h_owner.as<int>(),
-                             nullptr, st);
-}
-
-int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, double *image, double *z_buffer,
-                           double sigma, int antialiase_error, const double *obs, double *err_buffer) {
-    (void)obs; (void)err_buffer;
-    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
-    if (antialiase_error)
-        return set_error(DEODR_B200_EUNSUPPORTED, "antialiase_error mode is not implemented by deodr_b200 yet");
-    if (int rc = check_host_scene(scene, false)) return rc;
-    if (!image) return set_error(DEODR_B200_EINVAL, "image_ptr is NULL");
-    if (!z_buffer) return set_error(DEODR_B200_EINVAL, "z_buffer_ptr is NULL");
-    CUDA_TRY(cudaSetDevice(ws->device));
-    cudaStream_t st = 0;
-    DeodrSceneView v;
-    if (int rc = host_forward(ws, scene, sigma, &v, st)) return rc;
-    const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
-    if (ws->h_stage64.ensure(P * C * sizeof(double), &ws->bytes)) return DEODR_B200_ECUDA;
-    k_f32_to_f64<<<grid_for(P * C, 256), 256, 0, st>>>(ws->h_image.as<float>(), ws->h_stage64.as<double>(), P * C);
-    ws->launches++;
-    CUDA_TRY(cudaMemcpyAsync(image, ws->h_stage64.ptr, P * C * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(z_buffer, ws->h_z.ptr, P * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return DEODR_B200_OK;
-}
-
-int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, double *image, double *z_buffer,
-                             double *image_b, double sigma, int antialiase_error, const double *obs,
-                             double *err_buffer, double *err_buffer_b) {
-    (void)obs; (void)err_buffer; (void)err_buffer_b; (void)image; (void)z_buffer;
-    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
-    if (antialiase_error)
-        return set_error(DEODR_B200_EUNSUPPORTED, "antialiase_error mode is not implemented by deodr_b200 yet");
-    if (int rc = check_host_scene(scene, true)) return rc;
-    if (!scene->backface_culling)
-        return set_error(DEODR_B200_EUNSUPPORTED, "You have to use backface_culling true if you ant to compute gradients");
-    if (scene->perspective_correct)
-        return set_error(DEODR_B200_EUNSUPPORTED,
-                         "backward gradient propagation not supported yet with perspective_correct=True");
-    if (!image_b) return set_error(DEODR_B200_EINVAL, "image_b_ptr is NULL");
-    CUDA_TRY(cudaSetDevice(ws->device));
-    cudaStream_t st = 0;
-    DeodrSceneView v;
-    // The forward state (owner ids, tile edge lists) is rebuilt from the scene: the call is stateless like the
-    // reference's, which also re-derives everything from the scene and the z-buffer.
-    if (int rc = host_forward(ws, scene, sigma, &v, st)) return rc;
-    const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
-    const size_t V = scene->nb_vertices, U = scene->nb_uv;
-    const size_t tex = (size_t)scene->texture_height * scene->texture_width * C;
-    if (int rc = upload_f64_as_f32(ws, ws->h_image_b, image_b, P * C, st)) return rc;
-    const size_t n_ij = 2 * V, n_col = V * C, n_uv = 2 * U, n_sh = V, n_grad = n_ij + n_col + n_uv + n_sh + tex;
-    if (ws->h_grads.ensure(n_grad * sizeof(float), &ws->bytes)) return DEODR_B200_ECUDA;
-    CUDA_TRY(cudaMemsetAsync(ws->h_grads.ptr, 0, n_grad * sizeof(float), st));
-    DeodrGrads g;
-    g.ij_b = ws->h_grads.as<float>();
-    g.colors_b = g.ij_b + n_ij;
-    g.uv_b = g.colors_b + n_col;
-    g.shade_b = g.uv_b + n_uv;
-    g.texture_b = g.shade_b + n_sh;
-    if (int rc = deodr_b200_render_b(ws, &v, sigma, ws->h_z.as<double>(), ws->h_owner.as<int>(),
-                                     ws->h_image_b.as<float>(), &g, st))
-        return rc;
-    std::vector<float> host(n_grad);
-    CUDA_TRY(cudaMemcpyAsync(host.data(), ws->h_grads.ptr, n_grad * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    const float *p = host.data();
-    for (size_t i = 0; i < n_ij; i++) scene->ij_b[i] += (double)p[i];
-    p += n_ij;
-    for (size_t i = 0; i < n_col; i++) scene->colors_b[i] += (double)p[i];
-    p += n_col;
-    for (size_t i = 0; i < n_uv; i++) scene->uv_b[i] += (double)p[i];
-    p += n_uv;
-    for (size_t i = 0; i < n_sh; i++) scene->shade_b[i] += (double)p[i];
-    p += n_sh;
-    for (size_t i = 0; i < tex; i++) scene->texture_b[i] += (double)p[i];
     return DEODR_B200_OK;
 }
 

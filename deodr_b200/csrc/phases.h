@@ -52,24 +52,29 @@ struct TileBox {
     int tx0, tx1, ty0, ty1;  // inclusive; empty if tx0 > tx1
 };
 
-DEODR_HD TileBox tri_tile_box(const TriGeom &g, int width, int height) {
+DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int height) {
     TileBox b;
-    int y0, y1;
-    tri_row_range(g, height, &y0, &y1);
-    int x0 = g.x_min < 0 ? 0 : g.x_min, x1 = g.x_max > width - 1 ? width - 1 : g.x_max;
+    int x0, x1, y0, y1;
+    tri_bounds(V, strict, &x0, &x1, &y0, &y1);
+    if (x0 < 0) x0 = 0;
+    if (x1 > width - 1) x1 = width - 1;
+    if (y0 < 0) y0 = 0;
+    if (y1 > height - 1) y1 = height - 1;
     if (y0 > y1 || x0 > x1) { b.tx0 = 1; b.tx1 = 0; b.ty0 = 1; b.ty1 = 0; return b; }
     b.tx0 = x0 / TS; b.tx1 = x1 / TS; b.ty0 = y0 / TS; b.ty1 = y1 / TS;
     return b;
 }
 
-DEODR_HD TileBox edge_tile_box(const EdgeGeom &g, const double V[2][2], double sigma, int width) {
+DEODR_HD TileBox edge_tile_box(const double V[2][2], double sigma, int width, int height) {
     TileBox b;
+    int y_begin, y_end;
+    edge_row_range(V, height, sigma, &y_begin, &y_end);
     double lo = fmin(V[0][0], V[1][0]) - sigma, hi = fmax(V[0][0], V[1][0]) + sigma;
     int x0 = (int)floor(fmax(lo, -1.0)) - 1, x1 = (int)ceil(fmin(hi, (double)width)) + 1;
     if (x0 < 0) x0 = 0;
     if (x1 > width - 1) x1 = width - 1;
-    if (g.y_begin > g.y_end || x0 > x1) { b.tx0 = 1; b.tx1 = 0; b.ty0 = 1; b.ty1 = 0; return b; }
-    b.tx0 = x0 / TS; b.tx1 = x1 / TS; b.ty0 = g.y_begin / TS; b.ty1 = g.y_end / TS;
+    if (y_begin > y_end || x0 > x1) { b.tx0 = 1; b.tx1 = 0; b.ty0 = 1; b.ty1 = 0; return b; }
+    b.tx0 = x0 / TS; b.tx1 = x1 / TS; b.ty0 = y_begin / TS; b.ty1 = y_end / TS;
     return b;
 }
 
@@ -87,9 +92,7 @@ DEODR_HD void bin_triangle(const SceneView &s, int k, double sigma, int tiles_x,
             edge_selected[3 * k + n] = (uint8_t)(sigma > 0 && c.area_positive && s.edgeflags[3 * k + n]);
     if (!c.drawn) return;
     remove_offset(V, 3, pixel_offset(s));
-    TriGeom g;
-    tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
-    TileBox b = tri_tile_box(g, s.width, s.height);
+    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) {
             int t = ty * tiles_x + tx;
@@ -103,17 +106,14 @@ template <class Env>
 DEODR_HD void bin_edge(const SceneView &s, int edge_id, int rank, double sigma, int tiles_x, int mode, int *tile_count,
                        const int *tile_offset, int *tile_cursor, int *refs) {
     int k = edge_id / 3, n = edge_id - 3 * k;
-    double V[2][2], Zv[2];
+    double V[2][2];
     for (int i = 0; i < 2; i++) {
         uint32_t v = s.faces[3 * k + edge_vertex(n, i)];
         V[i][0] = s.ij[2 * (size_t)v];
         V[i][1] = s.ij[2 * (size_t)v + 1];
-        Zv[i] = s.depths[v];
     }
     remove_offset(V, 2, pixel_offset(s));
-    EdgeGeom g;
-    edge_geom(V, Zv, s.height, sigma, s.clockwise != 0, s.perspective_correct != 0, &g, nullptr, nullptr, nullptr);
-    TileBox b = edge_tile_box(g, V, sigma, s.width);
+    TileBox b = edge_tile_box(V, sigma, s.width, s.height);
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) {
             int t = ty * tiles_x + tx;

@@ -134,6 +134,18 @@ DEODR_HD void order3(const double v[3], double sv[3], int idx[3]) {
     if (sv[1] > sv[2]) { double t = sv[1]; sv[1] = sv[2]; sv[2] = t; int i = idx[1]; idx[1] = idx[2]; idx[2] = i; }
 }
 
+// Integer bounds of DR.h:676-711 alone (what the binning needs): x_min / x_max and the first / last row of the two
+// halves' union.  Identical to the fields tri_geom() derives, without the matrix inverse.
+DEODR_HD void tri_bounds(const double V[3][2], bool strict, int *x_min, int *x_max, int *y_first, int *y_last) {
+    double x_lo = fmin(fmin(V[0][0], V[1][0]), V[2][0]), x_hi = fmax(fmax(V[0][0], V[1][0]), V[2][0]);
+    double y_lo = fmin(fmin(V[0][1], V[1][1]), V[2][1]), y_hi = fmax(fmax(V[0][1], V[1][1]), V[2][1]);
+    *x_min = strict ? to_short(floor(x_lo)) : to_short(ceil(x_lo));
+    *x_max = to_short(floor(x_hi));
+    int yb = strict ? to_short(floor(y_lo)) + 1 : to_short(ceil(y_lo));
+    *y_first = yb > 32767 ? 32767 : yb;
+    *y_last = to_short(floor(y_hi));
+}
+
 // DR.h:633-739 (stencil) + DR.h:787 / 775 (z plane).  V already has the pixel-centre offset removed.
 // Minv (xy1_to_bary) is returned for callers that need the reference's planes; pass nullptr otherwise.
 DEODR_HD void tri_geom(const double V[3][2], const double Zv[3], bool strict, bool persp, TriGeom *g, double *Minv_out) {
@@ -238,6 +250,20 @@ struct EdgeGeom {
     int y_begin, y_end;
 };
 
+// DR.h:1437-1459: rows of the sigma-wide band (note the sequential update of the bound between the two vertices).
+DEODR_HD void edge_row_range(const double V[2][2], int height, double sigma, int *y_begin, int *y_end) {
+    int yb = height - 1;
+    for (int k = 0; k < 2; k++)
+        if (DSUB(V[k][1], sigma) < (double)yb) yb = (int)floor(DSUB(V[k][1], sigma)) + 1;
+    if (yb < 0) yb = 0;
+    int ye = 0;
+    for (int k = 0; k < 2; k++)
+        if (DADD(V[k][1], sigma) > (double)ye) ye = (int)floor(DADD(V[k][1], sigma));
+    if (ye > height - 1) ye = height - 1;
+    *y_begin = yb;
+    *y_end = ye;
+}
+
 // DR.h:1366-1460 + the z plane.  V = the two end points (offset removed), Zv their depths.
 // E / Einv / nt / inv_norm are returned for the adjoint (pass nullptr when not needed).
 DEODR_HD void edge_geom(const double V[2][2], const double Zv[2], int height, double sigma, bool cw, bool persp,
@@ -259,16 +285,7 @@ DEODR_HD void edge_geom(const double V[2][2], const double Zv[2], int height, do
     g->ineq[9] = -g->ineq[6];
     g->ineq[10] = -g->ineq[7];
     g->ineq[11] = DSUB(1.0, g->ineq[8]);
-    int yb = height - 1;
-    for (int k = 0; k < 2; k++)
-        if (DSUB(V[k][1], sigma) < (double)yb) yb = (int)floor(DSUB(V[k][1], sigma)) + 1;
-    if (yb < 0) yb = 0;
-    int ye = 0;
-    for (int k = 0; k < 2; k++)
-        if (DADD(V[k][1], sigma) > (double)ye) ye = (int)floor(DADD(V[k][1], sigma));
-    if (ye > height - 1) ye = height - 1;
-    g->y_begin = yb;
-    g->y_end = ye;
+    edge_row_range(V, height, sigma, &g->y_begin, &g->y_end);
     double zv[2] = {Zv[0], Zv[1]};
     if (persp) { zv[0] = DDIV(1.0, Zv[0]); zv[1] = DDIV(1.0, Zv[1]); }
     // mul_matrix(1,2,3) DR.h:296-309: (0 + z0*Einv[k]) + z1*Einv[3+k]

@@ -1,0 +1,84 @@
+// Host-side state shared by the translation units of libdeodr_b200.so (kernels.cu: device API, host_api.cu: the
+// reference-shaped host entry points).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/deodr_b200.h"
+
+char *deodr_error_buffer();  // thread-local, 512 bytes (defined in kernels.cu)
+
+static inline int set_error(int code, const char *fmt, const char *detail = "") {
+    snprintf(deodr_error_buffer(), 512, fmt, detail);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                \
+    do {                                                                                              \
+        cudaError_t err__ = (expr);                                                                   \
+        if (err__ != cudaSuccess) {                                                                   \
+            snprintf(deodr_error_buffer(), 512, "%s failed: %s", #expr, cudaGetErrorString(err__));   \
+            return DEODR_B200_ECUDA;                                                                  \
+        }                                                                                             \
+    } while (0)
+
+// growable device buffer
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need, int64_t *accounted) {
+        if (need <= bytes) return DEODR_B200_OK;
+        if (ptr) {
+            CUDA_TRY(cudaFree(ptr));
+            *accounted -= (int64_t)bytes;
+            ptr = nullptr;
+            bytes = 0;
+        }
+        size_t want = need + need / 4 + 256;
+        CUDA_TRY(cudaMalloc(&ptr, want));
+        bytes = want;
+        *accounted += (int64_t)want;
+        return DEODR_B200_OK;
+    }
+    template <class T>
+    T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct DeodrWorkspace {
+    int device = 0;
+    int64_t bytes = 0;
+    int64_t launches = 0;
+    // optional per-phase event timing (bench / profiling)
+    std::vector<cudaEvent_t> ev_start, ev_stop;
+    std::vector<int> ev_phase;
+    int ev_used = 0;
+    int *host_totals = nullptr;  // pinned: [0] tri refs, [1] selected edges, [2] edge refs, [3] tie counter, [4] flags
+    // forward state
+    int tiles_x = 0, tiles_y = 0, num_tiles = 0;
+    int num_edges = 0;           // silhouette edges of the last forward pass
+    double sigma = -1;
+    int fwd_valid = 0;
+    int fwd_T = 0, fwd_H = 0, fwd_W = 0, fwd_C = 0;
+    DevBuf tri_count, tri_offset, tri_cursor, tri_refs;
+    DevBuf edge_flags, edge_ids, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
+    DevBuf edge_count, edge_offset, edge_cursor, edge_refs_tmp, edge_refs;
+    DevBuf scalars;              // device ints: [0] tri total, [1] num selected, [2] edge total, [3] tie counter, [4] flags
+    DevBuf tie_pairs;
+    int tie_capacity = 0;
+    DevBuf edge_acc;
+    // host-path staging (canonical device copies of a DeodrHostScene)
+    DevBuf h_faces, h_faces_uv, h_ij, h_depths, h_uv, h_colors, h_shade, h_edgeflags, h_textured, h_shaded, h_texture,
+        h_background, h_image, h_z, h_owner, h_image_b, h_grads;
+    struct HostPath *host = nullptr;  // pinned staging, copy threads, cache of the last host forward (host_api.cu)
+};
+
+
+void deodr_host_path_destroy(DeodrWorkspace *ws);  // host_api.cu
+
+// deodr_b200_render with optional on-device index validation (checkSceneValid, DR.h:2703-2714)
+int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, float *image, double *z_buffer,
+                      int32_t *owner, int32_t *face_id, void *stream, bool check_indices);

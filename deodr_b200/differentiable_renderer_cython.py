@@ -22,8 +22,23 @@ from . import _cabi
 from .renderer import default_renderer
 
 
+def _call(fn, check_valid, *args):
+    """Runs a host entry point; an out-of-range face index surfaces as AssertionError when ``check_valid`` (the pyx
+    asserts, pyx:76-77) and as the library's error otherwise (the C core throws, DR.h:2703-2714)."""
+    try:
+        fn(*args)
+    except _cabi.DeodrB200Error as exc:
+        if check_valid and exc.code == _cabi.EINVAL and "greater than scene.nb_" in exc.message:
+            raise AssertionError(exc.message) from None
+        raise
+
+
 def _flat(a, dtype):
-    return np.ascontiguousarray(np.asarray(a.flatten() if hasattr(a, "flatten") else a).reshape(-1), dtype=dtype)
+    """1-D C-contiguous view of ``a`` with ``dtype``; copies only when the layout / dtype requires it (the pyx always
+    copies through ``flatten()``, pyx:117-131, which is pure overhead on a 1M-triangle scene)."""
+    if hasattr(a, "detach"):  # torch CPU tensor (Scene3DPytorch leaves colors / depths as tensors)
+        a = a.detach().numpy()
+    return np.ascontiguousarray(np.asarray(a), dtype=dtype).reshape(-1)
 
 
 def _marshal(scene, nb_colors, with_grads):
@@ -73,9 +88,8 @@ def _check_common(scene, image, z_buffer):
     nb_triangles = scene.faces.shape[0]
     assert nb_triangles == scene.faces_uv.shape[0]
     nb_vertices = scene.depths.shape[0]
-    nb_vertices_uv = scene.uv.shape[0]
-    assert np.all(np.asarray(scene.faces) < nb_vertices)
-    assert np.all(np.asarray(scene.faces_uv) < nb_vertices_uv)
+    # index ranges (`assert np.all(scene.faces < nb_vertices)`, pyx:76-77) are validated on the device by the call
+    # itself (k_check_scene), see _call below
     assert scene.colors.ndim == 2
     assert scene.uv.ndim == 2
     assert scene.ij.ndim == 2
@@ -129,7 +143,8 @@ def renderSceneCpp(scene, sigma, image, z_buffer, antialiase_error=0, obs=None, 
     if antialiase_error:
         assert err_buffer.shape[0] == image.shape[0] and err_buffer.shape[1] == image.shape[1]
         assert obs.shape == image.shape
-    default_renderer().render_host(h, image, z_buffer, sigma, bool(antialiase_error), obs, err_buffer)
+    _call(default_renderer().render_host, check_valid, h, image, z_buffer, sigma, bool(antialiase_error), obs,
+          err_buffer)
     del keep
 
 
@@ -153,8 +168,8 @@ def renderSceneBCpp(scene, sigma, image, z_buffer, image_b=None, antialiase_erro
             assert image_b.shape[0] == image.shape[0] and image_b.shape[1] == image.shape[1]
     nb_colors = image.shape[2]
     h, keep = _marshal(scene, nb_colors, with_grads=True)
-    default_renderer().render_b_host(h, image, z_buffer, image_b, sigma, bool(antialiase_error), obs, err_buffer,
-                                     err_buffer_b)
+    _call(default_renderer().render_b_host, check_valid, h, image, z_buffer, image_b, sigma, bool(antialiase_error),
+          obs, err_buffer, err_buffer_b)
     # the pyx rebinds the gradient attributes to the arrays the C core accumulated into (pyx:406-410)
     scene.uv_b = keep["uv_b"].reshape(scene.uv_b.shape)
     scene.ij_b = keep["ij_b"].reshape(scene.ij_b.shape)
