@@ -64,55 +64,60 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (every ~2 ms; nvidia-smi's 100 ms
+    loop is too coarse for a region of a few tens of milliseconds).  Falls back to one nvidia-smi query."""
 
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.samples = []
+        self.mask = 0
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
+        self.sm_max = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nvml:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.sm_max,
+                    "samples": len(self.samples), "reasons": reasons, "source": "nvml, 2 ms period, timed region only"}
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+            sm, smax = [float(x) for x in out.strip().split(",")]
+            return {"sm_mhz": sm, "sm_max_mhz": smax, "samples": 1, "reasons": [], "source": "nvidia-smi after the region"}
         except Exception:
-            pass
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            f = [x.strip() for x in row.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock query unavailable"]}
 
 
 def build_scene(workload: str, view: int, n_views: int):
@@ -287,18 +292,20 @@ def run_e2e(args, scene, world, dev):
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    scene_bytes = sum(np.asarray(getattr(scene, k)).size * (4 if k.startswith("faces") else 1 if k in
-                      ("edgeflags", "textured", "shaded") else 8) for k in
-                      ("faces", "faces_uv", "ij", "depths", "uv", "shade", "colors", "edgeflags", "textured", "shaded",
-                       "texture"))
+    # bytes that cross PCIe per step (counted from the arrays the host path copies, host_api.cu): the scene in its
+    # canonical device layout once (the adjoint call finds it unchanged in the pinned mirror), image_b as fp32;
+    # image as fp32, z_buffer as fp64, the five gradient arrays as fp32.
+    canon = {"faces": 4, "faces_uv": 4, "ij": 8, "depths": 8, "uv": 8, "colors": 4, "shade": 4, "edgeflags": 1,
+             "textured": 1, "shaded": 1, "texture": 4}
+    scene_bytes = sum(np.asarray(getattr(scene, k)).size * w for k, w in canon.items())
     bg = scene.background_image if scene.background_image is not None else scene.background_color
-    scene_bytes += np.asarray(bg).size * 8
+    scene_bytes += np.asarray(bg).size * 4
     grads_bytes = 4 * (s2.ij_b.size + s2.colors_b.size + s2.uv_b.size + s2.shade_b.size + s2.texture_b.size)
-    h2d = 2 * scene_bytes + image_b.size * 8                 # scene staged by both calls + image_b
-    d2h = image.size * 8 + z.size * 8 + grads_bytes          # image, z_buffer, gradients
+    h2d = scene_bytes + image_b.size * 4
+    d2h = image.size * 4 + z.size * 8 + grads_bytes
     return {"value": round(world * H * W / dt / 1e6, 2), "unit": UNIT, "ms_per_step": round(dt * 1e3, 3),
             "steps": steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "api": "renderSceneCpp + renderSceneBCpp (numpy fp64 host buffers, pageable)"}
+            "api": "renderSceneCpp + renderSceneBCpp (numpy fp64 host buffers; staged through pinned memory by copy threads)"}
 
 
 # ------------------------------------------------------------------------------------------- CPU (reference) arm

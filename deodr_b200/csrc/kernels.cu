@@ -16,8 +16,6 @@
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
-#include <thrust/iterator/counting_iterator.h>
 
 #include <cmath>
 #include <cstdio>
@@ -38,36 +36,63 @@ struct DevEnv {
     static __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
     static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
     static __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
-    // vertex-gradient scatter; null slots are skipped
-    static __device__ __forceinline__ void emit(float *p, float v) { atomicAdd(p, v); }
 };
+
+// Vertex-gradient scatter of the interior adjoint.  When every participating lane of the warp has the same owner
+// triangle (`uniform`), all lanes target the same addresses: sum over the warp with shuffles and let one lane issue a
+// single atomic (32x fewer same-address atomics for large triangles).  Otherwise one atomic per lane.
+struct WarpEmit {
+    unsigned mask;   // lanes taking part in the interior adjoint (they all execute every emit together)
+    bool uniform;    // same owner triangle on all of them
+    int leader;
+    static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }  // texel adjoints
+    __device__ __forceinline__ void emit(float *p, float v) const {
+        if (uniform) {
+            for (int off = 16; off > 0; off >>= 1) {
+                float o = __shfl_xor_sync(mask, v, off);
+                // lanes outside `mask` do not take part: their slot returns this lane's own value, drop it
+                v += ((mask >> ((threadIdx.x & 31) ^ off)) & 1u) ? o : 0.0f;
+            }
+            if ((int)(threadIdx.x & 31) == leader) atomicAdd(p, v);
+        } else {
+            atomicAdd(p, v);
+        }
+    }
+};
+
+// builds the WarpEmit of the calling warp; must be called by all 32 lanes
+static __device__ __forceinline__ WarpEmit make_warp_emit(bool has, int owner) {
+    WarpEmit e;
+    e.mask = __ballot_sync(0xffffffffu, has);
+    e.leader = e.mask ? __ffs(e.mask) - 1 : 0;
+    const int k0 = __shfl_sync(0xffffffffu, owner, e.leader);
+    e.uniform = __all_sync(0xffffffffu, !has || owner == k0) && __popc(e.mask) > 1;
+    return e;
+}
 
 static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirror DeodrSceneView");
 
 // ------------------------------------------------------------------------------------------------- kernels
 
-__global__ void k_bin_tri(SceneView s, double sigma, int tiles_x, int mode, int *tile_count, const int *tile_offset,
-                          int *tile_cursor, int *refs, uint8_t *edge_selected, const int *bad_indices) {
+// Count pass: one thread per triangle (tile counts, silhouette-edge append, edge tile counts).
+__global__ void k_bin_count(SceneView s, double sigma, int tiles_x, int *tri_tile_count, EdgeList edges,
+                            int *edge_tile_count, const int *bad_indices) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.nb_triangles) return;
     if (bad_indices && *bad_indices) return;  // out-of-range face indices found by k_check_scene: touch nothing
-    bin_triangle<DevEnv>(s, k, sigma, tiles_x, mode, tile_count, tile_offset, tile_cursor, refs, edge_selected);
+    bin_count_triangle<DevEnv>(s, k, sigma, tiles_x, tri_tile_count, edges, edge_tile_count);
 }
 
-__global__ void k_bin_edge(SceneView s, const int *edge_sorted, const int *num_edges, double sigma, int tiles_x,
-                           int mode, int *tile_count, const int *tile_offset, int *tile_cursor, int *refs) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= *num_edges) return;
-    bin_edge<DevEnv>(s, edge_sorted[r], r, sigma, tiles_x, mode, tile_count, tile_offset, tile_cursor, refs);
-}
-
-// Exclusive scan of the tile counts rounded up to a multiple of 4 entries (16-byte aligned list starts).
-// Single CTA of 1024 threads; offsets[n] and *total receive the grand total.
-__global__ void __launch_bounds__(1024) k_scan_tiles(const int *count, int *offset, int n, int *total) {
+// Exclusive scans of the triangle (blockIdx 0) and edge (blockIdx 1) tile counts, each rounded up to a multiple of 4
+// entries (16-byte aligned list starts).  1024 threads per CTA; offsets[n] and totals[blockIdx] get the grand total.
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int *tri_count, int *tri_offset, const int *edge_count,
+                                                     int *edge_offset, int n, int *totals) {
     __shared__ int partial[1024];
+    const int *count = blockIdx.x == 0 ? tri_count : edge_count;
+    int *offset = blockIdx.x == 0 ? tri_offset : edge_offset;
     const int tid = threadIdx.x;
     const int per = (n + 1023) / 1024;
-    const int lo = tid * per, hi = min(n, lo + per);
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
     int sum = 0;
     for (int i = lo; i < hi; i++) sum += (count[i] + 3) & ~3;
     partial[tid] = sum;
@@ -85,16 +110,43 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const int *count, int *offs
     }
     if (tid == 1023) {
         offset[n] = partial[1023];
-        *total = partial[1023];
+        totals[blockIdx.x == 0 ? 0 : 2] = partial[1023];
     }
 }
 
-__global__ void k_edge_keys(SceneView s, const int *edge_ids, const int *num_edges, unsigned long long *keys) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *num_edges) return;
-    int k = edge_ids[i] / 3;
-    double d0 = s.depths[s.faces[3 * k]], d1 = s.depths[s.faces[3 * k + 1]], d2 = s.depths[s.faces[3 * k + 2]];
-    keys[i] = depth_desc_key(DADD(DADD(DADD(0.0, d0), d1), d2));
+// Far-to-near order of the appended silhouette edges by rank counting; keys staged through shared memory.
+__global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *edge_sorted) {
+    __shared__ unsigned long long sk[1024];
+    __shared__ int si[1024];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long key = i < n ? edges.keys[i] : 0ull;
+    const int id = i < n ? edges.ids[i] : 0;
+    int rank = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int m = min(1024, n - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+            sk[j] = edges.keys[base + j];
+            si[j] = edges.ids[base + j];
+        }
+        __syncthreads();
+        for (int j = 0; j < m; j++) rank += (sk[j] < key) || (sk[j] == key && si[j] < id);
+    }
+    if (i < n) edge_sorted[rank] = id;
+}
+
+// Fill pass: blocks [0, tri_blocks) append triangles, the remaining blocks append silhouette edges (by rank).
+__global__ void k_bin_fill(SceneView s, double sigma, int tiles_x, int tri_blocks, const int *tri_offset,
+                           int *tri_cursor, int *tri_refs, const int *edge_sorted, int num_edges,
+                           const int *edge_offset, int *edge_cursor, int *edge_refs) {
+    if ((int)blockIdx.x < tri_blocks) {
+        int k = blockIdx.x * blockDim.x + threadIdx.x;
+        if (k < s.nb_triangles) bin_fill_triangle<DevEnv>(s, k, tiles_x, tri_offset, tri_cursor, tri_refs);
+    } else {
+        int r = (blockIdx.x - tri_blocks) * blockDim.x + threadIdx.x;
+        if (r < num_edges)
+            bin_fill_edge<DevEnv>(s, edge_sorted[r], r, sigma, tiles_x, edge_offset, edge_cursor, edge_refs);
+    }
 }
 
 // Orders every tile's edge list by far-to-near rank (ranks are unique): rank-counting sort, one CTA per tile.
@@ -135,9 +187,7 @@ __global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, in
     const int n_tri = tri_count[tile_id], tri_base = tri_offset[tile_id];
     for (int base = 0; base < n_tri; base += TRI_CHUNK) {
         const int m = min(TRI_CHUNK, n_tri - base);
-        phase_tri_setup(s, tid, m, tri_refs + tri_base + base, &sh);
-        __syncthreads();
-        phase_tri_masks(s, tid, m, tile, &sh);
+        phase_tri_setup(s, tid, m, tri_refs + tri_base + base, tile, &sh);
         __syncthreads();
         if (inside) phase_tri_test<MAXC>(s, tid, m, tile, &sh, &p);
         __syncthreads();
@@ -188,6 +238,9 @@ __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, in
     const bool inside = x < s.width && y < s.height;
     const size_t idx = inside ? (size_t)y * s.width + x : 0;
 
+    const int n_edge = edge_count ? edge_count[tile_id] : 0;
+    if (n_edge == 0) return;  // tiles without silhouette edges are handled by k_interior_bwd
+
     PixelState<MAXC> p;
     AdjointState<MAXC> a;
     a.has_colour = false;
@@ -205,8 +258,7 @@ __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, in
         for (int k = 0; k < s.nb_colors; k++) a.g[k] = image_b[idx * s.nb_colors + k];
     }
 
-    const int n_edge = edge_count ? edge_count[tile_id] : 0;
-    if (n_edge > 0) {
+    {
         const int edge_base = edge_offset[tile_id];
         const bool single = n_edge <= EDGE_CHUNK;
         // pass A: forward replay (far to near) to obtain the final colour in fp64
@@ -238,9 +290,44 @@ __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, in
             }
         }
     }
-    if (inside && p.bown >= 0)
-        phase_interior_adjoint<MAXC, DevEnv>(s, x, y, p, a.g, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
-                                             grads.texture_b);
+    const bool has = inside && p.bown >= 0;
+    const WarpEmit env = make_warp_emit(has, p.bown);
+    if (has)
+        phase_interior_adjoint<MAXC, WarpEmit>(s, x, y, p, a.g, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
+                                               grads.texture_b, env);
+}
+
+// Interior adjoint of the tiles WITHOUT silhouette edges (the vast majority): no shared memory, no z-buffer read,
+// few registers -> high occupancy to hide the dependent gathers owner -> faces -> vertices.
+template <int MAXC>
+__global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, const int *edge_count, TieTable ties,
+                                                     const int *owner, const float *image_b, DeodrGrads grads) {
+    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    if (edge_count && edge_count[tile_id] > 0) return;  // handled by k_raster_bwd
+    const Tile tile = tile_of(tile_id, tiles_x);
+    const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+    const bool inside = x < s.width && y < s.height;
+    PixelState<MAXC> p;
+    p.z = 0.0;  // only read by the perspective-correct forward path
+    p.own = p.bown = -1;
+    float g[MAXC];
+    if (inside) {
+        const size_t idx = (size_t)y * s.width + x;
+        const int code = owner[idx];
+        if (code <= -2) {
+            p.own = ties.pairs[2 * (-2 - code)];
+            p.bown = ties.pairs[2 * (-2 - code) + 1];
+        } else {
+            p.own = p.bown = code;
+        }
+        if (p.bown >= 0)
+            for (int k = 0; k < s.nb_colors; k++) g[k] = image_b[idx * s.nb_colors + k];
+    }
+    const bool has = inside && p.bown >= 0;
+    const WarpEmit env = make_warp_emit(has, p.bown);
+    if (has)
+        phase_interior_adjoint<MAXC, WarpEmit>(s, x, y, p, g, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
+                                               grads.texture_b, env);
 }
 
 __global__ void k_finalize_edges(SceneView s, const int *edge_sorted, const int *num_edges, double sigma,
@@ -289,7 +376,7 @@ static inline int grid_for(size_t n, int block) { return (int)((n + block - 1) /
 template <int MAXC>
 static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
                        float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
-    k_raster_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->tri_count.as<int>(),
+    k_raster_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->tri_count_ptr,
                                                      ws->tri_offset.as<int>(), ws->tri_refs.as<int>(), edge_count,
                                                      ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                      ws->edge_sorted.as<int>(), ties, image, z, owner, face_id);
@@ -298,9 +385,14 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
 template <int MAXC>
 static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
                        const double *z, const int *owner, const float *image_b, const DeodrGrads &g, cudaStream_t st) {
-    k_raster_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
-                                                     ws->edge_refs.as<int>(), ws->edge_sorted.as<int>(), ties, z, owner,
-                                                     image_b, g, ws->edge_acc.as<double>());
+    k_interior_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, edge_count, ties, owner, image_b, g);
+    ws->launches++;
+    if (edge_count) {
+        k_raster_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
+                                                         ws->edge_refs.as<int>(), ws->edge_sorted.as<int>(), ties, z,
+                                                         owner, image_b, g, ws->edge_acc.as<double>());
+        ws->launches++;
+    }
 }
 
 static int validate_view(const DeodrSceneView *v, bool backward) {
@@ -405,9 +497,9 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
 void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    DevBuf *bufs[] = {&ws->tri_count, &ws->tri_offset, &ws->tri_cursor, &ws->tri_refs, &ws->edge_flags, &ws->edge_ids,
-                      &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp, &ws->edge_count,
-                      &ws->edge_offset, &ws->edge_cursor, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
+    DevBuf *bufs[] = {&ws->zeroed, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids, &ws->edge_ids_tmp,
+                      &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
+                      &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
                       &ws->tie_pairs, &ws->edge_acc, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
                       &ws->h_colors, &ws->h_shade, &ws->h_edgeflags, &ws->h_textured, &ws->h_shaded, &ws->h_texture,
                       &ws->h_background, &ws->h_image, &ws->h_z, &ws->h_owner, &ws->h_image_b,
@@ -431,7 +523,7 @@ int deodr_b200_check_scene(DeodrWorkspace *ws, const DeodrSceneView *scene, void
     CUDA_TRY(cudaSetDevice(ws->device));
     SceneView s;
     memcpy(&s, scene, sizeof(s));
-    int *flag = ws->scalars.as<int>() + 4;
+    int *flag = ws->scalars.as<int>() + 4;  // private scratch (not the forward pass's zeroed block)
     CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
     if (s.nb_triangles > 0) {
         k_check_scene<<<grid_for(3 * (size_t)s.nb_triangles, 256), 256, 0, st>>>(s, flag);
@@ -469,53 +561,44 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     ws->tiles_y = (s.height + TS - 1) / TS;
     ws->num_tiles = ws->tiles_x * ws->tiles_y;
     const int nt = ws->num_tiles;
-    const size_t tile_bytes = (size_t)(nt + 1) * sizeof(int);
+    // one zero-initialised block: [scalars(8) | tri_count | tri_cursor | edge_count | edge_cursor], (nt+1) ints each
+    const size_t tile_ints = (size_t)nt + 1;
+    const size_t tile_bytes = tile_ints * sizeof(int);
     int rc = 0;
-    rc |= ws->tri_count.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->zeroed.ensure((8 + 4 * tile_ints) * sizeof(int), &ws->bytes);
     rc |= ws->tri_offset.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->tri_cursor.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->edge_count.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->edge_cursor.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->edge_flags.ensure((size_t)3 * T + 16, &ws->bytes);
     rc |= ws->edge_ids.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->edge_keys_in.ensure(((size_t)3 * T + 4) * 8, &ws->bytes);
     if (ws->tie_capacity == 0) {
         ws->tie_capacity = 1 << 16;
         rc |= ws->tie_pairs.ensure((size_t)2 * ws->tie_capacity * sizeof(int), &ws->bytes);
     }
     if (rc) return DEODR_B200_ECUDA;
-    int *scal = ws->scalars.as<int>();
-    const bool with_edges = sigma > 0 && T > 0;
-    {
-    PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI, st);
-    CUDA_TRY(cudaMemsetAsync(scal, 0, 8 * sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(ws->tri_count.ptr, 0, tile_bytes, st));
-    CUDA_TRY(cudaMemsetAsync(ws->tri_cursor.ptr, 0, tile_bytes, st));
-    CUDA_TRY(cudaMemsetAsync(ws->edge_count.ptr, 0, tile_bytes, st));
-    CUDA_TRY(cudaMemsetAsync(ws->edge_cursor.ptr, 0, tile_bytes, st));
+    int *scal = ws->zeroed.as<int>();
+    int *tri_count = scal + 8, *tri_cursor = tri_count + tile_ints, *edge_count_buf = tri_cursor + tile_ints,
+        *edge_cursor = edge_count_buf + tile_ints;
+    ws->scal = scal;
+    ws->tri_count_ptr = tri_count;
+    ws->edge_count_ptr = edge_count_buf;
+    EdgeList edges{scal + 1, ws->edge_ids.as<int>(), (uint64_t *)ws->edge_keys_in.ptr};
 
-    // ---- triangles: count -> scan ; silhouette edges: select
-    if (T > 0) {
-        if (check_indices) {  // checkSceneValid (DR.h:2703-2714) on the device, before anything dereferences an index
-            k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, scal + 4);
+    // ---- count pass + scans (triangles and silhouette edges together), then the ONE host read-back of the sizes
+    {
+        PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI, st);
+        CUDA_TRY(cudaMemsetAsync(scal, 0, (8 + 4 * tile_ints) * sizeof(int), st));
+        if (T > 0) {
+            if (check_indices) {  // checkSceneValid (DR.h:2703-2714) on the device, before any index is dereferenced
+                k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, scal + 4);
+                ws->launches++;
+            }
+            k_bin_count<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, tri_count, edges, edge_count_buf,
+                                                          check_indices ? scal + 4 : nullptr);
             ws->launches++;
         }
-        k_bin_tri<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, 0, ws->tri_count.as<int>(), nullptr, nullptr,
-                                                    nullptr, ws->edge_flags.as<uint8_t>(),
-                                                    check_indices ? scal + 4 : nullptr);
+        k_scan_tiles<<<2, 1024, 0, st>>>(tri_count, ws->tri_offset.as<int>(), edge_count_buf,
+                                         ws->edge_offset.as<int>(), nt, scal);
         ws->launches++;
-    }
-    k_scan_tiles<<<1, 1024, 0, st>>>(ws->tri_count.as<int>(), ws->tri_offset.as<int>(), nt, scal + 0);
-    ws->launches++;
-    if (with_edges) {
-        size_t temp = 0;
-        thrust::counting_iterator<int> ids(0);
-        CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, temp, ids, ws->edge_flags.as<uint8_t>(), ws->edge_ids.as<int>(),
-                                            scal + 1, 3 * T, st));
-        if (ws->cub_temp.ensure(temp, &ws->bytes)) return DEODR_B200_ECUDA;
-        CUDA_TRY(cub::DeviceSelect::Flagged(ws->cub_temp.ptr, temp, ids, ws->edge_flags.as<uint8_t>(),
-                                            ws->edge_ids.as<int>(), scal + 1, 3 * T, st));
-    }
     }
     CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -523,61 +606,59 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
         return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
     if (check_indices && (ws->host_totals[4] & 2))
         return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
-    const int tri_total = ws->host_totals[0];
-    const int E = with_edges ? ws->host_totals[1] : 0;
+    const int tri_total = ws->host_totals[0], E = ws->host_totals[1], edge_total = ws->host_totals[2];
     ws->num_edges = E;
-    if (ws->tri_refs.ensure(((size_t)tri_total + 4) * sizeof(int), &ws->bytes)) return DEODR_B200_ECUDA;
-    if (T > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI_FILL, st);
-        k_bin_tri<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, 1, nullptr, ws->tri_offset.as<int>(),
-                                                    ws->tri_cursor.as<int>(), ws->tri_refs.as<int>(), nullptr, nullptr);
-        ws->launches++;
+    rc = 0;
+    rc |= ws->tri_refs.ensure(((size_t)tri_total + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->edge_sorted.ensure(((size_t)E + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->edge_refs_tmp.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->edge_refs.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
+    if (rc) return DEODR_B200_ECUDA;
+
+    // ---- far-to-near order of the silhouette edges (DR.h:2781)
+    if (E > 0) {
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, st);
+        if (E <= 65536) {
+            k_rank_edges<<<grid_for(E, 256), 256, 0, st>>>(edges, E, ws->edge_sorted.as<int>());
+            ws->launches++;
+        } else {
+            // large soups: two stable radix sorts (by id, then by depth key) give the same total order
+            rc = 0;
+            rc |= ws->edge_keys_out.ensure((size_t)E * 8, &ws->bytes);
+            rc |= ws->edge_ids_tmp.ensure((size_t)E * sizeof(int), &ws->bytes);
+            if (rc) return DEODR_B200_ECUDA;
+            auto *k_in = ws->edge_keys_in.as<unsigned long long>(), *k_out = ws->edge_keys_out.as<unsigned long long>();
+            int *i_in = ws->edge_ids.as<int>(), *i_tmp = ws->edge_ids_tmp.as<int>();
+            size_t temp1 = 0, temp2 = 0;
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, st));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp2, k_out, k_in, i_tmp, i_in, E, 0, 64, st));
+            if (ws->cub_temp.ensure(temp1 > temp2 ? temp1 : temp2, &ws->bytes)) return DEODR_B200_ECUDA;
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, st));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp2, k_out, k_in, i_tmp,
+                                                     ws->edge_sorted.as<int>(), E, 0, 64, st));
+        }
     }
 
-    // ---- silhouette edges: far-to-near order, tile lists
-    if (E > 0) {
-        rc = 0;
-        rc |= ws->edge_keys_in.ensure((size_t)E * 8, &ws->bytes);
-        rc |= ws->edge_keys_out.ensure((size_t)E * 8, &ws->bytes);
-        rc |= ws->edge_sorted.ensure((size_t)E * sizeof(int), &ws->bytes);
-        if (rc) return DEODR_B200_ECUDA;
-        {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, st);
-        k_edge_keys<<<grid_for(E, 256), 256, 0, st>>>(s, ws->edge_ids.as<int>(), scal + 1,
-                                                      ws->edge_keys_in.as<unsigned long long>());
+    // ---- fill pass (triangles + edges) and per-tile ordering of the edge lists
+    if (T > 0) {
+        PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI_FILL, st);
+        const int tri_blocks = grid_for(T, 128), edge_blocks = E > 0 ? grid_for(E, 128) : 0;
+        k_bin_fill<<<tri_blocks + edge_blocks, 128, 0, st>>>(s, sigma, ws->tiles_x, tri_blocks, ws->tri_offset.as<int>(),
+                                                              tri_cursor, ws->tri_refs.as<int>(),
+                                                              ws->edge_sorted.as<int>(), E, ws->edge_offset.as<int>(),
+                                                              edge_cursor, ws->edge_refs_tmp.as<int>());
         ws->launches++;
-        size_t temp = 0;
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp, ws->edge_keys_in.as<unsigned long long>(),
-                                                 ws->edge_keys_out.as<unsigned long long>(), ws->edge_ids.as<int>(),
-                                                 ws->edge_sorted.as<int>(), E, 0, 64, st));
-        if (ws->cub_temp.ensure(temp, &ws->bytes)) return DEODR_B200_ECUDA;
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp, ws->edge_keys_in.as<unsigned long long>(),
-                                                 ws->edge_keys_out.as<unsigned long long>(), ws->edge_ids.as<int>(),
-                                                 ws->edge_sorted.as<int>(), E, 0, 64, st));
-        }
-        PhaseTimer timer_bin(ws, DEODR_B200_PH_EDGE_BIN, st);
-        k_bin_edge<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma, ws->tiles_x, 0,
-                                                     ws->edge_count.as<int>(), nullptr, nullptr, nullptr);
-        k_scan_tiles<<<1, 1024, 0, st>>>(ws->edge_count.as<int>(), ws->edge_offset.as<int>(), nt, scal + 2);
-        ws->launches += 2;
-        CUDA_TRY(cudaMemcpyAsync(ws->host_totals + 2, scal + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        const int edge_total = ws->host_totals[2];
-        rc = 0;
-        rc |= ws->edge_refs_tmp.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
-        rc |= ws->edge_refs.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
-        if (rc) return DEODR_B200_ECUDA;
-        k_bin_edge<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma, ws->tiles_x, 1,
-                                                     nullptr, ws->edge_offset.as<int>(), ws->edge_cursor.as<int>(),
-                                                     ws->edge_refs_tmp.as<int>());
-        k_sort_tile_edges<<<nt, 128, 0, st>>>(ws->edge_count.as<int>(), ws->edge_offset.as<int>(),
-                                              ws->edge_refs_tmp.as<int>(), ws->edge_refs.as<int>());
-        ws->launches += 2;
+    }
+    if (E > 0) {
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BIN, st);
+        k_sort_tile_edges<<<nt, 128, 0, st>>>(edge_count_buf, ws->edge_offset.as<int>(), ws->edge_refs_tmp.as<int>(),
+                                              ws->edge_refs.as<int>());
+        ws->launches++;
     }
 
     // ---- raster
     TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
-    const int *edge_count = E > 0 ? ws->edge_count.as<int>() : nullptr;
+    const int *edge_count = E > 0 ? edge_count_buf : nullptr;
     const int C = s.nb_colors;
     {
     PhaseTimer timer(ws, DEODR_B200_PH_RASTER_FWD, st);
@@ -611,7 +692,7 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(ws->device));
     // the tie table must not have overflowed in the forward pass
-    int *scal = ws->scalars.as<int>();
+    int *scal = ws->scal;
     CUDA_TRY(cudaMemcpyAsync(ws->host_totals + 3, scal + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (ws->host_totals[3] > ws->tie_capacity)
@@ -625,7 +706,7 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
         if (ws->edge_acc.ensure(acc_bytes, &ws->bytes)) return DEODR_B200_ECUDA;
     }
     TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
-    const int *edge_count = E > 0 ? ws->edge_count.as<int>() : nullptr;
+    const int *edge_count = E > 0 ? ws->edge_count_ptr : nullptr;
     {
     PhaseTimer timer(ws, DEODR_B200_PH_RASTER_BWD, st);
     if (E > 0)
@@ -634,7 +715,6 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
     else if (C <= 3) launch_bwd<3>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
     else if (C <= 4) launch_bwd<4>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
     else launch_bwd<16>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
-    ws->launches++;
     }
     if (E > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FINALIZE, st);

@@ -12,20 +12,27 @@ namespace deodr {
 
 constexpr int TS = 16;            // tile side in pixels
 constexpr int NT = TS * TS;       // threads per tile CTA, one per pixel
-constexpr int TRI_CHUNK = 128;    // triangle records staged in shared memory per pass
+constexpr int TRI_CHUNK = 256;    // triangles staged in shared memory per pass (one per thread)
 constexpr int EDGE_CHUNK = 64;    // edge records staged in shared memory per pass
 
+// What the z test needs from a triangle once its coverage masks exist.
 struct TriRec {
-    TriGeom g;
+    double zp[3];  // z (or 1/z) plane
     int32_t id;
     int32_t pad;
+};
+
+struct alignas(16) Mask4 {
+    uint32_t m[4];
 };
 
 struct TileShared {
     union {
         struct {
             TriRec rec[TRI_CHUNK];
-            uint16_t mask[TRI_CHUNK][TS];  // bit c of mask[t][r]: pixel (col c, row r) of the tile is covered by t
+            // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
+            // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time
+            alignas(16) uint32_t mask[TS / 2][TRI_CHUNK];
         } tri;
         struct {
             EdgeRec rec[EDGE_CHUNK];
@@ -78,47 +85,92 @@ DEODR_HD TileBox edge_tile_box(const double V[2][2], double sigma, int width, in
     return b;
 }
 
-// One thread per triangle.  mode 0 (count): tile_count[tile] += 1 and the effective edge flags are written;
-// mode 1 (fill): the triangle index is appended to the tile's list.
-template <class Env>
-DEODR_HD void bin_triangle(const SceneView &s, int k, double sigma, int tiles_x, int mode, int *tile_count,
-                           const int *tile_offset, int *tile_cursor, int *refs, uint8_t *edge_selected) {
-    uint32_t vid[3];
-    double V[3][2], Zv[3];
-    gather_tri(s, k, vid, V, Zv);
-    TriClass c = classify_tri(s, k, V, Zv);
-    if (mode == 0 && edge_selected)
-        for (int n = 0; n < 3; n++)  // DR.h:2839-2853: overdrawn iff sigma > 0, signedArea > 0 and the flag is set
-            edge_selected[3 * k + n] = (uint8_t)(sigma > 0 && c.area_positive && s.edgeflags[3 * k + n]);
-    if (!c.drawn) return;
-    remove_offset(V, 3, pixel_offset(s));
-    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
-    for (int ty = b.ty0; ty <= b.ty1; ty++)
-        for (int tx = b.tx0; tx <= b.tx1; tx++) {
-            int t = ty * tiles_x + tx;
-            if (mode == 0) Env::atomic_add(&tile_count[t], 1);
-            else refs[tile_offset[t] + Env::atomic_add(&tile_cursor[t], 1)] = k;
-        }
-}
+// Unordered list of the silhouette edges to overdraw (DR.h:2839-2853: sigma > 0, signedArea > 0, flag set), appended
+// by the count pass together with their depth-sum sort keys.
+struct EdgeList {
+    int *count;       // number of appended edges
+    int *ids;         // 3 * triangle + n
+    uint64_t *keys;   // depth_desc_key(sum of the triangle's vertex depths)
+};
 
-// One thread per silhouette edge in far-to-near order (rank r).
-template <class Env>
-DEODR_HD void bin_edge(const SceneView &s, int edge_id, int rank, double sigma, int tiles_x, int mode, int *tile_count,
-                       const int *tile_offset, int *tile_cursor, int *refs) {
+DEODR_HD void gather_edge(const SceneView &s, int edge_id, double V[2][2]) {
     int k = edge_id / 3, n = edge_id - 3 * k;
-    double V[2][2];
     for (int i = 0; i < 2; i++) {
         uint32_t v = s.faces[3 * k + edge_vertex(n, i)];
         V[i][0] = s.ij[2 * (size_t)v];
         V[i][1] = s.ij[2 * (size_t)v + 1];
     }
     remove_offset(V, 2, pixel_offset(s));
+}
+
+// Count pass, one thread per triangle: tile_count[tile] += 1 for every tile of the triangle's bounding box; the
+// triangle's silhouette edges are appended to `edges` and counted into edge_tile_count.
+template <class Env>
+DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int tiles_x, int *tile_count, EdgeList edges,
+                                 int *edge_tile_count) {
+    uint32_t vid[3];
+    double V[3][2], Zv[3];
+    gather_tri(s, k, vid, V, Zv);
+    TriClass c = classify_tri(s, k, V, Zv);
+    if (sigma > 0 && c.area_positive) {
+        for (int n = 0; n < 3; n++) {
+            if (!s.edgeflags[3 * k + n]) continue;
+            int slot = Env::atomic_add(edges.count, 1);
+            edges.ids[slot] = 3 * k + n;
+            edges.keys[slot] = depth_desc_key(c.sum_depth);
+            double E[2][2];
+            gather_edge(s, 3 * k + n, E);
+            TileBox b = edge_tile_box(E, sigma, s.width, s.height);
+            for (int ty = b.ty0; ty <= b.ty1; ty++)
+                for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&edge_tile_count[ty * tiles_x + tx], 1);
+        }
+    }
+    if (!c.drawn) return;
+    remove_offset(V, 3, pixel_offset(s));
+    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
+    for (int ty = b.ty0; ty <= b.ty1; ty++)
+        for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&tile_count[ty * tiles_x + tx], 1);
+}
+
+// Fill pass, one thread per triangle: append the triangle index to the list of every tile of its bounding box.
+template <class Env>
+DEODR_HD void bin_fill_triangle(const SceneView &s, int k, int tiles_x, const int *tile_offset, int *tile_cursor,
+                                int *refs) {
+    uint32_t vid[3];
+    double V[3][2], Zv[3];
+    gather_tri(s, k, vid, V, Zv);
+    TriClass c = classify_tri(s, k, V, Zv);
+    if (!c.drawn) return;
+    remove_offset(V, 3, pixel_offset(s));
+    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
+    for (int ty = b.ty0; ty <= b.ty1; ty++)
+        for (int tx = b.tx0; tx <= b.tx1; tx++) {
+            int t = ty * tiles_x + tx;
+            refs[tile_offset[t] + Env::atomic_add(&tile_cursor[t], 1)] = k;
+        }
+}
+
+// Far-to-near rank of appended edge i = number of edges that precede it in the reference order: descending depth sum
+// (DR.h:2656-2662, 2781), ties by ascending (triangle, edge) id.  O(E) per thread; E is O(sqrt(T)) for meshes.
+DEODR_HD int edge_rank(int i, int n, const uint64_t *keys, const int *ids) {
+    const uint64_t key = keys[i];
+    const int id = ids[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) rank += (keys[j] < key) || (keys[j] == key && ids[j] < id);
+    return rank;
+}
+
+// Fill pass, one thread per silhouette edge in far-to-near order (rank r): append r to the tiles of the edge band.
+template <class Env>
+DEODR_HD void bin_fill_edge(const SceneView &s, int edge_id, int rank, double sigma, int tiles_x, const int *tile_offset,
+                            int *tile_cursor, int *refs) {
+    double V[2][2];
+    gather_edge(s, edge_id, V);
     TileBox b = edge_tile_box(V, sigma, s.width, s.height);
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) {
             int t = ty * tiles_x + tx;
-            if (mode == 0) Env::atomic_add(&tile_count[t], 1);
-            else refs[tile_offset[t] + Env::atomic_add(&tile_cursor[t], 1)] = rank;
+            refs[tile_offset[t] + Env::atomic_add(&tile_cursor[t], 1)] = rank;
         }
 }
 
@@ -132,50 +184,72 @@ struct PixelState {
     float col[MAXC];
 };
 
-// Phase T1: thread tid < n sets up the record of triangle list[tid].
-DEODR_HD void phase_tri_setup(const SceneView &s, int tid, int n, const int *list, TileShared *sh) {
-    if (tid >= n) return;
-    int k = list[tid];
+// 16-bit coverage mask of tile row y for one triangle (exact spans of rmath.h, clipped to the tile).
+DEODR_HD uint32_t tri_row_mask(const SceneView &s, const TriGeom &g, int y, int tile_x0) {
+    int xb, xe;
+    tri_row_span(g, y, s.width, s.height, s.strict_edge != 0, &xb, &xe);
+    xb -= tile_x0;
+    xe -= tile_x0;
+    if (xb < 0) xb = 0;
+    if (xe > TS - 1) xe = TS - 1;
+    return xb <= xe ? (((1u << (xe - xb + 1)) - 1u) << xb) : 0u;
+}
+
+// Phase T1: thread tid < n sets up triangle list[tid] (stencil equations stay in registers) and writes its z plane and
+// its coverage masks of the 16 tile rows; threads up to the next multiple of 4 write empty masks (padding).
+DEODR_HD void phase_tri_setup(const SceneView &s, int tid, int n, const int *list, Tile tile, TileShared *sh) {
+    if (tid >= n) {
+        if (tid < ((n + 3) & ~3))
+            for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = 0u;
+        return;
+    }
+    const int k = list[tid];
     uint32_t vid[3];
     double V[3][2], Zv[3];
     gather_tri(s, k, vid, V, Zv);
     remove_offset(V, 3, pixel_offset(s));
-    tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &sh->tri.rec[tid].g, nullptr);
-    sh->tri.rec[tid].id = k;
-}
-
-// Phase T2: (triangle, row) items -> 16-bit coverage masks of the tile row.
-DEODR_HD void phase_tri_masks(const SceneView &s, int tid, int n, Tile tile, TileShared *sh) {
-    for (int item = tid; item < n * TS; item += NT) {
-        int t = item / TS, r = item % TS;
-        int y = tile.y0 + r;
+    TriGeom g;
+    tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
+    TriRec &rec = sh->tri.rec[tid];
+    rec.zp[0] = g.zp[0]; rec.zp[1] = g.zp[1]; rec.zp[2] = g.zp[2];
+    rec.id = k;
+    int y_first, y_last;
+    tri_row_range(g, s.height, &y_first, &y_last);
+    for (int p = 0; p < TS / 2; p++) {
+        const int y = tile.y0 + 2 * p;
         uint32_t m = 0;
-        if (y < s.height) {
-            int xb, xe;
-            tri_row_span(sh->tri.rec[t].g, y, s.width, s.height, s.strict_edge != 0, &xb, &xe);
-            xb -= tile.x0;
-            xe -= tile.x0;
-            if (xb < 0) xb = 0;
-            if (xe > TS - 1) xe = TS - 1;
-            if (xb <= xe) m = ((1u << (xe - xb + 1)) - 1u) << xb;
+        if (y + 1 >= y_first && y <= y_last) {
+            if (y >= y_first) m = tri_row_mask(s, g, y, tile.x0);
+            if (y + 1 <= y_last) m |= tri_row_mask(s, g, y + 1, tile.x0) << 16;
         }
-        sh->tri.mask[t][r] = (uint16_t)m;
+        sh->tri.mask[p][tid] = m;
     }
 }
 
-// Phase T3: each pixel walks the chunk and keeps the minimum z, order-independently:
+// Phase T2: each pixel walks the chunk and keeps the minimum z, order-independently:
 //   own = min index among ties (what a strict '<' walk in ascending index order leaves, DR.h:961),
 //   bown = max index among ties (what the '==' walk in descending index order finds first, DR.h:1024).
+// Lane l of warp p owns pixel (col l % 16, row 2p + l / 16) = bit l of mask[p][t].
 template <int MAXC>
 DEODR_HD void phase_tri_test(const SceneView &s, int tid, int n, Tile tile, const TileShared *sh, PixelState<MAXC> *p) {
-    int c = tid % TS, r = tid / TS;
-    int x = tile.x0 + c, y = tile.y0 + r;
-    for (int t = 0; t < n; t++) {
-        if (!((sh->tri.mask[t][r] >> c) & 1)) continue;
-        double z = tri_z(sh->tri.rec[t].g, x, y, s.perspective_correct != 0);
-        int id = sh->tri.rec[t].id;
-        if (z < p->z) { p->z = z; p->own = id; p->bown = id; }
-        else if (z == p->z && p->own >= 0) { if (id < p->own) p->own = id; if (id > p->bown) p->bown = id; }
+    const int lane = tid % 32, pair = tid / 32;
+    const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+    const bool persp = s.perspective_correct != 0;
+    for (int t0 = 0; t0 < n; t0 += 4) {
+        const Mask4 m4 = *reinterpret_cast<const Mask4 *>(&sh->tri.mask[pair][t0]);
+        if ((m4.m[0] | m4.m[1] | m4.m[2] | m4.m[3]) == 0u) continue;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; j++) {
+            if (!((m4.m[j] >> lane) & 1u)) continue;
+            const TriRec &rec = sh->tri.rec[t0 + j];
+            double z = plane_at(rec.zp, plane_row(rec.zp, y), x);
+            if (persp) z = DDIV(1.0, z);
+            const int id = rec.id;
+            if (z < p->z) { p->z = z; p->own = id; p->bown = id; }
+            else if (z == p->z && p->own >= 0) { if (id < p->own) p->own = id; if (id > p->bown) p->bown = id; }
+        }
     }
 }
 
@@ -339,9 +413,12 @@ DEODR_HD void phase_edge_adjoint(const SceneView &s, int x, int y, int r, int n,
 // Per pixel, with barycentrics b_v and their gradients (closed form of DR.h:841-858 / 1138-1156):
 //   attr_b[v]  += (d colour / d attr) g * b_v
 //   ij_b[v][d] += - b_v * sum_c g_c * d colour_c / d x_d
+// `env.emit(ptr, v)` adds v to a vertex-gradient slot; the device version sums over the warp first when all its
+// pixels share the same owner triangle (same addresses), see WarpEmit in kernels.cu.
 template <int MAXC, class Env>
 DEODR_HD void phase_interior_adjoint(const SceneView &s, int x, int y, const PixelState<MAXC> &p, const float *g,
-                                     float *ij_b, float *colors_b, float *uv_b, float *shade_b, float *texture_b) {
+                                     float *ij_b, float *colors_b, float *uv_b, float *shade_b, float *texture_b,
+                                     const Env &env) {
     const int C = s.nb_colors;
     const int k = p.bown;
     Owner<MAXC> o;
@@ -370,9 +447,9 @@ DEODR_HD void phase_interior_adjoint(const SceneView &s, int x, int y, const Pix
             float ui = (float)s.uv[2 * (size_t)o.uvid[i]], vi = (float)s.uv[2 * (size_t)o.uvid[i] + 1];
             float li = s.shade[o.vid[i]];
             dudx += gx * ui; dudy += gy * ui; dvdx += gx * vi; dvdy += gy * vi; dLdx += gx * li; dLdy += gy * li;
-            Env::emit(uv_b + 2 * (size_t)o.uvid[i], U_B * o.w[i]);
-            Env::emit(uv_b + 2 * (size_t)o.uvid[i] + 1, V_B * o.w[i]);
-            Env::emit(shade_b + o.vid[i], L_B * o.w[i]);
+            env.emit(uv_b + 2 * (size_t)o.uvid[i], U_B * o.w[i]);
+            env.emit(uv_b + 2 * (size_t)o.uvid[i] + 1, V_B * o.w[i]);
+            env.emit(shade_b + o.vid[i], L_B * o.w[i]);
         }
         dcdx = U_B * dudx + V_B * dvdx + L_B * dLdx;
         dcdy = U_B * dudy + V_B * dvdy + L_B * dLdy;
@@ -384,12 +461,12 @@ DEODR_HD void phase_interior_adjoint(const SceneView &s, int x, int y, const Pix
         for (int c = 0; c < C; c++) {
             dcdx += g[c] * (gx0 * a0[c] + gx1 * a1[c] + gx2 * a2[c]);
             dcdy += g[c] * (gy0 * a0[c] + gy1 * a1[c] + gy2 * a2[c]);
-            for (int i = 0; i < 3; i++) Env::emit(colors_b + (size_t)o.vid[i] * C + c, g[c] * o.w[i]);
+            for (int i = 0; i < 3; i++) env.emit(colors_b + (size_t)o.vid[i] * C + c, g[c] * o.w[i]);
         }
     }
     for (int i = 0; i < 3; i++) {
-        Env::emit(ij_b + 2 * (size_t)o.vid[i], -o.w[i] * dcdx);
-        Env::emit(ij_b + 2 * (size_t)o.vid[i] + 1, -o.w[i] * dcdy);
+        env.emit(ij_b + 2 * (size_t)o.vid[i], -o.w[i] * dcdx);
+        env.emit(ij_b + 2 * (size_t)o.vid[i] + 1, -o.w[i] * dcdy);
     }
 }
 

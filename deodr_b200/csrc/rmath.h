@@ -79,8 +79,74 @@ DEODR_HD int monotone_search(double a, double b, int x_min, int x_max, int mode)
     return lo;
 }
 
+// ---- floor(RN(a / b)) without the fp64 division in the common case ------------------------------------------
+// The reference computes (short)floor(a / b) with an IEEE division (DR.h:449).  An fp64 division costs ~40 issue slots
+// on the GPU and two of them are needed per (triangle, row); the quotient is only used through its floor.  We get a
+// candidate from an fp32 division (|error| < 0.01 in the admitted range |a/b| < 32768) and settle it with the exact
+// predicate G(x) = [RN(a/b) >= x], x integer:
+//   * RN is monotone and x is representable, so a/b >= x  ==>  RN(a/b) >= x;
+//   * a/b >= x is decided EXACTLY by the sign of g = fma(-x, b, a) (a correctly rounded value has the sign of the
+//     exact one);
+//   * if a/b < x, RN(a/b) can still round up to x only when x - a/b <= ulp(x)/2, i.e. |g| <= 2^-53 |x b|; inside a
+//     4x wider band (and for non-finite / tiny operands) we fall back to the real division.
+// Result: bit-identical to the reference for every input (tests/test_rmath.py drives both on adversarial inputs).
+DEODR_HD int floor_quotient_exact(double a, double b) { return to_short(floor(DDIV(a, b))); }
+
+#if defined(__CUDA_ARCH__)
+#define DEODR_FMA(x, y, z) __fma_rn((x), (y), (z))
+#else
+#define DEODR_FMA(x, y, z) fma((x), (y), (z))
+#endif
+
+// 1: RN(a/b) >= x, 0: RN(a/b) < x, -1: too close to call
+DEODR_HD int quotient_ge(double a, double b, int x) {
+    const double xd = (double)x;
+    const double g = DEODR_FMA(-xd, b, a);  // a - x*b, one rounding
+    const bool real_ge = b > 0 ? (g >= 0) : (g <= 0);
+    if (real_ge) return 1;
+    return fabs(g) > 4.5e-16 * fabs(xd * b) ? 0 : -1;
+}
+
+DEODR_HD int floor_quotient(double a, double b) {
+    const float af = (float)a, bf = (float)b;
+    const float qf = af / bf;
+    // operands must be comfortably inside the normal fp32 range for the 0.01 error bound to hold
+    if (!(fabsf(qf) < 33000.0f) || !(fabsf(bf) > 1e-30f) || !(fabsf(af) > 1e-30f || a == 0.0) ||
+        !(fabsf(af) < 1e30f) || !(fabsf(bf) < 1e30f))
+        return floor_quotient_exact(a, b);
+    const int c = (int)floorf(qf);
+    const int up = quotient_ge(a, b, c + 1);
+    if (up < 0) return floor_quotient_exact(a, b);
+    if (up) return to_short((double)(c + 1));
+    const int at = quotient_ge(a, b, c);
+    if (at < 0) return floor_quotient_exact(a, b);
+    return to_short((double)(at ? c : c - 1));
+}
+
 // DR.h:440-479: min(x_max, max(x_min, floor(a/b))) with the robust fall-back.  Result passes through `short`.
 DEODR_HD int floor_div_clamped(double a, double b, int x_min, int x_max) {
+    if (DMUL(fabs(b), 32767.0) > DADD(fabs(a), fabs(b))) {
+        int x = floor_quotient(a, b);
+        if (x < x_min) x = to_short((double)x_min);
+        if (x > x_max) x = to_short((double)x_max);
+        return x;
+    }
+    return monotone_search(a, b, x_min, x_max, b > 0 ? 0 : 1);
+}
+
+// DR.h:481-519.  ceil(RN(q)) = -floor(RN(-q)) (rounding to nearest is symmetric).
+DEODR_HD int ceil_div_clamped(double a, double b, int x_min, int x_max) {
+    if (DMUL(fabs(b), 32767.0) > DADD(fabs(a), fabs(b))) {
+        int x = to_short((double)(-floor_quotient(-a, b)));
+        if (x < x_min) x = to_short((double)x_min);
+        if (x > x_max) x = to_short((double)x_max);
+        return x;
+    }
+    return monotone_search(a, b, x_min, x_max, b > 0 ? 2 : 3);
+}
+
+// the reference formulation with the real division, kept for the equivalence tests
+DEODR_HD int floor_div_clamped_reference(double a, double b, int x_min, int x_max) {
     if (DMUL(fabs(b), 32767.0) > DADD(fabs(a), fabs(b))) {
         int x = to_short(floor(DDIV(a, b)));
         if (x < x_min) x = to_short((double)x_min);
@@ -89,9 +155,7 @@ DEODR_HD int floor_div_clamped(double a, double b, int x_min, int x_max) {
     }
     return monotone_search(a, b, x_min, x_max, b > 0 ? 0 : 1);
 }
-
-// DR.h:481-519
-DEODR_HD int ceil_div_clamped(double a, double b, int x_min, int x_max) {
+DEODR_HD int ceil_div_clamped_reference(double a, double b, int x_min, int x_max) {
     if (DMUL(fabs(b), 32767.0) > DADD(fabs(a), fabs(b))) {
         int x = to_short(ceil(DDIV(a, b)));
         if (x < x_min) x = to_short((double)x_min);

@@ -63,9 +63,11 @@ struct DeodrWorkspace {
     double sigma = -1;
     int fwd_valid = 0;
     int fwd_T = 0, fwd_H = 0, fwd_W = 0, fwd_C = 0;
-    DevBuf tri_count, tri_offset, tri_cursor, tri_refs;
-    DevBuf edge_flags, edge_ids, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
-    DevBuf edge_count, edge_offset, edge_cursor, edge_refs_tmp, edge_refs;
+    DevBuf zeroed;               // [scalars(8) | tri_count | tri_cursor | edge_count | edge_cursor], memset per forward
+    int *scal = nullptr, *tri_count_ptr = nullptr, *edge_count_ptr = nullptr;  // views into `zeroed`
+    DevBuf tri_offset, tri_refs;
+    DevBuf edge_ids, edge_ids_tmp, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
+    DevBuf edge_offset, edge_refs_tmp, edge_refs;
     DevBuf scalars;              // device ints: [0] tri total, [1] num selected, [2] edge total, [3] tie counter, [4] flags
     DevBuf tie_pairs;
     int tie_capacity = 0;

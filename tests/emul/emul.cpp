@@ -20,7 +20,7 @@ struct HostEnv {
     static int atomic_add(int *p, int v) { int old = *p; *p += v; return old; }
     static void atomic_add(float *p, float v) { *p += v; }
     static void atomic_add(double *p, double v) { *p += v; }
-    static void emit(float *p, float v) { *p += v; }
+    void emit(float *p, float v) const { *p += v; }
 };
 
 struct EmulState {
@@ -50,8 +50,7 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
         const int n_tri = st.tri_count[tile_id], tri_base = st.tri_offset[tile_id];
         for (int base = 0; base < n_tri; base += TRI_CHUNK) {
             const int m = std::min(TRI_CHUNK, n_tri - base);
-            for (int tid = 0; tid < NT; tid++) phase_tri_setup(s, tid, m, st.tri_refs.data() + tri_base + base, sh);
-            for (int tid = 0; tid < NT; tid++) phase_tri_masks(s, tid, m, tile, sh);
+            for (int tid = 0; tid < NT; tid++) phase_tri_setup(s, tid, m, st.tri_refs.data() + tri_base + base, tile, sh);
             for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<MAXC>(s, tid, m, tile, sh, &px[tid]);
         }
         for (int tid = 0; tid < NT; tid++)
@@ -148,7 +147,7 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
         for (int tid = 0; tid < NT; tid++)
             if (inside(tid) && px[tid].bown >= 0)
                 phase_interior_adjoint<MAXC, HostEnv>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, px[tid], adj[tid].g,
-                                                      g.ij_b, g.colors_b, g.uv_b, g.shade_b, g.texture_b);
+                                                      g.ij_b, g.colors_b, g.uv_b, g.shade_b, g.texture_b, HostEnv());
     }
     delete sh;
 }
@@ -167,40 +166,30 @@ int emul_render(const DeodrSceneView *scene, double sigma, float *image, double 
     st.tiles_y = (s.height + TS - 1) / TS;
     st.nt = st.tiles_x * st.tiles_y;
     st.tri_count.assign(st.nt, 0);
-    std::vector<uint8_t> flags((size_t)3 * T + 1, 0);
-    for (int k = 0; k < T; k++)
-        bin_triangle<HostEnv>(s, k, sigma, st.tiles_x, 0, st.tri_count.data(), nullptr, nullptr, nullptr, flags.data());
+    st.edge_count.assign(st.nt, 0);
+    int num_edges = 0;
+    std::vector<int> ids((size_t)3 * T + 4);
+    std::vector<uint64_t> keys((size_t)3 * T + 4);
+    EdgeList edges{&num_edges, ids.data(), keys.data()};
+    // k_bin_count, in DESCENDING triangle order: the device appends in an arbitrary order, nothing may depend on it
+    for (int k = T - 1; k >= 0; k--)
+        bin_count_triangle<HostEnv>(s, k, sigma, st.tiles_x, st.tri_count.data(), edges, st.edge_count.data());
     scan_tiles(st.tri_count, st.tri_offset);
+    scan_tiles(st.edge_count, st.edge_offset);
+    st.E = num_edges;
+    // k_rank_edges
+    st.edge_sorted.assign(st.E, -1);
+    for (int i = 0; i < st.E; i++) st.edge_sorted[edge_rank(i, st.E, keys.data(), ids.data())] = ids[i];
+    // k_bin_fill (again in reversed order)
     st.tri_refs.assign(st.tri_offset[st.nt] + 4, -1);
     std::vector<int> cursor(st.nt, 0);
-    // fill in DESCENDING triangle order: the device fills in an arbitrary order, the result must not depend on it
     for (int k = T - 1; k >= 0; k--)
-        bin_triangle<HostEnv>(s, k, sigma, st.tiles_x, 1, nullptr, st.tri_offset.data(), cursor.data(), st.tri_refs.data(), nullptr);
-    // silhouette edges: select in index order, stable sort by the depth key
-    std::vector<int> ids;
-    if (sigma > 0)
-        for (int i = 0; i < 3 * T; i++) if (flags[i]) ids.push_back(i);
-    st.E = (int)ids.size();
+        bin_fill_triangle<HostEnv>(s, k, st.tiles_x, st.tri_offset.data(), cursor.data(), st.tri_refs.data());
     if (st.E > 0) {
-        std::vector<uint64_t> keys(st.E);
-        for (int i = 0; i < st.E; i++) {
-            int k = ids[i] / 3;
-            double d0 = s.depths[s.faces[3 * k]], d1 = s.depths[s.faces[3 * k + 1]], d2 = s.depths[s.faces[3 * k + 2]];
-            keys[i] = depth_desc_key(((0.0 + d0) + d1) + d2);
-        }
-        std::vector<int> perm(st.E);
-        for (int i = 0; i < st.E; i++) perm[i] = i;
-        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return keys[a] < keys[b]; });
-        st.edge_sorted.resize(st.E);
-        for (int i = 0; i < st.E; i++) st.edge_sorted[i] = ids[perm[i]];
-        st.edge_count.assign(st.nt, 0);
-        for (int r = 0; r < st.E; r++)
-            bin_edge<HostEnv>(s, st.edge_sorted[r], r, sigma, st.tiles_x, 0, st.edge_count.data(), nullptr, nullptr, nullptr);
-        scan_tiles(st.edge_count, st.edge_offset);
         std::vector<int> tmp(st.edge_offset[st.nt] + 4, -1);
         std::fill(cursor.begin(), cursor.end(), 0);
-        for (int r = st.E - 1; r >= 0; r--)  // reversed on purpose, see above
-            bin_edge<HostEnv>(s, st.edge_sorted[r], r, sigma, st.tiles_x, 1, nullptr, st.edge_offset.data(), cursor.data(), tmp.data());
+        for (int r = st.E - 1; r >= 0; r--)
+            bin_fill_edge<HostEnv>(s, st.edge_sorted[r], r, sigma, st.tiles_x, st.edge_offset.data(), cursor.data(), tmp.data());
         st.edge_refs.assign(tmp.size(), -1);
         for (int t = 0; t < st.nt; t++) {  // k_sort_tile_edges
             const int n = st.edge_count[t], base = st.edge_offset[t];
@@ -235,6 +224,23 @@ int emul_render_b(const DeodrSceneView *scene, double sigma, const double *z_buf
         finalize_edge<HostEnv>(s, st.edge_sorted[r], sigma, acc.data() + (size_t)r * edge_acc_stride(C), grads->ij_b,
                                grads->colors_b, grads->uv_b, grads->shade_b);
     return 0;
+}
+
+// test hooks for the exact-arithmetic helpers of rmath.h
+int emul_floor_div(double a, double b, int lo, int hi, int fast) {
+    return fast ? floor_div_clamped(a, b, lo, hi) : floor_div_clamped_reference(a, b, lo, hi);
+}
+int emul_ceil_div(double a, double b, int lo, int hi, int fast) {
+    return fast ? ceil_div_clamped(a, b, lo, hi) : ceil_div_clamped_reference(a, b, lo, hi);
+}
+// batch comparison: returns the number of mismatches between the fast and the reference formulations
+long emul_div_mismatches(const double *a, const double *b, long n, int lo, int hi) {
+    long bad = 0;
+    for (long i = 0; i < n; i++) {
+        bad += floor_div_clamped(a[i], b[i], lo, hi) != floor_div_clamped_reference(a[i], b[i], lo, hi);
+        bad += ceil_div_clamped(a[i], b[i], lo, hi) != ceil_div_clamped_reference(a[i], b[i], lo, hi);
+    }
+    return bad;
 }
 
 int emul_num_ties(void) { return (int)g_state.tie_pairs.size() / 2; }
