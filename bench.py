@@ -35,6 +35,7 @@ WORKLOADS = {
     "c5": (708, 2048, 2048, False, 3, "1M-tri synthetic torus mesh (T=1002528), 2048x2048, C=3, sigma=1, fwd+bwd"),
     "c3": (158, 1024, 1024, True, 3, "50k-tri textured torus mesh (T=49928), 1024x1024, bilinear UV, sigma=1, fwd+bwd"),
     "c4": (316, 512, 512, False, 3, "200k-tri torus mesh (T=199712), 512x512 RGB view, sigma=1, fwd+bwd"),
+    "c2": (23, 640, 480, False, 3, "1k-tri torus mesh (T=1058; stand-in for the 1048-face hand mesh), 640x480, fwd+bwd"),
     "dev": (100, 512, 512, False, 3, "development-size torus"),
 }
 METRIC = "fwd+bwd Mpixels/s"

@@ -74,79 +74,132 @@ static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirro
 
 // ------------------------------------------------------------------------------------------------- kernels
 
-// Count pass: one thread per triangle (tile counts, silhouette-edge append, edge tile counts).
-__global__ void k_bin_count(SceneView s, double sigma, int tiles_x, int *tri_tile_count, EdgeList edges,
-                            int *edge_tile_count, const int *bad_indices) {
+// Count pass: one thread per triangle (small / large tile counts, silhouette-edge append, edge tile counts).
+__global__ void k_bin_count(SceneView s, double sigma, int tiles_x, TriBins bins, EdgeList edges, int *edge_tile_count,
+                            const int *bad_indices) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.nb_triangles) return;
     if (bad_indices && *bad_indices) return;  // out-of-range face indices found by k_check_scene: touch nothing
-    bin_count_triangle<DevEnv>(s, k, sigma, tiles_x, tri_tile_count, edges, edge_tile_count);
+    bin_count_triangle<DevEnv>(s, k, sigma, tiles_x, bins, edges, edge_tile_count);
 }
 
-// Exclusive scans of the triangle (blockIdx 0) and edge (blockIdx 1) tile counts, each rounded up to a multiple of 4
-// entries (16-byte aligned list starts).  1024 threads per CTA; offsets[n] and totals[blockIdx] get the grand total.
-__global__ void __launch_bounds__(1024) k_scan_tiles(const int *tri_count, int *tri_offset, const int *edge_count,
-                                                     int *edge_offset, int n, int *totals) {
-    __shared__ int partial[1024];
-    const int *count = blockIdx.x == 0 ? tri_count : edge_count;
-    int *offset = blockIdx.x == 0 ? tri_offset : edge_offset;
-    const int tid = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    int sum = 0;
-    for (int i = lo; i < hi; i++) sum += (count[i] + 3) & ~3;
-    partial[tid] = sum;
-    __syncthreads();
-    for (int step = 1; step < 1024; step <<= 1) {
-        int v = tid >= step ? partial[tid - step] : 0;
+// Exclusive scans of the tile counts: blockIdx 0 small triangles (records), 1 large triangles, 2 silhouette edges.
+// 1024 threads per CTA, coalesced loads with a one-chunk prefetch; offsets[n] and totals[] receive the grand totals.
+struct ScanJob {
+    const int *count[3];
+    int *offset[3];
+    int total_slot[3];
+};
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *totals) {
+    __shared__ int warp_sums[32];
+    const int *count = job.count[blockIdx.x];
+    int *offset = job.offset[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    int next = tid < n ? count[tid] : 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int idx = base + tid, v = next;
+        next = idx + 1024 < n ? count[idx + 1024] : 0;  // coalesced prefetch of the next chunk
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
         __syncthreads();
-        partial[tid] += v;
+        if (warp == 0) {
+            int w = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        if (idx < n) offset[idx] = carry + (warp ? warp_sums[warp - 1] : 0) + incl - v;
+        carry += warp_sums[31];
         __syncthreads();
     }
-    int run = partial[tid] - sum;
-    for (int i = lo; i < hi; i++) {
-        offset[i] = run;
-        run += (count[i] + 3) & ~3;
-    }
-    if (tid == 1023) {
-        offset[n] = partial[1023];
-        totals[blockIdx.x == 0 ? 0 : 2] = partial[1023];
+    if (tid == 0) {
+        offset[n] = carry;
+        totals[job.total_slot[blockIdx.x]] = carry;
     }
 }
 
-// Far-to-near order of the appended silhouette edges by rank counting; keys staged through shared memory.
-__global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *edge_sorted) {
+// Far-to-near order of the appended silhouette edges by rank counting (DR.h:2781; ties by id).  2-D grid: CTA (bx, by)
+// counts, for its 256 edges i, the edges j of chunk by (1024 keys staged in shared memory) that precede them, and adds
+// the partial count to rank[i]; k_scatter_edges then writes edge_sorted[rank[i]] = ids[i].
+__global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *rank) {
     __shared__ unsigned long long sk[1024];
     __shared__ int si[1024];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long key = i < n ? edges.keys[i] : 0ull;
-    const int id = i < n ? edges.ids[i] : 0;
-    int rank = 0;
-    for (int base = 0; base < n; base += 1024) {
-        const int m = min(1024, n - base);
-        __syncthreads();
-        for (int j = threadIdx.x; j < m; j += blockDim.x) {
-            sk[j] = edges.keys[base + j];
-            si[j] = edges.ids[base + j];
-        }
-        __syncthreads();
-        for (int j = 0; j < m; j++) rank += (sk[j] < key) || (sk[j] == key && si[j] < id);
+    const int base = blockIdx.y * 1024, m = min(1024, n - base);
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        sk[j] = edges.keys[base + j];
+        si[j] = edges.ids[base + j];
     }
-    if (i < n) edge_sorted[rank] = id;
+    __syncthreads();
+    if (i >= n) return;
+    const unsigned long long key = edges.keys[i];
+    const int id = edges.ids[i];
+    int partial = 0;
+    for (int j = 0; j < m; j++) partial += (sk[j] < key) || (sk[j] == key && si[j] < id);
+    if (partial) atomicAdd(&rank[i], partial);
+}
+
+__global__ void k_scatter_edges(EdgeList edges, int n, const int *rank, int *edge_sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) edge_sorted[rank[i]] = edges.ids[i];
 }
 
 // Fill pass: blocks [0, tri_blocks) append triangles, the remaining blocks append silhouette edges (by rank).
-__global__ void k_bin_fill(SceneView s, double sigma, int tiles_x, int tri_blocks, const int *tri_offset,
-                           int *tri_cursor, int *tri_refs, const int *edge_sorted, int num_edges,
-                           const int *edge_offset, int *edge_cursor, int *edge_refs) {
+__global__ void k_bin_fill(SceneView s, double sigma, int tiles_x, int tri_blocks, TriBins bins, const int *edge_sorted,
+                           int num_edges, const int *edge_offset, int *edge_cursor, int *edge_refs) {
     if ((int)blockIdx.x < tri_blocks) {
         int k = blockIdx.x * blockDim.x + threadIdx.x;
-        if (k < s.nb_triangles) bin_fill_triangle<DevEnv>(s, k, tiles_x, tri_offset, tri_cursor, tri_refs);
+        if (k < s.nb_triangles) bin_fill_triangle<DevEnv>(s, k, tiles_x, bins);
     } else {
         int r = (blockIdx.x - tri_blocks) * blockDim.x + threadIdx.x;
         if (r < num_edges)
             bin_fill_edge<DevEnv>(s, edge_sorted[r], r, sigma, tiles_x, edge_offset, edge_cursor, edge_refs);
     }
+}
+
+// ---------------------------------------------------------------------------- TMA (bulk async copy) + mbarrier
+
+static __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+static __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+static __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// global -> shared bulk copy (SASS: UBLKCP), completion signalled on `bar` as transaction bytes.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+static __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // Orders every tile's edge list by far-to-near rank (ranks are unique): rank-counting sort, one CTA per tile.
@@ -167,12 +220,12 @@ struct TieTable {
 };
 
 template <int MAXC>
-__global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, int tiles_x, const int *tri_count,
-                                                   const int *tri_offset, const int *tri_refs, const int *edge_count,
-                                                   const int *edge_offset, const int *edge_refs,
-                                                   const int *edge_sorted, TieTable ties, float *image,
-                                                   double *z_buffer, int *owner, int *face_id) {
+__global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, int tiles_x, TriBins bins,
+                                                   const int *edge_count, const int *edge_offset,
+                                                   const int *edge_refs, const int *edge_sorted, TieTable ties,
+                                                   float *image, double *z_buffer, int *owner, int *face_id) {
     __shared__ TileShared sh;
+    __shared__ alignas(8) uint64_t list_barrier;
     const int tile_id = blockIdx.x, tid = threadIdx.x;
     const Tile tile = tile_of(tile_id, tiles_x);
     const int c = tid % TS, r = tid / TS;
@@ -184,13 +237,39 @@ __global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, in
     p.own = -1;
     p.bown = -1;
 
-    const int n_tri = tri_count[tile_id], tri_base = tri_offset[tile_id];
-    for (int base = 0; base < n_tri; base += TRI_CHUNK) {
-        const int m = min(TRI_CHUNK, n_tri - base);
-        phase_tri_setup(s, tid, m, tri_refs + tri_base + base, tile, &sh);
+    // small triangles: the tile's pre-masked records are one contiguous array; each chunk is pulled into shared
+    // memory by a single bulk (TMA) copy issued by thread 0 and awaited by everybody on an mbarrier
+    const int n_small = bins.small_cursor[tile_id];
+    if (n_small > 0) {
+        const PreRec *list = bins.small_recs + bins.small_offset[tile_id];
+        if (tid == 0) mbar_init(&list_barrier, 1);
         __syncthreads();
-        if (inside) phase_tri_test<MAXC>(s, tid, m, tile, &sh, &p);
-        __syncthreads();
+        uint32_t parity = 0;
+        for (int base = 0; base < n_small; base += TRI_CHUNK) {
+            const int m = min(TRI_CHUNK, n_small - base);
+            if (tid == 0) {
+                mbar_expect_tx(&list_barrier, (uint32_t)(m * sizeof(PreRec)));
+                bulk_load(sh.tri.pre, list + base, (uint32_t)(m * sizeof(PreRec)), &list_barrier);
+            }
+            mbar_wait(&list_barrier, parity);
+            parity ^= 1u;
+            phase_pre_unpack(tid, m, sh.tri.pre, &sh);
+            __syncthreads();
+            if (inside) phase_tri_test<MAXC>(s, tid, m, tile, &sh, &p);
+            __syncthreads();
+        }
+    }
+    // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
+    const int n_large = bins.large_count[tile_id];
+    if (n_large > 0) {
+        const int *list = bins.large_refs + bins.large_offset[tile_id];
+        for (int base = 0; base < n_large; base += TRI_CHUNK) {
+            const int m = min(TRI_CHUNK, n_large - base);
+            phase_tri_setup(s, tid, m, list + base, tile, &sh);
+            __syncthreads();
+            if (inside) phase_tri_test<MAXC>(s, tid, m, tile, &sh, &p);
+            __syncthreads();
+        }
     }
     if (inside) phase_shade<MAXC>(s, x, y, &p);
 
@@ -376,8 +455,7 @@ static inline int grid_for(size_t n, int block) { return (int)((n + block - 1) /
 template <int MAXC>
 static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
                        float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
-    k_raster_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->tri_count_ptr,
-                                                     ws->tri_offset.as<int>(), ws->tri_refs.as<int>(), edge_count,
+    k_raster_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->bins, edge_count,
                                                      ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                      ws->edge_sorted.as<int>(), ties, image, z, owner, face_id);
 }
@@ -497,7 +575,8 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
 void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    DevBuf *bufs[] = {&ws->zeroed, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids, &ws->edge_ids_tmp,
+    DevBuf *bufs[] = {&ws->zeroed, &ws->small_offset, &ws->small_recs, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
+                      &ws->edge_ids_tmp, &ws->edge_rank,
                       &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
                       &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
                       &ws->tie_pairs, &ws->edge_acc, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
@@ -561,11 +640,13 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     ws->tiles_y = (s.height + TS - 1) / TS;
     ws->num_tiles = ws->tiles_x * ws->tiles_y;
     const int nt = ws->num_tiles;
-    // one zero-initialised block: [scalars(8) | tri_count | tri_cursor | edge_count | edge_cursor], (nt+1) ints each
+    // one zero-initialised block: [scalars(8) | small_count | small_cursor | large_count | large_cursor | edge_count |
+    // edge_cursor], (nt+1) ints each
     const size_t tile_ints = (size_t)nt + 1;
     const size_t tile_bytes = tile_ints * sizeof(int);
     int rc = 0;
-    rc |= ws->zeroed.ensure((8 + 4 * tile_ints) * sizeof(int), &ws->bytes);
+    rc |= ws->zeroed.ensure((8 + 6 * tile_ints) * sizeof(int), &ws->bytes);
+    rc |= ws->small_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->tri_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_ids.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
@@ -576,51 +657,65 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     }
     if (rc) return DEODR_B200_ECUDA;
     int *scal = ws->zeroed.as<int>();
-    int *tri_count = scal + 8, *tri_cursor = tri_count + tile_ints, *edge_count_buf = tri_cursor + tile_ints,
+    int *small_count = scal + 8, *small_cursor = small_count + tile_ints, *large_count = small_cursor + tile_ints,
+        *large_cursor = large_count + tile_ints, *edge_count_buf = large_cursor + tile_ints,
         *edge_cursor = edge_count_buf + tile_ints;
     ws->scal = scal;
-    ws->tri_count_ptr = tri_count;
     ws->edge_count_ptr = edge_count_buf;
     EdgeList edges{scal + 1, ws->edge_ids.as<int>(), (uint64_t *)ws->edge_keys_in.ptr};
+    TriBins bins{small_count, ws->small_offset.as<int>(), small_cursor, nullptr,
+                 large_count, ws->tri_offset.as<int>(), large_cursor, nullptr};
 
     // ---- count pass + scans (triangles and silhouette edges together), then the ONE host read-back of the sizes
     {
         PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI, st);
-        CUDA_TRY(cudaMemsetAsync(scal, 0, (8 + 4 * tile_ints) * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(scal, 0, (8 + 6 * tile_ints) * sizeof(int), st));
         if (T > 0) {
             if (check_indices) {  // checkSceneValid (DR.h:2703-2714) on the device, before any index is dereferenced
                 k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, scal + 4);
                 ws->launches++;
             }
-            k_bin_count<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, tri_count, edges, edge_count_buf,
+            k_bin_count<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, bins, edges, edge_count_buf,
                                                           check_indices ? scal + 4 : nullptr);
             ws->launches++;
         }
-        k_scan_tiles<<<2, 1024, 0, st>>>(tri_count, ws->tri_offset.as<int>(), edge_count_buf,
-                                         ws->edge_offset.as<int>(), nt, scal);
+        ScanJob job{{small_count, large_count, edge_count_buf},
+                    {ws->small_offset.as<int>(), ws->tri_offset.as<int>(), ws->edge_offset.as<int>()},
+                    {5, 0, 2}};
+        k_scan_tiles<<<3, 1024, 0, st>>>(job, nt, scal);
         ws->launches++;
     }
-    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (check_indices && (ws->host_totals[4] & 1))
         return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
     if (check_indices && (ws->host_totals[4] & 2))
         return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
-    const int tri_total = ws->host_totals[0], E = ws->host_totals[1], edge_total = ws->host_totals[2];
+    const int large_total = ws->host_totals[0], E = ws->host_totals[1], edge_total = ws->host_totals[2],
+              small_total = ws->host_totals[5];
     ws->num_edges = E;
     rc = 0;
-    rc |= ws->tri_refs.ensure(((size_t)tri_total + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->small_recs.ensure(((size_t)small_total + 1) * sizeof(PreRec), &ws->bytes);
+    rc |= ws->tri_refs.ensure(((size_t)large_total + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_sorted.ensure(((size_t)E + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->edge_rank.ensure(((size_t)E + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_refs_tmp.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_refs.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
     if (rc) return DEODR_B200_ECUDA;
+    bins.small_recs = ws->small_recs.as<PreRec>();
+    bins.large_refs = ws->tri_refs.as<int>();
+    ws->bins = bins;
 
     // ---- far-to-near order of the silhouette edges (DR.h:2781)
     if (E > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, st);
         if (E <= 65536) {
-            k_rank_edges<<<grid_for(E, 256), 256, 0, st>>>(edges, E, ws->edge_sorted.as<int>());
-            ws->launches++;
+            CUDA_TRY(cudaMemsetAsync(ws->edge_rank.ptr, 0, (size_t)E * sizeof(int), st));
+            dim3 grid(grid_for(E, 256), grid_for(E, 1024));
+            k_rank_edges<<<grid, 256, 0, st>>>(edges, E, ws->edge_rank.as<int>());
+            k_scatter_edges<<<grid_for(E, 256), 256, 0, st>>>(edges, E, ws->edge_rank.as<int>(),
+                                                               ws->edge_sorted.as<int>());
+            ws->launches += 2;
         } else {
             // large soups: two stable radix sorts (by id, then by depth key) give the same total order
             rc = 0;
@@ -643,8 +738,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     if (T > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI_FILL, st);
         const int tri_blocks = grid_for(T, 128), edge_blocks = E > 0 ? grid_for(E, 128) : 0;
-        k_bin_fill<<<tri_blocks + edge_blocks, 128, 0, st>>>(s, sigma, ws->tiles_x, tri_blocks, ws->tri_offset.as<int>(),
-                                                              tri_cursor, ws->tri_refs.as<int>(),
+        k_bin_fill<<<tri_blocks + edge_blocks, 128, 0, st>>>(s, sigma, ws->tiles_x, tri_blocks, bins,
                                                               ws->edge_sorted.as<int>(), E, ws->edge_offset.as<int>(),
                                                               edge_cursor, ws->edge_refs_tmp.as<int>());
         ws->launches++;

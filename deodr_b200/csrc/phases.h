@@ -26,9 +26,23 @@ struct alignas(16) Mask4 {
     uint32_t m[4];
 };
 
+// Pre-masked tile record of a SMALL triangle (bounding box <= SMALL_TILES tiles), written by the fill pass: the exact
+// coverage of the 16x16 tile (8 row pairs x 32 bits) + what the z test needs.  64 bytes, so a tile's list is one
+// contiguous, 16-byte aligned array that the raster kernel pulls into shared memory with one bulk (TMA) copy.
+struct alignas(16) PreRec {
+    uint32_t mask[TS / 2];
+    double zp[3];
+    int32_t id;
+    int32_t pad;
+};
+static_assert(sizeof(PreRec) == 64, "PreRec must be 64 bytes");
+
+constexpr int SMALL_TILES = 4;    // triangles whose bounding box spans more tiles are binned by index ("large")
+
 struct TileShared {
     union {
         struct {
+            PreRec pre[TRI_CHUNK];  // bulk-copy landing zone of the small-triangle records
             TriRec rec[TRI_CHUNK];
             // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
             // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time
@@ -103,10 +117,26 @@ DEODR_HD void gather_edge(const SceneView &s, int edge_id, double V[2][2]) {
     remove_offset(V, 2, pixel_offset(s));
 }
 
-// Count pass, one thread per triangle: tile_count[tile] += 1 for every tile of the triangle's bounding box; the
-// triangle's silhouette edges are appended to `edges` and counted into edge_tile_count.
+// Per-tile lists of the drawn triangles.  SMALL triangles (bounding box of at most SMALL_TILES tiles: the micro-
+// triangle regime) get a pre-masked PreRec per tile they actually cover; LARGE ones are binned by index into every
+// tile of their bounding box and their row spans are computed by the tile CTA in parallel.
+struct TriBins {
+    int *small_count;         // count pass: upper bound (bounding box); fill pass: exact via small_cursor
+    const int *small_offset;
+    int *small_cursor;
+    PreRec *small_recs;
+    int *large_count;
+    const int *large_offset;
+    int *large_cursor;
+    int *large_refs;
+};
+
+DEODR_HD bool is_small(const TileBox &b) { return (b.tx1 - b.tx0 + 1) * (b.ty1 - b.ty0 + 1) <= SMALL_TILES; }
+
+// Count pass, one thread per triangle: tile counters of the triangle's bounding box (small / large); the triangle's
+// silhouette edges are appended to `edges` and counted into edge_tile_count.
 template <class Env>
-DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int tiles_x, int *tile_count, EdgeList edges,
+DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int tiles_x, TriBins bins, EdgeList edges,
                                  int *edge_tile_count) {
     uint32_t vid[3];
     double V[3][2], Zv[3];
@@ -128,14 +158,37 @@ DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int ti
     if (!c.drawn) return;
     remove_offset(V, 3, pixel_offset(s));
     TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
+    int *count = is_small(b) ? bins.small_count : bins.large_count;
     for (int ty = b.ty0; ty <= b.ty1; ty++)
-        for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&tile_count[ty * tiles_x + tx], 1);
+        for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&count[ty * tiles_x + tx], 1);
 }
 
-// Fill pass, one thread per triangle: append the triangle index to the list of every tile of its bounding box.
+// 16-bit coverage mask of tile row y for one triangle (exact spans of rmath.h, clipped to the tile).
+DEODR_HD uint32_t tri_row_mask(const SceneView &s, const TriGeom &g, int y, int tile_x0) {
+    int xb, xe;
+    tri_row_span(g, y, s.width, s.height, s.strict_edge != 0, &xb, &xe);
+    xb -= tile_x0;
+    xe -= tile_x0;
+    if (xb < 0) xb = 0;
+    if (xe > TS - 1) xe = TS - 1;
+    return xb <= xe ? (((1u << (xe - xb + 1)) - 1u) << xb) : 0u;
+}
+
+// Coverage of row pair p of the tile at (tile_x0, tile_y0): rows 2p (bits 0-15) and 2p+1 (bits 16-31).
+DEODR_HD uint32_t tri_pair_mask(const SceneView &s, const TriGeom &g, int y_first, int y_last, int tile_x0, int tile_y0,
+                                int p) {
+    const int y = tile_y0 + 2 * p;
+    uint32_t m = 0;
+    if (y + 1 >= y_first && y <= y_last) {
+        if (y >= y_first) m = tri_row_mask(s, g, y, tile_x0);
+        if (y + 1 <= y_last) m |= tri_row_mask(s, g, y + 1, tile_x0) << 16;
+    }
+    return m;
+}
+
+// Fill pass, one thread per triangle.
 template <class Env>
-DEODR_HD void bin_fill_triangle(const SceneView &s, int k, int tiles_x, const int *tile_offset, int *tile_cursor,
-                                int *refs) {
+DEODR_HD void bin_fill_triangle(const SceneView &s, int k, int tiles_x, TriBins bins) {
     uint32_t vid[3];
     double V[3][2], Zv[3];
     gather_tri(s, k, vid, V, Zv);
@@ -143,10 +196,33 @@ DEODR_HD void bin_fill_triangle(const SceneView &s, int k, int tiles_x, const in
     if (!c.drawn) return;
     remove_offset(V, 3, pixel_offset(s));
     TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
+    if (b.tx0 > b.tx1) return;
+    if (!is_small(b)) {
+        for (int ty = b.ty0; ty <= b.ty1; ty++)
+            for (int tx = b.tx0; tx <= b.tx1; tx++) {
+                int t = ty * tiles_x + tx;
+                bins.large_refs[bins.large_offset[t] + Env::atomic_add(&bins.large_cursor[t], 1)] = k;
+            }
+        return;
+    }
+    TriGeom g;
+    tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
+    int y_first, y_last;
+    tri_row_range(g, s.height, &y_first, &y_last);
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) {
+            PreRec rec;
+            uint32_t any = 0;
+            for (int p = 0; p < TS / 2; p++) {
+                rec.mask[p] = tri_pair_mask(s, g, y_first, y_last, tx * TS, ty * TS, p);
+                any |= rec.mask[p];
+            }
+            if (!any) continue;  // bounding box touches the tile, the triangle does not
+            rec.zp[0] = g.zp[0]; rec.zp[1] = g.zp[1]; rec.zp[2] = g.zp[2];
+            rec.id = k;
+            rec.pad = 0;
             int t = ty * tiles_x + tx;
-            refs[tile_offset[t] + Env::atomic_add(&tile_cursor[t], 1)] = k;
+            bins.small_recs[bins.small_offset[t] + Env::atomic_add(&bins.small_cursor[t], 1)] = rec;
         }
 }
 
@@ -184,19 +260,23 @@ struct PixelState {
     float col[MAXC];
 };
 
-// 16-bit coverage mask of tile row y for one triangle (exact spans of rmath.h, clipped to the tile).
-DEODR_HD uint32_t tri_row_mask(const SceneView &s, const TriGeom &g, int y, int tile_x0) {
-    int xb, xe;
-    tri_row_span(g, y, s.width, s.height, s.strict_edge != 0, &xb, &xe);
-    xb -= tile_x0;
-    xe -= tile_x0;
-    if (xb < 0) xb = 0;
-    if (xe > TS - 1) xe = TS - 1;
-    return xb <= xe ? (((1u << (xe - xb + 1)) - 1u) << xb) : 0u;
+// Phase T1a: thread tid < n unpacks small-triangle record `pre[tid]` (already in shared memory, or anywhere on the
+// host) into the z-test layout; threads up to the next multiple of 4 write empty masks (padding).
+DEODR_HD void phase_pre_unpack(int tid, int n, const PreRec *pre, TileShared *sh) {
+    if (tid >= n) {
+        if (tid < ((n + 3) & ~3))
+            for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = 0u;
+        return;
+    }
+    const PreRec &r = pre[tid];
+    for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = r.mask[p];
+    TriRec &rec = sh->tri.rec[tid];
+    rec.zp[0] = r.zp[0]; rec.zp[1] = r.zp[1]; rec.zp[2] = r.zp[2];
+    rec.id = r.id;
 }
 
-// Phase T1: thread tid < n sets up triangle list[tid] (stencil equations stay in registers) and writes its z plane and
-// its coverage masks of the 16 tile rows; threads up to the next multiple of 4 write empty masks (padding).
+// Phase T1b: thread tid < n sets up LARGE triangle list[tid] (stencil equations stay in registers) and writes its z
+// plane and its coverage masks of the 16 tile rows; padding as above.
 DEODR_HD void phase_tri_setup(const SceneView &s, int tid, int n, const int *list, Tile tile, TileShared *sh) {
     if (tid >= n) {
         if (tid < ((n + 3) & ~3))
@@ -215,15 +295,7 @@ DEODR_HD void phase_tri_setup(const SceneView &s, int tid, int n, const int *lis
     rec.id = k;
     int y_first, y_last;
     tri_row_range(g, s.height, &y_first, &y_last);
-    for (int p = 0; p < TS / 2; p++) {
-        const int y = tile.y0 + 2 * p;
-        uint32_t m = 0;
-        if (y + 1 >= y_first && y <= y_last) {
-            if (y >= y_first) m = tri_row_mask(s, g, y, tile.x0);
-            if (y + 1 <= y_last) m |= tri_row_mask(s, g, y + 1, tile.x0) << 16;
-        }
-        sh->tri.mask[p][tid] = m;
-    }
+    for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = tri_pair_mask(s, g, y_first, y_last, tile.x0, tile.y0, p);
 }
 
 // Phase T2: each pixel walks the chunk and keeps the minimum z, order-independently:

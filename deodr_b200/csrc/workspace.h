@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/deodr_b200.h"
+#include "phases.h"
 
 char *deodr_error_buffer();  // thread-local, 512 bytes (defined in kernels.cu)
 
@@ -63,10 +64,11 @@ struct DeodrWorkspace {
     double sigma = -1;
     int fwd_valid = 0;
     int fwd_T = 0, fwd_H = 0, fwd_W = 0, fwd_C = 0;
-    DevBuf zeroed;               // [scalars(8) | tri_count | tri_cursor | edge_count | edge_cursor], memset per forward
-    int *scal = nullptr, *tri_count_ptr = nullptr, *edge_count_ptr = nullptr;  // views into `zeroed`
-    DevBuf tri_offset, tri_refs;
-    DevBuf edge_ids, edge_ids_tmp, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
+    DevBuf zeroed;               // [scalars(8) | 6 per-tile int arrays], one memset per forward
+    int *scal = nullptr, *edge_count_ptr = nullptr;  // views into `zeroed`
+    deodr::TriBins bins;         // small (pre-masked records) / large (indices) tile lists of the last forward
+    DevBuf small_offset, small_recs, tri_offset, tri_refs;
+    DevBuf edge_rank, edge_ids, edge_ids_tmp, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
     DevBuf edge_offset, edge_refs_tmp, edge_refs;
     DevBuf scalars;              // device ints: [0] tri total, [1] num selected, [2] edge total, [3] tie counter, [4] flags
     DevBuf tie_pairs;

@@ -25,7 +25,9 @@ struct HostEnv {
 
 struct EmulState {
     int tiles_x = 0, tiles_y = 0, nt = 0, E = 0;
-    std::vector<int> tri_count, tri_offset, tri_refs, edge_count, edge_offset, edge_refs, edge_sorted;
+    std::vector<int> small_count, small_offset, small_cursor, large_count, large_offset, large_cursor, large_refs;
+    std::vector<PreRec> small_recs;
+    std::vector<int> edge_count, edge_offset, edge_refs, edge_sorted;
     std::vector<int> tie_pairs;
 };
 
@@ -34,7 +36,7 @@ static EmulState g_state;
 static void scan_tiles(const std::vector<int> &count, std::vector<int> &offset) {
     int run = 0;
     offset.resize(count.size() + 1);
-    for (size_t i = 0; i < count.size(); i++) { offset[i] = run; run += (count[i] + 3) & ~3; }
+    for (size_t i = 0; i < count.size(); i++) { offset[i] = run; run += count[i]; }
     offset[count.size()] = run;
 }
 
@@ -47,10 +49,19 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
         const Tile tile = tile_of(tile_id, st.tiles_x);
         for (int tid = 0; tid < NT; tid++) { px[tid].z = std::numeric_limits<double>::infinity(); px[tid].own = px[tid].bown = -1; }
         auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
-        const int n_tri = st.tri_count[tile_id], tri_base = st.tri_offset[tile_id];
-        for (int base = 0; base < n_tri; base += TRI_CHUNK) {
-            const int m = std::min(TRI_CHUNK, n_tri - base);
-            for (int tid = 0; tid < NT; tid++) phase_tri_setup(s, tid, m, st.tri_refs.data() + tri_base + base, tile, sh);
+        const int n_small = st.small_cursor[tile_id];
+        for (int base = 0; base < n_small; base += TRI_CHUNK) {
+            const int m = std::min(TRI_CHUNK, n_small - base);
+            // the device pulls the chunk into sh->tri.pre with one bulk copy; same bytes here
+            memcpy(sh->tri.pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
+            for (int tid = 0; tid < NT; tid++) phase_pre_unpack(tid, m, sh->tri.pre, sh);
+            for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<MAXC>(s, tid, m, tile, sh, &px[tid]);
+        }
+        const int n_large = st.large_count[tile_id];
+        for (int base = 0; base < n_large; base += TRI_CHUNK) {
+            const int m = std::min(TRI_CHUNK, n_large - base);
+            for (int tid = 0; tid < NT; tid++)
+                phase_tri_setup(s, tid, m, st.large_refs.data() + st.large_offset[tile_id] + base, tile, sh);
             for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<MAXC>(s, tid, m, tile, sh, &px[tid]);
         }
         for (int tid = 0; tid < NT; tid++)
@@ -165,26 +176,36 @@ int emul_render(const DeodrSceneView *scene, double sigma, float *image, double 
     st.tiles_x = (s.width + TS - 1) / TS;
     st.tiles_y = (s.height + TS - 1) / TS;
     st.nt = st.tiles_x * st.tiles_y;
-    st.tri_count.assign(st.nt, 0);
+    st.small_count.assign(st.nt, 0);
+    st.large_count.assign(st.nt, 0);
+    st.small_cursor.assign(st.nt, 0);
+    st.large_cursor.assign(st.nt, 0);
     st.edge_count.assign(st.nt, 0);
     int num_edges = 0;
     std::vector<int> ids((size_t)3 * T + 4);
     std::vector<uint64_t> keys((size_t)3 * T + 4);
     EdgeList edges{&num_edges, ids.data(), keys.data()};
+    TriBins bins{st.small_count.data(), nullptr, st.small_cursor.data(), nullptr,
+                 st.large_count.data(), nullptr, st.large_cursor.data(), nullptr};
     // k_bin_count, in DESCENDING triangle order: the device appends in an arbitrary order, nothing may depend on it
     for (int k = T - 1; k >= 0; k--)
-        bin_count_triangle<HostEnv>(s, k, sigma, st.tiles_x, st.tri_count.data(), edges, st.edge_count.data());
-    scan_tiles(st.tri_count, st.tri_offset);
+        bin_count_triangle<HostEnv>(s, k, sigma, st.tiles_x, bins, edges, st.edge_count.data());
+    scan_tiles(st.small_count, st.small_offset);
+    scan_tiles(st.large_count, st.large_offset);
     scan_tiles(st.edge_count, st.edge_offset);
     st.E = num_edges;
-    // k_rank_edges
+    // k_rank_edges + k_scatter_edges
     st.edge_sorted.assign(st.E, -1);
     for (int i = 0; i < st.E; i++) st.edge_sorted[edge_rank(i, st.E, keys.data(), ids.data())] = ids[i];
     // k_bin_fill (again in reversed order)
-    st.tri_refs.assign(st.tri_offset[st.nt] + 4, -1);
+    st.small_recs.assign(st.small_offset[st.nt] + 1, PreRec());
+    st.large_refs.assign(st.large_offset[st.nt] + 4, -1);
+    bins.small_offset = st.small_offset.data();
+    bins.large_offset = st.large_offset.data();
+    bins.small_recs = st.small_recs.data();
+    bins.large_refs = st.large_refs.data();
+    for (int k = T - 1; k >= 0; k--) bin_fill_triangle<HostEnv>(s, k, st.tiles_x, bins);
     std::vector<int> cursor(st.nt, 0);
-    for (int k = T - 1; k >= 0; k--)
-        bin_fill_triangle<HostEnv>(s, k, st.tiles_x, st.tri_offset.data(), cursor.data(), st.tri_refs.data());
     if (st.E > 0) {
         std::vector<int> tmp(st.edge_offset[st.nt] + 4, -1);
         std::fill(cursor.begin(), cursor.end(), 0);
@@ -245,5 +266,10 @@ long emul_div_mismatches(const double *a, const double *b, long n, int lo, int h
 
 int emul_num_ties(void) { return (int)g_state.tie_pairs.size() / 2; }
 int emul_num_edges(void) { return g_state.E; }
-int emul_tri_refs(void) { return g_state.tri_offset.empty() ? 0 : g_state.tri_offset.back(); }
+int emul_tri_refs(void) {
+    int n = 0;
+    for (int v : g_state.small_cursor) n += v;
+    for (int v : g_state.large_count) n += v;
+    return n;
+}
 }
