@@ -43,16 +43,12 @@ struct DevEnv {
 // single atomic (32x fewer same-address atomics for large triangles).  Otherwise one atomic per lane.
 struct WarpEmit {
     unsigned mask;   // lanes taking part in the interior adjoint (they all execute every emit together)
-    bool uniform;    // same owner triangle on all of them
+    bool uniform;    // all 32 lanes take part and share the owner triangle
     int leader;
     static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }  // texel adjoints
     __device__ __forceinline__ void emit(float *p, float v) const {
-        if (uniform) {
-            for (int off = 16; off > 0; off >>= 1) {
-                float o = __shfl_xor_sync(mask, v, off);
-                // lanes outside `mask` do not take part: their slot returns this lane's own value, drop it
-                v += ((mask >> ((threadIdx.x & 31) ^ off)) & 1u) ? o : 0.0f;
-            }
+        if (uniform) {  // full warp, one owner: butterfly sum, one atomic
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             if ((int)(threadIdx.x & 31) == leader) atomicAdd(p, v);
         } else {
             atomicAdd(p, v);
@@ -66,7 +62,8 @@ static __device__ __forceinline__ WarpEmit make_warp_emit(bool has, int owner) {
     e.mask = __ballot_sync(0xffffffffu, has);
     e.leader = e.mask ? __ffs(e.mask) - 1 : 0;
     const int k0 = __shfl_sync(0xffffffffu, owner, e.leader);
-    e.uniform = __all_sync(0xffffffffu, !has || owner == k0) && __popc(e.mask) > 1;
+    // a butterfly needs every lane: only full warps inside one triangle take the aggregated path
+    e.uniform = e.mask == 0xffffffffu && __all_sync(0xffffffffu, owner == k0);
     return e;
 }
 
@@ -75,12 +72,12 @@ static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirro
 // ------------------------------------------------------------------------------------------------- kernels
 
 // Count pass: one thread per triangle (small / large tile counts, silhouette-edge append, edge tile counts).
-__global__ void k_bin_count(SceneView s, double sigma, int tiles_x, TriBins bins, EdgeList edges, int *edge_tile_count,
-                            const int *bad_indices) {
+__global__ void k_bin_count(SceneView s, double sigma, int tiles_x, TriBins bins, TriLists lists, EdgeList edges,
+                            int *edge_tile_count, const int *bad_indices) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.nb_triangles) return;
     if (bad_indices && *bad_indices) return;  // out-of-range face indices found by k_check_scene: touch nothing
-    bin_count_triangle<DevEnv>(s, k, sigma, tiles_x, bins, edges, edge_tile_count);
+    bin_count_triangle<DevEnv>(s, k, sigma, tiles_x, bins, lists, edges, edge_tile_count);
 }
 
 // Exclusive scans of the tile counts: blockIdx 0 small triangles (records), 1 large triangles, 2 silhouette edges.
@@ -144,7 +141,8 @@ __global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *
     const unsigned long long key = edges.keys[i];
     const int id = edges.ids[i];
     int partial = 0;
-    for (int j = 0; j < m; j++) partial += (sk[j] < key) || (sk[j] == key && si[j] < id);
+#pragma unroll 8
+    for (int j = 0; j < m; j++) partial += (int)(sk[j] < key) | ((int)(sk[j] == key) & (int)(si[j] < id));
     if (partial) atomicAdd(&rank[i], partial);
 }
 
@@ -153,17 +151,27 @@ __global__ void k_scatter_edges(EdgeList edges, int n, const int *rank, int *edg
     if (i < n) edge_sorted[rank[i]] = edges.ids[i];
 }
 
-// Fill pass: blocks [0, tri_blocks) append triangles, the remaining blocks append silhouette edges (by rank).
-__global__ void k_bin_fill(SceneView s, double sigma, int tiles_x, int tri_blocks, TriBins bins, const int *edge_sorted,
-                           int num_edges, const int *edge_offset, int *edge_cursor, int *edge_refs) {
-    if ((int)blockIdx.x < tri_blocks) {
-        int k = blockIdx.x * blockDim.x + threadIdx.x;
-        if (k < s.nb_triangles) bin_fill_triangle<DevEnv>(s, k, tiles_x, bins);
-    } else {
-        int r = (blockIdx.x - tri_blocks) * blockDim.x + threadIdx.x;
-        if (r < num_edges)
-            bin_fill_edge<DevEnv>(s, edge_sorted[r], r, sigma, tiles_x, edge_offset, edge_cursor, edge_refs);
+// Fill pass over the compacted lists: blocks [0, small_blocks) small triangles (pre-masked records), then large
+// triangles (indices), then silhouette edges (ranks).
+__global__ void k_bin_fill(SceneView s, double sigma, int tiles_x, int small_blocks, int large_blocks, TriBins bins,
+                           const int *small_ids, int num_small, const int *large_ids, int num_large,
+                           const int *edge_sorted, int num_edges, const int *edge_offset, int *edge_cursor,
+                           int *edge_refs) {
+    int b = blockIdx.x;
+    if (b < small_blocks) {
+        int i = b * blockDim.x + threadIdx.x;
+        if (i < num_small) bin_fill_small<DevEnv>(s, small_ids[i], tiles_x, bins);
+        return;
     }
+    b -= small_blocks;
+    if (b < large_blocks) {
+        int i = b * blockDim.x + threadIdx.x;
+        if (i < num_large) bin_fill_large<DevEnv>(s, large_ids[i], tiles_x, bins);
+        return;
+    }
+    b -= large_blocks;
+    int r = b * blockDim.x + threadIdx.x;
+    if (r < num_edges) bin_fill_edge<DevEnv>(s, edge_sorted[r], r, sigma, tiles_x, edge_offset, edge_cursor, edge_refs);
 }
 
 // ---------------------------------------------------------------------------- TMA (bulk async copy) + mbarrier
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, in
         }
     }
     owner[idx] = code;
-    if (face_id) face_id[idx] = p.own;
+    if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
 }
 
 template <int MAXC>
@@ -399,6 +407,7 @@ __global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, c
         } else {
             p.own = p.bown = code;
         }
+        if (p.bown >= 0 && (p.bown & SMALL_FLAG)) p.bown = -1;  // taken by k_small_tri_bwd (triangle-parallel)
         if (p.bown >= 0)
             for (int k = 0; k < s.nb_colors; k++) g[k] = image_b[idx * s.nb_colors + k];
     }
@@ -407,6 +416,17 @@ __global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, c
     if (has)
         phase_interior_adjoint<MAXC, WarpEmit>(s, x, y, p, g, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
                                                grads.texture_b, env);
+}
+
+// Triangle-parallel interior adjoint of the small triangles (one thread per entry of the compacted small list).
+template <int MAXC>
+__global__ void __launch_bounds__(128) k_small_tri_bwd(SceneView s, int tiles_x, const int *small_ids, int num_small,
+                                                       const int *edge_count, TieTable ties, const int *owner,
+                                                       const float *image_b, DeodrGrads grads) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_small) return;
+    small_triangle_adjoint<MAXC, DevEnv>(s, small_ids[i], tiles_x, edge_count, owner, ties.pairs, image_b, grads.ij_b,
+                                         grads.colors_b, grads.uv_b, grads.shade_b, grads.texture_b);
 }
 
 __global__ void k_finalize_edges(SceneView s, const int *edge_sorted, const int *num_edges, double sigma,
@@ -463,8 +483,16 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
 template <int MAXC>
 static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
                        const double *z, const int *owner, const float *image_b, const DeodrGrads &g, cudaStream_t st) {
-    k_interior_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, edge_count, ties, owner, image_b, g);
-    ws->launches++;
+    if (ws->num_small > 0) {
+        k_small_tri_bwd<MAXC><<<grid_for(ws->num_small, 128), 128, 0, st>>>(s, ws->tiles_x, ws->small_ids.as<int>(),
+                                                                           ws->num_small, edge_count, ties, owner,
+                                                                           image_b, g);
+        ws->launches++;
+    }
+    if (ws->num_large > 0) {  // pixels owned by large triangles, tiles without silhouette edges
+        k_interior_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, edge_count, ties, owner, image_b, g);
+        ws->launches++;
+    }
     if (edge_count) {
         k_raster_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
                                                          ws->edge_refs.as<int>(), ws->edge_sorted.as<int>(), ties, z,
@@ -575,7 +603,7 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
 void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    DevBuf *bufs[] = {&ws->zeroed, &ws->small_offset, &ws->small_recs, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
+    DevBuf *bufs[] = {&ws->zeroed, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
                       &ws->edge_ids_tmp, &ws->edge_rank,
                       &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
                       &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
@@ -651,6 +679,8 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_ids.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_keys_in.ensure(((size_t)3 * T + 4) * 8, &ws->bytes);
+    rc |= ws->small_ids.ensure(((size_t)T + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->large_ids.ensure(((size_t)T + 4) * sizeof(int), &ws->bytes);
     if (ws->tie_capacity == 0) {
         ws->tie_capacity = 1 << 16;
         rc |= ws->tie_pairs.ensure((size_t)2 * ws->tie_capacity * sizeof(int), &ws->bytes);
@@ -665,6 +695,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     EdgeList edges{scal + 1, ws->edge_ids.as<int>(), (uint64_t *)ws->edge_keys_in.ptr};
     TriBins bins{small_count, ws->small_offset.as<int>(), small_cursor, nullptr,
                  large_count, ws->tri_offset.as<int>(), large_cursor, nullptr};
+    TriLists lists{scal + 6, ws->small_ids.as<int>(), scal + 7, ws->large_ids.as<int>()};
 
     // ---- count pass + scans (triangles and silhouette edges together), then the ONE host read-back of the sizes
     {
@@ -675,7 +706,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
                 k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, scal + 4);
                 ws->launches++;
             }
-            k_bin_count<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, bins, edges, edge_count_buf,
+            k_bin_count<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, bins, lists, edges, edge_count_buf,
                                                           check_indices ? scal + 4 : nullptr);
             ws->launches++;
         }
@@ -685,7 +716,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
         k_scan_tiles<<<3, 1024, 0, st>>>(job, nt, scal);
         ws->launches++;
     }
-    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (check_indices && (ws->host_totals[4] & 1))
         return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
@@ -694,6 +725,8 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     const int large_total = ws->host_totals[0], E = ws->host_totals[1], edge_total = ws->host_totals[2],
               small_total = ws->host_totals[5];
     ws->num_edges = E;
+    ws->num_small = ws->host_totals[6];
+    ws->num_large = ws->host_totals[7];
     rc = 0;
     rc |= ws->small_recs.ensure(((size_t)small_total + 1) * sizeof(PreRec), &ws->bytes);
     rc |= ws->tri_refs.ensure(((size_t)large_total + 4) * sizeof(int), &ws->bytes);
@@ -737,11 +770,15 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     // ---- fill pass (triangles + edges) and per-tile ordering of the edge lists
     if (T > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI_FILL, st);
-        const int tri_blocks = grid_for(T, 128), edge_blocks = E > 0 ? grid_for(E, 128) : 0;
-        k_bin_fill<<<tri_blocks + edge_blocks, 128, 0, st>>>(s, sigma, ws->tiles_x, tri_blocks, bins,
-                                                              ws->edge_sorted.as<int>(), E, ws->edge_offset.as<int>(),
-                                                              edge_cursor, ws->edge_refs_tmp.as<int>());
-        ws->launches++;
+        const int small_blocks = grid_for(ws->num_small, 128), large_blocks = grid_for(ws->num_large, 128),
+                  edge_blocks = E > 0 ? grid_for(E, 128) : 0;
+        if (small_blocks + large_blocks + edge_blocks > 0) {
+            k_bin_fill<<<small_blocks + large_blocks + edge_blocks, 128, 0, st>>>(
+                s, sigma, ws->tiles_x, small_blocks, large_blocks, bins, ws->small_ids.as<int>(), ws->num_small,
+                ws->large_ids.as<int>(), ws->num_large, ws->edge_sorted.as<int>(), E, ws->edge_offset.as<int>(),
+                edge_cursor, ws->edge_refs_tmp.as<int>());
+            ws->launches++;
+        }
     }
     if (E > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BIN, st);

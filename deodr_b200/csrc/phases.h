@@ -38,6 +38,10 @@ struct alignas(16) PreRec {
 static_assert(sizeof(PreRec) == 64, "PreRec must be 64 bytes");
 
 constexpr int SMALL_TILES = 4;    // triangles whose bounding box spans more tiles are binned by index ("large")
+// owner codes: triangle index | SMALL_FLAG when the triangle went through the small (pre-masked) path; the adjoint of
+// such pixels is taken by the triangle-parallel kernel.  -1 = background, <= -2 = entry of the exact-tie table.
+constexpr int SMALL_FLAG = 0x40000000;
+constexpr int TRI_INDEX_MASK = 0x3fffffff;
 
 struct TileShared {
     union {
@@ -133,11 +137,21 @@ struct TriBins {
 
 DEODR_HD bool is_small(const TileBox &b) { return (b.tx1 - b.tx0 + 1) * (b.ty1 - b.ty0 + 1) <= SMALL_TILES; }
 
+// Compacted index lists of the drawn triangles, appended by the count pass (arbitrary order): the fill pass and the
+// triangle-parallel adjoint run one thread per ENTRY, so that whole warps do similar work instead of idling on
+// culled triangles.
+struct TriLists {
+    int *num_small;
+    int *small_ids;
+    int *num_large;
+    int *large_ids;
+};
+
 // Count pass, one thread per triangle: tile counters of the triangle's bounding box (small / large); the triangle's
 // silhouette edges are appended to `edges` and counted into edge_tile_count.
 template <class Env>
-DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int tiles_x, TriBins bins, EdgeList edges,
-                                 int *edge_tile_count) {
+DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int tiles_x, TriBins bins, TriLists lists,
+                                 EdgeList edges, int *edge_tile_count) {
     uint32_t vid[3];
     double V[3][2], Zv[3];
     gather_tri(s, k, vid, V, Zv);
@@ -158,9 +172,13 @@ DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int ti
     if (!c.drawn) return;
     remove_offset(V, 3, pixel_offset(s));
     TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
-    int *count = is_small(b) ? bins.small_count : bins.large_count;
+    if (b.tx0 > b.tx1) return;  // off screen
+    const bool small = is_small(b);
+    int *count = small ? bins.small_count : bins.large_count;
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&count[ty * tiles_x + tx], 1);
+    if (small) lists.small_ids[Env::atomic_add(lists.num_small, 1)] = k;
+    else lists.large_ids[Env::atomic_add(lists.num_large, 1)] = k;
 }
 
 // 16-bit coverage mask of tile row y for one triangle (exact spans of rmath.h, clipped to the tile).
@@ -186,25 +204,32 @@ DEODR_HD uint32_t tri_pair_mask(const SceneView &s, const TriGeom &g, int y_firs
     return m;
 }
 
-// Fill pass, one thread per triangle.
+// Fill pass, one thread per entry of the large list: the index goes to every tile of the bounding box.
 template <class Env>
-DEODR_HD void bin_fill_triangle(const SceneView &s, int k, int tiles_x, TriBins bins) {
+DEODR_HD void bin_fill_large(const SceneView &s, int k, int tiles_x, TriBins bins) {
+    double V[3][2];
+    for (int i = 0; i < 3; i++) {
+        uint32_t v = s.faces[3 * k + i];
+        V[i][0] = s.ij[2 * (size_t)v];
+        V[i][1] = s.ij[2 * (size_t)v + 1];
+    }
+    remove_offset(V, 3, pixel_offset(s));
+    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
+    for (int ty = b.ty0; ty <= b.ty1; ty++)
+        for (int tx = b.tx0; tx <= b.tx1; tx++) {
+            int t = ty * tiles_x + tx;
+            bins.large_refs[bins.large_offset[t] + Env::atomic_add(&bins.large_cursor[t], 1)] = k;
+        }
+}
+
+// Fill pass, one thread per entry of the small list: exact coverage masks of every tile the triangle really covers.
+template <class Env>
+DEODR_HD void bin_fill_small(const SceneView &s, int k, int tiles_x, TriBins bins) {
     uint32_t vid[3];
     double V[3][2], Zv[3];
     gather_tri(s, k, vid, V, Zv);
-    TriClass c = classify_tri(s, k, V, Zv);
-    if (!c.drawn) return;
     remove_offset(V, 3, pixel_offset(s));
     TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
-    if (b.tx0 > b.tx1) return;
-    if (!is_small(b)) {
-        for (int ty = b.ty0; ty <= b.ty1; ty++)
-            for (int tx = b.tx0; tx <= b.tx1; tx++) {
-                int t = ty * tiles_x + tx;
-                bins.large_refs[bins.large_offset[t] + Env::atomic_add(&bins.large_cursor[t], 1)] = k;
-            }
-        return;
-    }
     TriGeom g;
     tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
     int y_first, y_last;
@@ -219,7 +244,7 @@ DEODR_HD void bin_fill_triangle(const SceneView &s, int k, int tiles_x, TriBins 
             }
             if (!any) continue;  // bounding box touches the tile, the triangle does not
             rec.zp[0] = g.zp[0]; rec.zp[1] = g.zp[1]; rec.zp[2] = g.zp[2];
-            rec.id = k;
+            rec.id = k | SMALL_FLAG;
             rec.pad = 0;
             int t = ty * tiles_x + tx;
             bins.small_recs[bins.small_offset[t] + Env::atomic_add(&bins.small_cursor[t], 1)] = rec;
@@ -320,7 +345,10 @@ DEODR_HD void phase_tri_test(const SceneView &s, int tid, int n, Tile tile, cons
             if (persp) z = DDIV(1.0, z);
             const int id = rec.id;
             if (z < p->z) { p->z = z; p->own = id; p->bown = id; }
-            else if (z == p->z && p->own >= 0) { if (id < p->own) p->own = id; if (id > p->bown) p->bown = id; }
+            else if (z == p->z && p->own >= 0) {
+                if ((id & TRI_INDEX_MASK) < (p->own & TRI_INDEX_MASK)) p->own = id;
+                if ((id & TRI_INDEX_MASK) > (p->bown & TRI_INDEX_MASK)) p->bown = id;
+            }
         }
     }
 }
@@ -338,8 +366,10 @@ DEODR_HD void phase_shade(const SceneView &s, int x, int y, PixelState<MAXC> *p)
         }
         return;
     }
-    Owner<MAXC> o;
-    owner_colour<MAXC>(s, p->own, x, y, p->z, &o, p->col);
+    TriAttr t;
+    tri_attr(s, p->own & TRI_INDEX_MASK, &t);
+    PixelEval<MAXC> e;
+    pixel_colour<MAXC>(s, t, x, y, p->z, &e, p->col);
 }
 
 // Phase E1: thread tid < n sets up the record of the edge with far-to-near rank list[tid].
@@ -481,65 +511,68 @@ DEODR_HD void phase_edge_adjoint(const SceneView &s, int x, int y, int r, int n,
     }
 }
 
-// Interior adjoint of one pixel: the residual colour adjoint g goes to the adjoint owner's vertices.
-// Per pixel, with barycentrics b_v and their gradients (closed form of DR.h:841-858 / 1138-1156):
-//   attr_b[v]  += (d colour / d attr) g * b_v
-//   ij_b[v][d] += - b_v * sum_c g_c * d colour_c / d x_d
-// `env.emit(ptr, v)` adds v to a vertex-gradient slot; the device version sums over the warp first when all its
-// pixels share the same owner triangle (same addresses), see WarpEmit in kernels.cu.
+// Interior adjoint of one pixel (pixel-parallel kernels): the residual colour adjoint g goes to the vertices of the
+// adjoint owner.  `env.emit(ptr, v)` adds v to a vertex-gradient slot; the device version sums over the warp first when
+// the whole warp shares the owner triangle (WarpEmit in kernels.cu).
 template <int MAXC, class Env>
 DEODR_HD void phase_interior_adjoint(const SceneView &s, int x, int y, const PixelState<MAXC> &p, const float *g,
                                      float *ij_b, float *colors_b, float *uv_b, float *shade_b, float *texture_b,
                                      const Env &env) {
+    TriAttr t;
+    tri_attr(s, p.bown & TRI_INDEX_MASK, &t);
+    VertexGrads<MAXC> acc;
+    zero_vertex_grads<MAXC>(s, &acc);
+    pixel_adjoint<MAXC, Env>(s, t, x, y, g, &acc, texture_b);
+    flush_vertex_grads<MAXC, Env>(s, t, acc, ij_b, colors_b, uv_b, shade_b, env);
+}
+
+// Plain atomics for the triangle-parallel adjoint.
+template <class Env>
+struct AtomicEmit {
+    DEODR_HD void emit(float *p, float v) const { Env::atomic_add(p, v); }
+};
+
+// Triangle-parallel interior adjoint of one SMALL triangle (micro-triangle regime): the thread walks the triangle's
+// bounding box, takes the pixels whose adjoint owner it is (the reference's `Z == z_buffer` walk, DR.h:1024, resolved
+// to an owner id by the forward pass), accumulates its vertex gradients in registers and scatters them ONCE: 15
+// atomics per triangle instead of 15 per pixel, one barycentric set-up per triangle instead of one per pixel.
+// Pixels of tiles that contain silhouette edges are left to k_raster_bwd (their adjoint colour is not image_b).
+template <int MAXC, class Env>
+DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, const int *edge_tile_count,
+                                     const int *owner, const int *tie_pairs, const float *image_b, float *ij_b,
+                                     float *colors_b, float *uv_b, float *shade_b, float *texture_b) {
     const int C = s.nb_colors;
-    const int k = p.bown;
-    Owner<MAXC> o;
-    float colour[MAXC];
-    owner_colour<MAXC>(s, k, x, y, p.z, &o, colour);
-    float dcdx = 0, dcdy = 0;  // sum_c g_c * d colour_c / dx, dy
-    if (o.textured) {
-        float L_B = 0, e0_B = 0, e1_B = 0;
-        for (int c = 0; c < C; c++) {
-            float A_B = g[c] * o.L;
-            L_B += g[c] * o.texval[c];
-            texture_fetch_duv(o.tap, s.texture, c, A_B, &e0_B, &e1_B);
-            if (texture_b) {
-                float w00 = (1.0f - o.tap.e0) * (1.0f - o.tap.e1), w10 = o.tap.e0 * (1.0f - o.tap.e1);
-                float w01 = (1.0f - o.tap.e0) * o.tap.e1, w11 = o.tap.e0 * o.tap.e1;
-                Env::atomic_add(texture_b + o.tap.i00 + c, w00 * A_B);
-                Env::atomic_add(texture_b + o.tap.i10 + c, w10 * A_B);
-                Env::atomic_add(texture_b + o.tap.i01 + c, w01 * A_B);
-                Env::atomic_add(texture_b + o.tap.i11 + c, w11 * A_B);
-            }
-        }
-        float U_B = o.tap.out0 ? 0.0f : e0_B, V_B = o.tap.out1 ? 0.0f : e1_B;
-        float dudx = 0, dudy = 0, dvdx = 0, dvdy = 0, dLdx = 0, dLdy = 0;
-        for (int i = 0; i < 3; i++) {
-            float gx = (float)o.bary.gx[i], gy = (float)o.bary.gy[i];
-            float ui = (float)s.uv[2 * (size_t)o.uvid[i]], vi = (float)s.uv[2 * (size_t)o.uvid[i] + 1];
-            float li = s.shade[o.vid[i]];
-            dudx += gx * ui; dudy += gy * ui; dvdx += gx * vi; dvdy += gy * vi; dLdx += gx * li; dLdy += gy * li;
-            env.emit(uv_b + 2 * (size_t)o.uvid[i], U_B * o.w[i]);
-            env.emit(uv_b + 2 * (size_t)o.uvid[i] + 1, V_B * o.w[i]);
-            env.emit(shade_b + o.vid[i], L_B * o.w[i]);
-        }
-        dcdx = U_B * dudx + V_B * dvdx + L_B * dLdx;
-        dcdy = U_B * dudy + V_B * dvdy + L_B * dLdy;
-    } else {
-        const float *a0 = s.colors + (size_t)o.vid[0] * C, *a1 = s.colors + (size_t)o.vid[1] * C,
-                    *a2 = s.colors + (size_t)o.vid[2] * C;
-        float gx0 = (float)o.bary.gx[0], gx1 = (float)o.bary.gx[1], gx2 = (float)o.bary.gx[2];
-        float gy0 = (float)o.bary.gy[0], gy1 = (float)o.bary.gy[1], gy2 = (float)o.bary.gy[2];
-        for (int c = 0; c < C; c++) {
-            dcdx += g[c] * (gx0 * a0[c] + gx1 * a1[c] + gx2 * a2[c]);
-            dcdy += g[c] * (gy0 * a0[c] + gy1 * a1[c] + gy2 * a2[c]);
-            for (int i = 0; i < 3; i++) env.emit(colors_b + (size_t)o.vid[i] * C + c, g[c] * o.w[i]);
-        }
-    }
+    TriAttr t;
+    tri_attr(s, k, &t);
+    double V[3][2];
     for (int i = 0; i < 3; i++) {
-        env.emit(ij_b + 2 * (size_t)o.vid[i], -o.w[i] * dcdx);
-        env.emit(ij_b + 2 * (size_t)o.vid[i] + 1, -o.w[i] * dcdy);
+        V[i][0] = s.ij[2 * (size_t)t.vid[i]];
+        V[i][1] = s.ij[2 * (size_t)t.vid[i] + 1];
     }
+    remove_offset(V, 3, pixel_offset(s));
+    int x0, x1, y0, y1;
+    tri_bounds(V, s.strict_edge != 0, &x0, &x1, &y0, &y1);
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > s.width - 1) x1 = s.width - 1;
+    if (y1 > s.height - 1) y1 = s.height - 1;
+    const int code = k | SMALL_FLAG;
+    VertexGrads<MAXC> acc;
+    zero_vertex_grads<MAXC>(s, &acc);
+    bool any = false;
+    for (int y = y0; y <= y1; y++)
+        for (int x = x0; x <= x1; x++) {
+            const size_t idx = (size_t)y * s.width + x;
+            const int c = owner[idx];
+            const bool mine = c == code || (c <= -2 && tie_pairs[2 * (-2 - c) + 1] == code);
+            if (!mine) continue;
+            if (edge_tile_count && edge_tile_count[(y / TS) * tiles_x + x / TS] > 0) continue;
+            float g[MAXC];
+            for (int q = 0; q < C; q++) g[q] = image_b[idx * C + q];
+            pixel_adjoint<MAXC, Env>(s, t, x, y, g, &acc, texture_b);
+            any = true;
+        }
+    if (any) flush_vertex_grads<MAXC, AtomicEmit<Env>>(s, t, acc, ij_b, colors_b, uv_b, shade_b, AtomicEmit<Env>());
 }
 
 // One thread per sorted silhouette edge: turn the accumulated plane adjoints into vertex adjoints.

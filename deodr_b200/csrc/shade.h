@@ -134,51 +134,179 @@ DEODR_HD void texture_fetch_duv(const Tap &t, const float *tex, int k, float a_B
 
 // -------------------------------------------------------------------------------------------- owner-triangle data
 
-// Everything a pixel needs from its owner triangle, gathered once.
-template <int MAXC>
-struct Owner {
-    Bary bary;
+// Per-triangle constants of the attribute interpolation: gathered once per triangle (once per pixel in the
+// pixel-parallel kernels, once per triangle in the triangle-parallel adjoint).
+struct TriAttr {
     uint32_t vid[3], uvid[3];
+    double x0, y0;        // vertex 0, pixel-centre offset removed: barycentrics are evaluated in its frame
+    double gx[3], gy[3];  // d b_i / dx, d b_i / dy
+    double inv_z[3];      // 1 / depth of the vertices (perspective_correct only)
     bool textured;
-    float w[3];        // interpolation weights (barycentrics; times 1/z_k * Z when perspective_correct)
+};
+
+DEODR_HD void tri_attr(const SceneView &s, int k, TriAttr *t) {
+    double V[3][2];
+    for (int i = 0; i < 3; i++) {
+        t->vid[i] = s.faces[3 * k + i];
+        V[i][0] = s.ij[2 * (size_t)t->vid[i]];
+        V[i][1] = s.ij[2 * (size_t)t->vid[i] + 1];
+    }
+    remove_offset(V, 3, pixel_offset(s));
+    const double e1x = V[1][0] - V[0][0], e1y = V[1][1] - V[0][1];
+    const double e2x = V[2][0] - V[0][0], e2y = V[2][1] - V[0][1];
+    const double inv = 1.0 / (e1x * e2y - e2x * e1y);
+    t->x0 = V[0][0];
+    t->y0 = V[0][1];
+    t->gx[1] = e2y * inv;  t->gy[1] = -e2x * inv;
+    t->gx[2] = -e1y * inv; t->gy[2] = e1x * inv;
+    t->gx[0] = -(t->gx[1] + t->gx[2]);
+    t->gy[0] = -(t->gy[1] + t->gy[2]);
+    t->textured = s.textured[k] && s.shaded[k];
+    if (t->textured)
+        for (int i = 0; i < 3; i++) t->uvid[i] = s.faces_uv[3 * k + i];
+    if (s.perspective_correct)
+        for (int i = 0; i < 3; i++) t->inv_z[i] = 1.0 / s.depths[t->vid[i]];
+}
+
+// Interpolation weights of pixel (x, y): barycentrics in the frame of vertex 0 (well conditioned for small triangles
+// far from the origin); times (1/z_i) * Z with perspective_correct (DR.h:943-955), Z = the pixel's z-buffer value.
+DEODR_HD void tri_weights(const SceneView &s, const TriAttr &t, int x, int y, double Z, double w[3]) {
+    const double px = (double)x - t.x0, py = (double)y - t.y0;
+    w[1] = px * t.gx[1] + py * t.gy[1];
+    w[2] = px * t.gx[2] + py * t.gy[2];
+    w[0] = 1.0 - w[1] - w[2];
+    if (s.perspective_correct)
+        for (int i = 0; i < 3; i++) w[i] = w[i] * t.inv_z[i] * Z;
+}
+
+// What the adjoint needs from the evaluation of one pixel.
+template <int MAXC>
+struct PixelEval {
+    float w[3];
     // textured path
-    double u, v;
     float L;
     Tap tap;
     float texval[MAXC];
 };
 
-// Colour of pixel (x, y) inside its owner triangle k.  `Z` is the pixel's z-buffer value (used only by the
-// perspective-correct variant, DR.h:943-955 / 1206-1229).  Fills `o` for the adjoint.
+// Colour of pixel (x, y) inside triangle `t` (DR.h:960-965 interpolated, DR.h:1243-1251 textured gouraud).
 template <int MAXC>
-DEODR_HD void owner_colour(const SceneView &s, int k, int x, int y, double Z, Owner<MAXC> *o, float *colour) {
+DEODR_HD void pixel_colour(const SceneView &s, const TriAttr &t, int x, int y, double Z, PixelEval<MAXC> *e,
+                           float *colour) {
     const int C = s.nb_colors;
-    double V[3][2], Zv[3];
-    gather_tri(s, k, o->vid, V, Zv);
-    remove_offset(V, 3, pixel_offset(s));
-    tri_bary(V, x, y, &o->bary);
-    o->textured = s.textured[k] && s.shaded[k];
-    double wd[3] = {o->bary.b[0], o->bary.b[1], o->bary.b[2]};
-    if (s.perspective_correct)
-        for (int i = 0; i < 3; i++) wd[i] = wd[i] / Zv[i] * Z;
-    for (int i = 0; i < 3; i++) o->w[i] = (float)wd[i];
-    if (o->textured) {
-        o->u = 0; o->v = 0; o->L = 0;
+    double wd[3];
+    tri_weights(s, t, x, y, Z, wd);
+    for (int i = 0; i < 3; i++) e->w[i] = (float)wd[i];
+    if (t.textured) {
+        double u = 0, v = 0;
+        e->L = 0;
         for (int i = 0; i < 3; i++) {
-            o->uvid[i] = s.faces_uv[3 * k + i];
-            o->u += wd[i] * s.uv[2 * (size_t)o->uvid[i]];
-            o->v += wd[i] * s.uv[2 * (size_t)o->uvid[i] + 1];
-            o->L += o->w[i] * s.shade[o->vid[i]];
+            u += wd[i] * s.uv[2 * (size_t)t.uvid[i]];
+            v += wd[i] * s.uv[2 * (size_t)t.uvid[i] + 1];
+            e->L += e->w[i] * s.shade[t.vid[i]];
         }
-        o->tap = texture_tap(o->u, o->v, s.texture_width, s.texture_height, C);
+        e->tap = texture_tap(u, v, s.texture_width, s.texture_height, C);
         for (int c = 0; c < C; c++) {
-            o->texval[c] = texture_fetch(o->tap, s.texture, c);
-            colour[c] = o->texval[c] * o->L;
+            e->texval[c] = texture_fetch(e->tap, s.texture, c);
+            colour[c] = e->texval[c] * e->L;
         }
     } else {
-        const float *a0 = s.colors + (size_t)o->vid[0] * C, *a1 = s.colors + (size_t)o->vid[1] * C,
-                    *a2 = s.colors + (size_t)o->vid[2] * C;
-        for (int c = 0; c < C; c++) colour[c] = o->w[0] * a0[c] + o->w[1] * a1[c] + o->w[2] * a2[c];
+        const float *a0 = s.colors + (size_t)t.vid[0] * C, *a1 = s.colors + (size_t)t.vid[1] * C,
+                    *a2 = s.colors + (size_t)t.vid[2] * C;
+        for (int c = 0; c < C; c++) colour[c] = e->w[0] * a0[c] + e->w[1] * a1[c] + e->w[2] * a2[c];
+    }
+}
+
+// Gradients of one triangle's vertices, accumulated over its pixels before they are scattered.
+template <int MAXC>
+struct VertexGrads {
+    float ij[3][2];
+    float attr[3][MAXC];  // colours (interpolated triangles)
+    float uv[3][2];       // textured triangles
+    float shade[3];
+};
+
+template <int MAXC>
+DEODR_HD void zero_vertex_grads(const SceneView &s, VertexGrads<MAXC> *a) {
+    for (int i = 0; i < 3; i++) {
+        a->ij[i][0] = a->ij[i][1] = 0.0f;
+        a->uv[i][0] = a->uv[i][1] = 0.0f;
+        a->shade[i] = 0.0f;
+        for (int c = 0; c < s.nb_colors; c++) a->attr[i][c] = 0.0f;
+    }
+}
+
+// Adjoint of pixel_colour for one pixel with colour adjoint g (closed form of DR.h:841-858 / 1138-1156):
+//   attr_b[v]  += (d colour / d attr) g * b_v          ij_b[v][d] -= b_v * sum_c g_c * d colour_c / d x_d
+// accumulated into `acc`; texel adjoints go straight to texture_b (summed).
+template <int MAXC, class Env>
+DEODR_HD void pixel_adjoint(const SceneView &s, const TriAttr &t, int x, int y, const float *g, VertexGrads<MAXC> *acc,
+                            float *texture_b) {
+    const int C = s.nb_colors;
+    PixelEval<MAXC> e;
+    float colour[MAXC];
+    pixel_colour<MAXC>(s, t, x, y, 0.0, &e, colour);
+    float dcdx = 0, dcdy = 0;  // sum_c g_c * d colour_c / dx, dy
+    if (t.textured) {
+        float L_B = 0, e0_B = 0, e1_B = 0;
+        for (int c = 0; c < C; c++) {
+            float A_B = g[c] * e.L;
+            L_B += g[c] * e.texval[c];
+            texture_fetch_duv(e.tap, s.texture, c, A_B, &e0_B, &e1_B);
+            if (texture_b) {
+                float w00 = (1.0f - e.tap.e0) * (1.0f - e.tap.e1), w10 = e.tap.e0 * (1.0f - e.tap.e1);
+                float w01 = (1.0f - e.tap.e0) * e.tap.e1, w11 = e.tap.e0 * e.tap.e1;
+                Env::atomic_add(texture_b + e.tap.i00 + c, w00 * A_B);
+                Env::atomic_add(texture_b + e.tap.i10 + c, w10 * A_B);
+                Env::atomic_add(texture_b + e.tap.i01 + c, w01 * A_B);
+                Env::atomic_add(texture_b + e.tap.i11 + c, w11 * A_B);
+            }
+        }
+        float U_B = e.tap.out0 ? 0.0f : e0_B, V_B = e.tap.out1 ? 0.0f : e1_B;
+        float dudx = 0, dudy = 0, dvdx = 0, dvdy = 0, dLdx = 0, dLdy = 0;
+        for (int i = 0; i < 3; i++) {
+            float gx = (float)t.gx[i], gy = (float)t.gy[i];
+            float ui = (float)s.uv[2 * (size_t)t.uvid[i]], vi = (float)s.uv[2 * (size_t)t.uvid[i] + 1];
+            float li = s.shade[t.vid[i]];
+            dudx += gx * ui; dudy += gy * ui; dvdx += gx * vi; dvdy += gy * vi; dLdx += gx * li; dLdy += gy * li;
+            acc->uv[i][0] += U_B * e.w[i];
+            acc->uv[i][1] += V_B * e.w[i];
+            acc->shade[i] += L_B * e.w[i];
+        }
+        dcdx = U_B * dudx + V_B * dvdx + L_B * dLdx;
+        dcdy = U_B * dudy + V_B * dvdy + L_B * dLdy;
+    } else {
+        const float *a0 = s.colors + (size_t)t.vid[0] * C, *a1 = s.colors + (size_t)t.vid[1] * C,
+                    *a2 = s.colors + (size_t)t.vid[2] * C;
+        float gx0 = (float)t.gx[0], gx1 = (float)t.gx[1], gx2 = (float)t.gx[2];
+        float gy0 = (float)t.gy[0], gy1 = (float)t.gy[1], gy2 = (float)t.gy[2];
+        for (int c = 0; c < C; c++) {
+            dcdx += g[c] * (gx0 * a0[c] + gx1 * a1[c] + gx2 * a2[c]);
+            dcdy += g[c] * (gy0 * a0[c] + gy1 * a1[c] + gy2 * a2[c]);
+            for (int i = 0; i < 3; i++) acc->attr[i][c] += g[c] * e.w[i];
+        }
+    }
+    for (int i = 0; i < 3; i++) {
+        acc->ij[i][0] -= e.w[i] * dcdx;
+        acc->ij[i][1] -= e.w[i] * dcdy;
+    }
+}
+
+// Scatter of one triangle's accumulated vertex gradients; `emit.emit(ptr, value)` adds value to *ptr.
+template <int MAXC, class Emit>
+DEODR_HD void flush_vertex_grads(const SceneView &s, const TriAttr &t, const VertexGrads<MAXC> &acc, float *ij_b,
+                                 float *colors_b, float *uv_b, float *shade_b, const Emit &emit) {
+    const int C = s.nb_colors;
+    for (int i = 0; i < 3; i++) {
+        emit.emit(ij_b + 2 * (size_t)t.vid[i], acc.ij[i][0]);
+        emit.emit(ij_b + 2 * (size_t)t.vid[i] + 1, acc.ij[i][1]);
+        if (t.textured) {
+            emit.emit(uv_b + 2 * (size_t)t.uvid[i], acc.uv[i][0]);
+            emit.emit(uv_b + 2 * (size_t)t.uvid[i] + 1, acc.uv[i][1]);
+            emit.emit(shade_b + t.vid[i], acc.shade[i]);
+        } else {
+            for (int c = 0; c < C; c++) emit.emit(colors_b + (size_t)t.vid[i] * C + c, acc.attr[i][c]);
+        }
     }
 }
 

@@ -27,6 +27,7 @@ struct EmulState {
     int tiles_x = 0, tiles_y = 0, nt = 0, E = 0;
     std::vector<int> small_count, small_offset, small_cursor, large_count, large_offset, large_cursor, large_refs;
     std::vector<PreRec> small_recs;
+    std::vector<int> small_ids, large_ids;
     std::vector<int> edge_count, edge_offset, edge_refs, edge_sorted;
     std::vector<int> tie_pairs;
 };
@@ -94,7 +95,7 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
                 code = -2 - slot;
             }
             owner[idx] = code;
-            if (face_id) face_id[idx] = p.own;
+            if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
         }
     }
     delete sh;
@@ -155,12 +156,21 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
                 }
             }
         }
-        for (int tid = 0; tid < NT; tid++)
-            if (inside(tid) && px[tid].bown >= 0)
-                phase_interior_adjoint<MAXC, HostEnv>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, px[tid], adj[tid].g,
-                                                      g.ij_b, g.colors_b, g.uv_b, g.shade_b, g.texture_b, HostEnv());
+        // k_raster_bwd takes every pixel of the tiles with silhouette edges; elsewhere k_interior_bwd takes the pixels
+        // owned by large triangles and k_small_tri_bwd (below, triangle-parallel) those owned by small ones
+        for (int tid = 0; tid < NT; tid++) {
+            if (!inside(tid) || px[tid].bown < 0) continue;
+            if (n_edge == 0 && (px[tid].bown & SMALL_FLAG)) continue;
+            phase_interior_adjoint<MAXC, HostEnv>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, px[tid], adj[tid].g,
+                                                  g.ij_b, g.colors_b, g.uv_b, g.shade_b, g.texture_b, HostEnv());
+        }
     }
     delete sh;
+    // k_small_tri_bwd
+    const int *edge_count = st.E > 0 ? st.edge_count.data() : nullptr;
+    for (int k : st.small_ids)
+        small_triangle_adjoint<MAXC, HostEnv>(s, k, st.tiles_x, edge_count, owner, st.tie_pairs.data(), image_b, g.ij_b,
+                                              g.colors_b, g.uv_b, g.shade_b, g.texture_b);
 }
 
 extern "C" {
@@ -187,9 +197,13 @@ int emul_render(const DeodrSceneView *scene, double sigma, float *image, double 
     EdgeList edges{&num_edges, ids.data(), keys.data()};
     TriBins bins{st.small_count.data(), nullptr, st.small_cursor.data(), nullptr,
                  st.large_count.data(), nullptr, st.large_cursor.data(), nullptr};
+    int num_small = 0, num_large = 0;
+    st.small_ids.assign(T + 4, -1);
+    st.large_ids.assign(T + 4, -1);
+    TriLists lists{&num_small, st.small_ids.data(), &num_large, st.large_ids.data()};
     // k_bin_count, in DESCENDING triangle order: the device appends in an arbitrary order, nothing may depend on it
     for (int k = T - 1; k >= 0; k--)
-        bin_count_triangle<HostEnv>(s, k, sigma, st.tiles_x, bins, edges, st.edge_count.data());
+        bin_count_triangle<HostEnv>(s, k, sigma, st.tiles_x, bins, lists, edges, st.edge_count.data());
     scan_tiles(st.small_count, st.small_offset);
     scan_tiles(st.large_count, st.large_offset);
     scan_tiles(st.edge_count, st.edge_offset);
@@ -204,7 +218,10 @@ int emul_render(const DeodrSceneView *scene, double sigma, float *image, double 
     bins.large_offset = st.large_offset.data();
     bins.small_recs = st.small_recs.data();
     bins.large_refs = st.large_refs.data();
-    for (int k = T - 1; k >= 0; k--) bin_fill_triangle<HostEnv>(s, k, st.tiles_x, bins);
+    st.small_ids.resize(num_small);
+    st.large_ids.resize(num_large);
+    for (int k : st.small_ids) bin_fill_small<HostEnv>(s, k, st.tiles_x, bins);
+    for (int k : st.large_ids) bin_fill_large<HostEnv>(s, k, st.tiles_x, bins);
     std::vector<int> cursor(st.nt, 0);
     if (st.E > 0) {
         std::vector<int> tmp(st.edge_offset[st.nt] + 4, -1);
