@@ -34,6 +34,9 @@ using namespace deodr;
 
 struct DevEnv {
     static __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
+    static __device__ __forceinline__ void atomic_min(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
+    static __device__ __forceinline__ void atomic_min(int *p, int v) { atomicMin(p, v); }
+    static __device__ __forceinline__ void atomic_max(int *p, int v) { atomicMax(p, v); }
     static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
     static __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
 };
@@ -246,26 +249,33 @@ __global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, in
     p.bown = -1;
 
     // small triangles: the tile's pre-masked records are one contiguous array; each chunk is pulled into shared
-    // memory by a single bulk (TMA) copy issued by thread 0 and awaited by everybody on an mbarrier
+    // memory by a single bulk (TMA) copy issued by thread 0 and awaited by everybody on an mbarrier.  Thread t then
+    // owns record t: pass A takes the z minimum per pixel, pass B resolves the owner ids (phases.h).
     const int n_small = bins.small_cursor[tile_id];
     if (n_small > 0) {
         const PreRec *list = bins.small_recs + bins.small_offset[tile_id];
         if (tid == 0) mbar_init(&list_barrier, 1);
+        phase_tilez_init(tid, &sh.z);
         __syncthreads();
         uint32_t parity = 0;
-        for (int base = 0; base < n_small; base += TRI_CHUNK) {
-            const int m = min(TRI_CHUNK, n_small - base);
-            if (tid == 0) {
-                mbar_expect_tx(&list_barrier, (uint32_t)(m * sizeof(PreRec)));
-                bulk_load(sh.tri.pre, list + base, (uint32_t)(m * sizeof(PreRec)), &list_barrier);
+        const bool one_chunk = n_small <= TRI_CHUNK;
+        for (int pass = 0; pass < 2; pass++) {
+            for (int base = 0; base < n_small; base += TRI_CHUNK) {
+                const int m = min(TRI_CHUNK, n_small - base);
+                if (pass == 0 || !one_chunk) {  // a single chunk stays resident between the two passes
+                    if (tid == 0) {
+                        mbar_expect_tx(&list_barrier, (uint32_t)(m * sizeof(PreRec)));
+                        bulk_load(sh.pre, list + base, (uint32_t)(m * sizeof(PreRec)), &list_barrier);
+                    }
+                    mbar_wait(&list_barrier, parity);
+                    parity ^= 1u;
+                }
+                phase_small_pass<DevEnv>(s, tid, m, sh.pre, tile, &sh.z, pass);
+                __syncthreads();
             }
-            mbar_wait(&list_barrier, parity);
-            parity ^= 1u;
-            phase_pre_unpack(tid, m, sh.tri.pre, &sh);
-            __syncthreads();
-            if (inside) phase_tri_test<MAXC>(s, tid, m, tile, &sh, &p);
-            __syncthreads();
         }
+        phase_tilez_read<MAXC>(tid, &sh.z, &p);
+        __syncthreads();  // sh.pre is about to be reused by the large-triangle records
     }
     // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
     const int n_large = bins.large_count[tile_id];

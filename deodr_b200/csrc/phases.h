@@ -26,7 +26,7 @@ struct alignas(16) Mask4 {
     uint32_t m[4];
 };
 
-// Pre-masked tile record of a SMALL triangle (bounding box <= SMALL_TILES tiles), written by the fill pass: the exact
+// Pre-masked tile record of a SMALL triangle (bounding box <= SMALL_TILES tiles and <= SMALL_PIXELS pixels), written by the fill pass: the exact
 // coverage of the 16x16 tile (8 row pairs x 32 bits) + what the z test needs.  64 bytes, so a tile's list is one
 // contiguous, 16-byte aligned array that the raster kernel pulls into shared memory with one bulk (TMA) copy.
 struct alignas(16) PreRec {
@@ -43,10 +43,17 @@ constexpr int SMALL_TILES = 4;    // triangles whose bounding box spans more til
 constexpr int SMALL_FLAG = 0x40000000;
 constexpr int TRI_INDEX_MASK = 0x3fffffff;
 
+// Shared-memory z-buffer of the tile, used by the triangle-parallel pass over the small triangles.
+struct TileZ {
+    unsigned long long key[NT];  // order-preserving key of the running minimum z (z_key)
+    int own[NT];                 // min owner code among the triangles reaching the minimum z
+    int bown[NT];                // max owner code among them
+};
+
 struct TileShared {
     union {
-        struct {
-            PreRec pre[TRI_CHUNK];  // bulk-copy landing zone of the small-triangle records
+        PreRec pre[TRI_CHUNK];  // small triangles: bulk-copy landing zone of the pre-masked records
+        struct {                // large triangles
             TriRec rec[TRI_CHUNK];
             // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
             // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time
@@ -57,6 +64,7 @@ struct TileShared {
             uint32_t span[EDGE_CHUNK][TS];  // x_begin | x_end << 16 (absolute, int16 each); empty if begin > end
         } edge;
     };
+    TileZ z;
 };
 
 struct Tile {
@@ -77,7 +85,10 @@ struct TileBox {
     int tx0, tx1, ty0, ty1;  // inclusive; empty if tx0 > tx1
 };
 
-DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int height) {
+struct TileBox;
+DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int height, int *pixel_area = nullptr);
+
+DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int height, int *pixel_area) {
     TileBox b;
     int x0, x1, y0, y1;
     tri_bounds(V, strict, &x0, &x1, &y0, &y1);
@@ -85,6 +96,7 @@ DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int 
     if (x1 > width - 1) x1 = width - 1;
     if (y0 < 0) y0 = 0;
     if (y1 > height - 1) y1 = height - 1;
+    if (pixel_area) *pixel_area = (y0 > y1 || x0 > x1) ? 0 : (x1 - x0 + 1) * (y1 - y0 + 1);
     if (y0 > y1 || x0 > x1) { b.tx0 = 1; b.tx1 = 0; b.ty0 = 1; b.ty1 = 0; return b; }
     b.tx0 = x0 / TS; b.tx1 = x1 / TS; b.ty0 = y0 / TS; b.ty1 = y1 / TS;
     return b;
@@ -135,7 +147,11 @@ struct TriBins {
     int *large_refs;
 };
 
-DEODR_HD bool is_small(const TileBox &b) { return (b.tx1 - b.tx0 + 1) * (b.ty1 - b.ty0 + 1) <= SMALL_TILES; }
+// "small" = micro-triangle: few tiles AND few pixels, so that one thread can afford to walk it (fill pass, adjoint)
+constexpr int SMALL_PIXELS = 64;
+DEODR_HD bool is_small(const TileBox &b, int pixel_area) {
+    return (b.tx1 - b.tx0 + 1) * (b.ty1 - b.ty0 + 1) <= SMALL_TILES && pixel_area <= SMALL_PIXELS;
+}
 
 // Compacted index lists of the drawn triangles, appended by the count pass (arbitrary order): the fill pass and the
 // triangle-parallel adjoint run one thread per ENTRY, so that whole warps do similar work instead of idling on
@@ -171,9 +187,10 @@ DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int ti
     }
     if (!c.drawn) return;
     remove_offset(V, 3, pixel_offset(s));
-    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
+    int area;
+    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height, &area);
     if (b.tx0 > b.tx1) return;  // off screen
-    const bool small = is_small(b);
+    const bool small = is_small(b, area);
     int *count = small ? bins.small_count : bins.large_count;
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&count[ty * tiles_x + tx], 1);
@@ -285,19 +302,79 @@ struct PixelState {
     float col[MAXC];
 };
 
-// Phase T1a: thread tid < n unpacks small-triangle record `pre[tid]` (already in shared memory, or anywhere on the
-// host) into the z-test layout; threads up to the next multiple of 4 write empty masks (padding).
-DEODR_HD void phase_pre_unpack(int tid, int n, const PreRec *pre, TileShared *sh) {
-    if (tid >= n) {
-        if (tid < ((n + 3) & ~3))
-            for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = 0u;
-        return;
-    }
+// ---- small triangles: triangle-parallel z test on a shared-memory tile z-buffer ------------------------------
+// A micro-triangle covers a handful of the 256 pixels of a tile; letting the 256 pixel-threads look for it wastes the
+// machine (measured: ~40 issue slots per (record, row pair) with ~4 of 32 lanes active).  Instead thread t owns record
+// t and walks the set bits of its masks:
+//   pass A  key[pixel] = min(key[pixel], z_key(z))                      64-bit atomicMin in shared memory
+//   pass B  where z == the final minimum: own = min(own, id), bown = max(bown, id)
+// which is exactly what a strict '<' walk in ascending index order leaves (DR.h:961) and what the '==' walk in
+// descending order finds first (DR.h:1024).  z is evaluated by the same code in both passes.
+
+// Monotone map double -> uint64 (a < b  <=>  key(a) < key(b) for non-NaN); NaN -> max so that it never wins.
+DEODR_HD unsigned long long z_key(double z) {
+    if (z != z) return ~0ull;
+#if defined(__CUDA_ARCH__)
+    unsigned long long b = (unsigned long long)__double_as_longlong(z);
+#else
+    union { double d; unsigned long long u; } c; c.d = z; unsigned long long b = c.u;
+#endif
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+DEODR_HD double key_z(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    union { double d; unsigned long long u; } c; c.u = b; return c.d;
+#endif
+}
+
+constexpr unsigned long long Z_KEY_INF = 0xfff0000000000000ull;  // z_key(+inf)
+
+DEODR_HD void phase_tilez_init(int tid, TileZ *tz) {
+    tz->key[tid] = Z_KEY_INF;
+    tz->own[tid] = 0x7fffffff;
+    tz->bown[tid] = -1;
+}
+
+DEODR_HD double prerec_z(const PreRec &r, int x, int y, bool persp) {
+    double z = plane_at(r.zp, plane_row(r.zp, y), x);
+    return persp ? DDIV(1.0, z) : z;
+}
+
+// pass A (which == 0) / pass B (which == 1) of thread tid < n over record pre[tid]
+template <class Env>
+DEODR_HD void phase_small_pass(const SceneView &s, int tid, int n, const PreRec *pre, Tile tile, TileZ *tz, int which) {
+    if (tid >= n) return;
     const PreRec &r = pre[tid];
-    for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = r.mask[p];
-    TriRec &rec = sh->tri.rec[tid];
-    rec.zp[0] = r.zp[0]; rec.zp[1] = r.zp[1]; rec.zp[2] = r.zp[2];
-    rec.id = r.id;
+    const bool persp = s.perspective_correct != 0;
+    for (int p = 0; p < TS / 2; p++) {
+        uint32_t m = r.mask[p];
+        while (m) {
+            const int b = lowest_bit(m);
+            m &= m - 1;
+            const int pix = p * 32 + b;  // == thread index of the pixel: col b % 16, row 2p + b / 16
+            const double z = prerec_z(r, tile.x0 + (b & 15), tile.y0 + 2 * p + (b >> 4), persp);
+            if (which == 0) {
+                Env::atomic_min(&tz->key[pix], z_key(z));
+            } else if (z == key_z(tz->key[pix])) {
+                Env::atomic_min(&tz->own[pix], r.id);
+                Env::atomic_max(&tz->bown[pix], r.id);
+            }
+        }
+    }
+}
+
+// hands the shared-memory result over to the pixel threads (registers)
+template <int MAXC>
+DEODR_HD void phase_tilez_read(int tid, const TileZ *tz, PixelState<MAXC> *p) {
+    if (tz->bown[tid] >= 0) {
+        p->z = key_z(tz->key[tid]);
+        p->own = tz->own[tid];
+        p->bown = tz->bown[tid];
+    }
 }
 
 // Phase T1b: thread tid < n sets up LARGE triangle list[tid] (stencil equations stay in registers) and writes its z

@@ -375,6 +375,14 @@ DEODR_HD void edge_row_span(const EdgeGeom &g, int width, int y, int *x_begin, i
     *x_end = xe;
 }
 
+DEODR_HD int lowest_bit(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+
 // sort key: radix-ascending order of this key == descending order of the depth sum (DR.h:2656-2662, 2781)
 DEODR_HD uint64_t depth_desc_key(double s) {
 #if defined(__CUDA_ARCH__)

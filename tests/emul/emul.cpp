@@ -19,6 +19,9 @@ using namespace deodr;
 struct HostEnv {
     static int atomic_add(int *p, int v) { int old = *p; *p += v; return old; }
     static void atomic_add(float *p, float v) { *p += v; }
+    static void atomic_min(unsigned long long *p, unsigned long long v) { if (v < *p) *p = v; }
+    static void atomic_min(int *p, int v) { if (v < *p) *p = v; }
+    static void atomic_max(int *p, int v) { if (v > *p) *p = v; }
     static void atomic_add(double *p, double v) { *p += v; }
     void emit(float *p, float v) const { *p += v; }
 };
@@ -51,12 +54,17 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
         for (int tid = 0; tid < NT; tid++) { px[tid].z = std::numeric_limits<double>::infinity(); px[tid].own = px[tid].bown = -1; }
         auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
         const int n_small = st.small_cursor[tile_id];
-        for (int base = 0; base < n_small; base += TRI_CHUNK) {
-            const int m = std::min(TRI_CHUNK, n_small - base);
-            // the device pulls the chunk into sh->tri.pre with one bulk copy; same bytes here
-            memcpy(sh->tri.pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
-            for (int tid = 0; tid < NT; tid++) phase_pre_unpack(tid, m, sh->tri.pre, sh);
-            for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<MAXC>(s, tid, m, tile, sh, &px[tid]);
+        if (n_small > 0) {
+            for (int tid = 0; tid < NT; tid++) phase_tilez_init(tid, &sh->z);
+            for (int pass = 0; pass < 2; pass++)
+                for (int base = 0; base < n_small; base += TRI_CHUNK) {
+                    const int m = std::min(TRI_CHUNK, n_small - base);
+                    // the device pulls the chunk into sh->pre with one bulk copy; same bytes here
+                    memcpy(sh->pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
+                    for (int tid = NT - 1; tid >= 0; tid--)  // reversed: the result must not depend on the order
+                        phase_small_pass<HostEnv>(s, tid, m, sh->pre, tile, &sh->z, pass);
+                }
+            for (int tid = 0; tid < NT; tid++) phase_tilez_read<MAXC>(tid, &sh->z, &px[tid]);
         }
         const int n_large = st.large_count[tile_id];
         for (int base = 0; base < n_large; base += TRI_CHUNK) {
