@@ -150,7 +150,7 @@ struct TriBins {
 // "small" = micro-triangle: few tiles AND few pixels, so that one thread can afford to walk it (fill pass, adjoint)
 constexpr int SMALL_PIXELS = 64;
 DEODR_HD bool is_small(const TileBox &b, int pixel_area) {
-    return (b.tx1 - b.tx0 + 1) * (b.ty1 - b.ty0 + 1) <= SMALL_TILES && pixel_area <= SMALL_PIXELS;
+    return b.tx1 - b.tx0 <= 1 && b.ty1 - b.ty0 <= 1 && pixel_area <= SMALL_PIXELS;  // at most 2 x 2 tiles
 }
 
 // Compacted index lists of the drawn triangles, appended by the count pass (arbitrary order): the fill pass and the
@@ -240,6 +240,23 @@ DEODR_HD void bin_fill_large(const SceneView &s, int k, int tiles_x, TriBins bin
 }
 
 // Fill pass, one thread per entry of the small list: exact coverage masks of every tile the triangle really covers.
+// SIMT note: the loop runs over the triangle's ROWS (consecutive for every lane, so the lanes of a warp execute the
+// expensive span body together) and scatters each span into the masks of the <= 2 tile columns; a (tile, row-pair)
+// loop would make every lane wait for the bodies of all the others.
+template <class Env>
+DEODR_HD void bin_flush_small(int k, const TriGeom &g, int tiles_x, int tx, int ty, const uint32_t *mask, TriBins bins) {
+    uint32_t any = 0;
+    for (int p = 0; p < TS / 2; p++) any |= mask[p];
+    if (!any) return;  // the bounding box touches the tile, the triangle does not
+    PreRec rec;
+    for (int p = 0; p < TS / 2; p++) rec.mask[p] = mask[p];
+    rec.zp[0] = g.zp[0]; rec.zp[1] = g.zp[1]; rec.zp[2] = g.zp[2];
+    rec.id = k | SMALL_FLAG;
+    rec.pad = 0;
+    const int t = ty * tiles_x + tx;
+    bins.small_recs[bins.small_offset[t] + Env::atomic_add(&bins.small_cursor[t], 1)] = rec;
+}
+
 template <class Env>
 DEODR_HD void bin_fill_small(const SceneView &s, int k, int tiles_x, TriBins bins) {
     uint32_t vid[3];
@@ -251,21 +268,34 @@ DEODR_HD void bin_fill_small(const SceneView &s, int k, int tiles_x, TriBins bin
     tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
     int y_first, y_last;
     tri_row_range(g, s.height, &y_first, &y_last);
-    for (int ty = b.ty0; ty <= b.ty1; ty++)
-        for (int tx = b.tx0; tx <= b.tx1; tx++) {
-            PreRec rec;
-            uint32_t any = 0;
-            for (int p = 0; p < TS / 2; p++) {
-                rec.mask[p] = tri_pair_mask(s, g, y_first, y_last, tx * TS, ty * TS, p);
-                any |= rec.mask[p];
+    uint32_t mask[2][TS / 2];
+    for (int c = 0; c < 2; c++)
+        for (int p = 0; p < TS / 2; p++) mask[c][p] = 0u;
+    int cur_ty = y_first >> 4;
+    for (int y = y_first; y <= y_last; y++) {
+        const int ty = y >> 4;
+        if (ty != cur_ty) {
+            for (int c = 0; c < 2; c++) {
+                if (b.tx0 + c <= b.tx1) bin_flush_small<Env>(k, g, tiles_x, b.tx0 + c, cur_ty, mask[c], bins);
+                for (int p = 0; p < TS / 2; p++) mask[c][p] = 0u;
             }
-            if (!any) continue;  // bounding box touches the tile, the triangle does not
-            rec.zp[0] = g.zp[0]; rec.zp[1] = g.zp[1]; rec.zp[2] = g.zp[2];
-            rec.id = k | SMALL_FLAG;
-            rec.pad = 0;
-            int t = ty * tiles_x + tx;
-            bins.small_recs[bins.small_offset[t] + Env::atomic_add(&bins.small_cursor[t], 1)] = rec;
+            cur_ty = ty;
         }
+        int xb, xe;
+        tri_row_span(g, y, s.width, s.height, s.strict_edge != 0, &xb, &xe);
+        if (xb > xe) continue;
+        const int p = (y & (TS - 1)) >> 1, shift = (y & 1) * 16;
+        for (int c = 0; c < 2; c++) {
+            const int x0 = (b.tx0 + c) * TS;
+            int lb = xb - x0, le = xe - x0;
+            if (lb < 0) lb = 0;
+            if (le > TS - 1) le = TS - 1;
+            if (lb <= le) mask[c][p] |= (((1u << (le - lb + 1)) - 1u) << lb) << shift;
+        }
+    }
+    if (y_first <= y_last)
+        for (int c = 0; c < 2; c++)
+            if (b.tx0 + c <= b.tx1) bin_flush_small<Env>(k, g, tiles_x, b.tx0 + c, cur_ty, mask[c], bins);
 }
 
 // Far-to-near rank of appended edge i = number of edges that precede it in the reference order: descending depth sum
@@ -619,12 +649,11 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
                                      const int *owner, const int *tie_pairs, const float *image_b, float *ij_b,
                                      float *colors_b, float *uv_b, float *shade_b, float *texture_b) {
     const int C = s.nb_colors;
-    TriAttr t;
-    tri_attr(s, k, &t);
     double V[3][2];
     for (int i = 0; i < 3; i++) {
-        V[i][0] = s.ij[2 * (size_t)t.vid[i]];
-        V[i][1] = s.ij[2 * (size_t)t.vid[i] + 1];
+        const uint32_t v = s.faces[3 * k + i];
+        V[i][0] = s.ij[2 * (size_t)v];
+        V[i][1] = s.ij[2 * (size_t)v + 1];
     }
     remove_offset(V, 3, pixel_offset(s));
     int x0, x1, y0, y1;
@@ -633,23 +662,33 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
     if (y0 < 0) y0 = 0;
     if (x1 > s.width - 1) x1 = s.width - 1;
     if (y1 > s.height - 1) y1 = s.height - 1;
+    const int w = x1 - x0 + 1;  // w * h <= SMALL_PIXELS (64) by construction of the small list
     const int code = k | SMALL_FLAG;
-    VertexGrads<MAXC> acc;
-    zero_vertex_grads<MAXC>(s, &acc);
-    bool any = false;
+    // phase 1 (cheap, uniform): which pixels of the bounding box does this triangle own?  One bit per pixel.
+    unsigned long long mine = 0ull;
     for (int y = y0; y <= y1; y++)
         for (int x = x0; x <= x1; x++) {
-            const size_t idx = (size_t)y * s.width + x;
-            const int c = owner[idx];
-            const bool mine = c == code || (c <= -2 && tie_pairs[2 * (-2 - c) + 1] == code);
-            if (!mine) continue;
-            if (edge_tile_count && edge_tile_count[(y / TS) * tiles_x + x / TS] > 0) continue;
-            float g[MAXC];
-            for (int q = 0; q < C; q++) g[q] = image_b[idx * C + q];
-            pixel_adjoint<MAXC, Env>(s, t, x, y, g, &acc, texture_b);
-            any = true;
+            const int c = owner[(size_t)y * s.width + x];
+            bool hit = c == code || (c <= -2 && tie_pairs[2 * (-2 - c) + 1] == code);
+            if (hit && edge_tile_count && edge_tile_count[(y / TS) * tiles_x + x / TS] > 0) hit = false;
+            if (hit) mine |= 1ull << ((y - y0) * w + (x - x0));
         }
-    if (any) flush_vertex_grads<MAXC, AtomicEmit<Env>>(s, t, acc, ij_b, colors_b, uv_b, shade_b, AtomicEmit<Env>());
+    if (!mine) return;  // hidden triangle
+    // phase 2: lanes take their i-th owned pixel together
+    TriAttr t;
+    tri_attr(s, k, &t);
+    VertexGrads<MAXC> acc;
+    zero_vertex_grads<MAXC>(s, &acc);
+    while (mine) {
+        const int i = lowest_bit64(mine);
+        mine &= mine - 1;
+        const int y = y0 + i / w, x = x0 + i % w;
+        const size_t idx = (size_t)y * s.width + x;
+        float g[MAXC];
+        for (int q = 0; q < C; q++) g[q] = image_b[idx * C + q];
+        pixel_adjoint<MAXC, Env>(s, t, x, y, g, &acc, texture_b);
+    }
+    flush_vertex_grads<MAXC, AtomicEmit<Env>>(s, t, acc, ij_b, colors_b, uv_b, shade_b, AtomicEmit<Env>());
 }
 
 // One thread per sorted silhouette edge: turn the accumulated plane adjoints into vertex adjoints.

@@ -271,17 +271,22 @@ DEODR_HD void tri_half_span(const TriGeom &g, int half, int y, int width, bool s
 // pixel does not depend on the half the result is the union.  Both spans share the long-edge bound, so the union is
 // an interval.
 DEODR_HD void tri_row_span(const TriGeom &g, int y, int width, int height, bool strict, int *x_begin, int *x_end) {
+    // SIMT note: the half is selected as DATA (index h) so that a warp whose lanes sit in different halves still runs
+    // the expensive span body once; the second body only runs for rows that belong to both halves (rare).
+    int lo0 = g.y_begin[0] < 0 ? 0 : g.y_begin[0], hi0 = g.y_end[0] > height - 1 ? height - 1 : g.y_end[0];
+    int lo1 = g.y_begin[1] < 0 ? 0 : g.y_begin[1], hi1 = g.y_end[1] > height - 1 ? height - 1 : g.y_end[1];
+    const bool in0 = y >= lo0 && y <= hi0, in1 = y >= lo1 && y <= hi1;
     int xb = 1, xe = 0;
-    for (int half = 0; half < 2; half++) {
-        int y0 = g.y_begin[half], y1 = g.y_end[half];
-        if (y0 < 0) y0 = 0;
-        if (y1 > height - 1) y1 = height - 1;
-        if (y < y0 || y > y1) continue;
-        int b, e;
-        tri_half_span(g, half, y, width, strict, &b, &e);
-        if (b > e) continue;
-        if (xb > xe) { xb = b; xe = e; }
-        else { if (b < xb) xb = b; if (e > xe) xe = e; }
+    if (in0 || in1) {
+        tri_half_span(g, in0 ? 0 : 1, y, width, strict, &xb, &xe);
+        if (in0 && in1) {
+            int b, e;
+            tri_half_span(g, 1, y, width, strict, &b, &e);
+            if (b <= e) {
+                if (xb > xe) { xb = b; xe = e; }
+                else { if (b < xb) xb = b; if (e > xe) xe = e; }
+            }
+        }
     }
     *x_begin = xb;
     *x_end = xe;
@@ -380,6 +385,14 @@ DEODR_HD int lowest_bit(uint32_t m) {
     return __ffs((int)m) - 1;
 #else
     return __builtin_ctz(m);
+#endif
+}
+
+DEODR_HD int lowest_bit64(unsigned long long m) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)m) - 1;
+#else
+    return __builtin_ctzll(m);
 #endif
 }
 

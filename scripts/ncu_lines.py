@@ -49,5 +49,7 @@ by_file = collections.Counter()
 for (f, ln), v in agg.items():
     by_file[f] += v
 print({k: f"{100 * v / tot:.1f}%" for k, v in by_file.most_common()})
-for (f, ln), v in agg.most_common(40):
+order = samp.most_common(40) if len(sys.argv) > 5 else agg.most_common(40)
+for (f, ln), _ in order:
+    v = agg[(f, ln)]
     print(f"{f}:{ln:<5d} inst {100 * v / tot:5.1f}%   stall-samples {100 * samp[(f, ln)] / max(tots, 1):5.1f}%")
