@@ -230,20 +230,19 @@ struct TieTable {
     int capacity;
 };
 
-template <int MAXC>
-__global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, int tiles_x, TriBins bins,
-                                                   const int *edge_count, const int *edge_offset,
-                                                   const int *edge_refs, const int *edge_sorted, TieTable ties,
-                                                   float *image, double *z_buffer, int *owner, int *face_id) {
+// Forward, kernel 1 of 3 - z-buffer and owner ids of one 16x16 tile (no colour work: few registers, short critical
+// path).  Small triangles: triangle-parallel on a shared-memory tile z-buffer fed by TMA bulk copies; large triangles:
+// pixel-parallel over per-row-pair coverage masks.
+__global__ void __launch_bounds__(NT) k_tile_z(SceneView s, int tiles_x, TriBins bins, TieTable ties, double *z_buffer,
+                                               int *owner, int *face_id) {
     __shared__ TileShared sh;
     __shared__ alignas(8) uint64_t list_barrier;
     const int tile_id = blockIdx.x, tid = threadIdx.x;
     const Tile tile = tile_of(tile_id, tiles_x);
-    const int c = tid % TS, r = tid / TS;
-    const int x = tile.x0 + c, y = tile.y0 + r;
+    const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
     const bool inside = x < s.width && y < s.height;
 
-    PixelState<MAXC> p;
+    PixelState<1> p;
     p.z = __longlong_as_double(0x7ff0000000000000LL);
     p.own = -1;
     p.bown = -1;
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, in
                 __syncthreads();
             }
         }
-        phase_tilez_read<MAXC>(tid, &sh.z, &p);
+        phase_tilez_read<1>(tid, &sh.z, &p);
         __syncthreads();  // sh.pre is about to be reused by the large-triangle records
     }
     // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
@@ -285,29 +284,13 @@ __global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, in
             const int m = min(TRI_CHUNK, n_large - base);
             phase_tri_setup(s, tid, m, list + base, tile, &sh);
             __syncthreads();
-            if (inside) phase_tri_test<MAXC>(s, tid, m, tile, &sh, &p);
-            __syncthreads();
-        }
-    }
-    if (inside) phase_shade<MAXC>(s, x, y, &p);
-
-    const int n_edge = edge_count ? edge_count[tile_id] : 0;
-    if (n_edge > 0) {
-        const int edge_base = edge_offset[tile_id];
-        for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
-            const int m = min(EDGE_CHUNK, n_edge - base);
-            phase_edge_setup(s, tid, m, edge_refs + edge_base + base, edge_sorted, sigma, &sh);
-            __syncthreads();
-            phase_edge_spans(s, tid, m, tile, &sh);
-            __syncthreads();
-            if (inside) phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
+            if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
             __syncthreads();
         }
     }
     if (!inside) return;
     const size_t idx = (size_t)y * s.width + x;
     z_buffer[idx] = p.z;
-    for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
     int code = p.bown;
     if (p.own != p.bown) {  // exact z tie between distinct triangles: keep both ids in the side table
         int slot = atomicAdd(ties.counter, 1);
@@ -319,6 +302,67 @@ __global__ void __launch_bounds__(NT) k_raster_fwd(SceneView s, double sigma, in
     }
     owner[idx] = code;
     if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
+}
+
+// decodes an owner code into (forward owner, adjoint owner); -1 = background
+static __device__ __forceinline__ void decode_owner(int code, const TieTable &ties, int *own, int *bown) {
+    if (code <= -2) {
+        *own = ties.pairs[2 * (-2 - code)];
+        *bown = ties.pairs[2 * (-2 - code) + 1];
+    } else {
+        *own = *bown = code;
+    }
+}
+
+// Forward, kernel 2 of 3 - colour of every pixel from its owner (one thread per pixel, tile-shaped blocks for
+// locality of the vertex gathers).  Reads owner (and z with perspective_correct), writes image.
+template <int MAXC>
+__global__ void __launch_bounds__(NT) k_shade(SceneView s, int tiles_x, TieTable ties, const int *owner,
+                                              const double *z_buffer, float *image) {
+    const Tile tile = tile_of(blockIdx.x, tiles_x);
+    const int x = tile.x0 + threadIdx.x % TS, y = tile.y0 + threadIdx.x / TS;
+    if (x >= s.width || y >= s.height) return;
+    const size_t idx = (size_t)y * s.width + x;
+    PixelState<MAXC> p;
+    decode_owner(owner[idx], ties, &p.own, &p.bown);
+    p.z = s.perspective_correct && p.own >= 0 ? z_buffer[idx] : 0.0;
+    phase_shade<MAXC>(s, x, y, &p);
+    for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
+}
+
+// Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
+template <int MAXC>
+__global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_count,
+                                                 const int *edge_offset, const int *edge_refs, const int *edge_sorted,
+                                                 const double *z_buffer, float *image) {
+    __shared__ TileShared sh;
+    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const int n_edge = edge_count[tile_id];
+    if (n_edge == 0) return;
+    const Tile tile = tile_of(tile_id, tiles_x);
+    const int r = tid / TS;
+    const int x = tile.x0 + tid % TS, y = tile.y0 + r;
+    const bool inside = x < s.width && y < s.height;
+    const size_t idx = inside ? (size_t)y * s.width + x : 0;
+    PixelState<MAXC> p;
+    p.z = 0.0;
+    p.own = p.bown = -1;
+    if (inside) {
+        p.z = z_buffer[idx];
+        for (int k = 0; k < s.nb_colors; k++) p.col[k] = image[idx * s.nb_colors + k];
+    }
+    const int edge_base = edge_offset[tile_id];
+    for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
+        const int m = min(EDGE_CHUNK, n_edge - base);
+        phase_edge_setup(s, tid, m, edge_refs + edge_base + base, edge_sorted, sigma, &sh);
+        __syncthreads();
+        phase_edge_spans(s, tid, m, tile, &sh);
+        __syncthreads();
+        if (inside) phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
+        __syncthreads();
+    }
+    if (inside)
+        for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
 }
 
 template <int MAXC>
@@ -485,9 +529,14 @@ static inline int grid_for(size_t n, int block) { return (int)((n + block - 1) /
 template <int MAXC>
 static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
                        float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
-    k_raster_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->bins, edge_count,
-                                                     ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
-                                                     ws->edge_sorted.as<int>(), ties, image, z, owner, face_id);
+    k_tile_z<<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ws->bins, ties, z, owner, face_id);
+    k_shade<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ties, owner, z, image);
+    ws->launches += 2;
+    if (edge_count) {
+        k_edge_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
+                                                       ws->edge_refs.as<int>(), ws->edge_sorted.as<int>(), z, image);
+        ws->launches++;
+    }
 }
 
 template <int MAXC>
@@ -807,7 +856,6 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     else if (C <= 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
     else if (C <= 4) launch_fwd<4>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
     else launch_fwd<16>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
-    ws->launches++;
     }
     CUDA_TRY(cudaGetLastError());
     ws->sigma = sigma;

@@ -380,19 +380,24 @@ DEODR_HD void phase_small_pass(const SceneView &s, int tid, int n, const PreRec 
     if (tid >= n) return;
     const PreRec &r = pre[tid];
     const bool persp = s.perspective_correct != 0;
-    for (int p = 0; p < TS / 2; p++) {
-        uint32_t m = r.mask[p];
-        while (m) {
-            const int b = lowest_bit(m);
-            m &= m - 1;
-            const int pix = p * 32 + b;  // == thread index of the pixel: col b % 16, row 2p + b / 16
-            const double z = prerec_z(r, tile.x0 + (b & 15), tile.y0 + 2 * p + (b >> 4), persp);
-            if (which == 0) {
-                Env::atomic_min(&tz->key[pix], z_key(z));
-            } else if (z == key_z(tz->key[pix])) {
-                Env::atomic_min(&tz->own[pix], r.id);
-                Env::atomic_max(&tz->bown[pix], r.id);
-            }
+    // SIMT note: one flat loop over the set bits of all 8 masks, so that the lanes of a warp run the body together
+    // whatever row pairs their triangles sit in (a per-row-pair loop would serialise them).
+    int p = 0;
+    uint32_t m = r.mask[0];
+    for (;;) {
+        while (m == 0u) {
+            if (++p == TS / 2) return;
+            m = r.mask[p];
+        }
+        const int b = lowest_bit(m);
+        m &= m - 1;
+        const int pix = p * 32 + b;  // == thread index of the pixel: col b % 16, row 2p + b / 16
+        const double z = prerec_z(r, tile.x0 + (b & 15), tile.y0 + 2 * p + (b >> 4), persp);
+        if (which == 0) {
+            Env::atomic_min(&tz->key[pix], z_key(z));
+        } else if (z == key_z(tz->key[pix])) {
+            Env::atomic_min(&tz->own[pix], r.id);
+            Env::atomic_max(&tz->bown[pix], r.id);
         }
     }
 }

@@ -44,66 +44,97 @@ static void scan_tiles(const std::vector<int> &count, std::vector<int> &offset) 
     offset[count.size()] = run;
 }
 
+static void decode_owner(int code, const EmulState &st, int *own, int *bown) {
+    if (code <= -2) { *own = st.tie_pairs[2 * (-2 - code)]; *bown = st.tie_pairs[2 * (-2 - code) + 1]; }
+    else *own = *bown = code;
+}
+
+// k_tile_z + k_shade<MAXC> + k_edge_fwd<MAXC>
 template <int MAXC>
 static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *image, double *z_buffer, int *owner,
                        int *face_id) {
-    std::vector<PixelState<MAXC>> px(NT);
     TileShared *sh = new TileShared;
-    for (int tile_id = 0; tile_id < st.nt; tile_id++) {
-        const Tile tile = tile_of(tile_id, st.tiles_x);
-        for (int tid = 0; tid < NT; tid++) { px[tid].z = std::numeric_limits<double>::infinity(); px[tid].own = px[tid].bown = -1; }
-        auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
-        const int n_small = st.small_cursor[tile_id];
-        if (n_small > 0) {
-            for (int tid = 0; tid < NT; tid++) phase_tilez_init(tid, &sh->z);
-            for (int pass = 0; pass < 2; pass++)
-                for (int base = 0; base < n_small; base += TRI_CHUNK) {
-                    const int m = std::min(TRI_CHUNK, n_small - base);
-                    // the device pulls the chunk into sh->pre with one bulk copy; same bytes here
-                    memcpy(sh->pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
-                    for (int tid = NT - 1; tid >= 0; tid--)  // reversed: the result must not depend on the order
-                        phase_small_pass<HostEnv>(s, tid, m, sh->pre, tile, &sh->z, pass);
-                }
-            for (int tid = 0; tid < NT; tid++) phase_tilez_read<MAXC>(tid, &sh->z, &px[tid]);
-        }
-        const int n_large = st.large_count[tile_id];
-        for (int base = 0; base < n_large; base += TRI_CHUNK) {
-            const int m = std::min(TRI_CHUNK, n_large - base);
-            for (int tid = 0; tid < NT; tid++)
-                phase_tri_setup(s, tid, m, st.large_refs.data() + st.large_offset[tile_id] + base, tile, sh);
-            for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<MAXC>(s, tid, m, tile, sh, &px[tid]);
-        }
-        for (int tid = 0; tid < NT; tid++)
-            if (inside(tid)) phase_shade<MAXC>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, &px[tid]);
-        const int n_edge = st.E > 0 ? st.edge_count[tile_id] : 0;
-        if (n_edge > 0) {
-            const int edge_base = st.edge_offset[tile_id];
-            for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
-                const int m = std::min(EDGE_CHUNK, n_edge - base);
-                for (int tid = 0; tid < NT; tid++)
-                    phase_edge_setup(s, tid, m, st.edge_refs.data() + edge_base + base, st.edge_sorted.data(), sigma, sh);
-                for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
-                for (int tid = 0; tid < NT; tid++)
-                    if (inside(tid))
-                        phase_edge_blend<MAXC>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, tid / TS, m, sh, &px[tid]);
+    // ---- k_tile_z
+    {
+        std::vector<PixelState<1>> px(NT);
+        for (int tile_id = 0; tile_id < st.nt; tile_id++) {
+            const Tile tile = tile_of(tile_id, st.tiles_x);
+            for (int tid = 0; tid < NT; tid++) { px[tid].z = std::numeric_limits<double>::infinity(); px[tid].own = px[tid].bown = -1; }
+            auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
+            const int n_small = st.small_cursor[tile_id];
+            if (n_small > 0) {
+                for (int tid = 0; tid < NT; tid++) phase_tilez_init(tid, &sh->z);
+                for (int pass = 0; pass < 2; pass++)
+                    for (int base = 0; base < n_small; base += TRI_CHUNK) {
+                        const int m = std::min(TRI_CHUNK, n_small - base);
+                        // the device pulls the chunk into sh->pre with one bulk copy; same bytes here
+                        memcpy(sh->pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
+                        for (int tid = NT - 1; tid >= 0; tid--)  // reversed: the result must not depend on the order
+                            phase_small_pass<HostEnv>(s, tid, m, sh->pre, tile, &sh->z, pass);
+                    }
+                for (int tid = 0; tid < NT; tid++) phase_tilez_read<1>(tid, &sh->z, &px[tid]);
             }
+            const int n_large = st.large_count[tile_id];
+            for (int base = 0; base < n_large; base += TRI_CHUNK) {
+                const int m = std::min(TRI_CHUNK, n_large - base);
+                for (int tid = 0; tid < NT; tid++)
+                    phase_tri_setup(s, tid, m, st.large_refs.data() + st.large_offset[tile_id] + base, tile, sh);
+                for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<1>(s, tid, m, tile, sh, &px[tid]);
+            }
+            for (int tid = 0; tid < NT; tid++) {
+                if (!inside(tid)) continue;
+                const size_t idx = (size_t)(tile.y0 + tid / TS) * s.width + tile.x0 + tid % TS;
+                const PixelState<1> &p = px[tid];
+                z_buffer[idx] = p.z;
+                int code = p.bown;
+                if (p.own != p.bown) {
+                    int slot = (int)st.tie_pairs.size() / 2;
+                    st.tie_pairs.push_back(p.own);
+                    st.tie_pairs.push_back(p.bown);
+                    code = -2 - slot;
+                }
+                owner[idx] = code;
+                if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
+            }
+        }
+    }
+    // ---- k_shade
+    for (int y = 0; y < s.height; y++)
+        for (int x = 0; x < s.width; x++) {
+            const size_t idx = (size_t)y * s.width + x;
+            PixelState<MAXC> p;
+            decode_owner(owner[idx], st, &p.own, &p.bown);
+            p.z = s.perspective_correct && p.own >= 0 ? z_buffer[idx] : 0.0;
+            phase_shade<MAXC>(s, x, y, &p);
+            for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
+        }
+    // ---- k_edge_fwd
+    std::vector<PixelState<MAXC>> px(NT);
+    for (int tile_id = 0; tile_id < st.nt && st.E > 0; tile_id++) {
+        const int n_edge = st.edge_count[tile_id];
+        if (n_edge == 0) continue;
+        const Tile tile = tile_of(tile_id, st.tiles_x);
+        auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
+        for (int tid = 0; tid < NT; tid++) {
+            if (!inside(tid)) continue;
+            const size_t idx = (size_t)(tile.y0 + tid / TS) * s.width + tile.x0 + tid % TS;
+            px[tid].z = z_buffer[idx];
+            for (int k = 0; k < s.nb_colors; k++) px[tid].col[k] = image[idx * s.nb_colors + k];
+        }
+        const int edge_base = st.edge_offset[tile_id];
+        for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
+            const int m = std::min(EDGE_CHUNK, n_edge - base);
+            for (int tid = 0; tid < NT; tid++)
+                phase_edge_setup(s, tid, m, st.edge_refs.data() + edge_base + base, st.edge_sorted.data(), sigma, sh);
+            for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
+            for (int tid = 0; tid < NT; tid++)
+                if (inside(tid))
+                    phase_edge_blend<MAXC>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, tid / TS, m, sh, &px[tid]);
         }
         for (int tid = 0; tid < NT; tid++) {
             if (!inside(tid)) continue;
-            const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
-            const size_t idx = (size_t)y * s.width + x;
-            const PixelState<MAXC> &p = px[tid];
-            z_buffer[idx] = p.z;
-            for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
-            int code = p.bown;
-            if (p.own != p.bown) {
-                int slot = (int)st.tie_pairs.size() / 2;
-                st.tie_pairs.push_back(p.own);
-                st.tie_pairs.push_back(p.bown);
-                code = -2 - slot;
-            }
-            owner[idx] = code;
-            if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
+            const size_t idx = (size_t)(tile.y0 + tid / TS) * s.width + tile.x0 + tid % TS;
+            for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = px[tid].col[k];
         }
     }
     delete sh;
