@@ -34,9 +34,6 @@ using namespace deodr;
 
 struct DevEnv {
     static __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
-    static __device__ __forceinline__ void atomic_min(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
-    static __device__ __forceinline__ void atomic_min(int *p, int v) { atomicMin(p, v); }
-    static __device__ __forceinline__ void atomic_max(int *p, int v) { atomicMax(p, v); }
     static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
     static __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
 };
@@ -154,6 +151,12 @@ __global__ void k_scatter_edges(EdgeList edges, int n, const int *rank, int *edg
     if (i < n) edge_sorted[rank[i]] = edges.ids[i];
 }
 
+// One thread per silhouette edge (far-to-near rank r): band stencil of DR.h:1366-1460 + z plane, once per forward.
+__global__ void k_edge_records(SceneView s, const int *edge_sorted, int n, double sigma, EdgeRec *recs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) edge_record(s, edge_sorted[r], r, sigma, &recs[r]);
+}
+
 // Fill pass over the compacted lists: blocks [0, small_blocks) small triangles (pre-masked records), then large
 // triangles (indices), then silhouette edges (ranks).
 __global__ void k_bin_fill(SceneView s, double sigma, int tiles_x, int small_blocks, int large_blocks, TriBins bins,
@@ -233,7 +236,7 @@ struct TieTable {
 // Forward, kernel 1 of 3 - z-buffer and owner ids of one 16x16 tile (no colour work: few registers, short critical
 // path).  Small triangles: triangle-parallel on a shared-memory tile z-buffer fed by TMA bulk copies; large triangles:
 // pixel-parallel over per-row-pair coverage masks.
-__global__ void __launch_bounds__(NT) k_tile_z(SceneView s, int tiles_x, TriBins bins, TieTable ties, double *z_buffer,
+__global__ void __launch_bounds__(NT, 4) k_tile_z(SceneView s, int tiles_x, TriBins bins, TieTable ties, double *z_buffer,
                                                int *owner, int *face_id) {
     __shared__ TileShared sh;
     __shared__ alignas(8) uint64_t list_barrier;
@@ -248,33 +251,27 @@ __global__ void __launch_bounds__(NT) k_tile_z(SceneView s, int tiles_x, TriBins
     p.bown = -1;
 
     // small triangles: the tile's pre-masked records are one contiguous array; each chunk is pulled into shared
-    // memory by a single bulk (TMA) copy issued by thread 0 and awaited by everybody on an mbarrier.  Thread t then
-    // owns record t: pass A takes the z minimum per pixel, pass B resolves the owner ids (phases.h).
+    // memory by a single bulk (TMA) copy issued by thread 0 and awaited by everybody on an mbarrier, then transposed
+    // into the row-pair-major mask layout and z-tested by the pixel threads
     const int n_small = bins.small_cursor[tile_id];
     if (n_small > 0) {
         const PreRec *list = bins.small_recs + bins.small_offset[tile_id];
         if (tid == 0) mbar_init(&list_barrier, 1);
-        phase_tilez_init(tid, &sh.z);
         __syncthreads();
         uint32_t parity = 0;
-        const bool one_chunk = n_small <= TRI_CHUNK;
-        for (int pass = 0; pass < 2; pass++) {
-            for (int base = 0; base < n_small; base += TRI_CHUNK) {
-                const int m = min(TRI_CHUNK, n_small - base);
-                if (pass == 0 || !one_chunk) {  // a single chunk stays resident between the two passes
-                    if (tid == 0) {
-                        mbar_expect_tx(&list_barrier, (uint32_t)(m * sizeof(PreRec)));
-                        bulk_load(sh.pre, list + base, (uint32_t)(m * sizeof(PreRec)), &list_barrier);
-                    }
-                    mbar_wait(&list_barrier, parity);
-                    parity ^= 1u;
-                }
-                phase_small_pass<DevEnv>(s, tid, m, sh.pre, tile, &sh.z, pass);
-                __syncthreads();
+        for (int base = 0; base < n_small; base += TRI_CHUNK) {
+            const int m = min(TRI_CHUNK, n_small - base);
+            if (tid == 0) {
+                mbar_expect_tx(&list_barrier, (uint32_t)(m * sizeof(PreRec)));
+                bulk_load(sh.tri.pre, list + base, (uint32_t)(m * sizeof(PreRec)), &list_barrier);
             }
+            mbar_wait(&list_barrier, parity);
+            parity ^= 1u;
+            phase_pre_unpack(tid, m, sh.tri.pre, &sh);
+            __syncthreads();
+            if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
+            __syncthreads();
         }
-        phase_tilez_read<1>(tid, &sh.z, &p);
-        __syncthreads();  // sh.pre is about to be reused by the large-triangle records
     }
     // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
     const int n_large = bins.large_count[tile_id];
@@ -333,8 +330,8 @@ __global__ void __launch_bounds__(NT) k_shade(SceneView s, int tiles_x, TieTable
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
 template <int MAXC>
 __global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_count,
-                                                 const int *edge_offset, const int *edge_refs, const int *edge_sorted,
-                                                 const double *z_buffer, float *image) {
+                                                 const int *edge_offset, const int *edge_refs,
+                                                 const EdgeRec *edge_recs, const double *z_buffer, float *image) {
     __shared__ TileShared sh;
     const int tile_id = blockIdx.x, tid = threadIdx.x;
     const int n_edge = edge_count[tile_id];
@@ -354,7 +351,7 @@ __global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int 
     const int edge_base = edge_offset[tile_id];
     for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
         const int m = min(EDGE_CHUNK, n_edge - base);
-        phase_edge_setup(s, tid, m, edge_refs + edge_base + base, edge_sorted, sigma, &sh);
+        phase_edge_setup(tid, m, edge_refs + edge_base + base, edge_recs, &sh);
         __syncthreads();
         phase_edge_spans(s, tid, m, tile, &sh);
         __syncthreads();
@@ -368,7 +365,7 @@ __global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int 
 template <int MAXC>
 __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_count,
                                                    const int *edge_offset, const int *edge_refs,
-                                                   const int *edge_sorted, TieTable ties, const double *z_buffer,
+                                                   const EdgeRec *edge_recs, TieTable ties, const double *z_buffer,
                                                    const int *owner, const float *image_b, DeodrGrads grads,
                                                    double *edge_acc) {
     __shared__ TileShared sh;
@@ -405,7 +402,7 @@ __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, in
         // pass A: forward replay (far to near) to obtain the final colour in fp64
         for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
             const int m = min(EDGE_CHUNK, n_edge - base);
-            phase_edge_setup(s, tid, m, edge_refs + edge_base + base, edge_sorted, sigma, &sh);
+            phase_edge_setup(tid, m, edge_refs + edge_base + base, edge_recs, &sh);
             __syncthreads();
             phase_edge_spans(s, tid, m, tile, &sh);
             __syncthreads();
@@ -421,7 +418,7 @@ __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, in
             const int last = ((n_edge - 1) / EDGE_CHUNK) * EDGE_CHUNK;
             for (int base = last; base >= 0; base -= EDGE_CHUNK) {
                 const int m = min(EDGE_CHUNK, n_edge - base);
-                phase_edge_setup(s, tid, m, edge_refs + edge_base + base, edge_sorted, sigma, &sh);
+                phase_edge_setup(tid, m, edge_refs + edge_base + base, edge_recs, &sh);
                 __syncthreads();
                 phase_edge_spans(s, tid, m, tile, &sh);
                 __syncthreads();
@@ -529,12 +526,19 @@ static inline int grid_for(size_t n, int block) { return (int)((n + block - 1) /
 template <int MAXC>
 static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
                        float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
-    k_tile_z<<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ws->bins, ties, z, owner, face_id);
-    k_shade<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ties, owner, z, image);
+    {
+        PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
+        k_tile_z<<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ws->bins, ties, z, owner, face_id);
+    }
+    {
+        PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
+        k_shade<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ties, owner, z, image);
+    }
     ws->launches += 2;
     if (edge_count) {
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
         k_edge_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
-                                                       ws->edge_refs.as<int>(), ws->edge_sorted.as<int>(), z, image);
+                                                       ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), z, image);
         ws->launches++;
     }
 }
@@ -543,18 +547,21 @@ template <int MAXC>
 static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
                        const double *z, const int *owner, const float *image_b, const DeodrGrads &g, cudaStream_t st) {
     if (ws->num_small > 0) {
+        PhaseTimer timer(ws, DEODR_B200_PH_SMALL_BWD, st);
         k_small_tri_bwd<MAXC><<<grid_for(ws->num_small, 128), 128, 0, st>>>(s, ws->tiles_x, ws->small_ids.as<int>(),
                                                                            ws->num_small, edge_count, ties, owner,
                                                                            image_b, g);
         ws->launches++;
     }
     if (ws->num_large > 0) {  // pixels owned by large triangles, tiles without silhouette edges
+        PhaseTimer timer(ws, DEODR_B200_PH_INTERIOR_BWD, st);
         k_interior_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, edge_count, ties, owner, image_b, g);
         ws->launches++;
     }
     if (edge_count) {
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, st);
         k_raster_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
-                                                         ws->edge_refs.as<int>(), ws->edge_sorted.as<int>(), ties, z,
+                                                         ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), ties, z,
                                                          owner, image_b, g, ws->edge_acc.as<double>());
         ws->launches++;
     }
@@ -601,8 +608,8 @@ const char *deodr_b200_last_error(void) { return deodr_error_buffer(); }
 const char *deodr_b200_version(void) { return "deodr_b200 0.1 (sm_100a)"; }
 
 const char *deodr_b200_phase_name(int phase) {
-    static const char *names[] = {"bin_tri",    "bin_tri_fill", "edge_order",   "edge_bin",
-                                  "raster_fwd", "raster_bwd",   "edge_finalize"};
+    static const char *names[] = {"bin_count", "edge_order",    "bin_fill",     "edge_tile_sort", "tile_z",       "shade",
+                                  "edge_fwd",  "small_tri_bwd", "interior_bwd", "edge_bwd",       "edge_finalize"};
     return phase >= 0 && phase < DEODR_B200_PH_COUNT ? names[phase] : "?";
 }
 
@@ -663,7 +670,7 @@ void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
     DevBuf *bufs[] = {&ws->zeroed, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
-                      &ws->edge_ids_tmp, &ws->edge_rank,
+                      &ws->edge_ids_tmp, &ws->edge_rank, &ws->edge_recs,
                       &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
                       &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
                       &ws->tie_pairs, &ws->edge_acc, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
@@ -758,7 +765,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
 
     // ---- count pass + scans (triangles and silhouette edges together), then the ONE host read-back of the sizes
     {
-        PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI, st);
+        PhaseTimer timer(ws, DEODR_B200_PH_BIN_COUNT, st);
         CUDA_TRY(cudaMemsetAsync(scal, 0, (8 + 6 * tile_ints) * sizeof(int), st));
         if (T > 0) {
             if (check_indices) {  // checkSceneValid (DR.h:2703-2714) on the device, before any index is dereferenced
@@ -791,6 +798,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     rc |= ws->tri_refs.ensure(((size_t)large_total + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_sorted.ensure(((size_t)E + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_rank.ensure(((size_t)E + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->edge_recs.ensure(((size_t)E + 1) * sizeof(EdgeRec), &ws->bytes);
     rc |= ws->edge_refs_tmp.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_refs.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
     if (rc) return DEODR_B200_ECUDA;
@@ -826,9 +834,15 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
         }
     }
 
+    if (E > 0) {
+        k_edge_records<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), E, sigma,
+                                                         ws->edge_recs.as<EdgeRec>());
+        ws->launches++;
+    }
+
     // ---- fill pass (triangles + edges) and per-tile ordering of the edge lists
     if (T > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_BIN_TRI_FILL, st);
+        PhaseTimer timer(ws, DEODR_B200_PH_BIN_FILL, st);
         const int small_blocks = grid_for(ws->num_small, 128), large_blocks = grid_for(ws->num_large, 128),
                   edge_blocks = E > 0 ? grid_for(E, 128) : 0;
         if (small_blocks + large_blocks + edge_blocks > 0) {
@@ -840,7 +854,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
         }
     }
     if (E > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BIN, st);
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, st);
         k_sort_tile_edges<<<nt, 128, 0, st>>>(edge_count_buf, ws->edge_offset.as<int>(), ws->edge_refs_tmp.as<int>(),
                                               ws->edge_refs.as<int>());
         ws->launches++;
@@ -851,7 +865,6 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     const int *edge_count = E > 0 ? edge_count_buf : nullptr;
     const int C = s.nb_colors;
     {
-    PhaseTimer timer(ws, DEODR_B200_PH_RASTER_FWD, st);
     if (C == 1) launch_fwd<1>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
     else if (C <= 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
     else if (C <= 4) launch_fwd<4>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
@@ -897,7 +910,6 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
     TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
     const int *edge_count = E > 0 ? ws->edge_count_ptr : nullptr;
     {
-    PhaseTimer timer(ws, DEODR_B200_PH_RASTER_BWD, st);
     if (E > 0)
         CUDA_TRY(cudaMemsetAsync(ws->edge_acc.ptr, 0, (size_t)E * edge_acc_stride(C) * sizeof(double), st));
     if (C == 1) launch_bwd<1>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);

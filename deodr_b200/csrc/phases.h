@@ -43,17 +43,10 @@ constexpr int SMALL_TILES = 4;    // triangles whose bounding box spans more til
 constexpr int SMALL_FLAG = 0x40000000;
 constexpr int TRI_INDEX_MASK = 0x3fffffff;
 
-// Shared-memory z-buffer of the tile, used by the triangle-parallel pass over the small triangles.
-struct TileZ {
-    unsigned long long key[NT];  // order-preserving key of the running minimum z (z_key)
-    int own[NT];                 // min owner code among the triangles reaching the minimum z
-    int bown[NT];                // max owner code among them
-};
-
 struct TileShared {
     union {
-        PreRec pre[TRI_CHUNK];  // small triangles: bulk-copy landing zone of the pre-masked records
-        struct {                // large triangles
+        struct {
+            PreRec pre[TRI_CHUNK];  // small triangles: bulk-copy (TMA) landing zone of the pre-masked records
             TriRec rec[TRI_CHUNK];
             // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
             // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time
@@ -64,7 +57,6 @@ struct TileShared {
             uint32_t span[EDGE_CHUNK][TS];  // x_begin | x_end << 16 (absolute, int16 each); empty if begin > end
         } edge;
     };
-    TileZ z;
 };
 
 struct Tile {
@@ -250,7 +242,7 @@ DEODR_HD void bin_flush_small(int k, const TriGeom &g, int tiles_x, int tx, int 
     if (!any) return;  // the bounding box touches the tile, the triangle does not
     PreRec rec;
     for (int p = 0; p < TS / 2; p++) rec.mask[p] = mask[p];
-    rec.zp[0] = g.zp[0]; rec.zp[1] = g.zp[1]; rec.zp[2] = g.zp[2];
+    canonical_plane(g.zp, rec.zp);
     rec.id = k | SMALL_FLAG;
     rec.pad = 0;
     const int t = ty * tiles_x + tx;
@@ -332,84 +324,19 @@ struct PixelState {
     float col[MAXC];
 };
 
-// ---- small triangles: triangle-parallel z test on a shared-memory tile z-buffer ------------------------------
-// A micro-triangle covers a handful of the 256 pixels of a tile; letting the 256 pixel-threads look for it wastes the
-// machine (measured: ~40 issue slots per (record, row pair) with ~4 of 32 lanes active).  Instead thread t owns record
-// t and walks the set bits of its masks:
-//   pass A  key[pixel] = min(key[pixel], z_key(z))                      64-bit atomicMin in shared memory
-//   pass B  where z == the final minimum: own = min(own, id), bown = max(bown, id)
-// which is exactly what a strict '<' walk in ascending index order leaves (DR.h:961) and what the '==' walk in
-// descending order finds first (DR.h:1024).  z is evaluated by the same code in both passes.
-
-// Monotone map double -> uint64 (a < b  <=>  key(a) < key(b) for non-NaN); NaN -> max so that it never wins.
-DEODR_HD unsigned long long z_key(double z) {
-    if (z != z) return ~0ull;
-#if defined(__CUDA_ARCH__)
-    unsigned long long b = (unsigned long long)__double_as_longlong(z);
-#else
-    union { double d; unsigned long long u; } c; c.d = z; unsigned long long b = c.u;
-#endif
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-
-DEODR_HD double key_z(unsigned long long k) {
-    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
-#if defined(__CUDA_ARCH__)
-    return __longlong_as_double((long long)b);
-#else
-    union { double d; unsigned long long u; } c; c.u = b; return c.d;
-#endif
-}
-
-constexpr unsigned long long Z_KEY_INF = 0xfff0000000000000ull;  // z_key(+inf)
-
-DEODR_HD void phase_tilez_init(int tid, TileZ *tz) {
-    tz->key[tid] = Z_KEY_INF;
-    tz->own[tid] = 0x7fffffff;
-    tz->bown[tid] = -1;
-}
-
-DEODR_HD double prerec_z(const PreRec &r, int x, int y, bool persp) {
-    double z = plane_at(r.zp, plane_row(r.zp, y), x);
-    return persp ? DDIV(1.0, z) : z;
-}
-
-// pass A (which == 0) / pass B (which == 1) of thread tid < n over record pre[tid]
-template <class Env>
-DEODR_HD void phase_small_pass(const SceneView &s, int tid, int n, const PreRec *pre, Tile tile, TileZ *tz, int which) {
-    if (tid >= n) return;
+// Phase T1a: thread tid < n unpacks small-triangle record `pre[tid]` (pulled into shared memory by the bulk copy)
+// into the z-test layout; threads up to the next multiple of 4 write empty masks (padding).
+DEODR_HD void phase_pre_unpack(int tid, int n, const PreRec *pre, TileShared *sh) {
+    if (tid >= n) {
+        if (tid < ((n + 3) & ~3))
+            for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = 0u;
+        return;
+    }
     const PreRec &r = pre[tid];
-    const bool persp = s.perspective_correct != 0;
-    // SIMT note: one flat loop over the set bits of all 8 masks, so that the lanes of a warp run the body together
-    // whatever row pairs their triangles sit in (a per-row-pair loop would serialise them).
-    int p = 0;
-    uint32_t m = r.mask[0];
-    for (;;) {
-        while (m == 0u) {
-            if (++p == TS / 2) return;
-            m = r.mask[p];
-        }
-        const int b = lowest_bit(m);
-        m &= m - 1;
-        const int pix = p * 32 + b;  // == thread index of the pixel: col b % 16, row 2p + b / 16
-        const double z = prerec_z(r, tile.x0 + (b & 15), tile.y0 + 2 * p + (b >> 4), persp);
-        if (which == 0) {
-            Env::atomic_min(&tz->key[pix], z_key(z));
-        } else if (z == key_z(tz->key[pix])) {
-            Env::atomic_min(&tz->own[pix], r.id);
-            Env::atomic_max(&tz->bown[pix], r.id);
-        }
-    }
-}
-
-// hands the shared-memory result over to the pixel threads (registers)
-template <int MAXC>
-DEODR_HD void phase_tilez_read(int tid, const TileZ *tz, PixelState<MAXC> *p) {
-    if (tz->bown[tid] >= 0) {
-        p->z = key_z(tz->key[tid]);
-        p->own = tz->own[tid];
-        p->bown = tz->bown[tid];
-    }
+    for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = r.mask[p];
+    TriRec &rec = sh->tri.rec[tid];
+    rec.zp[0] = r.zp[0]; rec.zp[1] = r.zp[1]; rec.zp[2] = r.zp[2];
+    rec.id = r.id;
 }
 
 // Phase T1b: thread tid < n sets up LARGE triangle list[tid] (stencil equations stay in registers) and writes its z
@@ -428,7 +355,7 @@ DEODR_HD void phase_tri_setup(const SceneView &s, int tid, int n, const int *lis
     TriGeom g;
     tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
     TriRec &rec = sh->tri.rec[tid];
-    rec.zp[0] = g.zp[0]; rec.zp[1] = g.zp[1]; rec.zp[2] = g.zp[2];
+    canonical_plane(g.zp, rec.zp);
     rec.id = k;
     int y_first, y_last;
     tri_row_range(g, s.height, &y_first, &y_last);
@@ -443,6 +370,7 @@ template <int MAXC>
 DEODR_HD void phase_tri_test(const SceneView &s, int tid, int n, Tile tile, const TileShared *sh, PixelState<MAXC> *p) {
     const int lane = tid % 32, pair = tid / 32;
     const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+    const double xd = (double)x, yd = (double)y;
     const bool persp = s.perspective_correct != 0;
     for (int t0 = 0; t0 < n; t0 += 4) {
         const Mask4 m4 = *reinterpret_cast<const Mask4 *>(&sh->tri.mask[pair][t0]);
@@ -453,7 +381,7 @@ DEODR_HD void phase_tri_test(const SceneView &s, int tid, int n, Tile tile, cons
         for (int j = 0; j < 4; j++) {
             if (!((m4.m[j] >> lane) & 1u)) continue;
             const TriRec &rec = sh->tri.rec[t0 + j];
-            double z = plane_at(rec.zp, plane_row(rec.zp, y), x);
+            double z = plane_z(rec.zp, xd, yd, x, y);
             if (persp) z = DDIV(1.0, z);
             const int id = rec.id;
             if (z < p->z) { p->z = z; p->own = id; p->bown = id; }
@@ -484,12 +412,11 @@ DEODR_HD void phase_shade(const SceneView &s, int x, int y, PixelState<MAXC> *p)
     pixel_colour<MAXC>(s, t, x, y, p->z, &e, p->col);
 }
 
-// Phase E1: thread tid < n sets up the record of the edge with far-to-near rank list[tid].
-DEODR_HD void phase_edge_setup(const SceneView &s, int tid, int n, const int *list, const int *edge_sorted,
-                               double sigma, TileShared *sh) {
+// Phase E1: thread tid < n fetches the record of the edge with far-to-near rank list[tid] (records are built once per
+// forward pass by k_edge_records: stencil equations with their sqrt / divisions are not redone per tile).
+DEODR_HD void phase_edge_setup(int tid, int n, const int *list, const EdgeRec *edge_recs, TileShared *sh) {
     if (tid >= n) return;
-    int rank = list[tid];
-    edge_record(s, edge_sorted[rank], rank, sigma, &sh->edge.rec[tid]);
+    sh->edge.rec[tid] = edge_recs[list[tid]];
 }
 
 // Phase E2: (edge, row) items -> x spans.

@@ -311,6 +311,23 @@ DEODR_HD double tri_z(const TriGeom &g, int x, int y, bool persp) {
     return persp ? DDIV(1.0, z) : z;
 }
 
+// The reference evaluates Z = (((0 + zp0*0) + zp1*y) + zp2*1) + zp0*x (DR.h:934, 960).  For a finite zp0 the first
+// term is +0 and adding it only matters for the sign of an exactly-zero result; for an infinite zp0 it is NaN and so
+// is Z.  plane_z() drops the no-op terms (2 DMUL + 2 DADD per pixel instead of 4 + 4) and stays bit-identical by
+// (a) storing NaN for an infinite zp0 at record creation (canonical_plane) and (b) re-evaluating the full expression
+// when the short one returns zero.
+DEODR_HD void canonical_plane(const double *zp, double *out) {
+    out[0] = (zp[0] - zp[0] == 0.0 || zp[0] != zp[0]) ? zp[0] : (zp[0] - zp[0]);  // +-inf -> NaN
+    out[1] = zp[1];
+    out[2] = zp[2];
+}
+
+DEODR_HD double plane_z(const double *zp, double xd, double yd, int x, int y) {
+    double z = DADD(DADD(DMUL(zp[1], yd), zp[2]), DMUL(zp[0], xd));
+    if (z == 0.0) z = plane_at(zp, plane_row(zp, y), x);
+    return z;
+}
+
 // ---------------------------------------------------------------------------------------------- silhouette edges
 
 struct EdgeGeom {

@@ -147,14 +147,18 @@ int deodr_b200_check_scene(DeodrWorkspace *ws, const DeodrSceneView *scene, void
  * collect: synchronises the recorded events, writes up to `capacity` (phase, milliseconds) pairs in launch order,
  * resets the pool and returns the number of records written (negative on error). */
 enum {
-    DEODR_B200_PH_BIN_TRI = 0,      /* memsets + bin_tri(count) + scan + silhouette-edge select */
-    DEODR_B200_PH_BIN_TRI_FILL = 1, /* bin_tri(fill) */
-    DEODR_B200_PH_EDGE_ORDER = 2,   /* depth keys + stable radix sort of the silhouette edges */
-    DEODR_B200_PH_EDGE_BIN = 3,     /* bin_edge(count) + scan + bin_edge(fill) + per-tile ordering */
-    DEODR_B200_PH_RASTER_FWD = 4,   /* the forward tile kernel */
-    DEODR_B200_PH_RASTER_BWD = 5,   /* the backward tile kernel (+ accumulator memset) */
-    DEODR_B200_PH_EDGE_FINALIZE = 6,/* per-edge adjoint finalisation */
-    DEODR_B200_PH_COUNT = 7
+    DEODR_B200_PH_BIN_COUNT = 0,    /* memset + (index check) + k_bin_count + k_scan_tiles */
+    DEODR_B200_PH_EDGE_ORDER = 1,   /* k_rank_edges + k_scatter_edges (or CUB radix sorts) + k_edge_records */
+    DEODR_B200_PH_BIN_FILL = 2,     /* k_bin_fill */
+    DEODR_B200_PH_EDGE_TILE_SORT = 3,/* k_sort_tile_edges */
+    DEODR_B200_PH_TILE_Z = 4,       /* k_tile_z: z-buffer + owner ids */
+    DEODR_B200_PH_SHADE = 5,        /* k_shade: colour of every pixel */
+    DEODR_B200_PH_EDGE_FWD = 6,     /* k_edge_fwd: ordered silhouette-edge overdraw */
+    DEODR_B200_PH_SMALL_BWD = 7,    /* k_small_tri_bwd: triangle-parallel interior adjoint */
+    DEODR_B200_PH_INTERIOR_BWD = 8, /* k_interior_bwd: pixel-parallel interior adjoint (large triangles) */
+    DEODR_B200_PH_EDGE_BWD = 9,     /* accumulator memset + k_raster_bwd: tiles with silhouette edges */
+    DEODR_B200_PH_EDGE_FINALIZE = 10,/* k_finalize_edges */
+    DEODR_B200_PH_COUNT = 11
 };
 int deodr_b200_timing_enable(DeodrWorkspace *ws, int max_records);
 int deodr_b200_timing_collect(DeodrWorkspace *ws, int32_t *phase, float *ms, int capacity);

@@ -19,9 +19,6 @@ using namespace deodr;
 struct HostEnv {
     static int atomic_add(int *p, int v) { int old = *p; *p += v; return old; }
     static void atomic_add(float *p, float v) { *p += v; }
-    static void atomic_min(unsigned long long *p, unsigned long long v) { if (v < *p) *p = v; }
-    static void atomic_min(int *p, int v) { if (v < *p) *p = v; }
-    static void atomic_max(int *p, int v) { if (v > *p) *p = v; }
     static void atomic_add(double *p, double v) { *p += v; }
     void emit(float *p, float v) const { *p += v; }
 };
@@ -32,6 +29,7 @@ struct EmulState {
     std::vector<PreRec> small_recs;
     std::vector<int> small_ids, large_ids;
     std::vector<int> edge_count, edge_offset, edge_refs, edge_sorted;
+    std::vector<EdgeRec> edge_recs;
     std::vector<int> tie_pairs;
 };
 
@@ -62,17 +60,12 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
             for (int tid = 0; tid < NT; tid++) { px[tid].z = std::numeric_limits<double>::infinity(); px[tid].own = px[tid].bown = -1; }
             auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
             const int n_small = st.small_cursor[tile_id];
-            if (n_small > 0) {
-                for (int tid = 0; tid < NT; tid++) phase_tilez_init(tid, &sh->z);
-                for (int pass = 0; pass < 2; pass++)
-                    for (int base = 0; base < n_small; base += TRI_CHUNK) {
-                        const int m = std::min(TRI_CHUNK, n_small - base);
-                        // the device pulls the chunk into sh->pre with one bulk copy; same bytes here
-                        memcpy(sh->pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
-                        for (int tid = NT - 1; tid >= 0; tid--)  // reversed: the result must not depend on the order
-                            phase_small_pass<HostEnv>(s, tid, m, sh->pre, tile, &sh->z, pass);
-                    }
-                for (int tid = 0; tid < NT; tid++) phase_tilez_read<1>(tid, &sh->z, &px[tid]);
+            for (int base = 0; base < n_small; base += TRI_CHUNK) {
+                const int m = std::min(TRI_CHUNK, n_small - base);
+                // the device pulls the chunk into sh->tri.pre with one bulk (TMA) copy; same bytes here
+                memcpy(sh->tri.pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
+                for (int tid = 0; tid < NT; tid++) phase_pre_unpack(tid, m, sh->tri.pre, sh);
+                for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<1>(s, tid, m, tile, sh, &px[tid]);
             }
             const int n_large = st.large_count[tile_id];
             for (int base = 0; base < n_large; base += TRI_CHUNK) {
@@ -125,7 +118,7 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
         for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
             const int m = std::min(EDGE_CHUNK, n_edge - base);
             for (int tid = 0; tid < NT; tid++)
-                phase_edge_setup(s, tid, m, st.edge_refs.data() + edge_base + base, st.edge_sorted.data(), sigma, sh);
+                phase_edge_setup(tid, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
             for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
             for (int tid = 0; tid < NT; tid++)
                 if (inside(tid))
@@ -170,7 +163,7 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
             for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
                 const int m = std::min(EDGE_CHUNK, n_edge - base);
                 for (int tid = 0; tid < NT; tid++)
-                    phase_edge_setup(s, tid, m, st.edge_refs.data() + edge_base + base, st.edge_sorted.data(), sigma, sh);
+                    phase_edge_setup(tid, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
                 for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
                 for (int tid = 0; tid < NT; tid++) {
                     if (!inside(tid)) continue;
@@ -185,7 +178,7 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
                 for (int base = last; base >= 0; base -= EDGE_CHUNK) {
                     const int m = std::min(EDGE_CHUNK, n_edge - base);
                     for (int tid = 0; tid < NT; tid++)
-                        phase_edge_setup(s, tid, m, st.edge_refs.data() + edge_base + base, st.edge_sorted.data(), sigma, sh);
+                        phase_edge_setup(tid, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
                     for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
                     for (int tid = 0; tid < NT; tid++) {
                         if (!inside(tid) || !adj[tid].has_colour) continue;
@@ -250,6 +243,9 @@ int emul_render(const DeodrSceneView *scene, double sigma, float *image, double 
     // k_rank_edges + k_scatter_edges
     st.edge_sorted.assign(st.E, -1);
     for (int i = 0; i < st.E; i++) st.edge_sorted[edge_rank(i, st.E, keys.data(), ids.data())] = ids[i];
+    // k_edge_records
+    st.edge_recs.resize(st.E);
+    for (int r = 0; r < st.E; r++) edge_record(s, st.edge_sorted[r], r, sigma, &st.edge_recs[r]);
     // k_bin_fill (again in reversed order)
     st.small_recs.assign(st.small_offset[st.nt] + 1, PreRec());
     st.large_refs.assign(st.large_offset[st.nt] + 4, -1);
