@@ -597,28 +597,84 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
     const int w = x1 - x0 + 1;  // w * h <= SMALL_PIXELS (64) by construction of the small list
     const int code = k | SMALL_FLAG;
     // phase 1 (cheap, uniform): which pixels of the bounding box does this triangle own?  One bit per pixel.
+    // Loads of a row are independent: unrolled so that several are in flight.
     unsigned long long mine = 0ull;
-    for (int y = y0; y <= y1; y++)
+    for (int y = y0; y <= y1; y++) {
+        const int *row = owner + (size_t)y * s.width;
+        const int bit0 = (y - y0) * w - x0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
         for (int x = x0; x <= x1; x++) {
-            const int c = owner[(size_t)y * s.width + x];
-            bool hit = c == code || (c <= -2 && tie_pairs[2 * (-2 - c) + 1] == code);
-            if (hit && edge_tile_count && edge_tile_count[(y / TS) * tiles_x + x / TS] > 0) hit = false;
-            if (hit) mine |= 1ull << ((y - y0) * w + (x - x0));
+            const int c = row[x];
+            bool hit = c == code;
+            if (c <= -2) hit = tie_pairs[2 * (-2 - c) + 1] == code;
+            if (hit) mine |= 1ull << (bit0 + x);
         }
+    }
     if (!mine) return;  // hidden triangle
-    // phase 2: lanes take their i-th owned pixel together
+    if (edge_tile_count) {  // pixels of tiles with silhouette edges belong to k_raster_bwd
+        for (int ty = y0 / TS; ty <= y1 / TS; ty++)
+            for (int tx = x0 / TS; tx <= x1 / TS; tx++) {
+                if (edge_tile_count[ty * tiles_x + tx] == 0) continue;
+                for (int y = (ty * TS > y0 ? ty * TS : y0); y <= y1 && y < (ty + 1) * TS; y++)
+                    for (int x = (tx * TS > x0 ? tx * TS : x0); x <= x1 && x < (tx + 1) * TS; x++)
+                        mine &= ~(1ull << ((y - y0) * w + (x - x0)));
+            }
+        if (!mine) return;
+    }
+    // phase 2: lanes take their i-th owned pixel together; the adjoint colour of the NEXT pixel is loaded while the
+    // current one is processed
     TriAttr t;
     tri_attr(s, k, &t);
     VertexGrads<MAXC> acc;
     zero_vertex_grads<MAXC>(s, &acc);
-    while (mine) {
-        const int i = lowest_bit64(mine);
-        mine &= mine - 1;
-        const int y = y0 + i / w, x = x0 + i % w;
-        const size_t idx = (size_t)y * s.width + x;
+    // per-triangle constants of the interpolated (untextured) case: vertex colours and their screen-space gradient
+    float a[3][MAXC], dadx[MAXC], dady[MAXC];
+    if (!t.textured)
+        for (int q = 0; q < C; q++) {
+            for (int i = 0; i < 3; i++) a[i][q] = s.colors[(size_t)t.vid[i] * C + q];
+            dadx[q] = (float)t.gx[0] * a[0][q] + (float)t.gx[1] * a[1][q] + (float)t.gx[2] * a[2][q];
+            dady[q] = (float)t.gy[0] * a[0][q] + (float)t.gy[1] * a[1][q] + (float)t.gy[2] * a[2][q];
+        }
+    float g_next[MAXC];
+    int i_next = lowest_bit64(mine);
+    mine &= mine - 1;
+    {
+        const size_t idx = (size_t)(y0 + i_next / w) * s.width + x0 + i_next % w;
+        for (int q = 0; q < C; q++) g_next[q] = image_b[idx * C + q];
+    }
+    for (;;) {
+        const int i = i_next;
         float g[MAXC];
-        for (int q = 0; q < C; q++) g[q] = image_b[idx * C + q];
-        pixel_adjoint<MAXC, Env>(s, t, x, y, g, &acc, texture_b);
+        for (int q = 0; q < C; q++) g[q] = g_next[q];
+        const bool more = mine != 0ull;
+        if (more) {
+            i_next = lowest_bit64(mine);
+            mine &= mine - 1;
+            const size_t idx = (size_t)(y0 + i_next / w) * s.width + x0 + i_next % w;
+            for (int q = 0; q < C; q++) g_next[q] = image_b[idx * C + q];
+        }
+        const int y = y0 + i / w, x = x0 + i % w;
+        if (t.textured) {
+            pixel_adjoint<MAXC, Env>(s, t, x, y, g, &acc, texture_b);
+        } else {
+            double wd[3];
+            tri_weights(s, t, x, y, 0.0, wd);
+            const float w0 = (float)wd[0], w1 = (float)wd[1], w2 = (float)wd[2];
+            float dcdx = 0, dcdy = 0;
+            for (int q = 0; q < C; q++) {
+                dcdx += g[q] * dadx[q];
+                dcdy += g[q] * dady[q];
+                acc.attr[0][q] += g[q] * w0;
+                acc.attr[1][q] += g[q] * w1;
+                acc.attr[2][q] += g[q] * w2;
+            }
+            acc.ij[0][0] -= w0 * dcdx; acc.ij[0][1] -= w0 * dcdy;
+            acc.ij[1][0] -= w1 * dcdx; acc.ij[1][1] -= w1 * dcdy;
+            acc.ij[2][0] -= w2 * dcdx; acc.ij[2][1] -= w2 * dcdy;
+        }
+        if (!more) break;
     }
     flush_vertex_grads<MAXC, AtomicEmit<Env>>(s, t, acc, ij_b, colors_b, uv_b, shade_b, AtomicEmit<Env>());
 }
