@@ -18,7 +18,27 @@
 #include <new>
 #include <thread>
 
+#include <chrono>
+#include <cstdlib>
+
 #include "workspace.h"
+
+// DEODR_B200_TRACE=1 prints the wall-clock breakdown of the host entry points (development aid)
+struct HostTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    const char *what;
+    explicit HostTrace(const char *w) : on(getenv("DEODR_B200_TRACE") != nullptr), what(w) {
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    void lap(const char *label) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[deodr_b200 %s] %-28s %8.3f ms\n", what, label,
+                std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------- copy thread pool
 
@@ -410,8 +430,10 @@ int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, doub
     if (!z_buffer) return set_error(DEODR_B200_EINVAL, "z_buffer_ptr is NULL");
     CUDA_TRY(cudaSetDevice(ws->device));
     HostPath *hp;
+    HostTrace trace("render_host");
     if (int rc = host_path(ws, &hp)) return rc;
     if (int rc = host_forward(ws, hp, scene, sigma)) return rc;
+    trace.lap("stage + forward (enqueued)");
     const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
     if (int rc = hp->staging.ensure(P * C * 4 + P * 8 + 512)) return rc;
     char *stage_image = (char *)hp->staging.ptr, *stage_z = stage_image + ((P * C * 4 + 255) & ~(size_t)255);
@@ -421,7 +443,9 @@ int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, doub
     if (int rc = queue_download(hp, &d_image, 40, hp->stream)) return rc;
     if (int rc = queue_download(hp, &d_z, 24, hp->stream)) return rc;
     if (int rc = finish_download(hp, &d_image)) return rc;
+    trace.lap("image DMA + fp32->fp64");
     if (int rc = finish_download(hp, &d_z)) return rc;
+    trace.lap("z DMA + copy");
     return DEODR_B200_OK;
 }
 
@@ -441,6 +465,7 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
     if (!image_b) return set_error(DEODR_B200_EINVAL, "image_b_ptr is NULL");
     CUDA_TRY(cudaSetDevice(ws->device));
     HostPath *hp;
+    HostTrace trace("render_b_host");
     if (int rc = host_path(ws, &hp)) return rc;
     cudaStream_t st = hp->stream;
     const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
@@ -460,10 +485,13 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
                                      cudaMemcpyHostToDevice, st));
         }
     }
+    trace.lap("image_b fp64->fp32 + DMA");
     // forward state: reuse the cached one iff the caller's scene is bit-identical to the last forward's
     if (!scene_matches_mirror(hp, scene, sigma)) {
         if (int rc = host_forward(ws, hp, scene, sigma)) return rc;
+        trace.lap("scene changed: re-forward");
     }
+    trace.lap("scene == mirror check");
     if (ws->h_grads.ensure(n_grad * sizeof(float), &ws->bytes)) return DEODR_B200_ECUDA;
     CUDA_TRY(cudaMemsetAsync(ws->h_grads.ptr, 0, n_grad * sizeof(float), st));
     DeodrGrads g;
@@ -477,6 +505,7 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
         return rc;
     // gradients are ACCUMULATED into scene.*_b (DR.h:3019-3049, 3126-3128)
     CUDA_TRY(cudaStreamSynchronize(st));  // staging is reused: image_b DMA must have completed
+    trace.lap("backward kernels");
     double *dst[5] = {scene->ij_b, scene->colors_b, scene->uv_b, scene->shade_b, scene->texture_b};
     const size_t cnt[5] = {n_ij, n_col, n_uv, n_sh, tex};
     size_t off = 0;
@@ -491,6 +520,7 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
     for (int i = 0; i < 5; i++)
         if (cnt[i])
             if (int rc = finish_download(hp, &d[i])) return rc;
+    trace.lap("gradients DMA + accumulate");
     return DEODR_B200_OK;
 }
 

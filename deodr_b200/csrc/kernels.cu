@@ -86,41 +86,51 @@ struct ScanJob {
     const int *count[3];
     int *offset[3];
     int total_slot[3];
+    int *nonempty[3];        // optional: compact list of the tiles with count > 0 (nullptr to skip)
+    int nonempty_slot[3];    // totals[] slot receiving the length of that list
 };
 
+// One 64-bit scan carries both the running sum of the counts (low word) and the number of non-empty tiles (high word).
 __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *totals) {
-    __shared__ int warp_sums[32];
+    __shared__ unsigned long long warp_sums[32];
     const int *count = job.count[blockIdx.x];
     int *offset = job.offset[blockIdx.x];
+    int *nonempty = job.nonempty[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int carry = 0;
+    unsigned long long carry = 0;
     int next = tid < n ? count[tid] : 0;
     for (int base = 0; base < n; base += 1024) {
-        const int idx = base + tid, v = next;
+        const int idx = base + tid, c = next;
         next = idx + 1024 < n ? count[idx + 1024] : 0;  // coalesced prefetch of the next chunk
-        int incl = v;
+        const unsigned long long v = (unsigned long long)(unsigned)c | ((unsigned long long)(c > 0) << 32);
+        unsigned long long incl = v;
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
         if (lane == 31) warp_sums[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            int w = warp_sums[lane];
+            unsigned long long w = warp_sums[lane];
             for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, w, o);
+                unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
                 if (lane >= o) w += t;
             }
             warp_sums[lane] = w;
         }
         __syncthreads();
-        if (idx < n) offset[idx] = carry + (warp ? warp_sums[warp - 1] : 0) + incl - v;
+        const unsigned long long excl = carry + (warp ? warp_sums[warp - 1] : 0ull) + incl - v;
+        if (idx < n) {
+            offset[idx] = (int)(unsigned)excl;
+            if (nonempty && c > 0) nonempty[(int)(excl >> 32)] = idx;
+        }
         carry += warp_sums[31];
         __syncthreads();
     }
     if (tid == 0) {
-        offset[n] = carry;
-        totals[job.total_slot[blockIdx.x]] = carry;
+        offset[n] = (int)(unsigned)carry;
+        totals[job.total_slot[blockIdx.x]] = (int)(unsigned)carry;
+        if (nonempty) totals[job.nonempty_slot[blockIdx.x]] = (int)(carry >> 32);
     }
 }
 
@@ -217,8 +227,9 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // Orders every tile's edge list by far-to-near rank (ranks are unique): rank-counting sort, one CTA per tile.
-__global__ void k_sort_tile_edges(const int *count, const int *offset, const int *refs_in, int *refs_out) {
-    const int tile = blockIdx.x;
+__global__ void k_sort_tile_edges(const int *edge_tiles, const int *count, const int *offset, const int *refs_in,
+                                  int *refs_out) {
+    const int tile = edge_tiles[blockIdx.x];
     const int n = count[tile], base = offset[tile];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int mine = refs_in[base + i], pos = 0;
@@ -329,13 +340,12 @@ __global__ void __launch_bounds__(NT) k_shade(SceneView s, int tiles_x, TieTable
 
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
 template <int MAXC>
-__global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_count,
-                                                 const int *edge_offset, const int *edge_refs,
+__global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles,
+                                                 const int *edge_count, const int *edge_offset, const int *edge_refs,
                                                  const EdgeRec *edge_recs, const double *z_buffer, float *image) {
     __shared__ TileShared sh;
-    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const int tile_id = edge_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile that HAS edges
     const int n_edge = edge_count[tile_id];
-    if (n_edge == 0) return;
     const Tile tile = tile_of(tile_id, tiles_x);
     const int r = tid / TS;
     const int x = tile.x0 + tid % TS, y = tile.y0 + r;
@@ -363,21 +373,19 @@ __global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int 
 }
 
 template <int MAXC>
-__global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_count,
-                                                   const int *edge_offset, const int *edge_refs,
+__global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles,
+                                                   const int *edge_count, const int *edge_offset, const int *edge_refs,
                                                    const EdgeRec *edge_recs, TieTable ties, const double *z_buffer,
                                                    const int *owner, const float *image_b, DeodrGrads grads,
                                                    double *edge_acc) {
     __shared__ TileShared sh;
-    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const int tile_id = edge_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile that HAS edges
     const Tile tile = tile_of(tile_id, tiles_x);
     const int c = tid % TS, r = tid / TS;
     const int x = tile.x0 + c, y = tile.y0 + r;
     const bool inside = x < s.width && y < s.height;
     const size_t idx = inside ? (size_t)y * s.width + x : 0;
-
-    const int n_edge = edge_count ? edge_count[tile_id] : 0;
-    if (n_edge == 0) return;  // tiles without silhouette edges are handled by k_interior_bwd
+    const int n_edge = edge_count[tile_id];
 
     PixelState<MAXC> p;
     AdjointState<MAXC> a;
@@ -438,9 +446,10 @@ __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, in
 // Interior adjoint of the tiles WITHOUT silhouette edges (the vast majority): no shared memory, no z-buffer read,
 // few registers -> high occupancy to hide the dependent gathers owner -> faces -> vertices.
 template <int MAXC>
-__global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, const int *edge_count, TieTable ties,
-                                                     const int *owner, const float *image_b, DeodrGrads grads) {
-    const int tile_id = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, const int *large_tiles,
+                                                     const int *edge_count, TieTable ties, const int *owner,
+                                                     const float *image_b, DeodrGrads grads) {
+    const int tile_id = large_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile with large triangles binned
     if (edge_count && edge_count[tile_id] > 0) return;  // handled by k_raster_bwd
     const Tile tile = tile_of(tile_id, tiles_x);
     const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
@@ -535,10 +544,11 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
         k_shade<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ties, owner, z, image);
     }
     ws->launches += 2;
-    if (edge_count) {
+    if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
-        k_edge_fwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
-                                                       ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), z, image);
+        k_edge_fwd<MAXC><<<ws->num_edge_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles.as<int>(), edge_count,
+                                                            ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
+                                                            ws->edge_recs.as<EdgeRec>(), z, image);
         ws->launches++;
     }
 }
@@ -553,15 +563,17 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
                                                                            image_b, g);
         ws->launches++;
     }
-    if (ws->num_large > 0) {  // pixels owned by large triangles, tiles without silhouette edges
+    if (ws->num_large_tiles > 0) {  // pixels owned by large triangles, tiles without silhouette edges
         PhaseTimer timer(ws, DEODR_B200_PH_INTERIOR_BWD, st);
-        k_interior_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, edge_count, ties, owner, image_b, g);
+        k_interior_bwd<MAXC><<<ws->num_large_tiles, NT, 0, st>>>(s, ws->tiles_x, ws->large_tiles.as<int>(), edge_count,
+                                                                 ties, owner, image_b, g);
         ws->launches++;
     }
-    if (edge_count) {
+    if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, st);
-        k_raster_bwd<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, edge_count, ws->edge_offset.as<int>(),
-                                                         ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), ties, z,
+        k_raster_bwd<MAXC><<<ws->num_edge_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles.as<int>(), edge_count,
+                                                              ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
+                                                              ws->edge_recs.as<EdgeRec>(), ties, z,
                                                          owner, image_b, g, ws->edge_acc.as<double>());
         ws->launches++;
     }
@@ -659,7 +671,7 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
     DeodrWorkspace *ws = new (std::nothrow) DeodrWorkspace();
     if (!ws) return set_error(DEODR_B200_ENOMEM, "out of host memory");
     ws->device = device;
-    CUDA_TRY(cudaMallocHost(&ws->host_totals, 8 * sizeof(int)));
+    CUDA_TRY(cudaMallocHost(&ws->host_totals, 16 * sizeof(int)));
     if (ws->scalars.ensure(8 * sizeof(int), &ws->bytes)) return DEODR_B200_ECUDA;
     if (!sm_count_cached) cudaDeviceGetAttribute(&sm_count_cached, cudaDevAttrMultiProcessorCount, device);
     *out = ws;
@@ -669,7 +681,7 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
 void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    DevBuf *bufs[] = {&ws->zeroed, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
+    DevBuf *bufs[] = {&ws->zeroed, &ws->large_tiles, &ws->edge_tiles, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
                       &ws->edge_ids_tmp, &ws->edge_rank, &ws->edge_recs,
                       &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
                       &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
@@ -734,13 +746,15 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     ws->tiles_y = (s.height + TS - 1) / TS;
     ws->num_tiles = ws->tiles_x * ws->tiles_y;
     const int nt = ws->num_tiles;
-    // one zero-initialised block: [scalars(8) | small_count | small_cursor | large_count | large_cursor | edge_count |
+    // one zero-initialised block: [scalars(16) | small_count | small_cursor | large_count | large_cursor | edge_count |
     // edge_cursor], (nt+1) ints each
     const size_t tile_ints = (size_t)nt + 1;
     const size_t tile_bytes = tile_ints * sizeof(int);
     int rc = 0;
-    rc |= ws->zeroed.ensure((8 + 6 * tile_ints) * sizeof(int), &ws->bytes);
+    rc |= ws->zeroed.ensure((16 + 6 * tile_ints) * sizeof(int), &ws->bytes);
     rc |= ws->small_offset.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->large_tiles.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->edge_tiles.ensure(tile_bytes, &ws->bytes);
     rc |= ws->tri_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_ids.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
@@ -753,7 +767,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     }
     if (rc) return DEODR_B200_ECUDA;
     int *scal = ws->zeroed.as<int>();
-    int *small_count = scal + 8, *small_cursor = small_count + tile_ints, *large_count = small_cursor + tile_ints,
+    int *small_count = scal + 16, *small_cursor = small_count + tile_ints, *large_count = small_cursor + tile_ints,
         *large_cursor = large_count + tile_ints, *edge_count_buf = large_cursor + tile_ints,
         *edge_cursor = edge_count_buf + tile_ints;
     ws->scal = scal;
@@ -766,7 +780,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     // ---- count pass + scans (triangles and silhouette edges together), then the ONE host read-back of the sizes
     {
         PhaseTimer timer(ws, DEODR_B200_PH_BIN_COUNT, st);
-        CUDA_TRY(cudaMemsetAsync(scal, 0, (8 + 6 * tile_ints) * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(scal, 0, (16 + 6 * tile_ints) * sizeof(int), st));
         if (T > 0) {
             if (check_indices) {  // checkSceneValid (DR.h:2703-2714) on the device, before any index is dereferenced
                 k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, scal + 4);
@@ -778,11 +792,13 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
         }
         ScanJob job{{small_count, large_count, edge_count_buf},
                     {ws->small_offset.as<int>(), ws->tri_offset.as<int>(), ws->edge_offset.as<int>()},
-                    {5, 0, 2}};
+                    {5, 0, 2},
+                    {nullptr, ws->large_tiles.as<int>(), ws->edge_tiles.as<int>()},
+                    {15, 8, 9}};
         k_scan_tiles<<<3, 1024, 0, st>>>(job, nt, scal);
         ws->launches++;
     }
-    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (check_indices && (ws->host_totals[4] & 1))
         return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
@@ -793,6 +809,8 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     ws->num_edges = E;
     ws->num_small = ws->host_totals[6];
     ws->num_large = ws->host_totals[7];
+    ws->num_large_tiles = ws->host_totals[8];
+    ws->num_edge_tiles = E > 0 ? ws->host_totals[9] : 0;
     rc = 0;
     rc |= ws->small_recs.ensure(((size_t)small_total + 1) * sizeof(PreRec), &ws->bytes);
     rc |= ws->tri_refs.ensure(((size_t)large_total + 4) * sizeof(int), &ws->bytes);
@@ -853,10 +871,11 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
             ws->launches++;
         }
     }
-    if (E > 0) {
+    if (E > 0 && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, st);
-        k_sort_tile_edges<<<nt, 128, 0, st>>>(edge_count_buf, ws->edge_offset.as<int>(), ws->edge_refs_tmp.as<int>(),
-                                              ws->edge_refs.as<int>());
+        k_sort_tile_edges<<<ws->num_edge_tiles, 128, 0, st>>>(ws->edge_tiles.as<int>(), edge_count_buf,
+                                                              ws->edge_offset.as<int>(), ws->edge_refs_tmp.as<int>(),
+                                                              ws->edge_refs.as<int>());
         ws->launches++;
     }
 
