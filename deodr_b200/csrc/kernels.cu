@@ -150,9 +150,16 @@ __global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *
     if (i >= n) return;
     const unsigned long long key = edges.keys[i];
     const int id = edges.ids[i];
-    int partial = 0;
+    // keys are almost always distinct: count the smaller keys and the equal ones; only when another edge shares the
+    // key (same triangle, or an exactly equal depth sum) is the id tie-break loop run
+    int partial = 0, equal = 0;
 #pragma unroll 8
-    for (int j = 0; j < m; j++) partial += (int)(sk[j] < key) | ((int)(sk[j] == key) & (int)(si[j] < id));
+    for (int j = 0; j < m; j++) {
+        partial += (int)(sk[j] < key);
+        equal += (int)(sk[j] == key);
+    }
+    if (equal > 0)
+        for (int j = 0; j < m; j++) partial += (int)(sk[j] == key) & (int)(si[j] < id);
     if (partial) atomicAdd(&rank[i], partial);
 }
 
@@ -761,8 +768,9 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     rc |= ws->edge_keys_in.ensure(((size_t)3 * T + 4) * 8, &ws->bytes);
     rc |= ws->small_ids.ensure(((size_t)T + 4) * sizeof(int), &ws->bytes);
     rc |= ws->large_ids.ensure(((size_t)T + 4) * sizeof(int), &ws->bytes);
-    if (ws->tie_capacity == 0) {
-        ws->tie_capacity = 1 << 16;
+    // one (own, bown) slot per pixel: the exact-tie table can never overflow, so the adjoint needs no read-back
+    if (ws->tie_capacity < s.height * s.width) {
+        ws->tie_capacity = s.height * s.width;
         rc |= ws->tie_pairs.ensure((size_t)2 * ws->tie_capacity * sizeof(int), &ws->bytes);
     }
     if (rc) return DEODR_B200_ECUDA;
@@ -912,12 +920,7 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
         return set_error(DEODR_B200_EINVAL, "render_b must follow render on the same workspace, scene and sigma");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(ws->device));
-    // the tie table must not have overflowed in the forward pass
     int *scal = ws->scal;
-    CUDA_TRY(cudaMemcpyAsync(ws->host_totals + 3, scal + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (ws->host_totals[3] > ws->tie_capacity)
-        return set_error(DEODR_B200_EUNSUPPORTED, "more exact z-buffer ties than the tie table holds");
     const int E = ws->num_edges, C = s.nb_colors;
     DeodrGrads g = *grads;
     if ((s.nb_vertices > 0 && (!g.ij_b || !g.colors_b || !g.shade_b)) || (s.nb_uv > 0 && !g.uv_b))

@@ -75,8 +75,15 @@ def _marshal(scene, nb_colors, with_grads):
     h.perspective_correct = int(bool(scene.perspective_correct))
     h.integer_pixel_centers = int(bool(scene.integer_pixel_centers))
     if with_grads:
+        # The pyx accumulates into flattened COPIES of scene.*_b and rebinds the attributes (pyx:297-312, 406-410).
+        # Copying (and later re-faulting) tens of MB per call is pure overhead, so C-contiguous float64 arrays are
+        # accumulated in place; anything else goes through a converted copy that is rebound, exactly like the pyx.
         for name in ("uv_b", "ij_b", "shade_b", "colors_b", "texture_b"):
-            keep[name] = _flat(getattr(scene, name), np.double).copy()
+            cur = getattr(scene, name)
+            if isinstance(cur, np.ndarray) and cur.dtype == np.float64 and cur.flags["C_CONTIGUOUS"] and cur.flags["WRITEABLE"]:
+                keep[name] = cur.reshape(-1)
+            else:
+                keep[name] = _flat(cur, np.double).copy()
             setattr(h, name, keep[name].ctypes.data)
     return h, keep
 
