@@ -346,15 +346,19 @@ __global__ void __launch_bounds__(NT) k_shade(SceneView s, int tiles_x, TieTable
 }
 
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
+// One CTA of 64 threads per 16x4 pixel strip (4 per tile): the tiles crowded with edges set the kernel's duration, and
+// a strip has a 4x shorter critical path than a tile.
 template <int MAXC>
-__global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles,
-                                                 const int *edge_count, const int *edge_offset, const int *edge_refs,
-                                                 const EdgeRec *edge_recs, const double *z_buffer, float *image) {
+__global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles,
+                                                      const int *edge_count, const int *edge_offset,
+                                                      const int *edge_refs, const EdgeRec *edge_recs,
+                                                      const double *z_buffer, float *image) {
     __shared__ TileShared sh;
-    const int tile_id = edge_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile that HAS edges
+    const int tile_id = edge_tiles[blockIdx.x / (TS / EDGE_ROWS)], tid = threadIdx.x;
+    const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
     const int n_edge = edge_count[tile_id];
     const Tile tile = tile_of(tile_id, tiles_x);
-    const int r = tid / TS;
+    const int r = row0 + tid / TS;
     const int x = tile.x0 + tid % TS, y = tile.y0 + r;
     const bool inside = x < s.width && y < s.height;
     const size_t idx = inside ? (size_t)y * s.width + x : 0;
@@ -368,9 +372,9 @@ __global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int 
     const int edge_base = edge_offset[tile_id];
     for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
         const int m = min(EDGE_CHUNK, n_edge - base);
-        phase_edge_setup(tid, m, edge_refs + edge_base + base, edge_recs, &sh);
+        phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
         __syncthreads();
-        phase_edge_spans(s, tid, m, tile, &sh);
+        phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
         __syncthreads();
         if (inside) phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
         __syncthreads();
@@ -380,15 +384,17 @@ __global__ void __launch_bounds__(NT) k_edge_fwd(SceneView s, double sigma, int 
 }
 
 template <int MAXC>
-__global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles,
+__global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles,
                                                    const int *edge_count, const int *edge_offset, const int *edge_refs,
                                                    const EdgeRec *edge_recs, TieTable ties, const double *z_buffer,
                                                    const int *owner, const float *image_b, DeodrGrads grads,
                                                    double *edge_acc) {
     __shared__ TileShared sh;
-    const int tile_id = edge_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile that HAS edges
+    // one CTA of 64 threads per 16x4 strip of a tile that HAS edges (see k_edge_fwd)
+    const int tile_id = edge_tiles[blockIdx.x / (TS / EDGE_ROWS)], tid = threadIdx.x;
+    const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
     const Tile tile = tile_of(tile_id, tiles_x);
-    const int c = tid % TS, r = tid / TS;
+    const int c = tid % TS, r = row0 + tid / TS;
     const int x = tile.x0 + c, y = tile.y0 + r;
     const bool inside = x < s.width && y < s.height;
     const size_t idx = inside ? (size_t)y * s.width + x : 0;
@@ -417,9 +423,9 @@ __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, in
         // pass A: forward replay (far to near) to obtain the final colour in fp64
         for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
             const int m = min(EDGE_CHUNK, n_edge - base);
-            phase_edge_setup(tid, m, edge_refs + edge_base + base, edge_recs, &sh);
+            phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
             __syncthreads();
-            phase_edge_spans(s, tid, m, tile, &sh);
+            phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
             __syncthreads();
             if (inside) phase_edge_replay<MAXC>(s, x, y, r, m, &sh, p, &a);
             if (single) {
@@ -433,9 +439,9 @@ __global__ void __launch_bounds__(NT) k_raster_bwd(SceneView s, double sigma, in
             const int last = ((n_edge - 1) / EDGE_CHUNK) * EDGE_CHUNK;
             for (int base = last; base >= 0; base -= EDGE_CHUNK) {
                 const int m = min(EDGE_CHUNK, n_edge - base);
-                phase_edge_setup(tid, m, edge_refs + edge_base + base, edge_recs, &sh);
+                phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
                 __syncthreads();
-                phase_edge_spans(s, tid, m, tile, &sh);
+                phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
                 __syncthreads();
                 if (inside && a.has_colour)
                     phase_edge_adjoint<MAXC, DevEnv>(s, x, y, r, m, &sh, p, &a, edge_acc, grads.texture_b);
@@ -553,7 +559,7 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     ws->launches += 2;
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
-        k_edge_fwd<MAXC><<<ws->num_edge_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles.as<int>(), edge_count,
+        k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles.as<int>(), edge_count,
                                                             ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                             ws->edge_recs.as<EdgeRec>(), z, image);
         ws->launches++;
@@ -578,7 +584,7 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     }
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, st);
-        k_raster_bwd<MAXC><<<ws->num_edge_tiles, NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles.as<int>(), edge_count,
+        k_raster_bwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles.as<int>(), edge_count,
                                                               ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                               ws->edge_recs.as<EdgeRec>(), ties, z,
                                                          owner, image_b, g, ws->edge_acc.as<double>());

@@ -14,6 +14,8 @@ constexpr int TS = 16;            // tile side in pixels
 constexpr int NT = TS * TS;       // threads per tile CTA, one per pixel
 constexpr int TRI_CHUNK = 256;    // triangles staged in shared memory per pass (one per thread)
 constexpr int EDGE_CHUNK = 64;    // edge records staged in shared memory per pass
+constexpr int EDGE_ROWS = 4;      // the edge kernels work on 16 x 4 pixel strips (4 CTAs of 64 threads per tile):
+constexpr int EDGE_NT = TS * EDGE_ROWS;  // 4x shorter critical path for the tiles crowded with silhouette edges
 
 // What the z test needs from a triangle once its coverage masks exist.
 struct TriRec {
@@ -412,17 +414,23 @@ DEODR_HD void phase_shade(const SceneView &s, int x, int y, PixelState<MAXC> *p)
     pixel_colour<MAXC>(s, t, x, y, p->z, &e, p->col);
 }
 
-// Phase E1: thread tid < n fetches the record of the edge with far-to-near rank list[tid] (records are built once per
-// forward pass by k_edge_records: stencil equations with their sqrt / divisions are not redone per tile).
-DEODR_HD void phase_edge_setup(int tid, int n, const int *list, const EdgeRec *edge_recs, TileShared *sh) {
-    if (tid >= n) return;
-    sh->edge.rec[tid] = edge_recs[list[tid]];
+// Phase E1: the CTA fetches the records of the edges with far-to-near ranks list[0..n) (built once per forward pass by
+// k_edge_records: the stencil's sqrt / divisions are not redone per tile); 8-byte words, all threads cooperating.
+DEODR_HD void phase_edge_setup(int tid, int nthreads, int n, const int *list, const EdgeRec *edge_recs, TileShared *sh) {
+    constexpr int WORDS = (int)(sizeof(EdgeRec) / 8);
+    static_assert(sizeof(EdgeRec) % 8 == 0, "EdgeRec is copied as 8-byte words");
+    for (int item = tid; item < n * WORDS; item += nthreads) {
+        const int e = item / WORDS, w = item % WORDS;
+        reinterpret_cast<unsigned long long *>(&sh->edge.rec[e])[w] =
+            reinterpret_cast<const unsigned long long *>(&edge_recs[list[e]])[w];
+    }
 }
 
-// Phase E2: (edge, row) items -> x spans.
-DEODR_HD void phase_edge_spans(const SceneView &s, int tid, int n, Tile tile, TileShared *sh) {
-    for (int item = tid; item < n * TS; item += NT) {
-        int e = item / TS, r = item % TS;
+// Phase E2: (edge, row) items of rows [row0, row0 + nrows) of the tile -> x spans.
+DEODR_HD void phase_edge_spans(const SceneView &s, int tid, int nthreads, int n, Tile tile, int row0, int nrows,
+                               TileShared *sh) {
+    for (int item = tid; item < n * nrows; item += nthreads) {
+        int e = item / nrows, r = row0 + item % nrows;
         int y = tile.y0 + r;
         uint32_t packed = 1u;  // begin = 1, end = 0: empty
         const EdgeGeom &g = sh->edge.rec[e].g;

@@ -318,7 +318,9 @@ struct EdgeRec {
     uint32_t vid[2], uvid[2];
     int32_t rank;     // position in the far-to-near order (index into the sorted edge array / accumulators)
     uint8_t textured;
+    uint8_t has_col;  // col[][] holds the end-point colours (C <= 4): no gathers in the blend loop
     double inv_z[2];  // 1/z of the end points (perspective_correct only)
+    float col[2][4];
 };
 
 DEODR_HD void edge_record(const SceneView &s, int edge_id, int rank, double sigma, EdgeRec *r) {
@@ -337,6 +339,9 @@ DEODR_HD void edge_record(const SceneView &s, int edge_id, int rank, double sigm
     edge_geom(V, Zv, s.height, sigma, s.clockwise != 0, s.perspective_correct != 0, &r->g, nullptr, nullptr, nullptr);
     r->rank = rank;
     r->textured = (uint8_t)(s.textured[k] && s.shaded[k]);
+    r->has_col = (uint8_t)(s.nb_colors <= 4);
+    for (int i = 0; i < 2; i++)
+        for (int c = 0; c < 4; c++) r->col[i][c] = c < s.nb_colors ? s.colors[(size_t)r->vid[i] * s.nb_colors + c] : 0.0f;
 }
 
 // What one edge contributes at one pixel of its band.
@@ -380,7 +385,8 @@ DEODR_HD void edge_hit(const SceneView &s, const EdgeRec &r, int x, int y, doubl
             h->A[c] = h->texval[c] * h->L;
         }
     } else {
-        const float *a0 = s.colors + (size_t)r.vid[0] * C, *a1 = s.colors + (size_t)r.vid[1] * C;
+        const float *a0 = r.has_col ? r.col[0] : s.colors + (size_t)r.vid[0] * C;
+        const float *a1 = r.has_col ? r.col[1] : s.colors + (size_t)r.vid[1] * C;
         for (int c = 0; c < C; c++) h->A[c] = h->w[0] * a0[c] + h->w[1] * a1[c];
     }
 }

@@ -118,8 +118,8 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
         for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
             const int m = std::min(EDGE_CHUNK, n_edge - base);
             for (int tid = 0; tid < NT; tid++)
-                phase_edge_setup(tid, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
-            for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
+                phase_edge_setup(tid, NT, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
+            for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, NT, m, tile, 0, TS, sh);
             for (int tid = 0; tid < NT; tid++)
                 if (inside(tid))
                     phase_edge_blend<MAXC>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, tid / TS, m, sh, &px[tid]);
@@ -163,8 +163,8 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
             for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
                 const int m = std::min(EDGE_CHUNK, n_edge - base);
                 for (int tid = 0; tid < NT; tid++)
-                    phase_edge_setup(tid, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
-                for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
+                    phase_edge_setup(tid, NT, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
+                for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, NT, m, tile, 0, TS, sh);
                 for (int tid = 0; tid < NT; tid++) {
                     if (!inside(tid)) continue;
                     const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
@@ -178,8 +178,8 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
                 for (int base = last; base >= 0; base -= EDGE_CHUNK) {
                     const int m = std::min(EDGE_CHUNK, n_edge - base);
                     for (int tid = 0; tid < NT; tid++)
-                        phase_edge_setup(tid, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
-                    for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, m, tile, sh);
+                        phase_edge_setup(tid, NT, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
+                    for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, NT, m, tile, 0, TS, sh);
                     for (int tid = 0; tid < NT; tid++) {
                         if (!inside(tid) || !adj[tid].has_colour) continue;
                         phase_edge_adjoint<MAXC, HostEnv>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, tid / TS, m, sh,
