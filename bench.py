@@ -172,14 +172,22 @@ def run_ours(args):
     ij_dev = ds.t["ij"].clone()
     colors_dev = ds.t["colors"].clone()
     image_b = torch.from_numpy(np.random.default_rng(1 + rank).random((H, W, C), dtype=np.float32) * 2 - 1).to(dev)
-    grads = ds.zero_grads()
+    # the five gradient slots are views of ONE flat buffer: callers clear scene.*_b before every backward, one memset
+    names = ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b")
+    shapes = {"ij_b": ds.t["ij"].shape, "colors_b": ds.t["colors"].shape, "uv_b": ds.t["uv"].shape,
+              "shade_b": ds.t["shade"].shape, "texture_b": ds.t["texture"].shape}
+    sizes = {k: int(np.prod(shapes[k])) for k in names}
+    flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
+    grads, off = {}, 0
+    for k in names:
+        grads[k] = flat[off:off + sizes[k]].view(shapes[k])
+        off += sizes[k]
     out = None
 
     def step():
         nonlocal out
         ds.update(ij=ij_dev, colors=colors_dev)          # per-iteration refresh of the optimised inputs
-        for g in grads.values():
-            g.zero_()                                     # callers clear scene.*_b before every backward
+        flat.zero_()                                      # callers clear scene.*_b before every backward
         out = renderer.render(ds, SIGMA, out=out)
         renderer.render_b(ds, SIGMA, out, image_b, grads)
         if world > 1:

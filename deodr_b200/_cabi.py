@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeodr_b200.so")
+# DEODR_B200_LIB selects an alternative build of the same library (A/B experiments on one GPU box)
+LIB_PATH = os.environ.get("DEODR_B200_LIB") or os.path.join(_HERE, "libdeodr_b200.so")
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, 1, 2, 3, 4
 

@@ -163,9 +163,14 @@ __global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *
     if (partial) atomicAdd(&rank[i], partial);
 }
 
-__global__ void k_scatter_edges(EdgeList edges, int n, const int *rank, int *edge_sorted) {
+// edge_sorted[rank] = id, and the edge's band stencil record (DR.h:1366-1460 + z plane) at the same rank: built ONCE
+// per forward pass, not per tile.
+__global__ void k_scatter_edges(SceneView s, EdgeList edges, int n, double sigma, int *edge_sorted, EdgeRec *recs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) edge_sorted[rank[i]] = edges.ids[i];
+    if (i >= n) return;
+    const int r = edges.rank[i], id = edges.ids[i];
+    edge_sorted[r] = id;
+    edge_record(s, id, r, sigma, &recs[r]);
 }
 
 // One thread per silhouette edge (far-to-near rank r): band stencil of DR.h:1366-1460 + z plane, once per forward.
@@ -772,6 +777,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_ids.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_keys_in.ensure(((size_t)3 * T + 4) * 8, &ws->bytes);
+    rc |= ws->edge_rank.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
     rc |= ws->small_ids.ensure(((size_t)T + 4) * sizeof(int), &ws->bytes);
     rc |= ws->large_ids.ensure(((size_t)T + 4) * sizeof(int), &ws->bytes);
     // one (own, bown) slot per pixel: the exact-tie table can never overflow, so the adjoint needs no read-back
@@ -786,7 +792,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
         *edge_cursor = edge_count_buf + tile_ints;
     ws->scal = scal;
     ws->edge_count_ptr = edge_count_buf;
-    EdgeList edges{scal + 1, ws->edge_ids.as<int>(), (uint64_t *)ws->edge_keys_in.ptr};
+    EdgeList edges{scal + 1, ws->edge_ids.as<int>(), (uint64_t *)ws->edge_keys_in.ptr, ws->edge_rank.as<int>()};
     TriBins bins{small_count, ws->small_offset.as<int>(), small_cursor, nullptr,
                  large_count, ws->tri_offset.as<int>(), large_cursor, nullptr};
     TriLists lists{scal + 6, ws->small_ids.as<int>(), scal + 7, ws->large_ids.as<int>()};
@@ -829,7 +835,6 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     rc |= ws->small_recs.ensure(((size_t)small_total + 1) * sizeof(PreRec), &ws->bytes);
     rc |= ws->tri_refs.ensure(((size_t)large_total + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_sorted.ensure(((size_t)E + 4) * sizeof(int), &ws->bytes);
-    rc |= ws->edge_rank.ensure(((size_t)E + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_recs.ensure(((size_t)E + 1) * sizeof(EdgeRec), &ws->bytes);
     rc |= ws->edge_refs_tmp.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_refs.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
@@ -842,11 +847,10 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     if (E > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, st);
         if (E <= 65536) {
-            CUDA_TRY(cudaMemsetAsync(ws->edge_rank.ptr, 0, (size_t)E * sizeof(int), st));
             dim3 grid(grid_for(E, 256), grid_for(E, 1024));
             k_rank_edges<<<grid, 256, 0, st>>>(edges, E, ws->edge_rank.as<int>());
-            k_scatter_edges<<<grid_for(E, 256), 256, 0, st>>>(edges, E, ws->edge_rank.as<int>(),
-                                                               ws->edge_sorted.as<int>());
+            k_scatter_edges<<<grid_for(E, 128), 128, 0, st>>>(s, edges, E, sigma, ws->edge_sorted.as<int>(),
+                                                               ws->edge_recs.as<EdgeRec>());
             ws->launches += 2;
         } else {
             // large soups: two stable radix sorts (by id, then by depth key) give the same total order
@@ -863,13 +867,10 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
             CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, st));
             CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp2, k_out, k_in, i_tmp,
                                                      ws->edge_sorted.as<int>(), E, 0, 64, st));
+            k_edge_records<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), E, sigma,
+                                                             ws->edge_recs.as<EdgeRec>());
+            ws->launches++;
         }
-    }
-
-    if (E > 0) {
-        k_edge_records<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), E, sigma,
-                                                         ws->edge_recs.as<EdgeRec>());
-        ws->launches++;
     }
 
     // ---- fill pass (triangles + edges) and per-tile ordering of the edge lists

@@ -14,8 +14,14 @@ constexpr int TS = 16;            // tile side in pixels
 constexpr int NT = TS * TS;       // threads per tile CTA, one per pixel
 constexpr int TRI_CHUNK = 256;    // triangles staged in shared memory per pass (one per thread)
 constexpr int EDGE_CHUNK = 64;    // edge records staged in shared memory per pass
-constexpr int EDGE_ROWS = 4;      // the edge kernels work on 16 x 4 pixel strips (4 CTAs of 64 threads per tile):
-constexpr int EDGE_NT = TS * EDGE_ROWS;  // 4x shorter critical path for the tiles crowded with silhouette edges
+#ifndef DEODR_EDGE_ROWS
+#define DEODR_EDGE_ROWS 16
+#endif
+// Rows of a tile handled by one CTA of the edge kernels.  16 = whole tile; 4 (16x4 strips, 4 CTAs per tile) was measured
+// slower on B200 (edge_fwd 79 vs 56 us, edge_bwd 164 vs 118 us on the 1M-triangle scene: the per-CTA record fetch and span
+// set-up are replicated per strip).
+constexpr int EDGE_ROWS = DEODR_EDGE_ROWS;
+constexpr int EDGE_NT = TS * EDGE_ROWS;
 
 // What the z test needs from a triangle once its coverage masks exist.
 struct TriRec {
@@ -28,7 +34,7 @@ struct alignas(16) Mask4 {
     uint32_t m[4];
 };
 
-// Pre-masked tile record of a SMALL triangle (bounding box <= SMALL_TILES tiles and <= SMALL_PIXELS pixels), written by the fill pass: the exact
+// Pre-masked tile record of a SMALL triangle (bounding box that fits a 64-bit mask), written by the fill pass: the exact
 // coverage of the 16x16 tile (8 row pairs x 32 bits) + what the z test needs.  64 bytes, so a tile's list is one
 // contiguous, 16-byte aligned array that the raster kernel pulls into shared memory with one bulk (TMA) copy.
 struct alignas(16) PreRec {
@@ -39,7 +45,7 @@ struct alignas(16) PreRec {
 };
 static_assert(sizeof(PreRec) == 64, "PreRec must be 64 bytes");
 
-constexpr int SMALL_TILES = 4;    // triangles whose bounding box spans more tiles are binned by index ("large")
+
 // owner codes: triangle index | SMALL_FLAG when the triangle went through the small (pre-masked) path; the adjoint of
 // such pixels is taken by the triangle-parallel kernel.  -1 = background, <= -2 = entry of the exact-tie table.
 constexpr int SMALL_FLAG = 0x40000000;
@@ -80,9 +86,10 @@ struct TileBox {
 };
 
 struct TileBox;
-DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int height, int *pixel_area = nullptr);
+DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int height, int *box_w = nullptr,
+                              int *box_h = nullptr);
 
-DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int height, int *pixel_area) {
+DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int height, int *box_w, int *box_h) {
     TileBox b;
     int x0, x1, y0, y1;
     tri_bounds(V, strict, &x0, &x1, &y0, &y1);
@@ -90,7 +97,8 @@ DEODR_HD TileBox tri_tile_box(const double V[3][2], bool strict, int width, int 
     if (x1 > width - 1) x1 = width - 1;
     if (y0 < 0) y0 = 0;
     if (y1 > height - 1) y1 = height - 1;
-    if (pixel_area) *pixel_area = (y0 > y1 || x0 > x1) ? 0 : (x1 - x0 + 1) * (y1 - y0 + 1);
+    if (box_w) *box_w = x1 - x0 + 1;
+    if (box_h) *box_h = y1 - y0 + 1;
     if (y0 > y1 || x0 > x1) { b.tx0 = 1; b.tx1 = 0; b.ty0 = 1; b.ty1 = 0; return b; }
     b.tx0 = x0 / TS; b.tx1 = x1 / TS; b.ty0 = y0 / TS; b.ty1 = y1 / TS;
     return b;
@@ -115,6 +123,7 @@ struct EdgeList {
     int *count;       // number of appended edges
     int *ids;         // 3 * triangle + n
     uint64_t *keys;   // depth_desc_key(sum of the triangle's vertex depths)
+    int *rank;        // zeroed at append time: k_rank_edges accumulates the far-to-near rank into it
 };
 
 DEODR_HD void gather_edge(const SceneView &s, int edge_id, double V[2][2]) {
@@ -127,7 +136,7 @@ DEODR_HD void gather_edge(const SceneView &s, int edge_id, double V[2][2]) {
     remove_offset(V, 2, pixel_offset(s));
 }
 
-// Per-tile lists of the drawn triangles.  SMALL triangles (bounding box of at most SMALL_TILES tiles: the micro-
+// Per-tile lists of the drawn triangles.  SMALL triangles (bounding box fitting a 64-bit pixel mask: the micro-
 // triangle regime) get a pre-masked PreRec per tile they actually cover; LARGE ones are binned by index into every
 // tile of their bounding box and their row spans are computed by the tile CTA in parallel.
 struct TriBins {
@@ -141,10 +150,15 @@ struct TriBins {
     int *large_refs;
 };
 
-// "small" = micro-triangle: few tiles AND few pixels, so that one thread can afford to walk it (fill pass, adjoint)
-constexpr int SMALL_PIXELS = 64;
-DEODR_HD bool is_small(const TileBox &b, int pixel_area) {
-    return b.tx1 - b.tx0 <= 1 && b.ty1 - b.ty0 <= 1 && pixel_area <= SMALL_PIXELS;  // at most 2 x 2 tiles
+// "small" = micro-triangle: at most 2 x 2 tiles and a bounding box that fits a 64-bit mask with a power-of-two row
+// stride (pixel <-> bit without a division), so that one thread can afford to walk it (fill pass, adjoint).
+DEODR_HD int small_shift(int box_w) {  // log2 of the row stride
+    int sh = 0;
+    while ((1 << sh) < box_w) sh++;
+    return sh;
+}
+DEODR_HD bool is_small(const TileBox &b, int box_w, int box_h) {
+    return b.tx1 - b.tx0 <= 1 && b.ty1 - b.ty0 <= 1 && box_w <= 32 && (box_h << small_shift(box_w)) <= 64;
 }
 
 // Compacted index lists of the drawn triangles, appended by the count pass (arbitrary order): the fill pass and the
@@ -172,6 +186,7 @@ DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int ti
             int slot = Env::atomic_add(edges.count, 1);
             edges.ids[slot] = 3 * k + n;
             edges.keys[slot] = depth_desc_key(c.sum_depth);
+            edges.rank[slot] = 0;
             double E[2][2];
             gather_edge(s, 3 * k + n, E);
             TileBox b = edge_tile_box(E, sigma, s.width, s.height);
@@ -181,10 +196,10 @@ DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int ti
     }
     if (!c.drawn) return;
     remove_offset(V, 3, pixel_offset(s));
-    int area;
-    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height, &area);
+    int box_w, box_h;
+    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height, &box_w, &box_h);
     if (b.tx0 > b.tx1) return;  // off screen
-    const bool small = is_small(b, area);
+    const bool small = is_small(b, box_w, box_h);
     int *count = small ? bins.small_count : bins.large_count;
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&count[ty * tiles_x + tx], 1);
@@ -602,14 +617,15 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
     if (y0 < 0) y0 = 0;
     if (x1 > s.width - 1) x1 = s.width - 1;
     if (y1 > s.height - 1) y1 = s.height - 1;
-    const int w = x1 - x0 + 1;  // w * h <= SMALL_PIXELS (64) by construction of the small list
     const int code = k | SMALL_FLAG;
+    // bit index of pixel (x, y) = ((y - y0) << shift) + (x - x0); fits 64 bits by construction of the small list
+    const int shift = small_shift(x1 - x0 + 1), stride_mask = (1 << shift) - 1;
     // phase 1 (cheap, uniform): which pixels of the bounding box does this triangle own?  One bit per pixel.
     // Loads of a row are independent: unrolled so that several are in flight.
     unsigned long long mine = 0ull;
     for (int y = y0; y <= y1; y++) {
         const int *row = owner + (size_t)y * s.width;
-        const int bit0 = (y - y0) * w - x0;
+        const int bit0 = ((y - y0) << shift) - x0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 4
 #endif
@@ -627,7 +643,7 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
                 if (edge_tile_count[ty * tiles_x + tx] == 0) continue;
                 for (int y = (ty * TS > y0 ? ty * TS : y0); y <= y1 && y < (ty + 1) * TS; y++)
                     for (int x = (tx * TS > x0 ? tx * TS : x0); x <= x1 && x < (tx + 1) * TS; x++)
-                        mine &= ~(1ull << ((y - y0) * w + (x - x0)));
+                        mine &= ~(1ull << (((y - y0) << shift) + (x - x0)));
             }
         if (!mine) return;
     }
@@ -649,7 +665,7 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
     int i_next = lowest_bit64(mine);
     mine &= mine - 1;
     {
-        const size_t idx = (size_t)(y0 + i_next / w) * s.width + x0 + i_next % w;
+        const size_t idx = (size_t)(y0 + (i_next >> shift)) * s.width + x0 + (i_next & stride_mask);
         for (int q = 0; q < C; q++) g_next[q] = image_b[idx * C + q];
     }
     for (;;) {
@@ -660,10 +676,10 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
         if (more) {
             i_next = lowest_bit64(mine);
             mine &= mine - 1;
-            const size_t idx = (size_t)(y0 + i_next / w) * s.width + x0 + i_next % w;
+            const size_t idx = (size_t)(y0 + (i_next >> shift)) * s.width + x0 + (i_next & stride_mask);
             for (int q = 0; q < C; q++) g_next[q] = image_b[idx * C + q];
         }
-        const int y = y0 + i / w, x = x0 + i % w;
+        const int y = y0 + (i >> shift), x = x0 + (i & stride_mask);
         if (t.textured) {
             pixel_adjoint<MAXC, Env>(s, t, x, y, g, &acc, texture_b);
         } else {

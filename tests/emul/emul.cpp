@@ -226,7 +226,8 @@ int emul_render(const DeodrSceneView *scene, double sigma, float *image, double 
     int num_edges = 0;
     std::vector<int> ids((size_t)3 * T + 4);
     std::vector<uint64_t> keys((size_t)3 * T + 4);
-    EdgeList edges{&num_edges, ids.data(), keys.data()};
+    std::vector<int> rank0((size_t)3 * T + 4);
+    EdgeList edges{&num_edges, ids.data(), keys.data(), rank0.data()};
     TriBins bins{st.small_count.data(), nullptr, st.small_cursor.data(), nullptr,
                  st.large_count.data(), nullptr, st.large_cursor.data(), nullptr};
     int num_small = 0, num_large = 0;
