@@ -238,6 +238,21 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// Longest-processing-time-first order of the tiles that have silhouette edges: the edge kernels are bound by their most
+// crowded tiles, which must therefore start first.  Rank counting on the edge counts (descending), a few thousand tiles.
+__global__ void __launch_bounds__(1024) k_order_edge_tiles(const int *tiles_in, int n, const int *edge_count,
+                                                           int *tiles_out) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int t = tiles_in[i], c = edge_count[t];
+        int pos = 0;
+        for (int j = 0; j < n; j++) {
+            const int cj = edge_count[tiles_in[j]];
+            pos += (cj > c) || (cj == c && j < i);
+        }
+        tiles_out[pos] = t;
+    }
+}
+
 // Orders every tile's edge list by far-to-near rank (ranks are unique): rank-counting sort, one CTA per tile.
 __global__ void k_sort_tile_edges(const int *edge_tiles, const int *count, const int *offset, const int *refs_in,
                                   int *refs_out) {
@@ -256,72 +271,98 @@ struct TieTable {
     int capacity;
 };
 
-// Forward, kernel 1 of 3 - z-buffer and owner ids of one 16x16 tile (no colour work: few registers, short critical
-// path).  Small triangles: triangle-parallel on a shared-memory tile z-buffer fed by TMA bulk copies; large triangles:
-// pixel-parallel over per-row-pair coverage masks.
-__global__ void __launch_bounds__(NT, 4) k_tile_z(SceneView s, int tiles_x, TriBins bins, TieTable ties, double *z_buffer,
-                                               int *owner, int *face_id) {
+// Forward, kernel 1 of 3 - z-buffer and owner ids, one 16x16 tile at a time (no colour work: few registers).
+// PERSISTENT CTAs (4 per SM) walk the tiles with a stride of gridDim.x and a two-stage TMA pipeline: while the CTA
+// z-tests tile i out of buffer `cur`, thread 0 has already issued the bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP)
+// of tile i+1's pre-masked records into the other buffer, so neither the list-size loads nor the copy latency sit on
+// the critical path of a tile.  Small triangles: records -> row-pair-major masks -> pixel-parallel exact z test;
+// large triangles: per-thread stencil + row spans -> the same masks.
+__global__ void __launch_bounds__(NT, 4) k_tile_z(SceneView s, int tiles_x, int num_tiles, TriBins bins, TieTable ties,
+                                                  double *z_buffer, int *owner, int *face_id) {
     __shared__ TileShared sh;
-    __shared__ alignas(8) uint64_t list_barrier;
-    const int tile_id = blockIdx.x, tid = threadIdx.x;
-    const Tile tile = tile_of(tile_id, tiles_x);
-    const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
-    const bool inside = x < s.width && y < s.height;
+    __shared__ alignas(16) PreRec pre[2][PRE_CHUNK];
+    __shared__ alignas(8) uint64_t bar[2];
+    __shared__ int info[2][2];  // [buffer][0] = number of small records of the tile, [1] = offset of its list
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+    }
+    uint32_t parity0 = 0, parity1 = 0;
 
-    PixelState<1> p;
-    p.z = __longlong_as_double(0x7ff0000000000000LL);
-    p.own = -1;
-    p.bown = -1;
+    // thread 0: fetch the list size of tile t and start the copy of its first chunk into buffer b
+    auto prefetch = [&](int t, int b) {
+        if (tid != 0 || t >= num_tiles) return;
+        const int n = bins.small_cursor[t], off = bins.small_offset[t];
+        info[b][0] = n;
+        info[b][1] = off;
+        const int m = min(n, PRE_CHUNK);
+        if (m > 0) {
+            mbar_expect_tx(&bar[b], (uint32_t)(m * sizeof(PreRec)));
+            bulk_load(pre[b], bins.small_recs + off, (uint32_t)(m * sizeof(PreRec)), &bar[b]);
+        }
+    };
+    __syncthreads();  // barriers initialised
+    int cur = 0;
+    prefetch(blockIdx.x, 0);
+    for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, cur ^= 1) {
+        __syncthreads();  // info[cur] is visible; everybody is done with buffer cur^1 and with sh (previous tile)
+        const int n_small = info[cur][0];
+        const PreRec *list = bins.small_recs + info[cur][1];
+        prefetch(tile_id + gridDim.x, cur ^ 1);  // overlaps with the work on this tile
 
-    // small triangles: the tile's pre-masked records are one contiguous array; each chunk is pulled into shared
-    // memory by a single bulk (TMA) copy issued by thread 0 and awaited by everybody on an mbarrier, then transposed
-    // into the row-pair-major mask layout and z-tested by the pixel threads
-    const int n_small = bins.small_cursor[tile_id];
-    if (n_small > 0) {
-        const PreRec *list = bins.small_recs + bins.small_offset[tile_id];
-        if (tid == 0) mbar_init(&list_barrier, 1);
-        __syncthreads();
-        uint32_t parity = 0;
-        for (int base = 0; base < n_small; base += TRI_CHUNK) {
-            const int m = min(TRI_CHUNK, n_small - base);
-            if (tid == 0) {
-                mbar_expect_tx(&list_barrier, (uint32_t)(m * sizeof(PreRec)));
-                bulk_load(sh.tri.pre, list + base, (uint32_t)(m * sizeof(PreRec)), &list_barrier);
+        const Tile tile = tile_of(tile_id, tiles_x);
+        const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+        const bool inside = x < s.width && y < s.height;
+        PixelState<1> p;
+        p.z = __longlong_as_double(0x7ff0000000000000LL);
+        p.own = -1;
+        p.bown = -1;
+
+        for (int base = 0; base < n_small; base += PRE_CHUNK) {
+            const int m = min(PRE_CHUNK, n_small - base);
+            if (base > 0) {  // tiles with more than one chunk: the later chunks are fetched synchronously
+                __syncthreads();  // buffer cur fully consumed
+                if (tid == 0) {
+                    mbar_expect_tx(&bar[cur], (uint32_t)(m * sizeof(PreRec)));
+                    bulk_load(pre[cur], list + base, (uint32_t)(m * sizeof(PreRec)), &bar[cur]);
+                }
             }
-            mbar_wait(&list_barrier, parity);
-            parity ^= 1u;
-            phase_pre_unpack(tid, m, sh.tri.pre, &sh);
+            if (cur == 0) { mbar_wait(&bar[0], parity0); parity0 ^= 1u; }
+            else          { mbar_wait(&bar[1], parity1); parity1 ^= 1u; }
+            phase_pre_unpack(tid, m, pre[cur], &sh);
             __syncthreads();
             if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
             __syncthreads();
         }
-    }
-    // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
-    const int n_large = bins.large_count[tile_id];
-    if (n_large > 0) {
-        const int *list = bins.large_refs + bins.large_offset[tile_id];
-        for (int base = 0; base < n_large; base += TRI_CHUNK) {
-            const int m = min(TRI_CHUNK, n_large - base);
-            phase_tri_setup(s, tid, m, list + base, tile, &sh);
-            __syncthreads();
-            if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
-            __syncthreads();
+        // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
+        const int n_large = bins.large_count[tile_id];
+        if (n_large > 0) {
+            const int *large = bins.large_refs + bins.large_offset[tile_id];
+            for (int base = 0; base < n_large; base += TRI_CHUNK) {
+                const int m = min(TRI_CHUNK, n_large - base);
+                phase_tri_setup(s, tid, m, large + base, tile, &sh);
+                __syncthreads();
+                if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
+                __syncthreads();
+            }
+        }
+        if (inside) {
+            const size_t idx = (size_t)y * s.width + x;
+            z_buffer[idx] = p.z;
+            int code = p.bown;
+            if (p.own != p.bown) {  // exact z tie between distinct triangles: keep both ids in the side table
+                int slot = atomicAdd(ties.counter, 1);
+                if (slot < ties.capacity) {
+                    ties.pairs[2 * slot] = p.own;
+                    ties.pairs[2 * slot + 1] = p.bown;
+                    code = -2 - slot;
+                }
+            }
+            owner[idx] = code;
+            if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
         }
     }
-    if (!inside) return;
-    const size_t idx = (size_t)y * s.width + x;
-    z_buffer[idx] = p.z;
-    int code = p.bown;
-    if (p.own != p.bown) {  // exact z tie between distinct triangles: keep both ids in the side table
-        int slot = atomicAdd(ties.counter, 1);
-        if (slot < ties.capacity) {
-            ties.pairs[2 * slot] = p.own;
-            ties.pairs[2 * slot + 1] = p.bown;
-            code = -2 - slot;
-        }
-    }
-    owner[idx] = code;
-    if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
 }
 
 // decodes an owner code into (forward owner, adjoint owner); -1 = background
@@ -555,7 +596,9 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
                        float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
     {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
-        k_tile_z<<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ws->bins, ties, z, owner, face_id);
+        const int persistent = sm_count_cached > 0 ? 4 * sm_count_cached : 592;
+        k_tile_z<<<ws->num_tiles < persistent ? ws->num_tiles : persistent, NT, 0, st>>>(
+            s, ws->tiles_x, ws->num_tiles, ws->bins, ties, z, owner, face_id);
     }
     {
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
@@ -564,7 +607,7 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     ws->launches += 2;
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
-        k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles.as<int>(), edge_count,
+        k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles_ptr, edge_count,
                                                             ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                             ws->edge_recs.as<EdgeRec>(), z, image);
         ws->launches++;
@@ -589,7 +632,7 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     }
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, st);
-        k_raster_bwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles.as<int>(), edge_count,
+        k_raster_bwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles_ptr, edge_count,
                                                               ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                               ws->edge_recs.as<EdgeRec>(), ties, z,
                                                          owner, image_b, g, ws->edge_acc.as<double>());
@@ -699,7 +742,7 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
 void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    DevBuf *bufs[] = {&ws->zeroed, &ws->large_tiles, &ws->edge_tiles, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
+    DevBuf *bufs[] = {&ws->zeroed, &ws->large_tiles, &ws->edge_tiles, &ws->edge_tiles_lpt, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
                       &ws->edge_ids_tmp, &ws->edge_rank, &ws->edge_recs,
                       &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
                       &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
@@ -773,6 +816,8 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     rc |= ws->small_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->large_tiles.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_tiles.ensure(tile_bytes, &ws->bytes);
+    rc |= ws->edge_tiles_lpt.ensure(tile_bytes, &ws->bytes);
+    ws->edge_tiles_ptr = ws->edge_tiles.as<int>();
     rc |= ws->tri_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_ids.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
@@ -888,6 +933,12 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     }
     if (E > 0 && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, st);
+        if (ws->num_edge_tiles <= 16384) {  // above that the O(n^2) ordering is not worth it: keep raster order
+            k_order_edge_tiles<<<1, 1024, 0, st>>>(ws->edge_tiles.as<int>(), ws->num_edge_tiles, edge_count_buf,
+                                                   ws->edge_tiles_lpt.as<int>());
+            ws->launches++;
+            ws->edge_tiles_ptr = ws->edge_tiles_lpt.as<int>();
+        }
         k_sort_tile_edges<<<ws->num_edge_tiles, 128, 0, st>>>(ws->edge_tiles.as<int>(), edge_count_buf,
                                                               ws->edge_offset.as<int>(), ws->edge_refs_tmp.as<int>(),
                                                               ws->edge_refs.as<int>());

@@ -13,6 +13,7 @@ namespace deodr {
 constexpr int TS = 16;            // tile side in pixels
 constexpr int NT = TS * TS;       // threads per tile CTA, one per pixel
 constexpr int TRI_CHUNK = 256;    // triangles staged in shared memory per pass (one per thread)
+constexpr int PRE_CHUNK = 128;    // pre-masked records per TMA bulk copy (double-buffered landing zone: 2 x 8 KB)
 constexpr int EDGE_CHUNK = 64;    // edge records staged in shared memory per pass
 #ifndef DEODR_EDGE_ROWS
 #define DEODR_EDGE_ROWS 16
@@ -54,7 +55,6 @@ constexpr int TRI_INDEX_MASK = 0x3fffffff;
 struct TileShared {
     union {
         struct {
-            PreRec pre[TRI_CHUNK];  // small triangles: bulk-copy (TMA) landing zone of the pre-masked records
             TriRec rec[TRI_CHUNK];
             // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
             // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time

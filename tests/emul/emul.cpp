@@ -60,11 +60,12 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
             for (int tid = 0; tid < NT; tid++) { px[tid].z = std::numeric_limits<double>::infinity(); px[tid].own = px[tid].bown = -1; }
             auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
             const int n_small = st.small_cursor[tile_id];
-            for (int base = 0; base < n_small; base += TRI_CHUNK) {
-                const int m = std::min(TRI_CHUNK, n_small - base);
-                // the device pulls the chunk into sh->tri.pre with one bulk (TMA) copy; same bytes here
-                memcpy(sh->tri.pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
-                for (int tid = 0; tid < NT; tid++) phase_pre_unpack(tid, m, sh->tri.pre, sh);
+            for (int base = 0; base < n_small; base += PRE_CHUNK) {
+                const int m = std::min(PRE_CHUNK, n_small - base);
+                // the device pulls the chunk into shared memory with one bulk (TMA) copy; same bytes here
+                PreRec pre[PRE_CHUNK];
+                memcpy(pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
+                for (int tid = 0; tid < NT; tid++) phase_pre_unpack(tid, m, pre, sh);
                 for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<1>(s, tid, m, tile, sh, &px[tid]);
             }
             const int n_large = st.large_count[tile_id];
