@@ -18,6 +18,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -163,6 +164,36 @@ __global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *
     if (partial) atomicAdd(&rank[i], partial);
 }
 
+// Far-to-near order for up to 8192 silhouette edges (E ~ sqrt(T): the common case) - bitonic sort of (key, id) pairs in
+// the shared memory of ONE CTA (96 KB dynamic), 91 compare-exchange sweeps for 8192 elements.
+__global__ void __launch_bounds__(1024) k_sort_edges_bitonic(EdgeList edges, int n, int npad, int *edge_sorted) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    int *ids = reinterpret_cast<int *>(keys + npad);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        keys[i] = i < n ? edges.keys[i] : ~0ull;  // padding sorts last
+        ids[i] = i < n ? edges.ids[i] : 0x7fffffff;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long ka = keys[i], kb = keys[l];
+                    const int ia = ids[i], ib = ids[l];
+                    const bool a_after_b = ka > kb || (ka == kb && ia > ib);
+                    if (a_after_b == ((i & k) == 0)) {
+                        keys[i] = kb; keys[l] = ka;
+                        ids[i] = ib; ids[l] = ia;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) edge_sorted[i] = ids[i];
+}
+
 // edge_sorted[rank] = id, and the edge's band stencil record (DR.h:1366-1460 + z plane) at the same rank: built ONCE
 // per forward pass, not per tile.
 __global__ void k_scatter_edges(SceneView s, EdgeList edges, int n, double sigma, int *edge_sorted, EdgeRec *recs) {
@@ -242,14 +273,15 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // crowded tiles, which must therefore start first.  Rank counting on the edge counts (descending), a few thousand tiles.
 __global__ void __launch_bounds__(1024) k_order_edge_tiles(const int *tiles_in, int n, const int *edge_count,
                                                            int *tiles_out) {
+    __shared__ int cnt[8192];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cnt[i] = edge_count[tiles_in[i]];
+    __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int t = tiles_in[i], c = edge_count[t];
+        const int c = cnt[i];
         int pos = 0;
-        for (int j = 0; j < n; j++) {
-            const int cj = edge_count[tiles_in[j]];
-            pos += (cj > c) || (cj == c && j < i);
-        }
-        tiles_out[pos] = t;
+#pragma unroll 8
+        for (int j = 0; j < n; j++) pos += (int)(cnt[j] > c) | ((int)(cnt[j] == c) & (int)(j < i));
+        tiles_out[pos] = tiles_in[i];
     }
 }
 
@@ -290,26 +322,34 @@ __global__ void __launch_bounds__(NT, 4) k_tile_z(SceneView s, int tiles_x, int 
     }
     uint32_t parity0 = 0, parity1 = 0;
 
-    // thread 0: fetch the list size of tile t and start the copy of its first chunk into buffer b
-    auto prefetch = [&](int t, int b) {
+    // thread 0 runs a two-deep software pipeline: the list size / offset of tile i+2 are LOADED (registers nn, noff)
+    // while the copy of tile i+1 is ISSUED from values loaded one iteration earlier, so the loads' latency never stalls
+    // warp 0 (which also does pixel work).
+    int nn = 0, noff = 0;
+    auto load_info = [&](int t) {
+        if (tid == 0 && t < num_tiles) { nn = bins.small_cursor[t]; noff = bins.small_offset[t]; }
+    };
+    auto issue = [&](int t, int b) {  // publish (nn, noff) for tile t and start the copy of its first chunk
         if (tid != 0 || t >= num_tiles) return;
-        const int n = bins.small_cursor[t], off = bins.small_offset[t];
-        info[b][0] = n;
-        info[b][1] = off;
-        const int m = min(n, PRE_CHUNK);
+        info[b][0] = nn;
+        info[b][1] = noff;
+        const int m = min(nn, PRE_CHUNK);
         if (m > 0) {
             mbar_expect_tx(&bar[b], (uint32_t)(m * sizeof(PreRec)));
-            bulk_load(pre[b], bins.small_recs + off, (uint32_t)(m * sizeof(PreRec)), &bar[b]);
+            bulk_load(pre[b], bins.small_recs + noff, (uint32_t)(m * sizeof(PreRec)), &bar[b]);
         }
     };
     __syncthreads();  // barriers initialised
     int cur = 0;
-    prefetch(blockIdx.x, 0);
+    load_info(blockIdx.x);
+    issue(blockIdx.x, 0);
+    load_info(blockIdx.x + gridDim.x);
     for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, cur ^= 1) {
         __syncthreads();  // info[cur] is visible; everybody is done with buffer cur^1 and with sh (previous tile)
         const int n_small = info[cur][0];
         const PreRec *list = bins.small_recs + info[cur][1];
-        prefetch(tile_id + gridDim.x, cur ^ 1);  // overlaps with the work on this tile
+        issue(tile_id + gridDim.x, cur ^ 1);        // overlaps with the work on this tile
+        load_info(tile_id + 2 * gridDim.x);         // consumed by the next iteration's issue()
 
         const Tile tile = tile_of(tile_id, tiles_x);
         const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
@@ -596,7 +636,10 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
                        float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
     {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
-        const int persistent = sm_count_cached > 0 ? 4 * sm_count_cached : 592;
+        // DEODR_B200_TILEZ_CTAS_PER_SM: persistent CTAs per SM (default 4 = what 64 registers allow); 0 = one CTA per
+        // tile (the same kernel then runs its loop once) - kept for A/B measurements
+        static const int per_sm = getenv("DEODR_B200_TILEZ_CTAS_PER_SM") ? atoi(getenv("DEODR_B200_TILEZ_CTAS_PER_SM")) : 4;
+        const int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : ws->num_tiles;
         k_tile_z<<<ws->num_tiles < persistent ? ws->num_tiles : persistent, NT, 0, st>>>(
             s, ws->tiles_x, ws->num_tiles, ws->bins, ties, z, owner, face_id);
     }
@@ -891,7 +934,20 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     // ---- far-to-near order of the silhouette edges (DR.h:2781)
     if (E > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, st);
-        if (E <= 65536) {
+        if (E <= 8192) {
+            int npad = 2;
+            while (npad < E) npad <<= 1;
+            static bool attr_set = false;
+            if (!attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(k_sort_edges_bitonic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              8192 * 12));
+                attr_set = true;
+            }
+            k_sort_edges_bitonic<<<1, 1024, (size_t)npad * 12, st>>>(edges, E, npad, ws->edge_sorted.as<int>());
+            k_edge_records<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), E, sigma,
+                                                             ws->edge_recs.as<EdgeRec>());
+            ws->launches += 2;
+        } else if (E <= 65536) {
             dim3 grid(grid_for(E, 256), grid_for(E, 1024));
             k_rank_edges<<<grid, 256, 0, st>>>(edges, E, ws->edge_rank.as<int>());
             k_scatter_edges<<<grid_for(E, 128), 128, 0, st>>>(s, edges, E, sigma, ws->edge_sorted.as<int>(),
@@ -933,7 +989,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     }
     if (E > 0 && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, st);
-        if (ws->num_edge_tiles <= 16384) {  // above that the O(n^2) ordering is not worth it: keep raster order
+        if (ws->num_edge_tiles <= 8192) {  // above that the O(n^2) ordering is not worth it: keep raster order
             k_order_edge_tiles<<<1, 1024, 0, st>>>(ws->edge_tiles.as<int>(), ws->num_edge_tiles, edge_count_buf,
                                                    ws->edge_tiles_lpt.as<int>());
             ws->launches++;
