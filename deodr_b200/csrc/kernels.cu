@@ -136,13 +136,14 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
 }
 
 // Far-to-near order of the appended silhouette edges by rank counting (DR.h:2781; ties by id).  2-D grid: CTA (bx, by)
-// counts, for its 256 edges i, the edges j of chunk by (1024 keys staged in shared memory) that precede them, and adds
+// counts, for its 256 edges i, the edges j of chunk by (256 keys staged in shared memory) that precede them, and adds
 // the partial count to rank[i]; k_scatter_edges then writes edge_sorted[rank[i]] = ids[i].
+constexpr int RANK_CHUNK = 256;  // keys per CTA: E/256 x E/256 CTAs keep the whole chip busy for a few thousand edges
 __global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *rank) {
-    __shared__ unsigned long long sk[1024];
-    __shared__ int si[1024];
+    __shared__ unsigned long long sk[RANK_CHUNK];
+    __shared__ int si[RANK_CHUNK];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int base = blockIdx.y * 1024, m = min(1024, n - base);
+    const int base = blockIdx.y * RANK_CHUNK, m = min(RANK_CHUNK, n - base);
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         sk[j] = edges.keys[base + j];
         si[j] = edges.ids[base + j];
@@ -162,36 +163,6 @@ __global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *
     if (equal > 0)
         for (int j = 0; j < m; j++) partial += (int)(sk[j] == key) & (int)(si[j] < id);
     if (partial) atomicAdd(&rank[i], partial);
-}
-
-// Far-to-near order for up to 8192 silhouette edges (E ~ sqrt(T): the common case) - bitonic sort of (key, id) pairs in
-// the shared memory of ONE CTA (96 KB dynamic), 91 compare-exchange sweeps for 8192 elements.
-__global__ void __launch_bounds__(1024) k_sort_edges_bitonic(EdgeList edges, int n, int npad, int *edge_sorted) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
-    int *ids = reinterpret_cast<int *>(keys + npad);
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-        keys[i] = i < n ? edges.keys[i] : ~0ull;  // padding sorts last
-        ids[i] = i < n ? edges.ids[i] : 0x7fffffff;
-    }
-    __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const unsigned long long ka = keys[i], kb = keys[l];
-                    const int ia = ids[i], ib = ids[l];
-                    const bool a_after_b = ka > kb || (ka == kb && ia > ib);
-                    if (a_after_b == ((i & k) == 0)) {
-                        keys[i] = kb; keys[l] = ka;
-                        ids[i] = ib; ids[l] = ia;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) edge_sorted[i] = ids[i];
 }
 
 // edge_sorted[rank] = id, and the edge's band stencil record (DR.h:1366-1460 + z plane) at the same rank: built ONCE
@@ -267,22 +238,6 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
-}
-
-// Longest-processing-time-first order of the tiles that have silhouette edges: the edge kernels are bound by their most
-// crowded tiles, which must therefore start first.  Rank counting on the edge counts (descending), a few thousand tiles.
-__global__ void __launch_bounds__(1024) k_order_edge_tiles(const int *tiles_in, int n, const int *edge_count,
-                                                           int *tiles_out) {
-    __shared__ int cnt[8192];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) cnt[i] = edge_count[tiles_in[i]];
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int c = cnt[i];
-        int pos = 0;
-#pragma unroll 8
-        for (int j = 0; j < n; j++) pos += (int)(cnt[j] > c) | ((int)(cnt[j] == c) & (int)(j < i));
-        tiles_out[pos] = tiles_in[i];
-    }
 }
 
 // Orders every tile's edge list by far-to-near rank (ranks are unique): rank-counting sort, one CTA per tile.
@@ -379,9 +334,11 @@ __global__ void __launch_bounds__(NT, 4) k_tile_z(SceneView s, int tiles_x, int 
         const int n_large = bins.large_count[tile_id];
         if (n_large > 0) {
             const int *large = bins.large_refs + bins.large_offset[tile_id];
-            for (int base = 0; base < n_large; base += TRI_CHUNK) {
-                const int m = min(TRI_CHUNK, n_large - base);
-                phase_tri_setup(s, tid, m, large + base, tile, &sh);
+            for (int base = 0; base < n_large; base += LARGE_CHUNK) {
+                const int m = min(LARGE_CHUNK, n_large - base);
+                phase_tri_setup(s, tid, m, large + base, &sh);
+                __syncthreads();
+                phase_tri_masks(s, tid, m, tile, &sh);
                 __syncthreads();
                 if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
                 __syncthreads();
@@ -636,9 +593,11 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
                        float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
     {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
-        // DEODR_B200_TILEZ_CTAS_PER_SM: persistent CTAs per SM (default 4 = what 64 registers allow); 0 = one CTA per
-        // tile (the same kernel then runs its loop once) - kept for A/B measurements
-        static const int per_sm = getenv("DEODR_B200_TILEZ_CTAS_PER_SM") ? atoi(getenv("DEODR_B200_TILEZ_CTAS_PER_SM")) : 4;
+        // DEODR_B200_TILEZ_CTAS_PER_SM = k > 0 runs k persistent CTAs per SM with the two-stage TMA pipeline; default 0 =
+        // one CTA per tile (the same kernel, its loop runs once).  Measured on B200, 1M-triangle scene: 168 us per-tile
+        // vs 199 us persistent x4 vs 300 us persistent x2 - the hardware CTA scheduler balances the very uneven tiles
+        // better than a static stride, and 4 resident CTAs already overlap each other's copy latency.
+        static const int per_sm = getenv("DEODR_B200_TILEZ_CTAS_PER_SM") ? atoi(getenv("DEODR_B200_TILEZ_CTAS_PER_SM")) : 0;
         const int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : ws->num_tiles;
         k_tile_z<<<ws->num_tiles < persistent ? ws->num_tiles : persistent, NT, 0, st>>>(
             s, ws->tiles_x, ws->num_tiles, ws->bins, ties, z, owner, face_id);
@@ -785,7 +744,7 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
 void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    DevBuf *bufs[] = {&ws->zeroed, &ws->large_tiles, &ws->edge_tiles, &ws->edge_tiles_lpt, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
+    DevBuf *bufs[] = {&ws->zeroed, &ws->large_tiles, &ws->edge_tiles, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
                       &ws->edge_ids_tmp, &ws->edge_rank, &ws->edge_recs,
                       &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
                       &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
@@ -859,7 +818,6 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     rc |= ws->small_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->large_tiles.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_tiles.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->edge_tiles_lpt.ensure(tile_bytes, &ws->bytes);
     ws->edge_tiles_ptr = ws->edge_tiles.as<int>();
     rc |= ws->tri_offset.ensure(tile_bytes, &ws->bytes);
     rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
@@ -934,21 +892,8 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     // ---- far-to-near order of the silhouette edges (DR.h:2781)
     if (E > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, st);
-        if (E <= 8192) {
-            int npad = 2;
-            while (npad < E) npad <<= 1;
-            static bool attr_set = false;
-            if (!attr_set) {
-                CUDA_TRY(cudaFuncSetAttribute(k_sort_edges_bitonic, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              8192 * 12));
-                attr_set = true;
-            }
-            k_sort_edges_bitonic<<<1, 1024, (size_t)npad * 12, st>>>(edges, E, npad, ws->edge_sorted.as<int>());
-            k_edge_records<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), E, sigma,
-                                                             ws->edge_recs.as<EdgeRec>());
-            ws->launches += 2;
-        } else if (E <= 65536) {
-            dim3 grid(grid_for(E, 256), grid_for(E, 1024));
+        if (E <= 65536) {
+            dim3 grid(grid_for(E, 256), grid_for(E, RANK_CHUNK));
             k_rank_edges<<<grid, 256, 0, st>>>(edges, E, ws->edge_rank.as<int>());
             k_scatter_edges<<<grid_for(E, 128), 128, 0, st>>>(s, edges, E, sigma, ws->edge_sorted.as<int>(),
                                                                ws->edge_recs.as<EdgeRec>());
@@ -989,12 +934,6 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     }
     if (E > 0 && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, st);
-        if (ws->num_edge_tiles <= 8192) {  // above that the O(n^2) ordering is not worth it: keep raster order
-            k_order_edge_tiles<<<1, 1024, 0, st>>>(ws->edge_tiles.as<int>(), ws->num_edge_tiles, edge_count_buf,
-                                                   ws->edge_tiles_lpt.as<int>());
-            ws->launches++;
-            ws->edge_tiles_ptr = ws->edge_tiles_lpt.as<int>();
-        }
         k_sort_tile_edges<<<ws->num_edge_tiles, 128, 0, st>>>(ws->edge_tiles.as<int>(), edge_count_buf,
                                                               ws->edge_offset.as<int>(), ws->edge_refs_tmp.as<int>(),
                                                               ws->edge_refs.as<int>());

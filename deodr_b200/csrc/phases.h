@@ -14,6 +14,7 @@ constexpr int TS = 16;            // tile side in pixels
 constexpr int NT = TS * TS;       // threads per tile CTA, one per pixel
 constexpr int TRI_CHUNK = 256;    // triangles staged in shared memory per pass (one per thread)
 constexpr int PRE_CHUNK = 128;    // pre-masked records per TMA bulk copy (double-buffered landing zone: 2 x 8 KB)
+constexpr int LARGE_CHUNK = 64;   // large triangles staged per pass (stencil records kept in shared memory)
 constexpr int EDGE_CHUNK = 64;    // edge records staged in shared memory per pass
 #ifndef DEODR_EDGE_ROWS
 #define DEODR_EDGE_ROWS 16
@@ -55,6 +56,7 @@ constexpr int TRI_INDEX_MASK = 0x3fffffff;
 struct TileShared {
     union {
         struct {
+            TriGeom geo[LARGE_CHUNK];  // large triangles: stencils, so that their row spans are computed by 8 threads each
             TriRec rec[TRI_CHUNK];
             // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
             // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time
@@ -356,27 +358,37 @@ DEODR_HD void phase_pre_unpack(int tid, int n, const PreRec *pre, TileShared *sh
     rec.id = r.id;
 }
 
-// Phase T1b: thread tid < n sets up LARGE triangle list[tid] (stencil equations stay in registers) and writes its z
-// plane and its coverage masks of the 16 tile rows; padding as above.
-DEODR_HD void phase_tri_setup(const SceneView &s, int tid, int n, const int *list, Tile tile, TileShared *sh) {
-    if (tid >= n) {
-        if (tid < ((n + 3) & ~3))
-            for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = 0u;
-        return;
-    }
+// Phase T1b: thread tid < n sets up the stencil of LARGE triangle list[tid] into shared memory (n <= LARGE_CHUNK).
+DEODR_HD void phase_tri_setup(const SceneView &s, int tid, int n, const int *list, TileShared *sh) {
+    if (tid >= n) return;
     const int k = list[tid];
     uint32_t vid[3];
     double V[3][2], Zv[3];
     gather_tri(s, k, vid, V, Zv);
     remove_offset(V, 3, pixel_offset(s));
-    TriGeom g;
+    TriGeom &g = sh->tri.geo[tid];
     tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
     TriRec &rec = sh->tri.rec[tid];
     canonical_plane(g.zp, rec.zp);
     rec.id = k;
-    int y_first, y_last;
-    tri_row_range(g, s.height, &y_first, &y_last);
-    for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = tri_pair_mask(s, g, y_first, y_last, tile.x0, tile.y0, p);
+}
+
+// Phase T1c: (triangle, row pair) items -> coverage masks; 8 threads per large triangle instead of one, which shortens
+// the critical path of every tile that holds a large triangle 4x (measured: that barrier was 32 % of k_tile_z's stalls).
+// Triangles up to the next multiple of 4 get empty masks (padding).
+DEODR_HD void phase_tri_masks(const SceneView &s, int tid, int n, Tile tile, TileShared *sh) {
+    const int n4 = (n + 3) & ~3;
+    for (int item = tid; item < n4 * (TS / 2); item += NT) {
+        const int t = item / (TS / 2), p = item % (TS / 2);
+        uint32_t m = 0u;
+        if (t < n) {
+            const TriGeom &g = sh->tri.geo[t];
+            int y_first, y_last;
+            tri_row_range(g, s.height, &y_first, &y_last);
+            m = tri_pair_mask(s, g, y_first, y_last, tile.x0, tile.y0, p);
+        }
+        sh->tri.mask[p][t] = m;
+    }
 }
 
 // Phase T2: each pixel walks the chunk and keeps the minimum z, order-independently:

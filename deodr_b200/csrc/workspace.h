@@ -70,7 +70,7 @@ struct DeodrWorkspace {
     DevBuf small_offset, small_recs, tri_offset, tri_refs;
     DevBuf small_ids, large_ids;  // compacted lists of the drawn triangles (count pass), reused by the adjoint
     int num_small = 0, num_large = 0;
-    DevBuf large_tiles, edge_tiles, edge_tiles_lpt;
+    DevBuf large_tiles, edge_tiles;
     int *edge_tiles_ptr = nullptr;  // the list the edge kernels walk (LPT order when built)  // compact lists of the tiles with large triangles / silhouette edges
     int num_large_tiles = 0, num_edge_tiles = 0;
     DevBuf edge_recs;            // per-edge band stencils in far-to-near order (k_edge_records)

@@ -69,10 +69,11 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
                 for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<1>(s, tid, m, tile, sh, &px[tid]);
             }
             const int n_large = st.large_count[tile_id];
-            for (int base = 0; base < n_large; base += TRI_CHUNK) {
-                const int m = std::min(TRI_CHUNK, n_large - base);
+            for (int base = 0; base < n_large; base += LARGE_CHUNK) {
+                const int m = std::min(LARGE_CHUNK, n_large - base);
                 for (int tid = 0; tid < NT; tid++)
-                    phase_tri_setup(s, tid, m, st.large_refs.data() + st.large_offset[tile_id] + base, tile, sh);
+                    phase_tri_setup(s, tid, m, st.large_refs.data() + st.large_offset[tile_id] + base, sh);
+                for (int tid = 0; tid < NT; tid++) phase_tri_masks(s, tid, m, tile, sh);
                 for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<1>(s, tid, m, tile, sh, &px[tid]);
             }
             for (int tid = 0; tid < NT; tid++) {
