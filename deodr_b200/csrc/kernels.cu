@@ -37,6 +37,7 @@ struct DevEnv {
     static __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
     static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
     static __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
+    static __device__ __forceinline__ int shared_inc(int *p) { return atomicAdd(p, 1); }  // p in shared memory
 };
 
 // Vertex-gradient scatter of the interior adjoint.  When every participating lane of the warp has the same owner
@@ -92,18 +93,35 @@ struct ScanJob {
 };
 
 // One 64-bit scan carries both the running sum of the counts (low word) and the number of non-empty tiles (high word).
+// Each thread owns SCAN_IPT consecutive tiles, so 16384 tiles take ONE block scan instead of sixteen; counts and
+// offsets pass through a padded shared-memory stage so that every global access stays coalesced (the kernel runs on
+// three SMs only: 16 uncoalesced wavefronts per load instruction would be its whole duration).
+constexpr int SCAN_IPT = 16;
+constexpr int SCAN_TILE = 1024 * SCAN_IPT;
+constexpr int SCAN_SMEM = (SCAN_TILE + SCAN_TILE / 32) * (int)sizeof(int);
+static __device__ __forceinline__ int scan_slot(int i) { return i + (i >> 5); }  // conflict-free for stride-16 readers
 __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *totals) {
+    extern __shared__ int stage[];
     __shared__ unsigned long long warp_sums[32];
     const int *count = job.count[blockIdx.x];
     int *offset = job.offset[blockIdx.x];
     int *nonempty = job.nonempty[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long carry = 0;
-    int next = tid < n ? count[tid] : 0;
-    for (int base = 0; base < n; base += 1024) {
-        const int idx = base + tid, c = next;
-        next = idx + 1024 < n ? count[idx + 1024] : 0;  // coalesced prefetch of the next chunk
-        const unsigned long long v = (unsigned long long)(unsigned)c | ((unsigned long long)(c > 0) << 32);
+    for (int base = 0; base < n; base += SCAN_TILE) {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) {
+            const int i = k * 1024 + tid;
+            stage[scan_slot(i)] = base + i < n ? count[base + i] : 0;
+        }
+        __syncthreads();
+        const int first = tid * SCAN_IPT;
+        int c[SCAN_IPT];
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) c[k] = stage[scan_slot(first + k)];
+        unsigned long long v = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) v += (unsigned long long)(unsigned)c[k] | ((unsigned long long)(c[k] > 0) << 32);
         unsigned long long incl = v;
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -120,12 +138,20 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
             warp_sums[lane] = w;
         }
         __syncthreads();
-        const unsigned long long excl = carry + (warp ? warp_sums[warp - 1] : 0ull) + incl - v;
-        if (idx < n) {
-            offset[idx] = (int)(unsigned)excl;
-            if (nonempty && c > 0) nonempty[(int)(excl >> 32)] = idx;
+        unsigned long long run = carry + (warp ? warp_sums[warp - 1] : 0ull) + incl - v;
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) {
+            stage[scan_slot(first + k)] = (int)(unsigned)run;
+            if (nonempty && c[k] > 0) nonempty[(int)(run >> 32)] = base + first + k;
+            run += (unsigned long long)(unsigned)c[k] | ((unsigned long long)(c[k] > 0) << 32);
         }
         carry += warp_sums[31];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) {
+            const int i = k * 1024 + tid;
+            if (base + i < n) offset[base + i] = stage[scan_slot(i)];
+        }
         __syncthreads();
     }
     if (tid == 0) {
@@ -141,27 +167,32 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
 constexpr int RANK_CHUNK = 256;  // keys per CTA: E/256 x E/256 CTAs keep the whole chip busy for a few thousand edges
 __global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *rank) {
     __shared__ unsigned long long sk[RANK_CHUNK];
+    __shared__ uint32_t shi[RANK_CHUNK];
     __shared__ int si[RANK_CHUNK];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int base = blockIdx.y * RANK_CHUNK, m = min(RANK_CHUNK, n - base);
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         sk[j] = edges.keys[base + j];
+        shi[j] = (uint32_t)(sk[j] >> 32);
         si[j] = edges.ids[base + j];
     }
     __syncthreads();
     if (i >= n) return;
     const unsigned long long key = edges.keys[i];
+    const uint32_t key_hi = (uint32_t)(key >> 32);
     const int id = edges.ids[i];
-    // keys are almost always distinct: count the smaller keys and the equal ones; only when another edge shares the
-    // key (same triangle, or an exactly equal depth sum) is the id tie-break loop run
+    // the high words (sign, exponent, 20 mantissa bits of the depth sum) decide almost every comparison: count them
+    // with 32-bit compares; only when another edge shares the high word (same triangle, nearly equal depth sums, the
+    // edge itself on the diagonal chunks) is the full (key, id) comparison run
     int partial = 0, equal = 0;
 #pragma unroll 8
     for (int j = 0; j < m; j++) {
-        partial += (int)(sk[j] < key);
-        equal += (int)(sk[j] == key);
+        partial += (int)(shi[j] < key_hi);
+        equal += (int)(shi[j] == key_hi);
     }
     if (equal > 0)
-        for (int j = 0; j < m; j++) partial += (int)(sk[j] == key) & (int)(si[j] < id);
+        for (int j = 0; j < m; j++)
+            if (shi[j] == key_hi) partial += (int)(sk[j] < key || (sk[j] == key && si[j] < id));
     if (partial) atomicAdd(&rank[i], partial);
 }
 
@@ -271,6 +302,7 @@ __global__ void __launch_bounds__(NT, 4) k_tile_z(SceneView s, int tiles_x, int 
     __shared__ alignas(8) uint64_t bar[2];
     __shared__ int info[2][2];  // [buffer][0] = number of small records of the tile, [1] = offset of its list
     const int tid = threadIdx.x;
+    sh.tri.pix_cnt[tid] = 0;
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -325,9 +357,9 @@ __global__ void __launch_bounds__(NT, 4) k_tile_z(SceneView s, int tiles_x, int 
             }
             if (cur == 0) { mbar_wait(&bar[0], parity0); parity0 ^= 1u; }
             else          { mbar_wait(&bar[1], parity1); parity1 ^= 1u; }
-            phase_pre_unpack(tid, m, pre[cur], &sh);
+            phase_pre_scatter<DevEnv>(tid, m, pre[cur], &sh);
             __syncthreads();
-            if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
+            phase_pix_test<1>(s, tid, m, tile, pre[cur], &sh, &p);  // (pixels outside the image have no candidates)
             __syncthreads();
         }
         // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
@@ -388,6 +420,21 @@ __global__ void __launch_bounds__(NT) k_shade(SceneView s, int tiles_x, TieTable
     for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
 }
 
+#ifdef DEODR_PROFILE_EDGE
+// development aid: per-phase clock stamps of k_edge_fwd summed over CTAs (thread 0 of each CTA)
+__device__ unsigned long long g_prof[16];
+#define PROF_STAMP(i)                                                                     \
+    do {                                                                                  \
+        if (threadIdx.x == 0) { long long now_ = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(now_ - prof_t)); prof_t = now_; } \
+    } while (0)
+extern "C" void deodr_b200_debug_prof(unsigned long long *out, int reset) {
+    cudaMemcpyFromSymbol(out, g_prof, sizeof(g_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
+}
+#else
+#define PROF_STAMP(i)
+#endif
+
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
 // One CTA of 64 threads per 16x4 pixel strip (4 per tile): the tiles crowded with edges set the kernel's duration, and
 // a strip has a 4x shorter critical path than a tile.
@@ -397,6 +444,9 @@ __global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma,
                                                       const int *edge_refs, const EdgeRec *edge_recs,
                                                       const double *z_buffer, float *image) {
     __shared__ TileShared sh;
+#ifdef DEODR_PROFILE_EDGE
+    long long prof_t = clock64();
+#endif
     const int tile_id = edge_tiles[blockIdx.x / (TS / EDGE_ROWS)], tid = threadIdx.x;
     const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
     const int n_edge = edge_count[tile_id];
@@ -413,17 +463,29 @@ __global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma,
         for (int k = 0; k < s.nb_colors; k++) p.col[k] = image[idx * s.nb_colors + k];
     }
     const int edge_base = edge_offset[tile_id];
+#ifdef DEODR_PROFILE_EDGE
+    if (n_edge < 0 || edge_base < 0 || p.col[0] == -12345.f || p.z == -12345.0) return;  // wait for the loads
+#endif
+    PROF_STAMP(0);
     for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
         const int m = min(EDGE_CHUNK, n_edge - base);
         phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
         __syncthreads();
+        PROF_STAMP(1);
         phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
         __syncthreads();
+        PROF_STAMP(2);
         if (inside) phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
+        PROF_STAMP(3);
         __syncthreads();
+        PROF_STAMP(4);
     }
     if (inside)
         for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
+    PROF_STAMP(5);
+#ifdef DEODR_PROFILE_EDGE
+    if (threadIdx.x == 0) atomicAdd(&g_prof[8], 1ull);
+#endif
 }
 
 template <int MAXC>
@@ -588,9 +650,23 @@ struct PhaseTimer {
 
 static inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
 
+// Fork: auxiliary stream i continues from the current point of the caller's stream; join: the caller's stream waits
+// for it.  Independent kernel chains then overlap (tails of one fill with CTAs of the other; no launch gaps).
+static inline cudaStream_t fork_stream(DeodrWorkspace *ws, int i, cudaStream_t st, bool *first) {
+    if (!ws->overlap) return st;
+    if (*first) { cudaEventRecord(ws->ev_fork, st); *first = false; }
+    cudaStreamWaitEvent(ws->aux[i], ws->ev_fork, 0);
+    return ws->aux[i];
+}
+static inline void join_stream(DeodrWorkspace *ws, int i, cudaStream_t st) {
+    if (!ws->overlap) return;
+    cudaEventRecord(ws->ev_join[i], ws->aux[i]);
+    cudaStreamWaitEvent(st, ws->ev_join[i], 0);
+}
+
 template <int MAXC>
 static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
-                       float *image, double *z, int *owner, int *face_id, cudaStream_t st) {
+                       float *image, double *z, int *owner, int *face_id, bool edge_chain, cudaStream_t st) {
     {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
         // DEODR_B200_TILEZ_CTAS_PER_SM = k > 0 runs k persistent CTAs per SM with the two-stage TMA pipeline; default 0 =
@@ -607,6 +683,7 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
         k_shade<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ties, owner, z, image);
     }
     ws->launches += 2;
+    if (edge_chain) join_stream(ws, 0, st);  // the edge lists are ready
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
         k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles_ptr, edge_count,
@@ -618,7 +695,37 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
 
 template <int MAXC>
 static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
-                       const double *z, const int *owner, const float *image_b, const DeodrGrads &g, cudaStream_t st) {
+                       const double *z, const int *owner, const float *image_b, const DeodrGrads &g, int *scal,
+                       cudaStream_t st) {
+    // Three independent chains (disjoint pixel sets, all accumulate with atomics): edge tiles (longest tail: launched
+    // first so that its CTAs are dispatched first), tiles with large triangles, small triangles.
+    bool first = true;
+    const int E = ws->num_edges, C = s.nb_colors;
+    const bool edges = edge_count && ws->num_edge_tiles > 0 && E > 0;
+    if (edges) {
+        cudaStream_t se = fork_stream(ws, 0, st, &first);
+        cudaMemsetAsync(ws->edge_acc.ptr, 0, (size_t)E * edge_acc_stride(C) * sizeof(double), se);
+        {
+            PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, se);
+            k_raster_bwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, se>>>(
+                s, sigma, ws->tiles_x, ws->edge_tiles_ptr, edge_count, ws->edge_offset.as<int>(),
+                ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), ties, z, owner, image_b, g,
+                ws->edge_acc.as<double>());
+        }
+        {
+            PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FINALIZE, se);
+            k_finalize_edges<<<grid_for(E, 128), 128, 0, se>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma,
+                                                               ws->edge_acc.as<double>(), g);
+        }
+        ws->launches += 2;
+    }
+    if (ws->num_large_tiles > 0) {  // pixels owned by large triangles, tiles without silhouette edges
+        cudaStream_t sl = fork_stream(ws, 1, st, &first);
+        PhaseTimer timer(ws, DEODR_B200_PH_INTERIOR_BWD, sl);
+        k_interior_bwd<MAXC><<<ws->num_large_tiles, NT, 0, sl>>>(s, ws->tiles_x, ws->large_tiles.as<int>(), edge_count,
+                                                                 ties, owner, image_b, g);
+        ws->launches++;
+    }
     if (ws->num_small > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_SMALL_BWD, st);
         k_small_tri_bwd<MAXC><<<grid_for(ws->num_small, 128), 128, 0, st>>>(s, ws->tiles_x, ws->small_ids.as<int>(),
@@ -626,20 +733,8 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
                                                                            image_b, g);
         ws->launches++;
     }
-    if (ws->num_large_tiles > 0) {  // pixels owned by large triangles, tiles without silhouette edges
-        PhaseTimer timer(ws, DEODR_B200_PH_INTERIOR_BWD, st);
-        k_interior_bwd<MAXC><<<ws->num_large_tiles, NT, 0, st>>>(s, ws->tiles_x, ws->large_tiles.as<int>(), edge_count,
-                                                                 ties, owner, image_b, g);
-        ws->launches++;
-    }
-    if (edge_count && ws->num_edge_tiles > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, st);
-        k_raster_bwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles_ptr, edge_count,
-                                                              ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
-                                                              ws->edge_recs.as<EdgeRec>(), ties, z,
-                                                         owner, image_b, g, ws->edge_acc.as<double>());
-        ws->launches++;
-    }
+    if (edges) join_stream(ws, 0, st);
+    if (ws->num_large_tiles > 0) join_stream(ws, 1, st);
 }
 
 static int validate_view(const DeodrSceneView *v, bool backward) {
@@ -718,6 +813,18 @@ int deodr_b200_timing_collect(DeodrWorkspace *ws, int32_t *phase, float *ms, int
         phase[i] = ws->ev_phase[i];
         ms[i] = t;
     }
+    if (getenv("DEODR_B200_TRACE_GAPS")) {  // development aid: idle time between consecutive timed phases
+        double gap[DEODR_B200_PH_COUNT] = {0};
+        int cnt[DEODR_B200_PH_COUNT] = {0};
+        for (int i = 1; i < n; i++) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, ws->ev_stop[i - 1], ws->ev_start[i]) != cudaSuccess) continue;
+            gap[ws->ev_phase[i]] += t;
+            cnt[ws->ev_phase[i]]++;
+        }
+        for (int k = 0; k < DEODR_B200_PH_COUNT; k++)
+            if (cnt[k]) fprintf(stderr, "[deodr_b200] gap before %-14s %.1f us\n", deodr_b200_phase_name(k), 1e3 * gap[k] / cnt[k]);
+    }
     ws->ev_used = 0;
     return n;
 }
@@ -735,6 +842,13 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
     if (!ws) return set_error(DEODR_B200_ENOMEM, "out of host memory");
     ws->device = device;
     CUDA_TRY(cudaMallocHost(&ws->host_totals, 16 * sizeof(int)));
+    CUDA_TRY(cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
+    ws->overlap = !(getenv("DEODR_B200_SERIAL") && atoi(getenv("DEODR_B200_SERIAL")));
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
     if (ws->scalars.ensure(8 * sizeof(int), &ws->bytes)) return DEODR_B200_ECUDA;
     if (!sm_count_cached) cudaDeviceGetAttribute(&sm_count_cached, cudaDevAttrMultiProcessorCount, device);
     *out = ws;
@@ -758,6 +872,11 @@ void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (ws->host_totals) cudaFreeHost(ws->host_totals);
     for (cudaEvent_t e : ws->ev_start) cudaEventDestroy(e);
     for (cudaEvent_t e : ws->ev_stop) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (ws->aux[i]) cudaStreamDestroy(ws->aux[i]);
+        if (ws->ev_join[i]) cudaEventDestroy(ws->ev_join[i]);
+    }
+    if (ws->ev_fork) cudaEventDestroy(ws->ev_fork);
     delete ws;
 }
 
@@ -861,7 +980,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
                     {5, 0, 2},
                     {nullptr, ws->large_tiles.as<int>(), ws->edge_tiles.as<int>()},
                     {15, 8, 9}};
-        k_scan_tiles<<<3, 1024, 0, st>>>(job, nt, scal);
+        k_scan_tiles<<<3, 1024, SCAN_SMEM, st>>>(job, nt, scal);
         ws->launches++;
     }
     CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -889,13 +1008,16 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     bins.large_refs = ws->tri_refs.as<int>();
     ws->bins = bins;
 
-    // ---- far-to-near order of the silhouette edges (DR.h:2781)
+    // ---- far-to-near order of the silhouette edges (DR.h:2781) + per-tile edge lists: a chain of its own (stream se)
+    // that overlaps the triangle fill, the z pass and the shading; joined before k_edge_fwd
+    bool first_fork = true;
+    cudaStream_t se = E > 0 ? fork_stream(ws, 0, st, &first_fork) : st;
     if (E > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, st);
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, se);
         if (E <= 65536) {
             dim3 grid(grid_for(E, 256), grid_for(E, RANK_CHUNK));
-            k_rank_edges<<<grid, 256, 0, st>>>(edges, E, ws->edge_rank.as<int>());
-            k_scatter_edges<<<grid_for(E, 128), 128, 0, st>>>(s, edges, E, sigma, ws->edge_sorted.as<int>(),
+            k_rank_edges<<<grid, 256, 0, se>>>(edges, E, ws->edge_rank.as<int>());
+            k_scatter_edges<<<grid_for(E, 128), 128, 0, se>>>(s, edges, E, sigma, ws->edge_sorted.as<int>(),
                                                                ws->edge_recs.as<EdgeRec>());
             ws->launches += 2;
         } else {
@@ -907,37 +1029,42 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
             auto *k_in = ws->edge_keys_in.as<unsigned long long>(), *k_out = ws->edge_keys_out.as<unsigned long long>();
             int *i_in = ws->edge_ids.as<int>(), *i_tmp = ws->edge_ids_tmp.as<int>();
             size_t temp1 = 0, temp2 = 0;
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, st));
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp2, k_out, k_in, i_tmp, i_in, E, 0, 64, st));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, se));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp2, k_out, k_in, i_tmp, i_in, E, 0, 64, se));
             if (ws->cub_temp.ensure(temp1 > temp2 ? temp1 : temp2, &ws->bytes)) return DEODR_B200_ECUDA;
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, st));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, se));
             CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp2, k_out, k_in, i_tmp,
-                                                     ws->edge_sorted.as<int>(), E, 0, 64, st));
-            k_edge_records<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), E, sigma,
+                                                     ws->edge_sorted.as<int>(), E, 0, 64, se));
+            k_edge_records<<<grid_for(E, 128), 128, 0, se>>>(s, ws->edge_sorted.as<int>(), E, sigma,
                                                              ws->edge_recs.as<EdgeRec>());
             ws->launches++;
         }
     }
 
-    // ---- fill pass (triangles + edges) and per-tile ordering of the edge lists
-    if (T > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_BIN_FILL, st);
-        const int small_blocks = grid_for(ws->num_small, 128), large_blocks = grid_for(ws->num_large, 128),
-                  edge_blocks = E > 0 ? grid_for(E, 128) : 0;
-        if (small_blocks + large_blocks + edge_blocks > 0) {
-            k_bin_fill<<<small_blocks + large_blocks + edge_blocks, 128, 0, st>>>(
-                s, sigma, ws->tiles_x, small_blocks, large_blocks, bins, ws->small_ids.as<int>(), ws->num_small,
-                ws->large_ids.as<int>(), ws->num_large, ws->edge_sorted.as<int>(), E, ws->edge_offset.as<int>(),
-                edge_cursor, ws->edge_refs_tmp.as<int>());
+    // ---- per-tile edge lists: fill, then order every list by far-to-near rank
+    if (E > 0) {
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, se);
+        k_bin_fill<<<grid_for(E, 128), 128, 0, se>>>(s, sigma, ws->tiles_x, 0, 0, bins, nullptr, 0, nullptr, 0,
+                                                     ws->edge_sorted.as<int>(), E, ws->edge_offset.as<int>(),
+                                                     edge_cursor, ws->edge_refs_tmp.as<int>());
+        ws->launches++;
+        if (ws->num_edge_tiles > 0) {
+            k_sort_tile_edges<<<ws->num_edge_tiles, 128, 0, se>>>(ws->edge_tiles.as<int>(), edge_count_buf,
+                                                                  ws->edge_offset.as<int>(),
+                                                                  ws->edge_refs_tmp.as<int>(), ws->edge_refs.as<int>());
             ws->launches++;
         }
     }
-    if (E > 0 && ws->num_edge_tiles > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, st);
-        k_sort_tile_edges<<<ws->num_edge_tiles, 128, 0, st>>>(ws->edge_tiles.as<int>(), edge_count_buf,
-                                                              ws->edge_offset.as<int>(), ws->edge_refs_tmp.as<int>(),
-                                                              ws->edge_refs.as<int>());
-        ws->launches++;
+    // ---- triangle fill: pre-masked records of the small triangles, index lists of the large ones
+    if (T > 0) {
+        PhaseTimer timer(ws, DEODR_B200_PH_BIN_FILL, st);
+        const int small_blocks = grid_for(ws->num_small, 128), large_blocks = grid_for(ws->num_large, 128);
+        if (small_blocks + large_blocks > 0) {
+            k_bin_fill<<<small_blocks + large_blocks, 128, 0, st>>>(
+                s, sigma, ws->tiles_x, small_blocks, large_blocks, bins, ws->small_ids.as<int>(), ws->num_small,
+                ws->large_ids.as<int>(), ws->num_large, nullptr, 0, nullptr, nullptr, nullptr);
+            ws->launches++;
+        }
     }
 
     // ---- raster
@@ -945,10 +1072,10 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     const int *edge_count = E > 0 ? edge_count_buf : nullptr;
     const int C = s.nb_colors;
     {
-    if (C == 1) launch_fwd<1>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
-    else if (C <= 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
-    else if (C <= 4) launch_fwd<4>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
-    else launch_fwd<16>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, st);
+    if (C == 1) launch_fwd<1>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
+    else if (C <= 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
+    else if (C <= 4) launch_fwd<4>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
+    else launch_fwd<16>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
     }
     CUDA_TRY(cudaGetLastError());
     ws->sigma = sigma;
@@ -984,20 +1111,10 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
     }
     TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
     const int *edge_count = E > 0 ? ws->edge_count_ptr : nullptr;
-    {
-    if (E > 0)
-        CUDA_TRY(cudaMemsetAsync(ws->edge_acc.ptr, 0, (size_t)E * edge_acc_stride(C) * sizeof(double), st));
-    if (C == 1) launch_bwd<1>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
-    else if (C <= 3) launch_bwd<3>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
-    else if (C <= 4) launch_bwd<4>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
-    else launch_bwd<16>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, st);
-    }
-    if (E > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FINALIZE, st);
-        k_finalize_edges<<<grid_for(E, 128), 128, 0, st>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma,
-                                                           ws->edge_acc.as<double>(), g);
-        ws->launches++;
-    }
+    if (C == 1) launch_bwd<1>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
+    else if (C <= 3) launch_bwd<3>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
+    else if (C <= 4) launch_bwd<4>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
+    else launch_bwd<16>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
     CUDA_TRY(cudaGetLastError());
     return DEODR_B200_OK;
 }

@@ -12,9 +12,9 @@ namespace deodr {
 
 constexpr int TS = 16;            // tile side in pixels
 constexpr int NT = TS * TS;       // threads per tile CTA, one per pixel
-constexpr int TRI_CHUNK = 256;    // triangles staged in shared memory per pass (one per thread)
 constexpr int PRE_CHUNK = 128;    // pre-masked records per TMA bulk copy (double-buffered landing zone: 2 x 8 KB)
 constexpr int LARGE_CHUNK = 64;   // large triangles staged per pass (stencil records kept in shared memory)
+constexpr int PIX_SLOTS = 8;      // candidate small triangles kept per pixel and chunk before the pixel falls back to a scan
 constexpr int EDGE_CHUNK = 64;    // edge records staged in shared memory per pass
 #ifndef DEODR_EDGE_ROWS
 #define DEODR_EDGE_ROWS 16
@@ -57,10 +57,13 @@ struct TileShared {
     union {
         struct {
             TriGeom geo[LARGE_CHUNK];  // large triangles: stencils, so that their row spans are computed by 8 threads each
-            TriRec rec[TRI_CHUNK];
+            TriRec rec[LARGE_CHUNK];
             // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
             // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time
-            alignas(16) uint32_t mask[TS / 2][TRI_CHUNK];
+            alignas(16) uint32_t mask[TS / 2][LARGE_CHUNK];
+            // small triangles: per-pixel candidate lists filled by the record threads (phase_pre_scatter)
+            int pix_cnt[NT];
+            uint8_t pix_list[PIX_SLOTS][NT];
         } tri;
         struct {
             EdgeRec rec[EDGE_CHUNK];
@@ -343,19 +346,68 @@ struct PixelState {
     float col[MAXC];
 };
 
-// Phase T1a: thread tid < n unpacks small-triangle record `pre[tid]` (pulled into shared memory by the bulk copy)
-// into the z-test layout; threads up to the next multiple of 4 write empty masks (padding).
-DEODR_HD void phase_pre_unpack(int tid, int n, const PreRec *pre, TileShared *sh) {
-    if (tid >= n) {
-        if (tid < ((n + 3) & ~3))
-            for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = 0u;
-        return;
-    }
+// Phase T1a: thread tid < n walks the set bits of small-triangle record `pre[tid]` (pulled into shared memory by the bulk
+// copy) and appends its index to the candidate list of every pixel it covers.  A record covers ~4 pixels, a pixel is
+// covered by ~1.3 records: the z test then runs over a pixel's own candidates instead of over every record of the tile.
+// pix_cnt[] must be zero on entry (phase_pix_test leaves it so).  One flat loop over the bits (SIMT: lanes with few
+// bits idle only for max-over-lanes iterations).
+template <class Env>
+DEODR_HD void phase_pre_scatter(int tid, int n, const PreRec *pre, TileShared *sh) {
+    if (tid >= n) return;
     const PreRec &r = pre[tid];
-    for (int p = 0; p < TS / 2; p++) sh->tri.mask[p][tid] = r.mask[p];
-    TriRec &rec = sh->tri.rec[tid];
-    rec.zp[0] = r.zp[0]; rec.zp[1] = r.zp[1]; rec.zp[2] = r.zp[2];
-    rec.id = r.id;
+    uint32_t words = 0u;  // bit p set <=> mask word p is not empty
+    for (int p = 0; p < TS / 2; p++) words |= (uint32_t)(r.mask[p] != 0u) << p;
+    int p = 0;
+    uint32_t w = 0u;
+    for (;;) {
+        if (w == 0u) {
+            if (words == 0u) break;
+            p = lowest_bit(words);
+            words &= words - 1;
+            w = r.mask[p];
+        }
+        const int px = p * 32 + lowest_bit(w);
+        w &= w - 1;
+        const int slot = Env::shared_inc(&sh->tri.pix_cnt[px]);
+        if (slot < PIX_SLOTS) sh->tri.pix_list[slot][px] = (uint8_t)tid;
+    }
+}
+
+// One candidate against the running state of a pixel, order-independently:
+//   own = min index among ties (what a strict '<' walk in ascending index order leaves, DR.h:961),
+//   bown = max index among ties (what the '==' walk in descending index order finds first, DR.h:1024).
+template <int MAXC>
+DEODR_HD void z_candidate(const double *zp, int id, double xd, double yd, int x, int y, bool persp, PixelState<MAXC> *p) {
+    double z = plane_z(zp, xd, yd, x, y);
+    if (persp) z = DDIV(1.0, z);
+    if (z < p->z) { p->z = z; p->own = id; p->bown = id; }
+    else if (z == p->z && p->own >= 0) {
+        if ((id & TRI_INDEX_MASK) < (p->own & TRI_INDEX_MASK)) p->own = id;
+        if ((id & TRI_INDEX_MASK) > (p->bown & TRI_INDEX_MASK)) p->bown = id;
+    }
+}
+
+// Phase T2a: each pixel z-tests its candidates of this chunk (any order: ties are resolved by index) and clears its
+// counter for the next chunk.  A pixel with more than PIX_SLOTS candidates scans the chunk's masks instead.
+template <int MAXC>
+DEODR_HD void phase_pix_test(const SceneView &s, int tid, int n, Tile tile, const PreRec *pre, TileShared *sh,
+                             PixelState<MAXC> *p) {
+    const int count = sh->tri.pix_cnt[tid];
+    sh->tri.pix_cnt[tid] = 0;
+    if (count == 0) return;
+    const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+    const double xd = (double)x, yd = (double)y;
+    const bool persp = s.perspective_correct != 0;
+    if (count <= PIX_SLOTS) {
+        for (int i = 0; i < count; i++) {
+            const PreRec &r = pre[sh->tri.pix_list[i][tid]];
+            z_candidate<MAXC>(r.zp, r.id, xd, yd, x, y, persp, p);
+        }
+    } else {
+        const int lane = tid % 32, pair = tid / 32;
+        for (int t = 0; t < n; t++)
+            if ((pre[t].mask[pair] >> lane) & 1u) z_candidate<MAXC>(pre[t].zp, pre[t].id, xd, yd, x, y, persp, p);
+    }
 }
 
 // Phase T1b: thread tid < n sets up the stencil of LARGE triangle list[tid] into shared memory (n <= LARGE_CHUNK).
@@ -410,14 +462,7 @@ DEODR_HD void phase_tri_test(const SceneView &s, int tid, int n, Tile tile, cons
         for (int j = 0; j < 4; j++) {
             if (!((m4.m[j] >> lane) & 1u)) continue;
             const TriRec &rec = sh->tri.rec[t0 + j];
-            double z = plane_z(rec.zp, xd, yd, x, y);
-            if (persp) z = DDIV(1.0, z);
-            const int id = rec.id;
-            if (z < p->z) { p->z = z; p->own = id; p->bown = id; }
-            else if (z == p->z && p->own >= 0) {
-                if ((id & TRI_INDEX_MASK) < (p->own & TRI_INDEX_MASK)) p->own = id;
-                if ((id & TRI_INDEX_MASK) > (p->bown & TRI_INDEX_MASK)) p->bown = id;
-            }
+            z_candidate<MAXC>(rec.zp, rec.id, xd, yd, x, y, persp, p);
         }
     }
 }
@@ -476,13 +521,23 @@ DEODR_HD bool edge_covers(const TileShared *sh, int e, int r, int x) {
     return x >= xb && x <= xe;
 }
 
+// Bit e set <=> edge e of the chunk (n <= EDGE_CHUNK = 64) has pixel (x, row r) inside its band.  A short uniform loop;
+// the per-edge work then runs over the set bits only, so the lanes of a warp step through DIFFERENT edges side by side
+// (a warp takes max-over-lanes hits, not the number of distinct edges that touch its 32 pixels).
+DEODR_HD unsigned long long edge_hit_mask(const TileShared *sh, int n, int r, int x) {
+    static_assert(EDGE_CHUNK <= 64, "one bit per edge of a chunk");
+    unsigned long long mask = 0ull;
+    for (int e = 0; e < n; e++)
+        if (edge_covers(sh, e, r, x)) mask |= 1ull << e;
+    return mask;
+}
+
 // Phase E3 (forward): overdraw in list order.  image = T*image + (1-T)*A where Z_edge < z_buffer (DR.h:1632-1641).
 template <int MAXC>
 DEODR_HD void phase_edge_blend(const SceneView &s, int x, int y, int r, int n, const TileShared *sh, PixelState<MAXC> *p) {
     const int C = s.nb_colors;
-    for (int e = 0; e < n; e++) {
-        if (!edge_covers(sh, e, r, x)) continue;
-        const EdgeRec &rec = sh->edge.rec[e];
+    for (unsigned long long mask = edge_hit_mask(sh, n, r, x); mask; mask &= mask - 1) {
+        const EdgeRec &rec = sh->edge.rec[lowest_bit64(mask)];
         double ze = edge_z(rec, x, y, s.perspective_correct != 0);
         if (!(ze < p->z)) continue;
         EdgeHit<MAXC> h;
@@ -508,9 +563,8 @@ template <int MAXC>
 DEODR_HD void phase_edge_replay(const SceneView &s, int x, int y, int r, int n, const TileShared *sh,
                                 const PixelState<MAXC> &p, AdjointState<MAXC> *a) {
     const int C = s.nb_colors;
-    for (int e = 0; e < n; e++) {
-        if (!edge_covers(sh, e, r, x)) continue;
-        const EdgeRec &rec = sh->edge.rec[e];
+    for (unsigned long long mask = edge_hit_mask(sh, n, r, x); mask; mask &= mask - 1) {
+        const EdgeRec &rec = sh->edge.rec[lowest_bit64(mask)];
         double ze = edge_z(rec, x, y, false);
         if (!(ze < p.z)) continue;
         if (!a->has_colour) {
@@ -532,8 +586,9 @@ DEODR_HD void phase_edge_adjoint(const SceneView &s, int x, int y, int r, int n,
                                  const PixelState<MAXC> &p, AdjointState<MAXC> *a, double *edge_acc, float *texture_b) {
     const int C = s.nb_colors;
     const int stride = edge_acc_stride(C);
-    for (int e = n - 1; e >= 0; e--) {
-        if (!edge_covers(sh, e, r, x)) continue;
+    for (unsigned long long mask = edge_hit_mask(sh, n, r, x); mask;) {  // near to far: highest bit first
+        const int e = highest_bit64(mask);
+        mask &= ~(1ull << e);
         const EdgeRec &rec = sh->edge.rec[e];
         double ze = edge_z(rec, x, y, false);
         if (!(ze < p.z)) continue;

@@ -413,6 +413,14 @@ DEODR_HD int lowest_bit64(unsigned long long m) {
 #endif
 }
 
+DEODR_HD int highest_bit64(unsigned long long m) {
+#if defined(__CUDA_ARCH__)
+    return 63 - __clzll((long long)m);
+#else
+    return 63 - __builtin_clzll(m);
+#endif
+}
+
 // sort key: radix-ascending order of this key == descending order of the depth sum (DR.h:2656-2662, 2781)
 DEODR_HD uint64_t depth_desc_key(double s) {
 #if defined(__CUDA_ARCH__)

@@ -54,6 +54,10 @@ struct DeodrWorkspace {
     int64_t bytes = 0;
     int64_t launches = 0;
     // optional per-phase event timing (bench / profiling)
+    // independent kernel chains run on two auxiliary streams forked from / joined to the caller's stream
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    bool overlap = true;  // DEODR_B200_SERIAL=1 keeps every launch on the caller's stream (profiling, A/B)
     std::vector<cudaEvent_t> ev_start, ev_stop;
     std::vector<int> ev_phase;
     int ev_used = 0;

@@ -6,6 +6,7 @@ Both list the kernel's instructions in address order, so they are joined by posi
     python scripts/ncu_lines.py <report.ncu-rep> <cubin> <kernel-regex> <mangled-kernel-name-substring>
 """
 import csv
+import os
 import collections
 import re
 import subprocess
@@ -52,4 +53,9 @@ print({k: f"{100 * v / tot:.1f}%" for k, v in by_file.most_common()})
 order = samp.most_common(40) if len(sys.argv) > 5 else agg.most_common(40)
 for (f, ln), _ in order:
     v = agg[(f, ln)]
-    print(f"{f}:{ln:<5d} inst {100 * v / tot:5.1f}%   stall-samples {100 * samp[(f, ln)] / max(tots, 1):5.1f}%")
+    text = ""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deodr_b200", "csrc", f)
+    if os.path.exists(path):
+        src_lines = open(path).read().splitlines()
+        text = src_lines[ln - 1].strip()[:100] if 0 < ln <= len(src_lines) else ""
+    print(f"{f}:{ln:<5d} inst {100 * v / tot:5.1f}%  stall {100 * samp[(f, ln)] / max(tots, 1):5.1f}%  | {text}")

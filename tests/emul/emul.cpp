@@ -20,6 +20,7 @@ struct HostEnv {
     static int atomic_add(int *p, int v) { int old = *p; *p += v; return old; }
     static void atomic_add(float *p, float v) { *p += v; }
     static void atomic_add(double *p, double v) { *p += v; }
+    static int shared_inc(int *p) { return (*p)++; }
     void emit(float *p, float v) const { *p += v; }
 };
 
@@ -52,6 +53,7 @@ template <int MAXC>
 static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *image, double *z_buffer, int *owner,
                        int *face_id) {
     TileShared *sh = new TileShared;
+    memset(sh, 0, sizeof(TileShared));
     // ---- k_tile_z
     {
         std::vector<PixelState<1>> px(NT);
@@ -65,8 +67,8 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
                 // the device pulls the chunk into shared memory with one bulk (TMA) copy; same bytes here
                 PreRec pre[PRE_CHUNK];
                 memcpy(pre, st.small_recs.data() + st.small_offset[tile_id] + base, m * sizeof(PreRec));
-                for (int tid = 0; tid < NT; tid++) phase_pre_unpack(tid, m, pre, sh);
-                for (int tid = 0; tid < NT; tid++) if (inside(tid)) phase_tri_test<1>(s, tid, m, tile, sh, &px[tid]);
+                for (int tid = 0; tid < NT; tid++) phase_pre_scatter<HostEnv>(tid, m, pre, sh);
+                for (int tid = 0; tid < NT; tid++) phase_pix_test<1>(s, tid, m, tile, pre, sh, &px[tid]);
             }
             const int n_large = st.large_count[tile_id];
             for (int base = 0; base < n_large; base += LARGE_CHUNK) {
