@@ -90,7 +90,16 @@ struct ScanJob {
     int total_slot[3];
     int *nonempty[3];        // optional: compact list of the tiles with count > 0 (nullptr to skip)
     int nonempty_slot[3];    // totals[] slot receiving the length of that list
+    // two-ended list (threshold > 0): tiles with count > threshold fill the list from the front, the other non-empty
+    // tiles from the back (position n-1 downwards), so that the kernels that walk it start the crowded tiles first
+    int heavy_threshold[3];
+    int heavy_slot[3];       // totals[] slot receiving the number of crowded tiles
 };
+
+// Block b of a kernel that walks a two-ended tile list of capacity n with `heavy` crowded tiles at its front.
+static __device__ __forceinline__ int two_ended_at(const int *list, int n, int heavy, int b) {
+    return b < heavy ? list[b] : list[n - 1 - (b - heavy)];
+}
 
 // One 64-bit scan carries both the running sum of the counts (low word) and the number of non-empty tiles (high word).
 // Each thread owns SCAN_IPT consecutive tiles, so 16384 tiles take ONE block scan instead of sixteen; counts and
@@ -103,6 +112,9 @@ static __device__ __forceinline__ int scan_slot(int i) { return i + (i >> 5); } 
 __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *totals) {
     extern __shared__ int stage[];
     __shared__ unsigned long long warp_sums[32];
+    __shared__ int heavy_sums[32];
+    const int threshold = job.heavy_threshold[blockIdx.x];
+    int heavy_carry = 0;
     const int *count = job.count[blockIdx.x];
     int *offset = job.offset[blockIdx.x];
     int *nonempty = job.nonempty[blockIdx.x];
@@ -122,30 +134,47 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
         unsigned long long v = 0;
 #pragma unroll
         for (int k = 0; k < SCAN_IPT; k++) v += (unsigned long long)(unsigned)c[k] | ((unsigned long long)(c[k] > 0) << 32);
+        int hv = 0;
+        if (threshold > 0) {
+#pragma unroll
+            for (int k = 0; k < SCAN_IPT; k++) hv += (int)(c[k] > threshold);
+        }
         unsigned long long incl = v;
+        int hincl = hv;
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            int ht = __shfl_up_sync(0xffffffffu, hincl, o);
+            if (lane >= o) { incl += t; hincl += ht; }
         }
-        if (lane == 31) warp_sums[warp] = incl;
+        if (lane == 31) { warp_sums[warp] = incl; heavy_sums[warp] = hincl; }
         __syncthreads();
         if (warp == 0) {
             unsigned long long w = warp_sums[lane];
+            int hw = heavy_sums[lane];
             for (int o = 1; o < 32; o <<= 1) {
                 unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
+                int ht = __shfl_up_sync(0xffffffffu, hw, o);
+                if (lane >= o) { w += t; hw += ht; }
             }
             warp_sums[lane] = w;
+            heavy_sums[lane] = hw;
         }
         __syncthreads();
+        int hrun = heavy_carry + (warp ? heavy_sums[warp - 1] : 0) + hincl - hv;
         unsigned long long run = carry + (warp ? warp_sums[warp - 1] : 0ull) + incl - v;
 #pragma unroll
         for (int k = 0; k < SCAN_IPT; k++) {
             stage[scan_slot(first + k)] = (int)(unsigned)run;
-            if (nonempty && c[k] > 0) nonempty[(int)(run >> 32)] = base + first + k;
+            if (nonempty && c[k] > 0) {
+                const int rank = (int)(run >> 32);  // non-empty tiles before this one
+                if (threshold <= 0) nonempty[rank] = base + first + k;
+                else if (c[k] > threshold) nonempty[hrun++] = base + first + k;
+                else nonempty[n - 1 - (rank - hrun)] = base + first + k;
+            }
             run += (unsigned long long)(unsigned)c[k] | ((unsigned long long)(c[k] > 0) << 32);
         }
         carry += warp_sums[31];
+        heavy_carry += heavy_sums[31];
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < SCAN_IPT; k++) {
@@ -158,6 +187,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
         offset[n] = (int)(unsigned)carry;
         totals[job.total_slot[blockIdx.x]] = (int)(unsigned)carry;
         if (nonempty) totals[job.nonempty_slot[blockIdx.x]] = (int)(carry >> 32);
+        if (threshold > 0) totals[job.heavy_slot[blockIdx.x]] = heavy_carry;
     }
 }
 
@@ -272,9 +302,9 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // Orders every tile's edge list by far-to-near rank (ranks are unique): rank-counting sort, one CTA per tile.
-__global__ void k_sort_tile_edges(const int *edge_tiles, const int *count, const int *offset, const int *refs_in,
-                                  int *refs_out) {
-    const int tile = edge_tiles[blockIdx.x];
+__global__ void k_sort_tile_edges(const int *edge_tiles, int num_tiles, int heavy, const int *count, const int *offset,
+                                  const int *refs_in, int *refs_out) {
+    const int tile = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x);
     const int n = count[tile], base = offset[tile];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int mine = refs_in[base + i], pos = 0;
@@ -435,19 +465,21 @@ extern "C" void deodr_b200_debug_prof(unsigned long long *out, int reset) {
 #define PROF_STAMP(i)
 #endif
 
+static_assert(EDGE_ROWS == TS, "the span cache shared by k_edge_fwd and k_raster_bwd holds whole tiles");
+
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
 // One CTA of 64 threads per 16x4 pixel strip (4 per tile): the tiles crowded with edges set the kernel's duration, and
 // a strip has a 4x shorter critical path than a tile.
 template <int MAXC>
-__global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles,
+__global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                       const int *edge_count, const int *edge_offset,
                                                       const int *edge_refs, const EdgeRec *edge_recs,
-                                                      const double *z_buffer, float *image) {
+                                                      uint32_t *span_cache, const double *z_buffer, float *image) {
     __shared__ TileShared sh;
 #ifdef DEODR_PROFILE_EDGE
     long long prof_t = clock64();
 #endif
-    const int tile_id = edge_tiles[blockIdx.x / (TS / EDGE_ROWS)], tid = threadIdx.x;
+    const int tile_id = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x / (TS / EDGE_ROWS)), tid = threadIdx.x;
     const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
     const int n_edge = edge_count[tile_id];
     const Tile tile = tile_of(tile_id, tiles_x);
@@ -475,6 +507,9 @@ __global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma,
         phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
         __syncthreads();
         PROF_STAMP(2);
+        // the backward pass reuses the spans (same scene, same sigma): 64 bytes per (tile, edge), coalesced
+        for (int item = tid; item < m * TS; item += EDGE_NT)
+            span_cache[(size_t)(edge_base + base) * TS + item] = sh.edge.span[item / TS][item % TS];
         if (inside) phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
         PROF_STAMP(3);
         __syncthreads();
@@ -489,14 +524,15 @@ __global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma,
 }
 
 template <int MAXC>
-__global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles,
+__global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                    const int *edge_count, const int *edge_offset, const int *edge_refs,
-                                                   const EdgeRec *edge_recs, TieTable ties, const double *z_buffer,
+                                                   const EdgeRec *edge_recs, const uint32_t *span_cache, TieTable ties,
+                                                   const double *z_buffer,
                                                    const int *owner, const float *image_b, DeodrGrads grads,
                                                    double *edge_acc) {
     __shared__ TileShared sh;
     // one CTA of 64 threads per 16x4 strip of a tile that HAS edges (see k_edge_fwd)
-    const int tile_id = edge_tiles[blockIdx.x / (TS / EDGE_ROWS)], tid = threadIdx.x;
+    const int tile_id = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x / (TS / EDGE_ROWS)), tid = threadIdx.x;
     const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
     const Tile tile = tile_of(tile_id, tiles_x);
     const int c = tid % TS, r = row0 + tid / TS;
@@ -525,12 +561,15 @@ __global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigm
     {
         const int edge_base = edge_offset[tile_id];
         const bool single = n_edge <= EDGE_CHUNK;
+        auto load_spans = [&](int base, int m) {
+            for (int item = tid; item < m * TS; item += EDGE_NT)
+                sh.edge.span[item / TS][item % TS] = span_cache[(size_t)(edge_base + base) * TS + item];
+        };
         // pass A: forward replay (far to near) to obtain the final colour in fp64
         for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
             const int m = min(EDGE_CHUNK, n_edge - base);
             phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
-            __syncthreads();
-            phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
+            load_spans(base, m);  // computed by the forward pass (k_edge_fwd)
             __syncthreads();
             if (inside) phase_edge_replay<MAXC>(s, x, y, r, m, &sh, p, &a);
             if (single) {
@@ -545,8 +584,7 @@ __global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigm
             for (int base = last; base >= 0; base -= EDGE_CHUNK) {
                 const int m = min(EDGE_CHUNK, n_edge - base);
                 phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
-                __syncthreads();
-                phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
+                load_spans(base, m);
                 __syncthreads();
                 if (inside && a.has_colour)
                     phase_edge_adjoint<MAXC, DevEnv>(s, x, y, r, m, &sh, p, &a, edge_acc, grads.texture_b);
@@ -686,9 +724,9 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     if (edge_chain) join_stream(ws, 0, st);  // the edge lists are ready
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
-        k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles_ptr, edge_count,
+        k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
                                                             ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
-                                                            ws->edge_recs.as<EdgeRec>(), z, image);
+                                                            ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), z, image);
         ws->launches++;
     }
 }
@@ -708,8 +746,10 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, se);
             k_raster_bwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, se>>>(
-                s, sigma, ws->tiles_x, ws->edge_tiles_ptr, edge_count, ws->edge_offset.as<int>(),
-                ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), ties, z, owner, image_b, g,
+                s, sigma, ws->tiles_x, ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
+                ws->edge_offset.as<int>(),
+                ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), ties, z, owner,
+                image_b, g,
                 ws->edge_acc.as<double>());
         }
         {
@@ -861,7 +901,7 @@ void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     DevBuf *bufs[] = {&ws->zeroed, &ws->large_tiles, &ws->edge_tiles, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
                       &ws->edge_ids_tmp, &ws->edge_rank, &ws->edge_recs,
                       &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
-                      &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->scalars,
+                      &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->edge_spans, &ws->scalars,
                       &ws->tie_pairs, &ws->edge_acc, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
                       &ws->h_colors, &ws->h_shade, &ws->h_edgeflags, &ws->h_textured, &ws->h_shaded, &ws->h_texture,
                       &ws->h_background, &ws->h_image, &ws->h_z, &ws->h_owner, &ws->h_image_b,
@@ -979,7 +1019,9 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
                     {ws->small_offset.as<int>(), ws->tri_offset.as<int>(), ws->edge_offset.as<int>()},
                     {5, 0, 2},
                     {nullptr, ws->large_tiles.as<int>(), ws->edge_tiles.as<int>()},
-                    {15, 8, 9}};
+                    {15, 8, 9},
+                    {0, 0, EDGE_CHUNK},
+                    {15, 15, 10}};
         k_scan_tiles<<<3, 1024, SCAN_SMEM, st>>>(job, nt, scal);
         ws->launches++;
     }
@@ -996,6 +1038,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     ws->num_large = ws->host_totals[7];
     ws->num_large_tiles = ws->host_totals[8];
     ws->num_edge_tiles = E > 0 ? ws->host_totals[9] : 0;
+    ws->num_heavy_edge_tiles = E > 0 ? ws->host_totals[10] : 0;
     rc = 0;
     rc |= ws->small_recs.ensure(((size_t)small_total + 1) * sizeof(PreRec), &ws->bytes);
     rc |= ws->tri_refs.ensure(((size_t)large_total + 4) * sizeof(int), &ws->bytes);
@@ -1003,6 +1046,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     rc |= ws->edge_recs.ensure(((size_t)E + 1) * sizeof(EdgeRec), &ws->bytes);
     rc |= ws->edge_refs_tmp.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
     rc |= ws->edge_refs.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
+    rc |= ws->edge_spans.ensure(((size_t)edge_total + 4) * TS * sizeof(uint32_t), &ws->bytes);
     if (rc) return DEODR_B200_ECUDA;
     bins.small_recs = ws->small_recs.as<PreRec>();
     bins.large_refs = ws->tri_refs.as<int>();
@@ -1049,7 +1093,8 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
                                                      edge_cursor, ws->edge_refs_tmp.as<int>());
         ws->launches++;
         if (ws->num_edge_tiles > 0) {
-            k_sort_tile_edges<<<ws->num_edge_tiles, 128, 0, se>>>(ws->edge_tiles.as<int>(), edge_count_buf,
+            k_sort_tile_edges<<<ws->num_edge_tiles, 128, 0, se>>>(ws->edge_tiles.as<int>(), nt, ws->num_heavy_edge_tiles,
+                                                                  edge_count_buf,
                                                                   ws->edge_offset.as<int>(),
                                                                   ws->edge_refs_tmp.as<int>(), ws->edge_refs.as<int>());
             ws->launches++;

@@ -123,6 +123,26 @@ DEODR_HD int floor_quotient(double a, double b) {
     return to_short((double)(at ? c : c - 1));
 }
 
+// (short)(double)i for an int i: the reference's pass through `short` without the two conversions
+DEODR_HD int wrap16(int i) { return (int)(int16_t)(i & 0xffff); }
+
+// floor_quotient as straight-line code (no branches: several independent quotients interleave in the pipeline).
+// Returns true when the result is not settled and floor_quotient_exact must be used instead; same decisions as
+// floor_quotient.
+DEODR_HD bool floor_quotient_try(double a, double b, int *out) {
+    const float af = (float)a, bf = (float)b;
+    const float qf = af / bf;
+    const bool ok = (fabsf(qf) < 33000.0f) && (fabsf(bf) > 1e-30f) && (fabsf(af) > 1e-30f || a == 0.0) &&
+                    (fabsf(af) < 1e30f) && (fabsf(bf) < 1e30f);
+    const int c = ok ? (int)floorf(qf) : 0;
+    const double c1 = (double)(c + 1), c0 = (double)c;
+    const double g1 = DEODR_FMA(-c1, b, a), g0 = DEODR_FMA(-c0, b, a);
+    const bool up_ge = b > 0 ? (g1 >= 0) : (g1 <= 0), at_ge = b > 0 ? (g0 >= 0) : (g0 <= 0);
+    const bool up_far = fabs(g1) > 4.5e-16 * fabs(c1 * b), at_far = fabs(g0) > 4.5e-16 * fabs(c0 * b);
+    *out = wrap16(up_ge ? c + 1 : (at_ge ? c : c - 1));
+    return !ok || (!up_ge && (!up_far || (!at_ge && !at_far)));
+}
+
 // DR.h:440-479: min(x_max, max(x_min, floor(a/b))) with the robust fall-back.  Result passes through `short`.
 DEODR_HD int floor_div_clamped(double a, double b, int x_min, int x_max) {
     if (DMUL(fabs(b), 32767.0) > DADD(fabs(a), fabs(b))) {
@@ -380,7 +400,8 @@ DEODR_HD void edge_geom(const double V[2][2], const double Zv[2], int height, do
 }
 
 // DR.h:2620-2648: the four half-planes are applied in sequence, each clamped against the running bounds.
-DEODR_HD void edge_row_span(const EdgeGeom &g, int width, int y, int *x_begin, int *x_end) {
+// (formulation that follows the reference line by line; kept for the equivalence test)
+DEODR_HD void edge_row_span_reference(const EdgeGeom &g, int width, int y, int *x_begin, int *x_end) {
     int xb = 0, xe = width - 1;
     for (int k = 0; k < 4; k++) {
         const double *q = g.ineq + 3 * k;
@@ -390,6 +411,53 @@ DEODR_HD void edge_row_span(const EdgeGeom &g, int width, int y, int *x_begin, i
             if (t < xe) xe = t;
         } else {
             int t = to_short((double)(1 + floor_div_clamped(num, q[0], xb - 1, xe + 1)));
+            if (t > xb) xb = t;
+        }
+    }
+    *x_begin = xb;
+    *x_end = xe;
+}
+
+// Same result with the four quotients computed side by side first (they do not depend on the running bounds; only
+// the clamps and the rare incremental fall-back do), which shortens the dependent chain ~4x.
+DEODR_HD void edge_row_span(const EdgeGeom &g, int width, int y, int *x_begin, int *x_end) {
+    const double yd = (double)y;
+    double num[4];
+    int fq[4];
+    bool normal[4], unsettled[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) {
+        const double *q = g.ineq + 3 * k;
+        num[k] = -DADD(DMUL(q[1], yd), q[2]);
+        normal[k] = DMUL(fabs(q[0]), 32767.0) > DADD(fabs(num[k]), fabs(q[0]));
+        unsettled[k] = floor_quotient_try(num[k], q[0], &fq[k]);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++)
+        if (normal[k] && unsettled[k]) fq[k] = floor_quotient_exact(num[k], g.ineq[3 * k]);
+    int xb = 0, xe = width - 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) {
+        const double q0 = g.ineq[3 * k];
+        const int lo = xb - 1, hi = xe + 1;
+        int x;
+        if (normal[k]) {
+            x = fq[k];
+            if (x < lo) x = wrap16(lo);
+            if (x > hi) x = wrap16(hi);
+        } else {
+            x = monotone_search(num[k], q0, lo, hi, q0 > 0 ? 0 : 1);
+        }
+        if (q0 < 0) {
+            if (x < xe) xe = x;
+        } else {
+            const int t = wrap16(1 + x);
             if (t > xb) xb = t;
         }
     }

@@ -75,11 +75,13 @@ struct DeodrWorkspace {
     DevBuf small_ids, large_ids;  // compacted lists of the drawn triangles (count pass), reused by the adjoint
     int num_small = 0, num_large = 0;
     DevBuf large_tiles, edge_tiles;
-    int *edge_tiles_ptr = nullptr;  // the list the edge kernels walk (LPT order when built)  // compact lists of the tiles with large triangles / silhouette edges
+    int *edge_tiles_ptr = nullptr;  // the two-ended list the edge kernels walk (crowded tiles first)  // compact lists of the tiles with large triangles / silhouette edges
     int num_large_tiles = 0, num_edge_tiles = 0;
+    int num_heavy_edge_tiles = 0;  // crowded tiles (more than one chunk of edges) at the front of the two-ended edge_tiles list
     DevBuf edge_recs;            // per-edge band stencils in far-to-near order (k_edge_records)
     DevBuf edge_rank, edge_ids, edge_ids_tmp, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
     DevBuf edge_offset, edge_refs_tmp, edge_refs;
+    DevBuf edge_spans;  // x spans of every (tile, edge, row), written by k_edge_fwd and reused by k_raster_bwd
     DevBuf scalars;              // device ints: [0] tri total, [1] num selected, [2] edge total, [3] tie counter, [4] flags
     DevBuf tie_pairs;
     int tie_capacity = 0;

@@ -317,6 +317,23 @@ long emul_div_mismatches(const double *a, const double *b, long n, int lo, int h
     for (long i = 0; i < n; i++) {
         bad += floor_div_clamped(a[i], b[i], lo, hi) != floor_div_clamped_reference(a[i], b[i], lo, hi);
         bad += ceil_div_clamped(a[i], b[i], lo, hi) != ceil_div_clamped_reference(a[i], b[i], lo, hi);
+        int x;  // the branch-free variant used by edge_row_span makes the same decisions
+        if (floor_quotient_try(a[i], b[i], &x)) x = floor_quotient_exact(a[i], b[i]);
+        bad += x != floor_quotient(a[i], b[i]);
+    }
+    return bad;
+}
+
+// edge_row_span (four quotients side by side) against the line-by-line formulation; ineq = n x 12 doubles
+long emul_span_mismatches(const double *ineq, const int *y, long n, int width) {
+    long bad = 0;
+    for (long i = 0; i < n; i++) {
+        EdgeGeom g;
+        memcpy(g.ineq, ineq + 12 * i, sizeof(g.ineq));
+        int b0, e0, b1, e1;
+        edge_row_span(g, width, y[i], &b0, &e0);
+        edge_row_span_reference(g, width, y[i], &b1, &e1);
+        bad += (b0 != b1) || (e0 != e1);
     }
     return bad;
 }

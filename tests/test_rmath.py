@@ -13,6 +13,8 @@ def lib():
     e = Emulator().lib
     e.emul_div_mismatches.restype = C.c_long
     e.emul_div_mismatches.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int]
+    e.emul_span_mismatches.restype = C.c_long
+    e.emul_span_mismatches.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int]
     return e
 
 
@@ -53,3 +55,24 @@ def test_special_operands(lib):
     a, b = np.meshgrid(sp, sp)
     assert mismatches(lib, a.ravel(), b.ravel()) == 0
     assert mismatches(lib, a.ravel(), b.ravel(), lo=5, hi=9) == 0
+
+
+def test_edge_row_span_matches_line_by_line_formulation(lib):
+    """edge_row_span computes the four half-plane quotients side by side before the sequential clamps; it must give
+    the spans of the formulation that follows DifferentiableRenderer.h:2620-2648 line by line, including the
+    degenerate half-planes (zero / tiny / huge coefficients) that take the incremental fall-back."""
+    rng = np.random.default_rng(7)
+    n = 400_000
+    ineq = rng.normal(size=(n, 12)) * rng.choice([1e-6, 1e-2, 1.0, 50.0], size=(n, 1))
+    # constant terms of the size of pixel coordinates; some exactly-integer crossings; some degenerate rows
+    ineq[:, 2::3] *= rng.choice([1.0, 100.0, 2000.0], size=(n, 4))
+    k = rng.integers(0, n, size=n // 10)
+    ineq[k, 0] = rng.choice([0.0, 1e-300, -1e-300, 1e-20, 1.0, -1.0], size=k.size)
+    k = rng.integers(0, n, size=n // 10)
+    ineq[k, 3] = np.round(ineq[k, 3])
+    ineq[k, 4] = np.round(ineq[k, 4])
+    ineq[k, 5] = np.round(ineq[k, 5])
+    y = rng.integers(0, 2048, size=n).astype(np.int32)
+    ineq = np.ascontiguousarray(ineq)
+    assert lib.emul_span_mismatches(ineq.ctypes.data, y.ctypes.data, n, 2048) == 0
+    assert lib.emul_span_mismatches(ineq.ctypes.data, y.ctypes.data, n, 37) == 0
