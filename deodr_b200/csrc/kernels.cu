@@ -35,38 +35,72 @@ using namespace deodr;
 
 struct DevEnv {
     static __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
+#ifdef DEODR_EXPERIMENT_NO_ATOMICS  // development aid: how much of the backward pass is float-atomic throughput?
+    static __device__ __forceinline__ void atomic_add(float *p, float v) { if (v == 1.2345e-38f) atomicAdd(p, v); }
+#else
     static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
+#endif
     static __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
     static __device__ __forceinline__ int shared_inc(int *p) { return atomicAdd(p, 1); }  // p in shared memory
 };
 
-// Vertex-gradient scatter of the interior adjoint.  When every participating lane of the warp has the same owner
-// triangle (`uniform`), all lanes target the same addresses: sum over the warp with shuffles and let one lane issue a
-// single atomic (32x fewer same-address atomics for large triangles).  Otherwise one atomic per lane.
-struct WarpEmit {
-    unsigned mask;   // lanes taking part in the interior adjoint (they all execute every emit together)
-    bool uniform;    // all 32 lanes take part and share the owner triangle
-    int leader;
-    static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }  // texel adjoints
-    __device__ __forceinline__ void emit(float *p, float v) const {
-        if (uniform) {  // full warp, one owner: butterfly sum, one atomic
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if ((int)(threadIdx.x & 31) == leader) atomicAdd(p, v);
-        } else {
-            atomicAdd(p, v);
-        }
+// Interior adjoint of one pixel per lane with a warp-level reduce-by-owner before the scatter: the lanes of a warp that
+// share the adjoint owner (neighbouring pixels of a large triangle) first sum their vertex gradients with a tree of
+// shuffles over the group (__match_any_sync gives the groups), then ONE lane per group issues the atomics.  Measured on
+// the 1M-triangle scene: float-atomic throughput was 38 of k_interior_bwd's 67 us.  Must be called by all 32 lanes.
+template <int MAXC>
+static __device__ __forceinline__ void interior_adjoint_warp(const SceneView &s, int x, int y, bool has,
+                                                             const PixelState<MAXC> &p, const float *g,
+                                                             const DeodrGrads &grads) {
+    const int lane = (int)(threadIdx.x & 31), C = s.nb_colors;
+    TriAttr t;
+    VertexGrads<MAXC> acc;
+    zero_vertex_grads<MAXC>(s, &acc);
+    t.textured = false;
+    if (has) {
+        tri_attr(s, p.bown & TRI_INDEX_MASK, &t);
+        pixel_adjoint<MAXC, DevEnv>(s, t, x, y, g, &acc, grads.texture_b);
     }
-};
-
-// builds the WarpEmit of the calling warp; must be called by all 32 lanes
-static __device__ __forceinline__ WarpEmit make_warp_emit(bool has, int owner) {
-    WarpEmit e;
-    e.mask = __ballot_sync(0xffffffffu, has);
-    e.leader = e.mask ? __ffs(e.mask) - 1 : 0;
-    const int k0 = __shfl_sync(0xffffffffu, owner, e.leader);
-    // a butterfly needs every lane: only full warps inside one triangle take the aggregated path
-    e.uniform = e.mask == 0xffffffffu && __all_sync(0xffffffffu, owner == k0);
-    return e;
+    const int key = has ? (p.bown & TRI_INDEX_MASK) : -1 - lane;  // idle lanes: groups of one
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int rank = __popc(peers & ((1u << lane) - 1u)), size = __popc(peers);
+    const int max_size = __reduce_max_sync(0xffffffffu, size);
+    const bool any_textured = __any_sync(0xffffffffu, has && t.textured);
+    const bool any_plain = __any_sync(0xffffffffu, has && !t.textured);
+    for (int stride = 1; stride < max_size; stride <<= 1) {
+        // tree over the members of a group: member `rank` (a multiple of 2*stride) takes member rank + stride
+        const bool take = (rank & (2 * stride - 1)) == 0 && rank + stride < size;
+        const int src = take ? (int)__fns(peers, 0, rank + stride + 1) : lane;
+#define DEODR_TAKE(field)                                                  \
+        {                                                                      \
+            const float other = __shfl_sync(0xffffffffu, (field), src);        \
+            if (take) (field) += other;                                        \
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            DEODR_TAKE(acc.ij[i][0]);
+            DEODR_TAKE(acc.ij[i][1]);
+        }
+        if (any_textured) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                DEODR_TAKE(acc.uv[i][0]);
+                DEODR_TAKE(acc.uv[i][1]);
+                DEODR_TAKE(acc.shade[i]);
+            }
+        }
+        if (any_plain) {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int c = 0; c < MAXC; c++)
+                    if (c < C) DEODR_TAKE(acc.attr[i][c]);
+        }
+#undef DEODR_TAKE
+    }
+    if (has && rank == 0)
+        flush_vertex_grads<MAXC, AtomicEmit<DevEnv>>(s, t, acc, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
+                                                     AtomicEmit<DevEnv>());
 }
 
 static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirror DeodrSceneView");
@@ -592,15 +626,11 @@ __global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigm
             }
         }
     }
-    const bool has = inside && p.bown >= 0;
-    const WarpEmit env = make_warp_emit(has, p.bown);
-    if (has)
-        phase_interior_adjoint<MAXC, WarpEmit>(s, x, y, p, a.g, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
-                                               grads.texture_b, env);
+    interior_adjoint_warp<MAXC>(s, x, y, inside && p.bown >= 0, p, a.g, grads);
 }
 
-// Interior adjoint of the tiles WITHOUT silhouette edges (the vast majority): no shared memory, no z-buffer read,
-// few registers -> high occupancy to hide the dependent gathers owner -> faces -> vertices.
+// Interior adjoint of the pixels owned by LARGE triangles in the tiles without silhouette edges: no shared memory, no
+// z-buffer read; the gradients are summed per owner inside each warp before the scatter (interior_adjoint_warp).
 template <int MAXC>
 __global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, const int *large_tiles,
                                                      const int *edge_count, TieTable ties, const int *owner,
@@ -627,11 +657,7 @@ __global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, c
         if (p.bown >= 0)
             for (int k = 0; k < s.nb_colors; k++) g[k] = image_b[idx * s.nb_colors + k];
     }
-    const bool has = inside && p.bown >= 0;
-    const WarpEmit env = make_warp_emit(has, p.bown);
-    if (has)
-        phase_interior_adjoint<MAXC, WarpEmit>(s, x, y, p, g, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
-                                               grads.texture_b, env);
+    interior_adjoint_warp<MAXC>(s, x, y, inside && p.bown >= 0, p, g, grads);
 }
 
 // Triangle-parallel interior adjoint of the small triangles (one thread per entry of the compacted small list).

@@ -642,7 +642,8 @@ DEODR_HD void phase_edge_adjoint(const SceneView &s, int x, int y, int r, int n,
 
 // Interior adjoint of one pixel (pixel-parallel kernels): the residual colour adjoint g goes to the vertices of the
 // adjoint owner.  `env.emit(ptr, v)` adds v to a vertex-gradient slot; the device version sums over the warp first when
-// the whole warp shares the owner triangle (WarpEmit in kernels.cu).
+// the whole warp shares the owner triangle.  (The device kernels use interior_adjoint_warp of kernels.cu, which sums
+// per owner inside the warp first; this per-pixel form is what the CPU emulation runs.)
 template <int MAXC, class Env>
 DEODR_HD void phase_interior_adjoint(const SceneView &s, int x, int y, const PixelState<MAXC> &p, const float *g,
                                      float *ij_b, float *colors_b, float *uv_b, float *shade_b, float *texture_b,

@@ -269,7 +269,8 @@ DEODR_HD void tri_geom(const double V[3][2], const double Zv[3], bool strict, bo
 }
 
 // DR.h:864-906 for one half.  Returns an empty span as x_begin > x_end.
-DEODR_HD void tri_half_span(const TriGeom &g, int half, int y, int width, bool strict, int *x_begin, int *x_end) {
+// (formulation that follows the reference line by line; kept for the equivalence test)
+DEODR_HD void tri_half_span_reference(const TriGeom &g, int half, int y, int width, bool strict, int *x_begin, int *x_end) {
     const double *l = g.eq[g.left[half]], *r = g.eq[g.right[half]];
     int x_min = g.x_min, x_max = g.x_max;
     if (x_min < 0) x_min = 0;
@@ -284,6 +285,43 @@ DEODR_HD void tri_half_span(const TriGeom &g, int half, int y, int width, bool s
     if (tmp < xe) xe = tmp;
     *x_begin = xb;
     *x_end = xe;
+}
+
+// Same result; the left and right bounds are clamped against the same [x_min - 1, x_max], so their two quotients are
+// computed side by side (branch-free candidates, rare exact fall-back afterwards): half the dependent chain.
+DEODR_HD void tri_half_span(const TriGeom &g, int half, int y, int width, bool strict, int *x_begin, int *x_end) {
+    const double *l = g.eq[g.left[half]], *r = g.eq[g.right[half]];
+    int x_min = g.x_min, x_max = g.x_max;
+    if (x_min < 0) x_min = 0;
+    if (x_max > width - 1) x_max = width - 1;
+    const int lo = x_min - 1, hi = x_max;
+    const double yd = (double)y;
+    const double nl = -DADD(DMUL(l[1], yd), l[2]), nr = -DADD(DMUL(r[1], yd), r[2]);
+    const bool normal_l = DMUL(fabs(l[0]), 32767.0) > DADD(fabs(nl), fabs(l[0]));
+    const bool normal_r = DMUL(fabs(r[0]), 32767.0) > DADD(fabs(nr), fabs(r[0]));
+    const double al = strict ? nl : -nl;  // ceil(RN(q)) = -floor(RN(-q))
+    int ql, qr;
+    const bool unsettled_l = floor_quotient_try(al, l[0], &ql), unsettled_r = floor_quotient_try(nr, r[0], &qr);
+    if (normal_l && unsettled_l) ql = floor_quotient_exact(al, l[0]);
+    if (normal_r && unsettled_r) qr = floor_quotient_exact(nr, r[0]);
+    int xl, xr;
+    if (normal_l) {
+        xl = strict ? ql : wrap16(-ql);
+        if (xl < lo) xl = wrap16(lo);
+        if (xl > hi) xl = wrap16(hi);
+    } else {
+        xl = monotone_search(nl, l[0], lo, hi, strict ? (l[0] > 0 ? 0 : 1) : (l[0] > 0 ? 2 : 3));
+    }
+    if (normal_r) {
+        xr = qr;
+        if (xr < lo) xr = wrap16(lo);
+        if (xr > hi) xr = wrap16(hi);
+    } else {
+        xr = monotone_search(nr, r[0], lo, hi, r[0] > 0 ? 0 : 1);
+    }
+    const int tmp = strict ? wrap16(1 + xl) : xl;
+    *x_begin = tmp > x_min ? tmp : x_min;
+    *x_end = xr < x_max ? xr : x_max;
 }
 
 // Coverage of row y = union of the (at most two) halves containing the row.  In non-strict mode the row of the

@@ -338,6 +338,28 @@ long emul_span_mismatches(const double *ineq, const int *y, long n, int width) {
     return bad;
 }
 
+// tri_half_span (two quotients side by side) against the line-by-line formulation, every row of both halves;
+// V = n x 6 doubles (x0 y0 x1 y1 x2 y2)
+long emul_tri_span_mismatches(const double *V, long n, int width, int height, int strict) {
+    long bad = 0;
+    for (long i = 0; i < n; i++) {
+        double P[3][2] = {{V[6 * i], V[6 * i + 1]}, {V[6 * i + 2], V[6 * i + 3]}, {V[6 * i + 4], V[6 * i + 5]}};
+        double Z[3] = {1.0, 2.0, 3.0};
+        TriGeom g;
+        tri_geom(P, Z, strict != 0, false, &g, nullptr);
+        for (int half = 0; half < 2; half++) {
+            int y0 = g.y_begin[half] < 0 ? 0 : g.y_begin[half], y1 = g.y_end[half] > height - 1 ? height - 1 : g.y_end[half];
+            for (int y = y0; y <= y1; y++) {
+                int b0, e0, b1, e1;
+                tri_half_span(g, half, y, width, strict != 0, &b0, &e0);
+                tri_half_span_reference(g, half, y, width, strict != 0, &b1, &e1);
+                bad += (b0 != b1) || (e0 != e1);
+            }
+        }
+    }
+    return bad;
+}
+
 int emul_num_ties(void) { return (int)g_state.tie_pairs.size() / 2; }
 int emul_num_edges(void) { return g_state.E; }
 int emul_tri_refs(void) {

@@ -13,6 +13,8 @@ def lib():
     e = Emulator().lib
     e.emul_div_mismatches.restype = C.c_long
     e.emul_div_mismatches.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int]
+    e.emul_tri_span_mismatches.restype = C.c_long
+    e.emul_tri_span_mismatches.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int]
     e.emul_span_mismatches.restype = C.c_long
     e.emul_span_mismatches.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int]
     return e
@@ -76,3 +78,23 @@ def test_edge_row_span_matches_line_by_line_formulation(lib):
     ineq = np.ascontiguousarray(ineq)
     assert lib.emul_span_mismatches(ineq.ctypes.data, y.ctypes.data, n, 2048) == 0
     assert lib.emul_span_mismatches(ineq.ctypes.data, y.ctypes.data, n, 37) == 0
+
+
+@pytest.mark.parametrize("strict", [1, 0])
+def test_triangle_row_spans_match_line_by_line_formulation(lib, strict):
+    """tri_half_span computes the left and right bounds side by side; same spans as the line-by-line formulation of
+    DifferentiableRenderer.h:864-906 on random, sliver, axis-aligned and integer-vertex triangles."""
+    rng = np.random.default_rng(11 + strict)
+    n = 60_000
+    c = rng.uniform(-20, 276, size=(n, 1, 2))
+    V = c + rng.normal(size=(n, 3, 2)) * rng.choice([0.3, 2.0, 15.0, 120.0], size=(n, 1, 1))
+    k = rng.integers(0, n, size=n // 8)
+    V[k] = np.round(V[k])                      # vertices on pixel centres: quotients exactly at integers
+    k = rng.integers(0, n, size=n // 8)
+    V[k, 1, 1] = V[k, 0, 1]                    # horizontal edge
+    k = rng.integers(0, n, size=n // 8)
+    V[k, 2, 0] = V[k, 0, 0]                    # vertical edge
+    k = rng.integers(0, n, size=n // 16)
+    V[k, 2] = (V[k, 0] + V[k, 1]) / 2 + 1e-9   # slivers
+    V = np.ascontiguousarray(V.reshape(n, 6))
+    assert lib.emul_tri_span_mismatches(V.ctypes.data, n, 256, 256, strict) == 0
