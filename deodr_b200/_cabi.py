@@ -115,6 +115,7 @@ SYMBOLS = [
     ("deodr_b200_render_b_host", C.c_int,
      [C.c_void_p, C.POINTER(HostScene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p,
       C.c_void_p, C.c_void_p]),
+    ("deodr_b200_host_zero", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int]),
     ("deodr_b200_check_scene", C.c_int, [C.c_void_p, C.POINTER(SceneView), C.c_void_p]),
     ("deodr_b200_timing_enable", C.c_int, [C.c_void_p, C.c_int]),
     ("deodr_b200_timing_collect", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

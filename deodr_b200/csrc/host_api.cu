@@ -11,16 +11,26 @@
 // lists instead of re-uploading and re-rendering.  Any difference -> full re-stage + forward, so the call stays
 // stateless in its semantics.
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
+#include <deque>
+#include <vector>
 #include <cstring>
 #include <functional>
 #include <mutex>
 #include <new>
 #include <thread>
 
+#include <cctype>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
+#if defined(__linux__)
+#include <pthread.h>
+#include <sched.h>
+#endif
 
+#include "host_simd.h"
 #include "workspace.h"
 
 // DEODR_B200_TRACE=1 prints the wall-clock breakdown of the host entry points (development aid)
@@ -40,73 +50,251 @@ struct HostTrace {
     }
 };
 
-// ---------------------------------------------------------------------------------------------- copy thread pool
+// ---------------------------------------------------------------------------------------------- copy thread crew
+//
+// A call moves a few hundred MB between the caller's arrays and pinned memory, as dozens of chunks that are each tied
+// to a DMA (an upload chunk is sent when its conversion is complete, a download chunk may be converted when its DMA has
+// landed).  One BATCH describes all of it: chunks in DMA order, cut into ~256 KB tasks that the workers claim with an
+// atomic counter.  The calling thread is the coordinator: it opens the gates of download chunks as their events
+// complete and enqueues the DMA of upload chunks as their last task retires.  Workers spin for a short while between
+// batches (a call issues several batches back to back) before they go to sleep on a condition variable, so that a
+// batch starts within microseconds instead of a futex wake-up per thread.
 
-class CopyPool {
-   public:
-    explicit CopyPool(int n) : stop_(false), generation_(0), pending_(0) {
-        for (int i = 0; i < n; i++) threads_.emplace_back([this, i] { loop(i); });
-    }
-    ~CopyPool() {
-        {
-            std::lock_guard<std::mutex> lock(mu_);
-            stop_ = true;
-            generation_++;
+enum OpKind { OP_COPY, OP_F64_TO_F32, OP_F32_TO_F64, OP_F32_ADD_F64, OP_ZERO, OP_EQ_RAW, OP_EQ_F32 };
+
+struct Chunk {
+    OpKind kind;
+    char *dst;        // OP_EQ_*: the mirror side of the comparison
+    const char *src;  // OP_EQ_*: the caller's side
+    size_t count;     // elements (bytes for OP_COPY / OP_ZERO / OP_EQ_RAW)
+    int n_tasks = 0;
+    std::atomic<int> remaining{0};
+    Chunk(OpKind k, void *d, const void *s, size_t c) : kind(k), dst((char *)d), src((const char *)s), count(c) {}
+};
+
+struct TaskRef {
+    int chunk;
+    size_t lo, hi;  // element range
+};
+
+struct Batch {
+    std::deque<Chunk> chunks;
+    std::vector<TaskRef> tasks;
+    std::atomic<int> next_task{0}, tasks_done{0}, open_chunks{0}, unequal{0};
+    // workers allowed on this batch (DEODR_B200_HOST_WIDE=0: development switch that keeps every batch narrow)
+    int width = (getenv("DEODR_B200_HOST_WIDE") && atoi(getenv("DEODR_B200_HOST_WIDE")) == 0) ? 7 : 1 << 20;  // (PCIe-bound batches run best with fewer threads than DRAM-bound ones)
+
+    static size_t src_elem(OpKind k) { return k == OP_F64_TO_F32 || k == OP_EQ_F32 ? 8 : k == OP_F32_TO_F64 || k == OP_F32_ADD_F64 ? 4 : 1; }
+    static size_t dst_elem(OpKind k) { return k == OP_F64_TO_F32 || k == OP_EQ_F32 ? 4 : k == OP_F32_TO_F64 || k == OP_F32_ADD_F64 ? 8 : 1; }
+
+    // appends one chunk and its tasks (`task_bytes` of the wider side each, whole cache lines)
+    int add(OpKind kind, void *dst, const void *src, size_t count, size_t task_bytes = 256 << 10) {
+        chunks.emplace_back(kind, dst, src, count);
+        Chunk &c = chunks.back();
+        const size_t wide = std::max(src_elem(kind), dst_elem(kind));
+        const size_t per = std::max<size_t>(64, (task_bytes / wide) & ~(size_t)63);
+        const int id = (int)chunks.size() - 1;
+        for (size_t lo = 0; lo < count; lo += per) {
+            tasks.push_back(TaskRef{id, lo, std::min(count, lo + per)});
+            c.n_tasks++;
         }
-        cv_.notify_all();
+        c.remaining.store(c.n_tasks, std::memory_order_relaxed);
+        return id;
+    }
+    void open_all() { open_chunks.store((int)chunks.size(), std::memory_order_release); }
+
+    void execute(const TaskRef &t) {
+        Chunk &c = chunks[t.chunk];
+        const size_t n = t.hi - t.lo;
+        switch (c.kind) {
+            case OP_COPY: deodr_simd_copy(c.dst + t.lo, c.src + t.lo, n); break;
+            case OP_ZERO: deodr_simd_zero(c.dst + t.lo, n); break;
+            case OP_F64_TO_F32: deodr_simd_f64_to_f32((float *)c.dst + t.lo, (const double *)c.src + t.lo, n); break;
+            case OP_F32_TO_F64: deodr_simd_f32_to_f64((double *)c.dst + t.lo, (const float *)c.src + t.lo, n); break;
+            case OP_F32_ADD_F64: deodr_simd_f32_add_f64((double *)c.dst + t.lo, (const float *)c.src + t.lo, n); break;
+            case OP_EQ_RAW:
+                if (memcmp(c.dst + t.lo, c.src + t.lo, n) != 0) unequal.store(1, std::memory_order_relaxed);
+                break;
+            case OP_EQ_F32:
+                if (!deodr_simd_equal_f32((const double *)c.src + t.lo, (const float *)c.dst + t.lo, n))
+                    unequal.store(1, std::memory_order_relaxed);
+                break;
+        }
+        c.remaining.fetch_sub(1, std::memory_order_release);
+        tasks_done.fetch_add(1, std::memory_order_release);
+    }
+    // claims and runs tasks until none is left; a task whose chunk is still gated is waited for (gates open in order)
+    void work() {
+        const int n = (int)tasks.size();
+        for (;;) {
+            const int t = next_task.fetch_add(1, std::memory_order_relaxed);
+            if (t >= n) return;
+            while (open_chunks.load(std::memory_order_acquire) <= tasks[t].chunk) cpu_relax();
+            execute(tasks[t]);
+        }
+    }
+    static void cpu_relax() {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    void wait_chunk(int id) {
+        while (chunks[id].remaining.load(std::memory_order_acquire) != 0) cpu_relax();
+    }
+};
+
+// CPUs of the NUMA node the calling thread runs on (Linux sysfs); empty when it cannot be determined.  The caller's
+// arrays and the pinned buffers were first touched from this thread, so the workers are kept on the same node: on a
+// two-socket host, workers of the other socket stream through the inter-socket link and slow everybody down.
+static std::vector<int> cpus_of_local_node() {
+    std::vector<int> cpus;
+#if defined(__linux__)
+    if (getenv("DEODR_B200_HOST_PIN") && atoi(getenv("DEODR_B200_HOST_PIN")) == 0) return cpus;
+    const int cpu = sched_getcpu();
+    if (cpu < 0) return cpus;
+    for (int node = 0; node < 64; node++) {
+        char path[96];
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+        FILE *f = fopen(path, "r");
+        if (!f) break;
+        char buf[1024] = "";
+        const bool got = fgets(buf, sizeof(buf), f) != nullptr;
+        fclose(f);
+        if (!got) continue;
+        std::vector<int> list;
+        for (char *p = buf; *p;) {  // "0-31,64-95"
+            char *end;
+            long a = strtol(p, &end, 10);
+            if (end == p) break;
+            long b = a;
+            if (*end == '-') b = strtol(end + 1, &end, 10);
+            for (long c = a; c <= b && c < CPU_SETSIZE; c++) list.push_back((int)c);
+            p = (*end == ',') ? end + 1 : end;
+            if (*end != ',' ) break;
+        }
+        if (std::find(list.begin(), list.end(), cpu) != list.end()) return list;
+    }
+#endif
+    return cpus;
+}
+
+class Crew {
+   public:
+    explicit Crew(int workers) {
+        // one worker per physical core of the caller's node (hyper-thread siblings and the caller's own core are left
+        // alone): streaming loops gain nothing from sharing a core
+        std::vector<int> cores;
+#if defined(__linux__)
+        const int self = sched_getcpu();
+        for (int c : cpus_of_local_node()) {
+            char path[128];
+            snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list", c);
+            int first = c;
+            if (FILE *f = fopen(path, "r")) {
+                if (fscanf(f, "%d", &first) != 1) first = c;
+                fclose(f);
+            }
+            bool mine = false;  // is the caller on this core?
+            if (first == c) {
+                if (FILE *f = fopen(path, "r")) {
+                    char buf[128] = "";
+                    if (fgets(buf, sizeof(buf), f)) {
+                        int a = -1, b = -1;
+                        if (sscanf(buf, "%d,%d", &a, &b) >= 1) mine = (a == self || b == self);
+                        if (sscanf(buf, "%d-%d", &a, &b) == 2) mine = mine || (self >= a && self <= b);
+                    }
+                    fclose(f);
+                }
+                if (!mine) cores.push_back(c);
+            }
+        }
+#endif
+        for (int i = 0; i < workers; i++) {
+            threads_.emplace_back([this, i] { loop(i); });
+#if defined(__linux__)
+            if ((int)cores.size() >= workers) {
+                cpu_set_t set;
+                CPU_ZERO(&set);
+                CPU_SET(cores[i], &set);
+                pthread_setaffinity_np(threads_.back().native_handle(), sizeof(set), &set);
+            }
+#endif
+        }
+    }
+    ~Crew() {
+        stop_.store(true);
+        publish(nullptr);
         for (auto &t : threads_) t.join();
     }
-    int size() const { return (int)threads_.size() + 1; }
-    // runs fn(part, nparts) on every worker and on the caller; returns when all parts are done
-    void run(const std::function<void(int, int)> &fn) {
-        const int nparts = size();
-        {
-            std::lock_guard<std::mutex> lock(mu_);
-            fn_ = &fn;
-            pending_ = (int)threads_.size();
-            generation_++;
-        }
-        cv_.notify_all();
-        fn(nparts - 1, nparts);
-        std::unique_lock<std::mutex> lock(mu_);
-        done_.wait(lock, [this] { return pending_ == 0; });
+    int workers() const { return (int)threads_.size(); }
+    // the workers start on `b` at once; the caller coordinates (gates, DMAs) and then calls finish(b)
+    void start(Batch *b) { publish(b); }
+    // the caller helps with what is left, then waits until every task has retired and no worker still looks at `b`
+    void finish(Batch *b) {
+        b->work();
+        const int n = (int)b->tasks.size();
+        while (b->tasks_done.load(std::memory_order_acquire) < n) Batch::cpu_relax();
+        current_.store(nullptr, std::memory_order_release);
+        while (inside_.load(std::memory_order_acquire) != 0) Batch::cpu_relax();
+    }
+    void run(Batch *b) {
+        b->open_all();
+        start(b);
+        finish(b);
     }
 
    private:
+    // Workers [0, WIDTH_PCIE_BOUND) follow every batch; the others only the wide (DRAM-bound) ones, through a generation
+    // counter of their own, so that a narrow batch neither wakes them nor has them spin next to the busy workers.
+    void publish(Batch *b) {
+        current_.store(b, std::memory_order_release);
+        const bool wide = b == nullptr || b->width > narrow_;
+        generation_[0].fetch_add(1, std::memory_order_release);
+        if (wide) generation_[1].fetch_add(1, std::memory_order_release);
+        if (sleepers_.load(std::memory_order_acquire) > 0 || b == nullptr) {
+            std::lock_guard<std::mutex> lock(mu_);
+            cv_[0].notify_all();
+            if (wide) cv_[1].notify_all();
+        }
+    }
     void loop(int index) {
+        const int group = index < narrow_ ? 0 : 1;
+        std::atomic<uint64_t> &generation = generation_[group];
         uint64_t seen = 0;
         for (;;) {
-            const std::function<void(int, int)> *fn;
-            {
-                std::unique_lock<std::mutex> lock(mu_);
-                cv_.wait(lock, [&] { return generation_ != seen; });
-                seen = generation_;
-                if (stop_) return;
-                fn = fn_;
+            // wait for a new generation: spin ~200 us (a call issues its batches back to back), then sleep
+            const auto t0 = std::chrono::steady_clock::now();
+            int spins = 0;
+            while (generation.load(std::memory_order_acquire) == seen) {
+                Batch::cpu_relax();
+                if (++spins % 512 == 0 &&
+                    std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
+                    std::unique_lock<std::mutex> lock(mu_);
+                    sleepers_.fetch_add(1, std::memory_order_acq_rel);
+                    cv_[group].wait(lock, [&] { return generation.load(std::memory_order_acquire) != seen; });
+                    sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+                }
             }
-            (*fn)(index, size());
-            {
-                std::lock_guard<std::mutex> lock(mu_);
-                pending_--;
-            }
-            done_.notify_one();
+            seen = generation.load(std::memory_order_acquire);
+            if (stop_.load()) return;
+            Batch *b = current_.load(std::memory_order_acquire);
+            if (!b) continue;
+            inside_.fetch_add(1, std::memory_order_acq_rel);
+            if (current_.load(std::memory_order_acquire) == b && index < b->width) b->work();
+            inside_.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
     std::vector<std::thread> threads_;
     std::mutex mu_;
-    std::condition_variable cv_, done_;
-    const std::function<void(int, int)> *fn_ = nullptr;
-    bool stop_;
-    uint64_t generation_;
-    int pending_;
+    std::condition_variable cv_[2];
+    std::atomic<Batch *> current_{nullptr};
+    std::atomic<uint64_t> generation_[2] = {{0}, {0}};
+    const int narrow_ = 7;  // = WIDTH_PCIE_BOUND (declared below)
+    std::atomic<int> sleepers_{0}, inside_{0};
+    std::atomic<bool> stop_{false};
 };
-
-static inline void part_range(size_t n, int part, int nparts, size_t *lo, size_t *hi) {
-    size_t per = (n + nparts - 1) / nparts;
-    per = (per + 63) & ~(size_t)63;  // whole cache lines per part
-    *lo = std::min(n, per * part);
-    *hi = std::min(n, *lo + per);
-}
 
 struct PinnedBuf {
     void *ptr = nullptr;
@@ -134,8 +322,21 @@ struct MirrorSlot {
 enum { SL_FACES, SL_FACES_UV, SL_IJ, SL_DEPTHS, SL_UV, SL_COLORS, SL_SHADE, SL_EDGEFLAGS, SL_TEXTURED, SL_SHADED,
        SL_TEXTURE, SL_BACKGROUND, SL_COUNT };
 
+static int crew_size() {
+    if (const char *e = getenv("DEODR_B200_HOST_THREADS")) return std::max(0, atoi(e) - 1);
+    // the staging loops are DRAM-bound: a quarter of the hardware threads saturates it without oversubscribing
+    return std::max(1, std::min(15, (int)std::thread::hardware_concurrency() / 4 - 1));
+}
+
+// Measured on a 2 x 32-core host with the workers kept on the caller's NUMA node (1M-triangle scene, 2048^2): the
+// forward call (PCIe-bound: 60 MB up, 83 MB down) is fastest with 8 threads (3.35 ms vs 3.6 ms with 16), the adjoint
+// call (DRAM-bound: 100 MB of image_b to convert + the 120 MB mirror comparison) with 16 (2.2 ms vs 3.3 ms with 8).
+constexpr int WIDTH_PCIE_BOUND = 7;  // workers besides the coordinator (Crew::narrow_)
+constexpr size_t DMA_CHUNK = (size_t)4 << 20;  // bytes of device-layout data per DMA / per gate
+constexpr int MAX_EVENTS = 96;
+
 struct HostPath {
-    CopyPool pool;
+    Crew crew;
     PinnedBuf mirror;   // canonical-layout copy of the last staged scene
     PinnedBuf staging;  // image_b upload / image, z, gradient download
     MirrorSlot slot[SL_COUNT];
@@ -144,8 +345,8 @@ struct HostPath {
     bool valid = false;   // mirror + device state describe a completed forward pass
     DeodrSceneView view;  // device view of the staged scene
     cudaStream_t stream = nullptr;
-    cudaEvent_t chunk_event[64];
-    HostPath() : pool(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() / 2 - 1))) {
+    cudaEvent_t chunk_event[MAX_EVENTS];
+    HostPath() : crew(crew_size()) {
         memset(&meta, 0, sizeof(meta));
         memset(&view, 0, sizeof(view));
     }
@@ -166,6 +367,24 @@ void deodr_host_path_destroy(DeodrWorkspace *ws) {
 
 static int host_path(DeodrWorkspace *ws, HostPath **out) {
     if (!ws->host) {
+#if defined(__linux__)
+        if (getenv("DEODR_B200_TRACE")) {  // development aid: where do the caller and the GPU sit?
+            char bus[32] = "";
+            int gpu_node = -2;
+            if (cudaDeviceGetPCIBusId(bus, sizeof(bus), ws->device) == cudaSuccess) {
+                for (char *p = bus; *p; p++) *p = (char)tolower(*p);
+                char path[128];
+                snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+                if (FILE *f = fopen(path, "r")) {
+                    if (fscanf(f, "%d", &gpu_node) != 1) gpu_node = -2;
+                    fclose(f);
+                }
+            }
+            const std::vector<int> cpus = cpus_of_local_node();
+            fprintf(stderr, "[deodr_b200 host path] caller on cpu %d (node cpus %d..), gpu %s numa_node %d\n", sched_getcpu(),
+                    cpus.empty() ? -1 : cpus[0], bus, gpu_node);
+        }
+#endif
         HostPath *h = new (std::nothrow) HostPath();
         if (!h) return set_error(DEODR_B200_ENOMEM, "out of host memory");
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -176,63 +395,31 @@ static int host_path(DeodrWorkspace *ws, HostPath **out) {
     return DEODR_B200_OK;
 }
 
-// ------------------------------------------------------------------------------------------ parallel host kernels
-
-static void par_copy(CopyPool &pool, void *dst, const void *src, size_t bytes) {
-    pool.run([&](int part, int nparts) {
-        size_t lo, hi;
-        part_range(bytes, part, nparts, &lo, &hi);
-        if (hi > lo) memcpy((char *)dst + lo, (const char *)src + lo, hi - lo);
-    });
+// Upload: `count` elements of `kind` (OP_COPY / OP_F64_TO_F32) from the caller's array to pinned `pin`, cut into DMA
+// chunks; returns the (chunk id, device offset, bytes) list the coordinator sends as the chunks complete.
+struct UploadPiece {
+    int chunk;
+    char *dev;
+    const char *pin;
+    size_t bytes;
+};
+static void add_upload(Batch *b, std::vector<UploadPiece> *pieces, OpKind kind, char *pin, const void *user, void *dev,
+                       size_t count) {
+    const size_t de = Batch::dst_elem(kind), se = Batch::src_elem(kind);
+    const size_t per = DMA_CHUNK / de;
+    for (size_t lo = 0; lo < count; lo += per) {
+        const size_t n = std::min(per, count - lo);
+        const int id = b->add(kind, pin + lo * de, (const char *)user + lo * se, n);
+        pieces->push_back(UploadPiece{id, (char *)dev + lo * de, pin + lo * de, n * de});
+    }
 }
-
-static void par_f64_to_f32(CopyPool &pool, float *dst, const double *src, size_t n) {
-    pool.run([&](int part, int nparts) {
-        size_t lo, hi;
-        part_range(n, part, nparts, &lo, &hi);
-        for (size_t i = lo; i < hi; i++) dst[i] = (float)src[i];
-    });
-}
-
-static void par_f32_to_f64(CopyPool &pool, double *dst, const float *src, size_t n) {
-    pool.run([&](int part, int nparts) {
-        size_t lo, hi;
-        part_range(n, part, nparts, &lo, &hi);
-        for (size_t i = lo; i < hi; i++) dst[i] = (double)src[i];
-    });
-}
-
-static void par_f32_add_to_f64(CopyPool &pool, double *dst, const float *src, size_t n) {
-    pool.run([&](int part, int nparts) {
-        size_t lo, hi;
-        part_range(n, part, nparts, &lo, &hi);
-        for (size_t i = lo; i < hi; i++) dst[i] += (double)src[i];
-    });
-}
-
-static bool par_equal_raw(CopyPool &pool, const void *a, const void *b, size_t bytes) {
-    std::vector<int> same(pool.size(), 1);
-    pool.run([&](int part, int nparts) {
-        size_t lo, hi;
-        part_range(bytes, part, nparts, &lo, &hi);
-        if (hi > lo && memcmp((const char *)a + lo, (const char *)b + lo, hi - lo) != 0) same[part] = 0;
-    });
-    return std::all_of(same.begin(), same.end(), [](int v) { return v != 0; });
-}
-
-static bool par_equal_as_float(CopyPool &pool, const double *user, const float *mirror, size_t n) {
-    std::vector<int> same(pool.size(), 1);
-    pool.run([&](int part, int nparts) {
-        size_t lo, hi;
-        part_range(n, part, nparts, &lo, &hi);
-        int ok = 1;
-        for (size_t i = lo; i < hi; i++) {
-            float f = (float)user[i];
-            ok &= (memcmp(&f, &mirror[i], sizeof(float)) == 0);
-        }
-        same[part] = ok;
-    });
-    return std::all_of(same.begin(), same.end(), [](int v) { return v != 0; });
+// the coordinator's half of an upload batch: DMA each piece as soon as its conversion has retired
+static int send_uploads(Batch *b, const std::vector<UploadPiece> &pieces, cudaStream_t st) {
+    for (const UploadPiece &p : pieces) {
+        b->wait_chunk(p.chunk);
+        CUDA_TRY(cudaMemcpyAsync(p.dev, p.pin, p.bytes, cudaMemcpyHostToDevice, st));
+    }
+    return DEODR_B200_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- scene staging
@@ -300,19 +487,22 @@ static bool same_meta(const DeodrHostScene &a, const DeodrHostScene &b) {
            a.integer_pixel_centers == b.integer_pixel_centers;
 }
 
-// true iff the caller's scene is bit-for-bit what the mirror (hence the device) already holds
-static bool scene_matches_mirror(HostPath *hp, const DeodrHostScene *h, double sigma) {
+// Appends to `b` the comparisons that decide whether the caller's scene is bit-for-bit what the mirror (hence the
+// device) already holds; false when the metadata alone rules it out (nothing appended).  The verdict is
+// b->unequal == 0 once the batch has run.
+static bool add_mirror_compare(HostPath *hp, const DeodrHostScene *h, double sigma, Batch *b) {
     if (!hp->valid || hp->sigma != sigma || !same_meta(hp->meta, *h)) return false;
     MirrorSlot slot[SL_COUNT];
     UserArrays u;
     size_t total;
     describe(h, slot, &u, &total);
-    for (int i = 0; i < SL_COUNT; i++) {
+    for (int i = 0; i < SL_COUNT; i++)
         if (slot[i].count != hp->slot[i].count) return false;
-        const char *m = (const char *)hp->mirror.ptr + hp->slot[i].offset;
-        bool eq = slot[i].as_float ? par_equal_as_float(hp->pool, (const double *)u.ptr[i], (const float *)m, slot[i].count)
-                                   : par_equal_raw(hp->pool, u.ptr[i], m, slot[i].count * slot[i].elem);
-        if (!eq) return false;
+    for (int i = 0; i < SL_COUNT; i++) {
+        if (slot[i].count == 0) continue;
+        char *m = (char *)hp->mirror.ptr + hp->slot[i].offset;
+        if (slot[i].as_float) b->add(OP_EQ_F32, m, u.ptr[i], slot[i].count, 1 << 20);
+        else b->add(OP_EQ_RAW, m, u.ptr[i], slot[i].count * slot[i].elem, 1 << 20);
     }
     return true;
 }
@@ -327,16 +517,25 @@ static int stage_scene(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *h
                              &ws->h_shade, &ws->h_edgeflags, &ws->h_textured, &ws->h_shaded, &ws->h_texture,
                              &ws->h_background};
     cudaStream_t st = hp->stream;
+    // one batch for the whole scene: every array is cut into DMA chunks, each sent as soon as the workers have
+    // written it into the mirror (conversion, copy and PCIe transfer of different chunks overlap)
+    Batch b;
+    b.width = WIDTH_PCIE_BOUND;
+    std::vector<UploadPiece> pieces;
     for (int i = 0; i < SL_COUNT; i++) {
         const MirrorSlot &s = hp->slot[i];
         const size_t bytes = s.count * s.elem;
         if (dev[i]->ensure(bytes + 16, &ws->bytes)) return DEODR_B200_ECUDA;
         if (bytes == 0) continue;
         char *m = (char *)hp->mirror.ptr + s.offset;
-        if (s.as_float) par_f64_to_f32(hp->pool, (float *)m, (const double *)u.ptr[i], s.count);
-        else par_copy(hp->pool, m, u.ptr[i], bytes);
-        CUDA_TRY(cudaMemcpyAsync(dev[i]->ptr, m, bytes, cudaMemcpyHostToDevice, st));  // overlaps the next array's copy
+        if (s.as_float) add_upload(&b, &pieces, OP_F64_TO_F32, m, u.ptr[i], dev[i]->ptr, s.count);
+        else add_upload(&b, &pieces, OP_COPY, m, u.ptr[i], dev[i]->ptr, bytes);
     }
+    b.open_all();
+    hp->crew.start(&b);
+    const int sent = send_uploads(&b, pieces, st);
+    hp->crew.finish(&b);
+    if (sent) return sent;
     DeodrSceneView *v = &hp->view;
     memset(v, 0, sizeof(*v));
     v->faces = ws->h_faces.as<uint32_t>();
@@ -378,46 +577,55 @@ static int host_forward(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *
     return DEODR_B200_OK;
 }
 
-// device -> user, chunked: DMA into pinned staging, copy threads convert / copy out while the next chunk is in flight.
-// queue_download enqueues every DMA of one buffer (events [ev0, ev0 + n_chunks)), finish_download consumes them.
-struct Download {
-    const void *dev;
-    void *user;
-    size_t count, chunk;
-    bool f32_to_f64, accumulate;
-    char *staging;
-    int ev0, n_chunks;
+// device -> user, chunked: DMA into pinned staging, workers convert / copy out chunk c while chunk c+1 is in flight.
+// add_download enqueues the DMAs of one buffer (one event per chunk, in order) and appends the gated chunks to the
+// batch; run_downloads opens the gates as the events complete.
+struct DownloadSet {
+    Batch batch;
+    int events = 0;
 };
-
-static int queue_download(HostPath *hp, Download *d, int max_events, cudaStream_t st) {
-    const size_t elem = d->f32_to_f64 ? 4 : 8;
-    d->chunk = std::max((size_t)4 << 20, (d->count + max_events - 1) / max_events);
-    d->n_chunks = (int)((d->count + d->chunk - 1) / d->chunk);
-    for (int c = 0; c < d->n_chunks; c++) {
-        size_t lo = c * d->chunk, n = std::min(d->chunk, d->count - lo);
-        CUDA_TRY(cudaMemcpyAsync(d->staging + lo * elem, (const char *)d->dev + lo * elem, n * elem,
-                                 cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaEventRecord(hp->chunk_event[d->ev0 + c], st));
+static int add_download(HostPath *hp, DownloadSet *d, OpKind kind, const void *dev, char *pin, void *user, size_t count,
+                        cudaStream_t st) {
+    const size_t se = Batch::src_elem(kind), de = Batch::dst_elem(kind);
+    const size_t per = DMA_CHUNK / se;
+    for (size_t lo = 0; lo < count; lo += per) {
+        const size_t n = std::min(per, count - lo);
+        if (d->events >= MAX_EVENTS) return set_error(DEODR_B200_EINVAL, "download too large for the event pool");
+        CUDA_TRY(cudaMemcpyAsync(pin + lo * se, (const char *)dev + lo * se, n * se, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(hp->chunk_event[d->events++], st));
+        d->batch.add(kind, (char *)user + lo * de, pin + lo * se, n);
     }
     return DEODR_B200_OK;
 }
-
-static int finish_download(HostPath *hp, const Download *d) {
-    for (int c = 0; c < d->n_chunks; c++) {
-        size_t lo = c * d->chunk, n = std::min(d->chunk, d->count - lo);
-        CUDA_TRY(cudaEventSynchronize(hp->chunk_event[d->ev0 + c]));
-        if (d->f32_to_f64) {
-            const float *src = (const float *)(d->staging + lo * 4);
-            if (d->accumulate) par_f32_add_to_f64(hp->pool, (double *)d->user + lo, src, n);
-            else par_f32_to_f64(hp->pool, (double *)d->user + lo, src, n);
-        } else {
-            par_copy(hp->pool, (char *)d->user + lo * 8, d->staging + lo * 8, n * 8);
-        }
+static int run_downloads(HostPath *hp, DownloadSet *d) {
+    hp->crew.start(&d->batch);
+    int rc = DEODR_B200_OK;
+    for (int c = 0; c < d->events; c++) {
+        if (cudaEventSynchronize(hp->chunk_event[c]) != cudaSuccess && rc == DEODR_B200_OK)
+            rc = set_error(DEODR_B200_ECUDA, "device to host copy failed");
+        d->batch.open_chunks.store(c + 1, std::memory_order_release);
     }
-    return DEODR_B200_OK;
+    hp->crew.finish(&d->batch);
+    return rc;
 }
 
 extern "C" {
+
+int deodr_b200_host_zero(DeodrWorkspace *ws, void *const *ptrs, const int64_t *bytes, int n) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    if (n < 0 || (n > 0 && (!ptrs || !bytes))) return set_error(DEODR_B200_EINVAL, "bad buffer list");
+    HostPath *hp;
+    CUDA_TRY(cudaSetDevice(ws->device));
+    if (int rc = host_path(ws, &hp)) return rc;
+    Batch b;
+    b.width = WIDTH_PCIE_BOUND;
+    for (int i = 0; i < n; i++) {
+        if (bytes[i] < 0 || (bytes[i] > 0 && !ptrs[i])) return set_error(DEODR_B200_EINVAL, "bad buffer");
+        if (bytes[i] > 0) b.add(OP_ZERO, ptrs[i], nullptr, (size_t)bytes[i], 1 << 20);
+    }
+    hp->crew.run(&b);
+    return DEODR_B200_OK;
+}
 
 int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, double *image, double *z_buffer,
                            double sigma, int antialiase_error, const double *obs, double *err_buffer) {
@@ -437,15 +645,17 @@ int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, doub
     const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
     if (int rc = hp->staging.ensure(P * C * 4 + P * 8 + 512)) return rc;
     char *stage_image = (char *)hp->staging.ptr, *stage_z = stage_image + ((P * C * 4 + 255) & ~(size_t)255);
-    // both DMAs are queued before the first chunk is consumed
-    Download d_image{ws->h_image.ptr, image, P * C, 0, true, false, stage_image, 0, 0};
-    Download d_z{ws->h_z.ptr, z_buffer, P, 0, false, false, stage_z, 40, 0};
-    if (int rc = queue_download(hp, &d_image, 40, hp->stream)) return rc;
-    if (int rc = queue_download(hp, &d_z, 24, hp->stream)) return rc;
-    if (int rc = finish_download(hp, &d_image)) return rc;
-    trace.lap("image DMA + fp32->fp64");
-    if (int rc = finish_download(hp, &d_z)) return rc;
-    trace.lap("z DMA + copy");
+    // every DMA is queued before the first chunk is consumed; z first (it is ready as soon as k_tile_z is... the
+    // stream is in order, so both follow the kernels) then the image
+    DownloadSet d;
+    d.batch.width = WIDTH_PCIE_BOUND;
+    // the event pool bounds the number of chunks: very large framebuffers use proportionally larger chunks
+    if ((P * C * 4 + P * 8) / DMA_CHUNK + 2 > (size_t)MAX_EVENTS)
+        return set_error(DEODR_B200_EUNSUPPORTED, "framebuffer too large for the host path's download pipeline");
+    if (int rc = add_download(hp, &d, OP_F32_TO_F64, ws->h_image.ptr, stage_image, image, P * C, hp->stream)) return rc;
+    if (int rc = add_download(hp, &d, OP_COPY, ws->h_z.ptr, stage_z, z_buffer, P * 8, hp->stream)) return rc;
+    if (int rc = run_downloads(hp, &d)) return rc;
+    trace.lap("image + z DMA, fp32->fp64");
     return DEODR_B200_OK;
 }
 
@@ -476,22 +686,27 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
 
     // image_b: fp64 -> fp32 into pinned staging in chunks, each chunk DMA'd while the next is converted
     if (ws->h_image_b.ensure(P * C * sizeof(float), &ws->bytes)) return DEODR_B200_ECUDA;
+    // forward state: reuse the cached one iff the caller's scene is bit-identical to the last forward's.  The
+    // comparison (host memory only) shares a batch with the image_b conversion, whose chunks go first so that their
+    // DMAs are in flight while the workers compare.
+    bool same;
     {
-        const size_t chunk = (size_t)4 << 20, count = P * C;
-        for (size_t lo = 0; lo < count; lo += chunk) {
-            size_t n = std::min(chunk, count - lo);
-            par_f64_to_f32(hp->pool, (float *)hp->staging.ptr + lo, image_b + lo, n);
-            CUDA_TRY(cudaMemcpyAsync(ws->h_image_b.as<float>() + lo, (float *)hp->staging.ptr + lo, n * 4,
-                                     cudaMemcpyHostToDevice, st));
-        }
+        Batch b;
+        std::vector<UploadPiece> pieces;
+        add_upload(&b, &pieces, OP_F64_TO_F32, (char *)hp->staging.ptr, image_b, ws->h_image_b.ptr, P * C);
+        same = add_mirror_compare(hp, scene, sigma, &b);
+        b.open_all();
+        hp->crew.start(&b);
+        const int sent = send_uploads(&b, pieces, st);
+        hp->crew.finish(&b);
+        if (sent) return sent;
+        same = same && b.unequal.load() == 0;
     }
-    trace.lap("image_b fp64->fp32 + DMA");
-    // forward state: reuse the cached one iff the caller's scene is bit-identical to the last forward's
-    if (!scene_matches_mirror(hp, scene, sigma)) {
+    trace.lap("image_b upload + mirror check");
+    if (!same) {
         if (int rc = host_forward(ws, hp, scene, sigma)) return rc;
         trace.lap("scene changed: re-forward");
     }
-    trace.lap("scene == mirror check");
     if (ws->h_grads.ensure(n_grad * sizeof(float), &ws->bytes)) return DEODR_B200_ECUDA;
     CUDA_TRY(cudaMemsetAsync(ws->h_grads.ptr, 0, n_grad * sizeof(float), st));
     DeodrGrads g;
@@ -508,18 +723,19 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
     trace.lap("backward kernels");
     double *dst[5] = {scene->ij_b, scene->colors_b, scene->uv_b, scene->shade_b, scene->texture_b};
     const size_t cnt[5] = {n_ij, n_col, n_uv, n_sh, tex};
+    if (n_grad * 4 / DMA_CHUNK + 6 > (size_t)MAX_EVENTS)
+        return set_error(DEODR_B200_EUNSUPPORTED, "gradient arrays too large for the host path's download pipeline");
+    DownloadSet d;
+    d.batch.width = WIDTH_PCIE_BOUND;
     size_t off = 0;
-    Download d[5];
     for (int i = 0; i < 5; i++) {
-        d[i] = Download{ws->h_grads.as<float>() + off, dst[i], cnt[i], 0, true, true, (char *)hp->staging.ptr + off * 4,
-                        12 * i, 0};
         if (cnt[i])
-            if (int rc = queue_download(hp, &d[i], 12, st)) return rc;
+            if (int rc = add_download(hp, &d, OP_F32_ADD_F64, ws->h_grads.as<float>() + off,
+                                      (char *)hp->staging.ptr + off * 4, dst[i], cnt[i], st))
+                return rc;
         off += cnt[i];
     }
-    for (int i = 0; i < 5; i++)
-        if (cnt[i])
-            if (int rc = finish_download(hp, &d[i])) return rc;
+    if (int rc = run_downloads(hp, &d)) return rc;
     trace.lap("gradients DMA + accumulate");
     return DEODR_B200_OK;
 }

@@ -33,12 +33,20 @@ def _call(fn, check_valid, *args):
         raise
 
 
+def zero_arrays(arrays) -> None:
+    """Zero-fills C-contiguous numpy arrays in place with the library's copy threads (host memory only)."""
+    default_renderer().zero_host(arrays)
+
+
 def _flat(a, dtype):
     """1-D C-contiguous view of ``a`` with ``dtype``; copies only when the layout / dtype requires it (the pyx always
     copies through ``flatten()``, pyx:117-131, which is pure overhead on a 1M-triangle scene)."""
     if hasattr(a, "detach"):  # torch CPU tensor (Scene3DPytorch leaves colors / depths as tensors)
         a = a.detach().numpy()
-    return np.ascontiguousarray(np.asarray(a), dtype=dtype).reshape(-1)
+    a = np.asarray(a)
+    if a.dtype == np.bool_ and dtype == np.uint8 and a.flags["C_CONTIGUOUS"]:
+        return a.view(np.uint8).reshape(-1)  # the pyx takes bool arrays as uint8 buffers (cast=True): no copy
+    return np.ascontiguousarray(a, dtype=dtype).reshape(-1)
 
 
 def _marshal(scene, nb_colors, with_grads):

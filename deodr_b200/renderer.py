@@ -212,6 +212,14 @@ class Renderer:
             int(bool(antialiase_error)), ptr(obs), ptr(err_buffer), ptr(err_buffer_b)))
 
 
+    def zero_host(self, arrays) -> None:
+        """Zero-fills C-contiguous numpy arrays in place with the host path's copy threads (deodr_b200_host_zero)."""
+        arrays = [a for a in arrays if a.size]
+        ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+        sizes = (C.c_int64 * len(arrays))(*[a.nbytes for a in arrays])
+        _cabi.check(self.lib.deodr_b200_host_zero(self._ws, ptrs, sizes, len(arrays)))
+
+
 _default: Dict[int, Renderer] = {}
 
 

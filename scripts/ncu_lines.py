@@ -55,7 +55,11 @@ for (f, ln), _ in order:
     v = agg[(f, ln)]
     text = ""
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deodr_b200", "csrc", f)
-    if os.path.exists(path):
+    rev = os.environ.get("SRC_REV")  # report taken from an older commit: show that commit's source text
+    if rev:
+        src_lines = subprocess.run(["git", "show", f"{rev}:deodr_b200/csrc/{f}"], capture_output=True, text=True).stdout.splitlines()
+        text = src_lines[ln - 1].strip()[:100] if 0 < ln <= len(src_lines) else ""
+    elif os.path.exists(path):
         src_lines = open(path).read().splitlines()
         text = src_lines[ln - 1].strip()[:100] if 0 < ln <= len(src_lines) else ""
     print(f"{f}:{ln:<5d} inst {100 * v / tot:5.1f}%  stall {100 * samp[(f, ln)] / max(tots, 1):5.1f}%  | {text}")
