@@ -155,10 +155,14 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long carry = 0;
     for (int base = 0; base < n; base += SCAN_TILE) {
+        {
+            // all sixteen loads first (the compiler cannot move a generic-pointer load above a shared-memory store on
+            // its own: interleaved they would cost sixteen serial memory round trips)
+            int in[SCAN_IPT];
 #pragma unroll
-        for (int k = 0; k < SCAN_IPT; k++) {
-            const int i = k * 1024 + tid;
-            stage[scan_slot(i)] = base + i < n ? count[base + i] : 0;
+            for (int k = 0; k < SCAN_IPT; k++) in[k] = base + k * 1024 + tid < n ? __ldg(count + base + k * 1024 + tid) : 0;
+#pragma unroll
+            for (int k = 0; k < SCAN_IPT; k++) stage[scan_slot(k * 1024 + tid)] = in[k];
         }
         __syncthreads();
         const int first = tid * SCAN_IPT;
@@ -210,10 +214,13 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
         carry += warp_sums[31];
         heavy_carry += heavy_sums[31];
         __syncthreads();
+        {
+            int outv[SCAN_IPT];
 #pragma unroll
-        for (int k = 0; k < SCAN_IPT; k++) {
-            const int i = k * 1024 + tid;
-            if (base + i < n) offset[base + i] = stage[scan_slot(i)];
+            for (int k = 0; k < SCAN_IPT; k++) outv[k] = stage[scan_slot(k * 1024 + tid)];
+#pragma unroll
+            for (int k = 0; k < SCAN_IPT; k++)
+                if (base + k * 1024 + tid < n) offset[base + k * 1024 + tid] = outv[k];
         }
         __syncthreads();
     }
@@ -595,9 +602,19 @@ __global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigm
     {
         const int edge_base = edge_offset[tile_id];
         const bool single = n_edge <= EDGE_CHUNK;
-        auto load_spans = [&](int base, int m) {
-            for (int item = tid; item < m * TS; item += EDGE_NT)
-                sh.edge.span[item / TS][item % TS] = span_cache[(size_t)(edge_base + base) * TS + item];
+        auto load_spans = [&](int base, int m) {  // (all loads of a pass before its stores, see phase_edge_setup)
+            const uint32_t *src = span_cache + (size_t)(edge_base + base) * TS;
+            for (int first = tid; first < m * TS; first += 4 * EDGE_NT) {
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (first + j * EDGE_NT < m * TS) v[j] = __ldg(src + first + j * EDGE_NT);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int item = first + j * EDGE_NT;
+                    if (item < m * TS) sh.edge.span[item / TS][item % TS] = v[j];
+                }
+            }
         };
         // pass A: forward replay (far to near) to obtain the final colour in fp64
         for (int base = 0; base < n_edge; base += EDGE_CHUNK) {

@@ -491,10 +491,27 @@ DEODR_HD void phase_shade(const SceneView &s, int x, int y, PixelState<MAXC> *p)
 DEODR_HD void phase_edge_setup(int tid, int nthreads, int n, const int *list, const EdgeRec *edge_recs, TileShared *sh) {
     constexpr int WORDS = (int)(sizeof(EdgeRec) / 8);
     static_assert(sizeof(EdgeRec) % 8 == 0, "EdgeRec is copied as 8-byte words");
-    for (int item = tid; item < n * WORDS; item += nthreads) {
-        const int e = item / WORDS, w = item % WORDS;
-        reinterpret_cast<unsigned long long *>(&sh->edge.rec[e])[w] =
-            reinterpret_cast<const unsigned long long *>(&edge_recs[list[e]])[w];
+    // four words per thread and pass, every load issued before the first store: the compiler cannot hoist a
+    // generic-pointer load above a shared-memory store itself, and one word per pass costs a memory round trip each
+    constexpr int BATCH = 4;
+    const int total = n * WORDS;
+    for (int first = tid; first < total; first += BATCH * nthreads) {
+        unsigned long long v[BATCH];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < BATCH; j++) {
+            const int item = first + j * nthreads;
+            if (item < total)
+                v[j] = reinterpret_cast<const unsigned long long *>(&edge_recs[list[item / WORDS]])[item % WORDS];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < BATCH; j++) {
+            const int item = first + j * nthreads;
+            if (item < total) reinterpret_cast<unsigned long long *>(&sh->edge.rec[item / WORDS])[item % WORDS] = v[j];
+        }
     }
 }
 

@@ -58,6 +58,25 @@ for r in rr[2:]:
     st = ", ".join(f"{k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} {v:.1f}"
                    for v, k in st)
     out.append(f"| `{name}` | " + " | ".join(vals) + f" | {st} |")
+# per-launch DRAM traffic of every raster kernel -> profiles/ncu_traffic.json (bench.py's roofline.traffic)
+phase_of = {"k_tile_z": "tile_z", "k_shade": "shade", "k_edge_fwd": "edge_fwd", "k_small_tri_bwd": "small_tri_bwd",
+            "k_interior_bwd": "interior_bwd", "k_raster_bwd": "edge_bwd", "k_bin_count": "bin_count"}
+workload = tag.split("_")[1] if "_" in tag else "c5"
+traffic = {}
+for r in rr[2:]:
+    name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+    if name in phase_of and phase_of[name] not in traffic:
+        def mb(k):
+            v, unit = float(r[idx[k]].replace(",", "")), rr[1][idx[k]]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        traffic[phase_of[name]] = int(mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum"))
+try:
+    all_traffic = json.load(open("profiles/ncu_traffic.json"))
+except Exception:
+    all_traffic = {}
+all_traffic[workload] = traffic
+all_traffic["_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (scripts/make_profile_summary.py)"
+json.dump(all_traffic, open("profiles/ncu_traffic.json", "w"), indent=1, sort_keys=True)
 if bench:
     d = json.loads(open(bench).read().strip().splitlines()[-1])
     out.append("\n## bench.py line of the same build\n\n```json\n" + json.dumps(d, indent=1) + "\n```")
