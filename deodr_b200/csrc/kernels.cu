@@ -366,7 +366,10 @@ struct TieTable {
 // of tile i+1's pre-masked records into the other buffer, so neither the list-size loads nor the copy latency sit on
 // the critical path of a tile.  Small triangles: records -> row-pair-major masks -> pixel-parallel exact z test;
 // large triangles: per-thread stencil + row spans -> the same masks.
-__global__ void __launch_bounds__(NT, 4) k_tile_z(SceneView s, int tiles_x, int num_tiles, TriBins bins, TieTable ties,
+#ifndef DEODR_TILEZ_MIN_CTAS
+#define DEODR_TILEZ_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s, TileDiv tiles_x, int num_tiles, TriBins bins, TieTable ties,
                                                   double *z_buffer, int *owner, int *face_id) {
     __shared__ TileShared sh;
     __shared__ alignas(16) PreRec pre[2][PRE_CHUNK];
@@ -478,7 +481,10 @@ static __device__ __forceinline__ void decode_owner(int code, const TieTable &ti
 // Forward, kernel 2 of 3 - colour of every pixel from its owner (one thread per pixel, tile-shaped blocks for
 // locality of the vertex gathers).  Reads owner (and z with perspective_correct), writes image.
 template <int MAXC>
-__global__ void __launch_bounds__(NT) k_shade(SceneView s, int tiles_x, TieTable ties, const int *owner,
+#ifndef DEODR_SHADE_MIN_CTAS
+#define DEODR_SHADE_MIN_CTAS 6  // 40 registers: measured 55.5 us vs 58.6 us at 48 (5 CTAs / SM) and 67 us at 56
+#endif
+__global__ void __launch_bounds__(NT, DEODR_SHADE_MIN_CTAS) k_shade(SceneView s, TileDiv tiles_x, TieTable ties, const int *owner,
                                               const double *z_buffer, float *image) {
     const Tile tile = tile_of(blockIdx.x, tiles_x);
     const int x = tile.x0 + threadIdx.x % TS, y = tile.y0 + threadIdx.x / TS;
@@ -506,13 +512,16 @@ extern "C" void deodr_b200_debug_prof(unsigned long long *out, int reset) {
 #define PROF_STAMP(i)
 #endif
 
+#ifndef DEODR_EDGE_MIN_CTAS
+#define DEODR_EDGE_MIN_CTAS 3  // 85 registers: edge_bwd 62.9 us vs 68 us at 64, 77 us at 51 (measured, c5)
+#endif
 static_assert(EDGE_ROWS == TS, "the span cache shared by k_edge_fwd and k_raster_bwd holds whole tiles");
 
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
 // One CTA of 64 threads per 16x4 pixel strip (4 per tile): the tiles crowded with edges set the kernel's duration, and
 // a strip has a 4x shorter critical path than a tile.
 template <int MAXC>
-__global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles, int num_tiles, int heavy,
+__global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                       const int *edge_count, const int *edge_offset,
                                                       const int *edge_refs, const EdgeRec *edge_recs,
                                                       uint32_t *span_cache, const double *z_buffer, float *image) {
@@ -565,7 +574,8 @@ __global__ void __launch_bounds__(EDGE_NT) k_edge_fwd(SceneView s, double sigma,
 }
 
 template <int MAXC>
-__global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigma, int tiles_x, const int *edge_tiles, int num_tiles, int heavy,
+// (register budgets are pinned: the allocator's own choice moved 64 -> 80 on an unrelated signature change)
+__global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                    const int *edge_count, const int *edge_offset, const int *edge_refs,
                                                    const EdgeRec *edge_recs, const uint32_t *span_cache, TieTable ties,
                                                    const double *z_buffer,
@@ -649,7 +659,10 @@ __global__ void __launch_bounds__(EDGE_NT) k_raster_bwd(SceneView s, double sigm
 // Interior adjoint of the pixels owned by LARGE triangles in the tiles without silhouette edges: no shared memory, no
 // z-buffer read; the gradients are summed per owner inside each warp before the scatter (interior_adjoint_warp).
 template <int MAXC>
-__global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, const int *large_tiles,
+#ifndef DEODR_INTERIOR_MIN_CTAS
+#define DEODR_INTERIOR_MIN_CTAS 5  // 51 registers: 37.8 us vs 39.9 us at 64 (measured, c5)
+#endif
+__global__ void __launch_bounds__(NT, DEODR_INTERIOR_MIN_CTAS) k_interior_bwd(SceneView s, TileDiv tiles_x, const int *large_tiles,
                                                      const int *edge_count, TieTable ties, const int *owner,
                                                      const float *image_b, DeodrGrads grads) {
     const int tile_id = large_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile with large triangles binned
@@ -679,7 +692,10 @@ __global__ void __launch_bounds__(NT) k_interior_bwd(SceneView s, int tiles_x, c
 
 // Triangle-parallel interior adjoint of the small triangles (one thread per entry of the compacted small list).
 template <int MAXC>
-__global__ void __launch_bounds__(128) k_small_tri_bwd(SceneView s, int tiles_x, const int *small_ids, int num_small,
+#ifndef DEODR_SMALL_MIN_CTAS
+#define DEODR_SMALL_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(128, DEODR_SMALL_MIN_CTAS) k_small_tri_bwd(SceneView s, int tiles_x, const int *small_ids, int num_small,
                                                        const int *edge_count, TieTable ties, const int *owner,
                                                        const float *image_b, DeodrGrads grads) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -755,19 +771,23 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
         // vs 199 us persistent x4 vs 300 us persistent x2 - the hardware CTA scheduler balances the very uneven tiles
         // better than a static stride, and 4 resident CTAs already overlap each other's copy latency.
         static const int per_sm = getenv("DEODR_B200_TILEZ_CTAS_PER_SM") ? atoi(getenv("DEODR_B200_TILEZ_CTAS_PER_SM")) : 0;
-        const int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : ws->num_tiles;
+        // DEODR_B200_TILEZ_TILES_PER_CTA = k: every CTA walks k tiles (stride = grid size) with the copy of the next
+        // tile in flight while it tests the current one
+        static const int per_cta = getenv("DEODR_B200_TILEZ_TILES_PER_CTA") ? atoi(getenv("DEODR_B200_TILEZ_TILES_PER_CTA")) : 1;
+        int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : ws->num_tiles;
+        if (per_sm <= 0 && per_cta > 1) persistent = (ws->num_tiles + per_cta - 1) / per_cta;
         k_tile_z<<<ws->num_tiles < persistent ? ws->num_tiles : persistent, NT, 0, st>>>(
-            s, ws->tiles_x, ws->num_tiles, ws->bins, ties, z, owner, face_id);
+            s, make_tile_div(ws->tiles_x), ws->num_tiles, ws->bins, ties, z, owner, face_id);
     }
     {
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
-        k_shade<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, ws->tiles_x, ties, owner, z, image);
+        k_shade<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, make_tile_div(ws->tiles_x), ties, owner, z, image);
     }
     ws->launches += 2;
     if (edge_chain) join_stream(ws, 0, st);  // the edge lists are ready
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
-        k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, ws->tiles_x, ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
+        k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
                                                             ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                             ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), z, image);
         ws->launches++;
@@ -789,7 +809,7 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, se);
             k_raster_bwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, se>>>(
-                s, sigma, ws->tiles_x, ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
+                s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
                 ws->edge_offset.as<int>(),
                 ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), ties, z, owner,
                 image_b, g,
@@ -805,7 +825,7 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     if (ws->num_large_tiles > 0) {  // pixels owned by large triangles, tiles without silhouette edges
         cudaStream_t sl = fork_stream(ws, 1, st, &first);
         PhaseTimer timer(ws, DEODR_B200_PH_INTERIOR_BWD, sl);
-        k_interior_bwd<MAXC><<<ws->num_large_tiles, NT, 0, sl>>>(s, ws->tiles_x, ws->large_tiles.as<int>(), edge_count,
+        k_interior_bwd<MAXC><<<ws->num_large_tiles, NT, 0, sl>>>(s, make_tile_div(ws->tiles_x), ws->large_tiles.as<int>(), edge_count,
                                                                  ties, owner, image_b, g);
         ws->launches++;
     }

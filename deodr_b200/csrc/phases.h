@@ -76,6 +76,27 @@ struct Tile {
     int x0, y0;  // pixel origin
 };
 
+// tile_id / tiles_x without the integer division (a runtime divisor costs ~20 instructions per thread and tile: 6 % of
+// the z pass): q = (tile_id * mul) >> 40 with mul = ceil(2^40 / tiles_x), exact while tile_id * tiles_x < 2^40
+// (tiles_x <= 2048, tile_id < 2^22 for the largest admitted image).
+struct TileDiv {
+    unsigned long long mul;
+    int tiles_x;
+};
+DEODR_HD TileDiv make_tile_div(int tiles_x) {
+    TileDiv d;
+    d.tiles_x = tiles_x;
+    d.mul = (((unsigned long long)1 << 40) + (unsigned long long)tiles_x - 1) / (unsigned long long)tiles_x;
+    return d;
+}
+DEODR_HD Tile tile_of(int tile_id, TileDiv d) {
+    const int row = (int)(((unsigned long long)(unsigned)tile_id * d.mul) >> 40);
+    Tile t;
+    t.y0 = row * TS;
+    t.x0 = (tile_id - row * d.tiles_x) * TS;
+    return t;
+}
+
 DEODR_HD Tile tile_of(int tile_id, int tiles_x) {
     Tile t;
     t.y0 = (tile_id / tiles_x) * TS;
@@ -346,17 +367,20 @@ struct PixelState {
     float col[MAXC];
 };
 
-// Phase T1a: thread tid < n walks the set bits of small-triangle record `pre[tid]` (pulled into shared memory by the bulk
+// Phase T1a: two threads per small-triangle record `pre[rec]` walk the set bits of its coverage words (pulled into shared memory by the bulk
 // copy) and appends its index to the candidate list of every pixel it covers.  A record covers ~4 pixels, a pixel is
 // covered by ~1.3 records: the z test then runs over a pixel's own candidates instead of over every record of the tile.
 // pix_cnt[] must be zero on entry (phase_pix_test leaves it so).  One flat loop over the bits (SIMT: lanes with few
 // bits idle only for max-over-lanes iterations).
 template <class Env>
 DEODR_HD void phase_pre_scatter(int tid, int n, const PreRec *pre, TileShared *sh) {
-    if (tid >= n) return;
-    const PreRec &r = pre[tid];
-    uint32_t words = 0u;  // bit p set <=> mask word p is not empty
-    for (int p = 0; p < TS / 2; p++) words |= (uint32_t)(r.mask[p] != 0u) << p;
+    // two threads per record (rows 0-7 and 8-15 of the tile): all eight warps take part in a 128-record chunk
+    static_assert(NT == 2 * PRE_CHUNK, "two threads per record of a chunk");
+    const int rec = tid % PRE_CHUNK, half = tid / PRE_CHUNK;
+    if (rec >= n) return;
+    const PreRec &r = pre[rec];
+    uint32_t words = 0u;  // bit p set <=> mask word p (of this thread's half) is not empty
+    for (int p = 4 * half; p < 4 * half + 4; p++) words |= (uint32_t)(r.mask[p] != 0u) << p;
     int p = 0;
     uint32_t w = 0u;
     for (;;) {
@@ -369,7 +393,7 @@ DEODR_HD void phase_pre_scatter(int tid, int n, const PreRec *pre, TileShared *s
         const int px = p * 32 + lowest_bit(w);
         w &= w - 1;
         const int slot = Env::shared_inc(&sh->tri.pix_cnt[px]);
-        if (slot < PIX_SLOTS) sh->tri.pix_list[slot][px] = (uint8_t)tid;
+        if (slot < PIX_SLOTS) sh->tri.pix_list[slot][px] = (uint8_t)rec;
     }
 }
 
