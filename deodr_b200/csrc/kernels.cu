@@ -143,7 +143,7 @@ constexpr int SCAN_IPT = 16;
 constexpr int SCAN_TILE = 1024 * SCAN_IPT;
 constexpr int SCAN_SMEM = (SCAN_TILE + SCAN_TILE / 32) * (int)sizeof(int);
 static __device__ __forceinline__ int scan_slot(int i) { return i + (i >> 5); }  // conflict-free for stride-16 readers
-__global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *totals) {
+__global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *totals, int *host_totals, int seq) {
     extern __shared__ int stage[];
     __shared__ unsigned long long warp_sums[32];
     __shared__ int heavy_sums[32];
@@ -229,6 +229,16 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
         totals[job.total_slot[blockIdx.x]] = (int)(unsigned)carry;
         if (nonempty) totals[job.nonempty_slot[blockIdx.x]] = (int)(carry >> 32);
         if (threshold > 0) totals[job.heavy_slot[blockIdx.x]] = heavy_carry;
+        // The last CTA to finish publishes the sixteen scalars straight into the host's (pinned, device-visible) buffer
+        // and raises a sequence flag the host is polling: no copy engine, no stream synchronisation on the critical path.
+        __threadfence();
+        const int ticket = atomicAdd(&totals[11], 1);
+        if (host_totals && ticket == (int)gridDim.x - 1) {
+            __threadfence();
+            for (int i = 0; i < 16; i++) host_totals[i] = ((volatile int *)totals)[i];
+            __threadfence_system();
+            ((volatile int *)host_totals)[16] = seq;
+        }
     }
 }
 
@@ -944,7 +954,8 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
     DeodrWorkspace *ws = new (std::nothrow) DeodrWorkspace();
     if (!ws) return set_error(DEODR_B200_ENOMEM, "out of host memory");
     ws->device = device;
-    CUDA_TRY(cudaMallocHost(&ws->host_totals, 16 * sizeof(int)));
+    CUDA_TRY(cudaMallocHost(&ws->host_totals, 32 * sizeof(int)));
+    memset(ws->host_totals, 0, 32 * sizeof(int));
     CUDA_TRY(cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
     ws->overlap = !(getenv("DEODR_B200_SERIAL") && atoi(getenv("DEODR_B200_SERIAL")));
     for (int i = 0; i < 2; i++) {
@@ -1085,11 +1096,32 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
                     {15, 8, 9},
                     {0, 0, EDGE_CHUNK},
                     {15, 15, 10}};
-        k_scan_tiles<<<3, 1024, SCAN_SMEM, st>>>(job, nt, scal);
+        ws->totals_seq = ws->totals_seq == 0x7fffffff ? 1 : ws->totals_seq + 1;
+        k_scan_tiles<<<3, 1024, SCAN_SMEM, st>>>(job, nt, scal, ws->host_totals, ws->totals_seq);
         ws->launches++;
     }
-    CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    {
+        // the one host read-back of the forward: poll the flag the scan kernel raises in pinned memory (a few
+        // microseconds after the kernel's last store) instead of a copy + stream synchronisation
+        volatile int *flag = ws->host_totals + 16;
+        for (unsigned spins = 1; *flag != ws->totals_seq; spins++) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 0xfffu) == 0) {  // every few microseconds: has the stream drained (flag lost) or failed?
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q == cudaSuccess) {
+                    if (*flag != ws->totals_seq) {  // not expected; fall back to an explicit copy
+                        CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
+                        CUDA_TRY(cudaStreamSynchronize(st));
+                    }
+                    break;
+                }
+                if (q != cudaErrorNotReady) return set_error(DEODR_B200_ECUDA, "forward pass failed: %s", cudaGetErrorString(q));
+            }
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    }
     if (check_indices && (ws->host_totals[4] & 1))
         return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
     if (check_indices && (ws->host_totals[4] & 2))

@@ -61,6 +61,7 @@ struct DeodrWorkspace {
     std::vector<cudaEvent_t> ev_start, ev_stop;
     std::vector<int> ev_phase;
     int ev_used = 0;
+    int totals_seq = 0;          // sequence number of the flag k_scan_tiles raises in host_totals[16]
     int *host_totals = nullptr;  // pinned: [0] tri refs, [1] selected edges, [2] edge refs, [3] tie counter, [4] flags
     // forward state
     int tiles_x = 0, tiles_y = 0, num_tiles = 0;
