@@ -103,6 +103,14 @@ static __device__ __forceinline__ void interior_adjoint_warp(const SceneView &s,
                                                      AtomicEmit<DevEnv>());
 }
 
+// The <1> and <3> instances are only launched for exactly 1 / 3 colour channels: telling the compiler turns every
+// `for (c < nb_colors)` loop of the inlined shading code into straight-line code (the <4> and <16> instances keep the
+// run-time channel count: 2 or 4, 5..16).
+template <int MAXC>
+static __device__ __forceinline__ void fix_channel_count(SceneView &s) {
+    if (MAXC == 1 || MAXC == 3) s.nb_colors = MAXC;
+}
+
 static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirror DeodrSceneView");
 
 // ------------------------------------------------------------------------------------------------- kernels
@@ -496,6 +504,7 @@ template <int MAXC>
 #endif
 __global__ void __launch_bounds__(NT, DEODR_SHADE_MIN_CTAS) k_shade(SceneView s, TileDiv tiles_x, TieTable ties, const int *owner,
                                               const double *z_buffer, float *image) {
+    fix_channel_count<MAXC>(s);
     const Tile tile = tile_of(blockIdx.x, tiles_x);
     const int x = tile.x0 + threadIdx.x % TS, y = tile.y0 + threadIdx.x / TS;
     if (x >= s.width || y >= s.height) return;
@@ -535,6 +544,7 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(Scene
                                                       const int *edge_count, const int *edge_offset,
                                                       const int *edge_refs, const EdgeRec *edge_recs,
                                                       uint32_t *span_cache, const double *z_buffer, float *image) {
+    fix_channel_count<MAXC>(s);
     __shared__ TileShared sh;
 #ifdef DEODR_PROFILE_EDGE
     long long prof_t = clock64();
@@ -591,6 +601,7 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(Sce
                                                    const double *z_buffer,
                                                    const int *owner, const float *image_b, DeodrGrads grads,
                                                    double *edge_acc) {
+    fix_channel_count<MAXC>(s);
     __shared__ TileShared sh;
     // one CTA of 64 threads per 16x4 strip of a tile that HAS edges (see k_edge_fwd)
     const int tile_id = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x / (TS / EDGE_ROWS)), tid = threadIdx.x;
@@ -675,6 +686,7 @@ template <int MAXC>
 __global__ void __launch_bounds__(NT, DEODR_INTERIOR_MIN_CTAS) k_interior_bwd(SceneView s, TileDiv tiles_x, const int *large_tiles,
                                                      const int *edge_count, TieTable ties, const int *owner,
                                                      const float *image_b, DeodrGrads grads) {
+    fix_channel_count<MAXC>(s);
     const int tile_id = large_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile with large triangles binned
     if (edge_count && edge_count[tile_id] > 0) return;  // handled by k_raster_bwd
     const Tile tile = tile_of(tile_id, tiles_x);
@@ -708,6 +720,7 @@ template <int MAXC>
 __global__ void __launch_bounds__(128, DEODR_SMALL_MIN_CTAS) k_small_tri_bwd(SceneView s, int tiles_x, const int *small_ids, int num_small,
                                                        const int *edge_count, TieTable ties, const int *owner,
                                                        const float *image_b, DeodrGrads grads) {
+    fix_channel_count<MAXC>(s);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_small) return;
     small_triangle_adjoint<MAXC, DevEnv>(s, small_ids[i], tiles_x, edge_count, owner, ties.pairs, image_b, grads.ij_b,
@@ -1213,7 +1226,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     const int C = s.nb_colors;
     {
     if (C == 1) launch_fwd<1>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
-    else if (C <= 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
+    else if (C == 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
     else if (C <= 4) launch_fwd<4>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
     else launch_fwd<16>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
     }
@@ -1252,7 +1265,7 @@ int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double 
     TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
     const int *edge_count = E > 0 ? ws->edge_count_ptr : nullptr;
     if (C == 1) launch_bwd<1>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
-    else if (C <= 3) launch_bwd<3>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
+    else if (C == 3) launch_bwd<3>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
     else if (C <= 4) launch_bwd<4>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
     else launch_bwd<16>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
     CUDA_TRY(cudaGetLastError());

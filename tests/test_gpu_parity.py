@@ -147,6 +147,7 @@ def test_meshes(gpu, checker):
     check(gpu, checker, torus_scene(40, 250, 200, textured=True, texture_size=64), 1.0)
     check(gpu, checker, torus_scene(100, 512, 512, nb_colors=1), 1.0)
     check(gpu, checker, torus_scene(64, 300, 200, nb_colors=4), 1.0)
+    check(gpu, checker, torus_scene(40, 160, 120, nb_colors=2), 1.0)  # 2 channels run in the <4> instance
     check(gpu, checker, torus_scene(48, 200, 200, nb_colors=7), 0.7)
 
 
