@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(Sce
 // z-buffer read; the gradients are summed per owner inside each warp before the scatter (interior_adjoint_warp).
 template <int MAXC>
 #ifndef DEODR_INTERIOR_MIN_CTAS
-#define DEODR_INTERIOR_MIN_CTAS 5  // 51 registers: 37.8 us vs 39.9 us at 64 (measured, c5)
+#define DEODR_INTERIOR_MIN_CTAS 3  // 85 registers: 39.2 us vs 40.3 us at 64 and 47.6 us at 51 (measured, c5)
 #endif
 __global__ void __launch_bounds__(NT, DEODR_INTERIOR_MIN_CTAS) k_interior_bwd(SceneView s, TileDiv tiles_x, const int *large_tiles,
                                                      const int *edge_count, TieTable ties, const int *owner,

@@ -760,16 +760,6 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
     // current one is processed
     TriAttr t;
     tri_attr(s, k, &t);
-    VertexGrads<MAXC> acc;
-    zero_vertex_grads<MAXC>(s, &acc);
-    // per-triangle constants of the interpolated (untextured) case: vertex colours and their screen-space gradient
-    float a[3][MAXC], dadx[MAXC], dady[MAXC];
-    if (!t.textured)
-        for (int q = 0; q < C; q++) {
-            for (int i = 0; i < 3; i++) a[i][q] = s.colors[(size_t)t.vid[i] * C + q];
-            dadx[q] = (float)t.gx[0] * a[0][q] + (float)t.gx[1] * a[1][q] + (float)t.gx[2] * a[2][q];
-            dady[q] = (float)t.gy[0] * a[0][q] + (float)t.gy[1] * a[1][q] + (float)t.gy[2] * a[2][q];
-        }
     float g_next[MAXC];
     int i_next = lowest_bit64(mine);
     mine &= mine - 1;
@@ -777,6 +767,39 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
         const size_t idx = (size_t)(y0 + (i_next >> shift)) * s.width + x0 + (i_next & stride_mask);
         for (int q = 0; q < C; q++) g_next[q] = image_b[idx * C + q];
     }
+    // The two kinds of triangle keep different accumulators (vertex colours vs uv + shade): separate loops, so that the
+    // common interpolated case holds 15 running sums in registers instead of a 24-float structure in local memory.
+    if (t.textured) {
+        VertexGrads<MAXC> acc;
+        zero_vertex_grads<MAXC>(s, &acc);
+        for (;;) {
+            const int i = i_next;
+            float g[MAXC];
+            for (int q = 0; q < C; q++) g[q] = g_next[q];
+            const bool more = mine != 0ull;
+            if (more) {
+                i_next = lowest_bit64(mine);
+                mine &= mine - 1;
+                const size_t idx = (size_t)(y0 + (i_next >> shift)) * s.width + x0 + (i_next & stride_mask);
+                for (int q = 0; q < C; q++) g_next[q] = image_b[idx * C + q];
+            }
+            pixel_adjoint<MAXC, Env>(s, t, x0 + (i & stride_mask), y0 + (i >> shift), g, &acc, texture_b);
+            if (!more) break;
+        }
+        flush_vertex_grads<MAXC, AtomicEmit<Env>>(s, t, acc, ij_b, colors_b, uv_b, shade_b, AtomicEmit<Env>());
+        return;
+    }
+    // interpolated triangle: per-triangle constants = vertex colours' screen-space gradient
+    float dadx[MAXC], dady[MAXC];
+    for (int q = 0; q < C; q++) {
+        const float a0 = s.colors[(size_t)t.vid[0] * C + q], a1 = s.colors[(size_t)t.vid[1] * C + q],
+                    a2 = s.colors[(size_t)t.vid[2] * C + q];
+        dadx[q] = (float)t.gx[0] * a0 + (float)t.gx[1] * a1 + (float)t.gx[2] * a2;
+        dady[q] = (float)t.gy[0] * a0 + (float)t.gy[1] * a1 + (float)t.gy[2] * a2;
+    }
+    float gij[3][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
+    float gcol[3][MAXC];
+    for (int q = 0; q < C; q++) gcol[0][q] = gcol[1][q] = gcol[2][q] = 0.0f;
     for (;;) {
         const int i = i_next;
         float g[MAXC];
@@ -788,28 +811,27 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
             const size_t idx = (size_t)(y0 + (i_next >> shift)) * s.width + x0 + (i_next & stride_mask);
             for (int q = 0; q < C; q++) g_next[q] = image_b[idx * C + q];
         }
-        const int y = y0 + (i >> shift), x = x0 + (i & stride_mask);
-        if (t.textured) {
-            pixel_adjoint<MAXC, Env>(s, t, x, y, g, &acc, texture_b);
-        } else {
-            double wd[3];
-            tri_weights(s, t, x, y, 0.0, wd);
-            const float w0 = (float)wd[0], w1 = (float)wd[1], w2 = (float)wd[2];
-            float dcdx = 0, dcdy = 0;
-            for (int q = 0; q < C; q++) {
-                dcdx += g[q] * dadx[q];
-                dcdy += g[q] * dady[q];
-                acc.attr[0][q] += g[q] * w0;
-                acc.attr[1][q] += g[q] * w1;
-                acc.attr[2][q] += g[q] * w2;
-            }
-            acc.ij[0][0] -= w0 * dcdx; acc.ij[0][1] -= w0 * dcdy;
-            acc.ij[1][0] -= w1 * dcdx; acc.ij[1][1] -= w1 * dcdy;
-            acc.ij[2][0] -= w2 * dcdx; acc.ij[2][1] -= w2 * dcdy;
+        double wd[3];
+        tri_weights(s, t, x0 + (i & stride_mask), y0 + (i >> shift), 0.0, wd);
+        const float w0 = (float)wd[0], w1 = (float)wd[1], w2 = (float)wd[2];
+        float dcdx = 0, dcdy = 0;
+        for (int q = 0; q < C; q++) {
+            dcdx += g[q] * dadx[q];
+            dcdy += g[q] * dady[q];
+            gcol[0][q] += g[q] * w0;
+            gcol[1][q] += g[q] * w1;
+            gcol[2][q] += g[q] * w2;
         }
+        gij[0][0] -= w0 * dcdx; gij[0][1] -= w0 * dcdy;
+        gij[1][0] -= w1 * dcdx; gij[1][1] -= w1 * dcdy;
+        gij[2][0] -= w2 * dcdx; gij[2][1] -= w2 * dcdy;
         if (!more) break;
     }
-    flush_vertex_grads<MAXC, AtomicEmit<Env>>(s, t, acc, ij_b, colors_b, uv_b, shade_b, AtomicEmit<Env>());
+    for (int i = 0; i < 3; i++) {  // same scatter as flush_vertex_grads, interpolated branch
+        Env::atomic_add(ij_b + 2 * (size_t)t.vid[i], gij[i][0]);
+        Env::atomic_add(ij_b + 2 * (size_t)t.vid[i] + 1, gij[i][1]);
+        for (int q = 0; q < C; q++) Env::atomic_add(colors_b + (size_t)t.vid[i] * C + q, gcol[i][q]);
+    }
 }
 
 // One thread per sorted silhouette edge: turn the accumulated plane adjoints into vertex adjoints.
