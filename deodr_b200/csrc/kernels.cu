@@ -385,10 +385,13 @@ struct TieTable {
 // the critical path of a tile.  Small triangles: records -> row-pair-major masks -> pixel-parallel exact z test;
 // large triangles: per-thread stencil + row spans -> the same masks.
 #ifndef DEODR_TILEZ_MIN_CTAS
-#define DEODR_TILEZ_MIN_CTAS 4
+#define DEODR_TILEZ_MIN_CTAS 5  // 51 registers: 98.5 us vs 102.6 us at 64 and 123 us at 85 (measured, c5)
 #endif
+// PERSP: perspective_correct as a compile-time constant (the 1/z division and its registers leave the common instance)
+template <bool PERSP>
 __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s, TileDiv tiles_x, int num_tiles, TriBins bins, TieTable ties,
                                                   double *z_buffer, int *owner, int *face_id) {
+    s.perspective_correct = PERSP ? 1 : 0;
     __shared__ TileShared sh;
     __shared__ alignas(16) PreRec pre[2][PRE_CHUNK];
     __shared__ alignas(8) uint64_t bar[2];
@@ -498,13 +501,14 @@ static __device__ __forceinline__ void decode_owner(int code, const TieTable &ti
 
 // Forward, kernel 2 of 3 - colour of every pixel from its owner (one thread per pixel, tile-shaped blocks for
 // locality of the vertex gathers).  Reads owner (and z with perspective_correct), writes image.
-template <int MAXC>
+template <int MAXC, bool PERSP>
 #ifndef DEODR_SHADE_MIN_CTAS
 #define DEODR_SHADE_MIN_CTAS 6  // 40 registers: measured 55.5 us vs 58.6 us at 48 (5 CTAs / SM) and 67 us at 56
 #endif
 __global__ void __launch_bounds__(NT, DEODR_SHADE_MIN_CTAS) k_shade(SceneView s, TileDiv tiles_x, TieTable ties, const int *owner,
                                               const double *z_buffer, float *image) {
     fix_channel_count<MAXC>(s);
+    s.perspective_correct = PERSP ? 1 : 0;
     const Tile tile = tile_of(blockIdx.x, tiles_x);
     const int x = tile.x0 + threadIdx.x % TS, y = tile.y0 + threadIdx.x / TS;
     if (x >= s.width || y >= s.height) return;
@@ -539,12 +543,13 @@ static_assert(EDGE_ROWS == TS, "the span cache shared by k_edge_fwd and k_raster
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
 // One CTA of 64 threads per 16x4 pixel strip (4 per tile): the tiles crowded with edges set the kernel's duration, and
 // a strip has a 4x shorter critical path than a tile.
-template <int MAXC>
+template <int MAXC, bool PERSP>
 __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                       const int *edge_count, const int *edge_offset,
                                                       const int *edge_refs, const EdgeRec *edge_recs,
                                                       uint32_t *span_cache, const double *z_buffer, float *image) {
     fix_channel_count<MAXC>(s);
+    s.perspective_correct = PERSP ? 1 : 0;
     __shared__ TileShared sh;
 #ifdef DEODR_PROFILE_EDGE
     long long prof_t = clock64();
@@ -602,6 +607,7 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(Sce
                                                    const int *owner, const float *image_b, DeodrGrads grads,
                                                    double *edge_acc) {
     fix_channel_count<MAXC>(s);
+    s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
     __shared__ TileShared sh;
     // one CTA of 64 threads per 16x4 strip of a tile that HAS edges (see k_edge_fwd)
     const int tile_id = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x / (TS / EDGE_ROWS)), tid = threadIdx.x;
@@ -687,6 +693,7 @@ __global__ void __launch_bounds__(NT, DEODR_INTERIOR_MIN_CTAS) k_interior_bwd(Sc
                                                      const int *edge_count, TieTable ties, const int *owner,
                                                      const float *image_b, DeodrGrads grads) {
     fix_channel_count<MAXC>(s);
+    s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
     const int tile_id = large_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile with large triangles binned
     if (edge_count && edge_count[tile_id] > 0) return;  // handled by k_raster_bwd
     const Tile tile = tile_of(tile_id, tiles_x);
@@ -721,6 +728,7 @@ __global__ void __launch_bounds__(128, DEODR_SMALL_MIN_CTAS) k_small_tri_bwd(Sce
                                                        const int *edge_count, TieTable ties, const int *owner,
                                                        const float *image_b, DeodrGrads grads) {
     fix_channel_count<MAXC>(s);
+    s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_small) return;
     small_triangle_adjoint<MAXC, DevEnv>(s, small_ids[i], tiles_x, edge_count, owner, ties.pairs, image_b, grads.ij_b,
@@ -799,18 +807,18 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
         static const int per_cta = getenv("DEODR_B200_TILEZ_TILES_PER_CTA") ? atoi(getenv("DEODR_B200_TILEZ_TILES_PER_CTA")) : 1;
         int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : ws->num_tiles;
         if (per_sm <= 0 && per_cta > 1) persistent = (ws->num_tiles + per_cta - 1) / per_cta;
-        k_tile_z<<<ws->num_tiles < persistent ? ws->num_tiles : persistent, NT, 0, st>>>(
+        (s.perspective_correct ? k_tile_z<true> : k_tile_z<false>)<<<ws->num_tiles < persistent ? ws->num_tiles : persistent, NT, 0, st>>>(
             s, make_tile_div(ws->tiles_x), ws->num_tiles, ws->bins, ties, z, owner, face_id);
     }
     {
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
-        k_shade<MAXC><<<ws->num_tiles, NT, 0, st>>>(s, make_tile_div(ws->tiles_x), ties, owner, z, image);
+        (s.perspective_correct ? k_shade<MAXC, true> : k_shade<MAXC, false>)<<<ws->num_tiles, NT, 0, st>>>(s, make_tile_div(ws->tiles_x), ties, owner, z, image);
     }
     ws->launches += 2;
     if (edge_chain) join_stream(ws, 0, st);  // the edge lists are ready
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
-        k_edge_fwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
+        (s.perspective_correct ? k_edge_fwd<MAXC, true> : k_edge_fwd<MAXC, false>)<<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
                                                             ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                             ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), z, image);
         ws->launches++;
