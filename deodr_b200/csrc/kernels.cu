@@ -106,9 +106,15 @@ static __device__ __forceinline__ void interior_adjoint_warp(const SceneView &s,
 // The <1> and <3> instances are only launched for exactly 1 / 3 colour channels: telling the compiler turns every
 // `for (c < nb_colors)` loop of the inlined shading code into straight-line code (the <4> and <16> instances keep the
 // run-time channel count: 2 or 4, 5..16).
-template <int MAXC>
+template <int MAXC, bool TEX = true>
 static __device__ __forceinline__ void fix_channel_count(SceneView &s) {
     if (MAXC == 1 || MAXC == 3) s.nb_colors = MAXC;
+    // TEX = false instances are launched for scenes without a textured triangle (flag raised by k_bin_count): nulling
+    // the texture pointer of the kernel's copy of the scene folds every texture branch (tri_attr / edge_hit test it)
+    if (!TEX) s.texture = nullptr;
+#ifdef DEODR_EXPERIMENT_NO_TEXTURE
+    s.texture = nullptr;
+#endif
 }
 
 static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirror DeodrSceneView");
@@ -117,10 +123,13 @@ static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirro
 
 // Count pass: one thread per triangle (small / large tile counts, silhouette-edge append, edge tile counts).
 __global__ void k_bin_count(SceneView s, double sigma, int tiles_x, TriBins bins, TriLists lists, EdgeList edges,
-                            int *edge_tile_count, const int *bad_indices) {
+                            int *edge_tile_count, const int *bad_indices, int *any_textured) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.nb_triangles) return;
     if (bad_indices && *bad_indices) return;  // out-of-range face indices found by k_check_scene: touch nothing
+    // does the scene hold ANY textured triangle?  (read back with the list sizes: scenes without one run kernel
+    // instances compiled without the texture paths - fewer registers, no local memory)
+    if (s.textured[k] && s.shaded[k] && *(volatile int *)any_textured == 0) atomicOr(any_textured, 1);
     bin_count_triangle<DevEnv>(s, k, sigma, tiles_x, bins, lists, edges, edge_tile_count);
 }
 
@@ -501,13 +510,13 @@ static __device__ __forceinline__ void decode_owner(int code, const TieTable &ti
 
 // Forward, kernel 2 of 3 - colour of every pixel from its owner (one thread per pixel, tile-shaped blocks for
 // locality of the vertex gathers).  Reads owner (and z with perspective_correct), writes image.
-template <int MAXC, bool PERSP>
+template <int MAXC, bool PERSP, bool TEX>
 #ifndef DEODR_SHADE_MIN_CTAS
 #define DEODR_SHADE_MIN_CTAS 6  // 40 registers: measured 55.5 us vs 58.6 us at 48 (5 CTAs / SM) and 67 us at 56
 #endif
 __global__ void __launch_bounds__(NT, DEODR_SHADE_MIN_CTAS) k_shade(SceneView s, TileDiv tiles_x, TieTable ties, const int *owner,
                                               const double *z_buffer, float *image) {
-    fix_channel_count<MAXC>(s);
+    fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = PERSP ? 1 : 0;
     const Tile tile = tile_of(blockIdx.x, tiles_x);
     const int x = tile.x0 + threadIdx.x % TS, y = tile.y0 + threadIdx.x / TS;
@@ -543,12 +552,12 @@ static_assert(EDGE_ROWS == TS, "the span cache shared by k_edge_fwd and k_raster
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
 // One CTA of 64 threads per 16x4 pixel strip (4 per tile): the tiles crowded with edges set the kernel's duration, and
 // a strip has a 4x shorter critical path than a tile.
-template <int MAXC, bool PERSP>
+template <int MAXC, bool PERSP, bool TEX>
 __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                       const int *edge_count, const int *edge_offset,
                                                       const int *edge_refs, const EdgeRec *edge_recs,
                                                       uint32_t *span_cache, const double *z_buffer, float *image) {
-    fix_channel_count<MAXC>(s);
+    fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = PERSP ? 1 : 0;
     __shared__ TileShared sh;
 #ifdef DEODR_PROFILE_EDGE
@@ -598,7 +607,7 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(Scene
 #endif
 }
 
-template <int MAXC>
+template <int MAXC, bool TEX>
 // (register budgets are pinned: the allocator's own choice moved 64 -> 80 on an unrelated signature change)
 __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                    const int *edge_count, const int *edge_offset, const int *edge_refs,
@@ -606,7 +615,7 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(Sce
                                                    const double *z_buffer,
                                                    const int *owner, const float *image_b, DeodrGrads grads,
                                                    double *edge_acc) {
-    fix_channel_count<MAXC>(s);
+    fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
     __shared__ TileShared sh;
     // one CTA of 64 threads per 16x4 strip of a tile that HAS edges (see k_edge_fwd)
@@ -685,14 +694,14 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(Sce
 
 // Interior adjoint of the pixels owned by LARGE triangles in the tiles without silhouette edges: no shared memory, no
 // z-buffer read; the gradients are summed per owner inside each warp before the scatter (interior_adjoint_warp).
-template <int MAXC>
+template <int MAXC, bool TEX>
 #ifndef DEODR_INTERIOR_MIN_CTAS
 #define DEODR_INTERIOR_MIN_CTAS 3  // 85 registers: 39.2 us vs 40.3 us at 64 and 47.6 us at 51 (measured, c5)
 #endif
 __global__ void __launch_bounds__(NT, DEODR_INTERIOR_MIN_CTAS) k_interior_bwd(SceneView s, TileDiv tiles_x, const int *large_tiles,
                                                      const int *edge_count, TieTable ties, const int *owner,
                                                      const float *image_b, DeodrGrads grads) {
-    fix_channel_count<MAXC>(s);
+    fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
     const int tile_id = large_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile with large triangles binned
     if (edge_count && edge_count[tile_id] > 0) return;  // handled by k_raster_bwd
@@ -720,14 +729,14 @@ __global__ void __launch_bounds__(NT, DEODR_INTERIOR_MIN_CTAS) k_interior_bwd(Sc
 }
 
 // Triangle-parallel interior adjoint of the small triangles (one thread per entry of the compacted small list).
-template <int MAXC>
+template <int MAXC, bool TEX>
 #ifndef DEODR_SMALL_MIN_CTAS
 #define DEODR_SMALL_MIN_CTAS 8
 #endif
 __global__ void __launch_bounds__(128, DEODR_SMALL_MIN_CTAS) k_small_tri_bwd(SceneView s, int tiles_x, const int *small_ids, int num_small,
                                                        const int *edge_count, TieTable ties, const int *owner,
                                                        const float *image_b, DeodrGrads grads) {
-    fix_channel_count<MAXC>(s);
+    fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_small) return;
@@ -795,6 +804,7 @@ static inline void join_stream(DeodrWorkspace *ws, int i, cudaStream_t st) {
 template <int MAXC>
 static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
                        float *image, double *z, int *owner, int *face_id, bool edge_chain, cudaStream_t st) {
+    const bool tex = ws->any_textured != 0;
     {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
         // DEODR_B200_TILEZ_CTAS_PER_SM = k > 0 runs k persistent CTAs per SM with the two-stage TMA pipeline; default 0 =
@@ -812,13 +822,15 @@ static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     }
     {
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
-        (s.perspective_correct ? k_shade<MAXC, true> : k_shade<MAXC, false>)<<<ws->num_tiles, NT, 0, st>>>(s, make_tile_div(ws->tiles_x), ties, owner, z, image);
+        (s.perspective_correct ? (tex ? k_shade<MAXC, true, true> : k_shade<MAXC, true, false>)
+                               : (tex ? k_shade<MAXC, false, true> : k_shade<MAXC, false, false>))<<<ws->num_tiles, NT, 0, st>>>(s, make_tile_div(ws->tiles_x), ties, owner, z, image);
     }
     ws->launches += 2;
     if (edge_chain) join_stream(ws, 0, st);  // the edge lists are ready
     if (edge_count && ws->num_edge_tiles > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
-        (s.perspective_correct ? k_edge_fwd<MAXC, true> : k_edge_fwd<MAXC, false>)<<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
+        (s.perspective_correct ? (tex ? k_edge_fwd<MAXC, true, true> : k_edge_fwd<MAXC, true, false>)
+                               : (tex ? k_edge_fwd<MAXC, false, true> : k_edge_fwd<MAXC, false, false>))<<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
                                                             ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
                                                             ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), z, image);
         ws->launches++;
@@ -832,6 +844,7 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     // Three independent chains (disjoint pixel sets, all accumulate with atomics): edge tiles (longest tail: launched
     // first so that its CTAs are dispatched first), tiles with large triangles, small triangles.
     bool first = true;
+    const bool tex = ws->any_textured != 0;
     const int E = ws->num_edges, C = s.nb_colors;
     const bool edges = edge_count && ws->num_edge_tiles > 0 && E > 0;
     if (edges) {
@@ -839,7 +852,7 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
         cudaMemsetAsync(ws->edge_acc.ptr, 0, (size_t)E * edge_acc_stride(C) * sizeof(double), se);
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, se);
-            k_raster_bwd<MAXC><<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, se>>>(
+            (tex ? k_raster_bwd<MAXC, true> : k_raster_bwd<MAXC, false>)<<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, se>>>(
                 s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
                 ws->edge_offset.as<int>(),
                 ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), ties, z, owner,
@@ -856,13 +869,13 @@ static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, con
     if (ws->num_large_tiles > 0) {  // pixels owned by large triangles, tiles without silhouette edges
         cudaStream_t sl = fork_stream(ws, 1, st, &first);
         PhaseTimer timer(ws, DEODR_B200_PH_INTERIOR_BWD, sl);
-        k_interior_bwd<MAXC><<<ws->num_large_tiles, NT, 0, sl>>>(s, make_tile_div(ws->tiles_x), ws->large_tiles.as<int>(), edge_count,
+        (tex ? k_interior_bwd<MAXC, true> : k_interior_bwd<MAXC, false>)<<<ws->num_large_tiles, NT, 0, sl>>>(s, make_tile_div(ws->tiles_x), ws->large_tiles.as<int>(), edge_count,
                                                                  ties, owner, image_b, g);
         ws->launches++;
     }
     if (ws->num_small > 0) {
         PhaseTimer timer(ws, DEODR_B200_PH_SMALL_BWD, st);
-        k_small_tri_bwd<MAXC><<<grid_for(ws->num_small, 128), 128, 0, st>>>(s, ws->tiles_x, ws->small_ids.as<int>(),
+        (tex ? k_small_tri_bwd<MAXC, true> : k_small_tri_bwd<MAXC, false>)<<<grid_for(ws->num_small, 128), 128, 0, st>>>(s, ws->tiles_x, ws->small_ids.as<int>(),
                                                                            ws->num_small, edge_count, ties, owner,
                                                                            image_b, g);
         ws->launches++;
@@ -1107,7 +1120,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
                 ws->launches++;
             }
             k_bin_count<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, bins, lists, edges, edge_count_buf,
-                                                          check_indices ? scal + 4 : nullptr);
+                                                          check_indices ? scal + 4 : nullptr, scal + 12);
             ws->launches++;
         }
         ScanJob job{{small_count, large_count, edge_count_buf},
@@ -1155,6 +1168,7 @@ int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double si
     ws->num_large_tiles = ws->host_totals[8];
     ws->num_edge_tiles = E > 0 ? ws->host_totals[9] : 0;
     ws->num_heavy_edge_tiles = E > 0 ? ws->host_totals[10] : 0;
+    ws->any_textured = ws->host_totals[12] != 0;
     rc = 0;
     rc |= ws->small_recs.ensure(((size_t)small_total + 1) * sizeof(PreRec), &ws->bytes);
     rc |= ws->tri_refs.ensure(((size_t)large_total + 4) * sizeof(int), &ws->bytes);

@@ -639,7 +639,7 @@ DEODR_HD void phase_edge_adjoint(const SceneView &s, int x, int y, int r, int n,
         const double T = h.T, omT = 1.0 - h.T;
         double T_B = 0;
         const double t3[3] = {(double)x, (double)y, 1.0};
-        if (rec.textured) {
+        if (s.texture != nullptr && rec.textured) {
             double L_B = 0;
             float e0_B = 0, e1_B = 0;
             for (int c = 0; c < C; c++) {

@@ -174,7 +174,9 @@ DEODR_HD void tri_attr(const SceneView &s, int k, TriAttr *t) {
     t->gx[2] = -e1y * inv; t->gy[2] = e1x * inv;
     t->gx[0] = -(t->gx[1] + t->gx[2]);
     t->gy[0] = -(t->gy[1] + t->gy[2]);
-    t->textured = s.textured[k] && s.shaded[k];
+    // (`s.texture != nullptr` is how a kernel instance compiled for scenes WITHOUT textured triangles folds every
+    // texture branch away: it nulls its copy of the pointer, see fix_scene_flags in kernels.cu)
+    t->textured = s.texture != nullptr && s.textured[k] && s.shaded[k];
     if (t->textured)
         for (int i = 0; i < 3; i++) t->uvid[i] = s.faces_uv[3 * k + i];
     if (s.perspective_correct)
@@ -388,7 +390,7 @@ DEODR_HD void edge_hit(const SceneView &s, const EdgeRec &r, int x, int y, doubl
     if (s.perspective_correct) { wd[0] = wd[0] * r.inv_z[0] * Ze; wd[1] = wd[1] * r.inv_z[1] * Ze; }
     h->w[0] = (float)wd[0];
     h->w[1] = (float)wd[1];
-    if (r.textured) {
+    if (s.texture != nullptr && r.textured) {
         h->u = wd[0] * s.uv[2 * (size_t)r.uvid[0]] + wd[1] * s.uv[2 * (size_t)r.uvid[1]];
         h->v = wd[0] * s.uv[2 * (size_t)r.uvid[0] + 1] + wd[1] * s.uv[2 * (size_t)r.uvid[1] + 1];
         h->L = h->w[0] * s.shade[r.vid[0]] + h->w[1] * s.shade[r.vid[1]];

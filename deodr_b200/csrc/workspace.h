@@ -68,6 +68,7 @@ struct DeodrWorkspace {
     int num_edges = 0;           // silhouette edges of the last forward pass
     double sigma = -1;
     int fwd_valid = 0;
+    int any_textured = 1;  // does the scene of the last forward hold a textured triangle? (k_bin_count raises the flag)
     int fwd_T = 0, fwd_H = 0, fwd_W = 0, fwd_C = 0;
     DevBuf zeroed;               // [scalars(8) | 6 per-tile int arrays], one memset per forward
     int *scal = nullptr, *edge_count_ptr = nullptr;  // views into `zeroed`
