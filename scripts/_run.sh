@@ -1,9 +1,6 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 2
-python scripts/gpu_parity_quick.py 2>&1 | grep -c "exact=True"
-python scripts/gpu_parity_quick.py 2>&1 | grep -A1 "torus158\|torus40" | head -6
-for i in 1 2; do
-for v in new tex notex; do
-DEODR_B200_LIB=build/ab/libdeodr_$v.so timeout 300 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read());print('$v overlapped',d['ms_per_step'])"; done; done
-for w in c3 c2; do for v in new tex; do DEODR_B200_LIB=build/ab/libdeodr_$v.so timeout 300 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --workload $w 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read());print('$w $v',d['ms_per_step'])"; done; done
+DEODR_B200_SERIAL=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 140 --csv --log-file gpurun_out/launches_r1n.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_n1.log 2>&1
+DEODR_B200_SERIAL=1 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name regex:k_ -s 56 -c 14 -f -o gpurun_out/prof_r1n python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_n2.log 2>&1
+tail -n 1 gpurun_out/ncu_n2.log
+timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/r42_bench.json 2> gpurun_out/r42_bench.err; cut -c1-300 gpurun_out/r42_bench.json
+for w in c3 c2; do timeout 300 python bench.py --steps 30 --warmup 5 --workload $w > gpurun_out/r42_$w.json 2>/dev/null; python -c "
+import json;d=json.load(open('gpurun_out/r42_$w.json'));print('$w',d['ms_per_step'],d['value'],d['e2e']['ms_per_step'],d['e2e']['value'],d['cpu_baseline']['value'])"; done
