@@ -35,11 +35,7 @@ using namespace deodr;
 
 struct DevEnv {
     static __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
-#ifdef DEODR_EXPERIMENT_NO_ATOMICS  // development aid: how much of the backward pass is float-atomic throughput?
-    static __device__ __forceinline__ void atomic_add(float *p, float v) { if (v == 1.2345e-38f) atomicAdd(p, v); }
-#else
     static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
-#endif
     static __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
     static __device__ __forceinline__ int shared_inc(int *p) { return atomicAdd(p, 1); }  // p in shared memory
 };
@@ -112,9 +108,6 @@ static __device__ __forceinline__ void fix_channel_count(SceneView &s) {
     // TEX = false instances are launched for scenes without a textured triangle (flag raised by k_bin_count): nulling
     // the texture pointer of the kernel's copy of the scene folds every texture branch (tri_attr / edge_hit test it)
     if (!TEX) s.texture = nullptr;
-#ifdef DEODR_EXPERIMENT_NO_TEXTURE
-    s.texture = nullptr;
-#endif
 }
 
 static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirror DeodrSceneView");
@@ -387,12 +380,13 @@ struct TieTable {
     int capacity;
 };
 
-// Forward, kernel 1 of 3 - z-buffer and owner ids, one 16x16 tile at a time (no colour work: few registers).
-// PERSISTENT CTAs (4 per SM) walk the tiles with a stride of gridDim.x and a two-stage TMA pipeline: while the CTA
-// z-tests tile i out of buffer `cur`, thread 0 has already issued the bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP)
-// of tile i+1's pre-masked records into the other buffer, so neither the list-size loads nor the copy latency sit on
-// the critical path of a tile.  Small triangles: records -> row-pair-major masks -> pixel-parallel exact z test;
-// large triangles: per-thread stencil + row spans -> the same masks.
+// Forward, kernel 1 of 3 - z-buffer and owner ids, one 16x16 tile per CTA (no colour work: few registers).
+// Small triangles: the tile's pre-masked records are pulled into shared memory by a bulk copy (cp.async.bulk +
+// mbarrier, SASS UBLKCP); two threads per record scatter its index into per-pixel candidate lists; each pixel then
+// z-tests its own candidates exactly.  Large triangles: stencil per triangle -> coverage masks (8 threads each) ->
+// mask test.  The kernel is written as a loop over tiles with a two-stage copy pipeline (the copy of the next tile in
+// flight while the current one is tested) and launched with one tile per CTA: measured faster than persistent CTAs
+// (DEODR_B200_TILEZ_CTAS_PER_SM / DEODR_B200_TILEZ_TILES_PER_CTA switch the other modes on for A/B runs).
 #ifndef DEODR_TILEZ_MIN_CTAS
 #define DEODR_TILEZ_MIN_CTAS 5  // 51 registers: 98.5 us vs 102.6 us at 64 and 123 us at 85 (measured, c5)
 #endif
@@ -529,20 +523,6 @@ __global__ void __launch_bounds__(NT, DEODR_SHADE_MIN_CTAS) k_shade(SceneView s,
     for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
 }
 
-#ifdef DEODR_PROFILE_EDGE
-// development aid: per-phase clock stamps of k_edge_fwd summed over CTAs (thread 0 of each CTA)
-__device__ unsigned long long g_prof[16];
-#define PROF_STAMP(i)                                                                     \
-    do {                                                                                  \
-        if (threadIdx.x == 0) { long long now_ = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(now_ - prof_t)); prof_t = now_; } \
-    } while (0)
-extern "C" void deodr_b200_debug_prof(unsigned long long *out, int reset) {
-    cudaMemcpyFromSymbol(out, g_prof, sizeof(g_prof));
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
-}
-#else
-#define PROF_STAMP(i)
-#endif
 
 #ifndef DEODR_EDGE_MIN_CTAS
 #define DEODR_EDGE_MIN_CTAS 3  // 85 registers: edge_bwd 62.9 us vs 68 us at 64, 77 us at 51 (measured, c5)
@@ -550,8 +530,10 @@ extern "C" void deodr_b200_debug_prof(unsigned long long *out, int reset) {
 static_assert(EDGE_ROWS == TS, "the span cache shared by k_edge_fwd and k_raster_bwd holds whole tiles");
 
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
-// One CTA of 64 threads per 16x4 pixel strip (4 per tile): the tiles crowded with edges set the kernel's duration, and
-// a strip has a 4x shorter critical path than a tile.
+// One CTA per tile, the tiles with more than one chunk of edges first (two-ended list built by k_scan_tiles): the few
+// crowded tiles set the kernel's duration.  Per chunk of <= 64 edges: records copied to shared memory, (edge, row) x
+// spans computed (and saved for the adjoint pass), then every pixel blends the edges of its own 64-bit hit mask in
+// far-to-near order.  (16x4 strips with four CTAs per tile were measured slower: the set-up work is per edge.)
 template <int MAXC, bool PERSP, bool TEX>
 __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                       const int *edge_count, const int *edge_offset,
@@ -560,9 +542,6 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(Scene
     fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = PERSP ? 1 : 0;
     __shared__ TileShared sh;
-#ifdef DEODR_PROFILE_EDGE
-    long long prof_t = clock64();
-#endif
     const int tile_id = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x / (TS / EDGE_ROWS)), tid = threadIdx.x;
     const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
     const int n_edge = edge_count[tile_id];
@@ -579,36 +558,24 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(Scene
         for (int k = 0; k < s.nb_colors; k++) p.col[k] = image[idx * s.nb_colors + k];
     }
     const int edge_base = edge_offset[tile_id];
-#ifdef DEODR_PROFILE_EDGE
-    if (n_edge < 0 || edge_base < 0 || p.col[0] == -12345.f || p.z == -12345.0) return;  // wait for the loads
-#endif
-    PROF_STAMP(0);
     for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
         const int m = min(EDGE_CHUNK, n_edge - base);
         phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
         __syncthreads();
-        PROF_STAMP(1);
         phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
         __syncthreads();
-        PROF_STAMP(2);
         // the backward pass reuses the spans (same scene, same sigma): 64 bytes per (tile, edge), coalesced
         for (int item = tid; item < m * TS; item += EDGE_NT)
             span_cache[(size_t)(edge_base + base) * TS + item] = sh.edge.span[item / TS][item % TS];
         if (inside) phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
-        PROF_STAMP(3);
         __syncthreads();
-        PROF_STAMP(4);
     }
     if (inside)
         for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
-    PROF_STAMP(5);
-#ifdef DEODR_PROFILE_EDGE
-    if (threadIdx.x == 0) atomicAdd(&g_prof[8], 1ull);
-#endif
 }
 
-template <int MAXC, bool TEX>
 // (register budgets are pinned: the allocator's own choice moved 64 -> 80 on an unrelated signature change)
+template <int MAXC, bool TEX>
 __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
                                                    const int *edge_count, const int *edge_offset, const int *edge_refs,
                                                    const EdgeRec *edge_recs, const uint32_t *span_cache, TieTable ties,
@@ -618,7 +585,7 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(Sce
     fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
     __shared__ TileShared sh;
-    // one CTA of 64 threads per 16x4 strip of a tile that HAS edges (see k_edge_fwd)
+    // one CTA per tile that HAS edges, crowded tiles first (see k_edge_fwd)
     const int tile_id = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x / (TS / EDGE_ROWS)), tid = threadIdx.x;
     const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
     const Tile tile = tile_of(tile_id, tiles_x);
