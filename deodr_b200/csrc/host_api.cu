@@ -2,14 +2,16 @@
 // reference's `struct Scene` (DR.h:56-90, HOST pointers, fp64) like renderScene (DR.h:2717) / renderScene_B (DR.h:2903).
 //
 // Data path of one call (everything below is inside the timed region of bench.py's `e2e`):
-//   user arrays --(copy threads: convert fp64->fp32 where the device layout is fp32)--> pinned mirror --(DMA)--> HBM
+//   user arrays --(copy crew: convert fp64->fp32 where the device layout is fp32)--> pinned mirror --(DMA)--> HBM
 //   kernels (kernels.cu)
-//   HBM --(DMA, chunked)--> pinned staging --(copy threads: fp32->fp64)--> user image / z_buffer / gradients
+//   HBM --(DMA, chunked)--> pinned staging --(copy crew: fp32->fp64)--> user image / z_buffer / gradients
+// Every transfer is ONE batch of gated chunks (see Crew / Batch below): conversion, copy and PCIe transfer of different
+// chunks overlap, and the streaming loops are AVX-512 with non-temporal stores (host_simd.cpp).
 // The pinned mirror of the scene outlives the forward call: renderScene_B re-derives everything from the scene in the
-// reference; here the adjoint call compares the caller's arrays with the mirror (exact, multi-threaded memcmp) and,
-// when they are identical to the last forward's, reuses the device-resident scene, z-buffer, owner ids and tile edge
-// lists instead of re-uploading and re-rendering.  Any difference -> full re-stage + forward, so the call stays
-// stateless in its semantics.
+// reference; here the adjoint call compares the caller's arrays with the mirror (exact, every byte, by the crew while
+// image_b is uploaded) and, when they are identical to the last forward's, reuses the device-resident scene, z-buffer,
+// owner ids and tile edge lists instead of re-uploading and re-rendering.  Any difference -> full re-stage + forward,
+// so the call stays stateless in its semantics.
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
