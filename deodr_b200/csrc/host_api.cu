@@ -213,13 +213,25 @@ class Crew {
             }
         }
 #endif
+        // Several ranks on one host (torchrun: LOCAL_RANK / LOCAL_WORLD_SIZE) must not pin their crews to the same
+        // cores: each rank takes its own slice of the node's cores and a crew that fits it.
+        int first = 0;
+        if (!getenv("DEODR_B200_HOST_THREADS")) {
+            const int local_world = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+            const int local_rank = getenv("LOCAL_RANK") ? std::max(0, atoi(getenv("LOCAL_RANK"))) : 0;
+            if (local_world > 1 && !cores.empty()) {
+                const int share = std::max(3, (int)cores.size() / local_world);
+                workers = std::max(1, std::min(workers, share - 1));
+                first = (int)(((long)(local_rank % local_world) * share) % (long)cores.size());
+            }
+        }
         for (int i = 0; i < workers; i++) {
             threads_.emplace_back([this, i] { loop(i); });
 #if defined(__linux__)
             if ((int)cores.size() >= workers) {
                 cpu_set_t set;
                 CPU_ZERO(&set);
-                CPU_SET(cores[i], &set);
+                CPU_SET(cores[(first + i) % (int)cores.size()], &set);
                 pthread_setaffinity_np(threads_.back().native_handle(), sizeof(set), &set);
             }
 #endif
