@@ -65,6 +65,45 @@ def _det3(tri2x3: np.ndarray) -> float:
     return float(np.linalg.det(np.vstack((tri2x3, np.ones(3)))))
 
 
+def confetti_scene(n_tri: int = 3000, width: int = 64, height: int = 48, size: float = 2.5, seed: int = 0,
+                   edge_ratio: float = 0.05, texture: Optional[np.ndarray] = None) -> SceneArrays:
+    """Many SMALL overlapping triangles (a few pixels each, random depths): dozens of micro-triangle records per tile
+    and more candidates per pixel than the z pass keeps in its per-pixel lists - the regime of the 1M-triangle
+    headline scene compressed into a test-sized image.  Own RNG (does not touch the global stream)."""
+    rng = np.random.default_rng(seed)
+    centre = rng.random((n_tri, 1, 2)) * np.array([height, width], dtype=np.float64)
+    tri = centre + rng.normal(size=(n_tri, 3, 2)) * size
+    # consistent orientation (front-facing for clockwise=False), degenerate ones nudged
+    det = (tri[:, 1, 0] - tri[:, 0, 0]) * (tri[:, 2, 1] - tri[:, 0, 1]) - (tri[:, 2, 0] - tri[:, 0, 0]) * (
+        tri[:, 1, 1] - tri[:, 0, 1])
+    flip = det > 0
+    tri[flip] = tri[flip][:, ::-1]
+    faces = np.arange(3 * n_tri, dtype=np.uint32).reshape(-1, 3)
+    if texture is None:
+        texture = np.zeros((2, 2, 3))
+    return SceneArrays(
+        faces=faces,
+        faces_uv=faces.copy(),
+        ij=np.ascontiguousarray(tri.reshape(-1, 2)),
+        depths=np.repeat(rng.random(n_tri) * 4 + 1, 3) + rng.random(3 * n_tri) * 0.05,
+        textured=np.zeros(n_tri, dtype=bool),
+        uv=np.zeros((3 * n_tri, 2)),
+        shade=np.zeros(3 * n_tri),
+        colors=rng.random((3 * n_tri, 3)),
+        shaded=np.zeros(n_tri, dtype=bool),
+        edgeflags=rng.random((n_tri, 3)) < edge_ratio,
+        height=height,
+        width=width,
+        nb_colors=3,
+        texture=texture,
+        background_image=None,
+        background_color=np.array([0.1, 0.2, 0.3]),
+        clockwise=False,
+        backface_culling=True,
+        perspective_correct=False,
+    )
+
+
 def soup_scene(
     n_tri: int = 30,
     width: int = 200,

@@ -9,7 +9,7 @@ import pytest
 from canon import Emulator
 from conftest import SMALL_TAGS, load_small
 
-from deodr_b200.scenes import dense_image_b, soup_scene, torus_scene
+from deodr_b200.scenes import confetti_scene, dense_image_b, soup_scene, torus_scene
 
 IMAGE_TOL = 1e-6
 GRAD_RTOL = 2e-5
@@ -64,6 +64,13 @@ def test_emulated_kernels_many_edges_per_tile(emulator, checker, texture):
     scene = soup_scene(n_tri=150, width=40, height=36, texture=texture[::4, ::4].copy(), min_det=100)
     fwd = check(emulator, checker, scene, 1.0)
     assert fwd["edges"] == 450
+
+
+def test_emulated_kernels_micro_triangle_pile(emulator, checker):
+    """Thousands of few-pixel triangles on a small image: several 128-record chunks per tile, pixels with more
+    candidates than the per-pixel lists hold (scan fall-back), small triangles carrying silhouette edges."""
+    check(emulator, checker, confetti_scene(3000, 64, 48, size=2.5, seed=1), 1.0)
+    check(emulator, checker, confetti_scene(1500, 50, 40, size=1.2, seed=2, edge_ratio=0.3), 0.7)
 
 
 def test_emulated_kernels_mesh(emulator, checker):

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 from conftest import GOLDEN, SMALL_TAGS, load_small
 
-from deodr_b200.scenes import dense_image_b, soup_scene, torus_scene
+from deodr_b200.scenes import confetti_scene, dense_image_b, soup_scene, torus_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -110,6 +110,13 @@ def test_more_primitives_than_one_shared_memory_chunk(gpu, checker, texture):
     np.random.seed(8)
     scene = soup_scene(n_tri=2000, width=256, height=256, texture=texture, min_det=300)
     check(gpu, checker, scene, 1.0)
+
+
+def test_micro_triangle_pile(gpu, checker):
+    """Several record chunks per tile and more candidates per pixel than the per-pixel lists of the z pass hold."""
+    check(gpu, checker, confetti_scene(3000, 64, 48, size=2.5, seed=1), 1.0)
+    check(gpu, checker, confetti_scene(1500, 50, 40, size=1.2, seed=2, edge_ratio=0.3), 0.7)
+    check(gpu, checker, confetti_scene(20000, 300, 200, size=2.0, seed=3), 1.0)
 
 
 def test_exact_z_ties(gpu, checker, texture):
