@@ -337,7 +337,8 @@ enum { SL_FACES, SL_FACES_UV, SL_IJ, SL_DEPTHS, SL_UV, SL_COLORS, SL_SHADE, SL_E
        SL_TEXTURE, SL_BACKGROUND, SL_COUNT };
 
 static int crew_size() {
-    if (const char *e = getenv("DEODR_B200_HOST_THREADS")) return std::max(0, atoi(e) - 1);
+    // at least one worker: the calling thread coordinates the DMAs while the workers convert
+    if (const char *e = getenv("DEODR_B200_HOST_THREADS")) return std::max(1, atoi(e) - 1);
     // the staging loops are DRAM-bound: a quarter of the hardware threads saturates it without oversubscribing
     return std::max(1, std::min(15, (int)std::thread::hardware_concurrency() / 4 - 1));
 }
