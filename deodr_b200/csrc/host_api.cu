@@ -598,11 +598,17 @@ static int host_forward(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *
 struct DownloadSet {
     Batch batch;
     int events = 0;
+    size_t chunk_bytes = DMA_CHUNK;  // grown for very large transfers so that the chunks fit the event pool
+    void size_for(size_t total_bytes, int buffers) {
+        const size_t budget = (size_t)(MAX_EVENTS - 2 * buffers - 2);
+        const size_t need = (total_bytes + budget - 1) / budget;
+        if (need > chunk_bytes) chunk_bytes = (need + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    }
 };
 static int add_download(HostPath *hp, DownloadSet *d, OpKind kind, const void *dev, char *pin, void *user, size_t count,
                         cudaStream_t st) {
     const size_t se = Batch::src_elem(kind), de = Batch::dst_elem(kind);
-    const size_t per = DMA_CHUNK / se;
+    const size_t per = d->chunk_bytes / se;
     for (size_t lo = 0; lo < count; lo += per) {
         const size_t n = std::min(per, count - lo);
         if (d->events >= MAX_EVENTS) return set_error(DEODR_B200_EINVAL, "download too large for the event pool");
@@ -664,9 +670,7 @@ int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, doub
     // stream is in order, so both follow the kernels) then the image
     DownloadSet d;
     d.batch.width = WIDTH_PCIE_BOUND;
-    // the event pool bounds the number of chunks: very large framebuffers use proportionally larger chunks
-    if ((P * C * 4 + P * 8) / DMA_CHUNK + 2 > (size_t)MAX_EVENTS)
-        return set_error(DEODR_B200_EUNSUPPORTED, "framebuffer too large for the host path's download pipeline");
+    d.size_for(P * C * 4 + P * 8, 2);  // the event pool bounds the number of chunks: huge framebuffers, larger chunks
     if (int rc = add_download(hp, &d, OP_F32_TO_F64, ws->h_image.ptr, stage_image, image, P * C, hp->stream)) return rc;
     if (int rc = add_download(hp, &d, OP_COPY, ws->h_z.ptr, stage_z, z_buffer, P * 8, hp->stream)) return rc;
     if (int rc = run_downloads(hp, &d)) return rc;
@@ -738,10 +742,9 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
     trace.lap("backward kernels");
     double *dst[5] = {scene->ij_b, scene->colors_b, scene->uv_b, scene->shade_b, scene->texture_b};
     const size_t cnt[5] = {n_ij, n_col, n_uv, n_sh, tex};
-    if (n_grad * 4 / DMA_CHUNK + 6 > (size_t)MAX_EVENTS)
-        return set_error(DEODR_B200_EUNSUPPORTED, "gradient arrays too large for the host path's download pipeline");
     DownloadSet d;
     d.batch.width = WIDTH_PCIE_BOUND;
+    d.size_for(n_grad * 4, 5);
     size_t off = 0;
     for (int i = 0; i < 5; i++) {
         if (cnt[i])
