@@ -666,8 +666,7 @@ int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, doub
     const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
     if (int rc = hp->staging.ensure(P * C * 4 + P * 8 + 512)) return rc;
     char *stage_image = (char *)hp->staging.ptr, *stage_z = stage_image + ((P * C * 4 + 255) & ~(size_t)255);
-    // every DMA is queued before the first chunk is consumed; z first (it is ready as soon as k_tile_z is... the
-    // stream is in order, so both follow the kernels) then the image
+    // every DMA is queued (in stream order behind the kernels) before the first chunk is consumed
     DownloadSet d;
     d.batch.width = WIDTH_PCIE_BOUND;
     d.size_for(P * C * 4 + P * 8, 2);  // the event pool bounds the number of chunks: huge framebuffers, larger chunks
