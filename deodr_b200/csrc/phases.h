@@ -794,8 +794,9 @@ DEODR_HD void small_triangle_adjoint(const SceneView &s, int k, int tiles_x, con
     for (int q = 0; q < C; q++) {
         const float a0 = s.colors[(size_t)t.vid[0] * C + q], a1 = s.colors[(size_t)t.vid[1] * C + q],
                     a2 = s.colors[(size_t)t.vid[2] * C + q];
-        dadx[q] = (float)t.gx[0] * a0 + (float)t.gx[1] * a1 + (float)t.gx[2] * a2;
-        dady[q] = (float)t.gy[0] * a0 + (float)t.gy[1] * a1 + (float)t.gy[2] * a2;
+        // (fp64: three terms of size |colour| / area that cancel - a sliver would lose every digit in fp32)
+        dadx[q] = (float)(t.gx[0] * (double)a0 + t.gx[1] * (double)a1 + t.gx[2] * (double)a2);
+        dady[q] = (float)(t.gy[0] * (double)a0 + t.gy[1] * (double)a1 + t.gy[2] * (double)a2);
     }
     float gij[3][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
     float gcol[3][MAXC];

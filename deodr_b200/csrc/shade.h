@@ -278,28 +278,32 @@ DEODR_HD void pixel_adjoint(const SceneView &s, const TriAttr &t, int x, int y, 
             }
         }
         float U_B = e.tap.out0 ? 0.0f : e0_B, V_B = e.tap.out1 ? 0.0f : e1_B;
-        float dudx = 0, dudy = 0, dvdx = 0, dvdy = 0, dLdx = 0, dLdy = 0;
+        // screen-space gradients of u, v, L: sums of three terms of size |attribute| / area that cancel - in fp64, or a
+        // sliver triangle (area 1e-3 px^2) loses every digit of them
+        double dudx = 0, dudy = 0, dvdx = 0, dvdy = 0, dLdx = 0, dLdy = 0;
         for (int i = 0; i < 3; i++) {
-            float gx = (float)t.gx[i], gy = (float)t.gy[i];
-            float ui = (float)s.uv[2 * (size_t)t.uvid[i]], vi = (float)s.uv[2 * (size_t)t.uvid[i] + 1];
-            float li = s.shade[t.vid[i]];
+            const double gx = t.gx[i], gy = t.gy[i];
+            const double ui = s.uv[2 * (size_t)t.uvid[i]], vi = s.uv[2 * (size_t)t.uvid[i] + 1];
+            const double li = (double)s.shade[t.vid[i]];
             dudx += gx * ui; dudy += gy * ui; dvdx += gx * vi; dvdy += gy * vi; dLdx += gx * li; dLdy += gy * li;
             acc->uv[i][0] += U_B * e.w[i];
             acc->uv[i][1] += V_B * e.w[i];
             acc->shade[i] += L_B * e.w[i];
         }
-        dcdx = U_B * dudx + V_B * dvdx + L_B * dLdx;
-        dcdy = U_B * dudy + V_B * dvdy + L_B * dLdy;
+        dcdx = (float)((double)U_B * dudx + (double)V_B * dvdx + (double)L_B * dLdx);
+        dcdy = (float)((double)U_B * dudy + (double)V_B * dvdy + (double)L_B * dLdy);
     } else {
         const float *a0 = s.colors + (size_t)t.vid[0] * C, *a1 = s.colors + (size_t)t.vid[1] * C,
                     *a2 = s.colors + (size_t)t.vid[2] * C;
-        float gx0 = (float)t.gx[0], gx1 = (float)t.gx[1], gx2 = (float)t.gx[2];
-        float gy0 = (float)t.gy[0], gy1 = (float)t.gy[1], gy2 = (float)t.gy[2];
+        double sx = 0, sy = 0;  // (fp64: the three terms cancel, see above)
         for (int c = 0; c < C; c++) {
-            dcdx += g[c] * (gx0 * a0[c] + gx1 * a1[c] + gx2 * a2[c]);
-            dcdy += g[c] * (gy0 * a0[c] + gy1 * a1[c] + gy2 * a2[c]);
+            const double c0 = (double)a0[c], c1 = (double)a1[c], c2 = (double)a2[c];
+            sx += (double)g[c] * (t.gx[0] * c0 + t.gx[1] * c1 + t.gx[2] * c2);
+            sy += (double)g[c] * (t.gy[0] * c0 + t.gy[1] * c1 + t.gy[2] * c2);
             for (int i = 0; i < 3; i++) acc->attr[i][c] += g[c] * e.w[i];
         }
+        dcdx = (float)sx;
+        dcdy = (float)sy;
     }
     for (int i = 0; i < 3; i++) {
         acc->ij[i][0] -= e.w[i] * dcdx;
