@@ -66,7 +66,7 @@ def _det3(tri2x3: np.ndarray) -> float:
 
 
 def confetti_scene(n_tri: int = 3000, width: int = 64, height: int = 48, size: float = 2.5, seed: int = 0,
-                   edge_ratio: float = 0.05, texture: Optional[np.ndarray] = None) -> SceneArrays:
+                   edge_ratio: float = 0.05, texture: Optional[np.ndarray] = None, nb_colors: int = 3) -> SceneArrays:
     """Many SMALL overlapping triangles (a few pixels each, random depths): dozens of micro-triangle records per tile
     and more candidates per pixel than the z pass keeps in its per-pixel lists - the regime of the 1M-triangle
     headline scene compressed into a test-sized image.  Own RNG (does not touch the global stream)."""
@@ -80,7 +80,7 @@ def confetti_scene(n_tri: int = 3000, width: int = 64, height: int = 48, size: f
     tri[flip] = tri[flip][:, ::-1]
     faces = np.arange(3 * n_tri, dtype=np.uint32).reshape(-1, 3)
     if texture is None:
-        texture = np.zeros((2, 2, 3))
+        texture = np.zeros((2, 2, nb_colors))
     return SceneArrays(
         faces=faces,
         faces_uv=faces.copy(),
@@ -89,15 +89,15 @@ def confetti_scene(n_tri: int = 3000, width: int = 64, height: int = 48, size: f
         textured=np.zeros(n_tri, dtype=bool),
         uv=np.zeros((3 * n_tri, 2)),
         shade=np.zeros(3 * n_tri),
-        colors=rng.random((3 * n_tri, 3)),
+        colors=rng.random((3 * n_tri, nb_colors)),
         shaded=np.zeros(n_tri, dtype=bool),
         edgeflags=rng.random((n_tri, 3)) < edge_ratio,
         height=height,
         width=width,
-        nb_colors=3,
+        nb_colors=nb_colors,
         texture=texture,
         background_image=None,
-        background_color=np.array([0.1, 0.2, 0.3]),
+        background_color=np.linspace(0.1, 0.9, nb_colors),
         clockwise=False,
         backface_culling=True,
         perspective_correct=False,
