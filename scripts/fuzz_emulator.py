@@ -3,7 +3,7 @@ __host__ __device__ code the CUDA kernels run) against the reference core compil
 
     python scripts/fuzz_emulator.py [seed] [seconds]
 
-Checks per scene: z-buffer BIT-EXACT; image error <= 6e-5 * max(1, largest |channel| of the pixel) (fp32 colours: the error is relative - at
+Checks per scene: z-buffer BIT-EXACT; image error <= 6e-5 * max(1, largest |channel| of the pixel, largest |interpolation weight| of its owner) (fp32 colours: the error is relative - at
 non-strict boundary pixels of sliver triangles the interpolation extrapolates to values of several hundred - and grows
 by half an ulp per stacked silhouette blend); gradients within 2e-4 * max|grad| in generic position.  Two measure-zero
 situations are generated on purpose and reported separately instead of failing: texture coordinates exactly on the
@@ -78,6 +78,8 @@ while time.time() - t0 < limit:
         msg += " Z-BUFFER-MISMATCH"
     # scale of a pixel = its largest channel (a small channel next to large ones is a cancellation of the same weights)
     scale = np.maximum(1.0, np.abs(image).max(axis=2, keepdims=True)) if image.size else 1.0
+    if image.size:  # ... or of the interpolation weights themselves (edge-on triangles under perspective_correct)
+        scale = np.maximum(scale, fwd["weight_scale"][:, :, None])
     err = (np.abs(fwd["image"] - image) / scale).max() if image.size else 0.0
     worst["image"] = max(worst["image"], err)
     if err > 6e-5:

@@ -56,6 +56,8 @@ class Emulator:
         subprocess.run(["make", "-C", os.path.join(_HERE, "emul")], check=True, capture_output=True)
         self.lib = C.CDLL(os.path.join(_HERE, "emul", "libemul.so"))
         self.lib.emul_render.argtypes = [C.POINTER(_cabi.SceneView), C.c_double] + [C.c_void_p] * 4
+        self.lib.emul_weight_scale.argtypes = [C.POINTER(_cabi.SceneView), C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.emul_weight_scale.restype = None
         self.lib.emul_render_b.argtypes = [C.POINTER(_cabi.SceneView), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(_cabi.Grads)]
 
@@ -71,6 +73,9 @@ class Emulator:
                                   out["owner"].ctypes.data, out["face_id"].ctypes.data)
         assert rc == 0
         out["_arrays"], out["_view"] = a, v
+        out["weight_scale"] = np.ones((H, W), np.float32)
+        self.lib.emul_weight_scale(C.byref(v), out["face_id"].ctypes.data, out["z"].ctypes.data,
+                                   out["weight_scale"].ctypes.data)
         out["ties"] = self.lib.emul_num_ties()
         out["edges"] = self.lib.emul_num_edges()
         out["tri_refs"] = self.lib.emul_tri_refs()

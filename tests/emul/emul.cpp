@@ -360,6 +360,26 @@ long emul_tri_span_mismatches(const double *V, long n, int width, int height, in
     return bad;
 }
 
+// Size of the interpolation weights of the forward owner at every pixel (1 where there is none): the scale of the fp32
+// rounding of a colour that is a sum w0 a0 + w1 a1 + w2 a2 (sliver or edge-on triangles extrapolate with |w| >> 1).
+void emul_weight_scale(const DeodrSceneView *scene, const int32_t *face_id, const double *z_buffer, float *out) {
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    for (int y = 0; y < s.height; y++)
+        for (int x = 0; x < s.width; x++) {
+            const size_t idx = (size_t)y * s.width + x;
+            float m = 1.0f;
+            if (face_id[idx] >= 0) {
+                TriAttr t;
+                tri_attr(s, face_id[idx], &t);
+                double w[3];
+                tri_weights(s, t, x, y, z_buffer[idx], w);
+                for (int i = 0; i < 3; i++) m = std::max(m, (float)std::fabs(w[i]));
+            }
+            out[idx] = m;
+        }
+}
+
 int emul_num_ties(void) { return (int)g_state.tie_pairs.size() / 2; }
 int emul_num_edges(void) { return g_state.E; }
 int emul_tri_refs(void) {
