@@ -40,7 +40,9 @@ while time.time() - t0 < limit:
     if kind == 0:
         np.random.seed(int(rng.integers(0, 1 << 30)))
         W, H = max(W, 24), max(H, 24)
-        scene = soup_scene(n_tri=int(rng.integers(1, 40)), width=W, height=H, clockwise=bool(rng.integers(0, 2)),
+        # one soup in five is crowded: hundreds of silhouette edges per tile (several edge chunks, two-pass adjoint)
+        n_soup = int(rng.integers(100, 300)) if rng.random() < 0.2 else int(rng.integers(1, 40))
+        scene = soup_scene(n_tri=n_soup, width=W, height=H, clockwise=bool(rng.integers(0, 2)),
                            textured_ratio=float(rng.random()), texture=tex[::4, ::4].copy(),
                            min_det=float(rng.choice([0.005, 0.02, 0.05])) * W * H)
     elif kind == 1:
