@@ -3,7 +3,7 @@
  *
  * This file restates, in plain C99 and with our own structure (setup records + row-span helpers shared by the
  * forward and the adjoint), the algorithm of the reference core C++/DifferentiableRenderer.h (DR.h below):
- * renderScene (DR.h:2717-2901) and renderScene_B (DR.h:2903-3135) in the antialiase_error=False mode.  Every
+ * renderScene (DR.h:2717-2901) and renderScene_B (DR.h:2903-3135), both modes (antialiase_error on / off).  Every
  * function cites the DR.h lines it follows.  It keeps the reference's operation ORDER (no FMA: compile with
  * -ffp-contract=off) so that z-buffer, coverage, image and gradients are bit-identical to the compiled reference;
  * tests/test_oracle.py checks that against oracle/_ref and against the reference's own pinned SHA-256 vectors
@@ -304,6 +304,10 @@ typedef struct {
     const OracleScene *sc;
     double *image, *z_buffer;
     int tex_size[2];
+    /* antialiase_error mode (DR.h:2066-2618): the silhouette edges overdraw the squared residual |image - obs|^2 held in
+     * `err` instead of the colours; NULL in the colour mode */
+    const double *obs;
+    double *err, *err_b;
 } Ctx;
 
 /* DR.h:741-794 + 908-972 (interpolated) and DR.h:1042-1092 + 1159-1258 (textured gouraud). */
@@ -509,6 +513,8 @@ static void draw_edge(const Ctx *c, int k, int n, double sigma, double off) {
             if (Z < c->z_buffer[idx]) {
                 double T = T0y + r.s.transp[0] * x;
                 double *px = c->image + (size_t)C * idx;
+                const double *ob = c->err ? c->obs + (size_t)C * idx : NULL;
+                double Err = 0;
                 if (r.textured) {
                     double L = L0y + r.planeL[0] * x, UV[2];
                     for (int q = 0; q < 2; q++) UV[q] = UV0y[q] + r.planeUV[3 * q] * x;
@@ -516,8 +522,18 @@ static void draw_edge(const Ctx *c, int k, int n, double sigma, double off) {
                     Tap tap = texture_tap(UV, c->tex_size[0], c->tex_size[1], C);
                     double *A = (double *)malloc(sizeof(double) * C);
                     texture_fetch(&tap, sc->texture, C, A);
-                    for (int i = 0; i < C; i++) { px[i] *= T; px[i] += (1 - T) * A[i] * L; }
+                    if (c->err)  /* DR.h:2180-2185 */
+                        for (int i = 0; i < C; i++) { double diff = A[i] * L - ob[i]; Err += diff * diff; }
+                    else
+                        for (int i = 0; i < C; i++) { px[i] *= T; px[i] += (1 - T) * A[i] * L; }
                     free(A);
+                } else if (c->err) {  /* DR.h:2457-2466 */
+                    for (int i = 0; i < C; i++) {
+                        double A = (row[i] + r.planeA[3 * i] * x);
+                        if (persp) A *= Z;
+                        double diff = A - ob[i];
+                        Err += diff * diff;
+                    }
                 } else {
                     for (int i = 0; i < C; i++) {
                         px[i] *= T;
@@ -525,6 +541,7 @@ static void draw_edge(const Ctx *c, int k, int n, double sigma, double off) {
                         px[i] += (1 - T) * A;
                     }
                 }
+                if (c->err) { c->err[idx] *= T; c->err[idx] += (1 - T) * Err; }  /* DR.h:2186-2187, 2467-2468 */
             }
         }
     }
@@ -594,11 +611,10 @@ static void gather_face(const OracleScene *sc, int k, double off, double V[3][2]
 /* DR.h:2717-2901 (antialiaseError == 0) */
 int deodr_oracle_render(const OracleScene *sc, double *image, double *z_buffer, double sigma, int antialiase_error,
                         double *obs, double *err_buffer) {
-    (void)obs; (void)err_buffer;
-    if (antialiase_error) return fail("oracle port: antialiase_error mode not restated");
+    if (antialiase_error && (!obs || !err_buffer)) return fail("antialiase_error mode needs obs and err_buffer");
     if (check_scene(sc, 0)) return 1;
     const int P = sc->height * sc->width, C = sc->nb_colors, T = sc->nb_triangles;
-    Ctx c = {sc, image, z_buffer, {sc->texture_width, sc->texture_height}};
+    Ctx c = {sc, image, z_buffer, {sc->texture_width, sc->texture_height}, NULL, NULL, NULL};
     if (sc->background_image) memcpy(image, sc->background_image, sizeof(double) * (size_t)P * C);
     else
         for (int i = 0; i < P; i++)
@@ -615,6 +631,18 @@ int deodr_oracle_render(const OracleScene *sc, double *image, double *z_buffer, 
             gather_face(sc, k, off, V, Zv);
             draw_triangle(&c, k, V, Zv);
         }
+    if (antialiase_error) {  /* DR.h:2824-2837: the residual the edges then overdraw */
+        for (int k = 0; k < P; k++) {
+            double s = 0;
+            for (int i = 0; i < C; i++) {
+                double d = image[(size_t)C * k + i] - obs[(size_t)C * k + i];
+                s += d * d;
+            }
+            err_buffer[k] = s;
+        }
+        c.obs = obs;
+        c.err = err_buffer;
+    }
     if (sigma > 0)
         for (int it = 0; it < T; it++) {
             int k = (int)keys[it].index;
@@ -686,7 +714,58 @@ static void edge_adjoint(const Ctx *c, double *image_b, int k, int n, double sig
             double Z = Z0y + r.planeZ[0] * x;
             if (!(Z < c->z_buffer[idx])) continue;
             double T = T0y + r.s.transp[0] * x, T_B = 0;
-            double *px = c->image + (size_t)C * idx, *px_b = image_b + (size_t)C * idx;
+            double *px = c->image + (size_t)C * idx, *px_b = image_b ? image_b + (size_t)C * idx : NULL;
+            if (c->err) {
+                /* antialiase_error mode: un-blend the residual, then the adjoint of Err = sum_k (A_k - obs_k)^2
+                 * (DR.h:2296-2336 textured, DR.h:2542-2576 interpolated) */
+                const double *ob = c->obs + (size_t)C * idx;
+                double L = 1, L_B = 0, UV[2] = {0, 0}, UV_B[2] = {0, 0}, Err = 0;
+                Tap tap;
+                if (r.textured) {
+                    L = L0y + r.planeL[0] * x;
+                    for (int q = 0; q < 2; q++) UV[q] = UV0y[q] + r.planeUV[3 * q] * x;
+                    tap = texture_tap(UV, c->tex_size[0], c->tex_size[1], C);
+                    texture_fetch(&tap, sc->texture, C, A);
+                    for (int i = 0; i < C; i++) A_B[i] = 0;
+                    for (int i = 0; i < C; i++) { double diff = A[i] * L - ob[i]; Err += diff * diff; }
+                } else {
+                    for (int i = 0; i < C; i++) {
+                        double Ai = row[i] + r.planeA[3 * i] * x;
+                        double diff = Ai - ob[i];
+                        Err += diff * diff;
+                    }
+                }
+                double Err_B = 0;
+                T_B += -Err * c->err_b[idx];
+                Err_B += (1 - T) * c->err_b[idx];
+                c->err[idx] -= (1 - T) * Err;
+                c->err[idx] /= T;
+                T_B += c->err_b[idx] * c->err[idx];
+                c->err_b[idx] *= T;
+                if (r.textured) {
+                    for (int i = 0; i < C; i++) {
+                        double diff = A[i] * L - ob[i];
+                        double diff_B = 2 * diff * Err_B;
+                        A_B[i] += diff_B * L;
+                        L_B += diff_B * A[i];
+                    }
+                    texture_fetch_adj(&tap, sc->texture, sc->texture_b, C, A_B, UV_B);
+                    for (int q = 0; q < 2; q++) { UV0y_B[q] += UV_B[q]; planeUV_B[3 * q] += UV_B[q] * x; }
+                    L0y_B += L_B;
+                    planeL_B[0] += x * L_B;
+                } else {
+                    for (int i = 0; i < C; i++) {
+                        double Ai = row[i] + r.planeA[3 * i] * x;
+                        double diff = Ai - ob[i];
+                        double diff_B = 2 * diff * Err_B;
+                        row_B[i] += diff_B;  /* A0y_B: accumulated and then DROPPED by the reference, see below */
+                        planeA_B[3 * i] += x * diff_B;
+                    }
+                }
+                T0y_B += T_B;
+                T_inc_B += x * T_B;
+                continue;
+            }
             if (r.textured) {
                 double L = L0y + r.planeL[0] * x, L_B = 0, UV[2], UV_B[2] = {0, 0};
                 for (int q = 0; q < 2; q++) UV[q] = UV0y[q] + r.planeUV[3 * q] * x;
@@ -726,8 +805,12 @@ static void edge_adjoint(const Ctx *c, double *image_b, int k, int n, double sig
                 for (int q = 0; q < 3; q++) planeUV_B[q + 3 * i] += UV0y_B[i] * t[q];
             for (int q = 0; q < 3; q++) planeL_B[q] += L0y_B * t[q];
         } else {
-            for (int i = 0; i < C; i++)
-                for (int j = 0; j < 3; j++) planeA_B[3 * i + j] += row_B[i] * t[j];
+            /* Reference defect kept on purpose (defect #2): rasterize_edge_interpolated_error_B never
+             * back-propagates the per-row A0y_B into xy1_to_A_B (no mul_matrixNx3_vect_B after the x loop, DR.h:2577-2583),
+             * so in antialiase_error mode the colour planes only receive their x-coefficient adjoint. */
+            if (!c->err)
+                for (int i = 0; i < C; i++)
+                    for (int j = 0; j < 3; j++) planeA_B[3 * i + j] += row_B[i] * t[j];
             for (int q = 0; q < 3; q++) transp_B[q] += T0y_B * t[q];
         }
     }
@@ -896,14 +979,15 @@ static void triangle_adjoint(const Ctx *c, double *image_b, int k, double off) {
 /* DR.h:2903-3135 (antialiaseError == 0).  `image` (AA undone) and `image_b` (scaled / zeroed) are MUTATED. */
 int deodr_oracle_render_b(const OracleScene *sc, double *image, double *z_buffer, double *image_b, double sigma,
                           int antialiase_error, double *obs, double *err_buffer, double *err_buffer_b) {
-    (void)obs; (void)err_buffer; (void)err_buffer_b;
-    if (antialiase_error) return fail("oracle port: antialiase_error mode not restated");
+    if (antialiase_error && (!obs || !err_buffer || !err_buffer_b))
+        return fail("antialiase_error mode needs obs, err_buffer and err_buffer_b");
     if (check_scene(sc, 1)) return 1;
     if (!sc->backface_culling) return fail("You have to use backface_culling true if you ant to compute gradients");
     if (sc->perspective_correct)
         return fail("backward gradient propagation not supported yet with perspective_correct=True");
     const int T = sc->nb_triangles;
-    Ctx c = {sc, image, z_buffer, {sc->texture_width, sc->texture_height}};
+    Ctx c = {sc, image, z_buffer, {sc->texture_width, sc->texture_height}, NULL, NULL, NULL};
+    if (antialiase_error) { c.obs = obs; c.err = err_buffer; c.err_b = err_buffer_b; }
     DepthKey *keys = (DepthKey *)malloc(sizeof(DepthKey) * (size_t)(T > 0 ? T : 1));
     double *area = (double *)malloc(sizeof(double) * (size_t)(T > 0 ? T : 1));
     classify(sc, keys, area);
@@ -914,10 +998,22 @@ int deodr_oracle_render_b(const OracleScene *sc, double *image, double *z_buffer
             int k = (int)keys[it].index;
             if (area[k] > 0)
                 for (int n = 2; n >= 0; n--)
-                    if (sc->edgeflags[n + k * 3]) edge_adjoint(&c, image_b, k, n, sigma, off);
+                    if (sc->edgeflags[n + k * 3]) edge_adjoint(&c, antialiase_error ? NULL : image_b, k, n, sigma, off);
         }
+    double *own_image_b = NULL;
+    if (antialiase_error) {  /* DR.h:3054-3060: the adjoint of the residual the edges started from */
+        const size_t n = (size_t)sc->width * sc->height * sc->nb_colors;
+        own_image_b = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
+        for (int k = 0; k < sc->width * sc->height; k++)
+            for (int i = 0; i < sc->nb_colors; i++)
+                own_image_b[(size_t)sc->nb_colors * k + i] =
+                    -2 * (obs[(size_t)sc->nb_colors * k + i] - image[(size_t)sc->nb_colors * k + i]) * err_buffer_b[k];
+        image_b = own_image_b;
+    }
+    c.err = NULL;  /* the triangle adjoints work on colours in both modes */
     for (int k = T - 1; k >= 0; k--)
         if (area[k] > 0) triangle_adjoint(&c, image_b, k, off);
+    free(own_image_b);
     free(keys);
     free(area);
     return 0;

@@ -110,6 +110,62 @@ def test_port_bit_identical_to_compiled_reference(texture, port_oracle, ref_orac
     assert np.array_equal(a, b) and np.array_equal(za, zb)
 
 
+def test_soup_fitting_hashes_antialiase_error_mode(texture, port_oracle):
+    """The reference's pinned run with antialiase_error=True (tests/test_triangle_soup_fitting.py:48-60: image hashes of
+    iterations 0 and 1, the second depends on the error-mode ij_b of the first), reproduced by the restatement through
+    the loop of examples/triangle_soup_fitting.py:145-175 / Scene2D.render_compare_and_backward (:701-734)."""
+    pinned = ("82a7b73fde3615ef7c70008965f4bfda8610b9001c20dd435a880bf45a31d3d6",
+              "0de2e8b80730cfc444d0552cd81e5071897a525ec6495e643ca17fb0792496c0")
+    np.random.seed(2)
+    gt = soup_scene(clockwise=False, texture=texture)
+    target, _ = port_oracle.render(gt, 1.0)
+    n = len(gt.depths)
+    gt.ij = gt.ij + np.random.randn(n, 2) * 10
+    gt.uv = np.minimum(np.maximum(gt.uv, 0), np.array(gt.texture.shape[:2]) - 1)
+    speed = np.zeros((n, 2))
+    mask = np.ones(target.shape[:2])
+    for it in range(2):
+        image, z, err = port_oracle.render(gt, 1.0, antialiase_error=True, obs=target)
+        assert sha(image) == pinned[it]
+        grads = port_oracle.render_b(gt, 1.0, image, z, None, antialiase_error=True, obs=target, err_buffer=err * mask,
+                                     err_buffer_b=mask.copy())
+        speed = 0.80 * speed - grads["ij_b"] * 0.01
+        gt.ij = gt.ij + speed
+
+
+def test_port_bit_identical_to_compiled_reference_antialiase_error_mode(texture, port_oracle, ref_oracle):
+    """antialiase_error=True (DR.h:2066-2618, 2824-2837, 3054-3060): the silhouette edges overdraw the squared residual
+    against `obs` instead of the colours.  Forward: image, z-buffer and err_buffer bit-identical; adjoint: all five
+    gradients bit-identical, including the reference's dropped row adjoint of the interpolated edges (defect #2 of
+    SURVEY.md section 0, restated on purpose)."""
+    rng = np.random.default_rng(5)
+    for seed in (3, 11):
+        for cw in (False, True):
+            np.random.seed(seed)
+            s = soup_scene(n_tri=20, width=96, height=80, clockwise=cw, texture=texture, min_det=300)
+            obs = rng.random((s.height, s.width, 3))
+            for strict, halfpix in ((True, True), (False, False), (True, False)):
+                s.strict_edge, s.integer_pixel_centers = strict, not halfpix
+                for sigma in (0.0, 1.0, 2.7):
+                    a, za, ea = ref_oracle.render(s, sigma, antialiase_error=True, obs=obs)
+                    b, zb, eb = port_oracle.render(s, sigma, antialiase_error=True, obs=obs)
+                    assert np.array_equal(a, b) and np.array_equal(za, zb) and np.array_equal(ea, eb)
+                    assert ea.min() >= 0 and np.isfinite(ea).all()
+                    err_b = rng.random((s.height, s.width)) * 2 - 1
+                    ga = ref_oracle.render_b(s, sigma, a, za, None, antialiase_error=True, obs=obs, err_buffer=ea,
+                                             err_buffer_b=err_b)
+                    gb = port_oracle.render_b(s, sigma, b, zb, None, antialiase_error=True, obs=obs, err_buffer=eb,
+                                              err_buffer_b=err_b)
+                    for name in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b"):
+                        assert np.array_equal(ga[name], gb[name]), (name, seed, cw, strict, halfpix, sigma)
+                    assert np.abs(ga["ij_b"]).max() > 0
+    # perspective-correct forward (the adjoint is not defined there)
+    s.perspective_correct = True
+    a, za, ea = ref_oracle.render(s, 1.0, antialiase_error=True, obs=obs)
+    b, zb, eb = port_oracle.render(s, 1.0, antialiase_error=True, obs=obs)
+    assert np.array_equal(a, b) and np.array_equal(za, zb) and np.array_equal(ea, eb)
+
+
 def test_oracle_error_paths(texture, port_oracle):
     np.random.seed(2)
     s = soup_scene(texture=texture)
