@@ -681,6 +681,144 @@ DEODR_HD void phase_edge_adjoint(const SceneView &s, int x, int y, int r, int n,
     }
 }
 
+// ------------------------------------------------------------------------ antialiase_error mode (row f3, DR.h:2066-2618)
+//
+// The silhouette edges overdraw the squared residual err = sum_c (image_c - obs_c)^2 instead of the colours: the image
+// keeps its aliased edges, err <- T * err + (1 - T) * Err_edge with Err_edge = sum_c (A_c - obs_c)^2 where
+// Z_edge < z_buffer.  These phases mirror phase_edge_blend / replay / adjoint on that scalar.  They are exercised by the
+// CPU emulation against the oracle (tests/test_emul.py); the CUDA entry points still report the mode as unsupported
+// until the kernels that call them have been validated on a GPU.
+
+// residual of one pixel before the edges (DR.h:2824-2837)
+template <int MAXC>
+DEODR_HD double pixel_residual(const SceneView &s, const float *col, const float *obs) {
+    double r = 0;
+    for (int c = 0; c < s.nb_colors; c++) {
+        const double d = (double)col[c] - (double)obs[c];
+        r += d * d;
+    }
+    return r;
+}
+
+template <int MAXC>
+DEODR_HD double edge_residual(const SceneView &s, const EdgeHit<MAXC> &h, const float *obs) {
+    double r = 0;
+    for (int c = 0; c < s.nb_colors; c++) {
+        const double d = (double)h.A[c] - (double)obs[c];
+        r += d * d;
+    }
+    return r;
+}
+
+// forward: overdraw of the residual in list order (DR.h:2186-2187, 2467-2468)
+template <int MAXC>
+DEODR_HD void phase_edge_blend_error(const SceneView &s, int x, int y, int r, int n, const TileShared *sh, double z,
+                                     const float *obs, float *err) {
+    for (unsigned long long mask = edge_hit_mask(sh, n, r, x); mask; mask &= mask - 1) {
+        const EdgeRec &rec = sh->edge.rec[lowest_bit64(mask)];
+        double ze = edge_z(rec, x, y, s.perspective_correct != 0);
+        if (!(ze < z)) continue;
+        EdgeHit<MAXC> h;
+        edge_hit<MAXC>(s, rec, x, y, ze, &h);
+        *err = *err * (float)h.T + (float)(1.0 - h.T) * (float)edge_residual<MAXC>(s, h, obs);
+    }
+}
+
+// Running state of a pixel during the backward edge sweep of the error mode.
+template <int MAXC>
+struct ErrorAdjointState {
+    double err;        // residual after the edges processed so far (forward) / before them (reverse), fp64
+    double g;          // adjoint of the residual
+    float col[MAXC];   // the pixel's (aliased) colour
+    bool has;          // err / col initialised (lazily: only pixels inside an edge band need them)
+};
+
+template <int MAXC>
+DEODR_HD void phase_edge_replay_error(const SceneView &s, int x, int y, int r, int n, const TileShared *sh,
+                                      const PixelState<MAXC> &p, const float *obs, ErrorAdjointState<MAXC> *a) {
+    for (unsigned long long mask = edge_hit_mask(sh, n, r, x); mask; mask &= mask - 1) {
+        const EdgeRec &rec = sh->edge.rec[lowest_bit64(mask)];
+        double ze = edge_z(rec, x, y, false);
+        if (!(ze < p.z)) continue;
+        if (!a->has) {
+            PixelState<MAXC> q = p;
+            phase_shade<MAXC>(s, x, y, &q);
+            for (int c = 0; c < s.nb_colors; c++) a->col[c] = q.col[c];
+            a->err = pixel_residual<MAXC>(s, a->col, obs);
+            a->has = true;
+        }
+        EdgeHit<MAXC> h;
+        edge_hit<MAXC>(s, rec, x, y, ze, &h);
+        a->err = a->err * h.T + (1.0 - h.T) * edge_residual<MAXC>(s, h, obs);
+    }
+}
+
+// Reverse sweep (near to far): un-blend the residual, per-edge plane adjoints, g <- T * g.
+// DR.h:2296-2336 (textured) / DR.h:2542-2576 (interpolated).  `compat` reproduces the reference's defect #2: for
+// interpolated edges only the x moment of the colour-plane adjoint is kept (the per-row A0y_B is never propagated,
+// DR.h:2577-2583); with compat = false the mathematically complete adjoint is accumulated.
+template <int MAXC, class Env>
+DEODR_HD void phase_edge_adjoint_error(const SceneView &s, int x, int y, int r, int n, const TileShared *sh,
+                                       const PixelState<MAXC> &p, const float *obs, ErrorAdjointState<MAXC> *a,
+                                       double *edge_acc, float *texture_b, bool compat) {
+    const int C = s.nb_colors;
+    const int stride = edge_acc_stride(C);
+    for (unsigned long long mask = edge_hit_mask(sh, n, r, x); mask;) {
+        const int e = highest_bit64(mask);
+        mask &= ~(1ull << e);
+        const EdgeRec &rec = sh->edge.rec[e];
+        double ze = edge_z(rec, x, y, false);
+        if (!(ze < p.z)) continue;
+        EdgeHit<MAXC> h;
+        edge_hit<MAXC>(s, rec, x, y, ze, &h);
+        double *acc = edge_acc + (size_t)rec.rank * stride;
+        const double T = h.T, omT = 1.0 - h.T;
+        const double Err = edge_residual<MAXC>(s, h, obs);
+        const double prev = (a->err - omT * Err) / T;  // residual before this edge
+        const double T_B = a->g * (prev - Err);
+        const double Err_B = omT * a->g;
+        a->err = prev;
+        a->g = a->g * T;
+        const double t3[3] = {(double)x, (double)y, 1.0};
+        if (s.texture != nullptr && rec.textured) {
+            double L_B = 0;
+            float e0_B = 0, e1_B = 0;
+            for (int c = 0; c < C; c++) {
+                const double diff_B = 2.0 * ((double)h.A[c] - (double)obs[c]) * Err_B;  // A_c = texval_c * L
+                const float A_B = (float)diff_B * h.L;                                   // adjoint of the texture sample
+                L_B += diff_B * (double)h.texval[c];
+                texture_fetch_duv(h.tap, s.texture, c, A_B, &e0_B, &e1_B);
+                if (texture_b) {
+                    float w00 = (1.0f - h.tap.e0) * (1.0f - h.tap.e1), w10 = h.tap.e0 * (1.0f - h.tap.e1);
+                    float w01 = (1.0f - h.tap.e0) * h.tap.e1, w11 = h.tap.e0 * h.tap.e1;
+                    Env::atomic_add(texture_b + h.tap.i00 + c, w00 * A_B);
+                    Env::atomic_add(texture_b + h.tap.i10 + c, w10 * A_B);
+                    Env::atomic_add(texture_b + h.tap.i01 + c, w01 * A_B);
+                    Env::atomic_add(texture_b + h.tap.i11 + c, w11 * A_B);
+                }
+            }
+            double U_B = h.tap.out0 ? 0.0 : (double)e0_B, V_B = h.tap.out1 ? 0.0 : (double)e1_B;
+            for (int j = 0; j < 3; j++) {
+                Env::atomic_add(acc + 3 + j, L_B * t3[j]);
+                Env::atomic_add(acc + 6 + j, U_B * t3[j]);
+                Env::atomic_add(acc + 9 + j, V_B * t3[j]);
+            }
+        } else {
+            for (int c = 0; c < C; c++) {
+                const double A_B = 2.0 * ((double)h.A[c] - (double)obs[c]) * Err_B;
+                for (int j = 0; j < (compat ? 1 : 3); j++) Env::atomic_add(acc + 12 + 3 * c + j, A_B * t3[j]);
+            }
+        }
+        for (int j = 0; j < 3; j++) Env::atomic_add(acc + j, T_B * t3[j]);
+    }
+}
+
+// colour adjoint of a pixel from the adjoint of its residual (DR.h:3054-3060)
+template <int MAXC>
+DEODR_HD void residual_adjoint(const SceneView &s, const float *col, const float *obs, double g, float *image_b) {
+    for (int c = 0; c < s.nb_colors; c++) image_b[c] = (float)(-2.0 * ((double)obs[c] - (double)col[c]) * g);
+}
+
 // Interior adjoint of one pixel (pixel-parallel kernels): the residual colour adjoint g goes to the vertices of the
 // adjoint owner.  `env.emit(ptr, v)` adds v to a vertex-gradient slot; the device version sums over the warp first when
 // the whole warp shares the owner triangle.  (The device kernels use interior_adjoint_warp of kernels.cu, which sums

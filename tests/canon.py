@@ -58,6 +58,9 @@ class Emulator:
         self.lib.emul_render.argtypes = [C.POINTER(_cabi.SceneView), C.c_double] + [C.c_void_p] * 4
         self.lib.emul_weight_scale.argtypes = [C.POINTER(_cabi.SceneView), C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib.emul_weight_scale.restype = None
+        self.lib.emul_render_error.argtypes = [C.POINTER(_cabi.SceneView), C.c_double] + [C.c_void_p] * 6
+        self.lib.emul_render_error_b.argtypes = [C.POINTER(_cabi.SceneView), C.c_double] + [C.c_void_p] * 5 + [
+            C.POINTER(_cabi.Grads), C.c_int]
         self.lib.emul_render_b.argtypes = [C.POINTER(_cabi.SceneView), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(_cabi.Grads)]
 
@@ -92,5 +95,37 @@ class Emulator:
         gs = _cabi.Grads(*(g[k].ctypes.data for k in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b")))
         rc = self.lib.emul_render_b(C.byref(fwd["_view"]), float(sigma), fwd["z"].ctypes.data, fwd["owner"].ctypes.data,
                                     ib.ctypes.data, C.byref(gs))
+        assert rc == 0
+        return g
+
+    # ---- antialiase_error mode (row f3): phases emulated on the CPU; the CUDA entry points do not offer it yet ----
+    def render_error(self, scene, sigma, obs):
+        a = canonical_arrays(scene)
+        v = view_of(scene, a)
+        H, W, Cc = scene.height, scene.width, scene.nb_colors
+        out = {
+            "image": np.zeros((H, W, Cc), np.float32), "z": np.zeros((H, W)), "owner": np.zeros((H, W), np.int32),
+            "face_id": np.zeros((H, W), np.int32), "err": np.zeros((H, W), np.float32),
+            "obs": np.ascontiguousarray(obs, dtype=np.float32),
+        }
+        rc = self.lib.emul_render_error(C.byref(v), float(sigma), out["obs"].ctypes.data, out["image"].ctypes.data,
+                                        out["z"].ctypes.data, out["owner"].ctypes.data, out["face_id"].ctypes.data,
+                                        out["err"].ctypes.data)
+        assert rc == 0
+        out["_arrays"], out["_view"] = a, v
+        return out
+
+    def render_error_b(self, scene, sigma, fwd, err_b, compat=True):
+        a = fwd["_arrays"]
+        eb = np.ascontiguousarray(err_b, dtype=np.float32)
+        g = {
+            "ij_b": np.zeros(a["ij"].shape, np.float32), "colors_b": np.zeros(a["colors"].shape, np.float32),
+            "uv_b": np.zeros(a["uv"].shape, np.float32), "shade_b": np.zeros(a["shade"].shape, np.float32),
+            "texture_b": np.zeros(a["texture"].shape, np.float32),
+        }
+        gs = _cabi.Grads(*(g[k].ctypes.data for k in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b")))
+        rc = self.lib.emul_render_error_b(C.byref(fwd["_view"]), float(sigma), fwd["z"].ctypes.data,
+                                          fwd["owner"].ctypes.data, fwd["image"].ctypes.data, fwd["obs"].ctypes.data,
+                                          eb.ctypes.data, C.byref(gs), int(bool(compat)))
         assert rc == 0
         return g

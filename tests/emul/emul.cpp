@@ -51,7 +51,7 @@ static void decode_owner(int code, const EmulState &st, int *own, int *bown) {
 // k_tile_z + k_shade<MAXC> + k_edge_fwd<MAXC>
 template <int MAXC>
 static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *image, double *z_buffer, int *owner,
-                       int *face_id) {
+                       int *face_id, const float *obs = nullptr, float *err = nullptr) {
     TileShared *sh = new TileShared;
     memset(sh, 0, sizeof(TileShared));
     // ---- k_tile_z
@@ -105,6 +105,10 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
             phase_shade<MAXC>(s, x, y, &p);
             for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
         }
+    // ---- antialiase_error mode: residual of every pixel, which the edges then overdraw instead of the colours
+    if (err)
+        for (size_t idx = 0; idx < (size_t)s.height * s.width; idx++)
+            err[idx] = (float)pixel_residual<MAXC>(s, image + idx * s.nb_colors, obs + idx * s.nb_colors);
     // ---- k_edge_fwd
     std::vector<PixelState<MAXC>> px(NT);
     for (int tile_id = 0; tile_id < st.nt && st.E > 0; tile_id++) {
@@ -124,11 +128,15 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
             for (int tid = 0; tid < NT; tid++)
                 phase_edge_setup(tid, NT, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
             for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, NT, m, tile, 0, TS, sh);
-            for (int tid = 0; tid < NT; tid++)
-                if (inside(tid))
-                    phase_edge_blend<MAXC>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, tid / TS, m, sh, &px[tid]);
+            for (int tid = 0; tid < NT; tid++) {
+                if (!inside(tid)) continue;
+                const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+                const size_t idx = (size_t)y * s.width + x;
+                if (err) phase_edge_blend_error<MAXC>(s, x, y, tid / TS, m, sh, px[tid].z, obs + idx * s.nb_colors, err + idx);
+                else phase_edge_blend<MAXC>(s, x, y, tid / TS, m, sh, &px[tid]);
+            }
         }
-        for (int tid = 0; tid < NT; tid++) {
+        for (int tid = 0; tid < NT && !err; tid++) {
             if (!inside(tid)) continue;
             const size_t idx = (size_t)(tile.y0 + tid / TS) * s.width + tile.x0 + tid % TS;
             for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = px[tid].col[k];
@@ -139,9 +147,11 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
 
 template <int MAXC>
 static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const double *z_buffer, const int *owner,
-                       const float *image_b, const DeodrGrads &g, double *edge_acc) {
+                       const float *image_b, const DeodrGrads &g, double *edge_acc, const float *obs = nullptr,
+                       const float *err_b = nullptr, bool compat = true) {
     std::vector<PixelState<MAXC>> px(NT);
     std::vector<AdjointState<MAXC>> adj(NT);
+    std::vector<ErrorAdjointState<MAXC>> eadj(NT);  // antialiase_error mode (obs != nullptr)
     TileShared *sh = new TileShared;
     for (int tile_id = 0; tile_id < st.nt; tile_id++) {
         const Tile tile = tile_of(tile_id, st.tiles_x);
@@ -159,6 +169,8 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
             if (code <= -2) { p.own = st.tie_pairs[2 * (-2 - code)]; p.bown = st.tie_pairs[2 * (-2 - code) + 1]; }
             else p.own = p.bown = code;
             for (int k = 0; k < s.nb_colors; k++) a.g[k] = image_b[idx * s.nb_colors + k];
+            eadj[tid].has = false;
+            eadj[tid].g = err_b ? (double)err_b[idx] : 0.0;
         }
         const int n_edge = st.E > 0 ? st.edge_count[tile_id] : 0;
         if (n_edge > 0) {
@@ -172,6 +184,14 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
                 for (int tid = 0; tid < NT; tid++) {
                     if (!inside(tid)) continue;
                     const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+                    if (obs) {
+                        const float *ob = obs + ((size_t)y * s.width + x) * s.nb_colors;
+                        phase_edge_replay_error<MAXC>(s, x, y, tid / TS, m, sh, px[tid], ob, &eadj[tid]);
+                        if (single && eadj[tid].has)
+                            phase_edge_adjoint_error<MAXC, HostEnv>(s, x, y, tid / TS, m, sh, px[tid], ob, &eadj[tid],
+                                                                    edge_acc, g.texture_b, compat);
+                        continue;
+                    }
                     phase_edge_replay<MAXC>(s, x, y, tid / TS, m, sh, px[tid], &adj[tid]);
                     if (single && adj[tid].has_colour)
                         phase_edge_adjoint<MAXC, HostEnv>(s, x, y, tid / TS, m, sh, px[tid], &adj[tid], edge_acc, g.texture_b);
@@ -185,9 +205,17 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
                         phase_edge_setup(tid, NT, m, st.edge_refs.data() + edge_base + base, st.edge_recs.data(), sh);
                     for (int tid = 0; tid < NT; tid++) phase_edge_spans(s, tid, NT, m, tile, 0, TS, sh);
                     for (int tid = 0; tid < NT; tid++) {
-                        if (!inside(tid) || !adj[tid].has_colour) continue;
-                        phase_edge_adjoint<MAXC, HostEnv>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, tid / TS, m, sh,
-                                                          px[tid], &adj[tid], edge_acc, g.texture_b);
+                        if (!inside(tid)) continue;
+                        const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+                        if (obs) {
+                            if (eadj[tid].has)
+                                phase_edge_adjoint_error<MAXC, HostEnv>(s, x, y, tid / TS, m, sh, px[tid],
+                                                                        obs + ((size_t)y * s.width + x) * s.nb_colors,
+                                                                        &eadj[tid], edge_acc, g.texture_b, compat);
+                            continue;
+                        }
+                        if (!adj[tid].has_colour) continue;
+                        phase_edge_adjoint<MAXC, HostEnv>(s, x, y, tid / TS, m, sh, px[tid], &adj[tid], edge_acc, g.texture_b);
                     }
                 }
             }
@@ -197,6 +225,10 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
         for (int tid = 0; tid < NT; tid++) {
             if (!inside(tid) || px[tid].bown < 0) continue;
             if (n_edge == 0 && (px[tid].bown & SMALL_FLAG)) continue;
+            if (obs && eadj[tid].has) {  // pixel overdrawn by edges: colour adjoint from what is left of the residual's
+                const size_t idx = (size_t)(tile.y0 + tid / TS) * s.width + tile.x0 + tid % TS;
+                residual_adjoint<MAXC>(s, eadj[tid].col, obs + idx * s.nb_colors, eadj[tid].g, adj[tid].g);
+            }
             phase_interior_adjoint<MAXC, HostEnv>(s, tile.x0 + tid % TS, tile.y0 + tid / TS, px[tid], adj[tid].g,
                                                   g.ij_b, g.colors_b, g.uv_b, g.shade_b, g.texture_b, HostEnv());
         }
@@ -283,6 +315,48 @@ int emul_render(const DeodrSceneView *scene, double sigma, float *image, double 
     else if (C <= 3) raster_fwd<3>(s, sigma, st, image, z_buffer, owner, face_id);
     else if (C <= 4) raster_fwd<4>(s, sigma, st, image, z_buffer, owner, face_id);
     else raster_fwd<16>(s, sigma, st, image, z_buffer, owner, face_id);
+    return 0;
+}
+
+// antialiase_error mode: emul_render, then the residual and its overdraw by the edges (image keeps its aliased edges).
+int emul_render_error(const DeodrSceneView *scene, double sigma, const float *obs, float *image, double *z_buffer,
+                      int32_t *owner, int32_t *face_id, float *err) {
+    // the binning / ordering half of emul_render does not depend on the mode: run it with sigma (edge lists are
+    // needed), then redo the raster with the error-mode edge pass
+    if (int rc = emul_render(scene, sigma, image, z_buffer, owner, face_id)) return rc;
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    EmulState &st = g_state;
+    st.tie_pairs.clear();
+    const int C = s.nb_colors;
+    if (C == 1) raster_fwd<1>(s, sigma, st, image, z_buffer, owner, face_id, obs, err);
+    else if (C <= 3) raster_fwd<3>(s, sigma, st, image, z_buffer, owner, face_id, obs, err);
+    else if (C <= 4) raster_fwd<4>(s, sigma, st, image, z_buffer, owner, face_id, obs, err);
+    else raster_fwd<16>(s, sigma, st, image, z_buffer, owner, face_id, obs, err);
+    return 0;
+}
+
+// adjoint of emul_render_error: `image` is its (aliased) output, err_b the adjoint of the residual buffer
+int emul_render_error_b(const DeodrSceneView *scene, double sigma, const double *z_buffer, const int32_t *owner,
+                        const float *image, const float *obs, const float *err_b, const DeodrGrads *grads, int compat) {
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    EmulState &st = g_state;
+    const int C = s.nb_colors;
+    const size_t P = (size_t)s.height * s.width;
+    // colour adjoint of the pixels no edge touches (one elementwise kernel on the device): DR.h:3054-3060
+    std::vector<float> image_b(P * C);
+    for (size_t i = 0; i < P; i++)
+        for (int c = 0; c < C; c++)
+            image_b[i * C + c] = (float)(-2.0 * ((double)obs[i * C + c] - (double)image[i * C + c]) * (double)err_b[i]);
+    std::vector<double> acc((size_t)std::max(st.E, 1) * edge_acc_stride(C), 0.0);
+    if (C == 1) raster_bwd<1>(s, sigma, st, z_buffer, owner, image_b.data(), *grads, acc.data(), obs, err_b, compat != 0);
+    else if (C <= 3) raster_bwd<3>(s, sigma, st, z_buffer, owner, image_b.data(), *grads, acc.data(), obs, err_b, compat != 0);
+    else if (C <= 4) raster_bwd<4>(s, sigma, st, z_buffer, owner, image_b.data(), *grads, acc.data(), obs, err_b, compat != 0);
+    else raster_bwd<16>(s, sigma, st, z_buffer, owner, image_b.data(), *grads, acc.data(), obs, err_b, compat != 0);
+    for (int r = 0; r < st.E; r++)
+        finalize_edge<HostEnv>(s, st.edge_sorted[r], sigma, acc.data() + (size_t)r * edge_acc_stride(C), grads->ij_b,
+                               grads->colors_b, grads->uv_b, grads->shade_b);
     return 0;
 }
 

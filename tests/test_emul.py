@@ -108,3 +108,33 @@ def test_exact_z_ties_are_split_like_the_reference(emulator, checker, texture):
         setattr(scene, name, dup(getattr(scene, name)))
     fwd = check(emulator, checker, scene, 1.0)
     assert fwd["ties"] > 0
+
+
+def test_emulated_antialiase_error_mode(emulator, checker, texture):
+    """Row f3 ahead of its kernels: the error-mode phases (edges overdraw the squared residual against `obs`) emulated on
+    the CPU against the oracle - forward image / z-buffer / err_buffer, adjoint with the reference's defect #2 kept
+    (compat) - on soups with textured and interpolated triangles, a mesh and a micro-triangle pile."""
+    rng = np.random.default_rng(3)
+    np.random.seed(2)
+    scenes = [(soup_scene(clockwise=False, texture=texture), 1.0),
+              (soup_scene(n_tri=150, width=40, height=36, texture=texture[::4, ::4].copy(), min_det=100), 1.5),
+              (torus_scene(24, 160, 120), 1.0), (torus_scene(20, 90, 80, textured=True, texture_size=32), 2.0),
+              (confetti_scene(800, 48, 40, size=2.0, seed=4, edge_ratio=0.2), 1.0)]
+    for scene, sigma in scenes:
+        if scene.textured.any():
+            scene.uv = scene.uv * 0.9973 + 0.0131  # keep the texture coordinates off the texel grid
+        obs = rng.random((scene.height, scene.width, scene.nb_colors)).astype(np.float32).astype(np.float64)
+        image, z, err = checker.render(scene, sigma, antialiase_error=True, obs=obs)
+        fwd = emulator.render_error(scene, sigma, obs)
+        assert np.array_equal(fwd["z"], z)
+        assert np.abs(fwd["image"] - image).max() <= IMAGE_TOL
+        assert np.abs(fwd["err"] - err).max() <= 2e-6 * max(1.0, err.max())
+        err_b = rng.random((scene.height, scene.width)) * 2 - 1
+        ref = checker.render_b(scene, sigma, image, z, None, antialiase_error=True, obs=obs, err_buffer=err,
+                               err_buffer_b=err_b)
+        got = emulator.render_error_b(scene, sigma, fwd, err_b, compat=True)
+        for name in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b"):
+            if ref[name].size == 0:
+                continue
+            tol = 5e-5 * np.abs(ref[name]).max() + 2e-6
+            assert np.abs(got[name] - ref[name]).max() <= tol, (name, np.abs(got[name] - ref[name]).max(), tol)
