@@ -71,6 +71,31 @@ while time.time() - t0 < limit:
     scene.perspective_correct = bool(rng.random() < 0.25)
     sigma = float(rng.choice([0.0, 0.5, 1.0, 2.5]))
     n += 1
+    if rng.random() < 0.2 and not scene.perspective_correct and scene.backface_culling:
+        # antialiase_error mode (row f3): phases emulated on the CPU, reference defect #2 kept
+        obs = rng.random((scene.height, scene.width, scene.nb_colors)).astype(np.float32).astype(np.float64)
+        err_b = rng.random((scene.height, scene.width)) * 2 - 1
+        image, z, err = ora.render(scene, sigma, antialiase_error=True, obs=obs)
+        fwd = emu.render_error(scene, sigma, obs)
+        msg = "" if np.array_equal(fwd["z"], z) else " Z-BUFFER-MISMATCH"
+        e_err = np.abs(fwd["err"] - err).max() / max(1.0, float(np.abs(err).max())) if err.size else 0.0
+        if e_err > 6e-5:
+            msg += f" err_buffer {e_err:.2e}"
+        ref = ora.render_b(scene, sigma, image, z, None, antialiase_error=True, obs=obs, err_buffer=err, err_buffer_b=err_b)
+        got = emu.render_error_b(scene, sigma, fwd, err_b, compat=True)
+        for name in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b"):
+            if ref[name].size == 0:
+                continue
+            m, d = np.abs(ref[name]).max(), np.abs(got[name] - ref[name]).max()
+            if d > 2e-4 * m + 1e-5:
+                if degenerate or (emu.lib.emul_num_ties() > 0 and scene.textured.any()):
+                    special += 1
+                    break
+                msg += f" (error mode) {name} {d:.2e}/{m:.2e}"
+        if msg:
+            bad += 1
+            print("FAIL scene", n, "kind", kind, (W, H), "T", scene.faces.shape[0], "sigma", sigma, "error mode", msg, flush=True)
+        continue
     image, z = ora.render(scene, sigma)
     fwd = emu.render(scene, sigma)
     if fwd["ties"] > 0 and scene.textured.any():
