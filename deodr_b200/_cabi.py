@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DEODR_B200_LIB selects an alternative build of the same library (A/B experiments on one GPU box)
 LIB_PATH = os.environ.get("DEODR_B200_LIB") or os.path.join(_HERE, "libdeodr_b200.so")
 
-OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, 1, 2, 3, 4
+OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM, EREPLAN = 0, 1, 2, 3, 4, 5
+ANTIALIASE_ERROR, ERROR_ADJOINT_COMPLETE = 1, 2  # flags of the *_views entry points
 
 
 class SceneView(C.Structure):
@@ -59,6 +60,51 @@ class Grads(C.Structure):
         ("uv_b", C.c_void_p),
         ("shade_b", C.c_void_p),
         ("texture_b", C.c_void_p),
+    ]
+
+
+class ViewIO(C.Structure):
+    """``DeodrViewIO``: per-view device framebuffers of the batched entry points."""
+
+    _fields_ = [
+        ("image", C.c_void_p),
+        ("z_buffer", C.c_void_p),
+        ("owner", C.c_void_p),
+        ("face_id", C.c_void_p),
+        ("barycentric", C.c_void_p),
+        ("obs", C.c_void_p),
+        ("err_buffer", C.c_void_p),
+        ("image_b", C.c_void_p),
+        ("err_buffer_b", C.c_void_p),
+    ]
+
+
+class Camera(C.Structure):
+    """``DeodrCamera``: extrinsic [3,4], intrinsic [3,3] (row-major), distortion k1 k2 p1 p2 k3."""
+
+    _fields_ = [
+        ("extrinsic", C.c_double * 12),
+        ("intrinsic", C.c_double * 9),
+        ("distortion", C.c_double * 5),
+        ("has_distortion", C.c_int32),
+        ("pad", C.c_int32),
+    ]
+
+
+class MeshTopology(C.Structure):
+    """``DeodrMeshTopology``: static adjacency of a triangulated mesh (device pointers)."""
+
+    _fields_ = [
+        ("faces", C.c_void_p),
+        ("faces_edges", C.c_void_p),
+        ("edge_face_offset", C.c_void_p),
+        ("edge_face_index", C.c_void_p),
+        ("vertex_face_offset", C.c_void_p),
+        ("vertex_face_index", C.c_void_p),
+        ("nb_faces", C.c_int32),
+        ("nb_edges", C.c_int32),
+        ("nb_vertices", C.c_int32),
+        ("clockwise", C.c_int32),
     ]
 
 
@@ -110,6 +156,28 @@ SYMBOLS = [
      [C.c_void_p, C.POINTER(SceneView), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("deodr_b200_render_b", C.c_int,
      [C.c_void_p, C.POINTER(SceneView), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p]),
+    ("deodr_b200_render_views", C.c_int,
+     [C.c_void_p, C.c_int, C.POINTER(SceneView), C.POINTER(ViewIO), C.c_double, C.c_int, C.c_void_p]),
+    ("deodr_b200_render_b_views", C.c_int,
+     [C.c_void_p, C.c_int, C.POINTER(SceneView), C.POINTER(ViewIO), C.POINTER(Grads), C.c_double, C.c_int, C.c_void_p]),
+    ("deodr_b200_workspace_set_deferred", C.c_int, [C.c_void_p, C.c_int]),
+    ("deodr_b200_workspace_status", C.c_int, [C.c_void_p]),
+    ("deodr_b200_view_generation", C.c_int64, [C.c_void_p, C.c_int]),
+    ("deodr_b200_project_points", C.c_int,
+     [C.c_void_p, C.c_int, C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("deodr_b200_project_points_b", C.c_int,
+     [C.c_void_p, C.c_int, C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("deodr_b200_vertex_luminosity", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("deodr_b200_vertex_luminosity_b", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+      C.c_void_p, C.c_void_p]),
+    ("deodr_b200_edge_on_silhouette", C.c_int,
+     [C.POINTER(MeshTopology), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("deodr_b200_vertex_normals", C.c_int,
+     [C.POINTER(MeshTopology), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("deodr_b200_vertex_normals_b", C.c_int,
+     [C.POINTER(MeshTopology), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("deodr_b200_render_host", C.c_int,
      [C.c_void_p, C.POINTER(HostScene), C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     ("deodr_b200_render_b_host", C.c_int,

@@ -100,6 +100,8 @@ struct HostPath {
     DeodrHostScene meta;  // scalar fields of the last staged scene (pointers unused)
     double sigma = -1;
     bool valid = false;   // mirror + device state describe a completed forward pass
+    int64_t generation = 0;  // stamp of that pass in slot 0 (another forward on the same workspace invalidates the cache)
+    int flags = 0;        // mode (antialiase_error) of that pass
     DeodrSceneView view;  // device view of the staged scene
     cudaStream_t stream = nullptr;
     cudaEvent_t chunk_event[MAX_EVENTS];
@@ -318,19 +320,48 @@ static int stage_scene(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *h
     return DEODR_B200_OK;
 }
 
-// stage + forward into the workspace's device framebuffers; on success the forward state is cached
-static int host_forward(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *h, double sigma) {
+// stage + forward into the workspace's device framebuffers; on success the forward state is cached.
+// antialiase_error mode: `obs` (host, fp64) is uploaded as fp32 and the residual buffer is produced next to the image.
+static int upload_f32(DeodrWorkspace *ws, HostPath *hp, DevBuf *dev, const double *user, size_t count, char *pin) {
+    if (dev->ensure(count * sizeof(float) + 16, &ws->bytes)) return DEODR_B200_ECUDA;
+    Batch b;
+    b.width = WIDTH_PCIE_BOUND;
+    std::vector<UploadPiece> pieces;
+    add_upload(&b, &pieces, OP_F64_TO_F32, pin, user, dev->ptr, count);
+    b.open_all();
+    hp->crew.start(&b);
+    const int sent = send_uploads(&b, pieces, hp->stream);
+    hp->crew.finish(&b);
+    return sent;
+}
+
+static int host_forward(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *h, double sigma, int flags,
+                        const double *obs) {
     if (int rc = stage_scene(ws, hp, h, sigma)) return rc;
     const size_t P = (size_t)h->height * h->width, C = h->nb_colors;
     int rc = 0;
     rc |= ws->h_image.ensure(P * C * sizeof(float), &ws->bytes);
     rc |= ws->h_z.ensure(P * sizeof(double), &ws->bytes);
     rc |= ws->h_owner.ensure(P * sizeof(int), &ws->bytes);
+    if (flags & DEODR_B200_ANTIALIASE_ERROR) rc |= ws->h_err.ensure(P * sizeof(float), &ws->bytes);
     if (rc) return DEODR_B200_ECUDA;
-    rc = deodr_render_impl(ws, &hp->view, sigma, ws->h_image.as<float>(), ws->h_z.as<double>(), ws->h_owner.as<int>(),
-                           nullptr, hp->stream, /*check_indices=*/true);
+    DeodrViewIO io;
+    memset(&io, 0, sizeof(io));
+    io.image = ws->h_image.as<float>();
+    io.z_buffer = ws->h_z.as<double>();
+    io.owner = ws->h_owner.as<int>();
+    if (flags & DEODR_B200_ANTIALIASE_ERROR) {
+        if (int rc2 = hp->staging.ensure(P * C * 4 + P * 8 + 512)) return rc2;
+        if (int rc2 = upload_f32(ws, hp, &ws->h_obs, obs, P * C, (char *)hp->staging.ptr)) return rc2;
+        CUDA_TRY(cudaStreamSynchronize(hp->stream));  // the staging buffer is reused by the downloads
+        io.obs = ws->h_obs.as<float>();
+        io.err_buffer = ws->h_err.as<float>();
+    }
+    rc = deodr_render_checked(ws, &hp->view, &io, sigma, flags & DEODR_B200_ANTIALIASE_ERROR, hp->stream);
     if (rc) return rc;
     hp->valid = true;
+    hp->generation = deodr_b200_view_generation(ws, 0);
+    hp->flags = flags & DEODR_B200_ANTIALIASE_ERROR;
     return DEODR_B200_OK;
 }
 
@@ -392,28 +423,31 @@ int deodr_b200_host_zero(DeodrWorkspace *ws, void *const *ptrs, const int64_t *b
 
 int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, double *image, double *z_buffer,
                            double sigma, int antialiase_error, const double *obs, double *err_buffer) {
-    (void)obs; (void)err_buffer;
     if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
-    if (antialiase_error)
-        return set_error(DEODR_B200_EUNSUPPORTED, "antialiase_error mode is not implemented by deodr_b200 yet");
     if (int rc = check_host_pointers(scene, false)) return rc;
     if (!image) return set_error(DEODR_B200_EINVAL, "image_ptr is NULL");
     if (!z_buffer) return set_error(DEODR_B200_EINVAL, "z_buffer_ptr is NULL");
+    if (antialiase_error && !obs) return set_error(DEODR_B200_EINVAL, "obs_ptr is NULL");
+    if (antialiase_error && !err_buffer) return set_error(DEODR_B200_EINVAL, "err_buffer_ptr is NULL");
     CUDA_TRY(cudaSetDevice(ws->device));
     HostPath *hp;
     HostTrace trace("render_host");
     if (int rc = host_path(ws, &hp)) return rc;
-    if (int rc = host_forward(ws, hp, scene, sigma)) return rc;
+    const int flags = antialiase_error ? DEODR_B200_ANTIALIASE_ERROR : 0;
+    if (int rc = host_forward(ws, hp, scene, sigma, flags, obs)) return rc;
     trace.lap("stage + forward (enqueued)");
     const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
-    if (int rc = hp->staging.ensure(P * C * 4 + P * 8 + 512)) return rc;
+    if (int rc = hp->staging.ensure(P * C * 4 + P * 8 + P * 4 + 1024)) return rc;
     char *stage_image = (char *)hp->staging.ptr, *stage_z = stage_image + ((P * C * 4 + 255) & ~(size_t)255);
+    char *stage_err = stage_z + ((P * 8 + 255) & ~(size_t)255);
     // every DMA is queued (in stream order behind the kernels) before the first chunk is consumed
     DownloadSet d;
     d.batch.width = WIDTH_PCIE_BOUND;
-    d.size_for(P * C * 4 + P * 8, 2);  // the event pool bounds the number of chunks: huge framebuffers, larger chunks
+    d.size_for(P * C * 4 + P * 8 + (antialiase_error ? P * 4 : 0), 3);  // the event pool bounds the number of chunks
     if (int rc = add_download(hp, &d, OP_F32_TO_F64, ws->h_image.ptr, stage_image, image, P * C, hp->stream)) return rc;
     if (int rc = add_download(hp, &d, OP_COPY, ws->h_z.ptr, stage_z, z_buffer, P * 8, hp->stream)) return rc;
+    if (antialiase_error)
+        if (int rc = add_download(hp, &d, OP_F32_TO_F64, ws->h_err.ptr, stage_err, err_buffer, P, hp->stream)) return rc;
     if (int rc = run_downloads(hp, &d)) return rc;
     trace.lap("image + z DMA, fp32->fp64");
     return DEODR_B200_OK;
@@ -422,39 +456,56 @@ int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, doub
 int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, double *image, double *z_buffer,
                              double *image_b, double sigma, int antialiase_error, const double *obs,
                              double *err_buffer, double *err_buffer_b) {
-    (void)obs; (void)err_buffer; (void)err_buffer_b; (void)image; (void)z_buffer;
+    // image / z_buffer / err_buffer (the forward's outputs, which the reference un-blends in place) are not read: the
+    // device keeps its own copies and the adjoint replays the blends in fp64
+    (void)err_buffer; (void)image; (void)z_buffer;
     if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
-    if (antialiase_error)
-        return set_error(DEODR_B200_EUNSUPPORTED, "antialiase_error mode is not implemented by deodr_b200 yet");
     if (int rc = check_host_pointers(scene, true)) return rc;
     if (!scene->backface_culling)
         return set_error(DEODR_B200_EUNSUPPORTED, "You have to use backface_culling true if you ant to compute gradients");
     if (scene->perspective_correct)
         return set_error(DEODR_B200_EUNSUPPORTED,
                          "backward gradient propagation not supported yet with perspective_correct=True");
-    if (!image_b) return set_error(DEODR_B200_EINVAL, "image_b_ptr is NULL");
+    if (antialiase_error) {
+        if (!err_buffer_b) return set_error(DEODR_B200_EINVAL, "err_buffer_b_ptr is NULL");
+        if (!obs) return set_error(DEODR_B200_EINVAL, "obs_ptr is NULL");
+    } else if (!image_b) {
+        return set_error(DEODR_B200_EINVAL, "image_b_ptr is NULL");
+    }
     CUDA_TRY(cudaSetDevice(ws->device));
     HostPath *hp;
     HostTrace trace("render_b_host");
     if (int rc = host_path(ws, &hp)) return rc;
     cudaStream_t st = hp->stream;
+    const int flags = antialiase_error ? DEODR_B200_ANTIALIASE_ERROR : 0;
     const size_t P = (size_t)scene->height * scene->width, C = scene->nb_colors;
     const size_t V = scene->nb_vertices, U = scene->nb_uv;
     const size_t tex = (size_t)scene->texture_height * scene->texture_width * C;
     const size_t n_ij = 2 * V, n_col = V * C, n_uv = 2 * U, n_sh = V, n_grad = n_ij + n_col + n_uv + n_sh + tex;
-    if (int rc = hp->staging.ensure(std::max(P * C * 4, n_grad * 4) + 512)) return rc;
+    if (int rc = hp->staging.ensure(std::max(P * C * 4 + P * 4, n_grad * 4) + 1024)) return rc;
 
-    // image_b: fp64 -> fp32 into pinned staging in chunks, each chunk DMA'd while the next is converted
+    // the pixel adjoint (image_b, or err_buffer_b + obs in antialiase_error mode): fp64 -> fp32 into pinned staging in
+    // chunks, each chunk DMA'd while the next is converted
     if (ws->h_image_b.ensure(P * C * sizeof(float), &ws->bytes)) return DEODR_B200_ECUDA;
-    // forward state: reuse the cached one iff the caller's scene is bit-identical to the last forward's.  The
-    // comparison (host memory only) shares a batch with the image_b conversion, whose chunks go first so that their
-    // DMAs are in flight while the workers compare.
+    if (antialiase_error) {
+        if (ws->h_err_b.ensure(P * sizeof(float), &ws->bytes)) return DEODR_B200_ECUDA;
+        if (ws->h_obs.ensure(P * C * sizeof(float) + 16, &ws->bytes)) return DEODR_B200_ECUDA;
+    }
+    // forward state: reuse the cached one iff the caller's scene is bit-identical to the last forward's AND no other
+    // forward has used the workspace since.  The comparison (host memory only) shares a batch with the conversions,
+    // whose chunks go first so that their DMAs are in flight while the workers compare.
     bool same;
     {
         Batch b;
         std::vector<UploadPiece> pieces;
-        add_upload(&b, &pieces, OP_F64_TO_F32, (char *)hp->staging.ptr, image_b, ws->h_image_b.ptr, P * C);
-        same = add_mirror_compare(hp, scene, sigma, &b);
+        if (antialiase_error) {
+            add_upload(&b, &pieces, OP_F64_TO_F32, (char *)hp->staging.ptr, obs, ws->h_obs.ptr, P * C);
+            add_upload(&b, &pieces, OP_F64_TO_F32, (char *)hp->staging.ptr + P * C * 4, err_buffer_b, ws->h_err_b.ptr, P);
+        } else {
+            add_upload(&b, &pieces, OP_F64_TO_F32, (char *)hp->staging.ptr, image_b, ws->h_image_b.ptr, P * C);
+        }
+        same = hp->generation == deodr_b200_view_generation(ws, 0) && hp->flags == flags &&
+               add_mirror_compare(hp, scene, sigma, &b);
         b.open_all();
         hp->crew.start(&b);
         const int sent = send_uploads(&b, pieces, st);
@@ -464,7 +515,8 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
     }
     trace.lap("image_b upload + mirror check");
     if (!same) {
-        if (int rc = host_forward(ws, hp, scene, sigma)) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));  // staging is reused by the re-forward's uploads
+        if (int rc = host_forward(ws, hp, scene, sigma, flags, obs)) return rc;
         trace.lap("scene changed: re-forward");
     }
     if (ws->h_grads.ensure(n_grad * sizeof(float), &ws->bytes)) return DEODR_B200_ECUDA;
@@ -475,8 +527,21 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
     g.uv_b = g.colors_b + n_col;
     g.shade_b = g.uv_b + n_uv;
     g.texture_b = g.shade_b + n_sh;
-    if (int rc = deodr_b200_render_b(ws, &hp->view, sigma, ws->h_z.as<double>(), ws->h_owner.as<int>(),
-                                     ws->h_image_b.as<float>(), &g, st))
+    DeodrViewIO io;
+    memset(&io, 0, sizeof(io));
+    io.image = ws->h_image.as<float>();
+    io.z_buffer = ws->h_z.as<double>();
+    io.owner = ws->h_owner.as<int>();
+    io.image_b = ws->h_image_b.as<float>();
+    if (antialiase_error) {
+        io.obs = ws->h_obs.as<float>();
+        io.err_buffer = ws->h_err.as<float>();
+        io.err_buffer_b = ws->h_err_b.as<float>();
+    }
+    // (the reference's mode is bug-compatible by default; DEODR_B200_ERROR_ADJOINT=complete selects the full adjoint)
+    static const bool complete = getenv("DEODR_B200_ERROR_ADJOINT") && !strcmp(getenv("DEODR_B200_ERROR_ADJOINT"), "complete");
+    if (int rc = deodr_b200_render_b_views(ws, 1, &hp->view, &io, &g, sigma,
+                                           flags | (complete ? DEODR_B200_ERROR_ADJOINT_COMPLETE : 0), st))
         return rc;
     // gradients are ACCUMULATED into scene.*_b (DR.h:3019-3049, 3126-3128)
     CUDA_TRY(cudaStreamSynchronize(st));  // staging is reused: image_b DMA must have completed

@@ -1,21 +1,26 @@
-// deodr_b200: sm_100a kernels + C-ABI (include/deodr_b200.h) of the differentiable rasteriser.
+// deodr_b200: sm_100a kernels + device-level C-ABI (include/deodr_b200.h) of the differentiable rasteriser.
 //
-// Pipeline of one forward pass (all on the caller's stream):
-//   bin_tri(count) -> scan -> bin_tri(fill)                       per-tile triangle lists (unordered: the z test is
-//                                                                  order independent, see phase_tri_test)
-//   select silhouette edges -> depth keys -> stable radix sort    far-to-near order of DR.h:2781 (CUB)
-//   bin_edge(count) -> scan -> bin_edge(fill) -> sort_tile_edges  per-tile edge lists in far-to-near order
-//   raster_fwd                                                    one CTA per 16x16 tile: z-buffer, owner ids, colour,
-//                                                                  ordered edge overdraw, single framebuffer write
-// and of one backward pass:
-//   raster_bwd                                                    per tile: edge replay + reverse sweep, interior
-//                                                                  adjoint scattered to the vertices
-//   finalize_edges                                                per edge: plane adjoints -> vertex adjoints
+// One forward pass of one view, nothing in it waits for the host:
+//   memset                                       scalars + segment cursors of the view's slot
+//   k_bin            1 thread / triangle         ONE gather per triangle: classify (DR.h:2751-2779), append silhouette
+//                                                edges, pre-masked 64-byte records of the small triangles / tile
+//                                                references of the large ones, into segments reserved by the PLAN
+//   k_bin_edges      1 thread / edge      (aux)  band stencil record (DR.h:1366-1460), slot -> tiles of the band
+//   k_sort_tile_edges 1 CTA / tile        (aux)  far-to-near order (DR.h:2781) inside every tile, list of edge tiles
+//   k_publish                             (aux)  verdict word + counts -> pinned host memory (read by the host AFTER
+//                                                the whole pass has been enqueued)
+//   k_tile_z         1 CTA / 16x16 tile          TMA bulk copy of the tile's records, exact z test, owner ids
+//   k_shade          1 thread / pixel            colour of the owner (+ residual / G-buffer weights)
+//   k_edge_fwd       1 CTA / edge tile           ordered silhouette-edge overdraw (DR.h:2839-2899)
+// and one adjoint pass:
+//   k_raster_bwd + k_finalize_edges       (aux)  edge tiles: replay, reverse sweep, per-edge plane adjoints
+//   k_interior_bwd                        (aux)  pixels of large triangles elsewhere
+//   k_small_tri_bwd                              triangle-parallel adjoint of the small triangles
+// The plan (segment capacities) comes from a count-only pass (k_bin<true> + k_scan_tiles) run once per shape and
+// again whenever a pass reports that a list outgrew it.
 //
 // There is no CPU fallback: every entry point fails with DEODR_B200_ECUDA if no device is usable.
 #include <cuda_runtime.h>
-
-#include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
 #include <cstdlib>
@@ -25,127 +30,43 @@
 #include <new>
 #include <vector>
 
-#include "../../include/deodr_b200.h"
-#include "phases.h"
-#include "workspace.h"
-
-using namespace deodr;
-
-// ------------------------------------------------------------------------------------------------ device Env
-
-struct DevEnv {
-    static __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
-    static __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
-    static __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
-    static __device__ __forceinline__ int shared_inc(int *p) { return atomicAdd(p, 1); }  // p in shared memory
-};
-
-// Interior adjoint of one pixel per lane with a warp-level reduce-by-owner before the scatter: the lanes of a warp that
-// share the adjoint owner (neighbouring pixels of a large triangle) first sum their vertex gradients with a tree of
-// shuffles over the group (__match_any_sync gives the groups), then ONE lane per group issues the atomics.  Measured on
-// the 1M-triangle scene: float-atomic throughput was 38 of k_interior_bwd's 67 us.  Must be called by all 32 lanes.
-template <int MAXC>
-static __device__ __forceinline__ void interior_adjoint_warp(const SceneView &s, int x, int y, bool has,
-                                                             const PixelState<MAXC> &p, const float *g,
-                                                             const DeodrGrads &grads) {
-    const int lane = (int)(threadIdx.x & 31), C = s.nb_colors;
-    TriAttr t;
-    VertexGrads<MAXC> acc;
-    zero_vertex_grads<MAXC>(s, &acc);
-    t.textured = false;
-    if (has) {
-        tri_attr(s, p.bown & TRI_INDEX_MASK, &t);
-        pixel_adjoint<MAXC, DevEnv>(s, t, x, y, g, &acc, grads.texture_b);
-    }
-    const int key = has ? (p.bown & TRI_INDEX_MASK) : -1 - lane;  // idle lanes: groups of one
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const int rank = __popc(peers & ((1u << lane) - 1u)), size = __popc(peers);
-    const int max_size = __reduce_max_sync(0xffffffffu, size);
-    const bool any_textured = __any_sync(0xffffffffu, has && t.textured);
-    const bool any_plain = __any_sync(0xffffffffu, has && !t.textured);
-    for (int stride = 1; stride < max_size; stride <<= 1) {
-        // tree over the members of a group: member `rank` (a multiple of 2*stride) takes member rank + stride
-        const bool take = (rank & (2 * stride - 1)) == 0 && rank + stride < size;
-        const int src = take ? (int)__fns(peers, 0, rank + stride + 1) : lane;
-#define DEODR_TAKE(field)                                                  \
-        {                                                                      \
-            const float other = __shfl_sync(0xffffffffu, (field), src);        \
-            if (take) (field) += other;                                        \
-        }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            DEODR_TAKE(acc.ij[i][0]);
-            DEODR_TAKE(acc.ij[i][1]);
-        }
-        if (any_textured) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                DEODR_TAKE(acc.uv[i][0]);
-                DEODR_TAKE(acc.uv[i][1]);
-                DEODR_TAKE(acc.shade[i]);
-            }
-        }
-        if (any_plain) {
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int c = 0; c < MAXC; c++)
-                    if (c < C) DEODR_TAKE(acc.attr[i][c]);
-        }
-#undef DEODR_TAKE
-    }
-    if (has && rank == 0)
-        flush_vertex_grads<MAXC, AtomicEmit<DevEnv>>(s, t, acc, grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b,
-                                                     AtomicEmit<DevEnv>());
-}
-
-// The <1> and <3> instances are only launched for exactly 1 / 3 colour channels: telling the compiler turns every
-// `for (c < nb_colors)` loop of the inlined shading code into straight-line code (the <4> and <16> instances keep the
-// run-time channel count: 2 or 4, 5..16).
-template <int MAXC, bool TEX = true>
-static __device__ __forceinline__ void fix_channel_count(SceneView &s) {
-    if (MAXC == 1 || MAXC == 3) s.nb_colors = MAXC;
-    // TEX = false instances are launched for scenes without a textured triangle (flag raised by k_bin_count): nulling
-    // the texture pointer of the kernel's copy of the scene folds every texture branch (tri_attr / edge_hit test it)
-    if (!TEX) s.texture = nullptr;
-}
-
-static_assert(sizeof(SceneView) == sizeof(DeodrSceneView), "SceneView must mirror DeodrSceneView");
+#include "kernels_common.cuh"
 
 // ------------------------------------------------------------------------------------------------- kernels
 
-// Count pass: one thread per triangle (small / large tile counts, silhouette-edge append, edge tile counts).
-__global__ void k_bin_count(SceneView s, double sigma, int tiles_x, TriBins bins, TriLists lists, EdgeList edges,
-                            int *edge_tile_count, const int *bad_indices, int *any_textured) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+// The binning pass (COUNT_ONLY = false) / the count pass that builds a plan (COUNT_ONLY = true): one thread per triangle.
+#ifndef DEODR_BIN_MIN_CTAS
+#define DEODR_BIN_MIN_CTAS 6
+#endif
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(128, DEODR_BIN_MIN_CTAS) k_bin(SceneView s, double sigma, int tiles_x, TriBins bins,
+                                                                int *scal, int *small_ids, EdgeList edges,
+                                                                int *edge_tile_count, int plan_tex) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.nb_triangles) return;
-    if (bad_indices && *bad_indices) return;  // out-of-range face indices found by k_check_scene: touch nothing
-    // does the scene hold ANY textured triangle?  (read back with the list sizes: scenes without one run kernel
-    // instances compiled without the texture paths - fewer registers, no local memory)
-    if (s.textured[k] && s.shaded[k] && *(volatile int *)any_textured == 0) atomicOr(any_textured, 1);
-    bin_count_triangle<DevEnv>(s, k, sigma, tiles_x, bins, lists, edges, edge_tile_count);
+    if (scal[SC_BAD_INDEX]) return;  // out-of-range face indices found by k_check_scene: touch nothing
+    // does the scene hold ANY textured triangle?  Scenes without one run kernel instances compiled without the
+    // texture paths (fewer registers, no local memory); the plan remembers the answer of the pass it was built from
+    if (s.textured[k] && s.shaded[k]) {
+        if (*(volatile int *)(scal + SC_TEXTURED) == 0) atomicOr(scal + SC_TEXTURED, 1);
+        if (!COUNT_ONLY && !plan_tex && (*(volatile int *)(scal + SC_OVERFLOW) & OVF_TEXTURE) == 0)
+            atomicOr(scal + SC_OVERFLOW, OVF_TEXTURE);
+    }
+    bin_triangle<DevEnv, COUNT_ONLY>(s, k, sigma, tiles_x, bins, scal + SC_SMALL, small_ids, edges, edge_tile_count);
 }
 
-// Exclusive scans of the tile counts: blockIdx 0 small triangles (records), 1 large triangles, 2 silhouette edges.
-// 1024 threads per CTA, coalesced loads with a one-chunk prefetch; offsets[n] and totals[] receive the grand totals.
+// Plan building: exclusive scans of the per-tile counts of the count pass, each count first padded with slack
+// (c + c/4 + SEG_SLACK) so that the segments survive the drift of an optimisation loop: blockIdx 0 small triangles
+// (records), 1 large triangles (references), 2 silhouette edges (references).  1024 threads per CTA; offsets[n] and
+// scal[] receive the grand totals; the number of non-empty tiles (launch hints) rides in the high word of the scan.
 struct ScanJob {
     const int *count[3];
     int *offset[3];
     int total_slot[3];
-    int *nonempty[3];        // optional: compact list of the tiles with count > 0 (nullptr to skip)
-    int nonempty_slot[3];    // totals[] slot receiving the length of that list
-    // two-ended list (threshold > 0): tiles with count > threshold fill the list from the front, the other non-empty
-    // tiles from the back (position n-1 downwards), so that the kernels that walk it start the crowded tiles first
-    int heavy_threshold[3];
-    int heavy_slot[3];       // totals[] slot receiving the number of crowded tiles
+    int nonempty_slot[3];  // scal[] slot receiving the number of tiles with count > 0 (-1: not wanted)
 };
+constexpr int SEG_SLACK = 4;
 
-// Block b of a kernel that walks a two-ended tile list of capacity n with `heavy` crowded tiles at its front.
-static __device__ __forceinline__ int two_ended_at(const int *list, int n, int heavy, int b) {
-    return b < heavy ? list[b] : list[n - 1 - (b - heavy)];
-}
-
-// One 64-bit scan carries both the running sum of the counts (low word) and the number of non-empty tiles (high word).
 // Each thread owns SCAN_IPT consecutive tiles, so 16384 tiles take ONE block scan instead of sixteen; counts and
 // offsets pass through a padded shared-memory stage so that every global access stays coalesced (the kernel runs on
 // three SMs only: 16 uncoalesced wavefronts per load instruction would be its whole duration).
@@ -153,15 +74,11 @@ constexpr int SCAN_IPT = 16;
 constexpr int SCAN_TILE = 1024 * SCAN_IPT;
 constexpr int SCAN_SMEM = (SCAN_TILE + SCAN_TILE / 32) * (int)sizeof(int);
 static __device__ __forceinline__ int scan_slot(int i) { return i + (i >> 5); }  // conflict-free for stride-16 readers
-__global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *totals, int *host_totals, int seq) {
+__global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *scal, int *host_totals, int seq) {
     extern __shared__ int stage[];
     __shared__ unsigned long long warp_sums[32];
-    __shared__ int heavy_sums[32];
-    const int threshold = job.heavy_threshold[blockIdx.x];
-    int heavy_carry = 0;
     const int *count = job.count[blockIdx.x];
     int *offset = job.offset[blockIdx.x];
-    int *nonempty = job.nonempty[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long carry = 0;
     for (int base = 0; base < n; base += SCAN_TILE) {
@@ -170,59 +87,44 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
             // its own: interleaved they would cost sixteen serial memory round trips)
             int in[SCAN_IPT];
 #pragma unroll
-            for (int k = 0; k < SCAN_IPT; k++) in[k] = base + k * 1024 + tid < n ? __ldg(count + base + k * 1024 + tid) : 0;
+            for (int k = 0; k < SCAN_IPT; k++) in[k] = base + k * 1024 + tid < n ? __ldg(count + base + k * 1024 + tid) : -1;
 #pragma unroll
             for (int k = 0; k < SCAN_IPT; k++) stage[scan_slot(k * 1024 + tid)] = in[k];
         }
         __syncthreads();
         const int first = tid * SCAN_IPT;
-        int c[SCAN_IPT];
-#pragma unroll
-        for (int k = 0; k < SCAN_IPT; k++) c[k] = stage[scan_slot(first + k)];
+        unsigned long long c[SCAN_IPT];  // low word: padded capacity of the tile, high word: 1 if it is not empty
         unsigned long long v = 0;
 #pragma unroll
-        for (int k = 0; k < SCAN_IPT; k++) v += (unsigned long long)(unsigned)c[k] | ((unsigned long long)(c[k] > 0) << 32);
-        int hv = 0;
-        if (threshold > 0) {
-#pragma unroll
-            for (int k = 0; k < SCAN_IPT; k++) hv += (int)(c[k] > threshold);
+        for (int k = 0; k < SCAN_IPT; k++) {
+            const int raw = stage[scan_slot(first + k)];
+            c[k] = raw < 0 ? 0ull
+                           : (unsigned long long)(unsigned)(raw + (raw >> 2) + SEG_SLACK) | ((unsigned long long)(raw > 0) << 32);
+            v += c[k];
         }
         unsigned long long incl = v;
-        int hincl = hv;
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-            int ht = __shfl_up_sync(0xffffffffu, hincl, o);
-            if (lane >= o) { incl += t; hincl += ht; }
+            if (lane >= o) incl += t;
         }
-        if (lane == 31) { warp_sums[warp] = incl; heavy_sums[warp] = hincl; }
+        if (lane == 31) warp_sums[warp] = incl;
         __syncthreads();
         if (warp == 0) {
             unsigned long long w = warp_sums[lane];
-            int hw = heavy_sums[lane];
             for (int o = 1; o < 32; o <<= 1) {
                 unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
-                int ht = __shfl_up_sync(0xffffffffu, hw, o);
-                if (lane >= o) { w += t; hw += ht; }
+                if (lane >= o) w += t;
             }
             warp_sums[lane] = w;
-            heavy_sums[lane] = hw;
         }
         __syncthreads();
-        int hrun = heavy_carry + (warp ? heavy_sums[warp - 1] : 0) + hincl - hv;
         unsigned long long run = carry + (warp ? warp_sums[warp - 1] : 0ull) + incl - v;
 #pragma unroll
         for (int k = 0; k < SCAN_IPT; k++) {
             stage[scan_slot(first + k)] = (int)(unsigned)run;
-            if (nonempty && c[k] > 0) {
-                const int rank = (int)(run >> 32);  // non-empty tiles before this one
-                if (threshold <= 0) nonempty[rank] = base + first + k;
-                else if (c[k] > threshold) nonempty[hrun++] = base + first + k;
-                else nonempty[n - 1 - (rank - hrun)] = base + first + k;
-            }
-            run += (unsigned long long)(unsigned)c[k] | ((unsigned long long)(c[k] > 0) << 32);
+            run += c[k];
         }
         carry += warp_sums[31];
-        heavy_carry += heavy_sums[31];
         __syncthreads();
         {
             int outv[SCAN_IPT];
@@ -236,97 +138,79 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *to
     }
     if (tid == 0) {
         offset[n] = (int)(unsigned)carry;
-        totals[job.total_slot[blockIdx.x]] = (int)(unsigned)carry;
-        if (nonempty) totals[job.nonempty_slot[blockIdx.x]] = (int)(carry >> 32);
-        if (threshold > 0) totals[job.heavy_slot[blockIdx.x]] = heavy_carry;
-        // The last CTA to finish publishes the sixteen scalars straight into the host's (pinned, device-visible) buffer
-        // and raises a sequence flag the host is polling: no copy engine, no stream synchronisation on the critical path.
+        scal[job.total_slot[blockIdx.x]] = (int)(unsigned)carry;
+        if (job.nonempty_slot[blockIdx.x] >= 0) scal[job.nonempty_slot[blockIdx.x]] = (int)(carry >> 32);
+        // The last CTA to finish publishes the scalars straight into the host's (pinned, device-visible) buffer and
+        // raises a sequence flag the host is polling: no copy engine, no stream synchronisation.
         __threadfence();
-        const int ticket = atomicAdd(&totals[11], 1);
+        const int ticket = atomicAdd(&scal[SC_TICKET], 1);
         if (host_totals && ticket == (int)gridDim.x - 1) {
             __threadfence();
-            for (int i = 0; i < 16; i++) host_totals[i] = ((volatile int *)totals)[i];
+            for (int i = 0; i < SC_WORDS; i++) host_totals[i] = ((volatile int *)scal)[i];
             __threadfence_system();
-            ((volatile int *)host_totals)[16] = seq;
+            ((volatile int *)host_totals)[SC_WORDS] = seq;
         }
     }
 }
 
-// Far-to-near order of the appended silhouette edges by rank counting (DR.h:2781; ties by id).  2-D grid: CTA (bx, by)
-// counts, for its 256 edges i, the edges j of chunk by (256 keys staged in shared memory) that precede them, and adds
-// the partial count to rank[i]; k_scatter_edges then writes edge_sorted[rank[i]] = ids[i].
-constexpr int RANK_CHUNK = 256;  // keys per CTA: E/256 x E/256 CTAs keep the whole chip busy for a few thousand edges
-__global__ void __launch_bounds__(256) k_rank_edges(EdgeList edges, int n, int *rank) {
-    __shared__ unsigned long long sk[RANK_CHUNK];
-    __shared__ uint32_t shi[RANK_CHUNK];
-    __shared__ int si[RANK_CHUNK];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int base = blockIdx.y * RANK_CHUNK, m = min(RANK_CHUNK, n - base);
-    for (int j = threadIdx.x; j < m; j += blockDim.x) {
-        sk[j] = edges.keys[base + j];
-        shi[j] = (uint32_t)(sk[j] >> 32);
-        si[j] = edges.ids[base + j];
-    }
-    __syncthreads();
-    if (i >= n) return;
-    const unsigned long long key = edges.keys[i];
-    const uint32_t key_hi = (uint32_t)(key >> 32);
-    const int id = edges.ids[i];
-    // the high words (sign, exponent, 20 mantissa bits of the depth sum) decide almost every comparison: count them
-    // with 32-bit compares; only when another edge shares the high word (same triangle, nearly equal depth sums, the
-    // edge itself on the diagonal chunks) is the full (key, id) comparison run
-    int partial = 0, equal = 0;
-#pragma unroll 8
-    for (int j = 0; j < m; j++) {
-        partial += (int)(shi[j] < key_hi);
-        equal += (int)(shi[j] == key_hi);
-    }
-    if (equal > 0)
-        for (int j = 0; j < m; j++)
-            if (shi[j] == key_hi) partial += (int)(sk[j] < key || (sk[j] == key && si[j] < id));
-    if (partial) atomicAdd(&rank[i], partial);
+// One thread per appended silhouette edge (stride loop over the device-side count): stencil record + tile lists.
+__global__ void __launch_bounds__(128) k_bin_edges(SceneView s, double sigma, int tiles_x, EdgeList edges, EdgeBins bins,
+                                                   EdgeRec *recs, const int *scal) {
+    if (scal[SC_OVERFLOW]) return;
+    const int n = min(*edges.count, edges.capacity);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        bin_edge<DevEnv>(s, i, sigma, tiles_x, edges, bins, recs);
 }
 
-// edge_sorted[rank] = id, and the edge's band stencil record (DR.h:1366-1460 + z plane) at the same rank: built ONCE
-// per forward pass, not per tile.
-__global__ void k_scatter_edges(SceneView s, EdgeList edges, int n, double sigma, int *edge_sorted, EdgeRec *recs) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int r = edges.rank[i], id = edges.ids[i];
-    edge_sorted[r] = id;
-    edge_record(s, id, r, sigma, &recs[r]);
+// Orders every tile's edge list far to near (tile_edge_position, phases.h) and appends the tile to the two-ended list
+// the edge kernels walk: tiles with more than one chunk of edges at the front (they set those kernels' duration and
+// must start first), the others from the back.  One CTA per tile, most return at once; (key, id) pairs are staged in
+// shared memory 256 at a time.
+constexpr int SORT_CHUNK = 256;
+__global__ void __launch_bounds__(128) k_sort_tile_edges(TileSegments seg, int num_tiles, const int *refs_in,
+                                                         int *refs_out, const EdgeRec *recs, int *edge_tiles, int *scal) {
+    if (scal[SC_OVERFLOW]) return;
+    __shared__ unsigned long long sk[SORT_CHUNK];
+    __shared__ int si[SORT_CHUNK];
+    const int tile = blockIdx.x;
+    const int n = segment_size(seg, tile), base = seg.offset[tile];
+    if (n == 0) return;
+    if (threadIdx.x == 0) {
+        if (n > EDGE_CHUNK) edge_tiles[atomicAdd(scal + SC_HEAVY_TILES, 1)] = tile;
+        else edge_tiles[num_tiles - 1 - atomicAdd(scal + SC_LIGHT_TILES, 1)] = tile;
+    }
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        int ref = 0, id = 0, pos = 0;
+        unsigned long long key = 0;
+        if (i < n) {
+            ref = refs_in[base + i];
+            key = recs[ref].key;
+            id = recs[ref].id;
+        }
+        for (int c0 = 0; c0 < n; c0 += SORT_CHUNK) {
+            const int m = min(SORT_CHUNK, n - c0);
+            __syncthreads();
+            for (int j = threadIdx.x; j < m; j += blockDim.x) {
+                const EdgeRec &o = recs[refs_in[base + c0 + j]];
+                sk[j] = o.key;
+                si[j] = o.id;
+            }
+            __syncthreads();
+            if (i < n)
+                for (int j = 0; j < m; j++) pos += (int)(sk[j] < key || (sk[j] == key && si[j] < id));
+        }
+        if (i < n) refs_out[base + pos] = ref;
+    }
 }
 
-// One thread per silhouette edge (far-to-near rank r): band stencil of DR.h:1366-1460 + z plane, once per forward.
-__global__ void k_edge_records(SceneView s, const int *edge_sorted, int n, double sigma, EdgeRec *recs) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) edge_record(s, edge_sorted[r], r, sigma, &recs[r]);
-}
-
-// Fill pass over the compacted lists: blocks [0, small_blocks) small triangles (pre-masked records), then large
-// triangles (indices), then silhouette edges (ranks).
-#ifndef DEODR_FILL_MIN_CTAS
-#define DEODR_FILL_MIN_CTAS 8  // 64 registers: fill 64.3 us vs 68.9 us at 74 (measured, c5)
-#endif
-__global__ void __launch_bounds__(128, DEODR_FILL_MIN_CTAS) k_bin_fill(SceneView s, double sigma, int tiles_x, int small_blocks, int large_blocks, TriBins bins,
-                           const int *small_ids, int num_small, const int *large_ids, int num_large,
-                           const int *edge_sorted, int num_edges, const int *edge_offset, int *edge_cursor,
-                           int *edge_refs) {
-    int b = blockIdx.x;
-    if (b < small_blocks) {
-        int i = b * blockDim.x + threadIdx.x;
-        if (i < num_small) bin_fill_small<DevEnv>(s, small_ids[i], tiles_x, bins);
-        return;
-    }
-    b -= small_blocks;
-    if (b < large_blocks) {
-        int i = b * blockDim.x + threadIdx.x;
-        if (i < num_large) bin_fill_large<DevEnv>(s, large_ids[i], tiles_x, bins);
-        return;
-    }
-    b -= large_blocks;
-    int r = b * blockDim.x + threadIdx.x;
-    if (r < num_edges) bin_fill_edge<DevEnv>(s, edge_sorted[r], r, sigma, tiles_x, edge_offset, edge_cursor, edge_refs);
+// Verdict + counts of the binning kernels -> pinned host memory + sequence flag (one warp).
+__global__ void k_publish(const int *scal, int *host_totals, int seq) {
+    const int lane = threadIdx.x;
+    if (lane < SC_WORDS) host_totals[lane] = ((const volatile int *)scal)[lane];
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) ((volatile int *)host_totals)[SC_WORDS] = seq;
 }
 
 // ---------------------------------------------------------------------------- TMA (bulk async copy) + mbarrier
@@ -365,24 +249,6 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-// Orders every tile's edge list by far-to-near rank (ranks are unique): rank-counting sort, one CTA per tile.
-__global__ void k_sort_tile_edges(const int *edge_tiles, int num_tiles, int heavy, const int *count, const int *offset,
-                                  const int *refs_in, int *refs_out) {
-    const int tile = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x);
-    const int n = count[tile], base = offset[tile];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int mine = refs_in[base + i], pos = 0;
-        for (int j = 0; j < n; j++) pos += refs_in[base + j] < mine;
-        refs_out[base + pos] = mine;
-    }
-}
-
-struct TieTable {
-    int *pairs;     // (own, bown) per tie pixel
-    int *counter;   // number of entries requested so far (may exceed capacity: overflow)
-    int capacity;
-};
-
 // Forward, kernel 1 of 3 - z-buffer and owner ids, one 16x16 tile per CTA (no colour work: few registers).
 // Small triangles: the tile's pre-masked records are pulled into shared memory by a bulk copy (cp.async.bulk +
 // mbarrier, SASS UBLKCP); two threads per record scatter its index into per-pixel candidate lists; each pixel then
@@ -396,7 +262,11 @@ struct TieTable {
 // PERSP: perspective_correct as a compile-time constant (the 1/z division and its registers leave the common instance)
 template <bool PERSP>
 __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s, TileDiv tiles_x, int num_tiles, TriBins bins, TieTable ties,
-                                                  double *z_buffer, int *owner, int *face_id) {
+                                                  double *z_buffer, int *owner, int *face_id, int *scal,
+                                                  int *large_tiles) {
+    // a list outgrew the plan: the pass is void (the host re-plans and re-runs).  OVF_EDGE_REFS is left out: it is
+    // raised by k_bin_edges, which runs beside this kernel, and the early return must be uniform across the CTA
+    if (scal[SC_OVERFLOW] & ~OVF_EDGE_REFS) return;
     s.perspective_correct = PERSP ? 1 : 0;
     __shared__ TileShared sh;
     __shared__ alignas(16) PreRec pre[2][PRE_CHUNK];
@@ -415,7 +285,10 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
     // warp 0 (which also does pixel work).
     int nn = 0, noff = 0;
     auto load_info = [&](int t) {
-        if (tid == 0 && t < num_tiles) { nn = bins.small_cursor[t]; noff = bins.small_offset[t]; }
+        if (tid == 0 && t < num_tiles) {
+            noff = bins.small.offset[t];
+            nn = min(bins.small.cursor[t], bins.small.offset[t + 1] - noff);
+        }
     };
     auto issue = [&](int t, int b) {  // publish (nn, noff) for tile t and start the copy of its first chunk
         if (tid != 0 || t >= num_tiles) return;
@@ -464,9 +337,11 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
             __syncthreads();
         }
         // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
-        const int n_large = bins.large_count[tile_id];
+        const int n_large = segment_size(bins.large, tile_id);
         if (n_large > 0) {
-            const int *large = bins.large_refs + bins.large_offset[tile_id];
+            // the adjoint's pixel-parallel kernel walks the tiles that hold large triangles
+            if (tid == 0) large_tiles[atomicAdd(scal + SC_LARGE_TILES, 1)] = tile_id;
+            const int *large = bins.large_refs + bins.large.offset[tile_id];
             for (int base = 0; base < n_large; base += LARGE_CHUNK) {
                 const int m = min(LARGE_CHUNK, n_large - base);
                 phase_tri_setup(s, tid, m, large + base, &sh);
@@ -495,24 +370,17 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
     }
 }
 
-// decodes an owner code into (forward owner, adjoint owner); -1 = background
-static __device__ __forceinline__ void decode_owner(int code, const TieTable &ties, int *own, int *bown) {
-    if (code <= -2) {
-        *own = ties.pairs[2 * (-2 - code)];
-        *bown = ties.pairs[2 * (-2 - code) + 1];
-    } else {
-        *own = *bown = code;
-    }
-}
-
 // Forward, kernel 2 of 3 - colour of every pixel from its owner (one thread per pixel, tile-shaped blocks for
-// locality of the vertex gathers).  Reads owner (and z with perspective_correct), writes image.
+// locality of the vertex gathers).  Reads owner (and z with perspective_correct), writes image; optionally the
+// squared residual against `obs` (antialiase_error mode, DR.h:2824-2837) and the owner's interpolation weights.
 template <int MAXC, bool PERSP, bool TEX>
 #ifndef DEODR_SHADE_MIN_CTAS
 #define DEODR_SHADE_MIN_CTAS 6  // 40 registers: measured 55.5 us vs 58.6 us at 48 (5 CTAs / SM) and 67 us at 56
 #endif
 __global__ void __launch_bounds__(NT, DEODR_SHADE_MIN_CTAS) k_shade(SceneView s, TileDiv tiles_x, TieTable ties, const int *owner,
-                                              const double *z_buffer, float *image) {
+                                              const double *z_buffer, float *image, const float *obs, float *err,
+                                              float *bary, const int *scal) {
+    if (scal[SC_OVERFLOW] & ~OVF_EDGE_REFS) return;  // (see k_tile_z)
     fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = PERSP ? 1 : 0;
     const Tile tile = tile_of(blockIdx.x, tiles_x);
@@ -522,204 +390,75 @@ __global__ void __launch_bounds__(NT, DEODR_SHADE_MIN_CTAS) k_shade(SceneView s,
     PixelState<MAXC> p;
     decode_owner(owner[idx], ties, &p.own, &p.bown);
     p.z = s.perspective_correct && p.own >= 0 ? z_buffer[idx] : 0.0;
-    phase_shade<MAXC>(s, x, y, &p);
+    if (bary) {
+        float w[3];
+        phase_shade<MAXC>(s, x, y, &p, w);
+        bary[3 * idx] = w[0];
+        bary[3 * idx + 1] = w[1];
+        bary[3 * idx + 2] = w[2];
+    } else {
+        phase_shade<MAXC>(s, x, y, &p);
+    }
     for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
+    if (err) err[idx] = (float)pixel_residual<MAXC>(s, p.col, obs + idx * s.nb_colors);
 }
 
-
-#ifndef DEODR_EDGE_MIN_CTAS
-#define DEODR_EDGE_MIN_CTAS 3  // 85 registers: edge_bwd 62.9 us vs 68 us at 64, 77 us at 51 (measured, c5)
-#endif
-static_assert(EDGE_ROWS == TS, "the span cache shared by k_edge_fwd and k_raster_bwd holds whole tiles");
-
 // Forward, kernel 3 of 3 - ordered silhouette-edge overdraw on the tiles that have edges (DR.h:2839-2899).
-// One CTA per tile, the tiles with more than one chunk of edges first (two-ended list built by k_scan_tiles): the few
+// One CTA per tile (stride loop over the device-side list), the tiles with more than one chunk of edges first: the few
 // crowded tiles set the kernel's duration.  Per chunk of <= 64 edges: records copied to shared memory, (edge, row) x
 // spans computed (and saved for the adjoint pass), then every pixel blends the edges of its own 64-bit hit mask in
-// far-to-near order.  (16x4 strips with four CTAs per tile were measured slower: the set-up work is per edge.)
-template <int MAXC, bool PERSP, bool TEX>
-__global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
-                                                      const int *edge_count, const int *edge_offset,
-                                                      const int *edge_refs, const EdgeRec *edge_recs,
-                                                      uint32_t *span_cache, const double *z_buffer, float *image) {
+// far-to-near order.  ERR: antialiase_error mode - the edges overdraw the squared residual instead of the colours
+// (DR.h:2186-2187, 2467-2468); the image keeps its aliased edges.
+template <int MAXC, bool PERSP, bool TEX, bool ERR>
+__global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(SceneView s, double sigma, TileDiv tiles_x, EdgeTiles et,
+                                                      uint32_t *span_cache, const double *z_buffer, float *image,
+                                                      const float *obs, float *err_buffer) {
+    if (et.scal[SC_OVERFLOW]) return;
     fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = PERSP ? 1 : 0;
     __shared__ TileShared sh;
-    const int tile_id = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x / (TS / EDGE_ROWS)), tid = threadIdx.x;
-    const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
-    const int n_edge = edge_count[tile_id];
-    const Tile tile = tile_of(tile_id, tiles_x);
-    const int r = row0 + tid / TS;
-    const int x = tile.x0 + tid % TS, y = tile.y0 + r;
-    const bool inside = x < s.width && y < s.height;
-    const size_t idx = inside ? (size_t)y * s.width + x : 0;
-    PixelState<MAXC> p;
-    p.z = 0.0;
-    p.own = p.bown = -1;
-    if (inside) {
-        p.z = z_buffer[idx];
-        for (int k = 0; k < s.nb_colors; k++) p.col[k] = image[idx * s.nb_colors + k];
-    }
-    const int edge_base = edge_offset[tile_id];
-    for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
-        const int m = min(EDGE_CHUNK, n_edge - base);
-        phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
-        __syncthreads();
-        phase_edge_spans(s, tid, EDGE_NT, m, tile, row0, EDGE_ROWS, &sh);
-        __syncthreads();
-        // the backward pass reuses the spans (same scene, same sigma): 64 bytes per (tile, edge), coalesced
-        for (int item = tid; item < m * TS; item += EDGE_NT)
-            span_cache[(size_t)(edge_base + base) * TS + item] = sh.edge.span[item / TS][item % TS];
-        if (inside) phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
-        __syncthreads();
-    }
-    if (inside)
-        for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
-}
-
-// (register budgets are pinned: the allocator's own choice moved 64 -> 80 on an unrelated signature change)
-template <int MAXC, bool TEX>
-__global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(SceneView s, double sigma, TileDiv tiles_x, const int *edge_tiles, int num_tiles, int heavy,
-                                                   const int *edge_count, const int *edge_offset, const int *edge_refs,
-                                                   const EdgeRec *edge_recs, const uint32_t *span_cache, TieTable ties,
-                                                   const double *z_buffer,
-                                                   const int *owner, const float *image_b, DeodrGrads grads,
-                                                   double *edge_acc) {
-    fix_channel_count<MAXC, TEX>(s);
-    s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
-    __shared__ TileShared sh;
-    // one CTA per tile that HAS edges, crowded tiles first (see k_edge_fwd)
-    const int tile_id = two_ended_at(edge_tiles, num_tiles, heavy, blockIdx.x / (TS / EDGE_ROWS)), tid = threadIdx.x;
-    const int row0 = (blockIdx.x % (TS / EDGE_ROWS)) * EDGE_ROWS;
-    const Tile tile = tile_of(tile_id, tiles_x);
-    const int c = tid % TS, r = row0 + tid / TS;
-    const int x = tile.x0 + c, y = tile.y0 + r;
-    const bool inside = x < s.width && y < s.height;
-    const size_t idx = inside ? (size_t)y * s.width + x : 0;
-    const int n_edge = edge_count[tile_id];
-
-    PixelState<MAXC> p;
-    AdjointState<MAXC> a;
-    a.has_colour = false;
-    p.z = __longlong_as_double(0x7ff0000000000000LL);
-    p.own = p.bown = -1;
-    if (inside) {
-        p.z = z_buffer[idx];
-        int code = owner[idx];
-        if (code <= -2) {
-            p.own = ties.pairs[2 * (-2 - code)];
-            p.bown = ties.pairs[2 * (-2 - code) + 1];
-        } else {
-            p.own = p.bown = code;
+    const int tid = threadIdx.x;
+    const int heavy = et.scal[SC_HEAVY_TILES], total = heavy + et.scal[SC_LIGHT_TILES];
+    for (int b = blockIdx.x; b < total; b += gridDim.x) {
+        const int tile_id = two_ended_at(et.list, et.num_tiles, heavy, b);
+        const int n_edge = segment_size(et.seg, tile_id);
+        const Tile tile = tile_of(tile_id, tiles_x);
+        const int r = tid / TS;
+        const int x = tile.x0 + tid % TS, y = tile.y0 + r;
+        const bool inside = x < s.width && y < s.height;
+        const size_t idx = inside ? (size_t)y * s.width + x : 0;
+        PixelState<MAXC> p;
+        float err = 0.0f;
+        p.z = 0.0;
+        p.own = p.bown = -1;
+        if (inside) {
+            p.z = z_buffer[idx];
+            if (ERR) err = err_buffer[idx];
+            else
+                for (int k = 0; k < s.nb_colors; k++) p.col[k] = image[idx * s.nb_colors + k];
         }
-        for (int k = 0; k < s.nb_colors; k++) a.g[k] = image_b[idx * s.nb_colors + k];
-    }
-
-    {
-        const int edge_base = edge_offset[tile_id];
-        const bool single = n_edge <= EDGE_CHUNK;
-        auto load_spans = [&](int base, int m) {  // (all loads of a pass before its stores, see phase_edge_setup)
-            const uint32_t *src = span_cache + (size_t)(edge_base + base) * TS;
-            for (int first = tid; first < m * TS; first += 4 * EDGE_NT) {
-                uint32_t v[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (first + j * EDGE_NT < m * TS) v[j] = __ldg(src + first + j * EDGE_NT);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int item = first + j * EDGE_NT;
-                    if (item < m * TS) sh.edge.span[item / TS][item % TS] = v[j];
-                }
-            }
-        };
-        // pass A: forward replay (far to near) to obtain the final colour in fp64
+        const int edge_base = et.seg.offset[tile_id];
         for (int base = 0; base < n_edge; base += EDGE_CHUNK) {
             const int m = min(EDGE_CHUNK, n_edge - base);
-            phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
-            load_spans(base, m);  // computed by the forward pass (k_edge_fwd)
+            phase_edge_setup(tid, EDGE_NT, m, et.refs + edge_base + base, et.recs, &sh);
             __syncthreads();
-            if (inside) phase_edge_replay<MAXC>(s, x, y, r, m, &sh, p, &a);
-            if (single) {
-                if (inside && a.has_colour)
-                    phase_edge_adjoint<MAXC, DevEnv>(s, x, y, r, m, &sh, p, &a, edge_acc, grads.texture_b);
+            phase_edge_spans(s, tid, EDGE_NT, m, tile, 0, EDGE_ROWS, &sh);
+            __syncthreads();
+            // the backward pass reuses the spans (same scene, same sigma): 64 bytes per (tile, edge), coalesced
+            for (int item = tid; item < m * TS; item += EDGE_NT)
+                span_cache[(size_t)(edge_base + base) * TS + item] = sh.edge.span[item / TS][item % TS];
+            if (inside) {
+                if (ERR) phase_edge_blend_error<MAXC>(s, x, y, r, m, &sh, p.z, obs + idx * s.nb_colors, &err);
+                else phase_edge_blend<MAXC>(s, x, y, r, m, &sh, &p);
             }
             __syncthreads();
         }
-        // pass B: reverse sweep (near to far), chunks in reverse order
-        if (!single) {
-            const int last = ((n_edge - 1) / EDGE_CHUNK) * EDGE_CHUNK;
-            for (int base = last; base >= 0; base -= EDGE_CHUNK) {
-                const int m = min(EDGE_CHUNK, n_edge - base);
-                phase_edge_setup(tid, EDGE_NT, m, edge_refs + edge_base + base, edge_recs, &sh);
-                load_spans(base, m);
-                __syncthreads();
-                if (inside && a.has_colour)
-                    phase_edge_adjoint<MAXC, DevEnv>(s, x, y, r, m, &sh, p, &a, edge_acc, grads.texture_b);
-                __syncthreads();
-            }
+        if (inside) {
+            if (ERR) err_buffer[idx] = err;
+            else
+                for (int k = 0; k < s.nb_colors; k++) image[idx * s.nb_colors + k] = p.col[k];
         }
     }
-    interior_adjoint_warp<MAXC>(s, x, y, inside && p.bown >= 0, p, a.g, grads);
-}
-
-// Interior adjoint of the pixels owned by LARGE triangles in the tiles without silhouette edges: no shared memory, no
-// z-buffer read; the gradients are summed per owner inside each warp before the scatter (interior_adjoint_warp).
-template <int MAXC, bool TEX>
-#ifndef DEODR_INTERIOR_MIN_CTAS
-#define DEODR_INTERIOR_MIN_CTAS 3  // 85 registers: 39.2 us vs 40.3 us at 64 and 47.6 us at 51 (measured, c5)
-#endif
-__global__ void __launch_bounds__(NT, DEODR_INTERIOR_MIN_CTAS) k_interior_bwd(SceneView s, TileDiv tiles_x, const int *large_tiles,
-                                                     const int *edge_count, TieTable ties, const int *owner,
-                                                     const float *image_b, DeodrGrads grads) {
-    fix_channel_count<MAXC, TEX>(s);
-    s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
-    const int tile_id = large_tiles[blockIdx.x], tid = threadIdx.x;  // one CTA per tile with large triangles binned
-    if (edge_count && edge_count[tile_id] > 0) return;  // handled by k_raster_bwd
-    const Tile tile = tile_of(tile_id, tiles_x);
-    const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
-    const bool inside = x < s.width && y < s.height;
-    PixelState<MAXC> p;
-    p.z = 0.0;  // only read by the perspective-correct forward path
-    p.own = p.bown = -1;
-    float g[MAXC];
-    if (inside) {
-        const size_t idx = (size_t)y * s.width + x;
-        const int code = owner[idx];
-        if (code <= -2) {
-            p.own = ties.pairs[2 * (-2 - code)];
-            p.bown = ties.pairs[2 * (-2 - code) + 1];
-        } else {
-            p.own = p.bown = code;
-        }
-        if (p.bown >= 0 && (p.bown & SMALL_FLAG)) p.bown = -1;  // taken by k_small_tri_bwd (triangle-parallel)
-        if (p.bown >= 0)
-            for (int k = 0; k < s.nb_colors; k++) g[k] = image_b[idx * s.nb_colors + k];
-    }
-    interior_adjoint_warp<MAXC>(s, x, y, inside && p.bown >= 0, p, g, grads);
-}
-
-// Triangle-parallel interior adjoint of the small triangles (one thread per entry of the compacted small list).
-template <int MAXC, bool TEX>
-#ifndef DEODR_SMALL_MIN_CTAS
-#define DEODR_SMALL_MIN_CTAS 8
-#endif
-__global__ void __launch_bounds__(128, DEODR_SMALL_MIN_CTAS) k_small_tri_bwd(SceneView s, int tiles_x, const int *small_ids, int num_small,
-                                                       const int *edge_count, TieTable ties, const int *owner,
-                                                       const float *image_b, DeodrGrads grads) {
-    fix_channel_count<MAXC, TEX>(s);
-    s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= num_small) return;
-    small_triangle_adjoint<MAXC, DevEnv>(s, small_ids[i], tiles_x, edge_count, owner, ties.pairs, image_b, grads.ij_b,
-                                         grads.colors_b, grads.uv_b, grads.shade_b, grads.texture_b);
-}
-
-__global__ void k_finalize_edges(SceneView s, const int *edge_sorted, const int *num_edges, double sigma,
-                                 const double *edge_acc, DeodrGrads grads) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= *num_edges) return;
-    finalize_edge<DevEnv>(s, edge_sorted[r], sigma, edge_acc + (size_t)r * edge_acc_stride(s.nb_colors), grads.ij_b,
-                          grads.colors_b, grads.uv_b, grads.shade_b);
 }
 
 __global__ void k_check_scene(SceneView s, int *bad) {
@@ -738,120 +477,10 @@ char *deodr_error_buffer() {
 
 static int sm_count_cached = 0;
 
-// RAII bracket: records a (start, stop) event pair around a group of launches when timing is enabled
-struct PhaseTimer {
-    DeodrWorkspace *ws;
-    cudaStream_t st;
-    int slot;
-    PhaseTimer(DeodrWorkspace *w, int phase, cudaStream_t s) : ws(w), st(s), slot(-1) {
-        if (ws->ev_used < (int)ws->ev_start.size()) {
-            slot = ws->ev_used++;
-            ws->ev_phase[slot] = phase;
-            cudaEventRecord(ws->ev_start[slot], st);
-        }
-    }
-    ~PhaseTimer() {
-        if (slot >= 0) cudaEventRecord(ws->ev_stop[slot], st);
-    }
-};
-
-static inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
-
-// Fork: auxiliary stream i continues from the current point of the caller's stream; join: the caller's stream waits
-// for it.  Independent kernel chains then overlap (tails of one fill with CTAs of the other; no launch gaps).
-static inline cudaStream_t fork_stream(DeodrWorkspace *ws, int i, cudaStream_t st, bool *first) {
-    if (!ws->overlap) return st;
-    if (*first) { cudaEventRecord(ws->ev_fork, st); *first = false; }
-    cudaStreamWaitEvent(ws->aux[i], ws->ev_fork, 0);
-    return ws->aux[i];
-}
-static inline void join_stream(DeodrWorkspace *ws, int i, cudaStream_t st) {
-    if (!ws->overlap) return;
-    cudaEventRecord(ws->ev_join[i], ws->aux[i]);
-    cudaStreamWaitEvent(st, ws->ev_join[i], 0);
-}
-
-template <int MAXC>
-static void launch_fwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
-                       float *image, double *z, int *owner, int *face_id, bool edge_chain, cudaStream_t st) {
-    const bool tex = ws->any_textured != 0;
-    {
-        PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
-        // DEODR_B200_TILEZ_CTAS_PER_SM = k > 0 runs k persistent CTAs per SM with the two-stage TMA pipeline; default 0 =
-        // one CTA per tile (the same kernel, its loop runs once).  Measured on B200, 1M-triangle scene: 168 us per-tile
-        // vs 199 us persistent x4 vs 300 us persistent x2 - the hardware CTA scheduler balances the very uneven tiles
-        // better than a static stride, and 4 resident CTAs already overlap each other's copy latency.
-        static const int per_sm = getenv("DEODR_B200_TILEZ_CTAS_PER_SM") ? atoi(getenv("DEODR_B200_TILEZ_CTAS_PER_SM")) : 0;
-        // DEODR_B200_TILEZ_TILES_PER_CTA = k: every CTA walks k tiles (stride = grid size) with the copy of the next
-        // tile in flight while it tests the current one
-        static const int per_cta = getenv("DEODR_B200_TILEZ_TILES_PER_CTA") ? atoi(getenv("DEODR_B200_TILEZ_TILES_PER_CTA")) : 1;
-        int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : ws->num_tiles;
-        if (per_sm <= 0 && per_cta > 1) persistent = (ws->num_tiles + per_cta - 1) / per_cta;
-        (s.perspective_correct ? k_tile_z<true> : k_tile_z<false>)<<<ws->num_tiles < persistent ? ws->num_tiles : persistent, NT, 0, st>>>(
-            s, make_tile_div(ws->tiles_x), ws->num_tiles, ws->bins, ties, z, owner, face_id);
-    }
-    {
-        PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
-        (s.perspective_correct ? (tex ? k_shade<MAXC, true, true> : k_shade<MAXC, true, false>)
-                               : (tex ? k_shade<MAXC, false, true> : k_shade<MAXC, false, false>))<<<ws->num_tiles, NT, 0, st>>>(s, make_tile_div(ws->tiles_x), ties, owner, z, image);
-    }
-    ws->launches += 2;
-    if (edge_chain) join_stream(ws, 0, st);  // the edge lists are ready
-    if (edge_count && ws->num_edge_tiles > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
-        (s.perspective_correct ? (tex ? k_edge_fwd<MAXC, true, true> : k_edge_fwd<MAXC, true, false>)
-                               : (tex ? k_edge_fwd<MAXC, false, true> : k_edge_fwd<MAXC, false, false>))<<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, st>>>(s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
-                                                            ws->edge_offset.as<int>(), ws->edge_refs.as<int>(),
-                                                            ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), z, image);
-        ws->launches++;
-    }
-}
-
-template <int MAXC>
-static void launch_bwd(DeodrWorkspace *ws, const SceneView &s, double sigma, const int *edge_count, TieTable ties,
-                       const double *z, const int *owner, const float *image_b, const DeodrGrads &g, int *scal,
-                       cudaStream_t st) {
-    // Three independent chains (disjoint pixel sets, all accumulate with atomics): edge tiles (longest tail: launched
-    // first so that its CTAs are dispatched first), tiles with large triangles, small triangles.
-    bool first = true;
-    const bool tex = ws->any_textured != 0;
-    const int E = ws->num_edges, C = s.nb_colors;
-    const bool edges = edge_count && ws->num_edge_tiles > 0 && E > 0;
-    if (edges) {
-        cudaStream_t se = fork_stream(ws, 0, st, &first);
-        cudaMemsetAsync(ws->edge_acc.ptr, 0, (size_t)E * edge_acc_stride(C) * sizeof(double), se);
-        {
-            PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, se);
-            (tex ? k_raster_bwd<MAXC, true> : k_raster_bwd<MAXC, false>)<<<ws->num_edge_tiles * (TS / EDGE_ROWS), EDGE_NT, 0, se>>>(
-                s, sigma, make_tile_div(ws->tiles_x), ws->edge_tiles_ptr, ws->num_tiles, ws->num_heavy_edge_tiles, edge_count,
-                ws->edge_offset.as<int>(),
-                ws->edge_refs.as<int>(), ws->edge_recs.as<EdgeRec>(), ws->edge_spans.as<uint32_t>(), ties, z, owner,
-                image_b, g,
-                ws->edge_acc.as<double>());
-        }
-        {
-            PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FINALIZE, se);
-            k_finalize_edges<<<grid_for(E, 128), 128, 0, se>>>(s, ws->edge_sorted.as<int>(), scal + 1, sigma,
-                                                               ws->edge_acc.as<double>(), g);
-        }
-        ws->launches += 2;
-    }
-    if (ws->num_large_tiles > 0) {  // pixels owned by large triangles, tiles without silhouette edges
-        cudaStream_t sl = fork_stream(ws, 1, st, &first);
-        PhaseTimer timer(ws, DEODR_B200_PH_INTERIOR_BWD, sl);
-        (tex ? k_interior_bwd<MAXC, true> : k_interior_bwd<MAXC, false>)<<<ws->num_large_tiles, NT, 0, sl>>>(s, make_tile_div(ws->tiles_x), ws->large_tiles.as<int>(), edge_count,
-                                                                 ties, owner, image_b, g);
-        ws->launches++;
-    }
-    if (ws->num_small > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_SMALL_BWD, st);
-        (tex ? k_small_tri_bwd<MAXC, true> : k_small_tri_bwd<MAXC, false>)<<<grid_for(ws->num_small, 128), 128, 0, st>>>(s, ws->tiles_x, ws->small_ids.as<int>(),
-                                                                           ws->num_small, edge_count, ties, owner,
-                                                                           image_b, g);
-        ws->launches++;
-    }
-    if (edges) join_stream(ws, 0, st);
-    if (ws->num_large_tiles > 0) join_stream(ws, 1, st);
+static bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &status) != cudaSuccess) { cudaGetLastError(); return false; }
+    return status != cudaStreamCaptureStatusNone;
 }
 
 static int validate_view(const DeodrSceneView *v, bool backward) {
@@ -889,14 +518,477 @@ static int validate_view(const DeodrSceneView *v, bool backward) {
     return DEODR_B200_OK;
 }
 
+// ---- view slots ------------------------------------------------------------------------------------------------
+
+static void free_slot(ViewSlot *v) {
+    if (!v) return;
+    DevBuf *bufs[] = {&v->zeroed, &v->small_offset, &v->large_offset, &v->edge_offset, &v->small_recs, &v->large_refs,
+                      &v->small_ids, &v->large_tiles, &v->edge_tiles, &v->edge_ids, &v->edge_keys, &v->edge_recs,
+                      &v->edge_refs_tmp, &v->edge_refs, &v->edge_spans, &v->edge_acc, &v->tie_pairs, &v->error_image_b};
+    for (DevBuf *b : bufs) b->release();
+    if (v->host_totals) cudaFreeHost(v->host_totals);
+    delete v;
+}
+
+static int get_slot(DeodrWorkspace *ws, int index, ViewSlot **out) {
+    if (index < 0 || index >= 65536) return set_error(DEODR_B200_EINVAL, "bad view index");
+    while ((int)ws->slots.size() <= index) ws->slots.push_back(nullptr);
+    if (!ws->slots[index]) {
+        ViewSlot *v = new (std::nothrow) ViewSlot();
+        if (!v) return set_error(DEODR_B200_ENOMEM, "out of host memory");
+        memset(&v->fwd_scene, 0, sizeof(v->fwd_scene));
+        memset(&v->fwd_io, 0, sizeof(v->fwd_io));
+        if (cudaMallocHost(&v->host_totals, (SC_WORDS + 8) * sizeof(int)) != cudaSuccess) {
+            delete v;
+            return set_error(DEODR_B200_ECUDA, "cudaMallocHost failed");
+        }
+        memset(v->host_totals, 0, (SC_WORDS + 8) * sizeof(int));
+        ws->slots[index] = v;
+    }
+    *out = ws->slots[index];
+    return DEODR_B200_OK;
+}
+
+// Buffers whose size follows from the shape alone; invalidates the plan when the shape differs from the plan's.
+static int prepare_slot(DeodrWorkspace *ws, ViewSlot *v, const SceneView &s, double sigma) {
+    const int tiles_x = (s.width + TS - 1) / TS, tiles_y = (s.height + TS - 1) / TS, nt = tiles_x * tiles_y;
+    FwdPlan &plan = v->plan;
+    if (plan.valid && (plan.T != s.nb_triangles || plan.H != s.height || plan.W != s.width ||
+                       plan.edges_possible != (sigma > 0)))
+        plan.valid = false;
+    v->tiles_x = tiles_x;
+    v->tiles_y = tiles_y;
+    v->num_tiles = nt;
+    const size_t T = (size_t)s.nb_triangles;
+    int rc = 0;
+    rc |= v->zeroed.ensure((SC_WORDS + 3 * (size_t)nt) * sizeof(int), &ws->bytes);
+    rc |= v->small_offset.ensure(((size_t)nt + 1) * sizeof(int), &ws->bytes);
+    rc |= v->large_offset.ensure(((size_t)nt + 1) * sizeof(int), &ws->bytes);
+    rc |= v->edge_offset.ensure(((size_t)nt + 1) * sizeof(int), &ws->bytes);
+    rc |= v->large_tiles.ensure(((size_t)nt + 1) * sizeof(int), &ws->bytes);
+    rc |= v->edge_tiles.ensure(((size_t)nt + 1) * sizeof(int), &ws->bytes);
+    rc |= v->small_ids.ensure((T + 4) * sizeof(int), &ws->bytes);
+    // one (own, bown) slot per pixel: the exact-tie table can never overflow
+    const size_t pixels = (size_t)s.height * s.width;
+    if ((size_t)v->tie_capacity < pixels) {
+        rc |= v->tie_pairs.ensure(2 * pixels * sizeof(int), &ws->bytes);
+        if (!rc) v->tie_capacity = (int)pixels;
+    }
+    if (rc) return DEODR_B200_ECUDA;
+    v->scal = v->zeroed.as<int>();
+    v->small_cursor = v->scal + SC_WORDS;
+    v->large_cursor = v->small_cursor + nt;
+    v->edge_cursor = v->large_cursor + nt;
+    return DEODR_B200_OK;
+}
+
+// Waits for the sequence flag a kernel raises in the slot's pinned totals (k_scan_tiles / k_publish); polls the stream
+// every few microseconds as a safety net (flag lost / launch failed).
+static int wait_totals(ViewSlot *v, cudaStream_t st) {
+    volatile int *flag = v->host_totals + SC_WORDS;
+    for (unsigned spins = 1; *flag != v->totals_seq; spins++) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xfffu) == 0) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaSuccess) {
+                if (*flag != v->totals_seq) {  // not expected; fall back to an explicit copy
+                    CUDA_TRY(cudaMemcpyAsync(v->host_totals, v->scal, SC_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                }
+                break;
+            }
+            if (q != cudaErrorNotReady) return set_error(DEODR_B200_ECUDA, "forward pass failed: %s", cudaGetErrorString(q));
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return DEODR_B200_OK;
+}
+
+static int next_seq(ViewSlot *v) {
+    v->totals_seq = v->totals_seq == 0x7fffffff ? 1 : v->totals_seq + 1;
+    return v->totals_seq;
+}
+
+static int bad_index_error(const ViewSlot *v) {
+    if (v->host_totals[SC_BAD_INDEX] & 1)
+        return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
+    if (v->host_totals[SC_BAD_INDEX] & 2)
+        return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
+    return DEODR_B200_OK;
+}
+
+// Plan building: count pass + scans + ONE read-back, then the list buffers are (re)allocated.
+static int build_plan(DeodrWorkspace *ws, ViewSlot *v, const SceneView &s, double sigma, cudaStream_t st,
+                      bool check_indices) {
+    PhaseTimer timer(ws, DEODR_B200_PH_PLAN, st);
+    FwdPlan &plan = v->plan;
+    plan.valid = false;
+    const int T = s.nb_triangles, nt = v->num_tiles;
+    CUDA_TRY(cudaMemsetAsync(v->scal, 0, (SC_WORDS + 3 * (size_t)nt) * sizeof(int), st));
+    if (T > 0) {
+        if (check_indices) {
+            k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, v->scal + SC_BAD_INDEX);
+            ws->launches++;
+        }
+        TriBins bins{{nullptr, v->small_cursor}, nullptr, {nullptr, v->large_cursor}, nullptr, v->scal + SC_OVERFLOW};
+        EdgeList edges{v->scal + SC_EDGES, nullptr, nullptr, 0};
+        k_bin<true><<<grid_for(T, 128), 128, 0, st>>>(s, sigma, v->tiles_x, bins, v->scal, nullptr, edges,
+                                                     v->edge_cursor, 1);
+        ws->launches++;
+    }
+    ScanJob job{{v->small_cursor, v->large_cursor, v->edge_cursor},
+                {v->small_offset.as<int>(), v->large_offset.as<int>(), v->edge_offset.as<int>()},
+                {SC_TOTAL_SMALL, SC_TOTAL_LARGE, SC_TOTAL_EDGE_REFS},
+                {-1, SC_PLAN_LARGE_TILES, SC_PLAN_EDGE_TILES}};
+    k_scan_tiles<<<3, 1024, SCAN_SMEM, st>>>(job, nt, v->scal, v->host_totals, next_seq(v));
+    ws->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (int rc = wait_totals(v, st)) return rc;
+    if (check_indices)
+        if (int rc = bad_index_error(v)) return rc;
+    const int *tot = v->host_totals;
+    const int E = tot[SC_EDGES];
+    plan.T = T; plan.H = s.height; plan.W = s.width;
+    plan.edges_possible = sigma > 0;
+    plan.cap_small = tot[SC_TOTAL_SMALL];
+    plan.cap_large = tot[SC_TOTAL_LARGE];
+    plan.cap_edges = E > 0 ? E + E / 4 + 64 : 0;
+    plan.cap_edge_refs = E > 0 ? tot[SC_TOTAL_EDGE_REFS] : 0;
+    plan.tex = tot[SC_TEXTURED] != 0;
+    plan.hint_small = T;
+    plan.hint_edges = E;
+    plan.hint_edge_tiles = E > 0 ? tot[SC_PLAN_EDGE_TILES] + tot[SC_PLAN_EDGE_TILES] / 4 + 8 : 0;
+    plan.hint_large_tiles = tot[SC_PLAN_LARGE_TILES] + tot[SC_PLAN_LARGE_TILES] / 4 + 8;
+    int rc = 0;
+    rc |= v->small_recs.ensure(((size_t)plan.cap_small + 1) * sizeof(PreRec), &ws->bytes);
+    rc |= v->large_refs.ensure(((size_t)plan.cap_large + 4) * sizeof(int), &ws->bytes);
+    if (plan.cap_edges > 0) {
+        rc |= v->edge_ids.ensure(((size_t)plan.cap_edges + 4) * sizeof(int), &ws->bytes);
+        rc |= v->edge_keys.ensure(((size_t)plan.cap_edges + 4) * sizeof(uint64_t), &ws->bytes);
+        rc |= v->edge_recs.ensure(((size_t)plan.cap_edges + 1) * sizeof(EdgeRec), &ws->bytes);
+        rc |= v->edge_refs_tmp.ensure(((size_t)plan.cap_edge_refs + 4) * sizeof(int), &ws->bytes);
+        rc |= v->edge_refs.ensure(((size_t)plan.cap_edge_refs + 4) * sizeof(int), &ws->bytes);
+        rc |= v->edge_spans.ensure(((size_t)plan.cap_edge_refs + 4) * TS * sizeof(uint32_t), &ws->bytes);
+    }
+    if (rc) return DEODR_B200_ECUDA;
+    plan.valid = true;
+    ws->replans++;
+    return DEODR_B200_OK;
+}
+
+template <int MAXC>
+static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneView &s, const DeodrViewIO &io,
+                              double sigma, bool err_mode, bool edge_chain, const TriBins &bins) {
+    cudaStream_t st = lane.main;
+    const bool tex = v->plan.tex != 0;
+    const TileDiv div = make_tile_div(v->tiles_x);
+    const TieTable ties = tie_table(v);
+    {
+        PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
+        // DEODR_B200_TILEZ_CTAS_PER_SM = k > 0 runs k persistent CTAs per SM with the two-stage TMA pipeline; default 0 =
+        // one CTA per tile (the same kernel, its loop runs once).  Measured on B200, 1M-triangle scene: 168 us per-tile
+        // vs 199 us persistent x4 vs 300 us persistent x2 - the hardware CTA scheduler balances the very uneven tiles
+        // better than a static stride, and 4 resident CTAs already overlap each other's copy latency.
+        static const int per_sm = getenv("DEODR_B200_TILEZ_CTAS_PER_SM") ? atoi(getenv("DEODR_B200_TILEZ_CTAS_PER_SM")) : 0;
+        // DEODR_B200_TILEZ_TILES_PER_CTA = k: every CTA walks k tiles (stride = grid size) with the copy of the next
+        // tile in flight while it tests the current one
+        static const int per_cta = getenv("DEODR_B200_TILEZ_TILES_PER_CTA") ? atoi(getenv("DEODR_B200_TILEZ_TILES_PER_CTA")) : 1;
+        int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : v->num_tiles;
+        if (per_sm <= 0 && per_cta > 1) persistent = (v->num_tiles + per_cta - 1) / per_cta;
+        (s.perspective_correct ? k_tile_z<true> : k_tile_z<false>)<<<v->num_tiles < persistent ? v->num_tiles : persistent, NT, 0, st>>>(
+            s, div, v->num_tiles, bins, ties, io.z_buffer, io.owner, io.face_id, v->scal, v->large_tiles.as<int>());
+    }
+    {
+        PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
+        (s.perspective_correct ? (tex ? k_shade<MAXC, true, true> : k_shade<MAXC, true, false>)
+                               : (tex ? k_shade<MAXC, false, true> : k_shade<MAXC, false, false>))<<<v->num_tiles, NT, 0, st>>>(
+            s, div, ties, io.owner, io.z_buffer, io.image, err_mode ? io.obs : nullptr, err_mode ? io.err_buffer : nullptr,
+            io.barycentric, v->scal);
+    }
+    ws->launches += 2;
+    if (edge_chain) {
+        join_stream(ws, lane, 0);  // the edge lists are ready
+        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
+        const EdgeTiles et = edge_tiles_of(v);
+        const int grid = at_least_one(v->plan.hint_edge_tiles < v->num_tiles ? v->plan.hint_edge_tiles : v->num_tiles);
+        uint32_t *spans = v->edge_spans.as<uint32_t>();
+#define DEODR_EDGE_FWD(P, X, R) k_edge_fwd<MAXC, P, X, R><<<grid, EDGE_NT, 0, st>>>(s, sigma, div, et, spans, io.z_buffer, io.image, io.obs, io.err_buffer)
+        const int sel = (s.perspective_correct ? 4 : 0) | (tex ? 2 : 0) | (err_mode ? 1 : 0);
+        switch (sel) {
+            case 0: DEODR_EDGE_FWD(false, false, false); break;
+            case 1: DEODR_EDGE_FWD(false, false, true); break;
+            case 2: DEODR_EDGE_FWD(false, true, false); break;
+            case 3: DEODR_EDGE_FWD(false, true, true); break;
+            case 4: DEODR_EDGE_FWD(true, false, false); break;
+            case 5: DEODR_EDGE_FWD(true, false, true); break;
+            case 6: DEODR_EDGE_FWD(true, true, false); break;
+            default: DEODR_EDGE_FWD(true, true, true); break;
+        }
+#undef DEODR_EDGE_FWD
+        ws->launches++;
+    }
+}
+
+// Enqueues one forward pass of the view on the lane's streams, against the slot's plan; nothing here waits.
+static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneView &s, const DeodrViewIO &io,
+                           double sigma, int flags, bool check_indices) {
+    cudaStream_t st = lane.main;
+    const FwdPlan &plan = v->plan;
+    const int T = s.nb_triangles, nt = v->num_tiles;
+    const bool err_mode = (flags & DEODR_B200_ANTIALIASE_ERROR) != 0;
+    TriBins bins{{v->small_offset.as<int>(), v->small_cursor}, v->small_recs.as<PreRec>(),
+                 {v->large_offset.as<int>(), v->large_cursor}, v->large_refs.as<int>(), v->scal + SC_OVERFLOW};
+    EdgeList edges{v->scal + SC_EDGES, v->edge_ids.as<int>(), v->edge_keys.as<uint64_t>(), plan.cap_edges};
+    const bool edge_chain = plan.cap_edges > 0;
+    {
+        PhaseTimer timer(ws, DEODR_B200_PH_BIN, st);
+        CUDA_TRY(cudaMemsetAsync(v->scal, 0, (SC_WORDS + 3 * (size_t)nt) * sizeof(int), st));
+        if (T > 0) {
+            if (check_indices) {  // checkSceneValid (DR.h:2703-2714) on the device, before any index is dereferenced
+                k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, v->scal + SC_BAD_INDEX);
+                ws->launches++;
+            }
+            k_bin<false><<<grid_for(T, 128), 128, 0, st>>>(s, sigma, v->tiles_x, bins, v->scal, v->small_ids.as<int>(),
+                                                          edges, nullptr, plan.tex);
+            ws->launches++;
+        }
+    }
+    // ---- side chain (aux stream 0): silhouette-edge records + tile lists + their order, then the verdict goes to
+    // the host; it overlaps the z pass and the shading and is joined before k_edge_fwd
+    bool first_fork = true;
+    cudaStream_t se = fork_stream(ws, lane, 0, &first_fork);
+    if (edge_chain) {
+        const EdgeBins ebins{{v->edge_offset.as<int>(), v->edge_cursor}, v->edge_refs_tmp.as<int>(), v->scal + SC_OVERFLOW};
+        {
+            PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BIN, se);
+            k_bin_edges<<<at_least_one(grid_for(plan.hint_edges, 128)), 128, 0, se>>>(s, sigma, v->tiles_x, edges, ebins,
+                                                                                      v->edge_recs.as<EdgeRec>(), v->scal);
+        }
+        {
+            PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, se);
+            k_sort_tile_edges<<<nt, 128, 0, se>>>(ebins.seg, nt, v->edge_refs_tmp.as<int>(), v->edge_refs.as<int>(),
+                                                 v->edge_recs.as<EdgeRec>(), v->edge_tiles.as<int>(), v->scal);
+        }
+        ws->launches += 2;
+    }
+    k_publish<<<1, 32, 0, se>>>(v->scal, v->host_totals, next_seq(v));
+    ws->launches++;
+    v->pending = true;
+    if (!ws->overlap || !edge_chain) {
+        // (serial mode: everything is on the main stream already; without an edge chain the main chain does not
+        // depend on the aux stream, but the lane must still be joined for stream capture / ordering of the next pass)
+    }
+    // ---- main chain: z pass, shading, (join) edge overdraw
+    const int C = s.nb_colors;
+    if (C == 1) launch_raster_fwd<1>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins);
+    else if (C == 3) launch_raster_fwd<3>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins);
+    else if (C <= 4) launch_raster_fwd<4>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins);
+    else launch_raster_fwd<16>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins);
+    if (!edge_chain) join_stream(ws, lane, 0);
+    CUDA_TRY(cudaGetLastError());
+    return DEODR_B200_OK;
+}
+
+// Reads the verdict of the slot's pending pass (waits for its flag) and folds the counts into the plan's hints.
+// *overflow: the pass is void.
+static int read_verdict(DeodrWorkspace *ws, ViewSlot *v, cudaStream_t st, bool *overflow) {
+    *overflow = false;
+    if (!v->pending) return DEODR_B200_OK;
+    if (int rc = wait_totals(v, st)) return rc;
+    v->pending = false;
+    const int *tot = v->host_totals;
+    FwdPlan &plan = v->plan;
+    if (tot[SC_OVERFLOW]) {
+        *overflow = true;
+        plan.valid = false;
+        v->fwd_valid = 0;
+        return DEODR_B200_OK;
+    }
+    plan.hint_small = tot[SC_SMALL];
+    plan.hint_edges = tot[SC_EDGES];
+    plan.hint_edge_tiles = tot[SC_HEAVY_TILES] + tot[SC_LIGHT_TILES];
+    if (plan.tex && !tot[SC_TEXTURED]) plan.tex = 0;  // next pass: instances without the texture paths
+    (void)ws;
+    return DEODR_B200_OK;
+}
+
+struct ViewCall {
+    SceneView s;
+    DeodrViewIO io;
+};
+
+static int check_forward_args(const DeodrSceneView *scene, const DeodrViewIO *io, double sigma, int flags) {
+    if (int rc = validate_view(scene, false)) return rc;
+    if (!io) return set_error(DEODR_B200_EINVAL, "io == NULL");
+    if (!io->image) return set_error(DEODR_B200_EINVAL, "image_ptr is NULL");
+    if (!io->z_buffer) return set_error(DEODR_B200_EINVAL, "z_buffer_ptr is NULL");
+    if (!io->owner) return set_error(DEODR_B200_EINVAL, "owner is NULL");
+    if (!(sigma >= 0)) return set_error(DEODR_B200_EINVAL, "sigma must be >= 0");
+    if (flags & DEODR_B200_ANTIALIASE_ERROR) {
+        if (!io->obs) return set_error(DEODR_B200_EINVAL, "obs_ptr is NULL");
+        if (!io->err_buffer) return set_error(DEODR_B200_EINVAL, "err_buffer_ptr is NULL");
+    }
+    return DEODR_B200_OK;
+}
+
+// Lanes of a multi-view call: lane 0 is the caller's stream, lanes > 0 are forked from it / joined to it.
+static void open_lanes(DeodrWorkspace *ws, cudaStream_t st, int used) {
+    ws->lanes[0].main = st;
+    if (used <= 1) return;
+    cudaEventRecord(ws->lanes[0].ev_begin, st);
+    for (int l = 1; l < used; l++) cudaStreamWaitEvent(ws->lanes[l].main, ws->lanes[0].ev_begin, 0);
+}
+static void close_lanes(DeodrWorkspace *ws, cudaStream_t st, int used) {
+    for (int l = 1; l < used; l++) {
+        cudaEventRecord(ws->lanes[l].ev_end, ws->lanes[l].main);
+        cudaStreamWaitEvent(st, ws->lanes[l].ev_end, 0);
+    }
+}
+static int lanes_for(const DeodrWorkspace *ws, int n_views) {
+    if (!ws->overlap || n_views <= 1) return 1;
+    return n_views < ws->num_lanes ? n_views : ws->num_lanes;
+}
+
+static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneView *views, const DeodrViewIO *io,
+                             double sigma, int flags, void *stream, bool check_indices) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    if (n_views < 0 || (n_views > 0 && (!views || !io))) return set_error(DEODR_B200_EINVAL, "bad view list");
+    for (int i = 0; i < n_views; i++)
+        if (int rc = check_forward_args(&views[i], &io[i], sigma, flags)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ws->device));
+    const bool capturing = stream_is_capturing(st);
+    const bool deferred = ws->deferred || capturing;
+    std::vector<ViewSlot *> slots(n_views);
+    std::vector<SceneView> scenes(n_views);
+    // ---- plans first (a plan needs the device: not possible while capturing)
+    for (int i = 0; i < n_views; i++) {
+        if (int rc = get_slot(ws, i, &slots[i])) return rc;
+        memcpy(&scenes[i], &views[i], sizeof(SceneView));
+        ViewSlot *v = slots[i];
+        if (v->pending && !capturing) {  // deferred mode: an unread verdict of an earlier pass
+            bool overflow;
+            if (int rc = read_verdict(ws, v, st, &overflow)) return rc;
+        }
+        v->fwd_valid = 0;
+        if (!capturing) {
+            if (int rc = prepare_slot(ws, v, scenes[i], sigma)) return rc;
+        } else if (!v->plan.valid || v->plan.T != scenes[i].nb_triangles || v->plan.H != scenes[i].height ||
+                   v->plan.W != scenes[i].width || v->plan.edges_possible != (sigma > 0)) {
+            return set_error(DEODR_B200_EINVAL,
+                             "stream capture needs a plan: run the same views once outside the capture first");
+        }
+        if (!v->plan.valid)
+            if (int rc = build_plan(ws, v, scenes[i], sigma, st, check_indices)) return rc;
+    }
+    // ---- enqueue every view, round-robin over the lanes
+    const int used = lanes_for(ws, n_views);
+    open_lanes(ws, st, used);
+    for (int i = 0; i < n_views; i++) {
+        ViewSlot *v = slots[i];
+        if (int rc = enqueue_forward(ws, v, ws->lanes[i % used], scenes[i], io[i], sigma, flags, check_indices)) return rc;
+        v->generation = ++ws->generation_counter;
+        v->sigma = sigma;
+        v->fwd_C = scenes[i].nb_colors;
+        v->fwd_flags = flags;
+        v->fwd_scene = views[i];
+        v->fwd_io = io[i];
+        v->fwd_check_indices = check_indices;
+        v->fwd_valid = 1;
+    }
+    close_lanes(ws, st, used);
+    if (deferred) return DEODR_B200_OK;
+    // ---- verdicts: every pass is already queued, the device does not wait for this
+    for (int i = 0; i < n_views; i++) {
+        ViewSlot *v = slots[i];
+        bool overflow = false;
+        if (int rc = read_verdict(ws, v, st, &overflow)) return rc;
+        if (check_indices)
+            if (int rc = bad_index_error(v)) { v->fwd_valid = 0; return rc; }
+        if (!overflow) continue;
+        // the lists outgrew the plan (the kernels of that pass returned at once): new plan, same pass again
+        if (int rc = build_plan(ws, v, scenes[i], sigma, st, check_indices)) return rc;
+        ws->lanes[0].main = st;
+        if (int rc = enqueue_forward(ws, v, ws->lanes[0], scenes[i], io[i], sigma, flags, check_indices)) return rc;
+        if (int rc = read_verdict(ws, v, st, &overflow)) return rc;
+        if (overflow) return set_error(DEODR_B200_ECUDA, "forward pass overflowed a freshly built plan (internal error)");
+        v->fwd_valid = 1;
+    }
+    return DEODR_B200_OK;
+}
+
+static int render_b_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneView *views, const DeodrViewIO *io,
+                               const DeodrGrads *grads, double sigma, int flags, void *stream) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    if (n_views < 0 || (n_views > 0 && (!views || !io || !grads))) return set_error(DEODR_B200_EINVAL, "bad view list");
+    const bool err_mode = (flags & DEODR_B200_ANTIALIASE_ERROR) != 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ws->device));
+    const bool capturing = stream_is_capturing(st);
+    for (int i = 0; i < n_views; i++) {
+        if (int rc = validate_view(&views[i], true)) return rc;
+        const DeodrViewIO &o = io[i];
+        if (!o.z_buffer || !o.owner) return set_error(DEODR_B200_EINVAL, "z_buffer / owner is NULL");
+        if (err_mode) {
+            if (!o.err_buffer_b) return set_error(DEODR_B200_EINVAL, "err_buffer_b_ptr is NULL");
+            if (!o.obs) return set_error(DEODR_B200_EINVAL, "obs_ptr is NULL");
+            if (!o.image) return set_error(DEODR_B200_EINVAL, "image_ptr is NULL");
+        } else if (!o.image_b) {
+            return set_error(DEODR_B200_EINVAL, "image_b_ptr is NULL");
+        }
+        const DeodrGrads &g = grads[i];
+        if ((views[i].nb_vertices > 0 && (!g.ij_b || !g.colors_b || !g.shade_b)) || (views[i].nb_uv > 0 && !g.uv_b))
+            return set_error(DEODR_B200_EINVAL, "ij_b / colors_b / uv_b / shade_b must be provided");
+        if (i >= (int)ws->slots.size() || !ws->slots[i])
+            return set_error(DEODR_B200_EINVAL, "render_b must follow render on the same workspace, scene and sigma");
+        const ViewSlot *v = ws->slots[i];
+        if (!v->fwd_valid || v->sigma != sigma || v->plan.T != views[i].nb_triangles || v->plan.H != views[i].height ||
+            v->plan.W != views[i].width || v->fwd_C != views[i].nb_colors || v->fwd_io.z_buffer != o.z_buffer ||
+            v->fwd_io.owner != o.owner || ((v->fwd_flags ^ flags) & DEODR_B200_ANTIALIASE_ERROR))
+            return set_error(DEODR_B200_EINVAL,
+                             "render_b must follow render on the same workspace slot, scene, sigma, mode and "
+                             "z_buffer / owner arrays");
+    }
+    if (err_mode && !capturing)
+        for (int i = 0; i < n_views; i++) {
+            ViewSlot *v = ws->slots[i];
+            const size_t need = (size_t)views[i].height * views[i].width * views[i].nb_colors * sizeof(float);
+            if (v->error_image_b.ensure(need, &ws->bytes)) return DEODR_B200_ECUDA;
+        }
+    for (int i = 0; i < n_views; i++) {  // accumulators (not while capturing: a warm-up pass has sized them)
+        ViewSlot *v = ws->slots[i];
+        if (v->plan.cap_edges > 0) {
+            const size_t need = (size_t)v->plan.cap_edges * edge_acc_stride(views[i].nb_colors) * sizeof(double);
+            if (need > v->edge_acc.bytes) {
+                if (capturing) return set_error(DEODR_B200_EINVAL, "stream capture needs a warm-up pass outside the capture");
+                if (v->edge_acc.ensure(need, &ws->bytes)) return DEODR_B200_ECUDA;
+            }
+        }
+    }
+    const int used = lanes_for(ws, n_views);
+    open_lanes(ws, st, used);
+    for (int i = 0; i < n_views; i++) {
+        ViewSlot *v = ws->slots[i];
+        SceneView s;
+        memcpy(&s, &views[i], sizeof(s));
+        Lane &lane = ws->lanes[i % used];
+        deodr_launch_backward(ws, v, lane, s, io[i], sigma, flags, grads[i]);
+    }
+    close_lanes(ws, st, used);
+    CUDA_TRY(cudaGetLastError());
+    return DEODR_B200_OK;
+}
+
 extern "C" {
 
 const char *deodr_b200_last_error(void) { return deodr_error_buffer(); }
-const char *deodr_b200_version(void) { return "deodr_b200 0.1 (sm_100a)"; }
+const char *deodr_b200_version(void) { return "deodr_b200 0.2 (sm_100a)"; }
 
 const char *deodr_b200_phase_name(int phase) {
-    static const char *names[] = {"bin_count", "edge_order",    "bin_fill",     "edge_tile_sort", "tile_z",       "shade",
-                                  "edge_fwd",  "small_tri_bwd", "interior_bwd", "edge_bwd",       "edge_finalize"};
+    static const char *names[] = {"plan",     "edge_bin",      "bin",          "edge_tile_sort", "tile_z",       "shade",
+                                  "edge_fwd", "small_tri_bwd", "interior_bwd", "edge_bwd",       "edge_finalize"};
     return phase >= 0 && phase < DEODR_B200_PH_COUNT ? names[phase] : "?";
 }
 
@@ -958,15 +1050,22 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
     DeodrWorkspace *ws = new (std::nothrow) DeodrWorkspace();
     if (!ws) return set_error(DEODR_B200_ENOMEM, "out of host memory");
     ws->device = device;
-    CUDA_TRY(cudaMallocHost(&ws->host_totals, 32 * sizeof(int)));
-    memset(ws->host_totals, 0, 32 * sizeof(int));
+    CUDA_TRY(cudaMallocHost(&ws->host_scratch, 32 * sizeof(int)));
+    memset(ws->host_scratch, 0, 32 * sizeof(int));
     CUDA_TRY(cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
     ws->overlap = !(getenv("DEODR_B200_SERIAL") && atoi(getenv("DEODR_B200_SERIAL")));
-    for (int i = 0; i < 2; i++) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&ws->aux[i], cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_join[i], cudaEventDisableTiming));
+    if (const char *e = getenv("DEODR_B200_LANES")) ws->num_lanes = atoi(e) < 1 ? 1 : (atoi(e) > MAX_LANES ? MAX_LANES : atoi(e));
+    for (int l = 0; l < MAX_LANES; l++) {
+        Lane &lane = ws->lanes[l];
+        if (l > 0) CUDA_TRY(cudaStreamCreateWithFlags(&lane.main, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&lane.aux[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_join[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_begin, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_end, cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
     if (ws->scalars.ensure(8 * sizeof(int), &ws->bytes)) return DEODR_B200_ECUDA;
     if (!sm_count_cached) cudaDeviceGetAttribute(&sm_count_cached, cudaDevAttrMultiProcessorCount, device);
     *out = ws;
@@ -976,30 +1075,62 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
 void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    DevBuf *bufs[] = {&ws->zeroed, &ws->large_tiles, &ws->edge_tiles, &ws->small_offset, &ws->small_recs, &ws->small_ids, &ws->large_ids, &ws->tri_offset, &ws->tri_refs, &ws->edge_ids,
-                      &ws->edge_ids_tmp, &ws->edge_rank, &ws->edge_recs,
-                      &ws->edge_keys_in, &ws->edge_keys_out, &ws->edge_sorted, &ws->cub_temp,
-                      &ws->edge_offset, &ws->edge_refs_tmp, &ws->edge_refs, &ws->edge_spans, &ws->scalars,
-                      &ws->tie_pairs, &ws->edge_acc, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
+    cudaDeviceSynchronize();
+    for (ViewSlot *v : ws->slots) free_slot(v);
+    DevBuf *bufs[] = {&ws->scalars, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
                       &ws->h_colors, &ws->h_shade, &ws->h_edgeflags, &ws->h_textured, &ws->h_shaded, &ws->h_texture,
                       &ws->h_background, &ws->h_image, &ws->h_z, &ws->h_owner, &ws->h_image_b,
-                      &ws->h_grads};
-    for (DevBuf *b : bufs)
-        if (b->ptr) cudaFree(b->ptr);
+                      &ws->h_grads, &ws->h_obs, &ws->h_err, &ws->h_err_b};
+    for (DevBuf *b : bufs) b->release();
     deodr_host_path_destroy(ws);
-    if (ws->host_totals) cudaFreeHost(ws->host_totals);
+    if (ws->host_scratch) cudaFreeHost(ws->host_scratch);
     for (cudaEvent_t e : ws->ev_start) cudaEventDestroy(e);
     for (cudaEvent_t e : ws->ev_stop) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) {
-        if (ws->aux[i]) cudaStreamDestroy(ws->aux[i]);
-        if (ws->ev_join[i]) cudaEventDestroy(ws->ev_join[i]);
+    for (int l = 0; l < MAX_LANES; l++) {
+        Lane &lane = ws->lanes[l];
+        if (l > 0 && lane.main) cudaStreamDestroy(lane.main);
+        for (int i = 0; i < 2; i++) {
+            if (lane.aux[i]) cudaStreamDestroy(lane.aux[i]);
+            if (lane.ev_join[i]) cudaEventDestroy(lane.ev_join[i]);
+        }
+        if (lane.ev_fork) cudaEventDestroy(lane.ev_fork);
+        if (lane.ev_begin) cudaEventDestroy(lane.ev_begin);
+        if (lane.ev_end) cudaEventDestroy(lane.ev_end);
     }
-    if (ws->ev_fork) cudaEventDestroy(ws->ev_fork);
     delete ws;
 }
 
 int64_t deodr_b200_workspace_bytes(const DeodrWorkspace *ws) { return ws ? ws->bytes : 0; }
 int64_t deodr_b200_workspace_launches(const DeodrWorkspace *ws) { return ws ? ws->launches : 0; }
+
+int deodr_b200_workspace_set_deferred(DeodrWorkspace *ws, int on) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    ws->deferred = on != 0;
+    return DEODR_B200_OK;
+}
+
+int deodr_b200_workspace_status(DeodrWorkspace *ws) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    CUDA_TRY(cudaDeviceSynchronize());  // every pending pass has raised its flag after this
+    int overflowed = 0;
+    for (ViewSlot *v : ws->slots) {
+        if (!v || !v->pending) continue;
+        bool overflow = false;
+        if (int rc = read_verdict(ws, v, (cudaStream_t)0, &overflow)) return rc;
+        if (overflow) overflowed++;
+    }
+    if (overflowed)
+        return set_error(DEODR_B200_EREPLAN,
+                         "a forward pass overflowed the lists its plan had reserved: its results are void, the plan has "
+                         "been dropped - run the pass again (outside a stream capture) to rebuild it");
+    return DEODR_B200_OK;
+}
+
+int64_t deodr_b200_view_generation(const DeodrWorkspace *ws, int view) {
+    if (!ws || view < 0 || view >= (int)ws->slots.size() || !ws->slots[view]) return 0;
+    return ws->slots[view]->generation;
+}
 
 int deodr_b200_check_scene(DeodrWorkspace *ws, const DeodrSceneView *scene, void *stream) {
     if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
@@ -1008,260 +1139,58 @@ int deodr_b200_check_scene(DeodrWorkspace *ws, const DeodrSceneView *scene, void
     CUDA_TRY(cudaSetDevice(ws->device));
     SceneView s;
     memcpy(&s, scene, sizeof(s));
-    int *flag = ws->scalars.as<int>() + 4;  // private scratch (not the forward pass's zeroed block)
+    int *flag = ws->scalars.as<int>();
     CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
     if (s.nb_triangles > 0) {
         k_check_scene<<<grid_for(3 * (size_t)s.nb_triangles, 256), 256, 0, st>>>(s, flag);
         ws->launches++;
     }
-    CUDA_TRY(cudaMemcpyAsync(ws->host_totals + 4, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->host_scratch, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (ws->host_totals[4] & 1) return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
-    if (ws->host_totals[4] & 2) return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
+    if (ws->host_scratch[0] & 1) return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
+    if (ws->host_scratch[0] & 2) return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
     return DEODR_B200_OK;
+}
+
+int deodr_b200_render_views(DeodrWorkspace *ws, int n_views, const DeodrSceneView *views, const DeodrViewIO *io,
+                            double sigma, int flags, void *stream) {
+    return render_views_impl(ws, n_views, views, io, sigma, flags, stream, false);
+}
+
+int deodr_b200_render_b_views(DeodrWorkspace *ws, int n_views, const DeodrSceneView *views, const DeodrViewIO *io,
+                              const DeodrGrads *grads, double sigma, int flags, void *stream) {
+    return render_b_views_impl(ws, n_views, views, io, grads, sigma, flags, stream);
 }
 
 int deodr_b200_render(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, float *image, double *z_buffer,
                       int32_t *owner, int32_t *face_id, void *stream) {
-    return deodr_render_impl(ws, scene, sigma, image, z_buffer, owner, face_id, stream, false);
+    DeodrViewIO io;
+    memset(&io, 0, sizeof(io));
+    io.image = image;
+    io.z_buffer = z_buffer;
+    io.owner = owner;
+    io.face_id = face_id;
+    return render_views_impl(ws, 1, scene, &io, sigma, 0, stream, false);
 }
-
-}  // extern "C"
-
-int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, float *image, double *z_buffer,
-                      int32_t *owner, int32_t *face_id, void *stream, bool check_indices) {
-    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
-    if (int rc = validate_view(scene, false)) return rc;
-    if (!image) return set_error(DEODR_B200_EINVAL, "image_ptr is NULL");
-    if (!z_buffer) return set_error(DEODR_B200_EINVAL, "z_buffer_ptr is NULL");
-    if (!owner) return set_error(DEODR_B200_EINVAL, "owner is NULL");
-    if (!(sigma >= 0)) return set_error(DEODR_B200_EINVAL, "sigma must be >= 0");
-    cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(ws->device));
-    SceneView s;
-    memcpy(&s, scene, sizeof(s));
-    ws->fwd_valid = 0;
-    const int T = s.nb_triangles;
-    ws->tiles_x = (s.width + TS - 1) / TS;
-    ws->tiles_y = (s.height + TS - 1) / TS;
-    ws->num_tiles = ws->tiles_x * ws->tiles_y;
-    const int nt = ws->num_tiles;
-    // one zero-initialised block: [scalars(16) | small_count | small_cursor | large_count | large_cursor | edge_count |
-    // edge_cursor], (nt+1) ints each
-    const size_t tile_ints = (size_t)nt + 1;
-    const size_t tile_bytes = tile_ints * sizeof(int);
-    int rc = 0;
-    rc |= ws->zeroed.ensure((16 + 6 * tile_ints) * sizeof(int), &ws->bytes);
-    rc |= ws->small_offset.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->large_tiles.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->edge_tiles.ensure(tile_bytes, &ws->bytes);
-    ws->edge_tiles_ptr = ws->edge_tiles.as<int>();
-    rc |= ws->tri_offset.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->edge_offset.ensure(tile_bytes, &ws->bytes);
-    rc |= ws->edge_ids.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
-    rc |= ws->edge_keys_in.ensure(((size_t)3 * T + 4) * 8, &ws->bytes);
-    rc |= ws->edge_rank.ensure(((size_t)3 * T + 4) * sizeof(int), &ws->bytes);
-    rc |= ws->small_ids.ensure(((size_t)T + 4) * sizeof(int), &ws->bytes);
-    rc |= ws->large_ids.ensure(((size_t)T + 4) * sizeof(int), &ws->bytes);
-    // one (own, bown) slot per pixel: the exact-tie table can never overflow, so the adjoint needs no read-back
-    if (ws->tie_capacity < s.height * s.width) {
-        ws->tie_capacity = s.height * s.width;
-        rc |= ws->tie_pairs.ensure((size_t)2 * ws->tie_capacity * sizeof(int), &ws->bytes);
-    }
-    if (rc) return DEODR_B200_ECUDA;
-    int *scal = ws->zeroed.as<int>();
-    int *small_count = scal + 16, *small_cursor = small_count + tile_ints, *large_count = small_cursor + tile_ints,
-        *large_cursor = large_count + tile_ints, *edge_count_buf = large_cursor + tile_ints,
-        *edge_cursor = edge_count_buf + tile_ints;
-    ws->scal = scal;
-    ws->edge_count_ptr = edge_count_buf;
-    EdgeList edges{scal + 1, ws->edge_ids.as<int>(), (uint64_t *)ws->edge_keys_in.ptr, ws->edge_rank.as<int>()};
-    TriBins bins{small_count, ws->small_offset.as<int>(), small_cursor, nullptr,
-                 large_count, ws->tri_offset.as<int>(), large_cursor, nullptr};
-    TriLists lists{scal + 6, ws->small_ids.as<int>(), scal + 7, ws->large_ids.as<int>()};
-
-    // ---- count pass + scans (triangles and silhouette edges together), then the ONE host read-back of the sizes
-    {
-        PhaseTimer timer(ws, DEODR_B200_PH_BIN_COUNT, st);
-        CUDA_TRY(cudaMemsetAsync(scal, 0, (16 + 6 * tile_ints) * sizeof(int), st));
-        if (T > 0) {
-            if (check_indices) {  // checkSceneValid (DR.h:2703-2714) on the device, before any index is dereferenced
-                k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, scal + 4);
-                ws->launches++;
-            }
-            k_bin_count<<<grid_for(T, 128), 128, 0, st>>>(s, sigma, ws->tiles_x, bins, lists, edges, edge_count_buf,
-                                                          check_indices ? scal + 4 : nullptr, scal + 12);
-            ws->launches++;
-        }
-        ScanJob job{{small_count, large_count, edge_count_buf},
-                    {ws->small_offset.as<int>(), ws->tri_offset.as<int>(), ws->edge_offset.as<int>()},
-                    {5, 0, 2},
-                    {nullptr, ws->large_tiles.as<int>(), ws->edge_tiles.as<int>()},
-                    {15, 8, 9},
-                    {0, 0, EDGE_CHUNK},
-                    {15, 15, 10}};
-        ws->totals_seq = ws->totals_seq == 0x7fffffff ? 1 : ws->totals_seq + 1;
-        k_scan_tiles<<<3, 1024, SCAN_SMEM, st>>>(job, nt, scal, ws->host_totals, ws->totals_seq);
-        ws->launches++;
-    }
-    {
-        // the one host read-back of the forward: poll the flag the scan kernel raises in pinned memory (a few
-        // microseconds after the kernel's last store) instead of a copy + stream synchronisation
-        volatile int *flag = ws->host_totals + 16;
-        for (unsigned spins = 1; *flag != ws->totals_seq; spins++) {
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
-            if ((spins & 0xfffu) == 0) {  // every few microseconds: has the stream drained (flag lost) or failed?
-                const cudaError_t q = cudaStreamQuery(st);
-                if (q == cudaSuccess) {
-                    if (*flag != ws->totals_seq) {  // not expected; fall back to an explicit copy
-                        CUDA_TRY(cudaMemcpyAsync(ws->host_totals, scal, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
-                        CUDA_TRY(cudaStreamSynchronize(st));
-                    }
-                    break;
-                }
-                if (q != cudaErrorNotReady) return set_error(DEODR_B200_ECUDA, "forward pass failed: %s", cudaGetErrorString(q));
-            }
-        }
-        __atomic_thread_fence(__ATOMIC_ACQUIRE);
-    }
-    if (check_indices && (ws->host_totals[4] & 1))
-        return set_error(DEODR_B200_EINVAL, "scene.faces value greater than scene.nb_vertices");
-    if (check_indices && (ws->host_totals[4] & 2))
-        return set_error(DEODR_B200_EINVAL, "scene.faces_uv value greater than scene.nb_uv");
-    const int large_total = ws->host_totals[0], E = ws->host_totals[1], edge_total = ws->host_totals[2],
-              small_total = ws->host_totals[5];
-    ws->num_edges = E;
-    ws->num_small = ws->host_totals[6];
-    ws->num_large = ws->host_totals[7];
-    ws->num_large_tiles = ws->host_totals[8];
-    ws->num_edge_tiles = E > 0 ? ws->host_totals[9] : 0;
-    ws->num_heavy_edge_tiles = E > 0 ? ws->host_totals[10] : 0;
-    ws->any_textured = ws->host_totals[12] != 0;
-    rc = 0;
-    rc |= ws->small_recs.ensure(((size_t)small_total + 1) * sizeof(PreRec), &ws->bytes);
-    rc |= ws->tri_refs.ensure(((size_t)large_total + 4) * sizeof(int), &ws->bytes);
-    rc |= ws->edge_sorted.ensure(((size_t)E + 4) * sizeof(int), &ws->bytes);
-    rc |= ws->edge_recs.ensure(((size_t)E + 1) * sizeof(EdgeRec), &ws->bytes);
-    rc |= ws->edge_refs_tmp.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
-    rc |= ws->edge_refs.ensure(((size_t)edge_total + 4) * sizeof(int), &ws->bytes);
-    rc |= ws->edge_spans.ensure(((size_t)edge_total + 4) * TS * sizeof(uint32_t), &ws->bytes);
-    if (rc) return DEODR_B200_ECUDA;
-    bins.small_recs = ws->small_recs.as<PreRec>();
-    bins.large_refs = ws->tri_refs.as<int>();
-    ws->bins = bins;
-
-    // ---- far-to-near order of the silhouette edges (DR.h:2781) + per-tile edge lists: a chain of its own (stream se)
-    // that overlaps the triangle fill, the z pass and the shading; joined before k_edge_fwd
-    bool first_fork = true;
-    cudaStream_t se = E > 0 ? fork_stream(ws, 0, st, &first_fork) : st;
-    if (E > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_ORDER, se);
-        if (E <= 65536) {
-            dim3 grid(grid_for(E, 256), grid_for(E, RANK_CHUNK));
-            k_rank_edges<<<grid, 256, 0, se>>>(edges, E, ws->edge_rank.as<int>());
-            k_scatter_edges<<<grid_for(E, 128), 128, 0, se>>>(s, edges, E, sigma, ws->edge_sorted.as<int>(),
-                                                               ws->edge_recs.as<EdgeRec>());
-            ws->launches += 2;
-        } else {
-            // large soups: two stable radix sorts (by id, then by depth key) give the same total order
-            rc = 0;
-            rc |= ws->edge_keys_out.ensure((size_t)E * 8, &ws->bytes);
-            rc |= ws->edge_ids_tmp.ensure((size_t)E * sizeof(int), &ws->bytes);
-            if (rc) return DEODR_B200_ECUDA;
-            auto *k_in = ws->edge_keys_in.as<unsigned long long>(), *k_out = ws->edge_keys_out.as<unsigned long long>();
-            int *i_in = ws->edge_ids.as<int>(), *i_tmp = ws->edge_ids_tmp.as<int>();
-            size_t temp1 = 0, temp2 = 0;
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, se));
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp2, k_out, k_in, i_tmp, i_in, E, 0, 64, se));
-            if (ws->cub_temp.ensure(temp1 > temp2 ? temp1 : temp2, &ws->bytes)) return DEODR_B200_ECUDA;
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp1, i_in, i_tmp, k_in, k_out, E, 0, 32, se));
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws->cub_temp.ptr, temp2, k_out, k_in, i_tmp,
-                                                     ws->edge_sorted.as<int>(), E, 0, 64, se));
-            k_edge_records<<<grid_for(E, 128), 128, 0, se>>>(s, ws->edge_sorted.as<int>(), E, sigma,
-                                                             ws->edge_recs.as<EdgeRec>());
-            ws->launches++;
-        }
-    }
-
-    // ---- per-tile edge lists: fill, then order every list by far-to-near rank
-    if (E > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, se);
-        k_bin_fill<<<grid_for(E, 128), 128, 0, se>>>(s, sigma, ws->tiles_x, 0, 0, bins, nullptr, 0, nullptr, 0,
-                                                     ws->edge_sorted.as<int>(), E, ws->edge_offset.as<int>(),
-                                                     edge_cursor, ws->edge_refs_tmp.as<int>());
-        ws->launches++;
-        if (ws->num_edge_tiles > 0) {
-            k_sort_tile_edges<<<ws->num_edge_tiles, 128, 0, se>>>(ws->edge_tiles.as<int>(), nt, ws->num_heavy_edge_tiles,
-                                                                  edge_count_buf,
-                                                                  ws->edge_offset.as<int>(),
-                                                                  ws->edge_refs_tmp.as<int>(), ws->edge_refs.as<int>());
-            ws->launches++;
-        }
-    }
-    // ---- triangle fill: pre-masked records of the small triangles, index lists of the large ones
-    if (T > 0) {
-        PhaseTimer timer(ws, DEODR_B200_PH_BIN_FILL, st);
-        const int small_blocks = grid_for(ws->num_small, 128), large_blocks = grid_for(ws->num_large, 128);
-        if (small_blocks + large_blocks > 0) {
-            k_bin_fill<<<small_blocks + large_blocks, 128, 0, st>>>(
-                s, sigma, ws->tiles_x, small_blocks, large_blocks, bins, ws->small_ids.as<int>(), ws->num_small,
-                ws->large_ids.as<int>(), ws->num_large, nullptr, 0, nullptr, nullptr, nullptr);
-            ws->launches++;
-        }
-    }
-
-    // ---- raster
-    TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
-    const int *edge_count = E > 0 ? edge_count_buf : nullptr;
-    const int C = s.nb_colors;
-    {
-    if (C == 1) launch_fwd<1>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
-    else if (C == 3) launch_fwd<3>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
-    else if (C <= 4) launch_fwd<4>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
-    else launch_fwd<16>(ws, s, sigma, edge_count, ties, image, z_buffer, owner, face_id, E > 0, st);
-    }
-    CUDA_TRY(cudaGetLastError());
-    ws->sigma = sigma;
-    ws->fwd_T = T; ws->fwd_H = s.height; ws->fwd_W = s.width; ws->fwd_C = C;
-    ws->fwd_valid = 1;
-    return DEODR_B200_OK;
-}
-
-extern "C" {
 
 int deodr_b200_render_b(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, const double *z_buffer,
                         const int32_t *owner, const float *image_b, const DeodrGrads *grads, void *stream) {
-    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
-    if (int rc = validate_view(scene, true)) return rc;
-    if (!z_buffer || !owner) return set_error(DEODR_B200_EINVAL, "z_buffer / owner is NULL");
-    if (!image_b) return set_error(DEODR_B200_EINVAL, "image_b_ptr is NULL");
     if (!grads) return set_error(DEODR_B200_EINVAL, "grads == NULL");
-    SceneView s;
-    memcpy(&s, scene, sizeof(s));
-    if (!ws->fwd_valid || ws->sigma != sigma || ws->fwd_T != s.nb_triangles || ws->fwd_H != s.height ||
-        ws->fwd_W != s.width || ws->fwd_C != s.nb_colors)
-        return set_error(DEODR_B200_EINVAL, "render_b must follow render on the same workspace, scene and sigma");
-    cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(ws->device));
-    int *scal = ws->scal;
-    const int E = ws->num_edges, C = s.nb_colors;
-    DeodrGrads g = *grads;
-    if ((s.nb_vertices > 0 && (!g.ij_b || !g.colors_b || !g.shade_b)) || (s.nb_uv > 0 && !g.uv_b))
-        return set_error(DEODR_B200_EINVAL, "ij_b / colors_b / uv_b / shade_b must be provided");
-    if (E > 0) {
-        size_t acc_bytes = (size_t)E * edge_acc_stride(C) * sizeof(double);
-        if (ws->edge_acc.ensure(acc_bytes, &ws->bytes)) return DEODR_B200_ECUDA;
-    }
-    TieTable ties{ws->tie_pairs.as<int>(), scal + 3, ws->tie_capacity};
-    const int *edge_count = E > 0 ? ws->edge_count_ptr : nullptr;
-    if (C == 1) launch_bwd<1>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
-    else if (C == 3) launch_bwd<3>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
-    else if (C <= 4) launch_bwd<4>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
-    else launch_bwd<16>(ws, s, sigma, edge_count, ties, z_buffer, owner, image_b, g, scal, st);
-    CUDA_TRY(cudaGetLastError());
-    return DEODR_B200_OK;
+    DeodrViewIO io;
+    memset(&io, 0, sizeof(io));
+    io.z_buffer = const_cast<double *>(z_buffer);
+    io.owner = const_cast<int32_t *>(owner);
+    io.image_b = image_b;
+    return render_b_views_impl(ws, 1, scene, &io, grads, sigma, 0, stream);
 }
 
 }  // extern "C"
+
+int deodr_render_checked(DeodrWorkspace *ws, const DeodrSceneView *scene, const DeodrViewIO *io, double sigma, int flags,
+                         void *stream) {
+    const bool was = ws->deferred;
+    ws->deferred = false;
+    const int rc = render_views_impl(ws, 1, scene, io, sigma, flags, stream, true);
+    ws->deferred = was;
+    return rc;
+}

@@ -143,13 +143,66 @@ DEODR_HD TileBox edge_tile_box(const double V[2][2], double sigma, int width, in
     return b;
 }
 
+// ---- the plan of a forward pass -----------------------------------------------------------------------------
+// Every per-tile list lives in a SEGMENT whose capacity was reserved by the plan (exclusive scan, with slack, of the
+// counts of an earlier pass over a scene of the same shape).  The forward pass appends with one atomic per item and
+// never waits for the host: an append that does not fit raises a bit of the verdict word instead of writing, every
+// later kernel of that forward returns at once when the word is non-zero, and the host - which reads the word from
+// pinned memory AFTER it has enqueued the whole pass - re-plans and re-runs (kernels.cu: build_plan / verify).
+enum {
+    OVF_SMALL = 1,      // pre-masked records of a tile
+    OVF_LARGE = 2,      // large-triangle references of a tile
+    OVF_EDGES = 4,      // silhouette edges of the view
+    OVF_EDGE_REFS = 8,  // edge references of a tile
+    OVF_TEXTURE = 16    // a textured triangle met by kernel instances compiled without the texture paths
+};
+
+// device scalars of one forward pass (zeroed together with the segment cursors, one memset)
+enum {
+    SC_OVERFLOW = 0,     // verdict word (OVF_* bits)
+    SC_EDGES = 1,        // silhouette edges appended
+    SC_SMALL = 2,        // drawn small triangles appended to the compact list
+    SC_TIES = 3,         // entries of the exact-tie table
+    SC_BAD_INDEX = 4,    // checkSceneValid: 1 = faces, 2 = faces_uv out of range
+    SC_TEXTURED = 5,     // the scene holds a textured (and shaded) triangle
+    SC_HEAVY_TILES = 6,  // edge tiles with more than one chunk of edges (front of the two-ended list)
+    SC_LIGHT_TILES = 7,  // the other edge tiles (back of the list)
+    SC_LARGE_TILES = 8,  // tiles that hold large triangles
+    SC_TICKET = 9,       // scan kernel: arrival counter of its CTAs
+    SC_TOTAL_SMALL = 10, // plan building: reserved record / reference totals (with slack)
+    SC_TOTAL_LARGE = 11,
+    SC_TOTAL_EDGE_REFS = 12,
+    SC_PLAN_LARGE_TILES = 14, // plan building: tiles with large triangles / with silhouette edges (launch hints)
+    SC_PLAN_EDGE_TILES = 15,
+    SC_WORDS = 32
+};
+
+struct TileSegments {
+    const int *offset;  // [tiles + 1] reserved by the plan
+    int *cursor;        // [tiles] items appended (or, in the count-only pass, counted) so far
+};
+
+DEODR_HD int segment_size(const TileSegments &seg, int t) {
+    const int cap = seg.offset[t + 1] - seg.offset[t], n = seg.cursor[t];
+    return n < cap ? n : cap;
+}
+
+// position of a new item of tile t, or -1 (verdict bit raised) when the segment is full
+template <class Env>
+DEODR_HD int segment_reserve(const TileSegments &seg, int t, int *verdict, int bit) {
+    const int pos = seg.offset[t] + Env::atomic_add(&seg.cursor[t], 1);
+    if (pos < seg.offset[t + 1]) return pos;
+    Env::atomic_or(verdict, bit);
+    return -1;
+}
+
 // Unordered list of the silhouette edges to overdraw (DR.h:2839-2853: sigma > 0, signedArea > 0, flag set), appended
-// by the count pass together with their depth-sum sort keys.
+// by the binning pass together with the depth-sum sort key of their triangle.
 struct EdgeList {
-    int *count;       // number of appended edges
+    int *count;       // number of appended edges (may exceed `capacity`: verdict bit OVF_EDGES)
     int *ids;         // 3 * triangle + n
     uint64_t *keys;   // depth_desc_key(sum of the triangle's vertex depths)
-    int *rank;        // zeroed at append time: k_rank_edges accumulates the far-to-near rank into it
+    int capacity;
 };
 
 DEODR_HD void gather_edge(const SceneView &s, int edge_id, double V[2][2]) {
@@ -166,18 +219,15 @@ DEODR_HD void gather_edge(const SceneView &s, int edge_id, double V[2][2]) {
 // triangle regime) get a pre-masked PreRec per tile they actually cover; LARGE ones are binned by index into every
 // tile of their bounding box and their row spans are computed by the tile CTA in parallel.
 struct TriBins {
-    int *small_count;         // count pass: upper bound (bounding box); fill pass: exact via small_cursor
-    const int *small_offset;
-    int *small_cursor;
+    TileSegments small;
     PreRec *small_recs;
-    int *large_count;
-    const int *large_offset;
-    int *large_cursor;
+    TileSegments large;
     int *large_refs;
+    int *verdict;  // scal + SC_OVERFLOW
 };
 
 // "small" = micro-triangle: at most 2 x 2 tiles and a bounding box that fits a 64-bit mask with a power-of-two row
-// stride (pixel <-> bit without a division), so that one thread can afford to walk it (fill pass, adjoint).
+// stride (pixel <-> bit without a division), so that one thread can afford to walk it (binning pass, adjoint).
 DEODR_HD int small_shift(int box_w) {  // log2 of the row stride
     int sh = 0;
     while ((1 << sh) < box_w) sh++;
@@ -185,52 +235,6 @@ DEODR_HD int small_shift(int box_w) {  // log2 of the row stride
 }
 DEODR_HD bool is_small(const TileBox &b, int box_w, int box_h) {
     return b.tx1 - b.tx0 <= 1 && b.ty1 - b.ty0 <= 1 && box_w <= 32 && (box_h << small_shift(box_w)) <= 64;
-}
-
-// Compacted index lists of the drawn triangles, appended by the count pass (arbitrary order): the fill pass and the
-// triangle-parallel adjoint run one thread per ENTRY, so that whole warps do similar work instead of idling on
-// culled triangles.
-struct TriLists {
-    int *num_small;
-    int *small_ids;
-    int *num_large;
-    int *large_ids;
-};
-
-// Count pass, one thread per triangle: tile counters of the triangle's bounding box (small / large); the triangle's
-// silhouette edges are appended to `edges` and counted into edge_tile_count.
-template <class Env>
-DEODR_HD void bin_count_triangle(const SceneView &s, int k, double sigma, int tiles_x, TriBins bins, TriLists lists,
-                                 EdgeList edges, int *edge_tile_count) {
-    uint32_t vid[3];
-    double V[3][2], Zv[3];
-    gather_tri(s, k, vid, V, Zv);
-    TriClass c = classify_tri(s, k, V, Zv);
-    if (sigma > 0 && c.area_positive) {
-        for (int n = 0; n < 3; n++) {
-            if (!s.edgeflags[3 * k + n]) continue;
-            int slot = Env::atomic_add(edges.count, 1);
-            edges.ids[slot] = 3 * k + n;
-            edges.keys[slot] = depth_desc_key(c.sum_depth);
-            edges.rank[slot] = 0;
-            double E[2][2];
-            gather_edge(s, 3 * k + n, E);
-            TileBox b = edge_tile_box(E, sigma, s.width, s.height);
-            for (int ty = b.ty0; ty <= b.ty1; ty++)
-                for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&edge_tile_count[ty * tiles_x + tx], 1);
-        }
-    }
-    if (!c.drawn) return;
-    remove_offset(V, 3, pixel_offset(s));
-    int box_w, box_h;
-    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height, &box_w, &box_h);
-    if (b.tx0 > b.tx1) return;  // off screen
-    const bool small = is_small(b, box_w, box_h);
-    int *count = small ? bins.small_count : bins.large_count;
-    for (int ty = b.ty0; ty <= b.ty1; ty++)
-        for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&count[ty * tiles_x + tx], 1);
-    if (small) lists.small_ids[Env::atomic_add(lists.num_small, 1)] = k;
-    else lists.large_ids[Env::atomic_add(lists.num_large, 1)] = k;
 }
 
 // 16-bit coverage mask of tile row y for one triangle (exact spans of rmath.h, clipped to the tile).
@@ -256,49 +260,29 @@ DEODR_HD uint32_t tri_pair_mask(const SceneView &s, const TriGeom &g, int y_firs
     return m;
 }
 
-// Fill pass, one thread per entry of the large list: the index goes to every tile of the bounding box.
 template <class Env>
-DEODR_HD void bin_fill_large(const SceneView &s, int k, int tiles_x, TriBins bins) {
-    double V[3][2];
-    for (int i = 0; i < 3; i++) {
-        uint32_t v = s.faces[3 * k + i];
-        V[i][0] = s.ij[2 * (size_t)v];
-        V[i][1] = s.ij[2 * (size_t)v + 1];
-    }
-    remove_offset(V, 3, pixel_offset(s));
-    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
-    for (int ty = b.ty0; ty <= b.ty1; ty++)
-        for (int tx = b.tx0; tx <= b.tx1; tx++) {
-            int t = ty * tiles_x + tx;
-            bins.large_refs[bins.large_offset[t] + Env::atomic_add(&bins.large_cursor[t], 1)] = k;
-        }
-}
-
-// Fill pass, one thread per entry of the small list: exact coverage masks of every tile the triangle really covers.
-// SIMT note: the loop runs over the triangle's ROWS (consecutive for every lane, so the lanes of a warp execute the
-// expensive span body together) and scatters each span into the masks of the <= 2 tile columns; a (tile, row-pair)
-// loop would make every lane wait for the bodies of all the others.
-template <class Env>
-DEODR_HD void bin_flush_small(int k, const TriGeom &g, int tiles_x, int tx, int ty, const uint32_t *mask, TriBins bins) {
+DEODR_HD void bin_flush_small(int k, const TriGeom &g, int tiles_x, int tx, int ty, const uint32_t *mask,
+                              const TriBins &bins) {
     uint32_t any = 0;
     for (int p = 0; p < TS / 2; p++) any |= mask[p];
     if (!any) return;  // the bounding box touches the tile, the triangle does not
+    const int pos = segment_reserve<Env>(bins.small, ty * tiles_x + tx, bins.verdict, OVF_SMALL);
+    if (pos < 0) return;
     PreRec rec;
     for (int p = 0; p < TS / 2; p++) rec.mask[p] = mask[p];
     canonical_plane(g.zp, rec.zp);
     rec.id = k | SMALL_FLAG;
     rec.pad = 0;
-    const int t = ty * tiles_x + tx;
-    bins.small_recs[bins.small_offset[t] + Env::atomic_add(&bins.small_cursor[t], 1)] = rec;
+    bins.small_recs[pos] = rec;
 }
 
+// Exact coverage masks of every tile a SMALL triangle really covers, one pre-masked record per such tile.
+// SIMT note: the loop runs over the triangle's ROWS (consecutive for every lane, so the lanes of a warp execute the
+// expensive span body together) and scatters each span into the masks of the <= 2 tile columns; a (tile, row-pair)
+// loop would make every lane wait for the bodies of all the others.
 template <class Env>
-DEODR_HD void bin_fill_small(const SceneView &s, int k, int tiles_x, TriBins bins) {
-    uint32_t vid[3];
-    double V[3][2], Zv[3];
-    gather_tri(s, k, vid, V, Zv);
-    remove_offset(V, 3, pixel_offset(s));
-    TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height);
+DEODR_HD void bin_small(const SceneView &s, int k, const double V[3][2], const double Zv[3], const TileBox &b,
+                        int tiles_x, const TriBins &bins) {
     TriGeom g;
     tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
     int y_first, y_last;
@@ -333,28 +317,98 @@ DEODR_HD void bin_fill_small(const SceneView &s, int k, int tiles_x, TriBins bin
             if (b.tx0 + c <= b.tx1) bin_flush_small<Env>(k, g, tiles_x, b.tx0 + c, cur_ty, mask[c], bins);
 }
 
-// Far-to-near rank of appended edge i = number of edges that precede it in the reference order: descending depth sum
-// (DR.h:2656-2662, 2781), ties by ascending (triangle, edge) id.  O(E) per thread; E is O(sqrt(T)) for meshes.
-DEODR_HD int edge_rank(int i, int n, const uint64_t *keys, const int *ids) {
-    const uint64_t key = keys[i];
-    const int id = ids[i];
-    int rank = 0;
-    for (int j = 0; j < n; j++) rank += (keys[j] < key) || (keys[j] == key && ids[j] < id);
-    return rank;
+// The binning pass, one thread per triangle: ONE gather of its vertices serves the classification (DR.h:2751-2779), the
+// append of its silhouette edges, and - for a drawn triangle - its pre-masked records (small) or tile references
+// (large).  COUNT_ONLY is the plan-building variant: the same decisions, but it only counts the items per tile
+// (bounding-box tiles for the small triangles: an upper bound of the records the real pass emits) and the edges per
+// tile of their band, so that the plan can reserve the segments.
+template <class Env, bool COUNT_ONLY>
+DEODR_HD void bin_triangle(const SceneView &s, int k, double sigma, int tiles_x, const TriBins &bins, int *num_small,
+                           int *small_ids, const EdgeList &edges, int *edge_tile_count) {
+    uint32_t vid[3];
+    double V[3][2], Zv[3];
+    gather_tri(s, k, vid, V, Zv);
+    const TriClass c = classify_tri(s, k, V, Zv);
+    if (sigma > 0 && c.area_positive) {
+        for (int n = 0; n < 3; n++) {
+            if (!s.edgeflags[3 * k + n]) continue;
+            const int slot = Env::atomic_add(edges.count, 1);
+            if (COUNT_ONLY) {
+                double E[2][2];
+                for (int i = 0; i < 2; i++) {
+                    E[i][0] = V[edge_vertex(n, i)][0];
+                    E[i][1] = V[edge_vertex(n, i)][1];
+                }
+                remove_offset(E, 2, pixel_offset(s));
+                const TileBox b = edge_tile_box(E, sigma, s.width, s.height);
+                for (int ty = b.ty0; ty <= b.ty1; ty++)
+                    for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&edge_tile_count[ty * tiles_x + tx], 1);
+            } else if (slot < edges.capacity) {
+                edges.ids[slot] = 3 * k + n;
+                edges.keys[slot] = depth_desc_key(c.sum_depth);
+            } else {
+                Env::atomic_or(bins.verdict, OVF_EDGES);
+            }
+        }
+    }
+    if (!c.drawn) return;
+    remove_offset(V, 3, pixel_offset(s));
+    int box_w, box_h;
+    const TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height, &box_w, &box_h);
+    if (b.tx0 > b.tx1) return;  // off screen
+    const bool small = is_small(b, box_w, box_h);
+    if (COUNT_ONLY) {
+        int *count = small ? bins.small.cursor : bins.large.cursor;
+        for (int ty = b.ty0; ty <= b.ty1; ty++)
+            for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&count[ty * tiles_x + tx], 1);
+        return;
+    }
+    if (small) {
+        // the compact list of the drawn small triangles is what the triangle-parallel adjoint walks (capacity T)
+        small_ids[Env::atomic_add(num_small, 1)] = k;
+        bin_small<Env>(s, k, V, Zv, b, tiles_x, bins);
+    } else {
+        for (int ty = b.ty0; ty <= b.ty1; ty++)
+            for (int tx = b.tx0; tx <= b.tx1; tx++) {
+                const int pos = segment_reserve<Env>(bins.large, ty * tiles_x + tx, bins.verdict, OVF_LARGE);
+                if (pos >= 0) bins.large_refs[pos] = k;
+            }
+    }
 }
 
-// Fill pass, one thread per silhouette edge in far-to-near order (rank r): append r to the tiles of the edge band.
+// Edge pass, one thread per appended silhouette edge (slot = position in the unordered list): the band stencil record
+// (DR.h:1366-1460 + z plane + end-point colours) is built ONCE per forward, and the slot goes to every tile of the band.
+struct EdgeBins {
+    TileSegments seg;
+    int *refs;
+    int *verdict;
+};
+
 template <class Env>
-DEODR_HD void bin_fill_edge(const SceneView &s, int edge_id, int rank, double sigma, int tiles_x, const int *tile_offset,
-                            int *tile_cursor, int *refs) {
+DEODR_HD void bin_edge(const SceneView &s, int slot, double sigma, int tiles_x, const EdgeList &edges,
+                       const EdgeBins &bins, EdgeRec *recs) {
+    const int id = edges.ids[slot];
     double V[2][2];
-    gather_edge(s, edge_id, V);
-    TileBox b = edge_tile_box(V, sigma, s.width, s.height);
+    edge_record(s, id, slot, edges.keys[slot], sigma, &recs[slot], V);
+    const TileBox b = edge_tile_box(V, sigma, s.width, s.height);
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) {
-            int t = ty * tiles_x + tx;
-            refs[tile_offset[t] + Env::atomic_add(&tile_cursor[t], 1)] = rank;
+            const int pos = segment_reserve<Env>(bins.seg, ty * tiles_x + tx, bins.verdict, OVF_EDGE_REFS);
+            if (pos >= 0) bins.refs[pos] = slot;
         }
+}
+
+// Far-to-near position of item i of a tile's edge list: the reference walks the edges in descending order of their
+// triangle's depth sum (DR.h:2656-2662, 2781), ties by ascending (triangle, edge) id.  Only the RELATIVE order of the
+// edges that meet in a pixel matters, and those share the tile: no global sort.
+DEODR_HD int tile_edge_position(int i, int n, const int *refs, const EdgeRec *recs) {
+    const EdgeRec &mine = recs[refs[i]];
+    int pos = 0;
+    for (int j = 0; j < n; j++) {
+        const EdgeRec &o = recs[refs[j]];
+        pos += (o.key < mine.key) || (o.key == mine.key && o.id < mine.id);
+    }
+    return pos;
 }
 
 // ------------------------------------------------------------------------------------------- tile kernel phases
@@ -493,8 +547,9 @@ DEODR_HD void phase_tri_test(const SceneView &s, int tid, int n, Tile tile, cons
 
 // Phase S: background + owner colour.
 template <int MAXC>
-DEODR_HD void phase_shade(const SceneView &s, int x, int y, PixelState<MAXC> *p) {
+DEODR_HD void phase_shade(const SceneView &s, int x, int y, PixelState<MAXC> *p, float *w_out = nullptr) {
     const int C = s.nb_colors;
+    if (w_out) w_out[0] = w_out[1] = w_out[2] = 0.0f;
     if (p->own < 0) {
         if (s.background_image) {
             const float *bg = s.background_image + ((size_t)y * s.width + x) * C;
@@ -508,10 +563,11 @@ DEODR_HD void phase_shade(const SceneView &s, int x, int y, PixelState<MAXC> *p)
     tri_attr(s, p->own & TRI_INDEX_MASK, &t);
     PixelEval<MAXC> e;
     pixel_colour<MAXC>(s, t, x, y, p->z, &e, p->col);
+    if (w_out) { w_out[0] = e.w[0]; w_out[1] = e.w[1]; w_out[2] = e.w[2]; }  // G-buffer: interpolation weights
 }
 
-// Phase E1: the CTA fetches the records of the edges with far-to-near ranks list[0..n) (built once per forward pass by
-// k_edge_records: the stencil's sqrt / divisions are not redone per tile); 8-byte words, all threads cooperating.
+// Phase E1: the CTA fetches the records of the edges list[0..n) of its tile, in far-to-near order (built once per
+// forward pass by bin_edge: the stencil's sqrt / divisions are not redone per tile); 8-byte words, all threads.
 DEODR_HD void phase_edge_setup(int tid, int nthreads, int n, const int *list, const EdgeRec *edge_recs, TileShared *sh) {
     constexpr int WORDS = (int)(sizeof(EdgeRec) / 8);
     static_assert(sizeof(EdgeRec) % 8 == 0, "EdgeRec is copied as 8-byte words");
@@ -635,7 +691,7 @@ DEODR_HD void phase_edge_adjoint(const SceneView &s, int x, int y, int r, int n,
         if (!(ze < p.z)) continue;
         EdgeHit<MAXC> h;
         edge_hit<MAXC>(s, rec, x, y, ze, &h);
-        double *acc = edge_acc + (size_t)rec.rank * stride;
+        double *acc = edge_acc + (size_t)rec.slot * stride;
         const double T = h.T, omT = 1.0 - h.T;
         double T_B = 0;
         const double t3[3] = {(double)x, (double)y, 1.0};
@@ -771,7 +827,7 @@ DEODR_HD void phase_edge_adjoint_error(const SceneView &s, int x, int y, int r, 
         if (!(ze < p.z)) continue;
         EdgeHit<MAXC> h;
         edge_hit<MAXC>(s, rec, x, y, ze, &h);
-        double *acc = edge_acc + (size_t)rec.rank * stride;
+        double *acc = edge_acc + (size_t)rec.slot * stride;
         const double T = h.T, omT = 1.0 - h.T;
         const double Err = edge_residual<MAXC>(s, h, obs);
         const double prev = (a->err - omT * Err) / T;  // residual before this edge

@@ -331,20 +331,26 @@ DEODR_HD void flush_vertex_grads(const SceneView &s, const TriAttr &t, const Ver
 
 // ------------------------------------------------------------------------------------------------ edge records
 
-// Shared-memory record of one silhouette edge of a tile list.
+// Record of one silhouette edge: built once per forward pass (bin_edge), staged in shared memory by the tile kernels.
 struct EdgeRec {
     EdgeGeom g;
+    uint64_t key;     // depth_desc_key of the edge's triangle: ascending key = far to near (DR.h:2781)
     uint32_t vid[2], uvid[2];
-    int32_t rank;     // position in the far-to-near order (index into the sorted edge array / accumulators)
+    int32_t id;       // 3 * triangle + n: breaks the ties of the key
+    int32_t slot;     // position in the view's unordered edge list (index of the record and of its accumulators)
     uint8_t textured;
     uint8_t has_col;  // col[][] holds the end-point colours (C <= 4): no gathers in the blend loop
+    uint8_t pad[6];
     double inv_z[2];  // 1/z of the end points (perspective_correct only)
     float col[2][4];
 };
+static_assert(sizeof(EdgeRec) % 8 == 0, "EdgeRec is copied as 8-byte words");
 
-DEODR_HD void edge_record(const SceneView &s, int edge_id, int rank, double sigma, EdgeRec *r) {
+// V receives the two end points with the pixel-centre offset removed (what the band's tile box is computed from).
+DEODR_HD void edge_record(const SceneView &s, int edge_id, int slot, uint64_t key, double sigma, EdgeRec *r,
+                          double V[2][2]) {
     int k = edge_id / 3, n = edge_id - 3 * k;
-    double V[2][2], Zv[2];
+    double Zv[2];
     for (int i = 0; i < 2; i++) {
         int loc = edge_vertex(n, i);
         r->vid[i] = s.faces[3 * k + loc];
@@ -356,9 +362,12 @@ DEODR_HD void edge_record(const SceneView &s, int edge_id, int rank, double sigm
     }
     remove_offset(V, 2, pixel_offset(s));
     edge_geom(V, Zv, s.height, sigma, s.clockwise != 0, s.perspective_correct != 0, &r->g, nullptr, nullptr, nullptr);
-    r->rank = rank;
+    r->key = key;
+    r->id = edge_id;
+    r->slot = slot;
     r->textured = (uint8_t)(s.textured[k] && s.shaded[k]);
     r->has_col = (uint8_t)(s.nb_colors <= 4);
+    for (int i = 0; i < 6; i++) r->pad[i] = 0;
     for (int i = 0; i < 2; i++)
         for (int c = 0; c < 4; c++) r->col[i][c] = c < s.nb_colors ? s.colors[(size_t)r->vid[i] * s.nb_colors + c] : 0.0f;
 }

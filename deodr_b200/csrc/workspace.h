@@ -45,58 +45,96 @@ struct DevBuf {
         *accounted += (int64_t)want;
         return DEODR_B200_OK;
     }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
     template <class T>
     T *as() const { return static_cast<T *>(ptr); }
 };
+
+// The plan of a view's forward pass: what the host knows WITHOUT asking the device.  Capacities of the per-tile
+// segments (their offsets live on the device, in the slot) and of the edge list, the kernel instances to run, and
+// launch-size hints (every kernel strides over the device-side counts, so a hint is never a correctness matter).
+struct FwdPlan {
+    bool valid = false;
+    // what the plan was built for
+    int T = -1, H = -1, W = -1;
+    bool edges_possible = false;  // sigma > 0
+    // reserved capacities
+    int cap_small = 0, cap_large = 0, cap_edges = 0, cap_edge_refs = 0;
+    int tex = 1;  // kernel instances with the texture paths compiled in
+    // hints
+    int hint_small = 0, hint_edge_tiles = 0, hint_large_tiles = 0, hint_edges = 0;
+};
+
+// One view's forward state + plan (see include/deodr_b200.h: "view slots").
+struct ViewSlot {
+    FwdPlan plan;
+    int64_t generation = 0;
+    // geometry of the tiling
+    int tiles_x = 0, tiles_y = 0, num_tiles = 0;
+    // the last forward pass (what the adjoint checks / what a re-run after an overflow needs)
+    int fwd_valid = 0;
+    double sigma = -1;
+    int fwd_C = 0, fwd_flags = 0;
+    DeodrSceneView fwd_scene;
+    DeodrViewIO fwd_io;
+    bool fwd_check_indices = false;
+    bool pending = false;     // a pass has been enqueued whose verdict has not been read yet
+    int totals_seq = 0;       // sequence number of the flag the publishing kernel raises in host_totals[SC_WORDS]
+    int *host_totals = nullptr;  // pinned: SC_WORDS scalars + the sequence flag
+    // device state
+    DevBuf zeroed;            // [scalars(SC_WORDS) | small cursor | large cursor | edge cursor], one memset per forward
+    int *scal = nullptr, *small_cursor = nullptr, *large_cursor = nullptr, *edge_cursor = nullptr;
+    DevBuf small_offset, large_offset, edge_offset;  // [tiles + 1] segment offsets of the plan
+    DevBuf small_recs, large_refs, small_ids;
+    DevBuf large_tiles, edge_tiles;  // compact lists of the tiles with large triangles / silhouette edges (two-ended)
+    DevBuf edge_ids, edge_keys, edge_recs, edge_refs_tmp, edge_refs;
+    DevBuf edge_spans;        // x spans of every (tile, edge, row), written by k_edge_fwd and reused by k_raster_bwd
+    DevBuf edge_acc;          // per-edge fp64 plane adjoints of the backward pass
+    DevBuf tie_pairs;
+    int tie_capacity = 0;
+    DevBuf error_image_b;     // antialiase_error adjoint: colour adjoint of the pixels outside every edge band
+};
+
+// One lane = the stream a view's main chain runs on + two auxiliary streams for its side chains.
+struct Lane {
+    cudaStream_t main = nullptr;  // lane 0: the caller's stream (not owned)
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // lanes > 0: fork from / join to the caller's stream
+};
+
+constexpr int MAX_LANES = 4;
 
 struct DeodrWorkspace {
     int device = 0;
     int64_t bytes = 0;
     int64_t launches = 0;
+    int64_t generation_counter = 0;
+    bool overlap = true;   // DEODR_B200_SERIAL=1 keeps every launch on the caller's stream (profiling, A/B)
+    bool deferred = false; // the entry points never read the verdict (CUDA-graph capture); see deodr_b200_workspace_status
+    int replans = 0;       // number of plans (re)built so far
+    int num_lanes = 2;
+    Lane lanes[MAX_LANES];
+    std::vector<ViewSlot *> slots;
     // optional per-phase event timing (bench / profiling)
-    // independent kernel chains run on two auxiliary streams forked from / joined to the caller's stream
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    bool overlap = true;  // DEODR_B200_SERIAL=1 keeps every launch on the caller's stream (profiling, A/B)
     std::vector<cudaEvent_t> ev_start, ev_stop;
     std::vector<int> ev_phase;
     int ev_used = 0;
-    int totals_seq = 0;          // sequence number of the flag k_scan_tiles raises in host_totals[16]
-    int *host_totals = nullptr;  // pinned: [0] tri refs, [1] selected edges, [2] edge refs, [3] tie counter, [4] flags
-    // forward state
-    int tiles_x = 0, tiles_y = 0, num_tiles = 0;
-    int num_edges = 0;           // silhouette edges of the last forward pass
-    double sigma = -1;
-    int fwd_valid = 0;
-    int any_textured = 1;  // does the scene of the last forward hold a textured triangle? (k_bin_count raises the flag)
-    int fwd_T = 0, fwd_H = 0, fwd_W = 0, fwd_C = 0;
-    DevBuf zeroed;               // [scalars(8) | 6 per-tile int arrays], one memset per forward
-    int *scal = nullptr, *edge_count_ptr = nullptr;  // views into `zeroed`
-    deodr::TriBins bins;         // small (pre-masked records) / large (indices) tile lists of the last forward
-    DevBuf small_offset, small_recs, tri_offset, tri_refs;
-    DevBuf small_ids, large_ids;  // compacted lists of the drawn triangles (count pass), reused by the adjoint
-    int num_small = 0, num_large = 0;
-    DevBuf large_tiles, edge_tiles;
-    int *edge_tiles_ptr = nullptr;  // the two-ended list the edge kernels walk (crowded tiles first)  // compact lists of the tiles with large triangles / silhouette edges
-    int num_large_tiles = 0, num_edge_tiles = 0;
-    int num_heavy_edge_tiles = 0;  // crowded tiles (more than one chunk of edges) at the front of the two-ended edge_tiles list
-    DevBuf edge_recs;            // per-edge band stencils in far-to-near order (k_edge_records)
-    DevBuf edge_rank, edge_ids, edge_ids_tmp, edge_keys_in, edge_keys_out, edge_sorted, cub_temp;
-    DevBuf edge_offset, edge_refs_tmp, edge_refs;
-    DevBuf edge_spans;  // x spans of every (tile, edge, row), written by k_edge_fwd and reused by k_raster_bwd
-    DevBuf scalars;              // device ints: [0] tri total, [1] num selected, [2] edge total, [3] tie counter, [4] flags
-    DevBuf tie_pairs;
-    int tie_capacity = 0;
-    DevBuf edge_acc;
+    DevBuf scalars;  // scratch of deodr_b200_check_scene
+    int *host_scratch = nullptr;  // pinned, 32 ints
     // host-path staging (canonical device copies of a DeodrHostScene)
     DevBuf h_faces, h_faces_uv, h_ij, h_depths, h_uv, h_colors, h_shade, h_edgeflags, h_textured, h_shaded, h_texture,
-        h_background, h_image, h_z, h_owner, h_image_b, h_grads;
+        h_background, h_image, h_z, h_owner, h_image_b, h_grads, h_obs, h_err, h_err_b;
     struct HostPath *host = nullptr;  // pinned staging, copy threads, cache of the last host forward (host_api.cu)
 };
 
-
 void deodr_host_path_destroy(DeodrWorkspace *ws);  // host_api.cu
 
-// deodr_b200_render with optional on-device index validation (checkSceneValid, DR.h:2703-2714)
-int deodr_render_impl(DeodrWorkspace *ws, const DeodrSceneView *scene, double sigma, float *image, double *z_buffer,
-                      int32_t *owner, int32_t *face_id, void *stream, bool check_indices);
+// forward pass of one view into slot 0 with optional on-device index validation (checkSceneValid, DR.h:2703-2714);
+// always verified before it returns (the host path synchronises anyway)
+int deodr_render_checked(DeodrWorkspace *ws, const DeodrSceneView *scene, const DeodrViewIO *io, double sigma, int flags,
+                         void *stream);

@@ -12,7 +12,7 @@ One process per GPU (``torchrun``); backend ``nccl`` on GPUs (NVLink 5 / NVSwitc
 
 from __future__ import annotations
 
-from typing import Callable, Dict, Iterable, List, Sequence
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -43,10 +43,18 @@ def allreduce_flat(tensors: Sequence[torch.Tensor], group=None) -> None:
 
 class ViewShardedBackward:
     """Runs ``render_view(view_index) -> dict of gradient tensors`` for the views of this rank, accumulates the shared
-    gradients over the local views (the ``+=`` of deodr/mesh_fitter.py:518-527) and all-reduces them once."""
+    gradients over the local views (the ``+=`` of deodr/mesh_fitter.py:518-527) and all-reduces them once.
+
+    Every rank must issue the SAME collective.  The list of tensors that go into it therefore comes from
+    ``shared_like`` - rank-independent templates ``{name: tensor}`` (the shared parameters themselves: the mesh is
+    replicated) - and a rank without views, or whose ``render_view`` leaves a shared gradient out, contributes zeros of
+    the template's shape.  Without templates the names are taken from what ``render_view`` returned, which is only
+    rank-independent when every rank has at least one view: the constructor refuses ``n_views < world`` in that case.
+    """
 
     def __init__(self, n_views: int, render_view: Callable[[int], Dict[str, torch.Tensor]],
-                 shared: Iterable[str] = SHARED_GRADS, group=None):
+                 shared: Iterable[str] = SHARED_GRADS, group=None,
+                 shared_like: Optional[Dict[str, torch.Tensor]] = None):
         self.n_views = n_views
         self.render_view = render_view
         self.shared = tuple(shared)
@@ -54,6 +62,11 @@ class ViewShardedBackward:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local_views = views_of_rank(n_views, self.rank, self.world)
+        self.shared_like = dict(shared_like) if shared_like is not None else None
+        if self.shared_like is None and n_views < self.world:
+            raise ValueError(
+                f"{n_views} views on {self.world} ranks: some ranks have no view, so the tensors of the all-reduce must "
+                "be described by `shared_like` (rank-independent templates of the shared gradients)")
 
     def step(self):
         """-> (shared gradients summed over ALL views of ALL ranks, {view: per-view gradients of the local views})."""
@@ -69,8 +82,17 @@ class ViewShardedBackward:
                     total[name] += grads[name]
                 else:
                     total[name] = grads[name].clone()
-        if self.world > 1:
-            # every rank must contribute the same set of tensors; a rank without views contributes zeros
+        if self.shared_like is not None:
+            # rank-independent list: zeros where this rank has nothing to add
+            names = [n for n in self.shared if n in self.shared_like and self.shared_like[n] is not None]
+            for n in names:
+                like = self.shared_like[n]
+                if n not in total:
+                    total[n] = torch.zeros_like(like)
+                elif total[n].shape != like.shape:
+                    raise ValueError(f"shared gradient {n}: shape {tuple(total[n].shape)} != template {tuple(like.shape)}")
+        else:
             names = [n for n in self.shared if n in total]
+        if self.world > 1:
             allreduce_flat([total[n] for n in names], self.group)
         return total, per_view

@@ -55,7 +55,11 @@ TorchDifferentiableRender2D = TorchDifferentiableRenderer2DFunc.apply
 
 
 class CudaDifferentiableRenderer2DFunc(torch.autograd.Function):
-    """Device-resident variant: ``image = f(ij[V,2] f64 cuda, colors[V,C] cuda, DeviceScene, sigma)``."""
+    """Device-resident variant: ``image = f(ij[V,2] f64 cuda, colors[V,C] cuda, DeviceScene, sigma)``.
+
+    The renderer keeps ONE live forward state per slot, and the ``DeviceScene`` is shared and mutable, so the node
+    snapshots its inputs; if another forward has used the slot by the time ``backward`` runs (two renders before
+    ``loss.backward()``), the forward is replayed from the snapshot first."""
 
     @staticmethod
     def forward(ctx: Any, ij: torch.Tensor, colors: torch.Tensor, scene: DeviceScene, sigma: float = 1.0):  # type: ignore
@@ -63,12 +67,21 @@ class CudaDifferentiableRenderer2DFunc(torch.autograd.Function):
         fwd = default_renderer(scene.device.index).render(scene, sigma)
         ctx.scene, ctx.sigma, ctx.fwd = scene, float(sigma), fwd
         ctx.in_dtypes = (ij.dtype, colors.dtype)
-        return fwd["image"]
+        ctx.save_for_backward(ij.detach().clone(), colors.detach().clone())
+        # the caller gets its own tensor: the framebuffers of ctx.fwd may be re-rendered into by backward
+        return fwd["image"].clone()
 
     @staticmethod
     def backward(ctx: Any, *grad_outputs: Any) -> Any:
         (image_b,) = grad_outputs
-        grads = default_renderer(ctx.scene.device.index).render_b(ctx.scene, ctx.sigma, ctx.fwd, image_b)
+        renderer = default_renderer(ctx.scene.device.index)
+        ij, colors = ctx.saved_tensors
+        if ctx.fwd["generation"] != renderer.generation(ctx.fwd["slot"]):
+            ctx.scene.update(ij=ij, colors=colors)
+            ctx.fwd = renderer.render(ctx.scene, ctx.sigma, out=ctx.fwd)
+        else:
+            ctx.scene.update(ij=ij, colors=colors)  # the shared scene may hold another node's inputs by now
+        grads = renderer.render_b(ctx.scene, ctx.sigma, ctx.fwd, image_b)
         return grads["ij_b"].to(ctx.in_dtypes[0]), grads["colors_b"].to(ctx.in_dtypes[1]), None, None
 
 

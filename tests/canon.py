@@ -84,6 +84,28 @@ class Emulator:
         out["tri_refs"] = self.lib.emul_tri_refs()
         return out
 
+    def build_plan(self, scene, sigma):
+        """Segment capacities from `scene` (count-only pass + scans), kept for the render_planned calls that follow."""
+        a = canonical_arrays(scene)
+        v = view_of(scene, a)
+        self.lib.emul_build_plan.argtypes = [C.POINTER(_cabi.SceneView), C.c_double]
+        assert self.lib.emul_build_plan(C.byref(v), float(sigma)) == 0
+
+    def render_planned(self, scene, sigma):
+        """Forward pass of `scene` against the plan of an EARLIER scene of the same shape -> (verdict word, outputs)."""
+        a = canonical_arrays(scene)
+        v = view_of(scene, a)
+        H, W, Cc = scene.height, scene.width, scene.nb_colors
+        out = {
+            "image": np.zeros((H, W, Cc), np.float32), "z": np.zeros((H, W)), "owner": np.zeros((H, W), np.int32),
+            "face_id": np.zeros((H, W), np.int32),
+        }
+        self.lib.emul_render_planned.argtypes = [C.POINTER(_cabi.SceneView), C.c_double] + [C.c_void_p] * 4
+        verdict = self.lib.emul_render_planned(C.byref(v), float(sigma), out["image"].ctypes.data, out["z"].ctypes.data,
+                                               out["owner"].ctypes.data, out["face_id"].ctypes.data)
+        out["_arrays"], out["_view"] = a, v
+        return verdict, out
+
     def render_b(self, scene, sigma, fwd, image_b):
         a = fwd["_arrays"]
         ib = np.ascontiguousarray(image_b, dtype=np.float32)
@@ -98,7 +120,7 @@ class Emulator:
         assert rc == 0
         return g
 
-    # ---- antialiase_error mode (row f3): phases emulated on the CPU; the CUDA entry points do not offer it yet ----
+    # ---- antialiase_error mode (row f3) ----
     def render_error(self, scene, sigma, obs):
         a = canonical_arrays(scene)
         v = view_of(scene, a)

@@ -20,26 +20,38 @@ struct HostEnv {
     static int atomic_add(int *p, int v) { int old = *p; *p += v; return old; }
     static void atomic_add(float *p, float v) { *p += v; }
     static void atomic_add(double *p, double v) { *p += v; }
+    static void atomic_or(int *p, int v) { *p |= v; }
     static int shared_inc(int *p) { return (*p)++; }
     void emit(float *p, float v) const { *p += v; }
 };
 
 struct EmulState {
     int tiles_x = 0, tiles_y = 0, nt = 0, E = 0;
-    std::vector<int> small_count, small_offset, small_cursor, large_count, large_offset, large_cursor, large_refs;
+    // the plan: segment offsets (counts of a count-only pass, padded with the device's slack) + edge capacity
+    std::vector<int> small_offset, large_offset, edge_offset;
+    int cap_edges = 0;
+    // one forward pass
+    int scal[SC_WORDS] = {0};
+    std::vector<int> small_cursor, large_cursor, edge_cursor, large_refs;
     std::vector<PreRec> small_recs;
-    std::vector<int> small_ids, large_ids;
-    std::vector<int> edge_count, edge_offset, edge_refs, edge_sorted;
+    std::vector<int> small_ids;
+    std::vector<int> edge_ids;
+    std::vector<uint64_t> edge_keys;
+    std::vector<int> edge_refs_tmp, edge_refs;
     std::vector<EdgeRec> edge_recs;
     std::vector<int> tie_pairs;
+    TileSegments small_seg() { return TileSegments{small_offset.data(), small_cursor.data()}; }
+    TileSegments large_seg() { return TileSegments{large_offset.data(), large_cursor.data()}; }
+    TileSegments edge_seg() { return TileSegments{edge_offset.data(), edge_cursor.data()}; }
 };
 
 static EmulState g_state;
 
+// k_scan_tiles: exclusive scan of the counts padded with slack (c + c/4 + 4, kernels.cu SEG_SLACK)
 static void scan_tiles(const std::vector<int> &count, std::vector<int> &offset) {
     int run = 0;
     offset.resize(count.size() + 1);
-    for (size_t i = 0; i < count.size(); i++) { offset[i] = run; run += count[i]; }
+    for (size_t i = 0; i < count.size(); i++) { offset[i] = run; run += count[i] + (count[i] >> 2) + 4; }
     offset[count.size()] = run;
 }
 
@@ -61,7 +73,7 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
             const Tile tile = tile_of(tile_id, st.tiles_x);
             for (int tid = 0; tid < NT; tid++) { px[tid].z = std::numeric_limits<double>::infinity(); px[tid].own = px[tid].bown = -1; }
             auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
-            const int n_small = st.small_cursor[tile_id];
+            const int n_small = segment_size(st.small_seg(), tile_id);
             for (int base = 0; base < n_small; base += PRE_CHUNK) {
                 const int m = std::min(PRE_CHUNK, n_small - base);
                 // the device pulls the chunk into shared memory with one bulk (TMA) copy; same bytes here
@@ -70,7 +82,7 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
                 for (int tid = 0; tid < NT; tid++) phase_pre_scatter<HostEnv>(tid, m, pre, sh);
                 for (int tid = 0; tid < NT; tid++) phase_pix_test<1>(s, tid, m, tile, pre, sh, &px[tid]);
             }
-            const int n_large = st.large_count[tile_id];
+            const int n_large = segment_size(st.large_seg(), tile_id);
             for (int base = 0; base < n_large; base += LARGE_CHUNK) {
                 const int m = std::min(LARGE_CHUNK, n_large - base);
                 for (int tid = 0; tid < NT; tid++)
@@ -112,7 +124,7 @@ static void raster_fwd(const SceneView &s, double sigma, EmulState &st, float *i
     // ---- k_edge_fwd
     std::vector<PixelState<MAXC>> px(NT);
     for (int tile_id = 0; tile_id < st.nt && st.E > 0; tile_id++) {
-        const int n_edge = st.edge_count[tile_id];
+        const int n_edge = segment_size(st.edge_seg(), tile_id);
         if (n_edge == 0) continue;
         const Tile tile = tile_of(tile_id, st.tiles_x);
         auto inside = [&](int tid) { return tile.x0 + tid % TS < s.width && tile.y0 + tid / TS < s.height; };
@@ -172,7 +184,7 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
             eadj[tid].has = false;
             eadj[tid].g = err_b ? (double)err_b[idx] : 0.0;
         }
-        const int n_edge = st.E > 0 ? st.edge_count[tile_id] : 0;
+        const int n_edge = st.E > 0 ? segment_size(st.edge_seg(), tile_id) : 0;
         if (n_edge > 0) {
             const int edge_base = st.edge_offset[tile_id];
             const bool single = n_edge <= EDGE_CHUNK;
@@ -235,105 +247,117 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
     }
     delete sh;
     // k_small_tri_bwd
-    const int *edge_count = st.E > 0 ? st.edge_count.data() : nullptr;
+    const int *edge_count = st.E > 0 ? st.edge_cursor.data() : nullptr;
     for (int k : st.small_ids)
         small_triangle_adjoint<MAXC, HostEnv>(s, k, st.tiles_x, edge_count, owner, st.tie_pairs.data(), image_b, g.ij_b,
                                               g.colors_b, g.uv_b, g.shade_b, g.texture_b);
 }
 
-extern "C" {
-
-// Same contract as deodr_b200_render, with HOST pointers in the canonical layout.
-int emul_render(const DeodrSceneView *scene, double sigma, float *image, double *z_buffer, int32_t *owner,
-                int32_t *face_id) {
-    SceneView s;
-    memcpy(&s, scene, sizeof(s));
-    EmulState &st = g_state;
-    st = EmulState();
+// Plan building (build_plan of kernels.cu): count-only pass + scans with slack.
+static void emul_plan(const SceneView &s, double sigma, EmulState &st) {
     const int T = s.nb_triangles;
     st.tiles_x = (s.width + TS - 1) / TS;
     st.tiles_y = (s.height + TS - 1) / TS;
     st.nt = st.tiles_x * st.tiles_y;
-    st.small_count.assign(st.nt, 0);
-    st.large_count.assign(st.nt, 0);
-    st.small_cursor.assign(st.nt, 0);
-    st.large_cursor.assign(st.nt, 0);
-    st.edge_count.assign(st.nt, 0);
-    int num_edges = 0;
-    std::vector<int> ids((size_t)3 * T + 4);
-    std::vector<uint64_t> keys((size_t)3 * T + 4);
-    std::vector<int> rank0((size_t)3 * T + 4);
-    EdgeList edges{&num_edges, ids.data(), keys.data(), rank0.data()};
-    TriBins bins{st.small_count.data(), nullptr, st.small_cursor.data(), nullptr,
-                 st.large_count.data(), nullptr, st.large_cursor.data(), nullptr};
-    int num_small = 0, num_large = 0;
-    st.small_ids.assign(T + 4, -1);
-    st.large_ids.assign(T + 4, -1);
-    TriLists lists{&num_small, st.small_ids.data(), &num_large, st.large_ids.data()};
-    // k_bin_count, in DESCENDING triangle order: the device appends in an arbitrary order, nothing may depend on it
-    for (int k = T - 1; k >= 0; k--)
-        bin_count_triangle<HostEnv>(s, k, sigma, st.tiles_x, bins, lists, edges, st.edge_count.data());
-    scan_tiles(st.small_count, st.small_offset);
-    scan_tiles(st.large_count, st.large_offset);
-    scan_tiles(st.edge_count, st.edge_offset);
-    st.E = num_edges;
-    // k_rank_edges + k_scatter_edges
-    st.edge_sorted.assign(st.E, -1);
-    for (int i = 0; i < st.E; i++) st.edge_sorted[edge_rank(i, st.E, keys.data(), ids.data())] = ids[i];
-    // k_edge_records
-    st.edge_recs.resize(st.E);
-    for (int r = 0; r < st.E; r++) edge_record(s, st.edge_sorted[r], r, sigma, &st.edge_recs[r]);
-    // k_bin_fill (again in reversed order)
-    st.small_recs.assign(st.small_offset[st.nt] + 1, PreRec());
-    st.large_refs.assign(st.large_offset[st.nt] + 4, -1);
-    bins.small_offset = st.small_offset.data();
-    bins.large_offset = st.large_offset.data();
-    bins.small_recs = st.small_recs.data();
-    bins.large_refs = st.large_refs.data();
-    st.small_ids.resize(num_small);
-    st.large_ids.resize(num_large);
-    for (int k : st.small_ids) bin_fill_small<HostEnv>(s, k, st.tiles_x, bins);
-    for (int k : st.large_ids) bin_fill_large<HostEnv>(s, k, st.tiles_x, bins);
-    std::vector<int> cursor(st.nt, 0);
-    if (st.E > 0) {
-        std::vector<int> tmp(st.edge_offset[st.nt] + 4, -1);
-        std::fill(cursor.begin(), cursor.end(), 0);
-        for (int r = st.E - 1; r >= 0; r--)
-            bin_fill_edge<HostEnv>(s, st.edge_sorted[r], r, sigma, st.tiles_x, st.edge_offset.data(), cursor.data(), tmp.data());
-        st.edge_refs.assign(tmp.size(), -1);
-        for (int t = 0; t < st.nt; t++) {  // k_sort_tile_edges
-            const int n = st.edge_count[t], base = st.edge_offset[t];
-            for (int i = 0; i < n; i++) {
-                int mine = tmp[base + i], pos = 0;
-                for (int j = 0; j < n; j++) pos += tmp[base + j] < mine;
-                st.edge_refs[base + pos] = mine;
-            }
-        }
-    }
-    const int C = s.nb_colors;
-    if (C == 1) raster_fwd<1>(s, sigma, st, image, z_buffer, owner, face_id);
-    else if (C <= 3) raster_fwd<3>(s, sigma, st, image, z_buffer, owner, face_id);
-    else if (C <= 4) raster_fwd<4>(s, sigma, st, image, z_buffer, owner, face_id);
-    else raster_fwd<16>(s, sigma, st, image, z_buffer, owner, face_id);
-    return 0;
+    std::vector<int> small_count(st.nt, 0), large_count(st.nt, 0), edge_count(st.nt, 0);
+    int scal[SC_WORDS] = {0};
+    TriBins bins{{nullptr, small_count.data()}, nullptr, {nullptr, large_count.data()}, nullptr, scal + SC_OVERFLOW};
+    EdgeList edges{scal + SC_EDGES, nullptr, nullptr, 0};
+    for (int k = 0; k < T; k++)
+        bin_triangle<HostEnv, true>(s, k, sigma, st.tiles_x, bins, scal + SC_SMALL, nullptr, edges, edge_count.data());
+    scan_tiles(small_count, st.small_offset);
+    scan_tiles(large_count, st.large_offset);
+    scan_tiles(edge_count, st.edge_offset);
+    const int E = scal[SC_EDGES];
+    st.cap_edges = E > 0 ? E + E / 4 + 64 : 0;
 }
 
-// antialiase_error mode: emul_render, then the residual and its overdraw by the edges (image keeps its aliased edges).
-int emul_render_error(const DeodrSceneView *scene, double sigma, const float *obs, float *image, double *z_buffer,
-                      int32_t *owner, int32_t *face_id, float *err) {
-    // the binning / ordering half of emul_render does not depend on the mode: run it with sigma (edge lists are
-    // needed), then redo the raster with the error-mode edge pass
-    if (int rc = emul_render(scene, sigma, image, z_buffer, owner, face_id)) return rc;
-    SceneView s;
-    memcpy(&s, scene, sizeof(s));
-    EmulState &st = g_state;
+// One forward pass against the current plan (enqueue_forward of kernels.cu); returns the verdict word.
+static int emul_forward(const SceneView &s, double sigma, EmulState &st, float *image, double *z_buffer, int32_t *owner,
+                        int32_t *face_id, const float *obs, float *err) {
+    const int T = s.nb_triangles;
+    memset(st.scal, 0, sizeof(st.scal));
+    st.small_cursor.assign(st.nt, 0);
+    st.large_cursor.assign(st.nt, 0);
+    st.edge_cursor.assign(st.nt, 0);
+    st.small_recs.assign(st.small_offset[st.nt] + 1, PreRec());
+    st.large_refs.assign(st.large_offset[st.nt] + 4, -1);
+    st.small_ids.assign(T + 4, -1);
+    st.edge_ids.assign(st.cap_edges + 4, -1);
+    st.edge_keys.assign(st.cap_edges + 4, 0);
     st.tie_pairs.clear();
+    TriBins bins{st.small_seg(), st.small_recs.data(), st.large_seg(), st.large_refs.data(), st.scal + SC_OVERFLOW};
+    EdgeList edges{st.scal + SC_EDGES, st.edge_ids.data(), st.edge_keys.data(), st.cap_edges};
+    // k_bin, in DESCENDING triangle order: the device appends in an arbitrary order, nothing may depend on it
+    for (int k = T - 1; k >= 0; k--)
+        bin_triangle<HostEnv, false>(s, k, sigma, st.tiles_x, bins, st.scal + SC_SMALL, st.small_ids.data(), edges, nullptr);
+    st.small_ids.resize(st.scal[SC_SMALL]);
+    st.E = std::min(st.scal[SC_EDGES], st.cap_edges);
+    if (st.cap_edges == 0) st.E = 0;
+    // k_bin_edges (again in reversed order) + k_sort_tile_edges
+    st.edge_recs.assign(st.cap_edges + 1, EdgeRec());
+    st.edge_refs_tmp.assign(st.edge_offset[st.nt] + 4, -1);
+    st.edge_refs.assign(st.edge_offset[st.nt] + 4, -1);
+    if (!st.scal[SC_OVERFLOW]) {
+        EdgeBins ebins{st.edge_seg(), st.edge_refs_tmp.data(), st.scal + SC_OVERFLOW};
+        for (int i = st.E - 1; i >= 0; i--) bin_edge<HostEnv>(s, i, sigma, st.tiles_x, edges, ebins, st.edge_recs.data());
+    }
+    if (!st.scal[SC_OVERFLOW])
+        for (int t = 0; t < st.nt; t++) {
+            const int n = segment_size(st.edge_seg(), t), base = st.edge_offset[t];
+            for (int i = 0; i < n; i++)
+                st.edge_refs[base + tile_edge_position(i, n, st.edge_refs_tmp.data() + base, st.edge_recs.data())] =
+                    st.edge_refs_tmp[base + i];
+        }
+    if (st.scal[SC_OVERFLOW]) return st.scal[SC_OVERFLOW];  // the device kernels return at once: the pass is void
     const int C = s.nb_colors;
     if (C == 1) raster_fwd<1>(s, sigma, st, image, z_buffer, owner, face_id, obs, err);
     else if (C <= 3) raster_fwd<3>(s, sigma, st, image, z_buffer, owner, face_id, obs, err);
     else if (C <= 4) raster_fwd<4>(s, sigma, st, image, z_buffer, owner, face_id, obs, err);
     else raster_fwd<16>(s, sigma, st, image, z_buffer, owner, face_id, obs, err);
     return 0;
+}
+
+extern "C" {
+
+// Same contract as deodr_b200_render, with HOST pointers in the canonical layout: plan + pass.
+int emul_render(const DeodrSceneView *scene, double sigma, float *image, double *z_buffer, int32_t *owner,
+                int32_t *face_id) {
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    EmulState &st = g_state;
+    st = EmulState();
+    emul_plan(s, sigma, st);
+    return emul_forward(s, sigma, st, image, z_buffer, owner, face_id, nullptr, nullptr) ? -1 : 0;
+}
+
+// The plan of one scene ...
+int emul_build_plan(const DeodrSceneView *scene, double sigma) {
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    g_state = EmulState();
+    emul_plan(s, sigma, g_state);
+    return 0;
+}
+
+// ... used by the pass over ANOTHER scene of the same shape (an optimisation loop moves the vertices between two
+// passes): returns the verdict word - 0 = the lists fitted, the outputs are valid; otherwise the pass is void.
+int emul_render_planned(const DeodrSceneView *scene, double sigma, float *image, double *z_buffer, int32_t *owner,
+                        int32_t *face_id) {
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    return emul_forward(s, sigma, g_state, image, z_buffer, owner, face_id, nullptr, nullptr);
+}
+
+// antialiase_error mode: the residual and its overdraw by the edges (the image keeps its aliased edges).
+int emul_render_error(const DeodrSceneView *scene, double sigma, const float *obs, float *image, double *z_buffer,
+                      int32_t *owner, int32_t *face_id, float *err) {
+    SceneView s;
+    memcpy(&s, scene, sizeof(s));
+    EmulState &st = g_state;
+    st = EmulState();
+    emul_plan(s, sigma, st);
+    return emul_forward(s, sigma, st, image, z_buffer, owner, face_id, obs, err) ? -1 : 0;
 }
 
 // adjoint of emul_render_error: `image` is its (aliased) output, err_b the adjoint of the residual buffer
@@ -355,7 +379,7 @@ int emul_render_error_b(const DeodrSceneView *scene, double sigma, const double 
     else if (C <= 4) raster_bwd<4>(s, sigma, st, z_buffer, owner, image_b.data(), *grads, acc.data(), obs, err_b, compat != 0);
     else raster_bwd<16>(s, sigma, st, z_buffer, owner, image_b.data(), *grads, acc.data(), obs, err_b, compat != 0);
     for (int r = 0; r < st.E; r++)
-        finalize_edge<HostEnv>(s, st.edge_sorted[r], sigma, acc.data() + (size_t)r * edge_acc_stride(C), grads->ij_b,
+        finalize_edge<HostEnv>(s, st.edge_ids[r], sigma, acc.data() + (size_t)r * edge_acc_stride(C), grads->ij_b,
                                grads->colors_b, grads->uv_b, grads->shade_b);
     return 0;
 }
@@ -373,7 +397,7 @@ int emul_render_b(const DeodrSceneView *scene, double sigma, const double *z_buf
     else if (C <= 4) raster_bwd<4>(s, sigma, st, z_buffer, owner, image_b, *grads, acc.data());
     else raster_bwd<16>(s, sigma, st, z_buffer, owner, image_b, *grads, acc.data());
     for (int r = 0; r < st.E; r++)
-        finalize_edge<HostEnv>(s, st.edge_sorted[r], sigma, acc.data() + (size_t)r * edge_acc_stride(C), grads->ij_b,
+        finalize_edge<HostEnv>(s, st.edge_ids[r], sigma, acc.data() + (size_t)r * edge_acc_stride(C), grads->ij_b,
                                grads->colors_b, grads->uv_b, grads->shade_b);
     return 0;
 }
@@ -459,7 +483,7 @@ int emul_num_edges(void) { return g_state.E; }
 int emul_tri_refs(void) {
     int n = 0;
     for (int v : g_state.small_cursor) n += v;
-    for (int v : g_state.large_count) n += v;
+    for (int v : g_state.large_cursor) n += v;
     return n;
 }
 }

@@ -26,6 +26,9 @@ def test_struct_layouts_match_header(build_native):
     assert C.sizeof(_cabi.SceneView) == 13 * 8 + 56
     assert C.sizeof(_cabi.Grads) == 5 * 8
     assert C.sizeof(_cabi.HostScene) == 200
+    assert C.sizeof(_cabi.ViewIO) == 9 * 8
+    assert C.sizeof(_cabi.Camera) == (12 + 9 + 5) * 8 + 8
+    assert C.sizeof(_cabi.MeshTopology) == 6 * 8 + 16
 
 
 def test_no_cpu_fallback_without_gpu(build_native):
@@ -48,7 +51,7 @@ def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "deodr_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text and "libemul" not in text, f

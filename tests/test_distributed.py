@@ -71,3 +71,31 @@ def test_sharded_backward_equals_sequential_accumulation(tmp_path, build_native)
     for v in range(N_VIEWS):
         owner = ranks[v % world]
         assert np.array_equal(owner[f"ij_b_{v}"], serial[v]["ij_b"].numpy())
+
+
+def _worker_fewer_views(rank, world, port, out_dir):
+    """world = 3, ONE view: ranks 1 and 2 have nothing to render and must still join the collective with zeros."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+
+    def render_view(view):
+        calls.append(view)
+        return {"ij_b": torch.ones(4, 2), "colors_b": torch.full((4, 3), 2.0), "uv_b": torch.full((2, 2), 3.0)}
+
+    like = {"colors_b": torch.empty(4, 3), "uv_b": torch.empty(2, 2), "shade_b": torch.empty(4), "texture_b": torch.empty(0)}
+    try:
+        ViewShardedBackward(1, render_view)  # no templates: refused instead of hanging later
+        raise AssertionError("expected ValueError")
+    except ValueError:
+        pass
+    total, per_view = ViewShardedBackward(1, render_view, shared_like=like).step()
+    assert calls == ([0] if rank == 0 else [])
+    assert torch.all(total["colors_b"] == 2.0) and torch.all(total["uv_b"] == 3.0) and torch.all(total["shade_b"] == 0.0)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ranks_without_views_contribute_zeros(tmp_path):
+    world = 3
+    mp.spawn(_worker_fewer_views, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)

@@ -138,3 +138,31 @@ def test_emulated_antialiase_error_mode(emulator, checker, texture):
                 continue
             tol = 5e-5 * np.abs(ref[name]).max() + 2e-6
             assert np.abs(got[name] - ref[name]).max() <= tol, (name, np.abs(got[name] - ref[name]).max(), tol)
+
+
+def test_plan_of_an_earlier_pass_serves_a_drifted_scene(emulator, checker):
+    """The forward pass never waits for the host: its per-tile lists live in segments reserved by the PLAN of an earlier
+    pass over a scene of the same shape (count pass + slack).  A drifted scene (vertices moved like one optimiser
+    step) must either fit - and then be bit-exact like any other pass - or raise the verdict word, never corrupt."""
+    base = torus_scene(20, 128, 96)
+    emulator.build_plan(base, 1.0)
+    rng = np.random.default_rng(0)
+    fitted = 0
+    for step in (0.05, 0.3, 1.0):
+        import copy
+
+        moved = copy.copy(base)
+        moved.ij = base.ij + rng.normal(scale=step, size=base.ij.shape)
+        moved.edgeflags = base.edgeflags  # topology and flags as the plan saw them
+        verdict, out = emulator.render_planned(moved, 1.0)
+        if verdict == 0:
+            fitted += 1
+            image, z = checker.render(moved, 1.0)
+            assert np.array_equal(out["z"], z)
+            assert np.abs(out["image"] - image).max() <= IMAGE_TOL * max(1.0, np.abs(image).max())
+    assert fitted >= 1  # the smallest drift fits into the slack
+    # a very different scene on the same plan: overflow is REPORTED (non-zero verdict), the host then re-plans
+    crowded = confetti_scene(4000, 128, 96, size=3.0, seed=3)
+    emulator.build_plan(torus_scene(4, 128, 96), 1.0)
+    verdict, _ = emulator.render_planned(crowded, 1.0)
+    assert verdict != 0
