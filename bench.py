@@ -6,9 +6,12 @@
 
 Workload (N = 1): BASELINE.json configs[4] - S-mesh(708): 1,002,528-triangle closed torus, 2048x2048, C = 3, Gouraud
 vertex colours, sigma = 1 edge-overdraw antialiasing, dense image_b; one "step" = per-iteration refresh of ij/colours
-+ gradient clear + renderScene (forward) + renderScene_B (adjoint) of one view.  N > 1: weak scaling over the
-batch-of-views axis (one view per rank, same mesh, different camera), plus ONE NCCL all-reduce per step of the
-gradient of the shared parameter (vertex colours, colors_b[V,C]); ij_b is per view.
++ gradient clear + renderScene (forward) + renderScene_B (adjoint) of the rank's views (--views-per-gpu, default 1;
+`--workload c4` = BASELINE configs[3]: 8 views per GPU of the 200k-triangle mesh at 512x512, an RGB and a depth render
+each).  N > 1: weak scaling over the batch-of-views axis (same mesh, different cameras), plus ONE NCCL all-reduce per
+step of the gradient of the shared parameter (vertex colours, colors_b[V,C]); ij_b is per view.  The all-reduce runs on a
+communication stream and only the colour readers of the NEXT forward wait for it (deodr_b200_workspace_set_colors_ready),
+so it overlaps that forward's binning and z pass.
 
 One JSON line on rank 0; keys follow the driver contract, plus `roofline`, `cpu_baseline`, `e2e`, `clocks`.
 """
@@ -64,6 +67,8 @@ def kernel_algorithmic_bytes(scene):
     tex = scene.texture.size * 4 if scene.textured.any() else 0
     tex_terms = (T * 12 + U * 16 + V * 4 + tex) if tex else 0
     return {
+        # the single binning pass: faces + flags (17 T) and ij + depths (24 V) read (its 64-byte records are overhead)
+        "bin": T * 17 + V * 24,
         # z-buffer (8) + face / owner id (4) written; faces + flags (17 T) and ij + depths (24 V) read
         "tile_z": P * 12 + T * 17 + V * 24,
         # image written (4C), vertex colours read (+ uv / shade / texture)
@@ -164,98 +169,189 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
 
-    scene = build_scene(args.workload, view=rank, n_views=max(world, 1))
+    per_gpu = args.views_per_gpu if args.views_per_gpu > 0 else (8 if args.workload == "c4" else 1)
+    n_views = per_gpu * max(world, 1)
+    depth_too = args.workload == "c4"  # configs[3]: "depth+RGB"
+    scenes = [build_scene(args.workload, view=rank * per_gpu + v, n_views=n_views) for v in range(per_gpu)]
+    if depth_too:
+        for v in range(per_gpu):
+            d = build_scene(args.workload, view=rank * per_gpu + v, n_views=n_views)
+            d.nb_colors, d.colors = 1, np.ascontiguousarray(d.depths[:, None])
+            d.background_color = np.array([float(d.depths.max())])
+            d.texture = np.zeros((2, 2, 1))
+            scenes.append(d)
+    scene = scenes[0]
     H, W, C = scene.height, scene.width, scene.nb_colors
     P = H * W
     renderer = Renderer(local)
-    ds = DeviceScene(scene, dev)
-    ij_dev = ds.t["ij"].clone()
-    colors_dev = ds.t["colors"].clone()
-    image_b = torch.from_numpy(np.random.default_rng(1 + rank).random((H, W, C), dtype=np.float32) * 2 - 1).to(dev)
-    # the five gradient slots are views of ONE flat buffer: callers clear scene.*_b before every backward, one memset
-    names = ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b")
-    shapes = {"ij_b": ds.t["ij"].shape, "colors_b": ds.t["colors"].shape, "uv_b": ds.t["uv"].shape,
-              "shade_b": ds.t["shade"].shape, "texture_b": ds.t["texture"].shape}
-    sizes = {k: int(np.prod(shapes[k])) for k in names}
-    flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
-    grads, off = {}, 0
-    for k in names:
-        grads[k] = flat[off:off + sizes[k]].view(shapes[k])
-        off += sizes[k]
-    out = None
+    dss = [DeviceScene(s, dev) for s in scenes]
+    ij_dev = [ds.t["ij"].clone() for ds in dss]
+    colors_dev = [ds.t["colors"].clone() for ds in dss]
+    rng = np.random.default_rng(1 + rank)
+    image_bs = [torch.from_numpy(rng.random((s.height, s.width, s.nb_colors), dtype=np.float32) * 2 - 1).to(dev)
+                for s in scenes]
+    # gradient slots: ONE flat buffer (callers clear scene.*_b before every backward: one memset); the gradients of
+    # the parameters the views share (colours per render kind, uv, shade, texture) are shared views of it, ij_b is
+    # per view - the `+=` of deodr/mesh_fitter.py:518-527 happens in place
+    kinds, total = {}, 0
+    for ds in dss:  # shared blocks first: they form the prefix that is all-reduced
+        if ds.nb_colors not in kinds:
+            kinds[ds.nb_colors] = {}
+            for k, n in (("colors_b", "colors"), ("uv_b", "uv"), ("shade_b", "shade"), ("texture_b", "texture")):
+                kinds[ds.nb_colors][k] = (total, ds.t[n].shape)
+                total += int(np.prod(ds.t[n].shape))
+    shared_end = total
+    layout = []
+    for ds in dss:
+        layout.append((total, ds.t["ij"].shape))
+        total += int(np.prod(ds.t["ij"].shape))
+    flat = torch.zeros(total, dtype=torch.float32, device=dev)
+    view_of = lambda off, shape: flat[off:off + int(np.prod(shape))].view(shape)  # noqa: E731
+    grads = []
+    for i, ds in enumerate(dss):
+        g = {k: view_of(*kinds[ds.nb_colors][k]) for k in ("colors_b", "uv_b", "shade_b", "texture_b")}
+        g["ij_b"] = view_of(*layout[i])
+        grads.append(g)
+    outs = None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_bwd = torch.cuda.Event()
+    ev_colors = torch.cuda.Event()
+    overlap = world > 1 and not args.no_overlap
 
     def step():
-        nonlocal out
-        ds.update(ij=ij_dev, colors=colors_dev)          # per-iteration refresh of the optimised inputs
-        flat.zero_()                                      # callers clear scene.*_b before every backward
-        out = renderer.render(ds, SIGMA, out=out)
-        renderer.render_b(ds, SIGMA, out, image_b, grads)
+        nonlocal outs
+        for ds, ij, col in zip(dss, ij_dev, colors_dev):      # per-iteration refresh of the optimised inputs
+            ds.update(ij=ij)
+        if overlap:
+            # the colours are written by the "optimiser" on the communication stream (after the all-reduce of the
+            # previous step): only the kernels of this forward that READ colours wait for that
+            renderer.set_colors_ready(ev_colors)
+        else:
+            for ds, col in zip(dss, colors_dev):
+                ds.update(colors=col)
+        if overlap:
+            # colors_b is zeroed on the communication stream once the all-reduce has consumed it
+            flat[shared_end:].zero_()                         # the per-view ij_b
+        else:
+            flat.zero_()                                      # callers clear scene.*_b before every backward
+        outs = renderer.render_views(dss, SIGMA, out=outs)
+        if overlap:
+            torch.cuda.current_stream().wait_event(ev_colors)  # the adjoint accumulates into colors_b
+        renderer.render_b_views(dss, SIGMA, outs, image_bs, grads)
         if world > 1:
-            dist.all_reduce(grads["colors_b"])            # shared-parameter gradient, one call per step
+            if overlap:
+                ev_bwd.record()
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev_bwd)
+                    work = dist.all_reduce(flat[:shared_end], async_op=True)  # one flat call: every shared gradient
+                    work.wait()
+                    for ds, col in zip(dss, colors_dev):       # stand-in for the optimiser's colour update
+                        ds.update(colors=col)
+                    flat[:shared_end].zero_()
+                    ev_colors.record(comm)
+            else:
+                dist.all_reduce(flat[:shared_end])             # shared-parameter gradients, one call per step
 
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    if overlap:
+        ev_colors.record(comm)
+    graph = None
     for _ in range(args.warmup):
         step()
     fence()
+    if args.graph and world == 1:
+        # the whole step captured once: nothing inside the passes touches the host (deferred verdicts)
+        renderer.set_deferred(True)
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(cap):
+            step()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=cap):
+                step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        renderer.status()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    renderer.timing_enable(12 * args.steps + 12)
+    if graph is None:
+        renderer.timing_enable(14 * args.steps * len(dss) + 16)
     launches0 = renderer.launches
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(args.steps):
-        step()
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+    if overlap:
+        torch.cuda.current_stream().wait_stream(comm)
     stop.record()
     fence()
     elapsed_ms = start.elapsed_time(stop)
     launches = renderer.launches - launches0
+    if graph is not None:
+        renderer.status()  # raises if a replay overflowed its plan
+        launches = args.steps * graph_launches(renderer, step)
     clocks = sampler.stop() if rank == 0 else None
-    phases = renderer.timing_collect()
+    phases = renderer.timing_collect() if graph is None else []
     renderer.timing_enable(0)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    value = world * P / (ms_per_step * 1e-3) / 1e6
+    pixels_per_step = world * sum(s.height * s.width for s in scenes)
+    value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
 
     # ---- per-kernel durations inside the timed region -> roofline of the dominant kernel
     per_phase = {}
     for name, ms in phases:
         per_phase.setdefault(name, []).append(ms)
     phase_ms = {k: statistics.mean(v) for k, v in per_phase.items()}
-    b_fwd, b_bwd = algorithmic_bytes(scene)
+    b_fwd = sum(algorithmic_bytes(s)[0] for s in scenes)
+    b_bwd = sum(algorithmic_bytes(s)[1] for s in scenes)
     kernel_bytes = kernel_algorithmic_bytes(scene)
     peak, peak_src = measured_peak_gbs()
     roofline = None
     # The forward's z pass and shading run back to back on the caller's stream, so their event brackets are their
     # own durations; the three adjoint kernels run CONCURRENTLY on forked streams (their brackets overlap and sum to
     # more than the backward pass), so they are reported in phase_ms but not used as the roofline kernel.
-    raster = {k: v for k, v in phase_ms.items() if k in ("tile_z", "shade")}
+    raster = {k: v for k, v in phase_ms.items() if k in ("tile_z", "shade", "bin")}
     if raster:
         kernel = max(raster, key=raster.get)
         t_k, b_k = raster[kernel], kernel_bytes[kernel]
         achieved = b_k / (t_k * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}).get(kernel)
+            doc = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = doc.get(args.workload, {}).get(kernel)
+            traffic_src = doc.get("source")
         except Exception:
             pass
         roofline = {
             "bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+            "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": b_k, "kernel_ms": round(t_k, 4),
             "phase_ms": {k: round(v, 4) for k, v in phase_ms.items()},
-            "phase_note": "edge_order/edge_tile_sort overlap bin_fill..shade; edge_bwd, interior_bwd and "
-                          "small_tri_bwd overlap each other (forked streams): brackets, not exclusive times",
+            "phase_note": "per launch (one view); edge_bin/edge_tile_sort overlap tile_z..shade; edge_bwd, interior_bwd "
+                          "and small_tri_bwd overlap each other (forked streams): brackets, not exclusive times; "
+                          "`plan` only appears when a plan was (re)built",
             "step_algorithmic_bytes": b_fwd + b_bwd,
             "step_frac_of_peak": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak, 4),
         }
+    elif graph is not None:
+        roofline = {"bound": "hbm", "kernel": "whole step (CUDA graph replay: no per-kernel events)", "peak": peak,
+                    "unit": "GB/s", "achieved": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9, 1),
+                    "frac": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                    "peak_source": peak_src, "step_algorithmic_bytes": b_fwd + b_bwd}
 
     # ---- end to end through the reference-facing plugin call with HOST (numpy fp64) buffers
     e2e = None
@@ -279,14 +375,29 @@ def run_ours(args):
         "config": {
             "workload": f"{args.workload}: {WORKLOADS[args.workload][5]}",
             "triangles": int(scene.faces.shape[0]), "vertices": int(scene.depths.shape[0]), "height": H, "width": W,
-            "nb_colors": C, "sigma": SIGMA, "views_per_gpu": 1,
-            "parallelism": f"views x{world}" + (" + NCCL all-reduce(colors_b)" if world > 1 else ""),
+            "nb_colors": C, "sigma": SIGMA, "views_per_gpu": per_gpu,
+            "renders_per_view": "RGB (C=3) + depth (C=1)" if depth_too else "RGB (C=3)" if C == 3 else f"C={C}",
+            "parallelism": f"views x{world}" + (" + NCCL all-reduce of the shared gradients" +
+                                                (" overlapped with the next forward (colours-ready event)" if overlap else "")
+                                                if world > 1 else ""),
+            "cuda_graph": graph is not None,
             "l2_policy": "inputs larger than L2: each step touches >= %.0f MB (algorithmic) vs 126 MB L2" % ((b_fwd + b_bwd) / 1e6),
         },
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
+
+
+def graph_launches(renderer, step):
+    """Kernels of one step, counted on an eager run of the same step (a replayed graph does not go through the library)."""
+    import torch
+
+    renderer.set_deferred(False)
+    before = renderer.launches
+    step()
+    torch.cuda.synchronize()
+    return renderer.launches - before
 
 
 def run_e2e(args, scene, world, dev):
@@ -384,10 +495,12 @@ def run_reference(args):
     threads = max(1, min(os.cpu_count() or 1, args.cpu_threads))
     for _ in range(min(args.warmup, 1)):
         time_cpu(scene, threads, 1)
-    res = time_cpu(scene, threads, max(1, min(args.steps, args.ref_steps)))
+    repeats = max(1, min(args.steps, args.ref_steps))
+    res = time_cpu(scene, threads, repeats)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(res["seconds_per_step"] * 1e3, 2),
+        # the steps actually TIMED (bounded sample: one step = `threads` concurrent fwd+bwd of the workload's view)
+        "steps": repeats, "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(res["seconds_per_step"] * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][5]}", "threads": threads,
                    "bounded_sample": res["sample"]},
@@ -405,6 +518,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--views-per-gpu", type=int, default=0, help="views rendered per step and GPU (0: 8 for c4, else 1)")
+    ap.add_argument("--graph", action="store_true", help="replay the whole step as one CUDA graph (N = 1)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce on the compute stream (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10, help="cap on the e2e (host-buffer) timed steps")

@@ -163,6 +163,7 @@ SYMBOLS = [
     ("deodr_b200_workspace_set_deferred", C.c_int, [C.c_void_p, C.c_int]),
     ("deodr_b200_workspace_status", C.c_int, [C.c_void_p]),
     ("deodr_b200_view_generation", C.c_int64, [C.c_void_p, C.c_int]),
+    ("deodr_b200_workspace_set_colors_ready", C.c_int, [C.c_void_p, C.c_void_p]),
     ("deodr_b200_project_points", C.c_int,
      [C.c_void_p, C.c_int, C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("deodr_b200_project_points_b", C.c_int,

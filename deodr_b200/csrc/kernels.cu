@@ -700,6 +700,7 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
         (s.perspective_correct ? k_tile_z<true> : k_tile_z<false>)<<<v->num_tiles < persistent ? v->num_tiles : persistent, NT, 0, st>>>(
             s, div, v->num_tiles, bins, ties, io.z_buffer, io.owner, io.face_id, v->scal, v->large_tiles.as<int>());
     }
+    if (ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, 0);  // first reader of the colours on this chain
     {
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
         (s.perspective_correct ? (tex ? k_shade<MAXC, true, true> : k_shade<MAXC, true, false>)
@@ -760,6 +761,7 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
     bool first_fork = true;
     cudaStream_t se = fork_stream(ws, lane, 0, &first_fork);
     if (edge_chain) {
+        if (ws->colors_ready) cudaStreamWaitEvent(se, ws->colors_ready, 0);  // the edge records hold end-point colours
         const EdgeBins ebins{{v->edge_offset.as<int>(), v->edge_cursor}, v->edge_refs_tmp.as<int>(), v->scal + SC_OVERFLOW};
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BIN, se);
@@ -899,6 +901,7 @@ static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneVi
         v->fwd_valid = 1;
     }
     close_lanes(ws, st, used);
+    ws->colors_ready = nullptr;  // one-shot
     if (deferred) return DEODR_B200_OK;
     // ---- verdicts: every pass is already queued, the device does not wait for this
     for (int i = 0; i < n_views; i++) {
@@ -1112,18 +1115,31 @@ int deodr_b200_workspace_set_deferred(DeodrWorkspace *ws, int on) {
 int deodr_b200_workspace_status(DeodrWorkspace *ws) {
     if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
     CUDA_TRY(cudaSetDevice(ws->device));
-    CUDA_TRY(cudaDeviceSynchronize());  // every pending pass has raised its flag after this
+    CUDA_TRY(cudaDeviceSynchronize());  // every pass enqueued so far has published its verdict after this
     int overflowed = 0;
     for (ViewSlot *v : ws->slots) {
-        if (!v || !v->pending) continue;
-        bool overflow = false;
-        if (int rc = read_verdict(ws, v, (cudaStream_t)0, &overflow)) return rc;
-        if (overflow) overflowed++;
+        if (!v) continue;
+        // a captured graph re-publishes with the sequence number it was captured with, so the flag cannot tell a new
+        // verdict from an old one: after the synchronisation the pinned words ARE the verdict of the slot's last pass
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        v->pending = false;
+        if (((volatile int *)v->host_totals)[SC_OVERFLOW]) {
+            v->host_totals[SC_OVERFLOW] = 0;
+            v->plan.valid = false;
+            v->fwd_valid = 0;
+            overflowed++;
+        }
     }
     if (overflowed)
         return set_error(DEODR_B200_EREPLAN,
                          "a forward pass overflowed the lists its plan had reserved: its results are void, the plan has "
                          "been dropped - run the pass again (outside a stream capture) to rebuild it");
+    return DEODR_B200_OK;
+}
+
+int deodr_b200_workspace_set_colors_ready(DeodrWorkspace *ws, void *event) {
+    if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
+    ws->colors_ready = (cudaEvent_t)event;
     return DEODR_B200_OK;
 }
 

@@ -117,6 +117,7 @@ struct DeodrWorkspace {
     bool overlap = true;   // DEODR_B200_SERIAL=1 keeps every launch on the caller's stream (profiling, A/B)
     bool deferred = false; // the entry points never read the verdict (CUDA-graph capture); see deodr_b200_workspace_status
     int replans = 0;       // number of plans (re)built so far
+    cudaEvent_t colors_ready = nullptr;  // one-shot: the next forward's colour readers wait for it (not owned)
     int num_lanes = 2;
     Lane lanes[MAX_LANES];
     std::vector<ViewSlot *> slots;

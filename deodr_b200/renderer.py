@@ -182,6 +182,14 @@ class Renderer:
         with self._lock:
             _cabi.check(self.lib.deodr_b200_workspace_status(self._ws))
 
+    def set_colors_ready(self, event: Optional["torch.cuda.Event"]) -> None:
+        """The next forward call makes only its colour readers (shading, edge records) wait for ``event`` - recorded by
+        the caller on the stream where the all-reduce of ``colors_b`` and the optimiser update run - so that they overlap
+        the binning and z pass of that forward (deodr_b200_workspace_set_colors_ready).  One-shot."""
+        with self._lock:
+            _cabi.check(self.lib.deodr_b200_workspace_set_colors_ready(
+                self._ws, event.cuda_event if event is not None else None))
+
     def generation(self, view: int = 0) -> int:
         return int(self.lib.deodr_b200_view_generation(self._ws, int(view)))
 

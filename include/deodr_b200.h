@@ -188,6 +188,13 @@ int deodr_b200_render_b_views(DeodrWorkspace *ws, int n_views, const DeodrSceneV
 int deodr_b200_workspace_set_deferred(DeodrWorkspace *ws, int on);
 int deodr_b200_workspace_status(DeodrWorkspace *ws);
 
+/* "Colours ready" event (a cudaEvent_t, or NULL): the NEXT forward call makes only the kernels that read the vertex
+ * colours (k_shade, the silhouette-edge records) wait for it; the geometry half of the pass - binning and the z pass,
+ * more than half of its duration - starts at once.  This is how the all-reduce of the shared colour gradient and the
+ * optimiser update that follows it (on the caller's communication stream, which records the event) overlap the next
+ * step instead of sitting between two steps.  One-shot: consumed by that call. */
+int deodr_b200_workspace_set_colors_ready(DeodrWorkspace *ws, void *event);
+
 /* Stamp of the last forward pass that ran in slot `view` (0 = none yet): lets a caller that keeps several forward
  * results alive (autograd) detect that the slot has been reused before it runs the adjoint. */
 int64_t deodr_b200_view_generation(const DeodrWorkspace *ws, int view);

@@ -1,0 +1,313 @@
+"""GPU (-m gpu): what round 2 added to the device-level C-ABI - batches of views (BASELINE configs[3]),
+plans and their verdicts (no read-back inside a pass, transparent re-plan, deferred mode + CUDA-graph capture), forward
+generation stamps, the antialiase_error mode (row f3) and the G-buffer weights (row f4).  Same tolerances as
+tests/test_gpu_parity.py."""
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+from test_gpu_parity import GRAD_RTOL, IMAGE_TOL, assert_gradient_close
+
+from deodr_b200.scenes import confetti_scene, dense_image_b, soup_scene, torus_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(build_native):
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from deodr_b200.renderer import Renderer
+
+    return Renderer(0)
+
+
+def _oracle_views(checker, scenes, sigma, image_bs, threads=16):
+    def one(i):
+        image, z = checker.render(scenes[i], sigma)
+        return image, z, checker.render_b(scenes[i], sigma, image, z, image_bs[i])
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:  # ctypes releases the GIL
+        return list(pool.map(one, range(len(scenes))))
+
+
+def _shared_grads(ds):
+    import torch
+
+    t = ds.t
+    return {k: torch.zeros(t[n].shape, dtype=torch.float32, device=ds.device)
+            for k, n in (("colors_b", "colors"), ("uv_b", "uv"), ("shade_b", "shade"), ("texture_b", "texture"))}
+
+
+def _run_batch(gpu, scenes, sigma, image_bs):
+    """render_views + render_b_views with per-view ij_b and SHARED colour / uv / shade / texture gradients."""
+    import torch
+
+    from deodr_b200.renderer import DeviceScene
+
+    dss = [DeviceScene(s, "cuda:0") for s in scenes]
+    fwds = gpu.render_views(dss, sigma)
+    shared = _shared_grads(dss[0])
+    grads = [dict(shared, ij_b=torch.zeros(ds.t["ij"].shape, dtype=torch.float32, device="cuda:0")) for ds in dss]
+    gpu.render_b_views(dss, sigma, fwds, [torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).cuda() for b in image_bs], grads)
+    torch.cuda.synchronize()
+    return fwds, grads, shared
+
+
+def _check_batch(gpu, checker, scenes, sigma):
+    rng = np.random.default_rng(5)
+    image_bs = [rng.random((s.height, s.width, s.nb_colors)) * 2 - 1 for s in scenes]
+    ref = _oracle_views(checker, scenes, sigma, image_bs)
+    fwds, grads, shared = _run_batch(gpu, scenes, sigma, image_bs)
+    for i, (image, z, g) in enumerate(ref):
+        assert np.array_equal(fwds[i]["z_buffer"].cpu().numpy(), z), f"view {i}: z-buffer not bit-exact"
+        assert np.abs(fwds[i]["image"].cpu().numpy() - image).max() <= IMAGE_TOL
+        assert_gradient_close(grads[i]["ij_b"].cpu().numpy(), g["ij_b"], f"view {i} ij_b")
+    for name in ("colors_b", "uv_b", "shade_b", "texture_b"):  # the `+=` of deodr/mesh_fitter.py:518-527
+        total = sum(g[name] for _, _, g in ref)
+        if total.size:
+            assert_gradient_close(shared[name].cpu().numpy(), total, f"summed {name}")
+
+
+def test_batch_of_views_small(gpu, checker):
+    views = 5
+    _check_batch(gpu, checker, [torus_scene(40, 160, 128, view=v, n_views=views) for v in range(views)], 1.0)
+    _check_batch(gpu, checker, [torus_scene(30, 96, 80, view=v, n_views=3, nb_colors=1) for v in range(3)], 1.0)
+    _check_batch(gpu, checker, [torus_scene(24, 120, 90, view=v, n_views=4, textured=True, texture_size=32) for v in range(4)], 1.5)
+
+
+def test_config4_64_views_512_rgb_and_depth(gpu, checker):
+    """BASELINE.json configs[3]: batch of 64 views x 512x512 of a 200k-triangle mesh, RGB (C = 3) and depth (C = 1)
+    renders, every view against the reference core, shared gradients against the sequential `+=` accumulation."""
+    views = 64
+    rgb = [torus_scene(316, 512, 512, view=v, n_views=views) for v in range(views)]
+    assert rgb[0].faces.shape[0] == 199712
+    _check_batch(gpu, checker, rgb, 1.0)
+    depth = [torus_scene(316, 512, 512, view=v, n_views=views, nb_colors=1) for v in range(views)]
+    for s in depth:  # depth render: the vertex "colour" is its depth (MeshDepthFitter, deodr/mesh_fitter.py:96-111)
+        s.colors = np.ascontiguousarray(s.depths[:, None])
+        s.background_color = np.array([float(s.depths.max())])
+    _check_batch(gpu, checker, depth, 1.0)
+
+
+def test_forward_generation_guard(gpu, checker, texture):
+    """Two forwards on one renderer slot, then the adjoint of the FIRST: refused (Python layer) / EINVAL (C-ABI) instead
+    of silently running on the second forward's lists; the autograd Function replays its forward and stays correct."""
+    import torch
+
+    from deodr_b200 import _cabi
+    from deodr_b200.pytorch import CudaDifferentiableRender2D
+    from deodr_b200.renderer import DeviceScene
+
+    import copy
+
+    np.random.seed(2)
+    a = soup_scene(clockwise=True, textured_ratio=0.0, texture=texture)
+    b = copy.copy(a)  # the same soup with its vertices moved: what two optimiser states of one scene look like
+    b.ij = a.ij + np.random.default_rng(3).normal(scale=1.5, size=a.ij.shape)
+    da, db = DeviceScene(a, "cuda:0"), DeviceScene(b, "cuda:0")
+    fa = gpu.render(da, 1.0)
+    fb = gpu.render(db, 1.0)
+    assert fb["generation"] == fa["generation"] + 1
+    with pytest.raises(RuntimeError, match="overwritten"):
+        gpu.render_b(da, 1.0, fa, torch.zeros_like(fa["image"]))
+    stale = dict(fa, generation=None)  # bypass the Python check: the library compares the z_buffer / owner arrays
+    with pytest.raises(_cabi.DeodrB200Error, match="must follow render"):
+        gpu.render_b(da, 1.0, stale, torch.zeros_like(fa["image"]))
+    gpu.render_b(db, 1.0, fb, torch.zeros_like(fb["image"]))  # the live one is fine
+
+    # autograd: two renders of the SAME DeviceScene with different inputs before one backward
+    image_a, z_a = checker.render(a, 1.0)
+    image_b, z_b = checker.render(b, 1.0)
+    obs = np.random.default_rng(1).random(image_a.shape)
+    ref_a = checker.render_b(a, 1.0, image_a, z_a, 2 * (image_a - obs))
+    ref_b = checker.render_b(b, 1.0, image_b, z_b, 2 * (image_b - obs))
+    ij_a = torch.tensor(a.ij, device="cuda", requires_grad=True)
+    ij_b = torch.tensor(b.ij, device="cuda", requires_grad=True)
+    col = torch.tensor(a.colors, device="cuda", dtype=torch.float32, requires_grad=True)
+    target = torch.tensor(obs, device="cuda", dtype=torch.float32)
+    la = torch.sum((CudaDifferentiableRender2D(ij_a, col, da, 1.0) - target) ** 2)
+    lb = torch.sum((CudaDifferentiableRender2D(ij_b, col, da, 1.0) - target) ** 2)
+    (la + lb).backward()
+    assert_gradient_close(ij_a.grad.cpu().numpy(), ref_a["ij_b"], "ij_a")
+    assert_gradient_close(ij_b.grad.cpu().numpy(), ref_b["ij_b"], "ij_b")
+    assert_gradient_close(col.grad.cpu().numpy(), ref_a["colors_b"] + ref_b["colors_b"], "colors")
+
+
+def test_replan_is_transparent_and_deferred_mode_reports_it(checker):
+    """A scene of the same shape whose lists outgrow the plan: by default the call re-plans and re-runs (valid result,
+    replan counted); in deferred mode nothing is read inside the call and workspace_status() reports EREPLAN."""
+    import torch
+
+    from deodr_b200 import _cabi
+    from deodr_b200.renderer import DeviceScene, Renderer
+
+    gpu = Renderer(0)
+    sparse = confetti_scene(6000, 256, 192, size=1.2, seed=1, edge_ratio=0.05)
+    crowded = confetti_scene(6000, 256, 192, size=14.0, seed=2, edge_ratio=0.6)  # same T / H / W, far larger lists
+    assert sparse.faces.shape == crowded.faces.shape
+    image, z = checker.render(crowded, 1.0)
+    gpu.render(DeviceScene(sparse, "cuda:0"), 1.0)
+    out = gpu.render(DeviceScene(crowded, "cuda:0"), 1.0)
+    assert np.array_equal(out["z_buffer"].cpu().numpy(), z)
+    assert np.abs(out["image"].cpu().numpy() - image).max() <= IMAGE_TOL * max(1.0, np.abs(image).max())
+    # deferred: plan from the sparse scene, then the crowded one overflows it and says so afterwards
+    gpu2 = Renderer(0)
+    gpu2.render(DeviceScene(sparse, "cuda:0"), 1.0)
+    gpu2.set_deferred(True)
+    dc = DeviceScene(crowded, "cuda:0")
+    fwd = gpu2.render(dc, 1.0)
+    grads = gpu2.render_b(dc, 1.0, fwd, torch.ones_like(fwd["image"]))
+    torch.cuda.synchronize()
+    assert all(float(g.abs().max()) == 0.0 for g in grads.values() if g.numel())  # a void pass accumulates nothing
+    with pytest.raises(_cabi.DeodrB200Error) as info:
+        gpu2.status()
+    assert info.value.code == _cabi.EREPLAN
+    gpu2.set_deferred(False)
+    out2 = gpu2.render(dc, 1.0)
+    assert np.array_equal(out2["z_buffer"].cpu().numpy(), z)
+    gpu2.status()
+
+
+def test_cuda_graph_capture_of_forward_and_adjoint(checker):
+    """fwd + bwd captured once in a CUDA graph (no host involvement inside the passes), replayed after the optimised
+    inputs were updated in place: same result as the eager calls."""
+    import torch
+
+    from deodr_b200.renderer import DeviceScene, Renderer
+
+    gpu = Renderer(0)
+    scene = torus_scene(23, 640, 480)  # configs[1]-sized stand-in
+    ds = DeviceScene(scene, "cuda:0")
+    image_b = torch.from_numpy(dense_image_b(np.zeros((480, 640, 3)), seed=3).astype(np.float32)).cuda()
+    grads = ds.zero_grads()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        out = gpu.render(ds, 1.0)                      # warm-up: builds the plan
+        gpu.render_b(ds, 1.0, out, image_b, grads)
+        torch.cuda.synchronize()
+        gpu.set_deferred(True)
+        graph = torch.cuda.CUDAGraph()
+        for g in grads.values():
+            g.zero_()
+        with torch.cuda.graph(graph, stream=stream):
+            for g in grads.values():
+                g.zero_()
+            gpu.render(ds, 1.0, out=out)
+            gpu.render_b(ds, 1.0, out, image_b, grads)
+        rng = np.random.default_rng(0)
+        for step in range(3):
+            moved = scene.ij + rng.normal(scale=0.05, size=scene.ij.shape)
+            ds.update(ij=moved)
+            graph.replay()
+            torch.cuda.synchronize()
+            gpu.status()  # the plan held
+            scene_k = torus_scene(23, 640, 480)
+            scene_k.ij = moved
+            image, z = checker.render(scene_k, 1.0)
+            ref = checker.render_b(scene_k, 1.0, image, z, image_b.cpu().numpy().astype(np.float64))
+            assert np.array_equal(out["z_buffer"].cpu().numpy(), z)
+            assert np.abs(out["image"].cpu().numpy() - image).max() <= IMAGE_TOL
+            assert_gradient_close(grads["ij_b"].cpu().numpy(), ref["ij_b"], "ij_b")
+            assert_gradient_close(grads["colors_b"].cpu().numpy(), ref["colors_b"], "colors_b")
+    gpu.set_deferred(False)
+
+
+@pytest.mark.parametrize("clockwise", [False, True])
+def test_antialiase_error_mode(clockwise, gpu, checker, texture):
+    """Row f3: the silhouette edges overdraw the squared residual (DR.h:2066-2618).  Forward: image (aliased), z-buffer
+    and err_buffer against the reference core; adjoint: bug-compatible with the reference's defect #2 by default, and
+    the complete adjoint against finite differences of the reference's own forward."""
+    import torch
+
+    from deodr_b200.renderer import DeviceScene
+
+    rng = np.random.default_rng(3)
+    np.random.seed(2)
+    scenes = [(soup_scene(clockwise=clockwise, texture=texture), 1.0),
+              (torus_scene(24, 160, 120), 1.0), (torus_scene(20, 90, 80, textured=True, texture_size=32), 2.0),
+              (confetti_scene(800, 48, 40, size=2.0, seed=4, edge_ratio=0.2), 1.0)]
+    for scene, sigma in scenes:
+        if scene.textured.any():
+            scene.uv = scene.uv * 0.9973 + 0.0131  # keep the texture coordinates off the texel grid
+        obs = rng.random((scene.height, scene.width, scene.nb_colors)).astype(np.float32).astype(np.float64)
+        image, z, err = checker.render(scene, sigma, antialiase_error=True, obs=obs)
+        ds = DeviceScene(scene, "cuda:0")
+        fwd = gpu.render(ds, sigma, obs=torch.from_numpy(obs).cuda())
+        assert np.array_equal(fwd["z_buffer"].cpu().numpy(), z)
+        assert np.abs(fwd["image"].cpu().numpy() - image).max() <= IMAGE_TOL
+        assert np.abs(fwd["err_buffer"].cpu().numpy() - err).max() <= 2e-6 * max(1.0, err.max())
+        err_b = rng.random((scene.height, scene.width)) * 2 - 1
+        ref = checker.render_b(scene, sigma, image, z, None, antialiase_error=True, obs=obs, err_buffer=err,
+                               err_buffer_b=err_b)
+        got = gpu.render_b(ds, sigma, fwd, err_buffer_b=torch.from_numpy(err_b).cuda())
+        for name in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b"):
+            if ref[name].size:
+                assert_gradient_close(got[name].cpu().numpy(), ref[name], name)
+
+
+def test_antialiase_error_complete_adjoint_matches_finite_differences(gpu, ref_oracle, texture):
+    """DEODR_B200_ERROR_ADJOINT_COMPLETE: the adjoint without the reference's dropped row term, against central finite
+    differences of the REFERENCE's forward pass (sum of err_buffer * weights as the scalar)."""
+    import torch
+
+    from deodr_b200.renderer import DeviceScene
+
+    np.random.seed(5)
+    scene = soup_scene(n_tri=12, width=64, height=64, textured_ratio=0.0, texture=texture[::4, ::4].copy(), min_det=200)
+    rng = np.random.default_rng(0)
+    obs = rng.random((64, 64, 3)).astype(np.float32).astype(np.float64)
+    weights = rng.random((64, 64))
+    ds = DeviceScene(scene, "cuda:0")
+    fwd = gpu.render(ds, 1.0, obs=torch.from_numpy(obs).cuda())
+    got = gpu.render_b(ds, 1.0, fwd, err_buffer_b=torch.from_numpy(weights).cuda(), error_adjoint_complete=True)
+    colors_b = got["colors_b"].cpu().numpy()
+
+    def loss(colors):
+        scene.colors = colors
+        _, _, err = ref_oracle.render(scene, 1.0, antialiase_error=True, obs=obs)
+        return float(np.sum(err * weights))
+
+    base = scene.colors.copy()
+    eps = 1e-5
+    worst = 0.0
+    for v in range(0, base.shape[0], 3):
+        for c in range(3):
+            hi, lo = base.copy(), base.copy()
+            hi[v, c] += eps
+            lo[v, c] -= eps
+            fd = (loss(hi) - loss(lo)) / (2 * eps)
+            worst = max(worst, abs(fd - colors_b[v, c]))
+    scene.colors = base
+    assert worst <= 2e-3 * np.abs(colors_b).max() + 1e-4, worst
+
+
+def test_barycentric_gbuffer(gpu, texture):
+    """Row f4: face id + interpolation weights as native forward outputs - the G-buffer that Scene3D.render_deferred
+    (deodr/differentiable_renderer.py:1053-1174) builds by interpolating 14 extra colour channels at sigma = 0.
+    Any per-vertex attribute interpolated with them equals the rasteriser's own interpolation of that attribute."""
+    import torch
+
+    from deodr_b200.renderer import DeviceScene
+
+    np.random.seed(3)
+    scene = soup_scene(n_tri=60, width=160, height=120, textured_ratio=0.0, texture=texture, min_det=500)
+    ds = DeviceScene(scene, "cuda:0")
+    out = gpu.render(ds, 0.0, face_id=True, barycentric=True)
+    fid = out["face_id"].cpu().numpy()
+    w = out["barycentric"].cpu().numpy()
+    image = out["image"].cpu().numpy()
+    covered = fid >= 0
+    assert np.allclose(w[covered].sum(axis=1), 1.0, atol=1e-5) and not w[~covered].any()
+    colors = scene.colors[scene.faces[fid[covered]]]                 # [n, 3 vertices, C]
+    assert np.abs(np.einsum("nv,nvc->nc", w[covered], colors) - image[covered]).max() <= 5e-6
+    # xyz / normal / uv channels of render_deferred are the same weights applied to other vertex attributes
+    attr = np.random.default_rng(0).random((scene.depths.shape[0], 5))
+    import copy
+
+    scene5 = copy.copy(scene)
+    scene5.colors, scene5.nb_colors = attr, 5
+    scene5.background_color, scene5.background_image, scene5.texture = np.zeros(5), None, np.zeros((2, 2, 5))
+    ref5 = gpu.render(DeviceScene(scene5, "cuda:0"), 0.0)["image"].cpu().numpy()
+    assert np.abs(np.einsum("nv,nvc->nc", w[covered], attr[scene.faces[fid[covered]]]) - ref5[covered]).max() <= 5e-6
