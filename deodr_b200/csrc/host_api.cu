@@ -105,11 +105,56 @@ struct HostPath {
     DeodrSceneView view;  // device view of the staged scene
     cudaStream_t stream = nullptr;
     cudaEvent_t chunk_event[MAX_EVENTS];
-    HostPath() : crew(crew_size()) {
+    explicit HostPath(CrewPlacement place) : crew(crew_size(), place) {
         memset(&meta, 0, sizeof(meta));
         memset(&view, 0, sizeof(view));
     }
 };
+
+// NUMA node of a CUDA device (sysfs, through its PCI bus id); -1 when unknown
+static int gpu_numa_node(int device) {
+    int node = -1;
+#if defined(__linux__)
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *p = bus; *p; p++) *p = (char)tolower(*p);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    if (FILE *f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+#endif
+    return node;
+}
+
+// Ranks of one job on one host (torchrun: LOCAL_RANK / LOCAL_WORLD_SIZE, rank r on device r): every rank keeps its crew,
+// its own thread and - allocated afterwards - its pinned buffers on the NUMA node of ITS GPU, and the ranks of a node
+// share the node's cores.  (Round 1 sliced the node the launcher happened to start the rank on: 3 workers per rank at
+// 8 ranks on a 2 x 32-core host, half of them across the inter-socket link from their GPU.)
+static CrewPlacement crew_placement(int device) {
+    CrewPlacement place;
+#if defined(__linux__)
+    const int local_world = getenv("LOCAL_WORLD_SIZE") ? atoi(getenv("LOCAL_WORLD_SIZE")) : 1;
+    if (local_world <= 1 || (getenv("DEODR_B200_HOST_NUMA") && atoi(getenv("DEODR_B200_HOST_NUMA")) == 0)) return place;
+    const int node = gpu_numa_node(device);
+    if (node < 0) return place;
+    int count = 0, index = 0, devices = 0;
+    cudaGetDeviceCount(&devices);
+    for (int d = 0; d < local_world && d < devices; d++) {
+        if (gpu_numa_node(d) != node) continue;
+        if (d < device) index++;
+        count++;
+    }
+    place.node = node;
+    place.index = index;
+    place.count = std::max(1, count);
+#endif
+    return place;
+}
 
 void deodr_host_path_destroy(DeodrWorkspace *ws) {
     if (!ws || !ws->host) return;
@@ -144,8 +189,22 @@ static int host_path(DeodrWorkspace *ws, HostPath **out) {
                     cpus.empty() ? -1 : cpus[0], bus, gpu_node);
         }
 #endif
-        HostPath *h = new (std::nothrow) HostPath();
+        const CrewPlacement place = crew_placement(ws->device);
+        HostPath *h = new (std::nothrow) HostPath(place);
         if (!h) return set_error(DEODR_B200_ENOMEM, "out of host memory");
+#if defined(__linux__)
+        if (place.node >= 0 && h->crew.caller_core() >= 0) {
+            // the rank's own thread moves to its slice of the node (the core its workers leave free, and theirs when
+            // they sleep) BEFORE the pinned buffers are allocated (first touch)
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (int c : h->crew.slice()) CPU_SET(c, &set);
+            sched_setaffinity(0, sizeof(set), &set);
+            if (getenv("DEODR_B200_TRACE"))
+                fprintf(stderr, "[deodr_b200 host path] device %d: NUMA node %d, rank %d of %d on it, %d workers, own core %d\n",
+                        ws->device, place.node, place.index, place.count, h->crew.workers(), h->crew.caller_core());
+        }
+#endif
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         for (auto &e : h->chunk_event) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ws->host = h;

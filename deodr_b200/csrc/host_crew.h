@@ -122,7 +122,8 @@ struct Batch {
 // CPUs of the NUMA node the calling thread runs on (Linux sysfs); empty when it cannot be determined.  The caller's
 // arrays and the pinned buffers were first touched from this thread, so the workers are kept on the same node: on a
 // two-socket host, workers of the other socket stream through the inter-socket link and slow everybody down.
-static std::vector<int> cpus_of_local_node() {
+// `want_node` >= 0 selects that node instead of the caller's (ranks of a multi-GPU job sit next to their GPU).
+static std::vector<int> cpus_of_local_node(int want_node = -1) {
     std::vector<int> cpus;
 #if defined(__linux__)
     if (getenv("DEODR_B200_HOST_PIN") && atoi(getenv("DEODR_B200_HOST_PIN")) == 0) return cpus;
@@ -148,21 +149,28 @@ static std::vector<int> cpus_of_local_node() {
             p = (*end == ',') ? end + 1 : end;
             if (*end != ',' ) break;
         }
-        if (std::find(list.begin(), list.end(), cpu) != list.end()) return list;
+        if (want_node >= 0 ? node == want_node : std::find(list.begin(), list.end(), cpu) != list.end()) return list;
     }
 #endif
     return cpus;
 }
 
+// Where a rank of a multi-GPU job on this host puts its crew: the NUMA node of its GPU, shared with `count` ranks of
+// which it is number `index` (host_api.cu works this out from the PCI bus ids).  node < 0: the caller's node, sliced by
+// LOCAL_RANK / LOCAL_WORLD_SIZE as a fallback.
+struct CrewPlacement {
+    int node = -1, index = 0, count = 1;
+};
+
 class Crew {
    public:
-    explicit Crew(int workers) {
+    explicit Crew(int workers, CrewPlacement place = CrewPlacement()) {
         // one worker per physical core of the caller's node (hyper-thread siblings and the caller's own core are left
         // alone): streaming loops gain nothing from sharing a core
         std::vector<int> cores;
 #if defined(__linux__)
-        const int self = sched_getcpu();
-        for (int c : cpus_of_local_node()) {
+        const int self = place.node >= 0 ? -1 : sched_getcpu();
+        for (int c : cpus_of_local_node(place.node)) {
             char path[128];
             snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list", c);
             int first = c;
@@ -188,7 +196,15 @@ class Crew {
         // Several ranks on one host (torchrun: LOCAL_RANK / LOCAL_WORLD_SIZE) must not pin their crews to the same
         // cores: each rank takes its own slice of the node's cores and a crew that fits it.
         int first = 0;
-        if (!getenv("DEODR_B200_HOST_THREADS")) {
+        if (place.node >= 0 && !cores.empty()) {
+            // the node's physical cores are split between the ranks whose GPU hangs off it: one core of the slice is
+            // left to the rank's own (coordinating) thread, the others run its workers
+            const int share = std::max(2, (int)cores.size() / std::max(1, place.count));
+            if (!getenv("DEODR_B200_HOST_THREADS")) workers = std::max(1, std::min(workers, share - 1));
+            first = (int)(((long)place.index * share + 1) % (long)cores.size());
+            caller_core_ = cores[(size_t)(((long)place.index * share) % (long)cores.size())];
+            for (int i = 0; i < share; i++) slice_.push_back(cores[(size_t)(((long)place.index * share + i) % (long)cores.size())]);
+        } else if (!getenv("DEODR_B200_HOST_THREADS")) {
             const int local_world = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
             const int local_rank = getenv("LOCAL_RANK") ? std::max(0, atoi(getenv("LOCAL_RANK"))) : 0;
             if (local_world > 1 && !cores.empty()) {
@@ -215,6 +231,8 @@ class Crew {
         for (auto &t : threads_) t.join();
     }
     int workers() const { return (int)threads_.size(); }
+    int caller_core() const { return caller_core_; }  // core set aside for the coordinating thread (-1: none)
+    const std::vector<int> &slice() const { return slice_; }  // the rank's share of its node's cores
     // the workers start on `b` at once; the caller coordinates (gates, DMAs) and then calls finish(b)
     void start(Batch *b) { publish(b); }
     // the caller helps with what is left, then waits until every task has retired and no worker still looks at `b`
@@ -273,6 +291,8 @@ class Crew {
         }
     }
     std::vector<std::thread> threads_;
+    int caller_core_ = -1;
+    std::vector<int> slice_;
     std::mutex mu_;
     std::condition_variable cv_[2];
     std::atomic<Batch *> current_{nullptr};

@@ -36,7 +36,7 @@
 
 // The binning pass (COUNT_ONLY = false) / the count pass that builds a plan (COUNT_ONLY = true): one thread per triangle.
 #ifndef DEODR_BIN_MIN_CTAS
-#define DEODR_BIN_MIN_CTAS 6
+#define DEODR_BIN_MIN_CTAS 8  // 61 registers, no spills (the 176-byte frame is the two tile-column mask arrays)
 #endif
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(128, DEODR_BIN_MIN_CTAS) k_bin(SceneView s, double sigma, int tiles_x, TriBins bins,
@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *sc
         unsigned long long v = 0;
 #pragma unroll
         for (int k = 0; k < SCAN_IPT; k++) {
-            const int raw = stage[scan_slot(first + k)];
+            // (bit 30 of a count: "the tile is touched by a triangle of the pixel-parallel adjoint", set by the count
+            // pass for record-path triangles that are not small: it only feeds the non-empty tally, a launch hint)
+            const int flagged = stage[scan_slot(first + k)];
+            const int raw = flagged < 0 ? -1 : (flagged & 0x3fffffff);
             c[k] = raw < 0 ? 0ull
-                           : (unsigned long long)(unsigned)(raw + (raw >> 2) + SEG_SLACK) | ((unsigned long long)(raw > 0) << 32);
+                           : (unsigned long long)(unsigned)(raw + (raw >> 2) + SEG_SLACK) | ((unsigned long long)(flagged > 0) << 32);
             v += c[k];
         }
         unsigned long long incl = v;
@@ -162,19 +165,20 @@ __global__ void __launch_bounds__(128) k_bin_edges(SceneView s, double sigma, in
         bin_edge<DevEnv>(s, i, sigma, tiles_x, edges, bins, recs);
 }
 
-// Orders every tile's edge list far to near (tile_edge_position, phases.h) and appends the tile to the two-ended list
-// the edge kernels walk: tiles with more than one chunk of edges at the front (they set those kernels' duration and
-// must start first), the others from the back.  One CTA per tile, most return at once; (key, id) pairs are staged in
-// shared memory 256 at a time.
+// Orders the edge list of every tile that has one far to near (tile_edge_position, phases.h) and moves the tile to the
+// two-ended list the edge kernels walk: tiles with more than one chunk of edges at the front (they set those kernels'
+// duration and must start first), the others from the back.  One CTA per entry of the arrival-order list k_bin_edges
+// built; (key, id) pairs are staged in shared memory 256 at a time.
 constexpr int SORT_CHUNK = 256;
 __global__ void __launch_bounds__(128) k_sort_tile_edges(TileSegments seg, int num_tiles, const int *refs_in,
-                                                         int *refs_out, const EdgeRec *recs, int *edge_tiles, int *scal) {
+                                                         int *refs_out, const EdgeRec *recs, const int *tiles_raw,
+                                                         int *edge_tiles, int *scal) {
     if (scal[SC_OVERFLOW]) return;
     __shared__ unsigned long long sk[SORT_CHUNK];
     __shared__ int si[SORT_CHUNK];
-    const int tile = blockIdx.x;
+    if ((int)blockIdx.x >= scal[SC_EDGE_TILES]) return;
+    const int tile = tiles_raw[blockIdx.x];
     const int n = segment_size(seg, tile), base = seg.offset[tile];
-    if (n == 0) return;
     if (threadIdx.x == 0) {
         if (n > EDGE_CHUNK) edge_tiles[atomicAdd(scal + SC_HEAVY_TILES, 1)] = tile;
         else edge_tiles[num_tiles - 1 - atomicAdd(scal + SC_LIGHT_TILES, 1)] = tile;
@@ -213,42 +217,6 @@ __global__ void k_publish(const int *scal, int *host_totals, int seq) {
     if (lane == 0) ((volatile int *)host_totals)[SC_WORDS] = seq;
 }
 
-// ---------------------------------------------------------------------------- TMA (bulk async copy) + mbarrier
-
-static __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-static __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-static __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-// global -> shared bulk copy (SASS: UBLKCP), completion signalled on `bar` as transaction bytes.
-// dst, src 16-byte aligned, bytes a multiple of 16.
-static __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 // Forward, kernel 1 of 3 - z-buffer and owner ids, one 16x16 tile per CTA (no colour work: few registers).
 // Small triangles: the tile's pre-masked records are pulled into shared memory by a bulk copy (cp.async.bulk +
 // mbarrier, SASS UBLKCP); two threads per record scatter its index into per-pixel candidate lists; each pixel then
@@ -259,11 +227,15 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 #ifndef DEODR_TILEZ_MIN_CTAS
 #define DEODR_TILEZ_MIN_CTAS 5  // 51 registers: 98.5 us vs 102.6 us at 64 and 123 us at 85 (measured, c5)
 #endif
-// PERSP: perspective_correct as a compile-time constant (the 1/z division and its registers leave the common instance)
-template <bool PERSP>
+// PERSP: perspective_correct as a compile-time constant (the 1/z division and its registers leave the common instance).
+// FUSE: the colour of every pixel is computed in this kernel's epilogue (the owner stays in registers: no owner map
+// re-read, no second launch); MAXC / TEX as in k_shade.  The unfused instance <1, PERSP, false, false> + k_shade is
+// what a forward uses when the colours arrive late (colours-ready event: the z pass then overlaps the all-reduce).
+template <int MAXC, bool PERSP, bool TEX, bool FUSE>
 __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s, TileDiv tiles_x, int num_tiles, TriBins bins, TieTable ties,
                                                   double *z_buffer, int *owner, int *face_id, int *scal,
-                                                  int *large_tiles) {
+                                                  int *large_tiles, float *image, const float *obs, float *err,
+                                                  float *bary, const __grid_constant__ TileMap image_map, int tma_store) {
     // a list outgrew the plan: the pass is void (the host re-plans and re-runs).  OVF_EDGE_REFS is left out: it is
     // raised by k_bin_edges, which runs beside this kernel, and the early return must be uniform across the CTA
     if (scal[SC_OVERFLOW] & ~OVF_EDGE_REFS) return;
@@ -272,6 +244,9 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
     __shared__ alignas(16) PreRec pre[2][PRE_CHUNK];
     __shared__ alignas(8) uint64_t bar[2];
     __shared__ int info[2][2];  // [buffer][0] = number of small records of the tile, [1] = offset of its list
+    // fused shading, up to 4 channels: the tile's colours are staged here and leave as ONE TMA tile store (UTMASTG)
+    // instead of C four-byte stores per pixel at a 4C-byte stride
+    __shared__ alignas(128) float stage[FUSE && MAXC <= 4 ? NT * MAXC : 4];
     const int tid = threadIdx.x;
     sh.tri.pix_cnt[tid] = 0;
     if (tid == 0) {
@@ -339,8 +314,6 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
         // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
         const int n_large = segment_size(bins.large, tile_id);
         if (n_large > 0) {
-            // the adjoint's pixel-parallel kernel walks the tiles that hold large triangles
-            if (tid == 0) large_tiles[atomicAdd(scal + SC_LARGE_TILES, 1)] = tile_id;
             const int *large = bins.large_refs + bins.large.offset[tile_id];
             for (int base = 0; base < n_large; base += LARGE_CHUNK) {
                 const int m = min(LARGE_CHUNK, n_large - base);
@@ -366,6 +339,36 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
             }
             owner[idx] = code;
             if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
+            if (FUSE) {
+                SceneView sc = s;
+                fix_channel_count<MAXC, TEX>(sc);
+                PixelState<MAXC> q;
+                q.own = p.own;
+                q.bown = p.bown;
+                q.z = PERSP && p.own >= 0 ? p.z : 0.0;
+                float w[3];
+                phase_shade<MAXC>(sc, x, y, &q, bary ? w : nullptr);
+                if (MAXC <= 4 && tma_store) {
+                    for (int k = 0; k < sc.nb_colors; k++) stage[tid * sc.nb_colors + k] = q.col[k];
+                } else {
+                    for (int k = 0; k < sc.nb_colors; k++) image[idx * sc.nb_colors + k] = q.col[k];
+                }
+                if (err) err[idx] = (float)pixel_residual<MAXC>(sc, q.col, obs + idx * sc.nb_colors);
+                if (bary) { bary[3 * idx] = w[0]; bary[3 * idx + 1] = w[1]; bary[3 * idx + 2] = w[2]; }
+            }
+        }
+        // the adjoint's pixel-parallel kernel walks the tiles where a pixel is owned by a triangle that the
+        // triangle-parallel adjoint does not take (medium and large triangles)
+        const bool other = inside && p.bown >= 0 && !(p.bown & SMALL_FLAG);
+        if (FUSE && MAXC <= 4 && tma_store) fence_proxy_async();  // this thread's staged colours -> visible to the TMA engine
+        const bool listed = __syncthreads_or(other);
+        if (tid == 0) {
+            if (listed) large_tiles[atomicAdd(scal + SC_LARGE_TILES, 1)] = tile_id;
+            if (FUSE && MAXC <= 4 && tma_store) {
+                // rows / columns of the box that stick out of the image are clipped by the hardware
+                tma_store_tile(&image_map, tile.x0 * s.nb_colors, tile.y0, stage);
+                tma_store_wait_read();  // the staging buffer is free again (next tile of a persistent launch / exit)
+            }
         }
     }
 }
@@ -419,8 +422,10 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_edge_fwd(Scene
     __shared__ TileShared sh;
     const int tid = threadIdx.x;
     const int heavy = et.scal[SC_HEAVY_TILES], total = heavy + et.scal[SC_LIGHT_TILES];
-    for (int b = blockIdx.x; b < total; b += gridDim.x) {
-        const int tile_id = two_ended_at(et.list, et.num_tiles, heavy, b);
+    // one CTA per entry of the list (the launch covers the plan's capacity; k_bin_edges raises OVF_EDGE_TILES beyond it)
+    if ((int)blockIdx.x >= total) return;
+    {
+        const int tile_id = two_ended_at(et.list, et.num_tiles, heavy, blockIdx.x);
         const int n_edge = segment_size(et.seg, tile_id);
         const Tile tile = tile_of(tile_id, tiles_x);
         const int r = tid / TS;
@@ -523,7 +528,7 @@ static int validate_view(const DeodrSceneView *v, bool backward) {
 static void free_slot(ViewSlot *v) {
     if (!v) return;
     DevBuf *bufs[] = {&v->zeroed, &v->small_offset, &v->large_offset, &v->edge_offset, &v->small_recs, &v->large_refs,
-                      &v->small_ids, &v->large_tiles, &v->edge_tiles, &v->edge_ids, &v->edge_keys, &v->edge_recs,
+                      &v->small_ids, &v->large_tiles, &v->edge_tiles, &v->edge_tiles_raw, &v->edge_ids, &v->edge_keys, &v->edge_recs,
                       &v->edge_refs_tmp, &v->edge_refs, &v->edge_spans, &v->edge_acc, &v->tie_pairs, &v->error_image_b};
     for (DevBuf *b : bufs) b->release();
     if (v->host_totals) cudaFreeHost(v->host_totals);
@@ -659,7 +664,8 @@ static int build_plan(DeodrWorkspace *ws, ViewSlot *v, const SceneView &s, doubl
     plan.tex = tot[SC_TEXTURED] != 0;
     plan.hint_small = T;
     plan.hint_edges = E;
-    plan.hint_edge_tiles = E > 0 ? tot[SC_PLAN_EDGE_TILES] + tot[SC_PLAN_EDGE_TILES] / 4 + 8 : 0;
+    plan.cap_edge_tiles = E > 0 ? std::min(nt, tot[SC_PLAN_EDGE_TILES] + tot[SC_PLAN_EDGE_TILES] / 4 + 8) : 0;
+    plan.hint_edge_tiles = plan.cap_edge_tiles;
     plan.hint_large_tiles = tot[SC_PLAN_LARGE_TILES] + tot[SC_PLAN_LARGE_TILES] / 4 + 8;
     int rc = 0;
     rc |= v->small_recs.ensure(((size_t)plan.cap_small + 1) * sizeof(PreRec), &ws->bytes);
@@ -671,6 +677,7 @@ static int build_plan(DeodrWorkspace *ws, ViewSlot *v, const SceneView &s, doubl
         rc |= v->edge_refs_tmp.ensure(((size_t)plan.cap_edge_refs + 4) * sizeof(int), &ws->bytes);
         rc |= v->edge_refs.ensure(((size_t)plan.cap_edge_refs + 4) * sizeof(int), &ws->bytes);
         rc |= v->edge_spans.ensure(((size_t)plan.cap_edge_refs + 4) * TS * sizeof(uint32_t), &ws->bytes);
+        rc |= v->edge_tiles_raw.ensure(((size_t)plan.cap_edge_tiles + 4) * sizeof(int), &ws->bytes);
     }
     if (rc) return DEODR_B200_ECUDA;
     plan.valid = true;
@@ -685,6 +692,9 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
     const bool tex = v->plan.tex != 0;
     const TileDiv div = make_tile_div(v->tiles_x);
     const TieTable ties = tie_table(v);
+    // shading fused into the z pass unless the colours arrive late (see k_tile_z) or DEODR_B200_FUSE_SHADE=0 (A/B)
+    static const bool fuse_allowed = !(getenv("DEODR_B200_FUSE_SHADE") && atoi(getenv("DEODR_B200_FUSE_SHADE")) == 0);
+    const bool fuse = fuse_allowed && !ws->colors_ready;
     {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
         // DEODR_B200_TILEZ_CTAS_PER_SM = k > 0 runs k persistent CTAs per SM with the two-stage TMA pipeline; default 0 =
@@ -697,23 +707,39 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
         static const int per_cta = getenv("DEODR_B200_TILEZ_TILES_PER_CTA") ? atoi(getenv("DEODR_B200_TILEZ_TILES_PER_CTA")) : 1;
         int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : v->num_tiles;
         if (per_sm <= 0 && per_cta > 1) persistent = (v->num_tiles + per_cta - 1) / per_cta;
-        (s.perspective_correct ? k_tile_z<true> : k_tile_z<false>)<<<v->num_tiles < persistent ? v->num_tiles : persistent, NT, 0, st>>>(
-            s, div, v->num_tiles, bins, ties, io.z_buffer, io.owner, io.face_id, v->scal, v->large_tiles.as<int>());
+        const int grid = v->num_tiles < persistent ? v->num_tiles : persistent;
+        const float *obs = err_mode ? io.obs : nullptr;
+        float *err = err_mode ? io.err_buffer : nullptr;
+        TileMap image_map;
+        memset(&image_map, 0, sizeof(image_map));
+        static const bool tma_allowed = !(getenv("DEODR_B200_TMA_TILES") && atoi(getenv("DEODR_B200_TMA_TILES")) == 0);
+        const int tma_store = fuse && tma_allowed && s.nb_colors <= 4 &&
+                              encode_tile_map(&image_map, io.image, 4, true, s.height, s.width * s.nb_colors, TS, TS * s.nb_colors);
+#define DEODR_TILE_Z(C_, P, X, F) k_tile_z<C_, P, X, F><<<grid, NT, 0, st>>>(s, div, v->num_tiles, bins, ties, io.z_buffer, io.owner, io.face_id, v->scal, v->large_tiles.as<int>(), io.image, obs, err, io.barycentric, image_map, tma_store)
+        if (!fuse) {
+            if (s.perspective_correct) DEODR_TILE_Z(1, true, false, false); else DEODR_TILE_Z(1, false, false, false);
+        } else if (s.perspective_correct) {
+            if (tex) DEODR_TILE_Z(MAXC, true, true, true); else DEODR_TILE_Z(MAXC, true, false, true);
+        } else {
+            if (tex) DEODR_TILE_Z(MAXC, false, true, true); else DEODR_TILE_Z(MAXC, false, false, true);
+        }
+#undef DEODR_TILE_Z
+        ws->launches++;
     }
-    if (ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, 0);  // first reader of the colours on this chain
-    {
+    if (!fuse) {
+        if (ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, 0);  // first reader of the colours on this chain
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
         (s.perspective_correct ? (tex ? k_shade<MAXC, true, true> : k_shade<MAXC, true, false>)
                                : (tex ? k_shade<MAXC, false, true> : k_shade<MAXC, false, false>))<<<v->num_tiles, NT, 0, st>>>(
             s, div, ties, io.owner, io.z_buffer, io.image, err_mode ? io.obs : nullptr, err_mode ? io.err_buffer : nullptr,
             io.barycentric, v->scal);
+        ws->launches++;
     }
-    ws->launches += 2;
     if (edge_chain) {
         join_stream(ws, lane, 0);  // the edge lists are ready
         PhaseTimer timer(ws, DEODR_B200_PH_EDGE_FWD, st);
         const EdgeTiles et = edge_tiles_of(v);
-        const int grid = at_least_one(v->plan.hint_edge_tiles < v->num_tiles ? v->plan.hint_edge_tiles : v->num_tiles);
+        const int grid = at_least_one(v->plan.cap_edge_tiles);
         uint32_t *spans = v->edge_spans.as<uint32_t>();
 #define DEODR_EDGE_FWD(P, X, R) k_edge_fwd<MAXC, P, X, R><<<grid, EDGE_NT, 0, st>>>(s, sigma, div, et, spans, io.z_buffer, io.image, io.obs, io.err_buffer)
         const int sel = (s.perspective_correct ? 4 : 0) | (tex ? 2 : 0) | (err_mode ? 1 : 0);
@@ -762,7 +788,8 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
     cudaStream_t se = fork_stream(ws, lane, 0, &first_fork);
     if (edge_chain) {
         if (ws->colors_ready) cudaStreamWaitEvent(se, ws->colors_ready, 0);  // the edge records hold end-point colours
-        const EdgeBins ebins{{v->edge_offset.as<int>(), v->edge_cursor}, v->edge_refs_tmp.as<int>(), v->scal + SC_OVERFLOW};
+        const EdgeBins ebins{{v->edge_offset.as<int>(), v->edge_cursor}, v->edge_refs_tmp.as<int>(), v->scal + SC_OVERFLOW,
+                             v->edge_tiles_raw.as<int>(), v->scal + SC_EDGE_TILES, plan.cap_edge_tiles};
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BIN, se);
             k_bin_edges<<<at_least_one(grid_for(plan.hint_edges, 128)), 128, 0, se>>>(s, sigma, v->tiles_x, edges, ebins,
@@ -770,14 +797,16 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
         }
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_TILE_SORT, se);
-            k_sort_tile_edges<<<nt, 128, 0, se>>>(ebins.seg, nt, v->edge_refs_tmp.as<int>(), v->edge_refs.as<int>(),
-                                                 v->edge_recs.as<EdgeRec>(), v->edge_tiles.as<int>(), v->scal);
+            k_sort_tile_edges<<<at_least_one(plan.cap_edge_tiles), 128, 0, se>>>(
+                ebins.seg, nt, v->edge_refs_tmp.as<int>(), v->edge_refs.as<int>(), v->edge_recs.as<EdgeRec>(),
+                v->edge_tiles_raw.as<int>(), v->edge_tiles.as<int>(), v->scal);
         }
         ws->launches += 2;
     }
     k_publish<<<1, 32, 0, se>>>(v->scal, v->host_totals, next_seq(v));
     ws->launches++;
     v->pending = true;
+    v->hints_exact = false;
     if (!ws->overlap || !edge_chain) {
         // (serial mode: everything is on the main stream already; without an edge chain the main chain does not
         // depend on the aux stream, but the lane must still be joined for stream capture / ordering of the next pass)
@@ -811,6 +840,7 @@ static int read_verdict(DeodrWorkspace *ws, ViewSlot *v, cudaStream_t st, bool *
     plan.hint_small = tot[SC_SMALL];
     plan.hint_edges = tot[SC_EDGES];
     plan.hint_edge_tiles = tot[SC_HEAVY_TILES] + tot[SC_LIGHT_TILES];
+    v->hints_exact = true;  // the adjoint of this pass can be launched for exactly these counts
     if (plan.tex && !tot[SC_TEXTURED]) plan.tex = 0;  // next pass: instances without the texture paths
     (void)ws;
     return DEODR_B200_OK;
@@ -1058,11 +1088,14 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
     ws->overlap = !(getenv("DEODR_B200_SERIAL") && atoi(getenv("DEODR_B200_SERIAL")));
     if (const char *e = getenv("DEODR_B200_LANES")) ws->num_lanes = atoi(e) < 1 ? 1 : (atoi(e) > MAX_LANES ? MAX_LANES : atoi(e));
+    int prio_low = 0, prio_high = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
     for (int l = 0; l < MAX_LANES; l++) {
         Lane &lane = ws->lanes[l];
         if (l > 0) CUDA_TRY(cudaStreamCreateWithFlags(&lane.main, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&lane.aux[i], cudaStreamNonBlocking));
+        for (int i = 0; i < LANE_AUX; i++) {
+            // the forward's side chain is short and the main chain waits for it at the join: its CTAs go first
+            CUDA_TRY(cudaStreamCreateWithPriority(&lane.aux[i], cudaStreamNonBlocking, i == 0 ? prio_high : prio_low));
             CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_join[i], cudaEventDisableTiming));
         }
         CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_fork, cudaEventDisableTiming));
@@ -1092,7 +1125,7 @@ void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     for (int l = 0; l < MAX_LANES; l++) {
         Lane &lane = ws->lanes[l];
         if (l > 0 && lane.main) cudaStreamDestroy(lane.main);
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < LANE_AUX; i++) {
             if (lane.aux[i]) cudaStreamDestroy(lane.aux[i]);
             if (lane.ev_join[i]) cudaEventDestroy(lane.ev_join[i]);
         }

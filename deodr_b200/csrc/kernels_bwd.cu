@@ -27,15 +27,26 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(Sce
                                                    const double *z_buffer,
                                                    const int *owner, const float *image_b, const float *obs,
                                                    const float *err_b, int compat, DeodrGrads grads,
-                                                   double *edge_acc) {
+                                                   double *edge_acc, const __grid_constant__ FrameMaps maps) {
     if (et.scal[SC_OVERFLOW]) return;
     fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
     __shared__ TileShared sh;
+    // the tile's image_b / owner / z-buffer blocks arrive as three TMA tile loads (UTMALDG) issued by one thread
+    __shared__ alignas(128) float t_img[MAXC <= 4 ? NT * MAXC : 4];
+    __shared__ alignas(128) int t_own[NT];
+    __shared__ alignas(128) double t_z[NT];
+    __shared__ alignas(8) uint64_t tile_bar;
     const int tid = threadIdx.x;
+    const bool tma_tiles = MAXC <= 4 && maps.ok;
+    if (tma_tiles) {
+        if (tid == 0) mbar_init(&tile_bar, 1);
+        __syncthreads();
+    }
     const int heavy = et.scal[SC_HEAVY_TILES], total = heavy + et.scal[SC_LIGHT_TILES];
-    for (int b = blockIdx.x; b < total; b += gridDim.x) {
-        const int tile_id = two_ended_at(et.list, et.num_tiles, heavy, b);
+    if ((int)blockIdx.x >= total) return;  // one CTA per entry of the list (launched for the plan's capacity)
+    {
+        const int tile_id = two_ended_at(et.list, et.num_tiles, heavy, blockIdx.x);
         const Tile tile = tile_of(tile_id, tiles_x);
         const int c = tid % TS, r = tid / TS;
         const int x = tile.x0 + c, y = tile.y0 + r;
@@ -51,12 +62,25 @@ __global__ void __launch_bounds__(EDGE_NT, DEODR_EDGE_MIN_CTAS) k_raster_bwd(Sce
         ea.g = 0.0;
         p.z = __longlong_as_double(0x7ff0000000000000LL);
         p.own = p.bown = -1;
-        if (inside) {
+        if (tma_tiles) {
+            if (tid == 0) {
+                mbar_expect_tx(&tile_bar, (uint32_t)(NT * (s.nb_colors * sizeof(float) + sizeof(int) + sizeof(double))));
+                tma_load_tile(t_img, &maps.image, tile.x0 * s.nb_colors, tile.y0, &tile_bar);
+                tma_load_tile(t_own, &maps.owner, tile.x0, tile.y0, &tile_bar);
+                tma_load_tile(t_z, &maps.z, tile.x0, tile.y0, &tile_bar);
+            }
+            mbar_wait(&tile_bar, 0);
+            if (inside) {
+                p.z = t_z[tid];
+                decode_owner(t_own[tid], ties, &p.own, &p.bown);
+                for (int k = 0; k < s.nb_colors; k++) a.g[k] = t_img[tid * s.nb_colors + k];
+            }
+        } else if (inside) {
             p.z = z_buffer[idx];
             decode_owner(owner[idx], ties, &p.own, &p.bown);
             for (int k = 0; k < s.nb_colors; k++) a.g[k] = image_b[idx * s.nb_colors + k];
-            if (ERR) ea.g = (double)err_b[idx];
         }
+        if (ERR && inside) ea.g = (double)err_b[idx];
         const float *obs_px = ERR ? obs + idx * s.nb_colors : nullptr;
 
         {
@@ -163,10 +187,12 @@ __global__ void __launch_bounds__(128, DEODR_SMALL_MIN_CTAS) k_small_tri_bwd(Sce
     if (scal[SC_OVERFLOW]) return;
     fix_channel_count<MAXC, TEX>(s);
     s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
-    const int num_small = scal[SC_SMALL];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_small; i += gridDim.x * blockDim.x)
-        small_triangle_adjoint<MAXC, DevEnv>(s, small_ids[i], tiles_x, edge_cursor, owner, ties.pairs, image_b,
-                                             grads.ij_b, grads.colors_b, grads.uv_b, grads.shade_b, grads.texture_b);
+    // one thread per entry (no stride loop: its registers cost this kernel its occupancy); the launch covers the exact
+    // count when the forward's verdict has been read, every triangle otherwise
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= scal[SC_SMALL]) return;
+    small_triangle_adjoint<MAXC, DevEnv>(s, small_ids[i], tiles_x, edge_cursor, owner, ties.pairs, image_b, grads.ij_b,
+                                         grads.colors_b, grads.uv_b, grads.shade_b, grads.texture_b);
 }
 
 __global__ void k_finalize_edges(SceneView s, EdgeList edges, const int *scal, double sigma, const double *edge_acc,
@@ -203,13 +229,20 @@ static void launch_bwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneV
         ws->launches++;
     }
     if (edges) {
-        cudaStream_t se = fork_stream(ws, lane, 0, &first);
+        cudaStream_t se = fork_stream(ws, lane, 1, &first);
         cudaMemsetAsync(v->edge_acc.ptr, 0, (size_t)plan.cap_edges * edge_acc_stride(C) * sizeof(double), se);
         const EdgeTiles et = edge_tiles_of(v);
-        const int grid = at_least_one(plan.hint_edge_tiles < v->num_tiles ? plan.hint_edge_tiles : v->num_tiles);
+        const int grid = at_least_one(v->hints_exact ? plan.hint_edge_tiles : plan.cap_edge_tiles);
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, se);
-#define DEODR_RASTER_BWD(X, R) k_raster_bwd<MAXC, X, R><<<grid, EDGE_NT, 0, se>>>(s, sigma, div, et, v->edge_spans.as<uint32_t>(), ties, io.z_buffer, io.owner, image_b, io.obs, io.err_buffer_b, compat, g, v->edge_acc.as<double>())
+        FrameMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        static const bool tma_allowed = !(getenv("DEODR_B200_TMA_TILES") && atoi(getenv("DEODR_B200_TMA_TILES")) == 0);
+        maps.ok = tma_allowed && C <= 4 &&
+                  encode_tile_map(&maps.image, image_b, 4, true, s.height, s.width * C, TS, TS * C) &&
+                  encode_tile_map(&maps.owner, io.owner, 4, false, s.height, s.width, TS, TS) &&
+                  encode_tile_map(&maps.z, io.z_buffer, 8, false, s.height, s.width, TS, TS);
+#define DEODR_RASTER_BWD(X, R) k_raster_bwd<MAXC, X, R><<<grid, EDGE_NT, 0, se>>>(s, sigma, div, et, v->edge_spans.as<uint32_t>(), ties, io.z_buffer, io.owner, image_b, io.obs, io.err_buffer_b, compat, g, v->edge_acc.as<double>(), maps)
             if (tex) { if (err_mode) DEODR_RASTER_BWD(true, true); else DEODR_RASTER_BWD(true, false); }
             else     { if (err_mode) DEODR_RASTER_BWD(false, true); else DEODR_RASTER_BWD(false, false); }
 #undef DEODR_RASTER_BWD
@@ -224,7 +257,7 @@ static void launch_bwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneV
     }
     const bool large = plan.cap_large > 0 && plan.hint_large_tiles > 0;
     if (large) {  // pixels owned by large triangles, tiles without silhouette edges
-        cudaStream_t sl = fork_stream(ws, lane, 1, &first);
+        cudaStream_t sl = fork_stream(ws, lane, 2, &first);
         PhaseTimer timer(ws, DEODR_B200_PH_INTERIOR_BWD, sl);
         const int grid = at_least_one(plan.hint_large_tiles < v->num_tiles ? plan.hint_large_tiles : v->num_tiles);
         (tex ? k_interior_bwd<MAXC, true> : k_interior_bwd<MAXC, false>)<<<grid, NT, 0, sl>>>(
@@ -233,12 +266,13 @@ static void launch_bwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneV
     }
     {
         PhaseTimer timer(ws, DEODR_B200_PH_SMALL_BWD, st);
-        (tex ? k_small_tri_bwd<MAXC, true> : k_small_tri_bwd<MAXC, false>)<<<at_least_one(grid_for(plan.hint_small, 128)), 128, 0, st>>>(
+        const int entries = v->hints_exact ? plan.hint_small : s.nb_triangles;
+        (tex ? k_small_tri_bwd<MAXC, true> : k_small_tri_bwd<MAXC, false>)<<<at_least_one(grid_for(entries, 128)), 128, 0, st>>>(
             s, v->tiles_x, v->small_ids.as<int>(), v->scal, edge_cursor, ties, io.owner, image_b, g);
         ws->launches++;
     }
-    if (edges) join_stream(ws, lane, 0);
-    if (large) join_stream(ws, lane, 1);
+    if (edges) join_stream(ws, lane, 1);
+    if (large) join_stream(ws, lane, 2);
 }
 
 

@@ -8,6 +8,7 @@
 
 #include "../../include/deodr_b200.h"
 #include "phases.h"
+#include "tma.cuh"
 #include "workspace.h"
 
 using namespace deodr;
@@ -130,6 +131,52 @@ struct EdgeTiles {
     TileSegments seg;       // edge references per tile
     const int *refs;        // ordered far to near
     const EdgeRec *recs;
+};
+
+// ---------------------------------------------------------------------------- TMA (bulk async copy) + mbarrier
+
+static __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+static __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+static __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// global -> shared bulk copy (SASS: UBLKCP), completion signalled on `bar` as transaction bytes.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+static __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+
+// Tensor maps over a view's framebuffers, for the kernels that move whole 16x16 tiles with the TMA engine; `ok` is false
+// when a buffer does not qualify (pitch / alignment / more than 4 channels): the kernels then use plain loads / stores.
+struct FrameMaps {
+    TileMap image;    // [H, W*C] fp32: forward output (stored) / image_b (loaded)
+    TileMap owner;    // [H, W] int32
+    TileMap z;        // [H, W] fp64
+    int ok;
 };
 
 // ------------------------------------------------------------------------------------------------- host side

@@ -154,7 +154,8 @@ enum {
     OVF_LARGE = 2,      // large-triangle references of a tile
     OVF_EDGES = 4,      // silhouette edges of the view
     OVF_EDGE_REFS = 8,  // edge references of a tile
-    OVF_TEXTURE = 16    // a textured triangle met by kernel instances compiled without the texture paths
+    OVF_TEXTURE = 16,   // a textured triangle met by kernel instances compiled without the texture paths
+    OVF_EDGE_TILES = 32 // more tiles with silhouette edges than the edge kernels were launched for
 };
 
 // device scalars of one forward pass (zeroed together with the segment cursors, one memset)
@@ -169,6 +170,7 @@ enum {
     SC_LIGHT_TILES = 7,  // the other edge tiles (back of the list)
     SC_LARGE_TILES = 8,  // tiles that hold large triangles
     SC_TICKET = 9,       // scan kernel: arrival counter of its CTAs
+    SC_EDGE_TILES = 13,  // tiles that received at least one silhouette edge (unordered list of k_bin_edges)
     SC_TOTAL_SMALL = 10, // plan building: reserved record / reference totals (with slack)
     SC_TOTAL_LARGE = 11,
     SC_TOTAL_EDGE_REFS = 12,
@@ -236,6 +238,15 @@ DEODR_HD int small_shift(int box_w) {  // log2 of the row stride
 DEODR_HD bool is_small(const TileBox &b, int box_w, int box_h) {
     return b.tx1 - b.tx0 <= 1 && b.ty1 - b.ty0 <= 1 && box_w <= 32 && (box_h << small_shift(box_w)) <= 64;
 }
+// Triangles that take the RECORD path of the forward pass (exact coverage masks computed once, by the binning thread):
+// at most two tile columns and RECORD_ROWS rows.  The small ones (above) are a subset - they also fit the 64-bit
+// ownership mask of the triangle-parallel adjoint; the others ("medium": e.g. 12 x 8 pixel triangles, 7 % of the drawn
+// triangles of the 1M-triangle scene) are owned without SMALL_FLAG and go through the pixel-parallel adjoint.
+// Everything else ("large") is binned by reference and set up inside the tile kernel.
+constexpr int RECORD_ROWS = 64;
+DEODR_HD bool takes_record_path(const TileBox &b, int box_w, int box_h) {
+    return b.tx1 - b.tx0 <= 1 && box_w <= 32 && box_h <= RECORD_ROWS;
+}
 
 // 16-bit coverage mask of tile row y for one triangle (exact spans of rmath.h, clipped to the tile).
 DEODR_HD uint32_t tri_row_mask(const SceneView &s, const TriGeom &g, int y, int tile_x0) {
@@ -261,7 +272,7 @@ DEODR_HD uint32_t tri_pair_mask(const SceneView &s, const TriGeom &g, int y_firs
 }
 
 template <class Env>
-DEODR_HD void bin_flush_small(int k, const TriGeom &g, int tiles_x, int tx, int ty, const uint32_t *mask,
+DEODR_HD void bin_flush_small(int code, const TriGeom &g, int tiles_x, int tx, int ty, const uint32_t *mask,
                               const TriBins &bins) {
     uint32_t any = 0;
     for (int p = 0; p < TS / 2; p++) any |= mask[p];
@@ -271,18 +282,18 @@ DEODR_HD void bin_flush_small(int k, const TriGeom &g, int tiles_x, int tx, int 
     PreRec rec;
     for (int p = 0; p < TS / 2; p++) rec.mask[p] = mask[p];
     canonical_plane(g.zp, rec.zp);
-    rec.id = k | SMALL_FLAG;
+    rec.id = code;  // triangle index, | SMALL_FLAG when the triangle-parallel adjoint takes it
     rec.pad = 0;
     bins.small_recs[pos] = rec;
 }
 
-// Exact coverage masks of every tile a SMALL triangle really covers, one pre-masked record per such tile.
+// Exact coverage masks of every tile a record-path triangle really covers, one pre-masked record per such tile.
 // SIMT note: the loop runs over the triangle's ROWS (consecutive for every lane, so the lanes of a warp execute the
 // expensive span body together) and scatters each span into the masks of the <= 2 tile columns; a (tile, row-pair)
 // loop would make every lane wait for the bodies of all the others.
 template <class Env>
 DEODR_HD void bin_small(const SceneView &s, int k, const double V[3][2], const double Zv[3], const TileBox &b,
-                        int tiles_x, const TriBins &bins) {
+                        int tiles_x, const TriBins &bins) {  // k = owner code of the triangle
     TriGeom g;
     tri_geom(V, Zv, s.strict_edge != 0, s.perspective_correct != 0, &g, nullptr);
     int y_first, y_last;
@@ -356,17 +367,24 @@ DEODR_HD void bin_triangle(const SceneView &s, int k, double sigma, int tiles_x,
     int box_w, box_h;
     const TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height, &box_w, &box_h);
     if (b.tx0 > b.tx1) return;  // off screen
-    const bool small = is_small(b, box_w, box_h);
+    const bool records = takes_record_path(b, box_w, box_h);
     if (COUNT_ONLY) {
-        int *count = small ? bins.small.cursor : bins.large.cursor;
+        int *count = records ? bins.small.cursor : bins.large.cursor;
+        // a record-path triangle that is not small is owned through the pixel-parallel adjoint: bit 30 of the tile's
+        // large counter marks the tile for the plan's launch hint (k_scan_tiles masks it out of the capacity)
+        const bool medium = records && !is_small(b, box_w, box_h);
         for (int ty = b.ty0; ty <= b.ty1; ty++)
-            for (int tx = b.tx0; tx <= b.tx1; tx++) Env::atomic_add(&count[ty * tiles_x + tx], 1);
+            for (int tx = b.tx0; tx <= b.tx1; tx++) {
+                Env::atomic_add(&count[ty * tiles_x + tx], 1);
+                if (medium) Env::atomic_or(&bins.large.cursor[ty * tiles_x + tx], 0x40000000);
+            }
         return;
     }
-    if (small) {
+    if (records) {
+        const bool small = is_small(b, box_w, box_h);
         // the compact list of the drawn small triangles is what the triangle-parallel adjoint walks (capacity T)
-        small_ids[Env::atomic_add(num_small, 1)] = k;
-        bin_small<Env>(s, k, V, Zv, b, tiles_x, bins);
+        if (small) small_ids[Env::atomic_add(num_small, 1)] = k;
+        bin_small<Env>(s, small ? (k | SMALL_FLAG) : k, V, Zv, b, tiles_x, bins);
     } else {
         for (int ty = b.ty0; ty <= b.ty1; ty++)
             for (int tx = b.tx0; tx <= b.tx1; tx++) {
@@ -382,6 +400,9 @@ struct EdgeBins {
     TileSegments seg;
     int *refs;
     int *verdict;
+    int *tile_list;    // tiles that hold at least one edge, in arrival order (appended by the first edge of each tile)
+    int *tile_count;
+    int tile_capacity;
 };
 
 template <class Env>
@@ -393,8 +414,15 @@ DEODR_HD void bin_edge(const SceneView &s, int slot, double sigma, int tiles_x, 
     const TileBox b = edge_tile_box(V, sigma, s.width, s.height);
     for (int ty = b.ty0; ty <= b.ty1; ty++)
         for (int tx = b.tx0; tx <= b.tx1; tx++) {
-            const int pos = segment_reserve<Env>(bins.seg, ty * tiles_x + tx, bins.verdict, OVF_EDGE_REFS);
-            if (pos >= 0) bins.refs[pos] = slot;
+            const int t = ty * tiles_x + tx;
+            const int pos = segment_reserve<Env>(bins.seg, t, bins.verdict, OVF_EDGE_REFS);
+            if (pos < 0) continue;
+            bins.refs[pos] = slot;
+            if (pos == bins.seg.offset[t]) {  // first edge of the tile: the tile joins the list the edge kernels walk
+                const int at = Env::atomic_add(bins.tile_count, 1);
+                if (at < bins.tile_capacity) bins.tile_list[at] = t;
+                else Env::atomic_or(bins.verdict, OVF_EDGE_TILES);
+            }
         }
 }
 

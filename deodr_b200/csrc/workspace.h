@@ -64,6 +64,7 @@ struct FwdPlan {
     bool edges_possible = false;  // sigma > 0
     // reserved capacities
     int cap_small = 0, cap_large = 0, cap_edges = 0, cap_edge_refs = 0;
+    int cap_edge_tiles = 0;  // tiles with silhouette edges the edge kernels are launched for (one CTA each)
     int tex = 1;  // kernel instances with the texture paths compiled in
     // hints
     int hint_small = 0, hint_edge_tiles = 0, hint_large_tiles = 0, hint_edges = 0;
@@ -83,6 +84,7 @@ struct ViewSlot {
     DeodrViewIO fwd_io;
     bool fwd_check_indices = false;
     bool pending = false;     // a pass has been enqueued whose verdict has not been read yet
+    bool hints_exact = false; // the plan's hints are the counts of the slot's last pass (its verdict has been read)
     int totals_seq = 0;       // sequence number of the flag the publishing kernel raises in host_totals[SC_WORDS]
     int *host_totals = nullptr;  // pinned: SC_WORDS scalars + the sequence flag
     // device state
@@ -90,6 +92,7 @@ struct ViewSlot {
     int *scal = nullptr, *small_cursor = nullptr, *large_cursor = nullptr, *edge_cursor = nullptr;
     DevBuf small_offset, large_offset, edge_offset;  // [tiles + 1] segment offsets of the plan
     DevBuf small_recs, large_refs, small_ids;
+    DevBuf edge_tiles_raw;    // tiles with silhouette edges in arrival order (k_bin_edges)
     DevBuf large_tiles, edge_tiles;  // compact lists of the tiles with large triangles / silhouette edges (two-ended)
     DevBuf edge_ids, edge_keys, edge_recs, edge_refs_tmp, edge_refs;
     DevBuf edge_spans;        // x spans of every (tile, edge, row), written by k_edge_fwd and reused by k_raster_bwd
@@ -99,11 +102,13 @@ struct ViewSlot {
     DevBuf error_image_b;     // antialiase_error adjoint: colour adjoint of the pixels outside every edge band
 };
 
-// One lane = the stream a view's main chain runs on + two auxiliary streams for its side chains.
+// One lane = the stream a view's main chain runs on + auxiliary streams for its side chains: aux[0] (high priority)
+// the forward's short silhouette-edge chain, which the main chain waits for; aux[1], aux[2] the adjoint's concurrent kernels.
+constexpr int LANE_AUX = 3;
 struct Lane {
     cudaStream_t main = nullptr;  // lane 0: the caller's stream (not owned)
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t aux[LANE_AUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[LANE_AUX] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // lanes > 0: fork from / join to the caller's stream
 };
 

@@ -51,7 +51,11 @@ static EmulState g_state;
 static void scan_tiles(const std::vector<int> &count, std::vector<int> &offset) {
     int run = 0;
     offset.resize(count.size() + 1);
-    for (size_t i = 0; i < count.size(); i++) { offset[i] = run; run += count[i] + (count[i] >> 2) + 4; }
+    for (size_t i = 0; i < count.size(); i++) {
+        const int raw = count[i] & 0x3fffffff;  // bit 30: launch-hint flag of the count pass (see k_scan_tiles)
+        offset[i] = run;
+        run += raw + (raw >> 2) + 4;
+    }
     offset[count.size()] = run;
 }
 
@@ -299,7 +303,9 @@ static int emul_forward(const SceneView &s, double sigma, EmulState &st, float *
     st.edge_refs_tmp.assign(st.edge_offset[st.nt] + 4, -1);
     st.edge_refs.assign(st.edge_offset[st.nt] + 4, -1);
     if (!st.scal[SC_OVERFLOW]) {
-        EdgeBins ebins{st.edge_seg(), st.edge_refs_tmp.data(), st.scal + SC_OVERFLOW};
+        std::vector<int> tiles_raw(st.nt + 1, -1);
+        EdgeBins ebins{st.edge_seg(), st.edge_refs_tmp.data(), st.scal + SC_OVERFLOW, tiles_raw.data(),
+                       st.scal + SC_EDGE_TILES, st.nt};
         for (int i = st.E - 1; i >= 0; i--) bin_edge<HostEnv>(s, i, sigma, st.tiles_x, edges, ebins, st.edge_recs.data());
     }
     if (!st.scal[SC_OVERFLOW])

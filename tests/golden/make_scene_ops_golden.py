@@ -105,7 +105,10 @@ tmesh = ColoredTriMesh(tf, tv, clockwise=False, nb_colors=3)
 out["torus_face_normals"], out["torus_vertex_normals"] = tmesh.face_normals, tmesh.vertex_normals
 
 # ---- configs[1]: the Scene2D the reference's Scene3D hands to the raster core for the hand mesh at 640x480
-cam = dr.default_camera(640, 480, 60, vertices_h, Rotation.from_euler("yx", [0.4, 0.3]).as_matrix())
+# (camera of deodr/examples/render_mesh.py:26-29: half a turn about x - PerspectiveCamera composes `rot` in a way
+# that only frames the mesh for symmetric rotation matrices)
+cam = dr.default_camera(640, 480, 60, vertices_h, Rotation.from_euler("xyz", [180, 0, 0], degrees=True).as_matrix())
+out["view_extrinsic"], out["view_intrinsic"] = cam.extrinsic, cam.intrinsic
 scene.set_background_color([0.3, 0.5, 0.7])
 scene.camera = cam
 ij, depths = cam.project_points(vertices_h)
@@ -113,6 +116,8 @@ out["c2_ij"], out["c2_depths"] = ij, depths
 out["c2_colors"] = colors
 out["c2_edgeflags"] = np.asarray(adj.edge_on_silhouette(ij)).astype(np.uint8)
 out["c2_background_color"] = np.array([0.3, 0.5, 0.7])
+inside = (ij[:, 0] > 0) & (ij[:, 0] < 640) & (ij[:, 1] > 0) & (ij[:, 1] < 480)
+assert inside.mean() > 0.9, inside.mean()
 
 np.savez_compressed(os.path.join(HERE, "scene_ops.npz"), **out)
 print({k: v.shape for k, v in out.items()})

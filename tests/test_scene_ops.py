@@ -142,7 +142,7 @@ def test_device_resident_mesh_view_matches_the_numpy_chain(gold, build_native):
     from oracle.oracle import Oracle, available
 
     faces, vertices = gold["hand_faces"], gold["hand_vertices"]
-    cam = CameraParams(gold["cam_plain_extrinsic"], gold["cam_plain_intrinsic"])
+    cam = CameraParams(gold["view_extrinsic"], gold["view_intrinsic"])  # the camera of the configs[1] fixture
     light, ambient = gold["lum_light"], float(gold["lum_ambient"])
     view = DeviceMeshView(faces, vertices.shape[0], cam, 480, 640, light_directional=light, ambient=ambient,
                           background_color=(0.3, 0.5, 0.7))
@@ -150,7 +150,7 @@ def test_device_resident_mesh_view_matches_the_numpy_chain(gold, build_native):
     image = view.render(torch.from_numpy(vertices).cuda(), torch.from_numpy(vcol).cuda())
     # the same Scene2D from the reference-generated pieces
     topo = topology_arrays(faces, vertices.shape[0])
-    ij, depths = gold["cam_plain_ij"], gold["cam_plain_depths"]
+    ij, depths = gold["c2_ij"], gold["c2_depths"]
     T, V = faces.shape[0], vertices.shape[0]
     scene = SceneArrays(
         faces=faces, faces_uv=np.zeros((T, 3), np.uint32), ij=ij, depths=depths, textured=np.zeros(T, bool),
@@ -160,6 +160,7 @@ def test_device_resident_mesh_view_matches_the_numpy_chain(gold, build_native):
         clockwise=False, backface_culling=True, strict_edge=True, perspective_correct=False, integer_pixel_centers=True)
     oracle = Oracle("reference" if available("reference") else "port")
     image_ref, z_ref = oracle.render(scene, 1.0)
+    assert np.isfinite(z_ref).mean() > 0.05  # the hand is in the picture
     assert np.abs(image.cpu().numpy() - image_ref).max() < 2e-6
     image_b = dense_image_b(image_ref)
     g_ref = oracle.render_b(scene, 1.0, image_ref, z_ref, image_b)
@@ -171,4 +172,11 @@ def test_device_resident_mesh_view_matches_the_numpy_chain(gold, build_native):
     assert np.abs(got["vertex_colors_b"].cpu().numpy() - g_ref["colors_b"] * lum[:, None]).max() < 1e-4 * np.abs(g_ref["colors_b"]).max()
     light_b = np.concatenate((-np.sum((lum_b * (directional > 0))[:, None] * gold["lum_normals"], axis=0), [lum_b.sum()]))
     assert np.abs(got["light_b"].cpu().numpy() - light_b).max() < 1e-4 * np.abs(light_b).max()
-    assert np.isfinite(got["vertices_b"].cpu().numpy()).all() and np.abs(got["vertices_b"].cpu().numpy()).max() > 0
+    # vertices_b = camera adjoint of ij_b + normals adjoint of the luminosity chain, both checked piecewise above
+    from deodr_b200.mesh_ops import MeshTopology, project_points_backward
+
+    normals_b = -((lum_b * (directional > 0))[:, None]) * light
+    expect = MeshTopology(faces, V).vertex_normals_backward(torch.from_numpy(vertices).cuda(), torch.from_numpy(normals_b).cuda())
+    project_points_backward(torch.from_numpy(vertices).cuda(), cam, torch.from_numpy(g_ref["ij_b"]).cuda(), out=expect)
+    expect = expect.cpu().numpy()
+    assert np.abs(got["vertices_b"].cpu().numpy() - expect).max() < 1e-4 * np.abs(expect).max()
