@@ -39,6 +39,7 @@ WORKLOADS = {
     "c3": (158, 1024, 1024, True, 3, "50k-tri textured torus mesh (T=49928), 1024x1024, bilinear UV, sigma=1, fwd+bwd"),
     "c4": (316, 512, 512, False, 3, "200k-tri torus mesh (T=199712), 512x512 RGB view, sigma=1, fwd+bwd"),
     "c2": (23, 640, 480, False, 3, "1k-tri torus mesh (T=1058; stand-in for the 1048-face hand mesh), 640x480, fwd+bwd"),
+    "c3u": (158, 1024, 1024, False, 3, "c3 without the texture (development A/B)"),
     "dev": (100, 512, 512, False, 3, "development-size torus"),
 }
 METRIC = "fwd+bwd Mpixels/s"
@@ -218,24 +219,24 @@ def run_ours(args):
     ev_colors = torch.cuda.Event()
     overlap = world > 1 and not args.no_overlap
 
-    def step():
+    def step(wait_colors=True):
+        """One fitting step.  wait_colors=False: the colours are known to be in place (first step of a captured graph)."""
         nonlocal outs
         for ds, ij, col in zip(dss, ij_dev, colors_dev):      # per-iteration refresh of the optimised inputs
             ds.update(ij=ij)
         if overlap:
             # the colours are written by the "optimiser" on the communication stream (after the all-reduce of the
             # previous step): only the kernels of this forward that READ colours wait for that
-            renderer.set_colors_ready(ev_colors)
-        else:
-            for ds, col in zip(dss, colors_dev):
-                ds.update(colors=col)
-        if overlap:
+            if wait_colors:
+                renderer.set_colors_ready(ev_colors)
             # colors_b is zeroed on the communication stream once the all-reduce has consumed it
             flat[shared_end:].zero_()                         # the per-view ij_b
         else:
+            for ds, col in zip(dss, colors_dev):
+                ds.update(colors=col)
             flat.zero_()                                      # callers clear scene.*_b before every backward
         outs = renderer.render_views(dss, SIGMA, out=outs)
-        if overlap:
+        if overlap and wait_colors:
             torch.cuda.current_stream().wait_event(ev_colors)  # the adjoint accumulates into colors_b
         renderer.render_b_views(dss, SIGMA, outs, image_bs, grads)
         if world > 1:
@@ -259,49 +260,66 @@ def run_ours(args):
 
     if overlap:
         ev_colors.record(comm)
-    graph = None
     for _ in range(args.warmup):
         step()
+    if overlap:
+        torch.cuda.current_stream().wait_stream(comm)
     fence()
-    if args.graph and world == 1:
-        # the whole step captured once: nothing inside the passes touches the host (deferred verdicts)
-        renderer.set_deferred(True)
-        graph = torch.cuda.CUDAGraph()
-        cap = torch.cuda.Stream(device=dev)
-        with torch.cuda.stream(cap):
-            step()
+
+    # ---- the timed region replays the step as a CUDA graph (nothing inside the passes touches the host: deferred
+    # verdicts, checked after the region).  A graph holds `per_graph` consecutive steps so that, at N > 1, the all-reduce
+    # of one step overlaps the forward of the next INSIDE the graph; K must be a multiple of it.  --eager times the plain
+    # calls instead (also the fallback when a capture fails).
+    graph, per_graph, graph_note = None, 1, None
+    if world > 1 and not args.graph:
+        # N > 1: the step holds an NCCL collective on a second stream; capturing that did not terminate on the 2-GPU box
+        # (round 2), so the ranks time the plain calls - with the all-reduce overlapped - unless --graph insists
+        graph_note = "N > 1: eager calls, all-reduce overlapped through the colours-ready event"
+    elif not args.eager:
+        per_graph = 1 if world == 1 else max(d for d in (10, 5, 4, 2, 1) if args.steps % d == 0)
+        try:
+            renderer.set_deferred(True)
+            cap = torch.cuda.Stream(device=dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(cap):
+                with torch.cuda.graph(graph, stream=cap):
+                    for i in range(per_graph):
+                        step(wait_colors=i > 0)
+                    if overlap:
+                        torch.cuda.current_stream().wait_stream(comm)
+            for _ in range(2):
+                graph.replay()
+            fence()
+            renderer.status()
+        except Exception as exc:  # capture is an optimisation of the launch path, never a requirement
+            graph, per_graph = None, 1
+            graph_note = f"capture failed, eager calls timed instead: {type(exc).__name__}: {str(exc)[:200]}"
+            renderer.set_deferred(False)
             torch.cuda.synchronize()
-            with torch.cuda.graph(graph, stream=cap):
-                step()
-        for _ in range(3):
-            graph.replay()
-        torch.cuda.synchronize()
-        renderer.status()
+            if overlap:
+                ev_colors.record(comm)
+            step()
+            fence()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    if graph is None:
-        renderer.timing_enable(14 * args.steps * len(dss) + 16)
-    launches0 = renderer.launches
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    for _ in range(args.steps):
-        if graph is not None:
+    if graph is not None:
+        for _ in range(args.steps // per_graph):
             graph.replay()
-        else:
+    else:
+        for _ in range(args.steps):
             step()
-    if overlap:
-        torch.cuda.current_stream().wait_stream(comm)
+        if overlap:
+            torch.cuda.current_stream().wait_stream(comm)
     stop.record()
     fence()
     elapsed_ms = start.elapsed_time(stop)
-    launches = renderer.launches - launches0
-    if graph is not None:
-        renderer.status()  # raises if a replay overflowed its plan
-        launches = args.steps * graph_launches(renderer, step)
     clocks = sampler.stop() if rank == 0 else None
-    phases = renderer.timing_collect() if graph is None else []
-    renderer.timing_enable(0)
+    if graph is not None:
+        renderer.status()  # raises if a replayed pass overflowed its plan (its results would be void)
+        renderer.set_deferred(False)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -309,6 +327,29 @@ def run_ours(args):
     ms_per_step = elapsed_ms / args.steps
     pixels_per_step = world * sum(s.height * s.width for s in scenes)
     value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- second region, same process, same K steps through the plain (eager) calls with the library's per-kernel CUDA
+    # events switched on: kernel durations for the roofline, launch count, and the eager step time next to the replayed one
+    if overlap:
+        ev_colors.record(comm)
+    step()
+    fence()
+    renderer.timing_enable(14 * args.steps * len(dss) + 16)
+    launches0 = renderer.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    if overlap:
+        torch.cuda.current_stream().wait_stream(comm)
+    e1.record()
+    fence()
+    eager_ms = e0.elapsed_time(e1) / args.steps
+    launches = renderer.launches - launches0
+    phases = renderer.timing_collect()
+    renderer.timing_enable(0)
+    if graph is None:
+        graph_note = graph_note or "--eager"
 
     # ---- per-kernel durations inside the timed region -> roofline of the dominant kernel
     per_phase = {}
@@ -341,17 +382,12 @@ def run_ours(args):
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": b_k, "kernel_ms": round(t_k, 4),
             "phase_ms": {k: round(v, 4) for k, v in phase_ms.items()},
-            "phase_note": "per launch (one view); edge_bin/edge_tile_sort overlap tile_z..shade; edge_bwd, interior_bwd "
+            "phase_note": "measured in the eager region that follows the timed one (same process, same K steps), per launch (one view); edge_bin/edge_tile_sort overlap tile_z..shade; edge_bwd, interior_bwd "
                           "and small_tri_bwd overlap each other (forked streams): brackets, not exclusive times; "
                           "`plan` only appears when a plan was (re)built",
             "step_algorithmic_bytes": b_fwd + b_bwd,
             "step_frac_of_peak": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak, 4),
         }
-    elif graph is not None:
-        roofline = {"bound": "hbm", "kernel": "whole step (CUDA graph replay: no per-kernel events)", "peak": peak,
-                    "unit": "GB/s", "achieved": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9, 1),
-                    "frac": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak, 4), "traffic": None,
-                    "peak_source": peak_src, "step_algorithmic_bytes": b_fwd + b_bwd}
 
     # ---- end to end through the reference-facing plugin call with HOST (numpy fp64) buffers
     e2e = None
@@ -380,24 +416,14 @@ def run_ours(args):
             "parallelism": f"views x{world}" + (" + NCCL all-reduce of the shared gradients" +
                                                 (" overlapped with the next forward (colours-ready event)" if overlap else "")
                                                 if world > 1 else ""),
-            "cuda_graph": graph is not None,
+            "timed_region": (f"CUDA graph replay, {per_graph} step(s) per graph" if graph is not None else f"eager calls ({graph_note})"),
+            "eager_ms_per_step": round(eager_ms, 4),
             "l2_policy": "inputs larger than L2: each step touches >= %.0f MB (algorithmic) vs 126 MB L2" % ((b_fwd + b_bwd) / 1e6),
         },
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
-
-
-def graph_launches(renderer, step):
-    """Kernels of one step, counted on an eager run of the same step (a replayed graph does not go through the library)."""
-    import torch
-
-    renderer.set_deferred(False)
-    before = renderer.launches
-    step()
-    torch.cuda.synchronize()
-    return renderer.launches - before
 
 
 def run_e2e(args, scene, world, dev):
@@ -519,7 +545,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--views-per-gpu", type=int, default=0, help="views rendered per step and GPU (0: 8 for c4, else 1)")
-    ap.add_argument("--graph", action="store_true", help="replay the whole step as one CUDA graph (N = 1)")
+    ap.add_argument("--eager", action="store_true", help="time the plain calls instead of a CUDA-graph replay of them")
+    ap.add_argument("--graph", action="store_true", help="N > 1: capture the step (with its collective) too")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce on the compute stream (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -611,9 +611,14 @@ static int wait_totals(ViewSlot *v, cudaStream_t st) {
     return DEODR_B200_OK;
 }
 
+// The handshake of the pinned totals: the HOST clears the flag before it launches the kernels of a pass, the publishing
+// kernel raises it to 1.  (A constant instead of a per-pass sequence number: the launch is then identical from pass to
+// pass, which is what lets the library replay it from a captured graph.)
 static int next_seq(ViewSlot *v) {
-    v->totals_seq = v->totals_seq == 0x7fffffff ? 1 : v->totals_seq + 1;
-    return v->totals_seq;
+    v->totals_seq = 1;
+    ((volatile int *)v->host_totals)[SC_WORDS] = 0;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    return 1;
 }
 
 static int bad_index_error(const ViewSlot *v) {
@@ -727,7 +732,10 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
         ws->launches++;
     }
     if (!fuse) {
-        if (ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, 0);  // first reader of the colours on this chain
+        // first reader of the colours on this chain (inside the library's own capture: an EXTERNAL event wait node, which
+        // waits for whatever the caller has recorded by the time the replay gets there)
+        if (ws->colors_ready)
+            cudaStreamWaitEvent(st, ws->colors_ready, ws->capturing_internally ? cudaEventWaitExternal : 0);
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
         (s.perspective_correct ? (tex ? k_shade<MAXC, true, true> : k_shade<MAXC, true, false>)
                                : (tex ? k_shade<MAXC, false, true> : k_shade<MAXC, false, false>))<<<v->num_tiles, NT, 0, st>>>(
@@ -787,7 +795,8 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
     bool first_fork = true;
     cudaStream_t se = fork_stream(ws, lane, 0, &first_fork);
     if (edge_chain) {
-        if (ws->colors_ready) cudaStreamWaitEvent(se, ws->colors_ready, 0);  // the edge records hold end-point colours
+        if (ws->colors_ready)  // the edge records hold end-point colours
+            cudaStreamWaitEvent(se, ws->colors_ready, ws->capturing_internally ? cudaEventWaitExternal : 0);
         const EdgeBins ebins{{v->edge_offset.as<int>(), v->edge_cursor}, v->edge_refs_tmp.as<int>(), v->scal + SC_OVERFLOW,
                              v->edge_tiles_raw.as<int>(), v->scal + SC_EDGE_TILES, plan.cap_edge_tiles};
         {
@@ -883,6 +892,101 @@ static int lanes_for(const DeodrWorkspace *ws, int n_views) {
     return n_views < ws->num_lanes ? n_views : ws->num_lanes;
 }
 
+// ---- captured launch sequences (GraphCache, workspace.h) -----------------------------------------------------------
+
+struct KeyWriter {
+    std::vector<unsigned char> bytes;
+    template <class T>
+    void put(const T &v) {
+        const unsigned char *p = reinterpret_cast<const unsigned char *>(&v);
+        bytes.insert(bytes.end(), p, p + sizeof(T));
+    }
+};
+
+// what a slot contributes to a key: its plan and the buffers the launches point into (a re-plan may move them)
+static void put_slot(KeyWriter *k, const ViewSlot *v) {
+    const FwdPlan &p = v->plan;
+    k->put(p.T); k->put(p.H); k->put(p.W); k->put(p.cap_small); k->put(p.cap_large); k->put(p.cap_edges);
+    k->put(p.cap_edge_refs); k->put(p.cap_edge_tiles); k->put(p.tex); k->put(p.hint_large_tiles);
+    const void *ptrs[] = {v->zeroed.ptr, v->small_offset.ptr, v->small_recs.ptr, v->large_refs.ptr, v->small_ids.ptr,
+                          v->edge_ids.ptr, v->edge_recs.ptr, v->edge_refs.ptr, v->edge_refs_tmp.ptr, v->edge_spans.ptr,
+                          v->edge_acc.ptr, v->tie_pairs.ptr, v->error_image_b.ptr, v->edge_tiles_raw.ptr,
+                          v->large_tiles.ptr, v->edge_tiles.ptr, v->host_totals};
+    for (const void *q : ptrs) k->put(q);
+}
+
+static bool is_default_stream(cudaStream_t st) { return st == nullptr || st == cudaStreamLegacy; }
+
+static bool graphs_usable(const DeodrWorkspace *ws, cudaStream_t st, bool capturing) {
+    // not inside the caller's own capture, not while the per-kernel events of the timing API are switched on (they would
+    // have to live inside the graph); the per-thread default stream is left alone
+    return ws->graphs && !capturing && st != cudaStreamPerThread && ws->ev_start.empty() && ws->overlap;
+}
+
+// The legacy default stream cannot be captured: work submitted on it runs on the workspace's proxy stream instead,
+// ordered after everything already in the default stream and before everything submitted to it afterwards.
+static cudaStream_t hop_in(DeodrWorkspace *ws, cudaStream_t st) {
+    if (!is_default_stream(st)) return st;
+    cudaEventRecord(ws->proxy_in, st);
+    cudaStreamWaitEvent(ws->proxy, ws->proxy_in, 0);
+    return ws->proxy;
+}
+static void hop_out(DeodrWorkspace *ws, cudaStream_t st) {
+    if (!is_default_stream(st)) return;
+    cudaEventRecord(ws->proxy_out, ws->proxy);
+    cudaStreamWaitEvent(st, ws->proxy_out, 0);
+}
+
+// Runs `enqueue` (which launches on `st` and on streams forked from it) either directly or through the cache: replay when
+// the key is the one the graph was captured for, capture + instantiate otherwise.  A failed capture switches the cache off.
+template <class Enqueue>
+static int launch_cached(DeodrWorkspace *ws, GraphCache *cache, const KeyWriter &key, cudaStream_t st, Enqueue enqueue) {
+    if (cache->exec && cache->key == key.bytes) {
+        cache->misses = 0;
+        ws->launches += cache->launches;
+        CUDA_TRY(cudaGraphLaunch(cache->exec, st));
+        return DEODR_B200_OK;
+    }
+    if (++cache->misses > 8) {  // the caller's arguments change every call: capturing every time would cost more than it saves
+        cache->drop();
+        return enqueue();
+    }
+    cache->drop();
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        ws->graphs = false;
+        return enqueue();
+    }
+    ws->capturing_internally = true;
+    const int64_t before = ws->launches;
+    const int rc = enqueue();
+    ws->capturing_internally = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end = cudaStreamEndCapture(st, &graph);
+    if (rc != DEODR_B200_OK || end != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ws->graphs = false;
+        ws->launches = before;
+        if (rc != DEODR_B200_OK) return rc;
+        return enqueue();  // nothing ran during the failed capture: run it now, kernel by kernel
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess || !exec) {
+        cudaGetLastError();
+        ws->graphs = false;
+        ws->launches = before;
+        return enqueue();
+    }
+    cache->exec = exec;
+    cache->key = key.bytes;
+    cache->launches = (int)(ws->launches - before);
+    CUDA_TRY(cudaGraphLaunch(exec, st));
+    return DEODR_B200_OK;
+}
+
 static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneView *views, const DeodrViewIO *io,
                              double sigma, int flags, void *stream, bool check_indices) {
     if (!ws) return set_error(DEODR_B200_EINVAL, "ws == NULL");
@@ -915,12 +1019,38 @@ static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneVi
         if (!v->plan.valid)
             if (int rc = build_plan(ws, v, scenes[i], sigma, st, check_indices)) return rc;
     }
-    // ---- enqueue every view, round-robin over the lanes
+    // ---- enqueue every view, round-robin over the lanes (directly, or as the replay of the captured sequence)
     const int used = lanes_for(ws, n_views);
-    open_lanes(ws, st, used);
+    const cudaStream_t caller_stream = st;
+    auto enqueue_all = [&]() -> int {
+        open_lanes(ws, st, used);
+        for (int i = 0; i < n_views; i++)
+            if (int rc = enqueue_forward(ws, slots[i], ws->lanes[i % used], scenes[i], io[i], sigma, flags, check_indices))
+                return rc;
+        close_lanes(ws, st, used);
+        return DEODR_B200_OK;
+    };
+    if (graphs_usable(ws, st, capturing)) {
+        const cudaStream_t caller = st;
+        st = hop_in(ws, caller);
+        KeyWriter key;
+        key.put(n_views); key.put(sigma); key.put(flags); key.put(check_indices); key.put(ws->colors_ready);
+        key.put(ws->overlap); key.put(used);
+        for (int i = 0; i < n_views; i++) {
+            key.put(views[i]);
+            key.put(io[i]);
+            put_slot(&key, slots[i]);
+        }
+        for (int i = 0; i < n_views; i++) next_seq(slots[i]);  // (clears the pinned flags: must happen for a replay too)
+        const int rc = launch_cached(ws, &ws->fwd_graph, key, st, enqueue_all);
+        hop_out(ws, caller);
+        if (rc) return rc;
+        for (int i = 0; i < n_views; i++) { slots[i]->pending = true; slots[i]->hints_exact = false; }
+    } else {
+        if (int rc = enqueue_all()) return rc;
+    }
     for (int i = 0; i < n_views; i++) {
         ViewSlot *v = slots[i];
-        if (int rc = enqueue_forward(ws, v, ws->lanes[i % used], scenes[i], io[i], sigma, flags, check_indices)) return rc;
         v->generation = ++ws->generation_counter;
         v->sigma = sigma;
         v->fwd_C = scenes[i].nb_colors;
@@ -930,7 +1060,6 @@ static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneVi
         v->fwd_check_indices = check_indices;
         v->fwd_valid = 1;
     }
-    close_lanes(ws, st, used);
     ws->colors_ready = nullptr;  // one-shot
     if (deferred) return DEODR_B200_OK;
     // ---- verdicts: every pass is already queued, the device does not wait for this
@@ -948,6 +1077,7 @@ static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneVi
         if (int rc = read_verdict(ws, v, st, &overflow)) return rc;
         if (overflow) return set_error(DEODR_B200_ECUDA, "forward pass overflowed a freshly built plan (internal error)");
         v->fwd_valid = 1;
+        if (st != caller_stream) hop_out(ws, caller_stream);  // the re-run went to the proxy stream too
     }
     return DEODR_B200_OK;
 }
@@ -1001,17 +1131,33 @@ static int render_b_views_impl(DeodrWorkspace *ws, int n_views, const DeodrScene
         }
     }
     const int used = lanes_for(ws, n_views);
-    open_lanes(ws, st, used);
-    for (int i = 0; i < n_views; i++) {
-        ViewSlot *v = ws->slots[i];
-        SceneView s;
-        memcpy(&s, &views[i], sizeof(s));
-        Lane &lane = ws->lanes[i % used];
-        deodr_launch_backward(ws, v, lane, s, io[i], sigma, flags, grads[i]);
+    auto enqueue_all = [&]() -> int {
+        open_lanes(ws, st, used);
+        for (int i = 0; i < n_views; i++) {
+            SceneView s;
+            memcpy(&s, &views[i], sizeof(s));
+            deodr_launch_backward(ws, ws->slots[i], ws->lanes[i % used], s, io[i], sigma, flags, grads[i]);
+        }
+        close_lanes(ws, st, used);
+        CUDA_TRY(cudaGetLastError());
+        return DEODR_B200_OK;
+    };
+    if (graphs_usable(ws, st, capturing)) {
+        const cudaStream_t caller = st;
+        st = hop_in(ws, caller);
+        KeyWriter key;
+        key.put(n_views); key.put(sigma); key.put(flags); key.put(ws->overlap); key.put(used);
+        for (int i = 0; i < n_views; i++) {
+            key.put(views[i]);
+            key.put(io[i]);
+            key.put(grads[i]);
+            put_slot(&key, ws->slots[i]);
+        }
+        const int rc = launch_cached(ws, &ws->bwd_graph, key, st, enqueue_all);
+        hop_out(ws, caller);
+        return rc;
     }
-    close_lanes(ws, st, used);
-    CUDA_TRY(cudaGetLastError());
-    return DEODR_B200_OK;
+    return enqueue_all();
 }
 
 extern "C" {
@@ -1087,6 +1233,7 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
     memset(ws->host_scratch, 0, 32 * sizeof(int));
     CUDA_TRY(cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
     ws->overlap = !(getenv("DEODR_B200_SERIAL") && atoi(getenv("DEODR_B200_SERIAL")));
+    ws->graphs = !(getenv("DEODR_B200_GRAPHS") && atoi(getenv("DEODR_B200_GRAPHS")) == 0);
     if (const char *e = getenv("DEODR_B200_LANES")) ws->num_lanes = atoi(e) < 1 ? 1 : (atoi(e) > MAX_LANES ? MAX_LANES : atoi(e));
     int prio_low = 0, prio_high = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
@@ -1102,6 +1249,9 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
         CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_begin, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&lane.ev_end, cudaEventDisableTiming));
     }
+    CUDA_TRY(cudaStreamCreateWithFlags(&ws->proxy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ws->proxy_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ws->proxy_out, cudaEventDisableTiming));
     if (ws->scalars.ensure(8 * sizeof(int), &ws->bytes)) return DEODR_B200_ECUDA;
     if (!sm_count_cached) cudaDeviceGetAttribute(&sm_count_cached, cudaDevAttrMultiProcessorCount, device);
     *out = ws;
@@ -1112,6 +1262,11 @@ void deodr_b200_workspace_destroy(DeodrWorkspace *ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
     cudaDeviceSynchronize();
+    ws->fwd_graph.drop();
+    ws->bwd_graph.drop();
+    if (ws->proxy) cudaStreamDestroy(ws->proxy);
+    if (ws->proxy_in) cudaEventDestroy(ws->proxy_in);
+    if (ws->proxy_out) cudaEventDestroy(ws->proxy_out);
     for (ViewSlot *v : ws->slots) free_slot(v);
     DevBuf *bufs[] = {&ws->scalars, &ws->h_faces, &ws->h_faces_uv, &ws->h_ij, &ws->h_depths, &ws->h_uv,
                       &ws->h_colors, &ws->h_shade, &ws->h_edgeflags, &ws->h_textured, &ws->h_shaded, &ws->h_texture,

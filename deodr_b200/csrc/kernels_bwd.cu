@@ -232,7 +232,7 @@ static void launch_bwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneV
         cudaStream_t se = fork_stream(ws, lane, 1, &first);
         cudaMemsetAsync(v->edge_acc.ptr, 0, (size_t)plan.cap_edges * edge_acc_stride(C) * sizeof(double), se);
         const EdgeTiles et = edge_tiles_of(v);
-        const int grid = at_least_one(v->hints_exact ? plan.hint_edge_tiles : plan.cap_edge_tiles);
+        const int grid = at_least_one(v->hints_exact && !ws->capturing_internally ? plan.hint_edge_tiles : plan.cap_edge_tiles);
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, se);
         FrameMaps maps;
@@ -266,7 +266,7 @@ static void launch_bwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneV
     }
     {
         PhaseTimer timer(ws, DEODR_B200_PH_SMALL_BWD, st);
-        const int entries = v->hints_exact ? plan.hint_small : s.nb_triangles;
+        const int entries = v->hints_exact && !ws->capturing_internally ? plan.hint_small : s.nb_triangles;
         (tex ? k_small_tri_bwd<MAXC, true> : k_small_tri_bwd<MAXC, false>)<<<at_least_one(grid_for(entries, 128)), 128, 0, st>>>(
             s, v->tiles_x, v->small_ids.as<int>(), v->scal, edge_cursor, ties, io.owner, image_b, g);
         ws->launches++;

@@ -239,11 +239,16 @@ DEODR_HD bool is_small(const TileBox &b, int box_w, int box_h) {
     return b.tx1 - b.tx0 <= 1 && b.ty1 - b.ty0 <= 1 && box_w <= 32 && (box_h << small_shift(box_w)) <= 64;
 }
 // Triangles that take the RECORD path of the forward pass (exact coverage masks computed once, by the binning thread):
-// at most two tile columns and RECORD_ROWS rows.  The small ones (above) are a subset - they also fit the 64-bit
+// at most two tile columns and RECORD_ROWS (16) rows.  The small ones (above) are a subset - they also fit the 64-bit
 // ownership mask of the triangle-parallel adjoint; the others ("medium": e.g. 12 x 8 pixel triangles, 7 % of the drawn
 // triangles of the 1M-triangle scene) are owned without SMALL_FLAG and go through the pixel-parallel adjoint.
-// Everything else ("large") is binned by reference and set up inside the tile kernel.
-constexpr int RECORD_ROWS = 64;
+// Everything else ("large") is binned by reference and set up inside the tile kernel: one binning thread walking the
+// 30+ rows of a 1k-triangle scene's triangles is slower than the tile kernel's parallel set-up (measured: the 640x480
+// hand-sized scene 0.154 -> 0.207 ms with a 64-row limit), so the record path stops at one tile height.
+#ifndef DEODR_RECORD_ROWS
+#define DEODR_RECORD_ROWS 16
+#endif
+constexpr int RECORD_ROWS = DEODR_RECORD_ROWS;
 DEODR_HD bool takes_record_path(const TileBox &b, int box_w, int box_h) {
     return b.tx1 - b.tx0 <= 1 && box_w <= 32 && box_h <= RECORD_ROWS;
 }

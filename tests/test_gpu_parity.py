@@ -249,3 +249,70 @@ def test_error_behaviour(gpu, texture):
     scene.faces[0, 0] = 10**6
     with pytest.raises(_cabi.DeodrB200Error, match="faces"):
         gpu.check_scene(DeviceScene(scene, "cuda:0"))
+
+
+def test_config1_soup_128(gpu, checker, texture):
+    """BASELINE.json configs[0] at its literal size: 30-triangle soup, 128x128 RGB, fwd+bwd (the reference pins this
+    scene at 200x200 - covered by test_soup_all_flags / the pinned hashes; no reference vector exists at 128, so the
+    checker is the compiled reference itself)."""
+    for seed, clockwise in ((2, False), (3, True)):
+        np.random.seed(seed)
+        check(gpu, checker, soup_scene(n_tri=30, width=128, height=128, clockwise=clockwise, texture=texture), 1.0)
+
+
+def test_config2_hand_mesh_640x480(gpu, checker, ref_oracle):
+    """BASELINE.json configs[1] on the REAL hand mesh: deodr/data/hand.obj (1048 faces) projected by the reference's own
+    Camera and lit by its Scene3D (tests/golden/scene_ops.npz, made by make_scene_ops_golden.py from the reference's
+    Python), 640x480 RGB Gouraud, fwd+bwd against the compiled reference core; face ids against the reference's
+    deferred face-id channel (Scene3D.render_deferred, sigma = 0)."""
+    from deodr_b200.scenes import SceneArrays
+
+    g = np.load(os.path.join(GOLDEN, "scene_ops.npz"))
+    faces, V = g["hand_faces"], g["hand_vertices"].shape[0]
+    T = faces.shape[0]
+
+    def scene_with(colors, nb_colors, background):
+        return SceneArrays(
+            faces=faces, faces_uv=np.zeros((T, 3), np.uint32), ij=g["c2_ij"], depths=g["c2_depths"],
+            textured=np.zeros(T, bool), uv=np.zeros((1, 2)), shade=np.zeros(V), colors=colors, shaded=np.zeros(T, bool),
+            edgeflags=g["c2_edgeflags"].astype(bool), height=480, width=640, nb_colors=nb_colors,
+            texture=np.zeros((2, 2, nb_colors)), background_image=None, background_color=background, clockwise=False,
+            backface_culling=True, strict_edge=True, perspective_correct=False, integer_pixel_centers=True)
+
+    scene = scene_with(g["c2_colors"], 3, g["c2_background_color"])
+    got = check(gpu, checker, scene, 1.0)
+    assert np.isfinite(got["z_buffer"]).mean() > 0.05
+    # face ids: the reference interpolates a per-vertex channel, so give every face its own three vertices
+    soup_faces = np.arange(3 * T, dtype=np.uint32).reshape(T, 3)
+    flat = faces.astype(np.int64).reshape(-1)
+    deferred = SceneArrays(
+        faces=soup_faces, faces_uv=np.zeros((T, 3), np.uint32), ij=g["c2_ij"][flat], depths=g["c2_depths"][flat],
+        textured=np.zeros(T, bool), uv=np.zeros((1, 2)), shade=np.zeros(3 * T),
+        colors=np.repeat(np.arange(T, dtype=np.float64), 3)[:, None], shaded=np.zeros(T, bool),
+        edgeflags=np.zeros((T, 3), bool), height=480, width=640, nb_colors=1, texture=np.zeros((2, 2, 1)),
+        background_image=None, background_color=np.array([-1.0]), clockwise=False, backface_culling=True,
+        strict_edge=True, perspective_correct=False, integer_pixel_centers=True)
+    channel, z = ref_oracle.render(deferred, 0.0)
+    out = run_device(gpu, deferred, 0.0)
+    assert np.array_equal(out["z_buffer"], z) and np.array_equal(z, got["z_buffer"])
+    assert np.array_equal(out["face_id"], np.rint(channel[:, :, 0]).astype(np.int32))
+    assert np.array_equal(got["face_id"], out["face_id"])  # the shared-vertex mesh owns the same faces
+
+
+def test_face_ids_at_config3_size(gpu, ref_oracle):
+    """Face ids against the reference's deferred face-id channel on the 50k-triangle mesh at 1024x1024 (sigma = 0)."""
+    scene = torus_scene(158, 1024, 1024)
+    T = scene.faces.shape[0]
+    flat = scene.faces.astype(np.int64).reshape(-1)
+    scene.ij, scene.depths, scene.shade = scene.ij[flat], scene.depths[flat], np.zeros(3 * T)
+    scene.faces = np.arange(3 * T, dtype=np.uint32).reshape(T, 3)
+    scene.faces_uv = np.zeros((T, 3), np.uint32)
+    scene.uv = np.zeros((1, 2))
+    scene.nb_colors, scene.colors = 1, np.repeat(np.arange(T, dtype=np.float64), 3)[:, None]
+    scene.background_image, scene.background_color = None, np.array([-1.0])
+    scene.texture = np.zeros((2, 2, 1))
+    scene.edgeflags = np.zeros((T, 3), bool)
+    channel, z = ref_oracle.render(scene, 0.0)
+    out = run_device(gpu, scene, 0.0)
+    assert np.array_equal(out["z_buffer"], z)
+    assert np.array_equal(out["face_id"], np.rint(channel[:, :, 0]).astype(np.int32))
