@@ -303,6 +303,13 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    side = torch.cuda.Stream(device=dev) if args.side_stream else None
+    if side is not None:  # (A/B: the steps on a non-default stream, where DEODR_B200_GRAPHS=1 can capture them)
+        side.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(side)
+        for _ in range(3):
+            step()
+        fence()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     if graph is not None:
@@ -545,6 +552,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--views-per-gpu", type=int, default=0, help="views rendered per step and GPU (0: 8 for c4, else 1)")
+    ap.add_argument("--side-stream", action="store_true", help="run the timed steps on a non-default stream (A/B)")
     ap.add_argument("--eager", action="store_true", help="time the plain calls instead of a CUDA-graph replay of them")
     ap.add_argument("--graph", action="store_true", help="N > 1: capture the step (with its collective) too")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce on the compute stream (A/B)")

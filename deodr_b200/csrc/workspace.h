@@ -139,7 +139,7 @@ struct DeodrWorkspace {
     bool deferred = false; // the entry points never read the verdict (CUDA-graph capture); see deodr_b200_workspace_status
     int replans = 0;       // number of plans (re)built so far
     cudaEvent_t colors_ready = nullptr;  // one-shot: the next forward's colour readers wait for it (not owned)
-    bool graphs = true;    // replay captured launch sequences (DEODR_B200_GRAPHS=0: always launch kernel by kernel)
+    bool graphs = false;   // replay captured launch sequences (opt-in: DEODR_B200_GRAPHS=1)
     bool capturing_internally = false;  // the library itself is capturing: external event waits, capacity-sized grids
     GraphCache fwd_graph, bwd_graph;
     // the legacy default stream cannot be captured: a call made on it hops to this stream (event in, event out)

@@ -14,10 +14,10 @@ out = [f"# ncu summary {tag}\n"]
 
 rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
 hdr = rows[0]
-i_name, i_val = hdr.index("Kernel Name"), hdr.index("Metric Value")
+i_name, i_val, i_grid = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
 agg = collections.OrderedDict()
-for r in rows[1:]:
-    agg.setdefault(r[i_name].split("(")[0][:48], []).append(float(r[i_val].replace(",", "")))
+for r in rows[1:]:  # one line per (kernel, grid): two launches of one kernel with different grids are different work
+    agg.setdefault(r[i_name].split("(")[0][:48] + " grid " + r[i_grid].split(",")[0].strip("( "), []).append(float(r[i_val].replace(",", "")))
 tot = sum(sum(v) for v in agg.values())
 out.append(f"## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, {len(rows) - 1} launches, "
            f"cold-cache / serialised: compare SHARES)\n")
@@ -42,7 +42,7 @@ out.append(f"\n## `ncu --set full --clock-control none` (one launch per kernel; 
 out.append("| kernel | " + " | ".join(w[1] for w in want) + " | top stalls |\n|---|" + "---|" * (len(want) + 1))
 seen = set()
 for r in rr[2:]:
-    name = r[idx["Kernel Name"]].split("(")[0][:40]
+    name = r[idx["Kernel Name"]].split("(")[0][:40] + " grid " + r[idx["Grid Size"]].split(",")[0].strip("( ")
     if name in seen:
         continue
     seen.add(name)
@@ -60,7 +60,7 @@ for r in rr[2:]:
     out.append(f"| `{name}` | " + " | ".join(vals) + f" | {st} |")
 # per-launch DRAM traffic of every raster kernel -> profiles/ncu_traffic.json (bench.py's roofline.traffic)
 phase_of = {"k_tile_z": "tile_z", "k_shade": "shade", "k_edge_fwd": "edge_fwd", "k_small_tri_bwd": "small_tri_bwd",
-            "k_interior_bwd": "interior_bwd", "k_raster_bwd": "edge_bwd", "k_bin_count": "bin_count"}
+            "k_interior_bwd": "interior_bwd", "k_raster_bwd": "edge_bwd", "k_bin": "bin"}
 workload = tag.split("_")[1] if "_" in tag else "c5"
 traffic = {}
 for r in rr[2:]:
@@ -75,7 +75,8 @@ try:
 except Exception:
     all_traffic = {}
 all_traffic[workload] = traffic
-all_traffic["_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (scripts/make_profile_summary.py)"
+all_traffic["source"] = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture {report.split('/')[-1]} "
+                         f"(summary profiles/{tag}.md, scripts/make_profile_summary.py)")
 json.dump(all_traffic, open("profiles/ncu_traffic.json", "w"), indent=1, sort_keys=True)
 if bench:
     d = json.loads(open(bench).read().strip().splitlines()[-1])
