@@ -219,39 +219,45 @@ def run_ours(args):
     ev_colors = torch.cuda.Event()
     overlap = world > 1 and not args.no_overlap
 
-    def step(wait_colors=True):
-        """One fitting step.  wait_colors=False: the colours are known to be in place (first step of a captured graph)."""
+    def compute(wait_colors=True):
+        """The device work of one fitting step on the compute stream: refresh, clear, forward, adjoint."""
         nonlocal outs
         for ds, ij, col in zip(dss, ij_dev, colors_dev):      # per-iteration refresh of the optimised inputs
             ds.update(ij=ij)
         if overlap:
             # the colours are written by the "optimiser" on the communication stream (after the all-reduce of the
-            # previous step): only the kernels of this forward that READ colours wait for that
+            # previous step): only the kernels of this forward that READ colours wait for that, and colors_b - which the
+            # communication stream zeroes once the all-reduce has consumed it - is only touched after that wait
             if wait_colors:
                 renderer.set_colors_ready(ev_colors)
-            # colors_b is zeroed on the communication stream once the all-reduce has consumed it
             flat[shared_end:].zero_()                         # the per-view ij_b
         else:
             for ds, col in zip(dss, colors_dev):
                 ds.update(colors=col)
             flat.zero_()                                      # callers clear scene.*_b before every backward
         outs = renderer.render_views(dss, SIGMA, out=outs)
-        if overlap and wait_colors:
-            torch.cuda.current_stream().wait_event(ev_colors)  # the adjoint accumulates into colors_b
         renderer.render_b_views(dss, SIGMA, outs, image_bs, grads)
-        if world > 1:
-            if overlap:
-                ev_bwd.record()
-                with torch.cuda.stream(comm):
-                    comm.wait_event(ev_bwd)
-                    work = dist.all_reduce(flat[:shared_end], async_op=True)  # one flat call: every shared gradient
-                    work.wait()
-                    for ds, col in zip(dss, colors_dev):       # stand-in for the optimiser's colour update
-                        ds.update(colors=col)
-                    flat[:shared_end].zero_()
-                    ev_colors.record(comm)
-            else:
-                dist.all_reduce(flat[:shared_end])             # shared-parameter gradients, one call per step
+
+    def communicate():
+        """One flat all-reduce of every shared gradient + the optimiser's colour update, on the communication stream."""
+        if world == 1:
+            return
+        if overlap:
+            ev_bwd.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_bwd)
+                work = dist.all_reduce(flat[:shared_end], async_op=True)
+                work.wait()
+                for ds, col in zip(dss, colors_dev):           # stand-in for the optimiser's colour update
+                    ds.update(colors=col)
+                flat[:shared_end].zero_()
+                ev_colors.record(comm)
+        else:
+            dist.all_reduce(flat[:shared_end])                 # shared-parameter gradients, one call per step
+
+    def step():
+        compute()
+        communicate()
 
     def fence():
         if world > 1:
@@ -271,28 +277,26 @@ def run_ours(args):
     # of one step overlaps the forward of the next INSIDE the graph; K must be a multiple of it.  --eager times the plain
     # calls instead (also the fallback when a capture fails).
     graph, per_graph, graph_note = None, 1, None
-    if world > 1 and not args.graph:
-        # N > 1: the step holds an NCCL collective on a second stream; capturing that did not terminate on the 2-GPU box
-        # (round 2), so the ranks time the plain calls - with the all-reduce overlapped - unless --graph insists
-        graph_note = "N > 1: eager calls, all-reduce overlapped through the colours-ready event"
-    elif not args.eager:
-        per_graph = 1 if world == 1 else max(d for d in (10, 5, 4, 2, 1) if args.steps % d == 0)
+    if not args.eager:
+        # what is captured is the COMPUTE part of the step; at N > 1 the collective stays outside the graph (capturing
+        # NCCL work on a second stream did not terminate on the 2-GPU box) and the colours-ready wait inside it is an
+        # external event wait node, so every replay waits for the all-reduce of the step before
         try:
             renderer.set_deferred(True)
             cap = torch.cuda.Stream(device=dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.stream(cap):
                 with torch.cuda.graph(graph, stream=cap):
-                    for i in range(per_graph):
-                        step(wait_colors=i > 0)
-                    if overlap:
-                        torch.cuda.current_stream().wait_stream(comm)
+                    compute()
             for _ in range(2):
                 graph.replay()
+                communicate()
+            if overlap:
+                torch.cuda.current_stream().wait_stream(comm)
             fence()
             renderer.status()
         except Exception as exc:  # capture is an optimisation of the launch path, never a requirement
-            graph, per_graph = None, 1
+            graph = None
             graph_note = f"capture failed, eager calls timed instead: {type(exc).__name__}: {str(exc)[:200]}"
             renderer.set_deferred(False)
             torch.cuda.synchronize()
@@ -313,8 +317,11 @@ def run_ours(args):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     if graph is not None:
-        for _ in range(args.steps // per_graph):
+        for _ in range(args.steps):
             graph.replay()
+            communicate()
+        if overlap:
+            torch.cuda.current_stream().wait_stream(comm)
     else:
         for _ in range(args.steps):
             step()
@@ -425,7 +432,8 @@ def run_ours(args):
             "parallelism": f"views x{world}" + (" + NCCL all-reduce of the shared gradients" +
                                                 (" overlapped with the next forward (colours-ready event)" if overlap else "")
                                                 if world > 1 else ""),
-            "timed_region": (f"CUDA graph replay, {per_graph} step(s) per graph" if graph is not None else f"eager calls ({graph_note})"),
+            "timed_region": (("CUDA graph replay of the step's device work" + (", collective outside the graph" if world > 1 else ""))
+                             if graph is not None else f"eager calls ({graph_note})"),
             "eager_ms_per_step": round(eager_ms, 4),
             "l2_policy": "inputs larger than L2: each step touches >= %.0f MB (algorithmic) vs 126 MB L2" % ((b_fwd + b_bwd) / 1e6),
         },
@@ -556,7 +564,7 @@ def main():
     ap.add_argument("--views-per-gpu", type=int, default=0, help="views rendered per step and GPU (0: 8 for c4, else 1)")
     ap.add_argument("--side-stream", action="store_true", help="run the timed steps on a non-default stream (A/B)")
     ap.add_argument("--eager", action="store_true", help="time the plain calls instead of a CUDA-graph replay of them")
-    ap.add_argument("--graph", action="store_true", help="N > 1: capture the step (with its collective) too")
+    ap.add_argument("--graph", action="store_true", help="(default) kept for compatibility")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-reduce on the compute stream (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -250,7 +250,17 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
     const int tid = threadIdx.x;
     // Tiles nothing was binned into (most of the image around a mesh: 60 % of the tiles of the 1M-triangle scene) take a
     // short cut in the one-tile-per-CTA launch: background written straight away, no barrier, no copy pipeline.
-    if (gridDim.x == (unsigned)num_tiles && bins.small.cursor[blockIdx.x] == 0 && bins.large.cursor[blockIdx.x] == 0) {
+    // (one-tile-per-CTA launch: the tile's four list words are fetched by every thread at once - broadcast loads, ONE
+    // memory round trip - instead of two dependent ones for the empty test and a third by thread 0 for the copy)
+    const bool per_tile = gridDim.x == (unsigned)num_tiles;
+    int c_small = 0, c_large = 0, o_begin = 0, o_end = 0;
+    if (per_tile) {
+        c_small = bins.small.cursor[blockIdx.x];
+        c_large = bins.large.cursor[blockIdx.x];
+        o_begin = bins.small.offset[blockIdx.x];
+        o_end = bins.small.offset[blockIdx.x + 1];
+    }
+    if (per_tile && (c_small | c_large) == 0) {
         const Tile tile = tile_of(blockIdx.x, tiles_x);
         const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
         if (x >= s.width || y >= s.height) return;
@@ -300,7 +310,8 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
     };
     __syncthreads();  // barriers initialised
     int cur = 0;
-    load_info(blockIdx.x);
+    if (per_tile) { noff = o_begin; nn = min(c_small, o_end - o_begin); }
+    else load_info(blockIdx.x);
     issue(blockIdx.x, 0);
     load_info(blockIdx.x + gridDim.x);
     for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, cur ^= 1) {
@@ -727,8 +738,10 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
     // the 1M-triangle scene, hides an all-reduce of the colour gradient, and fusion is worth 24 us every step)
     static const bool late_shade = getenv("DEODR_B200_LATE_COLORS") && !strcmp(getenv("DEODR_B200_LATE_COLORS"), "shade");
     const bool fuse = fuse_allowed && !(ws->colors_ready && late_shade);
-    if (fuse && ws->colors_ready)
-        cudaStreamWaitEvent(st, ws->colors_ready, ws->capturing_internally ? cudaEventWaitExternal : 0);
+    // (inside a capture - the library's own or the caller's - the wait becomes an EXTERNAL event wait node: every replay
+    // waits for whatever the caller has recorded on the event by the time the replay gets there)
+    const unsigned wait_flags = (ws->capturing_internally || stream_is_capturing(st)) ? cudaEventWaitExternal : 0;
+    if (fuse && ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, wait_flags);
     {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
         // DEODR_B200_TILEZ_CTAS_PER_SM = k > 0 runs k persistent CTAs per SM with the two-stage TMA pipeline; default 0 =
@@ -761,10 +774,7 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
         ws->launches++;
     }
     if (!fuse) {
-        // first reader of the colours on this chain (inside the library's own capture: an EXTERNAL event wait node, which
-        // waits for whatever the caller has recorded by the time the replay gets there)
-        if (ws->colors_ready)
-            cudaStreamWaitEvent(st, ws->colors_ready, ws->capturing_internally ? cudaEventWaitExternal : 0);
+        if (ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, wait_flags);  // first reader of the colours here
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
         (s.perspective_correct ? (tex ? k_shade<MAXC, true, true> : k_shade<MAXC, true, false>)
                                : (tex ? k_shade<MAXC, false, true> : k_shade<MAXC, false, false>))<<<v->num_tiles, NT, 0, st>>>(
@@ -824,8 +834,9 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
     bool first_fork = true;
     cudaStream_t se = fork_stream(ws, lane, 0, &first_fork);
     if (edge_chain) {
-        if (ws->colors_ready)  // the edge records hold end-point colours
-            cudaStreamWaitEvent(se, ws->colors_ready, ws->capturing_internally ? cudaEventWaitExternal : 0);
+        if (ws->colors_ready)  // the edge records hold end-point colours (external wait node inside a capture)
+            cudaStreamWaitEvent(se, ws->colors_ready,
+                                (ws->capturing_internally || stream_is_capturing(st)) ? cudaEventWaitExternal : 0);
         const EdgeBins ebins{{v->edge_offset.as<int>(), v->edge_cursor}, v->edge_refs_tmp.as<int>(), v->scal + SC_OVERFLOW,
                              v->edge_tiles_raw.as<int>(), v->scal + SC_EDGE_TILES, plan.cap_edge_tiles};
         {
