@@ -159,6 +159,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from deodr_b200.distributed import allreduce_flat
     from deodr_b200.renderer import DeviceScene, Renderer
 
     rank = int(os.environ.get("RANK", "0"))
@@ -246,14 +247,14 @@ def run_ours(args):
             ev_bwd.record()
             with torch.cuda.stream(comm):
                 comm.wait_event(ev_bwd)
-                work = dist.all_reduce(flat[:shared_end], async_op=True)
+                work = allreduce_flat([flat[:shared_end]], async_op=True)  # deodr_b200.distributed: ONE flat collective
                 work.wait()
                 for ds, col in zip(dss, colors_dev):           # stand-in for the optimiser's colour update
                     ds.update(colors=col)
                 flat[:shared_end].zero_()
                 ev_colors.record(comm)
         else:
-            dist.all_reduce(flat[:shared_end])                 # shared-parameter gradients, one call per step
+            allreduce_flat([flat[:shared_end]])                # shared-parameter gradients, one call per step
 
     def step():
         compute()

@@ -663,6 +663,14 @@ static int bad_index_error(const ViewSlot *v) {
     return DEODR_B200_OK;
 }
 
+// Height limit of the record path for triangles that are not small: RECORD_ROWS once the binning pass has enough
+// threads to fill the chip (a few resident warps per SM sub-partition), 0 below (DEODR_B200_RECORD_ROWS overrides).
+static int record_rows_for(int nb_triangles) {
+    static const int forced = getenv("DEODR_B200_RECORD_ROWS") ? atoi(getenv("DEODR_B200_RECORD_ROWS")) : -1;
+    if (forced >= 0) return forced < RECORD_ROWS ? forced : RECORD_ROWS;
+    return nb_triangles >= 32768 ? RECORD_ROWS : 0;
+}
+
 // Plan building: count pass + scans + ONE read-back, then the list buffers are (re)allocated.
 static int build_plan(DeodrWorkspace *ws, ViewSlot *v, const SceneView &s, double sigma, cudaStream_t st,
                       bool check_indices) {
@@ -676,7 +684,8 @@ static int build_plan(DeodrWorkspace *ws, ViewSlot *v, const SceneView &s, doubl
             k_check_scene<<<grid_for(3 * (size_t)T, 256), 256, 0, st>>>(s, v->scal + SC_BAD_INDEX);
             ws->launches++;
         }
-        TriBins bins{{nullptr, v->small_cursor}, nullptr, {nullptr, v->large_cursor}, nullptr, v->scal + SC_OVERFLOW};
+        TriBins bins{{nullptr, v->small_cursor}, nullptr, {nullptr, v->large_cursor}, nullptr, v->scal + SC_OVERFLOW,
+                     record_rows_for(T)};
         EdgeList edges{v->scal + SC_EDGES, nullptr, nullptr, 0};
         k_bin<true><<<grid_for(T, 128), 128, 0, st>>>(s, sigma, v->tiles_x, bins, v->scal, nullptr, edges,
                                                      v->edge_cursor, 1);
@@ -813,7 +822,8 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
     const int T = s.nb_triangles, nt = v->num_tiles;
     const bool err_mode = (flags & DEODR_B200_ANTIALIASE_ERROR) != 0;
     TriBins bins{{v->small_offset.as<int>(), v->small_cursor}, v->small_recs.as<PreRec>(),
-                 {v->large_offset.as<int>(), v->large_cursor}, v->large_refs.as<int>(), v->scal + SC_OVERFLOW};
+                 {v->large_offset.as<int>(), v->large_cursor}, v->large_refs.as<int>(), v->scal + SC_OVERFLOW,
+                 record_rows_for(T)};
     EdgeList edges{v->scal + SC_EDGES, v->edge_ids.as<int>(), v->edge_keys.as<uint64_t>(), plan.cap_edges};
     const bool edge_chain = plan.cap_edges > 0;
     {

@@ -225,7 +225,8 @@ struct TriBins {
     PreRec *small_recs;
     TileSegments large;
     int *large_refs;
-    int *verdict;  // scal + SC_OVERFLOW
+    int *verdict;      // scal + SC_OVERFLOW
+    int record_rows;   // height limit of the record path for triangles that are not small (see takes_record_path)
 };
 
 // "small" = micro-triangle: at most 2 x 2 tiles and a bounding box that fits a 64-bit mask with a power-of-two row
@@ -249,8 +250,11 @@ DEODR_HD bool is_small(const TileBox &b, int box_w, int box_h) {
 #define DEODR_RECORD_ROWS 16
 #endif
 constexpr int RECORD_ROWS = DEODR_RECORD_ROWS;
-DEODR_HD bool takes_record_path(const TileBox &b, int box_w, int box_h) {
-    return b.tx1 - b.tx0 <= 1 && box_w <= 32 && box_h <= RECORD_ROWS;
+// `rows` = RECORD_ROWS, or 0 for scenes of a few thousand triangles (TriBins::record_rows): with too few binning threads
+// to fill the chip, a thread walking 16 rows is the kernel's critical path and the tile kernel's parallel set-up wins
+// (small triangles always take the record path: it is what their adjoint relies on).
+DEODR_HD bool takes_record_path(const TileBox &b, int box_w, int box_h, int rows) {
+    return is_small(b, box_w, box_h) || (b.tx1 - b.tx0 <= 1 && box_w <= 32 && box_h <= rows);
 }
 
 // 16-bit coverage mask of tile row y for one triangle (exact spans of rmath.h, clipped to the tile).
@@ -372,7 +376,7 @@ DEODR_HD void bin_triangle(const SceneView &s, int k, double sigma, int tiles_x,
     int box_w, box_h;
     const TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height, &box_w, &box_h);
     if (b.tx0 > b.tx1) return;  // off screen
-    const bool records = takes_record_path(b, box_w, box_h);
+    const bool records = takes_record_path(b, box_w, box_h, bins.record_rows);
     if (COUNT_ONLY) {
         int *count = records ? bins.small.cursor : bins.large.cursor;
         // a record-path triangle that is not small is owned through the pixel-parallel adjoint: bit 30 of the tile's

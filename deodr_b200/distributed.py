@@ -25,13 +25,18 @@ def views_of_rank(n_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_views, world))
 
 
-def allreduce_flat(tensors: Sequence[torch.Tensor], group=None) -> None:
-    """Sum ``tensors`` across ranks with a single collective: pack -> all_reduce -> unpack (in place)."""
+def allreduce_flat(tensors: Sequence[torch.Tensor], group=None, async_op: bool = False):
+    """Sum ``tensors`` across ranks with a single collective: pack -> all_reduce -> unpack (in place).
+
+    A caller that already keeps its shared gradients in ONE contiguous buffer (``bench.py`` does: the gradient slots are
+    views of it) passes that buffer alone: no packing, and ``async_op=True`` returns the collective's work handle."""
     tensors = [t for t in tensors if t is not None and t.numel() > 0]
     if not tensors or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return
+        return None
     dtype = tensors[0].dtype
     assert all(t.dtype == dtype and t.device == tensors[0].device for t in tensors)
+    if len(tensors) == 1 and tensors[0].is_contiguous():
+        return dist.all_reduce(tensors[0], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
     flat = torch.cat([t.reshape(-1) for t in tensors])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     offset = 0

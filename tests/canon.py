@@ -84,6 +84,10 @@ class Emulator:
         out["tri_refs"] = self.lib.emul_tri_refs()
         return out
 
+    def set_record_rows(self, rows):
+        """Height limit of the record path for triangles that are not small (the device: 16, or 0 for tiny scenes)."""
+        self.lib.emul_set_record_rows(int(rows))
+
     def build_plan(self, scene, sigma):
         """Segment capacities from `scene` (count-only pass + scans), kept for the render_planned calls that follow."""
         a = canonical_arrays(scene)

@@ -88,6 +88,12 @@ def test_emulated_kernels_micro_triangle_pile_flags(flags, emulator, checker):
 
 def test_emulated_kernels_mesh(emulator, checker):
     check(emulator, checker, torus_scene(24, 160, 120), 1.0)
+    emulator.set_record_rows(0)  # what the device picks for scenes of a few thousand triangles
+    try:
+        check(emulator, checker, torus_scene(24, 160, 120), 1.0)
+        check(emulator, checker, torus_scene(30, 100, 90, textured=True, texture_size=32), 1.0)
+    finally:
+        emulator.set_record_rows(16)
     check(emulator, checker, torus_scene(30, 100, 90, textured=True, texture_size=32), 1.0)
     check(emulator, checker, torus_scene(16, 70, 50, nb_colors=1), 1.0)
 
