@@ -40,6 +40,7 @@ WORKLOADS = {
     "c4": (316, 512, 512, False, 3, "200k-tri torus mesh (T=199712), 512x512 RGB view, sigma=1, fwd+bwd"),
     "c2": (23, 640, 480, False, 3, "1k-tri torus mesh (T=1058; stand-in for the 1048-face hand mesh), 640x480, fwd+bwd"),
     "c3u": (158, 1024, 1024, False, 3, "c3 without the texture (development A/B)"),
+    "c5t": (708, 2048, 2048, True, 3, "c5 with a 512x512 texture on every triangle (development A/B)"),
     "dev": (100, 512, 512, False, 3, "development-size torus"),
 }
 METRIC = "fwd+bwd Mpixels/s"

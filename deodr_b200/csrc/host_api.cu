@@ -90,6 +90,14 @@ static int crew_size() {
 // forward call (PCIe-bound: 60 MB up, 83 MB down) is fastest with 8 threads (3.35 ms vs 3.6 ms with 16), the adjoint
 // call (DRAM-bound: 100 MB of image_b to convert + the 120 MB mirror comparison) with 16 (2.2 ms vs 3.3 ms with 8).
 constexpr size_t DMA_CHUNK = (size_t)4 << 20;  // bytes of device-layout data per DMA / per gate
+
+// Workers allowed on each kind of batch (DEODR_B200_HOST_WIDTH_<KIND> overrides; measured defaults)
+static int batch_width(const char *kind, int dflt) {
+    char name[64];
+    snprintf(name, sizeof(name), "DEODR_B200_HOST_WIDTH_%s", kind);
+    const char *e = getenv(name);
+    return e && atoi(e) > 0 ? atoi(e) : dflt;
+}
 constexpr int MAX_EVENTS = 96;
 
 struct HostPath {
@@ -338,7 +346,8 @@ static int stage_scene(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *h
     // one batch for the whole scene: every array is cut into DMA chunks, each sent as soon as the workers have
     // written it into the mirror (conversion, copy and PCIe transfer of different chunks overlap)
     Batch b;
-    b.width = WIDTH_PCIE_BOUND;
+    static const int width_up = batch_width("UP", WIDTH_PCIE_BOUND);
+    b.width = width_up;
     std::vector<UploadPiece> pieces;
     for (int i = 0; i < SL_COUNT; i++) {
         const MirrorSlot &s = hp->slot[i];
@@ -430,7 +439,10 @@ static int host_forward(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *
 struct DownloadSet {
     Batch batch;
     int events = 0;
-    size_t chunk_bytes = DMA_CHUNK;  // grown for very large transfers so that the chunks fit the event pool
+    // grown for very large transfers so that the chunks fit the event pool (DEODR_B200_HOST_DOWN_CHUNK_KB: A/B)
+    size_t chunk_bytes = getenv("DEODR_B200_HOST_DOWN_CHUNK_KB") && atoi(getenv("DEODR_B200_HOST_DOWN_CHUNK_KB")) >= 64
+                             ? (size_t)atoi(getenv("DEODR_B200_HOST_DOWN_CHUNK_KB")) << 10
+                             : DMA_CHUNK;
     void size_for(size_t total_bytes, int buffers) {
         const size_t budget = (size_t)(MAX_EVENTS - 2 * buffers - 2);
         const size_t need = (total_bytes + budget - 1) / budget;
@@ -471,7 +483,8 @@ int deodr_b200_host_zero(DeodrWorkspace *ws, void *const *ptrs, const int64_t *b
     CUDA_TRY(cudaSetDevice(ws->device));
     if (int rc = host_path(ws, &hp)) return rc;
     Batch b;
-    b.width = WIDTH_PCIE_BOUND;
+    static const int width_zero = batch_width("ZERO", WIDTH_PCIE_BOUND);
+    b.width = width_zero;
     for (int i = 0; i < n; i++) {
         if (bytes[i] < 0 || (bytes[i] > 0 && !ptrs[i])) return set_error(DEODR_B200_EINVAL, "bad buffer");
         if (bytes[i] > 0) b.add(OP_ZERO, ptrs[i], nullptr, (size_t)bytes[i], 1 << 20);
@@ -501,7 +514,8 @@ int deodr_b200_render_host(DeodrWorkspace *ws, const DeodrHostScene *scene, doub
     char *stage_err = stage_z + ((P * 8 + 255) & ~(size_t)255);
     // every DMA is queued (in stream order behind the kernels) before the first chunk is consumed
     DownloadSet d;
-    d.batch.width = WIDTH_PCIE_BOUND;
+    static const int width_down = batch_width("DOWN", WIDTH_PCIE_BOUND);
+    d.batch.width = width_down;
     d.size_for(P * C * 4 + P * 8 + (antialiase_error ? P * 4 : 0), 3);  // the event pool bounds the number of chunks
     if (int rc = add_download(hp, &d, OP_F32_TO_F64, ws->h_image.ptr, stage_image, image, P * C, hp->stream)) return rc;
     if (int rc = add_download(hp, &d, OP_COPY, ws->h_z.ptr, stage_z, z_buffer, P * 8, hp->stream)) return rc;
@@ -608,7 +622,8 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
     double *dst[5] = {scene->ij_b, scene->colors_b, scene->uv_b, scene->shade_b, scene->texture_b};
     const size_t cnt[5] = {n_ij, n_col, n_uv, n_sh, tex};
     DownloadSet d;
-    d.batch.width = WIDTH_PCIE_BOUND;
+    static const int width_grads = batch_width("GRADS", WIDTH_PCIE_BOUND);
+    d.batch.width = width_grads;
     d.size_for(n_grad * 4, 5);
     size_t off = 0;
     for (int i = 0; i < 5; i++) {

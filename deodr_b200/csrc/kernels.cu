@@ -217,15 +217,17 @@ __global__ void k_publish(const int *scal, int *host_totals, int seq) {
     if (lane == 0) ((volatile int *)host_totals)[SC_WORDS] = seq;
 }
 
-// Forward, kernel 1 of 3 - z-buffer and owner ids, one 16x16 tile per CTA (no colour work: few registers).
-// Small triangles: the tile's pre-masked records are pulled into shared memory by a bulk copy (cp.async.bulk +
-// mbarrier, SASS UBLKCP); two threads per record scatter its index into per-pixel candidate lists; each pixel then
-// z-tests its own candidates exactly.  Large triangles: stencil per triangle -> coverage masks (8 threads each) ->
-// mask test.  The kernel is written as a loop over tiles with a two-stage copy pipeline (the copy of the next tile in
-// flight while the current one is tested) and launched with one tile per CTA: measured faster than persistent CTAs
-// (DEODR_B200_TILEZ_CTAS_PER_SM / DEODR_B200_TILEZ_TILES_PER_CTA switch the other modes on for A/B runs).
+// Forward, kernel 1 of 3 - z-buffer, owner ids and (fused) colours, one 16x16 tile per CTA.
+// Small triangles: the tile's pre-masked records are pulled into shared memory by bulk copies (cp.async.bulk +
+// mbarrier, SASS UBLKCP) 128 at a time through a two-deep pipeline - chunks c and c+1 are in flight when the tile
+// starts, chunk c+2 is issued as soon as chunk c has been consumed, so a crowded tile (the 1M-triangle scene has 400
+// tiles with more than 256 records, the 200k-triangle 512^2 views average 280) pays the copy latency once; two threads
+// per record scatter its index into per-pixel candidate lists; each pixel then z-tests its own candidates exactly.
+// Large triangles: stencil per triangle -> coverage masks (8 threads each) -> mask test.
+// One tile per CTA, scheduled by the hardware: measured faster than persistent CTAs with a static stride (168 us vs
+// 199 us x4 / 300 us x2 per SM on the 1M-triangle scene, round 2) - the tiles are very uneven.
 #ifndef DEODR_TILEZ_MIN_CTAS
-#define DEODR_TILEZ_MIN_CTAS 5  // 51 registers: 98.5 us vs 102.6 us at 64 and 123 us at 85 (measured, c5)
+#define DEODR_TILEZ_MIN_CTAS 6  // measured on the 1M-triangle scene (fused instance): 117 us at 4, 103 us at 5, 94 us at 6
 #endif
 // PERSP: perspective_correct as a compile-time constant (the 1/z division and its registers leave the common instance).
 // FUSE: the colour of every pixel is computed in this kernel's epilogue (the owner stays in registers: no owner map
@@ -240,30 +242,29 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
     // raised by k_bin_edges, which runs beside this kernel, and the early return must be uniform across the CTA
     if (scal[SC_OVERFLOW] & ~OVF_EDGE_REFS) return;
     s.perspective_correct = PERSP ? 1 : 0;
-    __shared__ TileShared sh;
+    // (only the triangle part of the tile kernels' working set: shared memory is what bounds this kernel's CTAs per SM)
+    __shared__ alignas(16) unsigned char sh_raw[sizeof(TileShared::TriPart)];
+    TileShared &sh = *reinterpret_cast<TileShared *>(sh_raw);
     __shared__ alignas(16) PreRec pre[2][PRE_CHUNK];
     __shared__ alignas(8) uint64_t bar[2];
-    __shared__ int info[2][2];  // [buffer][0] = number of small records of the tile, [1] = offset of its list
     // fused shading, up to 4 channels: the tile's colours are staged here and leave as ONE TMA tile store (UTMASTG)
     // instead of C four-byte stores per pixel at a 4C-byte stride
     __shared__ alignas(128) float stage[FUSE && MAXC <= 4 ? NT * MAXC : 4];
     const int tid = threadIdx.x;
-    // Tiles nothing was binned into (most of the image around a mesh: 60 % of the tiles of the 1M-triangle scene) take a
-    // short cut in the one-tile-per-CTA launch: background written straight away, no barrier, no copy pipeline.
-    // (one-tile-per-CTA launch: the tile's four list words are fetched by every thread at once - broadcast loads, ONE
-    // memory round trip - instead of two dependent ones for the empty test and a third by thread 0 for the copy)
-    const bool per_tile = gridDim.x == (unsigned)num_tiles;
-    int c_small = 0, c_large = 0, o_begin = 0, o_end = 0;
-    if (per_tile) {
-        c_small = bins.small.cursor[blockIdx.x];
-        c_large = bins.large.cursor[blockIdx.x];
-        o_begin = bins.small.offset[blockIdx.x];
-        o_end = bins.small.offset[blockIdx.x + 1];
-    }
-    if (per_tile && (c_small | c_large) == 0) {
-        const Tile tile = tile_of(blockIdx.x, tiles_x);
-        const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
-        if (x >= s.width || y >= s.height) return;
+    const int tile_id = blockIdx.x;
+    if (tile_id >= num_tiles) return;
+    // the tile's four list words are fetched by every thread at once (broadcast loads, ONE memory round trip)
+    const int c_small = bins.small.cursor[tile_id];
+    const int c_large = bins.large.cursor[tile_id];
+    const int o_begin = bins.small.offset[tile_id];
+    const int o_end = bins.small.offset[tile_id + 1];
+    const Tile tile = tile_of(tile_id, tiles_x);
+    const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
+    const bool inside = x < s.width && y < s.height;
+    // Tiles nothing was binned into (most of the image around a mesh: half of the tiles of the 1M-triangle scene) take a
+    // short cut: background written straight away, no barrier, no copy pipeline.
+    if ((c_small | c_large) == 0) {
+        if (!inside) return;
         const size_t idx = (size_t)y * s.width + x;
         z_buffer[idx] = __longlong_as_double(0x7ff0000000000000LL);
         owner[idx] = -1;
@@ -281,128 +282,102 @@ __global__ void __launch_bounds__(NT, DEODR_TILEZ_MIN_CTAS) k_tile_z(SceneView s
         }
         return;
     }
+    const int n_small = min(c_small, o_end - o_begin);
+    const PreRec *list = bins.small_recs + o_begin;
+    const int n_chunks = (n_small + PRE_CHUNK - 1) / PRE_CHUNK;
     sh.tri.pix_cnt[tid] = 0;
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
     }
+    auto issue = [&](int chunk) {  // thread 0: start the copy of records [chunk * PRE_CHUNK, ...) into buffer chunk & 1
+        const int m = min(PRE_CHUNK, n_small - chunk * PRE_CHUNK);
+        mbar_expect_tx(&bar[chunk & 1], (uint32_t)(m * sizeof(PreRec)));
+        bulk_load(pre[chunk & 1], list + chunk * PRE_CHUNK, (uint32_t)(m * sizeof(PreRec)), &bar[chunk & 1]);
+    };
+    __syncthreads();  // barriers initialised, candidate counters cleared
+    if (tid == 0) {
+        if (n_chunks > 0) issue(0);
+        if (n_chunks > 1) issue(1);
+    }
+    PixelState<1> p;
+    p.z = __longlong_as_double(0x7ff0000000000000LL);
+    p.own = -1;
+    p.bown = -1;
     uint32_t parity0 = 0, parity1 = 0;
-
-    // thread 0 runs a two-deep software pipeline: the list size / offset of tile i+2 are LOADED (registers nn, noff)
-    // while the copy of tile i+1 is ISSUED from values loaded one iteration earlier, so the loads' latency never stalls
-    // warp 0 (which also does pixel work).
-    int nn = 0, noff = 0;
-    auto load_info = [&](int t) {
-        if (tid == 0 && t < num_tiles) {
-            noff = bins.small.offset[t];
-            nn = min(bins.small.cursor[t], bins.small.offset[t + 1] - noff);
-        }
-    };
-    auto issue = [&](int t, int b) {  // publish (nn, noff) for tile t and start the copy of its first chunk
-        if (tid != 0 || t >= num_tiles) return;
-        info[b][0] = nn;
-        info[b][1] = noff;
-        const int m = min(nn, PRE_CHUNK);
-        if (m > 0) {
-            mbar_expect_tx(&bar[b], (uint32_t)(m * sizeof(PreRec)));
-            bulk_load(pre[b], bins.small_recs + noff, (uint32_t)(m * sizeof(PreRec)), &bar[b]);
-        }
-    };
-    __syncthreads();  // barriers initialised
-    int cur = 0;
-    if (per_tile) { noff = o_begin; nn = min(c_small, o_end - o_begin); }
-    else load_info(blockIdx.x);
-    issue(blockIdx.x, 0);
-    load_info(blockIdx.x + gridDim.x);
-    for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, cur ^= 1) {
-        __syncthreads();  // info[cur] is visible; everybody is done with buffer cur^1 and with sh (previous tile)
-        const int n_small = info[cur][0];
-        const PreRec *list = bins.small_recs + info[cur][1];
-        issue(tile_id + gridDim.x, cur ^ 1);        // overlaps with the work on this tile
-        load_info(tile_id + 2 * gridDim.x);         // consumed by the next iteration's issue()
-
-        const Tile tile = tile_of(tile_id, tiles_x);
-        const int x = tile.x0 + tid % TS, y = tile.y0 + tid / TS;
-        const bool inside = x < s.width && y < s.height;
-        PixelState<1> p;
-        p.z = __longlong_as_double(0x7ff0000000000000LL);
-        p.own = -1;
-        p.bown = -1;
-
-        for (int base = 0; base < n_small; base += PRE_CHUNK) {
-            const int m = min(PRE_CHUNK, n_small - base);
-            if (base > 0) {  // tiles with more than one chunk: the later chunks are fetched synchronously
-                __syncthreads();  // buffer cur fully consumed
-                if (tid == 0) {
-                    mbar_expect_tx(&bar[cur], (uint32_t)(m * sizeof(PreRec)));
-                    bulk_load(pre[cur], list + base, (uint32_t)(m * sizeof(PreRec)), &bar[cur]);
-                }
-            }
-            if (cur == 0) { mbar_wait(&bar[0], parity0); parity0 ^= 1u; }
-            else          { mbar_wait(&bar[1], parity1); parity1 ^= 1u; }
-            phase_pre_scatter<DevEnv>(tid, m, pre[cur], &sh);
+    for (int chunk = 0; chunk < n_chunks; chunk++) {
+        const int b = chunk & 1;
+        const int m = min(PRE_CHUNK, n_small - chunk * PRE_CHUNK);
+        if (b == 0) { mbar_wait(&bar[0], parity0); parity0 ^= 1u; }
+        else        { mbar_wait(&bar[1], parity1); parity1 ^= 1u; }
+        phase_pre_scatter<DevEnv>(tid, m, pre[b], &sh);
+        __syncthreads();
+        phase_pix_test<1>(s, tid, m, tile, pre[b], &sh, &p);  // (pixels outside the image have no candidates)
+        if (chunk + 1 < n_chunks) {
+            // every pixel is done with buffer b and with its candidate list: the next chunk may be scattered, and the
+            // chunk after it may land in buffer b while that one is tested
             __syncthreads();
-            phase_pix_test<1>(s, tid, m, tile, pre[cur], &sh, &p);  // (pixels outside the image have no candidates)
+            if (tid == 0 && chunk + 2 < n_chunks) issue(chunk + 2);
+        }
+        // (after the last chunk: the large-triangle phases use other fields of sh, the epilogue ends with a barrier)
+    }
+    // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
+    const int n_large = min(c_large, bins.large.offset[tile_id + 1] - bins.large.offset[tile_id]);
+    if (n_large > 0) {
+        const int *large = bins.large_refs + bins.large.offset[tile_id];
+        for (int base = 0; base < n_large; base += LARGE_CHUNK) {
+            const int m = min(LARGE_CHUNK, n_large - base);
+            if (base > 0) __syncthreads();  // the previous chunk's stencils / masks have been consumed
+            phase_tri_setup(s, tid, m, large + base, &sh);
             __syncthreads();
+            phase_tri_masks(s, tid, m, tile, &sh);
+            __syncthreads();
+            if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
         }
-        // large triangles: by index, stencil set-up and row spans computed here, one thread per triangle
-        const int n_large = segment_size(bins.large, tile_id);
-        if (n_large > 0) {
-            const int *large = bins.large_refs + bins.large.offset[tile_id];
-            for (int base = 0; base < n_large; base += LARGE_CHUNK) {
-                const int m = min(LARGE_CHUNK, n_large - base);
-                phase_tri_setup(s, tid, m, large + base, &sh);
-                __syncthreads();
-                phase_tri_masks(s, tid, m, tile, &sh);
-                __syncthreads();
-                if (inside) phase_tri_test<1>(s, tid, m, tile, &sh, &p);
-                __syncthreads();
-            }
-        }
-        if (inside) {
-            const size_t idx = (size_t)y * s.width + x;
-            z_buffer[idx] = p.z;
-            int code = p.bown;
-            if (p.own != p.bown) {  // exact z tie between distinct triangles: keep both ids in the side table
-                int slot = atomicAdd(ties.counter, 1);
-                if (slot < ties.capacity) {
-                    ties.pairs[2 * slot] = p.own;
-                    ties.pairs[2 * slot + 1] = p.bown;
-                    code = -2 - slot;
-                }
-            }
-            owner[idx] = code;
-            if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
-            if (FUSE) {
-                SceneView sc = s;
-                fix_channel_count<MAXC, TEX>(sc);
-                PixelState<MAXC> q;
-                q.own = p.own;
-                q.bown = p.bown;
-                q.z = PERSP && p.own >= 0 ? p.z : 0.0;
-                float w[3];
-                phase_shade<MAXC>(sc, x, y, &q, bary ? w : nullptr);
-                if (MAXC <= 4 && tma_store) {
-                    for (int k = 0; k < sc.nb_colors; k++) stage[tid * sc.nb_colors + k] = q.col[k];
-                } else {
-                    for (int k = 0; k < sc.nb_colors; k++) image[idx * sc.nb_colors + k] = q.col[k];
-                }
-                if (err) err[idx] = (float)pixel_residual<MAXC>(sc, q.col, obs + idx * sc.nb_colors);
-                if (bary) { bary[3 * idx] = w[0]; bary[3 * idx + 1] = w[1]; bary[3 * idx + 2] = w[2]; }
+    }
+    if (inside) {
+        const size_t idx = (size_t)y * s.width + x;
+        z_buffer[idx] = p.z;
+        int code = p.bown;
+        if (p.own != p.bown) {  // exact z tie between distinct triangles: keep both ids in the side table
+            int slot = atomicAdd(ties.counter, 1);
+            if (slot < ties.capacity) {
+                ties.pairs[2 * slot] = p.own;
+                ties.pairs[2 * slot + 1] = p.bown;
+                code = -2 - slot;
             }
         }
-        // the adjoint's pixel-parallel kernel walks the tiles where a pixel is owned by a triangle that the
-        // triangle-parallel adjoint does not take (medium and large triangles)
-        const bool other = inside && p.bown >= 0 && !(p.bown & SMALL_FLAG);
-        if (FUSE && MAXC <= 4 && tma_store) fence_proxy_async();  // this thread's staged colours -> visible to the TMA engine
-        const bool listed = __syncthreads_or(other);
-        if (tid == 0) {
-            if (listed) large_tiles[atomicAdd(scal + SC_LARGE_TILES, 1)] = tile_id;
-            if (FUSE && MAXC <= 4 && tma_store) {
-                // rows / columns of the box that stick out of the image are clipped by the hardware
-                tma_store_tile(&image_map, tile.x0 * s.nb_colors, tile.y0, stage);
-                tma_store_wait_read();  // the staging buffer is free again (next tile of a persistent launch / exit)
+        owner[idx] = code;
+        if (face_id) face_id[idx] = p.own >= 0 ? (p.own & TRI_INDEX_MASK) : -1;
+        if (FUSE) {
+            SceneView sc = s;
+            fix_channel_count<MAXC, TEX>(sc);
+            PixelState<MAXC> q;
+            q.own = p.own;
+            q.bown = p.bown;
+            q.z = PERSP && p.own >= 0 ? p.z : 0.0;
+            float w[3];
+            phase_shade<MAXC>(sc, x, y, &q, bary ? w : nullptr);
+            if (MAXC <= 4 && tma_store) {
+                for (int k = 0; k < sc.nb_colors; k++) stage[tid * sc.nb_colors + k] = q.col[k];
+            } else {
+                for (int k = 0; k < sc.nb_colors; k++) image[idx * sc.nb_colors + k] = q.col[k];
             }
+            if (err) err[idx] = (float)pixel_residual<MAXC>(sc, q.col, obs + idx * sc.nb_colors);
+            if (bary) { bary[3 * idx] = w[0]; bary[3 * idx + 1] = w[1]; bary[3 * idx + 2] = w[2]; }
+        }
+    }
+    // the adjoint's pixel-parallel kernel walks the tiles where a pixel is owned by a triangle that the
+    // triangle-parallel adjoint does not take (medium and large triangles)
+    const bool other = inside && p.bown >= 0 && !(p.bown & SMALL_FLAG);
+    if (FUSE && MAXC <= 4 && tma_store) fence_proxy_async();  // this thread's staged colours -> visible to the TMA engine
+    const bool listed = __syncthreads_or(other);
+    if (tid == 0) {
+        if (listed) large_tiles[atomicAdd(scal + SC_LARGE_TILES, 1)] = tile_id;
+        if (FUSE && MAXC <= 4 && tma_store) {
+            // rows / columns of the box that stick out of the image are clipped by the hardware
+            tma_store_tile(&image_map, tile.x0 * s.nb_colors, tile.y0, stage);
+            tma_store_wait_read();  // the staging buffer must outlive the copy engine's read
         }
     }
 }
@@ -663,12 +638,25 @@ static int bad_index_error(const ViewSlot *v) {
     return DEODR_B200_OK;
 }
 
+#ifndef DEODR_SMALL_TEXTURED_MIN_TRIANGLES
+#define DEODR_SMALL_TEXTURED_MIN_TRIANGLES 262144  // measured: 50k-triangle scene 0.287 -> 0.204 ms without, 1M-triangle scene 0.600 vs 0.651 ms with
+#endif
 // Height limit of the record path for triangles that are not small: RECORD_ROWS once the binning pass has enough
 // threads to fill the chip (a few resident warps per SM sub-partition), 0 below (DEODR_B200_RECORD_ROWS overrides).
 static int record_rows_for(int nb_triangles) {
     static const int forced = getenv("DEODR_B200_RECORD_ROWS") ? atoi(getenv("DEODR_B200_RECORD_ROWS")) : -1;
     if (forced >= 0) return forced < RECORD_ROWS ? forced : RECORD_ROWS;
     return nb_triangles >= 32768 ? RECORD_ROWS : 0;
+}
+
+// May textured triangles be "small" (triangle-parallel adjoint, TriBins::small_textured)?  One thread then walks up to
+// 64 pixels of dependent texture fetches + twelve texel atomics each: it needs several hundred thousand triangles in
+// flight to hide that latency.  Below, textured triangles are owned through the pixel-parallel adjoint (measured on
+// the 50k-triangle textured scene).  DEODR_B200_SMALL_TEXTURED = 0 / 1 overrides.
+static int small_textured_for(int nb_triangles) {
+    static const int forced = getenv("DEODR_B200_SMALL_TEXTURED") ? atoi(getenv("DEODR_B200_SMALL_TEXTURED")) : -1;
+    if (forced >= 0) return forced != 0;
+    return nb_triangles >= DEODR_SMALL_TEXTURED_MIN_TRIANGLES;
 }
 
 // Plan building: count pass + scans + ONE read-back, then the list buffers are (re)allocated.
@@ -685,7 +673,7 @@ static int build_plan(DeodrWorkspace *ws, ViewSlot *v, const SceneView &s, doubl
             ws->launches++;
         }
         TriBins bins{{nullptr, v->small_cursor}, nullptr, {nullptr, v->large_cursor}, nullptr, v->scal + SC_OVERFLOW,
-                     record_rows_for(T)};
+                     record_rows_for(T), small_textured_for(T)};
         EdgeList edges{v->scal + SC_EDGES, nullptr, nullptr, 0};
         k_bin<true><<<grid_for(T, 128), 128, 0, st>>>(s, sigma, v->tiles_x, bins, v->scal, nullptr, edges,
                                                      v->edge_cursor, 1);
@@ -753,17 +741,7 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
     if (fuse && ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, wait_flags);
     {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
-        // DEODR_B200_TILEZ_CTAS_PER_SM = k > 0 runs k persistent CTAs per SM with the two-stage TMA pipeline; default 0 =
-        // one CTA per tile (the same kernel, its loop runs once).  Measured on B200, 1M-triangle scene: 168 us per-tile
-        // vs 199 us persistent x4 vs 300 us persistent x2 - the hardware CTA scheduler balances the very uneven tiles
-        // better than a static stride, and 4 resident CTAs already overlap each other's copy latency.
-        static const int per_sm = getenv("DEODR_B200_TILEZ_CTAS_PER_SM") ? atoi(getenv("DEODR_B200_TILEZ_CTAS_PER_SM")) : 0;
-        // DEODR_B200_TILEZ_TILES_PER_CTA = k: every CTA walks k tiles (stride = grid size) with the copy of the next
-        // tile in flight while it tests the current one
-        static const int per_cta = getenv("DEODR_B200_TILEZ_TILES_PER_CTA") ? atoi(getenv("DEODR_B200_TILEZ_TILES_PER_CTA")) : 1;
-        int persistent = per_sm > 0 ? per_sm * (sm_count_cached > 0 ? sm_count_cached : 148) : v->num_tiles;
-        if (per_sm <= 0 && per_cta > 1) persistent = (v->num_tiles + per_cta - 1) / per_cta;
-        const int grid = v->num_tiles < persistent ? v->num_tiles : persistent;
+        const int grid = v->num_tiles;  // one CTA per tile (see k_tile_z)
         const float *obs = err_mode ? io.obs : nullptr;
         float *err = err_mode ? io.err_buffer : nullptr;
         TileMap image_map;
@@ -823,7 +801,7 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
     const bool err_mode = (flags & DEODR_B200_ANTIALIASE_ERROR) != 0;
     TriBins bins{{v->small_offset.as<int>(), v->small_cursor}, v->small_recs.as<PreRec>(),
                  {v->large_offset.as<int>(), v->large_cursor}, v->large_refs.as<int>(), v->scal + SC_OVERFLOW,
-                 record_rows_for(T)};
+                 record_rows_for(T), small_textured_for(T)};
     EdgeList edges{v->scal + SC_EDGES, v->edge_ids.as<int>(), v->edge_keys.as<uint64_t>(), plan.cap_edges};
     const bool edge_chain = plan.cap_edges > 0;
     {

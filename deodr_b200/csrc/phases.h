@@ -13,7 +13,10 @@ namespace deodr {
 constexpr int TS = 16;            // tile side in pixels
 constexpr int NT = TS * TS;       // threads per tile CTA, one per pixel
 constexpr int PRE_CHUNK = 128;    // pre-masked records per TMA bulk copy (double-buffered landing zone: 2 x 8 KB)
-constexpr int LARGE_CHUNK = 64;   // large triangles staged per pass (stencil records kept in shared memory)
+#ifndef DEODR_LARGE_CHUNK
+#define DEODR_LARGE_CHUNK 64
+#endif
+constexpr int LARGE_CHUNK = DEODR_LARGE_CHUNK;  // large triangles staged per pass (stencil records kept in shared memory)
 constexpr int PIX_SLOTS = 8;      // candidate small triangles kept per pixel and chunk before the pixel falls back to a scan
 constexpr int EDGE_CHUNK = 64;    // edge records staged in shared memory per pass
 #ifndef DEODR_EDGE_ROWS
@@ -53,22 +56,26 @@ static_assert(sizeof(PreRec) == 64, "PreRec must be 64 bytes");
 constexpr int SMALL_FLAG = 0x40000000;
 constexpr int TRI_INDEX_MASK = 0x3fffffff;
 
+// Shared-memory working set of the tile kernels.  The z pass only uses `tri` and allocates just that part (it is what
+// bounds its CTAs per SM, see k_tile_z); the edge kernels only use `edge`.
 struct TileShared {
+    struct TriPart {
+        TriGeom geo[LARGE_CHUNK];  // large triangles: stencils, so that their row spans are computed by 8 threads each
+        TriRec rec[LARGE_CHUNK];
+        // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
+        // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time
+        alignas(16) uint32_t mask[TS / 2][LARGE_CHUNK];
+        // small triangles: per-pixel candidate lists filled by the record threads (phase_pre_scatter)
+        int pix_cnt[NT];
+        uint8_t pix_list[PIX_SLOTS][NT];
+    };
+    struct EdgePart {
+        EdgeRec rec[EDGE_CHUNK];
+        uint32_t span[EDGE_CHUNK][TS];  // x_begin | x_end << 16 (absolute, int16 each); empty if begin > end
+    };
     union {
-        struct {
-            TriGeom geo[LARGE_CHUNK];  // large triangles: stencils, so that their row spans are computed by 8 threads each
-            TriRec rec[LARGE_CHUNK];
-            // mask[p][t]: coverage of tile rows 2p (bits 0-15) and 2p+1 (bits 16-31) by triangle t, i.e. one bit per
-            // lane of warp p; row-pair-major so that a warp streams its own masks four triangles at a time
-            alignas(16) uint32_t mask[TS / 2][LARGE_CHUNK];
-            // small triangles: per-pixel candidate lists filled by the record threads (phase_pre_scatter)
-            int pix_cnt[NT];
-            uint8_t pix_list[PIX_SLOTS][NT];
-        } tri;
-        struct {
-            EdgeRec rec[EDGE_CHUNK];
-            uint32_t span[EDGE_CHUNK][TS];  // x_begin | x_end << 16 (absolute, int16 each); empty if begin > end
-        } edge;
+        TriPart tri;
+        EdgePart edge;
     };
 };
 
@@ -227,6 +234,11 @@ struct TriBins {
     int *large_refs;
     int *verdict;      // scal + SC_OVERFLOW
     int record_rows;   // height limit of the record path for triangles that are not small (see takes_record_path)
+    // May a TEXTURED triangle be "small" (adjoint by the triangle-parallel kernel)?  Its per-pixel adjoint is a chain of
+    // dependent texture fetches and twelve texel atomics; one thread walking up to 64 such pixels is only worth it when
+    // the scene has enough small triangles to fill the chip with threads (kernels.cu: small_textured_for).  0: textured
+    // triangles keep the record path of the forward pass but are owned without SMALL_FLAG (pixel-parallel adjoint).
+    int small_textured;
 };
 
 // "small" = micro-triangle: at most 2 x 2 tiles and a bounding box that fits a 64-bit mask with a power-of-two row
@@ -377,11 +389,13 @@ DEODR_HD void bin_triangle(const SceneView &s, int k, double sigma, int tiles_x,
     const TileBox b = tri_tile_box(V, s.strict_edge != 0, s.width, s.height, &box_w, &box_h);
     if (b.tx0 > b.tx1) return;  // off screen
     const bool records = takes_record_path(b, box_w, box_h, bins.record_rows);
+    // small = the triangle-parallel adjoint takes it (textured triangles only when the plan says so)
+    const bool small = is_small(b, box_w, box_h) && (bins.small_textured || !(s.textured[k] && s.shaded[k]));
     if (COUNT_ONLY) {
         int *count = records ? bins.small.cursor : bins.large.cursor;
         // a record-path triangle that is not small is owned through the pixel-parallel adjoint: bit 30 of the tile's
         // large counter marks the tile for the plan's launch hint (k_scan_tiles masks it out of the capacity)
-        const bool medium = records && !is_small(b, box_w, box_h);
+        const bool medium = records && !small;
         for (int ty = b.ty0; ty <= b.ty1; ty++)
             for (int tx = b.tx0; tx <= b.tx1; tx++) {
                 Env::atomic_add(&count[ty * tiles_x + tx], 1);
@@ -390,7 +404,6 @@ DEODR_HD void bin_triangle(const SceneView &s, int k, double sigma, int tiles_x,
         return;
     }
     if (records) {
-        const bool small = is_small(b, box_w, box_h);
         // the compact list of the drawn small triangles is what the triangle-parallel adjoint walks (capacity T)
         if (small) small_ids[Env::atomic_add(num_small, 1)] = k;
         bin_small<Env>(s, small ? (k | SMALL_FLAG) : k, V, Zv, b, tiles_x, bins);

@@ -88,6 +88,10 @@ class Emulator:
         """Height limit of the record path for triangles that are not small (the device: 16, or 0 for tiny scenes)."""
         self.lib.emul_set_record_rows(int(rows))
 
+    def set_small_textured(self, on):
+        """May textured triangles take the triangle-parallel adjoint (TriBins::small_textured)?"""
+        self.lib.emul_set_small_textured(int(bool(on)))
+
     def build_plan(self, scene, sigma):
         """Segment capacities from `scene` (count-only pass + scans), kept for the render_planned calls that follow."""
         a = canonical_arrays(scene)

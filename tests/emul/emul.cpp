@@ -46,6 +46,7 @@ struct EmulState {
 };
 
 static EmulState g_state;
+static int g_small_textured = 1;  // 0: textured triangles go through the pixel-parallel adjoint (TriBins::small_textured)
 static int g_record_rows = RECORD_ROWS;  // the device picks 0 for scenes of a few thousand triangles: both are emulated
 
 // k_scan_tiles: exclusive scan of the counts padded with slack (c + c/4 + 4, kernels.cu SEG_SLACK)
@@ -267,7 +268,7 @@ static void emul_plan(const SceneView &s, double sigma, EmulState &st) {
     std::vector<int> small_count(st.nt, 0), large_count(st.nt, 0), edge_count(st.nt, 0);
     int scal[SC_WORDS] = {0};
     TriBins bins{{nullptr, small_count.data()}, nullptr, {nullptr, large_count.data()}, nullptr, scal + SC_OVERFLOW,
-                 g_record_rows};
+                 g_record_rows, g_small_textured};
     EdgeList edges{scal + SC_EDGES, nullptr, nullptr, 0};
     for (int k = 0; k < T; k++)
         bin_triangle<HostEnv, true>(s, k, sigma, st.tiles_x, bins, scal + SC_SMALL, nullptr, edges, edge_count.data());
@@ -293,7 +294,7 @@ static int emul_forward(const SceneView &s, double sigma, EmulState &st, float *
     st.edge_keys.assign(st.cap_edges + 4, 0);
     st.tie_pairs.clear();
     TriBins bins{st.small_seg(), st.small_recs.data(), st.large_seg(), st.large_refs.data(), st.scal + SC_OVERFLOW,
-                 g_record_rows};
+                 g_record_rows, g_small_textured};
     EdgeList edges{st.scal + SC_EDGES, st.edge_ids.data(), st.edge_keys.data(), st.cap_edges};
     // k_bin, in DESCENDING triangle order: the device appends in an arbitrary order, nothing may depend on it
     for (int k = T - 1; k >= 0; k--)
@@ -488,6 +489,7 @@ void emul_weight_scale(const DeodrSceneView *scene, const int32_t *face_id, cons
 }
 
 void emul_set_record_rows(int rows) { g_record_rows = rows; }
+void emul_set_small_textured(int on) { g_small_textured = on; }
 int emul_num_ties(void) { return (int)g_state.tie_pairs.size() / 2; }
 int emul_num_edges(void) { return g_state.E; }
 int emul_tri_refs(void) {

@@ -98,6 +98,18 @@ def test_emulated_kernels_mesh(emulator, checker):
     check(emulator, checker, torus_scene(16, 70, 50, nb_colors=1), 1.0)
 
 
+def test_textured_triangles_through_the_pixel_parallel_adjoint(emulator, checker, texture):
+    """TriBins::small_textured = 0 (what the device picks below a few hundred thousand triangles): textured triangles
+    keep their forward records but are owned without SMALL_FLAG, so their adjoint is the pixel-parallel kernel's."""
+    emulator.set_small_textured(False)
+    try:
+        check(emulator, checker, torus_scene(30, 100, 90, textured=True, texture_size=32), 1.0)
+        np.random.seed(2)
+        check(emulator, checker, soup_scene(texture=texture), 1.0)  # textured and interpolated triangles mixed
+    finally:
+        emulator.set_small_textured(True)
+
+
 def test_exact_z_ties_are_split_like_the_reference(emulator, checker, texture):
     """Duplicated interpolated triangles tie exactly in z: forward keeps the lowest index (strict '<', DR.h:961),
     the adjoint credits the highest (DR.h:1024 in reverse order)."""
