@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("DEODR_B200_LIB") or os.path.join(_HERE, "libdeodr_b20
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM, EREPLAN = 0, 1, 2, 3, 4, 5
 ANTIALIASE_ERROR, ERROR_ADJOINT_COMPLETE = 1, 2  # flags of the *_views entry points
+FORWARD_GEOMETRY, FORWARD_RESUME = 4, 8        # a forward pass in two calls (render_views only)
 
 
 class SceneView(C.Structure):

@@ -91,7 +91,10 @@ static int crew_size() {
 // call (DRAM-bound: 100 MB of image_b to convert + the 120 MB mirror comparison) with 16 (2.2 ms vs 3.3 ms with 8).
 constexpr size_t DMA_CHUNK = (size_t)4 << 20;  // bytes of device-layout data per DMA / per gate
 
-// Workers allowed on each kind of batch (DEODR_B200_HOST_WIDTH_<KIND> overrides; measured defaults)
+// Workers allowed on each kind of batch (DEODR_B200_HOST_WIDTH_<KIND> overrides).  Measured on the 2 x 32-core host of
+// the B200 boxes, 1M-triangle scene at 2048^2, three interleaved repeats: scene upload 7 -> 15 workers 3.7 -> 3.27 ms per
+// forward call (the conversions feed the DMA queue faster), gradient download + accumulate 7 -> 15 workers 2.50 -> 2.37 ms
+// per adjoint call; the image / z download (PCIe-bound) and the zero fill are no faster with more than 7.
 static int batch_width(const char *kind, int dflt) {
     char name[64];
     snprintf(name, sizeof(name), "DEODR_B200_HOST_WIDTH_%s", kind);
@@ -346,7 +349,7 @@ static int stage_scene(DeodrWorkspace *ws, HostPath *hp, const DeodrHostScene *h
     // one batch for the whole scene: every array is cut into DMA chunks, each sent as soon as the workers have
     // written it into the mirror (conversion, copy and PCIe transfer of different chunks overlap)
     Batch b;
-    static const int width_up = batch_width("UP", WIDTH_PCIE_BOUND);
+    static const int width_up = batch_width("UP", 15);
     b.width = width_up;
     std::vector<UploadPiece> pieces;
     for (int i = 0; i < SL_COUNT; i++) {
@@ -622,7 +625,7 @@ int deodr_b200_render_b_host(DeodrWorkspace *ws, const DeodrHostScene *scene, do
     double *dst[5] = {scene->ij_b, scene->colors_b, scene->uv_b, scene->shade_b, scene->texture_b};
     const size_t cnt[5] = {n_ij, n_col, n_uv, n_sh, tex};
     DownloadSet d;
-    static const int width_grads = batch_width("GRADS", WIDTH_PCIE_BOUND);
+    static const int width_grads = batch_width("GRADS", 15);
     d.batch.width = width_grads;
     d.size_for(n_grad * 4, 5);
     size_t off = 0;

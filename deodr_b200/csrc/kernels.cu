@@ -721,9 +721,11 @@ static int build_plan(DeodrWorkspace *ws, ViewSlot *v, const SceneView &s, doubl
     return DEODR_B200_OK;
 }
 
+// `stage`: 0 = z pass (shading fused when possible), colour pass if unfused, edge overdraw; 1 = the UNFUSED z pass only
+// (the geometry half of a forward in two calls); 2 = what follows it (colour pass + edge overdraw).
 template <int MAXC>
 static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneView &s, const DeodrViewIO &io,
-                              double sigma, bool err_mode, bool edge_chain, const TriBins &bins) {
+                              double sigma, bool err_mode, bool edge_chain, const TriBins &bins, int stage = 0) {
     cudaStream_t st = lane.main;
     const bool tex = v->plan.tex != 0;
     const TileDiv div = make_tile_div(v->tiles_x);
@@ -734,12 +736,12 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
     // the caller's communication (default: stay fused and wait in front of the z pass - the binning pass alone, 75 us on
     // the 1M-triangle scene, hides an all-reduce of the colour gradient, and fusion is worth 24 us every step)
     static const bool late_shade = getenv("DEODR_B200_LATE_COLORS") && !strcmp(getenv("DEODR_B200_LATE_COLORS"), "shade");
-    const bool fuse = fuse_allowed && !(ws->colors_ready && late_shade);
+    const bool fuse = stage == 0 && fuse_allowed && !(ws->colors_ready && late_shade);
     // (inside a capture - the library's own or the caller's - the wait becomes an EXTERNAL event wait node: every replay
     // waits for whatever the caller has recorded on the event by the time the replay gets there)
     const unsigned wait_flags = (ws->capturing_internally || stream_is_capturing(st)) ? cudaEventWaitExternal : 0;
     if (fuse && ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, wait_flags);
-    {
+    if (stage != 2) {
         PhaseTimer timer(ws, DEODR_B200_PH_TILE_Z, st);
         const int grid = v->num_tiles;  // one CTA per tile (see k_tile_z)
         const float *obs = err_mode ? io.obs : nullptr;
@@ -760,6 +762,7 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
 #undef DEODR_TILE_Z
         ws->launches++;
     }
+    if (stage == 1) return;
     if (!fuse) {
         if (ws->colors_ready) cudaStreamWaitEvent(st, ws->colors_ready, wait_flags);  // first reader of the colours here
         PhaseTimer timer(ws, DEODR_B200_PH_SHADE, st);
@@ -793,8 +796,10 @@ static void launch_raster_fwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const
 }
 
 // Enqueues one forward pass of the view on the lane's streams, against the slot's plan; nothing here waits.
+// `part`: 0 = the whole pass; 1 = its head only (list reset, index check, binning: DEODR_B200_FORWARD_GEOMETRY);
+// 2 = everything after the head (DEODR_B200_FORWARD_RESUME).
 static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneView &s, const DeodrViewIO &io,
-                           double sigma, int flags, bool check_indices) {
+                           double sigma, int flags, bool check_indices, int part = 0) {
     cudaStream_t st = lane.main;
     const FwdPlan &plan = v->plan;
     const int T = s.nb_triangles, nt = v->num_tiles;
@@ -804,7 +809,7 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
                  record_rows_for(T), small_textured_for(T)};
     EdgeList edges{v->scal + SC_EDGES, v->edge_ids.as<int>(), v->edge_keys.as<uint64_t>(), plan.cap_edges};
     const bool edge_chain = plan.cap_edges > 0;
-    {
+    if (part != 2) {
         PhaseTimer timer(ws, DEODR_B200_PH_BIN, st);
         CUDA_TRY(cudaMemsetAsync(v->scal, 0, (SC_WORDS + 3 * (size_t)nt) * sizeof(int), st));
         if (T > 0) {
@@ -816,6 +821,26 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
                                                           edges, nullptr, plan.tex);
             ws->launches++;
         }
+    }
+    // A forward in two calls: the head is the binning pass (75 us on the 1M-triangle scene, enough to hide a 6 MB
+    // all-reduce on NVLink) and the second call runs the fused z pass.  DEODR_B200_GEOMETRY_Z=1 moves the z pass -
+    // unfused: it reads no colour either - into the head as well: 150+ us to hide a slower collective behind, at the
+    // price of the separate colour pass.  Measured on 2 GPUs (1M triangles, 2048^2): 0.352 ms per step without, 0.361 -
+    // 0.389 ms with; one GPU, no collective: 0.312 ms.
+    static const bool geometry_z = getenv("DEODR_B200_GEOMETRY_Z") && atoi(getenv("DEODR_B200_GEOMETRY_Z")) != 0;
+    const int C = s.nb_colors;
+    const int stage = part == 0 || !geometry_z ? 0 : part;
+#define DEODR_RASTER_FWD(STAGE)                                                                            \
+    do {                                                                                                   \
+        if (C == 1) launch_raster_fwd<1>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins, STAGE);     \
+        else if (C == 3) launch_raster_fwd<3>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins, STAGE); \
+        else if (C <= 4) launch_raster_fwd<4>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins, STAGE); \
+        else launch_raster_fwd<16>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins, STAGE);           \
+    } while (0)
+    if (part == 1) {
+        if (geometry_z) DEODR_RASTER_FWD(1);
+        CUDA_TRY(cudaGetLastError());
+        return DEODR_B200_OK;
     }
     // ---- side chain (aux stream 0): silhouette-edge records + tile lists + their order, then the verdict goes to
     // the host; it overlaps the z pass and the shading and is joined before k_edge_fwd
@@ -849,11 +874,8 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
         // depend on the aux stream, but the lane must still be joined for stream capture / ordering of the next pass)
     }
     // ---- main chain: z pass, shading, (join) edge overdraw
-    const int C = s.nb_colors;
-    if (C == 1) launch_raster_fwd<1>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins);
-    else if (C == 3) launch_raster_fwd<3>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins);
-    else if (C <= 4) launch_raster_fwd<4>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins);
-    else launch_raster_fwd<16>(ws, v, lane, s, io, sigma, err_mode, edge_chain, bins);
+    DEODR_RASTER_FWD(stage);
+#undef DEODR_RASTER_FWD
     if (!edge_chain) join_stream(ws, lane, 0);
     CUDA_TRY(cudaGetLastError());
     return DEODR_B200_OK;
@@ -1025,6 +1047,11 @@ static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneVi
     CUDA_TRY(cudaSetDevice(ws->device));
     const bool capturing = stream_is_capturing(st);
     const bool deferred = ws->deferred || capturing;
+    // a pass in two calls: 1 = head only, 2 = the rest of the pass whose head the previous call enqueued
+    const int part = (flags & DEODR_B200_FORWARD_GEOMETRY) ? 1 : (flags & DEODR_B200_FORWARD_RESUME) ? 2 : 0;
+    if ((flags & DEODR_B200_FORWARD_GEOMETRY) && (flags & DEODR_B200_FORWARD_RESUME))
+        return set_error(DEODR_B200_EINVAL, "FORWARD_GEOMETRY and FORWARD_RESUME are two calls, not one");
+    flags &= ~(DEODR_B200_FORWARD_GEOMETRY | DEODR_B200_FORWARD_RESUME);
     std::vector<ViewSlot *> slots(n_views);
     std::vector<SceneView> scenes(n_views);
     // ---- plans first (a plan needs the device: not possible while capturing)
@@ -1037,6 +1064,14 @@ static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneVi
             if (int rc = read_verdict(ws, v, st, &overflow)) return rc;
         }
         v->fwd_valid = 0;
+        const bool same_shape = v->plan.valid && v->plan.T == scenes[i].nb_triangles && v->plan.H == scenes[i].height &&
+                                v->plan.W == scenes[i].width && v->plan.edges_possible == (sigma > 0);
+        if (part == 2) {  // the head has filled the lists of THIS plan: nothing may be rebuilt in between
+            if (!v->head_enqueued || !same_shape)
+                return set_error(DEODR_B200_EINVAL, "FORWARD_RESUME must follow FORWARD_GEOMETRY of the same views");
+            continue;
+        }
+        v->head_enqueued = false;
         if (!capturing) {
             if (int rc = prepare_slot(ws, v, scenes[i], sigma)) return rc;
         } else if (!v->plan.valid || v->plan.T != scenes[i].nb_triangles || v->plan.H != scenes[i].height ||
@@ -1053,12 +1088,18 @@ static int render_views_impl(DeodrWorkspace *ws, int n_views, const DeodrSceneVi
     auto enqueue_all = [&]() -> int {
         open_lanes(ws, st, used);
         for (int i = 0; i < n_views; i++)
-            if (int rc = enqueue_forward(ws, slots[i], ws->lanes[i % used], scenes[i], io[i], sigma, flags, check_indices))
+            if (int rc = enqueue_forward(ws, slots[i], ws->lanes[i % used], scenes[i], io[i], sigma, flags, check_indices, part))
                 return rc;
         close_lanes(ws, st, used);
         return DEODR_B200_OK;
     };
-    if (graphs_usable(ws, st, capturing)) {
+    if (part == 1) {  // head only: no verdict yet, no forward state for the adjoint yet, the colours-ready event is kept
+        if (int rc = enqueue_all()) return rc;
+        for (int i = 0; i < n_views; i++) slots[i]->head_enqueued = true;
+        return DEODR_B200_OK;
+    }
+    for (int i = 0; i < n_views; i++) slots[i]->head_enqueued = false;
+    if (part == 0 && graphs_usable(ws, st, capturing)) {
         const cudaStream_t caller = st;
         st = hop_in(ws, caller);
         KeyWriter key;

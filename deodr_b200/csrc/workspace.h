@@ -84,6 +84,7 @@ struct ViewSlot {
     DeodrViewIO fwd_io;
     bool fwd_check_indices = false;
     bool pending = false;     // a pass has been enqueued whose verdict has not been read yet
+    bool head_enqueued = false;  // DEODR_B200_FORWARD_GEOMETRY has run; the RESUME call of the same pass must follow
     bool hints_exact = false; // the plan's hints are the counts of the slot's last pass (its verdict has been read)
     int totals_seq = 0;       // sequence number of the flag the publishing kernel raises in host_totals[SC_WORDS]
     int *host_totals = nullptr;  // pinned: SC_WORDS scalars + the sequence flag

@@ -236,9 +236,13 @@ class Renderer:
     # ---- batch of views (slots 0 .. n-1) --------------------------------------------------------------------------
     def render_views(self, scenes: Sequence[DeviceScene], sigma: float, face_id: bool = False,
                      out: Optional[List[dict]] = None, barycentric: bool = False,
-                     obs: Optional[Sequence[torch.Tensor]] = None) -> List[dict]:
+                     obs: Optional[Sequence[torch.Tensor]] = None, part: Optional[str] = None) -> List[dict]:
         """Forward passes of ``len(scenes)`` views in ONE library call (deodr_b200_render_views): the views are
-        interleaved on a few internal streams and no pass waits for the host."""
+        interleaved on a few internal streams and no pass waits for the host.
+
+        ``part="geometry"`` enqueues only the head of the passes (list reset + binning: reads no colour) and
+        ``part="resume"``, with the same arguments and ``out``, the rest: a caller whose colours come out of a
+        collective puts its stream wait between the two calls (DEODR_B200_FORWARD_GEOMETRY / _RESUME)."""
         n = len(scenes)
         err_mode = obs is not None
         if out is None:
@@ -250,9 +254,13 @@ class Renderer:
                 if o.get("err_buffer") is None:
                     o["err_buffer"] = torch.empty(o["z_buffer"].shape, dtype=torch.float32, device=o["z_buffer"].device)
         ios = (_cabi.ViewIO * n)(*[self._io(o, obs[i] if err_mode else None) for i, o in enumerate(out)])
+        part_flag = {None: 0, "geometry": _cabi.FORWARD_GEOMETRY, "resume": _cabi.FORWARD_RESUME}[part]
         with self._lock:
             _cabi.check(self.lib.deodr_b200_render_views(self._ws, n, views, ios, float(sigma),
-                                                         _cabi.ANTIALIASE_ERROR if err_mode else 0, self._stream()))
+                                                         (_cabi.ANTIALIASE_ERROR if err_mode else 0) | part_flag,
+                                                         self._stream()))
+            if part == "geometry":
+                return out  # no forward state yet: the "resume" call stamps the results
             for i, o in enumerate(out):
                 o["generation"] = self.generation(i)
                 o["slot"] = i

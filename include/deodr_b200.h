@@ -45,9 +45,19 @@ enum {
 enum {
     DEODR_B200_ANTIALIASE_ERROR = 1, /* renderScene(..., antialiaseError = true): the silhouette edges overdraw the
                                         squared residual err_buffer instead of the image (DR.h:2066-2618, 2824-2837) */
-    DEODR_B200_ERROR_ADJOINT_COMPLETE = 2 /* adjoint of the mode above WITHOUT the reference's dropped row term
+    DEODR_B200_ERROR_ADJOINT_COMPLETE = 2, /* adjoint of the mode above WITHOUT the reference's dropped row term
                                         (DR.h:2577-2583 never propagates A0y_B): the mathematically complete gradient.
                                         Default (flag clear) = bug-compatible with the reference. */
+    /* A forward pass in two calls (deodr_b200_render_views only), for callers that overlap a collective with it:
+     * GEOMETRY enqueues the head of the pass - list reset, index check, binning (with DEODR_B200_GEOMETRY_Z=1 in the
+     * environment also the z pass, unfused): kernels that read only faces, ij, depths and the flags - and returns;
+     * RESUME, with the same arguments, enqueues the rest (edge records, z pass + shading, edge overdraw: the readers of
+     * colours / uv / shade / texture).  Between the two the caller makes `stream`
+     * wait for whatever produces the colours (cudaStreamWaitEvent on its communication stream's event): unlike the
+     * colours-ready event below, that wait is an ordinary stream dependency, so both halves can be captured in CUDA
+     * graphs of their own and replayed with the wait in between.  The verdict of the pass belongs to the RESUME call. */
+    DEODR_B200_FORWARD_GEOMETRY = 4,
+    DEODR_B200_FORWARD_RESUME = 8
 };
 
 /* Device-resident scene ("SceneView"): the fields of struct Scene (DR.h:56-90) in the canonical device layout. */

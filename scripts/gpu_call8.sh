@@ -1,0 +1,19 @@
+#!/bin/bash
+# Round-2 session H (2 GPUs): the forward in two calls (test) and the N = 2 bench with the step as two graphs.
+tag=${1:-r2o}
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_views.py -k "two_calls or graph or batch_of_views" -m gpu -q -x -p no:cacheprovider --timeout 600 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${tag}_pytest.log
+show() { python - <<PY
+import json
+try:
+    d=[l for l in open("gpurun_out/${tag}_$1.json").read().strip().splitlines() if l.startswith("{")][-1]
+    d=json.loads(d)
+    print("$1:", d["ms_per_step"], d["value"], d["config"]["timed_region"], "eager", d["config"]["eager_ms_per_step"], "e2e", (d.get("e2e") or {}).get("ms_per_step"))
+except Exception as e:
+    print("$1 FAILED", e); print(open("gpurun_out/${tag}_$1.err").read()[-1500:])
+PY
+}
+python bench.py --steps 50 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/${tag}_n1.json 2> gpurun_out/${tag}_n1.err
+show n1
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_n2.json 2> gpurun_out/${tag}_n2.err
+show n2

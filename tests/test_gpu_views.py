@@ -214,6 +214,71 @@ def test_cuda_graph_capture_of_forward_and_adjoint(checker):
     gpu.set_deferred(False)
 
 
+def test_forward_in_two_calls_with_the_colours_arriving_in_between(checker):
+    """DEODR_B200_FORWARD_GEOMETRY / _RESUME: the head of the pass (binning) is enqueued - and captured in a graph of
+    its own - BEFORE the colours exist; they are written by another stream (the caller's communication stream) and the
+    rest of the pass (a second graph) runs behind an ordinary stream wait.  Same results as one call."""
+    import torch
+
+    from deodr_b200 import _cabi
+    from deodr_b200.renderer import DeviceScene, Renderer
+
+    gpu = Renderer(0)
+    scenes = [torus_scene(40, 256, 192, view=v, n_views=3) for v in range(3)]
+    dss = [DeviceScene(s, "cuda:0") for s in scenes]
+    image_bs = [torch.from_numpy(dense_image_b(np.zeros((192, 256, 3)), seed=v).astype(np.float32)).cuda() for v in range(3)]
+    colours = [ds.t["colors"].clone() for ds in dss]
+    with pytest.raises(_cabi.DeodrB200Error):  # nothing to resume yet
+        gpu.render_views(dss, 1.0, part="resume")
+    ref_out = gpu.render_views(dss, 1.0)           # one call (also builds the plans)
+    ref_g = gpu.render_b_views(dss, 1.0, ref_out, image_bs)
+    torch.cuda.synchronize()
+    ref = [(o["image"].clone(), o["z_buffer"].clone()) for o in ref_out]
+    # eager, two calls
+    out = gpu.render_views(dss, 1.0, part="geometry")
+    out = gpu.render_views(dss, 1.0, out=out, part="resume")
+    got_g = gpu.render_b_views(dss, 1.0, out, image_bs)
+    torch.cuda.synchronize()
+    for (image, z), o in zip(ref, out):
+        assert torch.equal(o["z_buffer"], z) and torch.equal(o["image"], image)
+    for a, b in zip(ref_g, got_g):
+        assert_gradient_close(b["ij_b"].cpu().numpy(), a["ij_b"].cpu().numpy().astype(np.float64), "ij_b")
+    # two graphs, the colours written by a second stream between them
+    main, side = torch.cuda.Stream(), torch.cuda.Stream()
+    ready = torch.cuda.Event()
+    grads = [ds.zero_grads() for ds in dss]
+    gpu.set_deferred(True)
+    head, tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.stream(main):
+        with torch.cuda.graph(head, stream=main):
+            gpu.render_views(dss, 1.0, out=out, part="geometry")
+        with torch.cuda.graph(tail, stream=main):
+            gpu.render_views(dss, 1.0, out=out, part="resume")
+            gpu.render_b_views(dss, 1.0, out, image_bs, grads)
+        for _ in range(2):
+            for ds in dss:
+                ds.t["colors"].zero_()             # stale colours: must not be read by the head
+            for g in grads:
+                for t in g.values():
+                    t.zero_()
+            side.wait_stream(main)
+            head.replay()
+            with torch.cuda.stream(side):
+                for ds, c in zip(dss, colours):
+                    ds.t["colors"].copy_(c)        # "all-reduce + optimiser" on the communication stream
+                ready.record(side)
+            main.wait_event(ready)
+            tail.replay()
+    torch.cuda.synchronize()
+    gpu.status()
+    gpu.set_deferred(False)
+    for (image, z), o in zip(ref, out):
+        assert torch.equal(o["z_buffer"], z) and torch.equal(o["image"], image)
+    for a, b in zip(ref_g, grads):
+        assert_gradient_close(b["ij_b"].cpu().numpy(), a["ij_b"].cpu().numpy().astype(np.float64), "ij_b")
+        assert_gradient_close(b["colors_b"].cpu().numpy(), a["colors_b"].cpu().numpy().astype(np.float64), "colors_b")
+
+
 @pytest.mark.parametrize("clockwise", [False, True])
 def test_antialiase_error_mode(clockwise, gpu, checker, texture):
     """Row f3: the silhouette edges overdraw the squared residual (DR.h:2066-2618).  Forward: image (aliased), z-buffer
