@@ -156,13 +156,24 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(ScanJob job, int n, int *sc
     }
 }
 
-// One thread per appended silhouette edge (stride loop over the device-side count): stencil record + tile lists.
+// One WARP per appended silhouette edge (stride loop over the device-side count): stencil record + tile lists.  Every
+// lane computes the edge's record (same instructions, one merged store) and then takes its share of the tiles of the
+// band, so that the returning atomics of the segment appends - 10 to 30 per edge, a serial chain of L2 round trips when
+// one thread walks them - are issued side by side.  The scenes this matters for are the small ones, where this kernel
+// sits on the forward's critical path (1k-triangle scene at 640x480: 32 us with one thread per edge).
 __global__ void __launch_bounds__(128) k_bin_edges(SceneView s, double sigma, int tiles_x, EdgeList edges, EdgeBins bins,
                                                    EdgeRec *recs, const int *scal) {
     if (scal[SC_OVERFLOW]) return;
     const int n = min(*edges.count, edges.capacity);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        bin_edge<DevEnv>(s, i, sigma, tiles_x, edges, bins, recs);
+    const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < n; slot += warps) {
+        double V[2][2];
+        edge_record(s, edges.ids[slot], slot, edges.keys[slot], sigma, &recs[slot], V);
+        const TileBox b = edge_tile_box(V, sigma, s.width, s.height);
+        if (b.tx0 > b.tx1) continue;
+        const int bw = b.tx1 - b.tx0 + 1, count = bw * (b.ty1 - b.ty0 + 1);
+        for (int j = lane; j < count; j += 32) bin_edge_tile<DevEnv>(slot, (b.ty0 + j / bw) * tiles_x + b.tx0 + j % bw, bins);
+    }
 }
 
 // Orders the edge list of every tile that has one far to near (tile_edge_position, phases.h) and moves the tile to the
@@ -854,7 +865,7 @@ static int enqueue_forward(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const Sc
                              v->edge_tiles_raw.as<int>(), v->scal + SC_EDGE_TILES, plan.cap_edge_tiles};
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BIN, se);
-            k_bin_edges<<<at_least_one(grid_for(plan.hint_edges, 128)), 128, 0, se>>>(s, sigma, v->tiles_x, edges, ebins,
+            k_bin_edges<<<at_least_one(grid_for(32 * (size_t)plan.hint_edges, 128)), 128, 0, se>>>(s, sigma, v->tiles_x, edges, ebins,
                                                                                       v->edge_recs.as<EdgeRec>(), v->scal);
         }
         {

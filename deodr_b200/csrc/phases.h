@@ -427,6 +427,20 @@ struct EdgeBins {
     int tile_capacity;
 };
 
+// edge `slot` -> list of tile t
+template <class Env>
+DEODR_HD void bin_edge_tile(int slot, int t, const EdgeBins &bins) {
+    const int pos = segment_reserve<Env>(bins.seg, t, bins.verdict, OVF_EDGE_REFS);
+    if (pos < 0) return;
+    bins.refs[pos] = slot;
+    if (pos == bins.seg.offset[t]) {  // first edge of the tile: the tile joins the list the edge kernels walk
+        const int at = Env::atomic_add(bins.tile_count, 1);
+        if (at < bins.tile_capacity) bins.tile_list[at] = t;
+        else Env::atomic_or(bins.verdict, OVF_EDGE_TILES);
+    }
+}
+
+// (one thread per edge: the CPU emulation's form; the device kernel spreads the tiles of the band over a warp)
 template <class Env>
 DEODR_HD void bin_edge(const SceneView &s, int slot, double sigma, int tiles_x, const EdgeList &edges,
                        const EdgeBins &bins, EdgeRec *recs) {
@@ -435,17 +449,7 @@ DEODR_HD void bin_edge(const SceneView &s, int slot, double sigma, int tiles_x, 
     edge_record(s, id, slot, edges.keys[slot], sigma, &recs[slot], V);
     const TileBox b = edge_tile_box(V, sigma, s.width, s.height);
     for (int ty = b.ty0; ty <= b.ty1; ty++)
-        for (int tx = b.tx0; tx <= b.tx1; tx++) {
-            const int t = ty * tiles_x + tx;
-            const int pos = segment_reserve<Env>(bins.seg, t, bins.verdict, OVF_EDGE_REFS);
-            if (pos < 0) continue;
-            bins.refs[pos] = slot;
-            if (pos == bins.seg.offset[t]) {  // first edge of the tile: the tile joins the list the edge kernels walk
-                const int at = Env::atomic_add(bins.tile_count, 1);
-                if (at < bins.tile_capacity) bins.tile_list[at] = t;
-                else Env::atomic_or(bins.verdict, OVF_EDGE_TILES);
-            }
-        }
+        for (int tx = b.tx0; tx <= b.tx1; tx++) bin_edge_tile<Env>(slot, ty * tiles_x + tx, bins);
 }
 
 // Far-to-near position of item i of a tile's edge list: the reference walks the edges in descending order of their

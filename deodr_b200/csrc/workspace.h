@@ -113,7 +113,7 @@ struct Lane {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // lanes > 0: fork from / join to the caller's stream
 };
 
-constexpr int MAX_LANES = 4;
+constexpr int MAX_LANES = 8;
 
 // A launch sequence captured once and replayed while nothing it depends on changes: a fitting loop calls the library
 // with the same buffers, shapes and plans step after step, and a replayed graph has none of the per-launch gaps of a
@@ -146,7 +146,9 @@ struct DeodrWorkspace {
     // the legacy default stream cannot be captured: a call made on it hops to this stream (event in, event out)
     cudaStream_t proxy = nullptr;
     cudaEvent_t proxy_in = nullptr, proxy_out = nullptr;
-    int num_lanes = 2;
+    // lanes a batch of views is spread over; measured on 16 renders of 200k triangles at 512^2 (graph replay): 1.22 ms with
+    // 2 lanes, 0.98 with 3, 0.83 with 4, 0.77 with 6, 0.73 with 8
+    int num_lanes = 8;
     Lane lanes[MAX_LANES];
     std::vector<ViewSlot *> slots;
     // optional per-phase event timing (bench / profiling)
