@@ -1316,6 +1316,7 @@ int deodr_b200_workspace_create(DeodrWorkspace **out, int device) {
     // opt-in (DEODR_B200_GRAPHS=1): measured neutral at N = 1 (two replays + the verdict read between them against the
     // gaps of a dozen launches) and the default-stream hop it needs serialises with a communication stream at N > 1
     ws->graphs = getenv("DEODR_B200_GRAPHS") && atoi(getenv("DEODR_B200_GRAPHS")) != 0;
+    ws->small_by_record = getenv("DEODR_B200_SMALL_ADJOINT") && !strcmp(getenv("DEODR_B200_SMALL_ADJOINT"), "record");
     if (const char *e = getenv("DEODR_B200_LANES")) ws->num_lanes = atoi(e) < 1 ? 1 : (atoi(e) > MAX_LANES ? MAX_LANES : atoi(e));
     int prio_low = 0, prio_high = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));

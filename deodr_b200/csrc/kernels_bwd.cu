@@ -4,6 +4,9 @@
 //   k_small_tri_bwd                              triangle-parallel adjoint of the small triangles
 // Everything strides over device-side counts left by the forward pass of the same view slot (kernels.cu); a forward
 // that overflowed its plan makes these kernels return at once (nothing is accumulated).
+#include <cstdlib>
+#include <cstring>
+
 #include "kernels_common.cuh"
 
 // antialiase_error adjoint, pixels outside every edge band: image_b = -2 (obs - image) err_b (DR.h:3054-3060), consumed
@@ -195,6 +198,69 @@ __global__ void __launch_bounds__(128, DEODR_SMALL_MIN_CTAS) k_small_tri_bwd(Sce
                                          grads.colors_b, grads.uv_b, grads.shade_b, grads.texture_b);
 }
 
+// Record-parallel interior adjoint of the small triangles (small_record_adjoint, phases.h; opt-in, see launch_bwd for the
+// measurements that keep the triangle-parallel form the default): one CTA per tile without
+// silhouette edges, one thread per pre-masked record of the tile's list (written by the binning pass for the z pass:
+// consecutive threads read consecutive 64-byte records).  The tile's owner codes and colour adjoints arrive in shared
+// memory as two TMA tile loads (UTMALDG.2D; cooperative loads when the buffers do not qualify): a record tests its 3-4
+// covered pixels there instead of reading the 33 pixels of its triangle's bounding box from the owner map.
+struct SharedTileFetch {
+    const int *own;
+    const float *img;
+    int C;
+    __device__ __forceinline__ int owner(int px) const { return own[px]; }
+    __device__ __forceinline__ float g(int px, int q) const { return img[px * C + q]; }
+};
+
+template <int MAXC, bool TEX>
+__global__ void __launch_bounds__(128, DEODR_SMALL_MIN_CTAS) k_small_rec_bwd(SceneView s, TileDiv tiles_x, TileSegments seg, const PreRec *recs,
+                                                       const int *scal, const int *edge_cursor, TieTable ties,
+                                                       const int *owner, const float *image_b, DeodrGrads grads,
+                                                       const __grid_constant__ FrameMaps maps) {
+    if (scal[SC_OVERFLOW]) return;
+    fix_channel_count<MAXC, TEX>(s);
+    s.perspective_correct = 0;  // the adjoint is only defined without it (validate_view rejects it): folds the branches
+    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const int n = segment_size(seg, tile_id);
+    if (n == 0) return;
+    if (edge_cursor && edge_cursor[tile_id] > 0) return;  // every pixel of that tile belongs to k_raster_bwd
+    const Tile tile = tile_of(tile_id, tiles_x);
+    const PreRec *list = recs + seg.offset[tile_id];
+    if constexpr (MAXC <= 4) {
+        __shared__ alignas(128) float t_img[NT * MAXC];
+        __shared__ alignas(128) int t_own[NT];
+        __shared__ alignas(8) uint64_t bar;
+        if (maps.ok) {
+            if (tid == 0) mbar_init(&bar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&bar, (uint32_t)(NT * (s.nb_colors * sizeof(float) + sizeof(int))));
+                tma_load_tile(t_img, &maps.image, tile.x0 * s.nb_colors, tile.y0, &bar);
+                tma_load_tile(t_own, &maps.owner, tile.x0, tile.y0, &bar);  // (outside the image: zeros, no record's code)
+            }
+            mbar_wait(&bar, 0);
+        } else {
+            for (int px = tid; px < NT; px += blockDim.x) {
+                const int x = tile.x0 + (px & (TS - 1)), y = tile.y0 + (px >> 4);
+                const bool inside = x < s.width && y < s.height;
+                const size_t idx = inside ? (size_t)y * s.width + x : 0;
+                t_own[px] = inside ? owner[idx] : -1;
+                for (int q = 0; q < s.nb_colors; q++) t_img[px * s.nb_colors + q] = inside ? image_b[idx * s.nb_colors + q] : 0.0f;
+            }
+            __syncthreads();
+        }
+        const SharedTileFetch fetch{t_own, t_img, s.nb_colors};
+        for (int i = tid; i < n; i += blockDim.x)
+            small_record_adjoint<MAXC, DevEnv>(s, list[i], tile, fetch, ties.pairs, grads.ij_b, grads.colors_b, grads.uv_b,
+                                               grads.shade_b, grads.texture_b);
+    } else {
+        const GlobalTileFetch fetch{owner, image_b, tile, s.width, s.height, s.nb_colors};
+        for (int i = tid; i < n; i += blockDim.x)
+            small_record_adjoint<MAXC, DevEnv>(s, list[i], tile, fetch, ties.pairs, grads.ij_b, grads.colors_b, grads.uv_b,
+                                               grads.shade_b, grads.texture_b);
+    }
+}
+
 __global__ void k_finalize_edges(SceneView s, EdgeList edges, const int *scal, double sigma, const double *edge_acc,
                                  DeodrGrads grads) {
     if (scal[SC_OVERFLOW]) return;
@@ -228,6 +294,14 @@ static void launch_bwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneV
         image_b = v->error_image_b.as<float>();
         ws->launches++;
     }
+    // tensor maps of the tile-shaped reads of the adjoint (image_b / owner / z-buffer blocks): k_raster_bwd, k_small_rec_bwd
+    FrameMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    static const bool tma_allowed = !(getenv("DEODR_B200_TMA_TILES") && atoi(getenv("DEODR_B200_TMA_TILES")) == 0);
+    maps.ok = tma_allowed && C <= 4 &&
+              encode_tile_map(&maps.image, image_b, 4, true, s.height, s.width * C, TS, TS * C) &&
+              encode_tile_map(&maps.owner, io.owner, 4, false, s.height, s.width, TS, TS) &&
+              encode_tile_map(&maps.z, io.z_buffer, 8, false, s.height, s.width, TS, TS);
     if (edges) {
         cudaStream_t se = fork_stream(ws, lane, 1, &first);
         cudaMemsetAsync(v->edge_acc.ptr, 0, (size_t)plan.cap_edges * edge_acc_stride(C) * sizeof(double), se);
@@ -235,13 +309,6 @@ static void launch_bwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneV
         const int grid = at_least_one(v->hints_exact && !ws->capturing_internally ? plan.hint_edge_tiles : plan.cap_edge_tiles);
         {
             PhaseTimer timer(ws, DEODR_B200_PH_EDGE_BWD, se);
-        FrameMaps maps;
-        memset(&maps, 0, sizeof(maps));
-        static const bool tma_allowed = !(getenv("DEODR_B200_TMA_TILES") && atoi(getenv("DEODR_B200_TMA_TILES")) == 0);
-        maps.ok = tma_allowed && C <= 4 &&
-                  encode_tile_map(&maps.image, image_b, 4, true, s.height, s.width * C, TS, TS * C) &&
-                  encode_tile_map(&maps.owner, io.owner, 4, false, s.height, s.width, TS, TS) &&
-                  encode_tile_map(&maps.z, io.z_buffer, 8, false, s.height, s.width, TS, TS);
 #define DEODR_RASTER_BWD(X, R) k_raster_bwd<MAXC, X, R><<<grid, EDGE_NT, 0, se>>>(s, sigma, div, et, v->edge_spans.as<uint32_t>(), ties, io.z_buffer, io.owner, image_b, io.obs, io.err_buffer_b, compat, g, v->edge_acc.as<double>(), maps)
             if (tex) { if (err_mode) DEODR_RASTER_BWD(true, true); else DEODR_RASTER_BWD(true, false); }
             else     { if (err_mode) DEODR_RASTER_BWD(false, true); else DEODR_RASTER_BWD(false, false); }
@@ -266,9 +333,20 @@ static void launch_bwd(DeodrWorkspace *ws, ViewSlot *v, Lane &lane, const SceneV
     }
     {
         PhaseTimer timer(ws, DEODR_B200_PH_SMALL_BWD, st);
-        const int entries = v->hints_exact && !ws->capturing_internally ? plan.hint_small : s.nb_triangles;
-        (tex ? k_small_tri_bwd<MAXC, true> : k_small_tri_bwd<MAXC, false>)<<<at_least_one(grid_for(entries, 128)), 128, 0, st>>>(
-            s, v->tiles_x, v->small_ids.as<int>(), v->scal, edge_cursor, ties, io.owner, image_b, g);
+        // Triangle-parallel (default) or record-parallel (DEODR_B200_SMALL_ADJOINT=record) adjoint of the small triangles.
+        // Measured, same session: 1M-triangle scene 0.324 ms per step (triangle) vs 0.331 (record: as long itself - the
+        // vertex gathers and the fifteen atomics per thread are what it costs, not the bounding-box reads, and 1.7x
+        // more threads pay them - and k_interior_bwd beside it slows from 61 to 73 us); 16 renders of 200k triangles at
+        // 512^2: 0.723 vs 0.695 ms; 1M textured triangles: 0.621 vs 0.632 ms.
+        if (!ws->small_by_record) {  // (read from the environment when the workspace is created)
+            const int entries = v->hints_exact && !ws->capturing_internally ? plan.hint_small : s.nb_triangles;
+            (tex ? k_small_tri_bwd<MAXC, true> : k_small_tri_bwd<MAXC, false>)<<<at_least_one(grid_for(entries, 128)), 128, 0, st>>>(
+                s, v->tiles_x, v->small_ids.as<int>(), v->scal, edge_cursor, ties, io.owner, image_b, g);
+        } else {
+            const TileSegments seg{v->small_offset.as<int>(), v->small_cursor};
+            (tex ? k_small_rec_bwd<MAXC, true> : k_small_rec_bwd<MAXC, false>)<<<v->num_tiles, 128, 0, st>>>(
+                s, div, seg, v->small_recs.as<PreRec>(), v->scal, edge_cursor, ties, io.owner, image_b, g, maps);
+        }
         ws->launches++;
     }
     if (edges) join_stream(ws, lane, 1);

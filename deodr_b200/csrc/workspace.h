@@ -149,6 +149,7 @@ struct DeodrWorkspace {
     // lanes a batch of views is spread over; measured on 16 renders of 200k triangles at 512^2 (graph replay): 1.22 ms with
     // 2 lanes, 0.98 with 3, 0.83 with 4, 0.77 with 6, 0.73 with 8
     int num_lanes = 8;
+    bool small_by_record = false;  // DEODR_B200_SMALL_ADJOINT=record at creation: k_small_rec_bwd instead of k_small_tri_bwd
     Lane lanes[MAX_LANES];
     std::vector<ViewSlot *> slots;
     // optional per-phase event timing (bench / profiling)

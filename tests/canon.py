@@ -92,6 +92,10 @@ class Emulator:
         """May textured triangles take the triangle-parallel adjoint (TriBins::small_textured)?"""
         self.lib.emul_set_small_textured(int(bool(on)))
 
+    def set_small_records(self, on):
+        """Adjoint of the small triangles: triangle-parallel (the device's default) or record-parallel (k_small_rec_bwd)."""
+        self.lib.emul_set_small_records(int(bool(on)))
+
     def build_plan(self, scene, sigma):
         """Segment capacities from `scene` (count-only pass + scans), kept for the render_planned calls that follow."""
         a = canonical_arrays(scene)

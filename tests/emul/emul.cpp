@@ -46,6 +46,7 @@ struct EmulState {
 };
 
 static EmulState g_state;
+static int g_small_records = 0;   // the small triangles' adjoint: 0 = triangle-parallel (device default), 1 = record-parallel (k_small_rec_bwd)
 static int g_small_textured = 1;  // 0: textured triangles go through the pixel-parallel adjoint (TriBins::small_textured)
 static int g_record_rows = RECORD_ROWS;  // the device picks 0 for scenes of a few thousand triangles: both are emulated
 
@@ -252,8 +253,20 @@ static void raster_bwd(const SceneView &s, double sigma, EmulState &st, const do
         }
     }
     delete sh;
-    // k_small_tri_bwd
     const int *edge_count = st.E > 0 ? st.edge_cursor.data() : nullptr;
+    if (g_small_records) {  // k_small_rec_bwd: one thread per record of the tiles without silhouette edges
+        for (int tile_id = 0; tile_id < st.nt; tile_id++) {
+            if (edge_count && edge_count[tile_id] > 0) continue;
+            const Tile tile = tile_of(tile_id, st.tiles_x);
+            const GlobalTileFetch fetch{owner, image_b, tile, s.width, s.height, s.nb_colors};
+            const int n = segment_size(st.small_seg(), tile_id);
+            for (int i = 0; i < n; i++)
+                small_record_adjoint<MAXC, HostEnv>(s, st.small_recs[st.small_offset[tile_id] + i], tile, fetch,
+                                                    st.tie_pairs.data(), g.ij_b, g.colors_b, g.uv_b, g.shade_b, g.texture_b);
+        }
+        return;
+    }
+    // k_small_tri_bwd
     for (int k : st.small_ids)
         small_triangle_adjoint<MAXC, HostEnv>(s, k, st.tiles_x, edge_count, owner, st.tie_pairs.data(), image_b, g.ij_b,
                                               g.colors_b, g.uv_b, g.shade_b, g.texture_b);
@@ -490,6 +503,7 @@ void emul_weight_scale(const DeodrSceneView *scene, const int32_t *face_id, cons
 
 void emul_set_record_rows(int rows) { g_record_rows = rows; }
 void emul_set_small_textured(int on) { g_small_textured = on; }
+void emul_set_small_records(int on) { g_small_records = on; }
 int emul_num_ties(void) { return (int)g_state.tie_pairs.size() / 2; }
 int emul_num_edges(void) { return g_state.E; }
 int emul_tri_refs(void) {

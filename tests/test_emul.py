@@ -98,6 +98,23 @@ def test_emulated_kernels_mesh(emulator, checker):
     check(emulator, checker, torus_scene(16, 70, 50, nb_colors=1), 1.0)
 
 
+def test_record_parallel_form_of_the_small_adjoint(emulator, checker, texture):
+    """k_small_rec_bwd (DEODR_B200_SMALL_ADJOINT=record): one thread per pre-masked record of a tile instead of one per
+    small triangle; same gradients."""
+    emulator.set_small_records(True)
+    try:
+        check(emulator, checker, confetti_scene(3000, 64, 48, size=2.5, seed=1), 1.0)
+        check(emulator, checker, torus_scene(24, 160, 120), 1.0)
+        check(emulator, checker, torus_scene(30, 100, 90, textured=True, texture_size=32), 1.0)
+        np.random.seed(2)
+        check(emulator, checker, soup_scene(texture=texture), 1.0)
+        scene = confetti_scene(1200, 48, 40, size=2.0, seed=5, edge_ratio=0.1)
+        scene.strict_edge, scene.integer_pixel_centers = False, False
+        check(emulator, checker, scene, 1.0, image_tol=5e-6)
+    finally:
+        emulator.set_small_records(False)
+
+
 def test_textured_triangles_through_the_pixel_parallel_adjoint(emulator, checker, texture):
     """TriBins::small_textured = 0 (what the device picks below a few hundred thousand triangles): textured triangles
     keep their forward records but are owned without SMALL_FLAG, so their adjoint is the pixel-parallel kernel's."""

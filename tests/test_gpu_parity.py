@@ -316,3 +316,19 @@ def test_face_ids_at_config3_size(gpu, ref_oracle):
     out = run_device(gpu, scene, 0.0)
     assert np.array_equal(out["z_buffer"], z)
     assert np.array_equal(out["face_id"], np.rint(channel[:, :, 0]).astype(np.int32))
+
+
+def test_record_parallel_small_adjoint(checker, texture, monkeypatch):
+    """DEODR_B200_SMALL_ADJOINT=record (read when a workspace is created): k_small_rec_bwd - one thread per pre-masked
+    record, the tile's owner / image_b blocks staged by TMA tile loads - gives the gradients of the default
+    triangle-parallel kernel."""
+    from deodr_b200.renderer import Renderer
+
+    monkeypatch.setenv("DEODR_B200_SMALL_ADJOINT", "record")
+    gpu = Renderer(0)
+    monkeypatch.delenv("DEODR_B200_SMALL_ADJOINT")
+    check(gpu, checker, confetti_scene(3000, 64, 48, size=2.5, seed=1), 1.0)
+    check(gpu, checker, torus_scene(60, 300, 300, nb_colors=1), 1.0)
+    check(gpu, checker, torus_scene(100, 512, 512), 1.0)           # TMA tile loads (C = 3, W % 4 == 0)
+    check(gpu, checker, torus_scene(24, 150, 130), 1.0)             # cooperative loads (row pitch not 16-byte)
+    check(gpu, checker, torus_scene(400, 512, 512, textured=True), 1.0)  # textured small triangles (T >= 262144)
