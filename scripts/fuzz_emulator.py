@@ -14,7 +14,8 @@ SLIVER (barycentric weights above 64 at some pixel, i.e. a triangle thinner than
 gradient is a sum of fp32 terms hundreds of times larger than the result (observed: up to 1e-3 relative).
 Round 1: over 2 million scenes over twenty seeds (1-7 colour channels, background colour / image, triangles from 0.3 to
 25 pixels, crowded soups, all flag combinations, one scene in five in antialiase_error mode): no z-buffer mismatch, no
-deviation outside these tolerances.
+deviation outside these tolerances.  Round 2 adds, per scene, a random choice of who takes the adjoint of the small
+triangles (TriBins::small_textured on / off, triangle-parallel / record-parallel kernel).
 """
 import os
 import sys
@@ -74,6 +75,9 @@ while time.time() - t0 < limit and (only == 0 or n < only):
     scene.backface_culling = bool(rng.random() < 0.8)
     scene.perspective_correct = bool(rng.random() < 0.25)
     sigma = float(rng.choice([0.0, 0.5, 1.0, 2.5]))
+    # round 2: who takes the adjoint of a small triangle (both device paths: textured ones triangle- or pixel-parallel;
+    # the triangle-parallel kernel or the record-parallel one)
+    small_textured, small_records = bool(rng.integers(0, 2)), bool(rng.random() < 0.3)
     n += 1
     error_mode = rng.random() < 0.2 and not scene.perspective_correct and scene.backface_culling
     if error_mode:
@@ -81,6 +85,8 @@ while time.time() - t0 < limit and (only == 0 or n < only):
         err_b = rng.random((scene.height, scene.width)) * 2 - 1
     if only and n != only:
         continue
+    emu.set_small_textured(small_textured)
+    emu.set_small_records(small_records)
     if only:
         print("replaying scene", n, "kind", kind, (W, H), "T", scene.faces.shape[0], "sigma", sigma, "error mode", error_mode,
               "degenerate", degenerate, flush=True)

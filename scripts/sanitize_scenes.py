@@ -4,7 +4,8 @@
     compute-sanitizer --tool racecheck  python scripts/sanitize_scenes.py
     compute-sanitizer --tool synccheck  python scripts/sanitize_scenes.py
 
-Covers: forward + adjoint (interpolated, textured, 1 / 3 channels, perspective), a batch of views on two lanes, the
+Covers: forward + adjoint (interpolated, textured, 1 / 3 channels, perspective), a batch of views on several lanes, the
+forward in two calls, the record-parallel adjoint, the
 antialiase_error mode, the G-buffer outputs, a re-plan (lists outgrowing the plan), image widths that do and do not qualify
 for the TMA tile store / loads, and the f1 / f2 scene ops."""
 import os
@@ -44,6 +45,22 @@ grads = [dict(shared, ij_b=torch.zeros_like(shared["ij_b"])) for _ in views]
 r.render_b_views(views, 1.0, outs, [torch.ones_like(o["image"]) for o in outs], grads)
 torch.cuda.synchronize()
 print("ok views", float(shared["colors_b"].abs().sum()))
+# the forward in two calls (binning | rest), then the adjoint
+half = r.render_views(views, 1.0, part="geometry")
+half = r.render_views(views, 1.0, out=half, part="resume")
+r.render_b_views(views, 1.0, half, [torch.ones_like(o["image"]) for o in half])
+torch.cuda.synchronize()
+print("ok two-call forward")
+# record-parallel adjoint of the small triangles (read from the environment when a workspace is created)
+os.environ["DEODR_B200_SMALL_ADJOINT"] = "record"
+r2 = Renderer(0)
+del os.environ["DEODR_B200_SMALL_ADJOINT"]
+for sc in (confetti_scene(3000, 64, 48, size=2.5, seed=1), torus_scene(24, 150, 130, nb_colors=3), torus_scene(60, 300, 300, nb_colors=1)):
+    ds = DeviceScene(sc, "cuda:0")
+    fwd = r2.render(ds, 1.0)
+    r2.render_b(ds, 1.0, fwd, torch.ones_like(fwd["image"]))
+torch.cuda.synchronize()
+print("ok record-parallel adjoint")
 # antialiase_error mode
 sc = torus_scene(24, 160, 120)
 ds = DeviceScene(sc, "cuda:0")
