@@ -31,6 +31,20 @@ def test_struct_layouts_match_header(build_native):
     assert C.sizeof(_cabi.MeshTopology) == 6 * 8 + 16
 
 
+def test_flag_values_match_header():
+    """The Python constants of the *_views flags and the error codes are the header's enum values."""
+    header = open(os.path.join(ROOT, "include", "deodr_b200.h")).read()
+    values = {name: int(v) for name, v in re.findall(r"\b(DEODR_B200_[A-Z_]+)\s*=\s*(-?\d+)", header)}
+    assert values["DEODR_B200_ANTIALIASE_ERROR"] == _cabi.ANTIALIASE_ERROR
+    assert values["DEODR_B200_ERROR_ADJOINT_COMPLETE"] == _cabi.ERROR_ADJOINT_COMPLETE
+    assert values["DEODR_B200_FORWARD_GEOMETRY"] == _cabi.FORWARD_GEOMETRY
+    assert values["DEODR_B200_FORWARD_RESUME"] == _cabi.FORWARD_RESUME
+    flags = [values[k] for k in ("DEODR_B200_ANTIALIASE_ERROR", "DEODR_B200_ERROR_ADJOINT_COMPLETE",
+                                 "DEODR_B200_FORWARD_GEOMETRY", "DEODR_B200_FORWARD_RESUME")]
+    assert all(f & (f - 1) == 0 for f in flags) and len(set(flags)) == 4  # distinct single bits
+    assert values["DEODR_B200_ECUDA"] == _cabi.ECUDA and values["DEODR_B200_EINVAL"] == _cabi.EINVAL
+
+
 def test_no_cpu_fallback_without_gpu(build_native):
     import torch
 
