@@ -5,17 +5,21 @@
 //   k_bin            1 thread / triangle         ONE gather per triangle: classify (DR.h:2751-2779), append silhouette
 //                                                edges, pre-masked 64-byte records of the small triangles / tile
 //                                                references of the large ones, into segments reserved by the PLAN
-//   k_bin_edges      1 thread / edge      (aux)  band stencil record (DR.h:1366-1460), slot -> tiles of the band
+//   k_bin_edges      1 warp / edge        (aux)  band stencil record (DR.h:1366-1460), slot -> tiles of the band
 //   k_sort_tile_edges 1 CTA / tile        (aux)  far-to-near order (DR.h:2781) inside every tile, list of edge tiles
 //   k_publish                             (aux)  verdict word + counts -> pinned host memory (read by the host AFTER
 //                                                the whole pass has been enqueued)
-//   k_tile_z         1 CTA / 16x16 tile          TMA bulk copy of the tile's records, exact z test, owner ids
-//   k_shade          1 thread / pixel            colour of the owner (+ residual / G-buffer weights)
+//   k_tile_z         1 CTA / 16x16 tile          TMA bulk copies of the tile's records (two-deep pipeline), exact z test,
+//                                                owner ids, colour of the owner (+ residual / G-buffer weights), TMA
+//                                                tile store of the colours
+//   k_shade          1 thread / pixel            the colour pass on its own, when the colours arrive after the z pass
 //   k_edge_fwd       1 CTA / edge tile           ordered silhouette-edge overdraw (DR.h:2839-2899)
 // and one adjoint pass:
 //   k_raster_bwd + k_finalize_edges       (aux)  edge tiles: replay, reverse sweep, per-edge plane adjoints
 //   k_interior_bwd                        (aux)  pixels of large triangles elsewhere
-//   k_small_tri_bwd                              triangle-parallel adjoint of the small triangles
+//   k_small_tri_bwd                              triangle-parallel adjoint of the small triangles (k_small_rec_bwd: its
+//                                                record-parallel form, opt-in)
+// A forward can also be enqueued in two calls (binning | everything else: DEODR_B200_FORWARD_GEOMETRY / _RESUME).
 // The plan (segment capacities) comes from a count-only pass (k_bin<true> + k_scan_tiles) run once per shape and
 // again whenever a pass reports that a list outgrew it.
 //
