@@ -172,3 +172,65 @@ def test_out_of_range_indices_surface_as_assertion_error_only_with_check_valid(s
         shim.renderSceneCpp(scene, 1.0, image, z, check_valid=1)
     with pytest.raises(_cabi.DeodrB200Error):        # the C core's own throw (DR.h:2703-2714), surfaced as an error
         shim.renderSceneCpp(scene, 1.0, image, z, check_valid=0)
+
+
+# ---- Scene2D / renderScene / renderSceneB (deodr/differentiable_renderer.py:48-249, 599-734): error behaviour ---------
+
+
+def test_scene2d_refuses_gradients_the_core_cannot_give(scene, no_native):
+    """BaseException, like the reference (differentiable_renderer.py:630-637, 666-672), and before any rendering."""
+    obs = np.zeros((scene.height, scene.width, scene.nb_colors))
+    scene.perspective_correct = True
+    with pytest.raises(BaseException, match="perspective_correct"):
+        scene.render_compare_and_backward(obs)
+    scene.store_backward = (1.0, obs.copy(), np.zeros((scene.height, scene.width)))
+    with pytest.raises(BaseException, match="perspective_correct"):
+        scene.render_backward(obs)
+    scene.perspective_correct, scene.backface_culling = False, False
+    with pytest.raises(BaseException, match="backface_culling"):
+        scene.render_backward(obs)
+    scene.store_backward = (1.0, obs, obs.copy(), np.zeros((scene.height, scene.width)), np.zeros((scene.height, scene.width)))
+    with pytest.raises(BaseException, match="backface_culling"):
+        scene.render_error_backward(np.ones((scene.height, scene.width)))
+
+
+def test_render_scene_checks_of_the_python_layer(scene, buffers, no_native):
+    from deodr_b200.differentiable_renderer import renderScene, renderSceneB
+
+    image, z = buffers
+    with pytest.raises(AssertionError):
+        renderScene(scene, 1.0, None, z)
+    with pytest.raises(AssertionError):
+        renderScene(scene, 1.0, image, None)
+    with pytest.raises(AssertionError, match="err_buffer"):  # differentiable_renderer.py:115-118
+        renderScene(scene, 1.0, image, z, antialiase_error=True, obs=image.copy())
+    with pytest.raises(AssertionError, match="obs"):
+        renderScene(scene, 1.0, image, z, antialiase_error=True, err_buffer=z.copy())
+    with pytest.raises(AssertionError):  # image_b is required without antialiase_error
+        renderSceneB(scene, 1.0, image, z)
+    with pytest.raises(AssertionError):  # ... and obs / err_buffer / err_buffer_b with it
+        renderSceneB(scene, 1.0, image, z, antialiase_error=True, obs=image.copy(), err_buffer=z.copy())
+    scene.colors_b = None
+    with pytest.raises(AssertionError, match="colors_b"):
+        renderSceneB(scene, 1.0, image, z, image_b=image.copy())
+    scene.colors_b = np.zeros(scene.colors.shape)
+    scene.faces = scene.faces.astype(np.int32)  # `assert scene.faces.dtype == np.uint32` (:75)
+    with pytest.raises(AssertionError):
+        renderScene(scene, 1.0, image, z)
+    scene.faces = scene.faces.astype(np.uint32)
+    scene.background_image = np.zeros((scene.height, scene.width, scene.nb_colors))  # both backgrounds: refused
+    with pytest.raises(AssertionError, match="background"):
+        renderScene(scene, 1.0, image, z)
+    scene.background_image = scene.background_color = None                            # ... and neither
+    with pytest.raises(AssertionError, match="background"):
+        renderScene(scene, 1.0, image, z)
+
+
+def test_clear_gradients_zeroes_in_place(scene):
+    views = {}
+    for name in ("uv_b", "ij_b", "shade_b", "colors_b", "texture_b"):
+        getattr(scene, name)[...] = 1.5
+        views[name] = getattr(scene, name)
+    scene.clear_gradients()  # (small arrays: numpy fill; the copy-crew path needs the library's workspace, i.e. a GPU)
+    for name, view in views.items():
+        assert getattr(scene, name) is view and not view.any()
