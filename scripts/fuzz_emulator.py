@@ -36,11 +36,14 @@ emu, ora = Emulator(), Oracle("reference", texfix=True)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 limit = float(sys.argv[2]) if len(sys.argv) > 2 else 300.0
 only = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # replay: generate every scene (same random stream), render one
+# DEODR_FUZZ_SCALE=3: canvases up to 270 x 270 (17 x 17 tiles: more tiles per triangle, longer per-tile lists, more
+# triangles and edges per scene); the default keeps the scenes of the earlier campaigns (same random streams)
+SCALE = float(os.environ.get("DEODR_FUZZ_SCALE", "1"))
 t0, n, bad, special = time.time(), 0, 0, 0
 worst = {"image": 0.0, "grad": 0.0}
 while time.time() - t0 < limit and (only == 0 or n < only):
     kind = int(rng.integers(0, 4))
-    W, H = int(rng.integers(5, 90)), int(rng.integers(5, 90))
+    W, H = int(rng.integers(5, int(90 * SCALE))), int(rng.integers(5, int(90 * SCALE)))
     degenerate = False
     if kind == 0:
         np.random.seed(int(rng.integers(0, 1 << 30)))
@@ -51,14 +54,14 @@ while time.time() - t0 < limit and (only == 0 or n < only):
                            textured_ratio=float(rng.random()), texture=tex[::4, ::4].copy(),
                            min_det=float(rng.choice([0.005, 0.02, 0.05])) * W * H)
     elif kind == 1:
-        scene = confetti_scene(int(rng.integers(1, 1500)), W, H, size=float(rng.choice([0.3, 1.0, 2.5, 6.0, 25.0])),
+        scene = confetti_scene(int(rng.integers(1, int(1500 * SCALE * SCALE))), W, H, size=float(rng.choice([0.3, 1.0, 2.5, 6.0, 25.0])),
                                seed=int(rng.integers(0, 1 << 30)), edge_ratio=float(rng.choice([0, 0.05, 0.5, 1.0])),
                                nb_colors=int(rng.choice([1, 2, 3, 4, 7])))
         if rng.random() < 0.3:  # a background image instead of a colour
             scene.background_image = rng.random((H, W, scene.nb_colors))
             scene.background_color = None
     elif kind == 2:
-        scene = torus_scene(int(rng.integers(4, 30)), max(W, 16), max(H, 16), textured=bool(rng.integers(0, 2)),
+        scene = torus_scene(int(rng.integers(4, int(30 * SCALE))), max(W, 16), max(H, 16), textured=bool(rng.integers(0, 2)),
                             nb_colors=3, texture_size=16)
         if rng.random() < 0.7:
             scene.uv = scene.uv * 0.9973 + 0.0131  # off the texel grid (generic position)
