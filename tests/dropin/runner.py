@@ -10,6 +10,9 @@
 INTEGRATION.md describes; nothing else of the staged package (baseline/_ref/deodr: a verbatim, git-ignored copy of
 /root/reference/deodr made by scripts/stage_reference.py) is touched.  <impl> = ref: no swap; needs the reference's own
 Cython extension next to the package (only used in the build container to validate this runner).
+<impl> = ref_noise (build container only, scripts/dropin_sensitivity.py): the reference's own extension with every image
+and gradient it returns multiplied element-wise by 1 + DEODR_NOISE_EPS * N(0, 1) (seed DEODR_NOISE_SEED) - a stand-in
+for fp32 rounding, used to MEASURE how far a perturbation of that size drives the example fits apart.
 Results of the example modes are printed as one JSON line prefixed with RESULT.
 """
 import json
@@ -39,6 +42,27 @@ def main():
         from deodr import differentiable_renderer_cython as bound
 
         assert bound.__name__ == "deodr_b200.differentiable_renderer_cython", bound.__name__
+    if impl == "ref_noise":
+        import numpy as np
+        from deodr import differentiable_renderer_cython as ffi
+
+        rng = np.random.default_rng(int(os.environ.get("DEODR_NOISE_SEED", "0")))
+        eps = float(os.environ.get("DEODR_NOISE_EPS", "1e-7"))
+        fwd, bwd = ffi.renderSceneCpp, ffi.renderSceneBCpp
+
+        def noisy(a):
+            a *= 1.0 + eps * rng.standard_normal(a.shape)
+
+        def render(scene, sigma, image, z_buffer, *a, **k):
+            fwd(scene, sigma, image, z_buffer, *a, **k)
+            noisy(image)
+
+        def render_b(scene, *a, **k):
+            bwd(scene, *a, **k)
+            for name in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b"):
+                noisy(getattr(scene, name))
+
+        ffi.renderSceneCpp, ffi.renderSceneBCpp = render, render_b
     if mode == "pytest":
         import pytest
 

@@ -9,9 +9,14 @@ INTEGRATION.md - and then runs the reference's OWN, unmodified test files and ex
 * fitting loops (losses the reference pins with `==` / 1e-5 on a float64 CPU path): the unmodified example code runs
   on the sm_100a path and its loss / energy trajectory is compared with the one the reference's own extension produced
   in the build container (tests/golden/dropin_reference.json, made by tests/golden/make_dropin_golden.py).
-  Stated tolerances: first 4 iterations within 2e-5 relative (fp32 colours and gradients against fp64); the soup fits
-  stay within 2e-3 over the whole 50-iteration trajectory; the hand fits (a momentum descent whose final energy
-  already differs by 4e-5 between the fp64 platforms the reference's own test lists) within 3e-2.
+  Stated tolerances: the soup fits stay within 2e-3 over the whole 50-iteration trajectory and within 2e-5 over the
+  first 4 iterations (measured on the B200: 1e-8 throughout).  The hand fits are chaotic 50-step momentum descents:
+  the REFERENCE ITSELF, with every image / gradient it returns perturbed by a relative 1e-7 (fp32-sized;
+  scripts/dropin_sensitivity.py, 16 seeds per fit), leaves its own trajectory by up to 3.5e-2 (median 2.5e-2 for the
+  depth fits, 1.5e-2 for the RGB fit), its final energy by up to 3.5e-2, and - when a pixel of the depth image changes
+  owner - the first four iterations by up to 3e-5.  Hence: first 4 iterations within 1e-4 (measured on the B200: 9e-9),
+  whole trajectory and final energy within 1e-1 = 3 x the largest excursion of the perturbed reference (measured on the
+  B200: 1.3e-2 / 1.5e-2 / 2.0e-2), and the fit must end as low as the reference's.
 """
 import json
 import os
@@ -86,12 +91,13 @@ def test_reference_depth_hand_fitting_example(library, staged, golden):
     ref = np.array(golden["hand_depth"][library]["energies"])
     got = np.array(_result(_run("hand_depth", library, 50), f"hand_depth_{library}")["energies"])
     rel = np.abs(got - ref) / ref
-    assert rel[:4].max() <= 2e-5, rel[:4]
+    assert rel[:4].max() <= 1e-4, rel[:4]
     # The fit is a 50-step momentum descent over a piecewise-smooth energy: the reference's own test lists final
-    # energies that differ by 4e-5 between fp64 platforms (251.3271 / 251.3165); an fp32-rounded gradient (1e-7
-    # relative perturbation at step 0) grows the same way.  The trajectory must stay a descent of the same quality.
-    assert rel.max() <= 3e-2, (rel.argmax(), rel.max())
-    assert abs(got[49] - 251.327) / 251.327 <= 3e-2  # the value the reference's test pins (1e-5 on its own path)
+    # energies that differ by 4e-5 between fp64 platforms (251.3271 / 251.3165), and a 1e-7 perturbation of the
+    # reference's own gradients moves its trajectory by up to 3.5e-2 (module docstring).  The trajectory must stay a
+    # descent of the same quality.
+    assert rel.max() <= 1e-1, (rel.argmax(), rel.max())
+    assert abs(got[49] - 251.327) / 251.327 <= 1e-1  # the value the reference's test pins (1e-5 on its own path)
     assert got[49] < 0.15 * got[0]
 
 
@@ -99,5 +105,6 @@ def test_reference_rgb_hand_fitting_example(staged, golden):
     ref = np.array(golden["hand_rgb"]["none"]["energies"])
     got = np.array(_result(_run("hand_rgb", "none", 50), "hand_rgb_none")["energies"])
     rel = np.abs(got - ref) / ref
-    assert rel[:4].max() <= 2e-5, rel[:4]
-    assert rel.max() <= 3e-2, (rel.argmax(), rel.max())
+    assert rel[:4].max() <= 1e-4, rel[:4]
+    assert rel.max() <= 1e-1, (rel.argmax(), rel.max())
+    assert got[49] < 0.6 * got[0]  # the reference's fit ends at 0.54 of its first energy
