@@ -104,7 +104,10 @@ while time.time() - t0 < limit and (only == 0 or n < only):
             degenerate = True
         fwd = emu.render_error(scene, sigma, obs)  # (the emulator keeps the state of its last forward)
         msg = "" if np.array_equal(fwd["z"], z) else " Z-BUFFER-MISMATCH"
-        e_err = np.abs(fwd["err"] - err).max() / max(1.0, float(np.abs(err).max())) if err.size else 0.0
+        # (per pixel relative to the interpolation weights of its owner, like the image criterion below: the residual of
+        # a pixel owned by a visible sliver - weights in the thousands - carries the fp32 error of that interpolation)
+        w_px = np.maximum(1.0, sliver) if sliver.size else 1.0
+        e_err = (np.abs(fwd["err"] - err) / w_px).max() / max(1.0, float(np.abs(err).max())) if err.size else 0.0
         if e_err > 6e-5:
             msg += f" err_buffer {e_err:.2e}"
         ref = ora.render_b(scene, sigma, image, z, None, antialiase_error=True, obs=obs, err_buffer=err, err_buffer_b=err_b)
