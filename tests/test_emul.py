@@ -201,3 +201,13 @@ def test_plan_of_an_earlier_pass_serves_a_drifted_scene(emulator, checker):
     emulator.build_plan(torus_scene(4, 128, 96), 1.0)
     verdict, _ = emulator.render_planned(crowded, 1.0)
     assert verdict != 0
+
+
+@pytest.mark.parametrize("sigma", [1e-3, 0.05, 9.0, 45.0])
+def test_emulated_kernels_extreme_sigma(sigma, emulator, checker, texture):
+    """Edge bands from a thousandth of a pixel to wider than the scene (every tile holds every silhouette edge: many
+    edge chunks per tile, band boxes clipped on all sides): same answers as the reference."""
+    np.random.seed(2)
+    check(emulator, checker, soup_scene(clockwise=False, texture=texture), sigma)
+    check(emulator, checker, torus_scene(24, 160, 120), sigma)
+    check(emulator, checker, confetti_scene(800, 96, 80, size=3.0, seed=3, edge_ratio=0.5), sigma)
