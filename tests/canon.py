@@ -52,9 +52,11 @@ def view_of(scene, arrays, ptr=lambda arr: arr.ctypes.data):
 
 
 class Emulator:
-    def __init__(self):
-        subprocess.run(["make", "-C", os.path.join(_HERE, "emul")], check=True, capture_output=True)
-        self.lib = C.CDLL(os.path.join(_HERE, "emul", "libemul.so"))
+    def __init__(self, exact_short_wrap: bool = False):
+        """exact_short_wrap: the build with DEODR_EXACT_SHORT_WRAP=1 (rmath.h) instead of the default one."""
+        name = "libemul_wrap.so" if exact_short_wrap else "libemul.so"
+        subprocess.run(["make", "-C", os.path.join(_HERE, "emul"), name], check=True, capture_output=True)
+        self.lib = C.CDLL(os.path.join(_HERE, "emul", name))
         self.lib.emul_render.argtypes = [C.POINTER(_cabi.SceneView), C.c_double] + [C.c_void_p] * 4
         self.lib.emul_weight_scale.argtypes = [C.POINTER(_cabi.SceneView), C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib.emul_weight_scale.restype = None

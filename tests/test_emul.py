@@ -211,3 +211,48 @@ def test_emulated_kernels_extreme_sigma(sigma, emulator, checker, texture):
     check(emulator, checker, soup_scene(clockwise=False, texture=texture), sigma)
     check(emulator, checker, torus_scene(24, 160, 120), sigma)
     check(emulator, checker, confetti_scene(800, 96, 80, size=3.0, seed=3, edge_ratio=0.5), sigma)
+
+
+def far_vertex_scene(seed, far):
+    """A confetti scene with 40 of its 600 vertices pushed up to `far` pixels away (scripts/probe_far_vertices.py)."""
+    rng = np.random.default_rng(seed)
+    scene = confetti_scene(200, 64, 48, size=float(rng.choice([5.0, 40.0])), seed=seed, edge_ratio=0.3)
+    idx = rng.choice(scene.ij.shape[0], size=40, replace=False)
+    scene.ij[idx] += rng.choice([-1, 1], size=(40, 2)) * far * rng.random((40, 2))
+    return scene
+
+
+@pytest.mark.parametrize("far", [1e3, 3.2e4])
+def test_vertices_far_outside_the_image_within_the_short_range(far, emulator, checker):
+    """Up to the reference's own limit (loop counters and bounds are `short`: +-32767 px) long triangles that cross the
+    image from far outside are rasterised bit for bit like the reference, gradients included."""
+    for seed in range(6):
+        check(emulator, checker, far_vertex_scene(seed, far), 1.0)
+
+
+@pytest.mark.parametrize("far", [4e4, 7e4, 1e6, 3e9, 1e15])
+def test_exact_short_wrap_build_follows_the_reference_beyond_the_short_range(far, checker):
+    """Beyond +-32767 px the reference's `(short)` casts wrap (x86) and a triangle with one far vertex is still drawn in
+    part.  The build with DEODR_EXACT_SHORT_WRAP=1 (rmath.h; not the default) reproduces
+    that bit for bit: z-buffer identical for every magnitude up to 1e15 px (image within tolerance up to 3e9 px)."""
+    exact = Emulator(exact_short_wrap=True)
+    for seed in range(8):
+        scene = far_vertex_scene(seed, far)
+        image, z = checker.render(scene, 1.0)
+        fwd = exact.render(scene, 1.0)
+        assert np.array_equal(fwd["z"], z), (far, seed)
+        # colours: measured 1.3e-7 up to 3e9 px; beyond, the interpolation of a triangle with a vertex 1e12 px away
+        # is ill-conditioned in any arithmetic (3e-5 at 1e12, 3e-2 at 1e15 between fp32 and fp64 attributes)
+        if far <= 3e9:
+            assert np.abs(fwd["image"] - image).max() <= IMAGE_TOL
+
+
+def test_exact_short_wrap_build_changes_nothing_within_the_short_range(checker, texture):
+    exact = Emulator(exact_short_wrap=True)
+    np.random.seed(2)
+    check(exact, checker, soup_scene(clockwise=False, texture=texture), 1.0)
+    check(exact, checker, torus_scene(24, 160, 120), 1.0)
+    check(exact, checker, torus_scene(30, 100, 90, textured=True, texture_size=32), 2.5)
+    check(exact, checker, confetti_scene(3000, 64, 48, size=2.5, seed=1), 1.0)
+    for seed in range(4):
+        check(exact, checker, far_vertex_scene(seed, 3.2e4), 1.0)
