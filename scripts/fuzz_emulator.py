@@ -32,7 +32,11 @@ from oracle.oracle import Oracle  # noqa: E402
 from deodr_b200.scenes import confetti_scene, dense_image_b, soup_scene, torus_scene  # noqa: E402
 
 tex = np.load(os.path.join(ROOT, "tests/golden/trefle_texture_u8.npy")).astype(np.float64) / 255
-emu, ora = Emulator(), Oracle("reference", texfix=True)
+# DEODR_FUZZ_EXACT_WRAP=1: the emulation built with DEODR_EXACT_SHORT_WRAP=1 (rmath.h), and one scene in three gets a few
+# vertices pushed 4e4 .. 1e9 pixels away (beyond the reference's `short` range: only that build follows the reference there)
+EXACT_WRAP = os.environ.get("DEODR_FUZZ_EXACT_WRAP", "0") == "1"
+emu, ora = Emulator(exact_short_wrap=EXACT_WRAP), Oracle("reference", texfix=True)
+rng_far = np.random.default_rng(12345 + (int(sys.argv[1]) if len(sys.argv) > 1 else 0))
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 limit = float(sys.argv[2]) if len(sys.argv) > 2 else 300.0
 only = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # replay: generate every scene (same random stream), render one
@@ -73,6 +77,13 @@ while time.time() - t0 < limit and (only == 0 or n < only):
         if rng.random() < 0.5:  # vertices snapped to half pixels, far outside the image
             scene.ij = np.round(scene.ij * 2) / 2 + rng.choice([0, -30, 40], size=(1, 2))
             degenerate = True
+    if EXACT_WRAP and rng_far.random() < 0.33:
+        n_far = max(1, scene.ij.shape[0] // 15)
+        idx = rng_far.choice(scene.ij.shape[0], size=n_far, replace=False)
+        far = float(rng_far.choice([4e4, 7e4, 1e6, 1e9]))
+        scene.ij = scene.ij.copy()
+        scene.ij[idx] += rng_far.choice([-1, 1], size=(n_far, 2)) * far * rng_far.random((n_far, 2))
+        degenerate = True  # gradients of triangles thousands of pixels long: fp32 attribute planes (reported apart)
     scene.strict_edge = bool(rng.integers(0, 2))
     scene.integer_pixel_centers = bool(rng.integers(0, 2))
     scene.backface_culling = bool(rng.random() < 0.8)
