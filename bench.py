@@ -416,10 +416,11 @@ def run_ours(args):
         kernel = max(raster, key=raster.get)
         t_k, b_k = raster[kernel], kernel_bytes[kernel]
         achieved = b_k / (t_k * 1e-3) / 1e9
-        traffic, traffic_src = None, None
+        traffic, traffic_src, step_traffic = None, None, None
         try:
             doc = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             traffic = doc.get(args.workload, {}).get(kernel)
+            step_traffic = doc.get(args.workload, {}).get("step")  # every kernel of one forward + adjoint
             traffic_src = doc.get("source")
         except Exception:
             pass
@@ -434,6 +435,8 @@ def run_ours(args):
                           "`plan` only appears when a plan was (re)built",
             "step_algorithmic_bytes": b_fwd + b_bwd,
             "step_frac_of_peak": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+            # DRAM traffic of all kernels of one view's forward + adjoint in the same ncu capture (one view per step only)
+            "step_traffic": step_traffic if len(scenes) == 1 else None,
         }
 
     # ---- end to end through the reference-facing plugin call with HOST (numpy fp64) buffers

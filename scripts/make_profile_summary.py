@@ -60,7 +60,8 @@ for r in rr[2:]:
     out.append(f"| `{name}` | " + " | ".join(vals) + f" | {st} |")
 # per-launch DRAM traffic of every raster kernel -> profiles/ncu_traffic.json (bench.py's roofline.traffic)
 phase_of = {"k_tile_z": "tile_z", "k_shade": "shade", "k_edge_fwd": "edge_fwd", "k_small_tri_bwd": "small_tri_bwd",
-            "k_interior_bwd": "interior_bwd", "k_raster_bwd": "edge_bwd", "k_bin": "bin"}
+            "k_interior_bwd": "interior_bwd", "k_raster_bwd": "edge_bwd", "k_bin": "bin", "k_bin_edges": "edge_bin",
+            "k_sort_tile_edges": "edge_tile_sort", "k_finalize_edges": "edge_finalize"}
 workload = tag.split("_")[1] if "_" in tag else "c5"
 traffic = {}
 for r in rr[2:]:
@@ -74,6 +75,7 @@ try:
     all_traffic = json.load(open("profiles/ncu_traffic.json"))
 except Exception:
     all_traffic = {}
+traffic["step"] = sum(traffic.values())  # every kernel of one forward + adjoint (memsets aside)
 all_traffic[workload] = traffic
 all_traffic["source"] = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture {report.split('/')[-1]} "
                          f"(summary profiles/{tag}.md, scripts/make_profile_summary.py)")
