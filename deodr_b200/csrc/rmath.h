@@ -256,8 +256,9 @@ DEODR_HD void tri_bounds(const double V[3][2], bool strict, int *x_min, int *x_m
     // rows of the two halves (DR.h:686-711), every bound through the reference's `short`: their union is [b0, e1] as
     // long as nothing wrapped; with a vertex beyond +-32767 one half can be empty while the other is not
     double y_mid = fmax(fmin(V[0][1], V[1][1]), fmin(fmax(V[0][1], V[1][1]), V[2][1]));
-    int b0 = strict ? to_short(floor(y_lo)) + 1 : to_short(ceil(y_lo)), e0 = to_short(floor(y_mid));
-    int b1 = strict ? to_short(floor(y_mid)) + 1 : to_short(ceil(y_mid)), e1 = to_short(floor(y_hi));
+    // (32768 = (short)32767 + 1 starts the reference's `short` row counter, DR.h:925, at -32768)
+    int b0 = strict ? wrap16(to_short(floor(y_lo)) + 1) : to_short(ceil(y_lo)), e0 = to_short(floor(y_mid));
+    int b1 = strict ? wrap16(to_short(floor(y_mid)) + 1) : to_short(ceil(y_mid)), e1 = to_short(floor(y_hi));
     int first = 32767, last = -32768;
     if (b0 <= e0) { first = b0; last = e0; }
     if (b1 <= e1) { if (b1 < first) first = b1; if (e1 > last) last = e1; }
@@ -289,9 +290,15 @@ DEODR_HD void tri_geom(const double V[3][2], const double Zv[3], bool strict, bo
     // NB: "(short)floor(y) + 1" is computed in int and then stored in an int: no 16-bit wrap of the +1
     int yb0 = strict ? to_short(floor(ys[0])) + 1 : to_short(ceil(ys[0]));
     int yb1 = strict ? to_short(floor(ys[1])) + 1 : to_short(ceil(ys[1]));
+#if DEODR_EXACT_SHORT_WRAP
+    // 32768 = (short)32767 + 1 starts the reference's `short` row counter (DR.h:925) at -32768: rows from 0
+    g->y_begin[0] = (int16_t)wrap16(yb0);
+    g->y_begin[1] = (int16_t)wrap16(yb1);
+#else
     // the +1 can only leave the int16 range at 32768, far outside any image: saturate for storage
     g->y_begin[0] = (int16_t)(yb0 > 32767 ? 32767 : yb0);
     g->y_begin[1] = (int16_t)(yb1 > 32767 ? 32767 : yb1);
+#endif
     g->y_end[0] = (int16_t)to_short(floor(ys[1]));
     g->y_end[1] = (int16_t)to_short(floor(ys[2]));
     int id = yo[0];
