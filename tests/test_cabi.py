@@ -141,4 +141,4 @@ def test_plain_c_caller_renders_through_the_host_entry_point(build_native, check
     assert out[0] == "render_host 0 ok", out
     covered, total = int(out[1].split()[1]), float(out[1].split()[3])
     assert covered == int(np.isfinite(z).sum()) and covered > 0
-    assert abs(total - float(image.sum())) <= 1e-4
+    assert abs(total - float(image.sum())) <= 192 * 1e-6 + 1e-5  # (IMAGE_TOL per pixel, 6 printed decimals)
