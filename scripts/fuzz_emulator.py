@@ -85,6 +85,14 @@ while time.time() - t0 < limit and (only == 0 or n < only):
         far = float(rng_far.choice([4e4, 7e4, 1e6, 1e9]))
         scene.ij = scene.ij.copy()
         scene.ij[idx] += rng_far.choice([-1, 1], size=(n_far, 2)) * far * rng_far.random((n_far, 2))
+        # A vertex whose row wraps to exactly 32767 makes the reference start its `short` row counter at
+        # (short)(32767 + 1) = -32768 and WRITE at negative pixel indices (DR.h:925-960: heap corruption that killed a
+        # campaign after 40 000 scenes).  The exact-wrap build gives the same picture without the stray writes
+        # (replayed: scene 9501/10377); the campaign keeps clear of it so that the reference survives.
+        for off in (0.0, 0.5):
+            rows = np.floor(scene.ij[:, 1] - off)
+            hit = np.isfinite(rows) & (np.abs(rows) < 2.0 ** 31) & ((rows.astype(np.int64) & 0xffff) == 32767)
+            scene.ij[hit, 1] += 1.0
         degenerate = True  # gradients of triangles thousands of pixels long: fp32 attribute planes (reported apart)
     scene.strict_edge = bool(rng.integers(0, 2))
     scene.integer_pixel_centers = bool(rng.integers(0, 2))
