@@ -219,6 +219,11 @@ def far_vertex_scene(seed, far):
     scene = confetti_scene(200, 64, 48, size=float(rng.choice([5.0, 40.0])), seed=seed, edge_ratio=0.3)
     idx = rng.choice(scene.ij.shape[0], size=40, replace=False)
     scene.ij[idx] += rng.choice([-1, 1], size=(40, 2)) * far * rng.random((40, 2))
+    # (a row that wraps to exactly 32767 starts the reference's `short` row counter at -32768 and makes it write at
+    # negative pixel indices, DR.h:925-960: the checker runs in this process, keep clear of it)
+    rows = np.floor(scene.ij[:, 1])
+    hit = (np.abs(rows) < 2.0 ** 31) & ((rows.astype(np.int64) & 0xFFFF) == 32767)
+    scene.ij[hit, 1] += 1.0
     return scene
 
 
