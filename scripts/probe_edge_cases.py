@@ -76,6 +76,8 @@ s = base(); s.perspective_correct = True; s.depths[::9] = 1e-12; compare("perspe
 for far in (3.2e4, 7e4, 1e9):
     s = base(); idx = rng.choice(900, 40, replace=False)
     s.ij[idx] += rng.choice([-1, 1], size=(40, 2)) * far * rng.random((40, 2))
+    rows = np.floor(s.ij[:, 1])  # (row 32767 after the wrap: the reference then writes at negative pixel indices)
+    s.ij[(np.abs(rows) < 2.0 ** 31) & ((rows.astype(np.int64) & 0xFFFF) == 32767), 1] += 1.0
     compare(f"40 vertices up to {far:g} px away", s)
 
 print("-- textures, flags, channels")

@@ -31,6 +31,8 @@ for far in (1e3, 1e4, 3.2e4, 4e4, 7e4, 1e6, 3e9, 1e15):
         scene = confetti_scene(200, 64, 48, size=float(rng.choice([5.0, 40.0])), seed=trial, edge_ratio=0.3)
         idx = rng.choice(scene.ij.shape[0], size=40, replace=False)  # 40 of 600 vertices pushed far away
         scene.ij[idx] += rng.choice([-1, 1], size=(40, 2)) * far * rng.random((40, 2))
+        rows = np.floor(scene.ij[:, 1])  # (row 32767 after the wrap: the reference then writes at negative pixel indices)
+        scene.ij[(np.abs(rows) < 2.0 ** 31) & ((rows.astype(np.int64) & 0xFFFF) == 32767), 1] += 1.0
         _, z = ref.render(scene, 1.0)
         _, zp = port.render(scene, 1.0)
         got = emu.render(scene, 1.0)["z"]
