@@ -56,8 +56,8 @@ def algorithmic_bytes(scene):
     b_bwd = b_fwd + V * (8 + 4 * C)
     if scene.textured.any():
         tex = scene.texture.size * 4
-        b_fwd += T * 12 + U * 16 + V * 4 + tex
-        b_bwd += T * 12 + U * 16 + V * 4 + tex + U * 8 + V * 4 + tex
+        b_fwd += T * 12 + U * 8 + V * 4 + tex
+        b_bwd += T * 12 + U * 8 + V * 4 + tex + U * 8 + V * 4 + tex
     return b_fwd, b_bwd
 
 
@@ -67,7 +67,7 @@ def kernel_algorithmic_bytes(scene):
     P, C = scene.height * scene.width, scene.nb_colors
     T, V, U = scene.faces.shape[0], scene.depths.shape[0], scene.uv.shape[0]
     tex = scene.texture.size * 4 if scene.textured.any() else 0
-    tex_terms = (T * 12 + U * 16 + V * 4 + tex) if tex else 0
+    tex_terms = (T * 12 + U * 8 + V * 4 + tex) if tex else 0
     return {
         # the single binning pass: faces + flags (17 T) and ij + depths (24 V) read (its 64-byte records are overhead)
         "bin": T * 17 + V * 24,
