@@ -261,3 +261,32 @@ def test_exact_short_wrap_build_changes_nothing_within_the_short_range(checker, 
     check(exact, checker, confetti_scene(3000, 64, 48, size=2.5, seed=1), 1.0)
     for seed in range(4):
         check(exact, checker, far_vertex_scene(seed, 3.2e4), 1.0)
+
+
+@pytest.mark.parametrize("workload", ["c3", "c5"])
+def test_emulated_kernels_at_the_full_benchmark_sizes(workload, emulator, checker):
+    """BASELINE.json configs[2] (50k textured triangles, 1024^2) and configs[4] (1M triangles, 2048^2) through the CPU
+    emulation of the kernel phases: z-buffer bit-exact, image within 1e-6, every gradient within the three-part
+    criterion of the GPU parity tests (tests/test_gpu_parity.py::assert_gradient_close)."""
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    scene = bench.build_scene(workload, view=0, n_views=1)
+    image, z = checker.render(scene, 1.0)
+    fwd = emulator.render(scene, 1.0)
+    assert np.array_equal(fwd["z"], z)
+    assert np.abs(fwd["image"] - image).max() <= IMAGE_TOL
+    image_b = dense_image_b(image)
+    ref, got = checker.render_b(scene, 1.0, image, z, image_b), emulator.render_b(scene, 1.0, fwd, image_b)
+    for name in ("ij_b", "colors_b", "uv_b", "shade_b", "texture_b"):
+        if ref[name].size == 0 or not np.abs(ref[name]).max() > 0:
+            continue
+        err, scale = np.abs(got[name] - ref[name]), np.abs(ref[name]).max()
+        assert err.max() <= 5e-5 * scale + 1e-6, name
+        assert np.linalg.norm(err.ravel()) <= 2e-5 * np.linalg.norm(ref[name].ravel()) + 1e-6, name
+        big = np.abs(ref[name]) > 1e-3 * scale
+        assert (err[big] / np.abs(ref[name][big])).max() <= 2e-3, name
