@@ -290,3 +290,29 @@ def test_emulated_kernels_at_the_full_benchmark_sizes(workload, emulator, checke
         assert np.linalg.norm(err.ravel()) <= 2e-5 * np.linalg.norm(ref[name].ravel()) + 1e-6, name
         big = np.abs(ref[name]) > 1e-3 * scale
         assert (err[big] / np.abs(ref[name][big])).max() <= 2e-3, name
+
+
+def test_emulated_kernels_on_views_of_config4(emulator, checker):
+    """BASELINE.json configs[3]: views of the 200k-triangle mesh at 512^2, an RGB and a depth (C = 1) render each -
+    eight of the 64 views here (all 64 run on the GPU, tests/test_gpu_views.py)."""
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for view in range(0, 64, 8):
+        rgb = bench.build_scene("c4", view=view, n_views=64)
+        depth = bench.build_scene("c4", view=view, n_views=64)
+        depth.nb_colors, depth.colors = 1, np.ascontiguousarray(depth.depths[:, None])
+        depth.background_color, depth.texture = np.array([float(depth.depths.max())]), np.zeros((2, 2, 1))
+        for scene in (rgb, depth):
+            image, z = checker.render(scene, 1.0)
+            fwd = emulator.render(scene, 1.0)
+            assert np.array_equal(fwd["z"], z), view
+            assert np.abs(fwd["image"] - image).max() <= IMAGE_TOL * max(1.0, np.abs(image).max())
+            image_b = dense_image_b(image)
+            ref, got = checker.render_b(scene, 1.0, image, z, image_b), emulator.render_b(scene, 1.0, fwd, image_b)
+            for name in ("ij_b", "colors_b"):
+                assert np.abs(got[name] - ref[name]).max() <= GRAD_RTOL * np.abs(ref[name]).max() + 1e-6, (view, name)
