@@ -316,3 +316,40 @@ def test_emulated_kernels_on_views_of_config4(emulator, checker):
             ref, got = checker.render_b(scene, 1.0, image, z, image_b), emulator.render_b(scene, 1.0, fwd, image_b)
             for name in ("ij_b", "colors_b"):
                 assert np.abs(got[name] - ref[name]).max() <= GRAD_RTOL * np.abs(ref[name]).max() + 1e-6, (view, name)
+
+
+def test_emulated_kernels_on_configs_1_and_2(emulator, checker, ref_oracle, texture):
+    """BASELINE.json configs[0] at its literal size (30-triangle soup, 128 x 128) and configs[1] on the REAL hand mesh
+    (deodr/data/hand.obj projected and lit by the reference's own Camera / Scene3D: tests/golden/scene_ops.npz), 640 x 480;
+    face ids against the reference's deferred face-id channel."""
+    import os
+
+    from conftest import GOLDEN
+
+    from deodr_b200.scenes import SceneArrays
+
+    for seed, clockwise in ((2, False), (3, True)):
+        np.random.seed(seed)
+        check(emulator, checker, soup_scene(n_tri=30, width=128, height=128, clockwise=clockwise, texture=texture), 1.0)
+    g = np.load(os.path.join(GOLDEN, "scene_ops.npz"))
+    faces, V = g["hand_faces"], g["hand_vertices"].shape[0]
+    T = faces.shape[0]
+    hand = SceneArrays(
+        faces=faces, faces_uv=np.zeros((T, 3), np.uint32), ij=g["c2_ij"], depths=g["c2_depths"],
+        textured=np.zeros(T, bool), uv=np.zeros((1, 2)), shade=np.zeros(V), colors=g["c2_colors"],
+        shaded=np.zeros(T, bool), edgeflags=g["c2_edgeflags"].astype(bool), height=480, width=640, nb_colors=3,
+        texture=np.zeros((2, 2, 3)), background_image=None, background_color=g["c2_background_color"], clockwise=False,
+        backface_culling=True, strict_edge=True, perspective_correct=False, integer_pixel_centers=True)
+    fwd = check(emulator, checker, hand, 1.0)
+    assert np.isfinite(fwd["z"]).mean() > 0.05
+    flat = faces.astype(np.int64).reshape(-1)  # every face its own three vertices: a per-vertex channel = the face id
+    deferred = SceneArrays(
+        faces=np.arange(3 * T, dtype=np.uint32).reshape(T, 3), faces_uv=np.zeros((T, 3), np.uint32),
+        ij=g["c2_ij"][flat], depths=g["c2_depths"][flat], textured=np.zeros(T, bool), uv=np.zeros((1, 2)),
+        shade=np.zeros(3 * T), colors=np.repeat(np.arange(T, dtype=np.float64), 3)[:, None], shaded=np.zeros(T, bool),
+        edgeflags=np.zeros((T, 3), bool), height=480, width=640, nb_colors=1, texture=np.zeros((2, 2, 1)),
+        background_image=None, background_color=np.array([-1.0]), clockwise=False, backface_culling=True,
+        strict_edge=True, perspective_correct=False, integer_pixel_centers=True)
+    channel, z = ref_oracle.render(deferred, 0.0)
+    assert np.array_equal(fwd["z"], z)
+    assert np.array_equal(fwd["face_id"], np.rint(channel[:, :, 0]).astype(np.int32))
