@@ -353,3 +353,27 @@ def test_emulated_kernels_on_configs_1_and_2(emulator, checker, ref_oracle, text
     channel, z = ref_oracle.render(deferred, 0.0)
     assert np.array_equal(fwd["z"], z)
     assert np.array_equal(fwd["face_id"], np.rint(channel[:, :, 0]).astype(np.int32))
+
+
+def test_emulated_antialiase_error_mode_at_config3_size(emulator, checker):
+    """antialiase_error = True (row f3) on the 50k-triangle textured mesh at 1024^2: err_buffer and the (bug-compatible)
+    adjoint of the emulated phases against the compiled reference."""
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    scene = bench.build_scene("c3", view=0, n_views=1)
+    rng = np.random.default_rng(0)
+    obs = rng.random((scene.height, scene.width, scene.nb_colors)).astype(np.float32).astype(np.float64)
+    err_b = rng.random((scene.height, scene.width)) * 2 - 1
+    image, z, err = checker.render(scene, 1.0, antialiase_error=True, obs=obs)
+    fwd = emulator.render_error(scene, 1.0, obs)
+    assert np.array_equal(fwd["z"], z)
+    assert np.abs(fwd["err"] - err).max() <= 2e-6 * max(1.0, err.max())
+    ref = checker.render_b(scene, 1.0, image, z, None, antialiase_error=True, obs=obs, err_buffer=err, err_buffer_b=err_b)
+    got = emulator.render_error_b(scene, 1.0, fwd, err_b, compat=True)
+    for name in ("ij_b", "uv_b", "shade_b", "texture_b"):
+        assert np.abs(got[name] - ref[name]).max() <= GRAD_RTOL * np.abs(ref[name]).max() + 1e-6, name
