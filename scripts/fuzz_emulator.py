@@ -16,8 +16,8 @@ Round 1: over 2 million scenes over twenty seeds (1-7 colour channels, backgroun
 25 pixels, crowded soups, all flag combinations, one scene in five in antialiase_error mode): no z-buffer mismatch, no
 deviation outside these tolerances.  Round 2 adds, per scene, a random choice of who takes the adjoint of the small
 triangles (TriBins::small_textured on / off, triangle-parallel / record-parallel kernel).
-End of round 2, at the final sources: 9.2 million scenes of the default campaign over seven seeds, 0.62 million on
-canvases up to 270 x 270 (DEODR_FUZZ_SCALE=3), 1.5 million with the exact-wrap build and vertices up to 1e9 px away
+End of round 2, at the final sources: 15.5 million scenes of the default campaign over ten seeds, 0.9 million on
+canvases up to 270 x 270 (DEODR_FUZZ_SCALE=3), 3.7 million with the exact-wrap build and vertices up to 1e9 px away
 (DEODR_FUZZ_EXACT_WRAP=1): no z-buffer mismatch, no gradient outside the tolerances; two far-vertex scenes under
 perspective_correct at 3-4e-4 relative image error (fp32 attributes of triangles 1e9 px long).  What the campaigns did
 find: a pixel owned by a visible sliver judged without its weight scale in error mode (criterion fixed), a first row
